@@ -1,0 +1,71 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.pt.
+
+Runs the reference's OWN files -- /root/reference/modules/pipeline.py (AntiGradientPipeline) and
+/root/reference/modules/latent_predictor.py (LatentEdgePredictor, hook_unet) -- imported unmodified on
+top of oracle/diffusers_shim, on CPU, with the seeded synthetic weights/inputs of oracle/port.py, and
+stores the per-step latents it reports through ``callback`` (pipeline.py:112-115).  Only runnable in the
+authoring container (needs /root/reference); the fixtures it writes travel with the repo.
+
+    python oracle/make_golden.py tiny 4 tiny 50 sd15 4 sd15 50
+"""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import port  # noqa: E402
+
+REF = "/root/reference"
+
+
+def run_reference(name, steps, guidance_scale=7.5, seed=port.SAMPLE_SEED):
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from modules.latent_predictor import LatentEdgePredictor
+    from modules.pipeline import AntiGradientPipeline
+
+    unet = port.make_unet(name)
+    lgp_o = port.make_lgp(unet)
+    lat, emb, tgt = port.make_inputs(unet, seed)
+    lgp = LatentEdgePredictor(port.lgp_input_dim(unet), 4, port.NUM_POS_LAYERS)
+    lgp.load_state_dict(lgp_o.float().state_dict())
+    lgp.half()
+    pipe = AntiGradientPipeline(unet=unet, scheduler=port.make_scheduler())
+    pipe.set_prompt_embeds(emb)
+    pipe.setup_lgp(lgp)
+    per_step = {}
+    t0 = time.perf_counter()
+    pipe("synthetic", num_inference_steps=steps, guidance_scale=guidance_scale, latents=lat.clone(),
+         sketch_image=tgt, output_type="np",
+         callback=lambda i, t, l: per_step.__setitem__(int(i), l.detach().clone().float()))
+    dt = time.perf_counter() - t0
+    return per_step, dt
+
+
+def main(argv):
+    torch.set_num_threads(os.cpu_count())
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    pairs = list(zip(argv[0::2], argv[1::2]))
+    for name, steps in pairs:
+        steps = int(steps)
+        per_step, dt = run_reference(name, steps)
+        keep = sorted(set(list(range(0, steps, max(1, steps // 10))) + [steps - 1]))
+        blob = {
+            "config": name, "steps": steps, "guidance_scale": 7.5, "beta": 1.6,
+            "weight_seed": port.WEIGHT_SEED, "sample_seed": port.SAMPLE_SEED,
+            "latents": {i: per_step[i] for i in keep},
+            "norms": torch.tensor([per_step[i].norm().item() for i in range(steps)]),
+            "cpu_seconds": dt, "cpu_threads": torch.get_num_threads(),
+            "source": "reference modules/pipeline.py + latent_predictor.py over oracle/diffusers_shim",
+        }
+        path = os.path.join(out_dir, f"{name}_{steps}step.pt")
+        torch.save(blob, path)
+        print(f"{name} {steps} steps: {dt:.1f}s  final norm {per_step[steps - 1].norm():.4f} -> {path}", flush=True)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or ["tiny", "4", "tiny", "50"])

@@ -1,0 +1,211 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY -- never imported by sketch2img_b200/ (the shipped CUDA path).
+
+Plain-PyTorch CPU restatement ("port") of the reference's sketch-guided sampling loop, written so it
+runs WITHOUT /root/reference (which does not exist on the GPU box).  Each function cites the
+reference lines it follows.  It is pinned in THIS container by tests/test_oracle_vs_reference.py,
+which imports the reference's own modules/pipeline.py + modules/latent_predictor.py unmodified over
+oracle/diffusers_shim and requires bit-identical latents, and by the committed fixtures under
+tests/golden/ (made by oracle/make_golden.py from the unmodified reference files).
+
+Parity status: the reference ships no tests / golden vectors of its own, and the
+arithmetic of diffusers' UNet/DDIM lives in an un-vendored dependency restated in
+oracle/diffusers_shim from SURVEY.md Appendix A.  => pinned against the reference's own Python files
+run here; "parity unpinned" with respect to genuine diffusers + real checkpoints.
+"""
+import math
+import os
+import sys
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "diffusers_shim")
+
+
+def add_shim_to_path():
+    if _SHIM not in sys.path:
+        sys.path.insert(0, _SHIM)
+
+
+add_shim_to_path()
+from diffusers import DDIMScheduler, UNet2DConditionModel  # noqa: E402  (the shim)
+from diffusers.models.unet_2d_condition import SD15_CONFIG, SD21_CONFIG, TINY_CONFIG  # noqa: E402,F401
+
+LGP_HIDDEN = (512, 256, 128, 64)
+NUM_POS_LAYERS = 9
+
+
+# --------------------------------------------------------------------------------------------------
+# Latent guidance predictor  (/root/reference/modules/latent_predictor.py:9-45)
+# --------------------------------------------------------------------------------------------------
+class LatentEdgePredictorOracle(nn.Module):
+    """Linear->ReLU->BatchNorm1d x4 -> Linear; state-dict keys ``layers.{0,3,6,9,12}`` (Linear) and
+    ``layers.{2,5,8,11}`` (BN) as in latent_predictor.py:15-29; kaiming-uniform weights, zero bias
+    (:32-35).  BatchNorm stays in TRAIN mode at inference in the reference."""
+
+    def __init__(self, input_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        mods, prev = [], input_dim
+        for width in LGP_HIDDEN:
+            mods += [nn.Linear(prev, width), nn.ReLU(), nn.BatchNorm1d(width)]
+            prev = width
+        mods.append(nn.Linear(prev, output_dim))
+        self.layers = nn.Sequential(*mods)
+        for m in self.layers:
+            if isinstance(m, nn.Linear):
+                nn.init.kaiming_uniform_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x, t):
+        # latent_predictor.py:39-45 -- sin(2*pi*t*2^-l) for l in range(num_layers), concat on C,
+        # rows ordered (b, w, h), hard cast to fp16.
+        pos = torch.cat([torch.sin(2 * math.pi * t * (2 ** -l)) for l in range(self.num_layers)], dim=1)
+        z = torch.cat((x, t, pos), dim=1)
+        b, c, h, w = z.shape
+        z = z.permute(0, 3, 2, 1).reshape(b * w * h, c).to(torch.float16)
+        return self.layers(z)
+
+
+def tap_modules(unet):
+    """The 9 tapped sub-modules in hook order (latent_predictor.py:63-80): down_blocks[0..2],
+    mid attentions then mid resnets, up_blocks[0..2]."""
+    mods = [blk for i, blk in enumerate(unet.down_blocks) if i in (0, 1, 2)]
+    mods += list(unet.mid_block.attentions) + list(unet.mid_block.resnets)
+    mods += [blk for i, blk in enumerate(unet.up_blocks) if i in (0, 1, 2)]
+    return mods
+
+
+def register_taps(unet):
+    """Forward hooks storing ``module.output = feature.float()`` (latent_predictor.py:50-62):
+    tuple -> [0]; dict-like (Transformer2DModelOutput) -> .sample; tensor as is."""
+    def _store(module, _inp, out):
+        if isinstance(out, tuple):
+            out = out[0]
+        if isinstance(out, dict):
+            out = out.sample
+        module.output = out.float()
+
+    mods = tap_modules(unet)
+    handles = [m.register_forward_hook(_store) for m in mods]
+    return mods, handles
+
+
+def lgp_input_dim(unet):
+    boc = unet.config.block_out_channels
+    # taps: down0,down1,down2 | mid x3 | up0,up1,up2  
+    ch = [boc[0], boc[1], boc[2], boc[3], boc[3], boc[3], boc[3], boc[2], boc[1]]
+    return sum(ch) + 4 + 4 * NUM_POS_LAYERS
+
+
+# --------------------------------------------------------------------------------------------------
+# Guidance update  (/root/reference/modules/pipeline.py:132-161)
+# --------------------------------------------------------------------------------------------------
+def noise_level(scheduler, noise, t):
+    """pipeline.py:132-139: sqrt(1 - alpha_bar_t) * noise, factor broadcast as fp32 [1,1,1,1]."""
+    s = ((1 - scheduler.alphas_cumprod[t]) ** 0.5).flatten()
+    while s.dim() < noise.dim():
+        s = s.unsqueeze(-1)
+    return s.to(noise.device) * noise
+
+
+def lgp_features(taps, size):
+    """pipeline.py:145-151: bilinear (align_corners=False) resize of each tap to size x size, concat on C."""
+    return torch.cat([F.interpolate(m.output, size=size, mode="bilinear") for m in taps], dim=1)
+
+
+def anti_gradient(lgp, scheduler, taps, x_in, latents, noise, t, target, beta):
+    """pipeline.py:141-161.  x_in is the CFG-doubled, grad-enabled UNet input [2,4,h,w]; the loss is the
+    MSE between the sketch target and the LGP prediction on the cond half; the step is
+    alpha = ||x_in - latents||_F / ||g_cond||_F * beta along g_cond = -dLoss/dx_in (cond half)."""
+    if target is None:
+        return latents
+    feats = lgp_features(taps, latents.shape[2])
+    for m in taps:
+        del m.output
+    lvl = noise_level(scheduler, noise, t)
+    out = lgp(feats, torch.cat([lvl] * 2))
+    b, _, h, w = x_in.shape
+    out = out.reshape(b, w, h, -1).permute(0, 3, 2, 1)          # "(b w h) c -> b c h w"
+    cond = out.chunk(2)[1]
+    loss = F.mse_loss(target.float(), cond.float(), reduction="mean")
+    g = (-torch.autograd.grad(loss, x_in)[0]).chunk(2)[1]
+    alpha = torch.linalg.norm(x_in - latents) / torch.linalg.norm(g) * beta
+    return latents + alpha * g
+
+
+@torch.no_grad()
+def guided_sample(unet, lgp, scheduler, text_emb, latents, target, num_steps=50, guidance_scale=7.5,
+                  beta=1.6, stop_frac=0.5, taps=None, callback=None):
+    """pipeline.py:59-115, CFG on, batch 1.  text_emb is [2,77,D] = [uncond, cond].
+    Returns the final latent; ``callback(i, t, latents)`` fires every step like :112-115."""
+    if taps is None:
+        taps, _ = register_taps(unet)
+    scheduler.set_timesteps(num_steps)
+    ts = scheduler.timesteps
+    latents = latents * scheduler.init_noise_sigma
+    noise = latents.detach().clone()                                        # :75
+    stop = stop_frac * len(ts)                                              # :90
+    for i, t in enumerate(ts):
+        x_in = torch.cat([latents] * 2)                                     # :85
+        x_in = scheduler.scale_model_input(x_in, t).requires_grad_(True)    # :86-87
+        guided = i <= stop                                                  # :89-92,108 (Q4)
+        with torch.enable_grad() if guided else torch.no_grad():
+            eps = unet(x_in, t, encoder_hidden_states=text_emb).sample      # :96
+        eps_u, eps_c = eps.chunk(2)                                         # :100
+        eps = eps_u + guidance_scale * (eps_c - eps_u)                      # :101
+        latents = scheduler.step(eps, t, latents, eta=0.0).prev_sample      # :104
+        if guided:
+            with torch.enable_grad():
+                latents = anti_gradient(lgp, scheduler, taps, x_in, latents, noise, t, target, beta)  # :109
+        if callback is not None:
+            callback(i, t, latents)
+    return latents
+
+
+# --------------------------------------------------------------------------------------------------
+# Seeded synthetic models / inputs shared by the oracle, the tests and bench.py
+# --------------------------------------------------------------------------------------------------
+CONFIGS = {"sd15": SD15_CONFIG, "sd21": SD21_CONFIG, "tiny": TINY_CONFIG}
+WEIGHT_SEED = 1138
+SAMPLE_SEED = 1139
+
+
+def make_unet(name="sd15", seed=WEIGHT_SEED):
+    """PyTorch-default-initialised UNet of the named topology under a fixed CPU seed (no checkpoints offline)."""
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    unet = UNet2DConditionModel(**CONFIGS[name])
+    torch.random.set_rng_state(g)
+    return unet.eval()
+
+
+def make_lgp(unet, seed=WEIGHT_SEED + 1, bn_affine_jitter=True):
+    """fp16 LGP (reference: app.py:67-69).  BN affine is (1,0) by default init; a small seeded jitter
+    makes the BN-affine code path observable in parity tests."""
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    lgp = LatentEdgePredictorOracle(lgp_input_dim(unet), 4, NUM_POS_LAYERS)
+    if bn_affine_jitter:
+        for m in lgp.layers:
+            if isinstance(m, nn.BatchNorm1d):
+                m.weight.data.add_(0.1 * torch.randn_like(m.weight))
+                m.bias.data.add_(0.1 * torch.randn_like(m.bias))
+    torch.random.set_rng_state(g)
+    return lgp.half()       # stays in train mode: SURVEY.md Q2
+
+
+def make_inputs(unet, seed=SAMPLE_SEED):
+    """CPU-seeded initial latents [1,4,L,L], prompt embeddings [2,77,D] ([uncond, cond]) and sketch
+    target [1,4,L,L]."""
+    gen = torch.Generator().manual_seed(seed)
+    L = unet.config.sample_size
+    latents = torch.randn(1, 4, L, L, generator=gen)
+    emb = torch.randn(2, 77, unet.config.cross_attention_dim, generator=gen)
+    target = torch.randn(1, 4, L, L, generator=gen)
+    return latents, emb, target
+
+
+def make_scheduler(prediction_type="epsilon"):
+    return DDIMScheduler(prediction_type=prediction_type)

@@ -1,0 +1,56 @@
+// Shared host/device helpers for libs2i: error reporting, launch accounting, small math.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+namespace s2i {
+
+enum : int {
+    S2I_OK = 0,
+    S2I_ERR_ARG = -1,
+    S2I_ERR_CUDA = -2,
+    S2I_ERR_STATE = -3,
+    S2I_ERR_OOM = -4,
+};
+
+// Thread-local last-error message (s2i_last_error()).
+int set_error(int code, const char* fmt, ...);
+const char* last_error();
+
+extern long g_launches;  // kernels launched by this library since load
+inline void count_launch(int n = 1) { g_launches += n; }
+
+#define S2I_CUDA(call)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return ::s2i::set_error(::s2i::S2I_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,        \
+                                    cudaGetErrorString(e__));                                                \
+    } while (0)
+
+#define S2I_LAUNCH_CHECK()                                                                                   \
+    do {                                                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                                \
+        if (e__ != cudaSuccess)                                                                              \
+            return ::s2i::set_error(::s2i::S2I_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__,           \
+                                    cudaGetErrorString(e__));                                                \
+        ::s2i::count_launch();                                                                               \
+    } while (0)
+
+#define S2I_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != 0) return rc__;    \
+    } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long ceil_div_l(long a, long b) { return (a + b - 1) / b; }
+inline long round_up_l(long a, long b) { return ceil_div_l(a, b) * b; }
+
+constexpr int kNumSMs = 148;
+
+}  // namespace s2i

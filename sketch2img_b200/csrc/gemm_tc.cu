@@ -1,0 +1,498 @@
+// tcgen05 + TMA implicit GEMM (see gemm_tc.cuh).  One CTA computes one 128 x BN output tile:
+//   warp 0      TMA producer  (cp.async.bulk.tensor, 128B-swizzled operand tiles, zero-filled halos)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (accumulator: 128 lanes x BN fp32 columns)
+//   warps 2..5  epilogue: tcgen05.ld -> bias / per-sample vector / ReLU / residual -> fp32 and/or fp16 stores
+// Stage ring: full[] (TMA -> MMA, transaction bytes) and empty[] (tcgen05.commit -> TMA).
+#include "gemm_tc.cuh"
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <cudaTypedefs.h>
+#include <cstring>
+#include <mutex>
+
+namespace s2i {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;             // elements; 128 bytes = one swizzle row
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kChunkBytes = 64 * kBlockK * 2;         // 8 KB: one 64-row (or 64-col, MN-major) box
+
+struct __align__(64) GemmParams {
+    CUtensorMap mapA;
+    CUtensorMap mapB;
+    int tw, th, tb, tiles_x, tiles_y;
+    int W, H, Bn, M, N;
+    int k_chunks, taps, a_mn, b_mn;
+    int BN, stages, tmem_cols;
+    int a_c0, a_hoff, a_zmode, b_c0, b_hoff, b_zmode, zh;
+    uint32_t idesc, tx_bytes;
+    float alpha;
+    const float* bias;
+    const float* rowvec;
+    int rowvec_ld;
+    const float* residual;
+    long res_ld;
+    float* out32;
+    long ld32;
+    void* out16;
+    long ld16;
+    int out16_bf16;
+    long c_sb, c_sh;
+    int relu;
+};
+
+__device__ __forceinline__ uint16_t to_half_bits(float v, int bf16) {
+    if (bf16) {
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        return *reinterpret_cast<uint16_t*>(&h);
+    }
+    __half h = __float2half_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_stage_bytes = ((p.BN + 63) >> 6) * kChunkBytes;
+    const int stage_bytes = kAStageBytes + b_stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* accum_full = empty + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int mt = blockIdx.x;
+    const int n0 = blockIdx.y * p.BN;
+    const int z = blockIdx.z;
+    const int zb = z / p.zh, zhd = z - zb * p.zh;
+    int x0 = 0, y0 = 0, b0 = 0, m0 = 0;
+    if (!p.a_mn) {
+        const int tx = mt % p.tiles_x;
+        const int ty = (mt / p.tiles_x) % p.tiles_y;
+        const int tbi = mt / (p.tiles_x * p.tiles_y);
+        x0 = tx * p.tw;
+        y0 = ty * p.th;
+        b0 = tbi * p.tb;
+    } else {
+        m0 = mt * kBlockM;
+    }
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&p.mapA);
+        ptx::prefetch_tmap(&p.mapB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < p.stages; ++s) {
+                ptx::mbar_init(&full[s], 1);
+                ptx::mbar_init(&empty[s], 1);
+            }
+            ptx::mbar_init(accum_full, 1);
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_iters = p.taps * p.k_chunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            const int a_inner = p.a_c0 + (p.a_zmode ? 0 : zhd * p.a_hoff);
+            const int a_bz = p.a_zmode ? z : zb;
+            const int b_inner = p.b_c0 + (p.b_zmode ? 0 : zhd * p.b_hoff);
+            const int b_bz = p.b_zmode ? z : zb;
+            const int nchunks_b = (p.BN + 63) >> 6;
+            for (int it = 0; it < num_iters; ++it) {
+                const int stage = it % p.stages;
+                const uint32_t phase = (it / p.stages) & 1;
+                ptx::mbar_wait(&empty[stage], phase ^ 1);
+                ptx::mbar_expect_tx(&full[stage], p.tx_bytes);
+                uint8_t* sa = smem + stage * stage_bytes;
+                uint8_t* sb = sa + kAStageBytes;
+                if (!p.a_mn) {
+                    const int tap = it / p.k_chunks;
+                    const int kc = it - tap * p.k_chunks;
+                    int dx = 0, dy = 0;
+                    if (p.taps == 9) {
+                        dy = tap / 3 - 1;
+                        dx = tap % 3 - 1;
+                    }
+                    ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + kc * kBlockK, x0 + dx, y0 + dy, b0 + a_bz);
+                } else {
+                    ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + m0, it * kBlockK, 0, a_bz);
+                    ptx::tma_load_4d(sa + kChunkBytes, &p.mapA, &full[stage], a_inner + m0 + 64, it * kBlockK, 0, a_bz);
+                }
+                if (!p.b_mn) {
+                    ptx::tma_load_3d(sb, &p.mapB, &full[stage], b_inner + it * kBlockK, n0, b_bz);
+                } else {
+                    for (int j = 0; j < nchunks_b; ++j)
+                        ptx::tma_load_3d(sb + j * kChunkBytes, &p.mapB, &full[stage], b_inner + n0 + j * 64,
+                                         it * kBlockK, b_bz);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer
+            const uint32_t a_kstep = p.a_mn ? 2048u : 32u;   // bytes per UMMA_K = 16 elements
+            const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
+            const uint32_t a_lbo = p.a_mn ? (uint32_t)kChunkBytes : 16u;
+            const uint32_t b_lbo = p.b_mn ? (uint32_t)kChunkBytes : 16u;
+            for (int it = 0; it < num_iters; ++it) {
+                const int stage = it % p.stages;
+                const uint32_t phase = (it / p.stages) & 1;
+                ptx::mbar_wait(&full[stage], phase);
+                ptx::tc_fence_after();
+                const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
+                const uint32_t sb = sa + kAStageBytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint64_t adesc = ptx::make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024u);
+                    const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024u);
+                    ptx::umma_f16(tmem_base, adesc, bdesc, p.idesc, (it | k) != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(&empty[stage]);   // frees the smem stage once these MMAs have read it
+            }
+            ptx::umma_commit(accum_full);          // accumulator complete
+        }
+    } else {
+        // ---------------------------------------------------- epilogue (warps 2..5)
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;            // tile row
+        bool valid;
+        long row;
+        int sample = 0;
+        if (!p.a_mn) {
+            const int xi = r % p.tw;
+            const int yi = (r / p.tw) % p.th;
+            const int bi = r / (p.tw * p.th);
+            valid = (bi < p.tb) && (x0 + xi < p.W) && (y0 + yi < p.H) && (b0 + bi < p.Bn);
+            row = ((long)(b0 + bi) * p.H + (y0 + yi)) * p.W + (x0 + xi);
+            sample = b0 + bi;
+        } else {
+            valid = (m0 + r) < p.M;
+            row = m0 + r;
+        }
+        const long zoff = (long)zb * p.c_sb + (long)zhd * p.c_sh;
+        float* o32 = p.out32 ? p.out32 + zoff + row * p.ld32 : nullptr;
+        uint16_t* o16 = p.out16 ? reinterpret_cast<uint16_t*>(p.out16) + zoff + row * p.ld16 : nullptr;
+        const float* res = p.residual ? p.residual + zoff + row * p.res_ld : nullptr;
+        const float* rvec = p.rowvec ? p.rowvec + (long)sample * p.rowvec_ld : nullptr;
+        const bool vec32 = o32 && ((p.ld32 & 3) == 0) && ((zoff & 3) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(p.out32) & 15) == 0);
+        const bool vec16 = o16 && ((p.ld16 & 7) == 0) && ((zoff & 7) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(p.out16) & 15) == 0);
+        const bool vecres = res && ((p.res_ld & 3) == 0) && ((zoff & 3) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+
+        ptx::mbar_wait(accum_full, 0);
+        ptx::tc_fence_after();
+
+        for (int c = 0; c < p.BN; c += 32) {
+            uint32_t raw[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+            if (c + 32 <= p.BN) {
+                ptx::tmem_ld_32x32(taddr, raw);
+            } else {   // BN is a multiple of 16: 16-column tail
+                uint32_t lo[16];
+                ptx::tmem_ld_32x16(taddr, lo);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    raw[j] = lo[j];
+                    raw[16 + j] = 0u;
+                }
+            }
+            ptx::tmem_ld_wait();
+            if (!valid) continue;
+            const int nbase = n0 + c;
+            const int ncols = min(min(32, p.BN - c), p.N - nbase);
+            if (ncols <= 0) continue;
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+                if (j4 >= ncols) break;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(raw[j4 + j]) * p.alpha;
+                const int n = nbase + j4;
+                const bool full4 = (j4 + 4 <= ncols);
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j4 + j < ncols) v[j] += __ldg(p.bias + n + j);
+                }
+                if (rvec) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j4 + j < ncols) v[j] += __ldg(rvec + n + j);
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (res) {
+                    if (full4 && vecres && ((n & 3) == 0)) {
+                        const float4 rr = *reinterpret_cast<const float4*>(res + n);
+                        v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j4 + j < ncols) v[j] += res[n + j];
+                    }
+                }
+                if (o32) {
+                    if (full4 && vec32 && ((n & 3) == 0)) {
+                        *reinterpret_cast<float4*>(o32 + n) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j4 + j < ncols) o32[n + j] = v[j];
+                    }
+                }
+                if (o16) {
+                    uint16_t h[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) h[j] = to_half_bits(v[j], p.out16_bf16);
+                    if (full4 && vec16 && ((n & 3) == 0)) {
+                        uint2 pk;
+                        pk.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+                        pk.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+                        *reinterpret_cast<uint2*>(o16 + n) = pk;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j4 + j < ncols) o16[n + j] = h[j];
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+    });
+    return fn;
+}
+
+int encode_map(CUtensorMap* m, int bf16, int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+    auto fn = get_encode_fn();
+    if (!fn) return set_error(S2I_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    uint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                    const_cast<void*>(ptr), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(S2I_ERR_CUDA,
+                         "cuTensorMapEncodeTiled failed (%d): rank %d ptr %p dims [%llu %llu %llu %llu] strides [%llu %llu "
+                         "%llu] box [%u %u %u %u]",
+                         (int)r, rank, ptr, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                         (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                         (unsigned long long)strides_bytes[0], (unsigned long long)(rank > 2 ? strides_bytes[1] : 0),
+                         (unsigned long long)(rank > 3 ? strides_bytes[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0,
+                         rank > 3 ? box[3] : 0);
+    return 0;
+}
+
+int pow2_floor(int v) {
+    int p = 1;
+    while (p * 2 <= v) p *= 2;
+    return p;
+}
+
+int choose_bn(int N, long ctas_mz) {
+    const int nr = (int)round_up_l(N, 16);
+    if (nr <= 32) return nr;
+    static const int cands[] = {256, 192, 160, 128, 96, 80, 64, 48, 32};
+    int best = 0;
+    double best_score = -1.0;
+    for (int c : cands) {
+        const int tiles = ceil_div(N, c);
+        const double eff = (double)N / ((double)tiles * c);          // useful fraction of MMA columns
+        const long ctas = ctas_mz * tiles;
+        const double fill = ctas >= kNumSMs ? 1.0 : (double)ctas / kNumSMs;
+        const double width = 0.6 + 0.4 * ((double)c / 256.0);         // wider tiles re-read A less
+        const double score = eff * fill * width;
+        if (score > best_score) {
+            best_score = score;
+            best = c;
+        }
+    }
+    return best;
+}
+
+}  // namespace
+
+long g_launches = 0;
+long gemm_launch_count() { return g_launches; }
+
+int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
+    if (!d.A || !d.B) return set_error(S2I_ERR_ARG, "gemm: null operand");
+    if (d.taps != 1 && d.taps != 9) return set_error(S2I_ERR_ARG, "gemm: taps must be 1 or 9");
+    if (d.a_mn && d.taps != 1) return set_error(S2I_ERR_ARG, "gemm: MN-major A has no taps");
+    if (d.taps == 9 && (d.Kc % kBlockK) != 0) return set_error(S2I_ERR_ARG, "gemm: conv3x3 needs Cin %% 64 == 0");
+    if (!d.out32 && !d.out16) return set_error(S2I_ERR_ARG, "gemm: no output");
+
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.a_mn = d.a_mn;
+    p.b_mn = d.b_mn;
+    p.taps = d.taps;
+    p.N = d.N;
+    p.k_chunks = ceil_div(d.Kc, kBlockK);
+    p.W = d.aW;
+    p.H = d.aH;
+    p.Bn = d.aB;
+    p.zh = d.zh > 0 ? d.zh : 1;
+
+    // ---- M tiling
+    long tiles_m;
+    if (!d.a_mn) {
+        int tw;
+        if (d.aW >= kBlockM) {
+            tw = kBlockM;
+        } else {
+            tw = pow2_floor(d.aW);
+            if (d.aW % tw != 0) {
+                int t = tw;
+                while (t > 1 && d.aW % t != 0) t /= 2;
+                if (t >= 4) tw = t;   // prefer an exact divisor when it is not tiny
+            }
+        }
+        int th = pow2_floor(kBlockM / tw);
+        if (th > d.aH) th = pow2_floor(d.aH) < d.aH ? pow2_floor(d.aH) * 2 : pow2_floor(d.aH);
+        if (th > kBlockM / tw) th = kBlockM / tw;
+        int tb = kBlockM / (tw * th);
+        if (tb > d.aB) tb = d.aB;
+        if (tb < 1) tb = 1;
+        p.tw = tw;
+        p.th = th;
+        p.tb = tb;
+        p.tiles_x = ceil_div(d.aW, tw);
+        p.tiles_y = ceil_div(d.aH, th);
+        const int tiles_b = d.Z > 1 ? 1 : ceil_div(d.aB, tb);
+        if (d.Z > 1) {
+            p.tb = 1;
+            p.Bn = 1 << 30;   // batch comes from z; no batch masking
+        }
+        tiles_m = (long)p.tiles_x * p.tiles_y * tiles_b;
+        p.M = 0;
+    } else {
+        p.M = d.aC;
+        tiles_m = ceil_div(d.aC, kBlockM);
+        p.tw = kBlockM;
+        p.th = p.tb = 1;
+        p.tiles_x = (int)tiles_m;
+        p.tiles_y = 1;
+    }
+    const int Z = d.Z > 0 ? d.Z : 1;
+
+    int BN = d.BN > 0 ? d.BN : choose_bn(d.N, tiles_m * Z);
+    if (BN % 16 != 0 || BN < 16 || BN > 256) return set_error(S2I_ERR_ARG, "gemm: BN %d invalid", BN);
+    p.BN = BN;
+    const int tiles_n = ceil_div(d.N, BN);
+    p.tmem_cols = 32;
+    while (p.tmem_cols < BN) p.tmem_cols *= 2;
+
+    const int b_stage_bytes = ceil_div(BN, 64) * kChunkBytes;
+    const int stage_bytes = kAStageBytes + b_stage_bytes;
+    const int num_iters = p.taps * p.k_chunks;
+    int stages = (100 * 1024) / stage_bytes;   // <= ~100 KB so two CTAs can share an SM
+    if (stages < 3) stages = 3;
+    if (stages > 6) stages = 6;
+    if (stages > num_iters) stages = num_iters < 1 ? 1 : num_iters;
+    p.stages = stages;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+
+    p.a_c0 = d.a_c0;
+    p.a_hoff = d.a_hoff;
+    p.a_zmode = d.a_zmode;
+    p.b_c0 = d.b_c0;
+    p.b_hoff = d.b_hoff;
+    p.b_zmode = d.b_zmode;
+    p.idesc = ptx::make_idesc_f16(kBlockM, BN, d.bf16, d.a_mn, d.b_mn);
+    const uint32_t a_bytes = d.a_mn ? 2 * kChunkBytes : (uint32_t)(p.tw * p.th * p.tb * kBlockK * 2);
+    const uint32_t b_bytes = d.b_mn ? (uint32_t)(ceil_div(BN, 64) * kChunkBytes) : (uint32_t)(BN * kBlockK * 2);
+    p.tx_bytes = a_bytes + b_bytes;
+
+    p.alpha = d.alpha;
+    p.bias = d.bias;
+    p.rowvec = d.rowvec;
+    p.rowvec_ld = d.rowvec_ld;
+    p.residual = d.residual;
+    p.res_ld = d.res_ld;
+    p.out32 = d.out32;
+    p.ld32 = d.ld32;
+    p.out16 = d.out16;
+    p.ld16 = d.ld16;
+    p.out16_bf16 = d.out16_bf16;
+    p.c_sb = d.c_sb;
+    p.c_sh = d.c_sh;
+    p.relu = d.relu;
+
+    // ---- tensor maps
+    {
+        const long sw = d.a_sw > 0 ? d.a_sw : d.aC;
+        const long sh = d.a_sh > 0 ? d.a_sh : sw * d.aW;
+        const long sb = d.a_sb > 0 ? d.a_sb : sh * d.aH;
+        uint64_t dims[4] = {(uint64_t)d.aC, (uint64_t)d.aW, (uint64_t)d.aH, (uint64_t)d.aB};
+        uint64_t str[3] = {(uint64_t)sw * 2, (uint64_t)sh * 2, (uint64_t)sb * 2};
+        uint32_t box[4];
+        if (!d.a_mn) {
+            box[0] = kBlockK; box[1] = (uint32_t)p.tw; box[2] = (uint32_t)p.th; box[3] = (uint32_t)p.tb;
+        } else {
+            box[0] = 64; box[1] = kBlockK; box[2] = 1; box[3] = 1;
+        }
+        S2I_TRY(encode_map(&p.mapA, d.bf16, 4, d.A, dims, str, box));
+    }
+    {
+        const long sr = d.b_sr > 0 ? d.b_sr : d.bI;
+        const long sz = d.b_sz > 0 ? d.b_sz : sr * d.bR;
+        uint64_t dims[3] = {(uint64_t)d.bI, (uint64_t)d.bR, (uint64_t)(d.bZ > 0 ? d.bZ : 1)};
+        uint64_t str[2] = {(uint64_t)sr * 2, (uint64_t)sz * 2};
+        uint32_t box[3];
+        if (!d.b_mn) {
+            box[0] = kBlockK; box[1] = (uint32_t)BN; box[2] = 1;
+        } else {
+            box[0] = 64; box[1] = kBlockK; box[2] = 1;
+        }
+        S2I_TRY(encode_map(&p.mapB, d.bf16, 3, d.B, dims, str, box));
+    }
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        S2I_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)Z);
+    gemm_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+    S2I_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace s2i
