@@ -1,0 +1,74 @@
+"""ctypes binding of libs2i.so (C ABI: include/s2i.h).  There is NO CPU fallback: if the CUDA library
+cannot be loaded every entry point raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libs2i.so")
+_lib = None
+
+
+class S2IError(RuntimeError):
+    pass
+
+
+class GemmDesc(C.Structure):
+    """Mirror of ``s2i_gemm_desc`` (include/s2i.h)."""
+    _fields_ = [
+        ("A", C.c_void_p), ("a_mn", C.c_int), ("aC", C.c_int), ("aW", C.c_int), ("aH", C.c_int), ("aB", C.c_int),
+        ("a_sw", C.c_longlong), ("a_sh", C.c_longlong), ("a_sb", C.c_longlong), ("taps", C.c_int),
+        ("a_c0", C.c_int), ("a_hoff", C.c_int), ("a_zmode", C.c_int),
+        ("B", C.c_void_p), ("b_mn", C.c_int), ("bI", C.c_int), ("bR", C.c_int), ("bZ", C.c_int),
+        ("b_sr", C.c_longlong), ("b_sz", C.c_longlong), ("b_c0", C.c_int), ("b_hoff", C.c_int), ("b_zmode", C.c_int),
+        ("N", C.c_int), ("Kc", C.c_int), ("Z", C.c_int), ("zh", C.c_int), ("bf16", C.c_int), ("BN", C.c_int),
+        ("alpha", C.c_float), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int),
+        ("residual", C.c_void_p), ("res_ld", C.c_longlong),
+        ("out32", C.c_void_p), ("ld32", C.c_longlong), ("out16", C.c_void_p), ("ld16", C.c_longlong),
+        ("out16_bf16", C.c_int), ("c_sb", C.c_longlong), ("c_sh", C.c_longlong), ("relu", C.c_int),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__()
+        self.taps = 1
+        self.aH = self.aB = self.bZ = self.Z = self.zh = 1
+        self.alpha = 1.0
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+def lib():
+    """Load (building in-tree first if only sources are present) and return the ctypes handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        from . import build as _build
+        _build.build()
+    try:
+        h = C.CDLL(_LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise S2IError(f"cannot load {_LIB_PATH}: {e}. The sketch-guided path has no CPU fallback.") from e
+    h.s2i_last_error.restype = C.c_char_p
+    h.s2i_launch_count.restype = C.c_longlong
+    h.s2i_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+    h.s2i_gemm.restype = C.c_int
+    _lib = h
+    return h
+
+
+def check(rc):
+    if rc != 0:
+        raise S2IError(f"libs2i error {rc}: {lib().s2i_last_error().decode(errors='replace')}")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gemm(desc):
+    check(lib().s2i_gemm(C.byref(desc), stream_ptr()))
+
+
+def launch_count():
+    return int(lib().s2i_launch_count())

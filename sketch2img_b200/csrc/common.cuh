@@ -7,15 +7,11 @@
 #include <cstdint>
 #include <cstdio>
 
+#include "../../include/s2i.h"
+
 namespace s2i {
 
-enum : int {
-    S2I_OK = 0,
-    S2I_ERR_ARG = -1,
-    S2I_ERR_CUDA = -2,
-    S2I_ERR_STATE = -3,
-    S2I_ERR_OOM = -4,
-};
+// error codes: S2I_OK / S2I_ERR_* macros from include/s2i.h
 
 // Thread-local last-error message (s2i_last_error()).
 int set_error(int code, const char* fmt, ...);
@@ -28,7 +24,7 @@ inline void count_launch(int n = 1) { g_launches += n; }
     do {                                                                                                     \
         cudaError_t e__ = (call);                                                                            \
         if (e__ != cudaSuccess)                                                                              \
-            return ::s2i::set_error(::s2i::S2I_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,        \
+            return ::s2i::set_error(S2I_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,        \
                                     cudaGetErrorString(e__));                                                \
     } while (0)
 
@@ -36,7 +32,7 @@ inline void count_launch(int n = 1) { g_launches += n; }
     do {                                                                                                     \
         cudaError_t e__ = cudaGetLastError();                                                                \
         if (e__ != cudaSuccess)                                                                              \
-            return ::s2i::set_error(::s2i::S2I_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__,           \
+            return ::s2i::set_error(S2I_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__,           \
                                     cudaGetErrorString(e__));                                                \
         ::s2i::count_launch();                                                                               \
     } while (0)

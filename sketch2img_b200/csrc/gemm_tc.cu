@@ -26,7 +26,7 @@ struct __align__(64) GemmParams {
     CUtensorMap mapB;
     int tw, th, tb, tiles_x, tiles_y;
     int W, H, Bn, M, N;
-    int k_chunks, taps, a_mn, b_mn;
+    int k_chunks, k_last_steps, taps, a_mn, b_mn;
     int BN, stages, tmem_cols;
     int a_c0, a_hoff, a_zmode, b_c0, b_hoff, b_zmode, zh;
     uint32_t idesc, tx_bytes;
@@ -158,8 +158,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
                 const uint32_t sb = sa + kAStageBytes;
-#pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
+                // The last K chunk of a tap may be partial: head-sliced operands must not read past Kc.
+                const int ksteps = ((it + 1) % p.k_chunks == 0) ? p.k_last_steps : kBlockK / 16;
+                for (int k = 0; k < ksteps; ++k) {
                     const uint64_t adesc = ptx::make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024u);
                     const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024u);
                     ptx::umma_f16(tmem_base, adesc, bdesc, p.idesc, (it | k) != 0 ? 1u : 0u);
@@ -365,6 +366,7 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     p.taps = d.taps;
     p.N = d.N;
     p.k_chunks = ceil_div(d.Kc, kBlockK);
+    p.k_last_steps = ceil_div(d.Kc - (p.k_chunks - 1) * kBlockK, 16);
     p.W = d.aW;
     p.H = d.aH;
     p.Bn = d.aB;

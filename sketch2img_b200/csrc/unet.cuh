@@ -1,0 +1,183 @@
+// SD-family UNet2DCondition forward with the 9 LGP feature taps and the input-gradient backward from those
+// taps (reference call sites: modules/pipeline.py:96 forward, :159 autograd.grad; tap set
+// modules/latent_predictor.py:63-80).  Activations are NHWC / token-major: fp32 residual stream, fp16 GEMM
+// operands; every contraction goes through gemm_tc.cu.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace s2i {
+
+struct UNetConfig {
+    int in_ch = 4, out_ch = 4;
+    int boc[4] = {320, 640, 1280, 1280};
+    int heads[4] = {8, 8, 8, 8};
+    int layers = 2;
+    int cross_dim = 768;
+    int sample_size = 64;
+    int ctx_len = 77;
+};
+
+struct HostParam {
+    const float* data;
+    std::vector<long> shape;
+};
+
+struct F32 {
+    float* p = nullptr;
+    long ld = 0;
+    int B = 0, H = 0, W = 0, C = 0;
+    long rows() const { return (long)B * H * W; }
+};
+struct H16 {
+    __half* p = nullptr;
+    long ld = 0;
+    int B = 0, H = 0, W = 0, C = 0;
+    long rows() const { return (long)B * H * W; }
+};
+
+struct Lin {     // y = x W^T + b;  w: [N][K] (forward), wd: [K][N] (input gradient)
+    __half* w = nullptr;
+    __half* wd = nullptr;
+    float* b = nullptr;
+    int N = 0, K = 0;
+};
+struct Conv3 {   // w: [Cout][9*Cin] (tap-major), wd: [Cin][9*Cout] (taps flipped)
+    __half* w = nullptr;
+    __half* wd = nullptr;
+    float* b = nullptr;
+    int Cin = 0, Cout = 0;
+};
+struct Norm {
+    float* g = nullptr;
+    float* b = nullptr;
+    int C = 0;
+    float eps = 1e-5f;
+};
+struct ResBlock {
+    Norm n1, n2;
+    Conv3 c1, c2;
+    Lin sc;            // 1x1 shortcut when Cin != Cout
+    bool has_sc = false;
+    int temb_off = 0;  // offset of this block's time_emb_proj slice in the fused projection
+    int Cin = 0, Cout = 0;
+};
+struct Transformer {
+    Norm gn, ln1, ln2, ln3;
+    Lin proj_in, proj_out;
+    Lin qkv;   // fused self-attention q|k|v, head-padded: [3*HP][C]
+    Lin o1;    // [C][HP]
+    Lin q2;    // [HP][C]
+    Lin kv2;   // [2*HP][Dctx]
+    Lin o2;    // [C][HP]
+    Lin ff1;   // [8C][C]
+    Lin ff2;   // [C][4C]
+    int C = 0, heads = 0, d = 0, dp = 0, HP = 0;
+};
+
+struct ResSave {
+    F32 x, h1;
+    double *s1 = nullptr, *s2 = nullptr;
+};
+struct TfmSave {
+    F32 x, t0, t1, t2, ff;
+    double* gs = nullptr;
+    float *l1 = nullptr, *l2 = nullptr, *l3 = nullptr;
+    H16 qkv, P1, q2, kv2, P2;
+};
+
+class Arena {
+  public:
+    char* base = nullptr;
+    size_t cap = 0, off = 0, peak = 0;
+    void* alloc(size_t bytes) {
+        off = (off + 255) & ~size_t(255);
+        void* p = base ? base + off : reinterpret_cast<void*>(off + 256);   // fake pointers while measuring
+        off += bytes;
+        if (off > peak) peak = off;
+        return p;
+    }
+    void reset() { off = 0; }
+};
+
+class UNet {
+  public:
+    UNetConfig cfg;
+    explicit UNet(const UNetConfig& c) : cfg(c) {}
+    ~UNet();
+
+    // Weights: host fp32 tensors under their diffusers names (valid until load() returns).
+    int load(const std::map<std::string, HostParam>& params);
+
+    // eps[B,4,H,W] (NCHW fp32, device) = unet(x[B,4,H,W], t, ctx[B,ctx_len,cross_dim]).  With save_for_backward the
+    // activations needed by backward() stay resident until the next forward().
+    int forward(const float* x_nchw, int B, int H, int W, float t, const float* ctx, float* eps_nchw,
+                bool save_for_backward, cudaStream_t st);
+    // dx[B,4,H,W] (NCHW fp32) = sum_k J_k^T tap_grad[k]; tap_grad[k] is NHWC fp32 shaped like tap(k).
+    int backward(float* const tap_grads[9], float* dx_nchw, cudaStream_t st);
+
+    // The 9 taps of the last forward (NHWC fp32), hook order of latent_predictor.py:63-80.
+    F32 taps[9];
+    // Named intermediates of the last forward (debugging / parity bisecting).
+    std::map<std::string, F32> debug;
+    bool keep_debug = false;
+
+    size_t arena_bytes() const { return arena_.cap; }
+
+  private:
+    // parameters
+    Lin conv_in_;       // as im2col GEMM: w [C0][64]
+    Conv3 conv_in_d_;   // dgrad form
+    Lin time1_, time2_, temb_all_;
+    std::vector<ResBlock> res_;
+    std::vector<Transformer> tfm_;
+    std::vector<Conv3> down_, up_;
+    Norm norm_out_;
+    Conv3 conv_out_;
+    std::vector<void*> owned_;
+    bool loaded_ = false;
+
+    // execution state
+    Arena arena_;
+    bool dry_ = false;
+    bool save_ = false;
+    cudaStream_t st_ = nullptr;
+    int B_ = 0, H_ = 0, W_ = 0;
+    const float* ctx_ = nullptr;
+    float* temb_ = nullptr;      // fused time_emb_proj output [sum Cout]
+    double* stats_ = nullptr;    // GroupNorm sums arena (zeroed once per pass)
+    size_t stats_off_ = 0, stats_cap_ = 0;
+    std::vector<ResSave> rsave_;
+    std::vector<TfmSave> tsave_;
+    std::vector<F32> skips_;
+    bool have_saved_ = false;
+
+    int run_forward(const float* x_nchw, float t, float* eps_nchw);
+    int run_backward(float* const tap_grads[9], float* dx_nchw);
+
+    F32 new32(int B, int H, int W, int C);
+    H16 new16(int B, int H, int W, int C);
+    double* new_stats();
+    template <class T> T* dalloc(size_t n);
+
+    int k(int rc) { return rc; }
+    int gemm(const H16& a, bool spatial, int taps, const __half* w, long w_ld, int N, int Kc, const float* bias,
+             const float* rowvec, const F32* residual, F32* out32, H16* out16);
+    int resblock(int idx, const F32& x, F32& out);
+    int resblock_bwd(int idx, const F32& dout, F32& dx);
+    int transformer(int idx, const F32& x, F32& out);
+    int transformer_bwd(int idx, const F32& dout, F32& dx);
+    int attention(const Transformer& T, const H16& q, long q_c0, const H16& kv, long k_c0, long v_c0, int Nk, H16& P,
+                  H16& o);
+    int attention_bwd(const Transformer& T, const H16& dO, const H16& q, long q_c0, const H16& kv, long k_c0, long v_c0,
+                      int Nk, const H16& P, H16& dq, long dq_c0, H16* dkv, long dk_c0, long dv_c0);
+    int accumulate(F32& acc, const F32& g);
+};
+
+}  // namespace s2i

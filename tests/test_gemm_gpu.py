@@ -1,0 +1,165 @@
+"""Parity of the tcgen05/TMA implicit-GEMM kernel (sketch2img_b200/csrc/gemm_tc.cu) against fp64 torch
+references computed from the same fp16/bf16-rounded operands.  Tolerance: 2e-3 relative L2 (fp32
+accumulation-order noise only; operands are identical)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _dt(bf16):
+    return torch.bfloat16 if bf16 else torch.float16
+
+
+@pytest.fixture(scope="module")
+def L(cuda):
+    from sketch2img_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 150, 200), (2048, 320, 320), (77, 96, 768), (8192, 16, 320)])
+@pytest.mark.parametrize("bf16", [0, 1])
+def test_linear(L, cuda, M, N, K, bf16):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, generator=g).to(cuda).to(_dt(bf16))
+    w = torch.randn(N, K, generator=g).to(cuda).to(_dt(bf16))
+    bias = torch.randn(N, generator=g).to(cuda)
+    res = torch.randn(M, N, generator=g).to(cuda)
+    out32 = torch.zeros(M, N, device=cuda)
+    out16 = torch.zeros(M, N, device=cuda, dtype=torch.float16)
+    d = L.GemmDesc(A=a.data_ptr(), aC=K, aW=M, a_sw=K, B=w.data_ptr(), bI=K, bR=N, b_sr=K, N=N, Kc=K, bf16=bf16,
+                   alpha=0.5, bias=bias.data_ptr(), residual=res.data_ptr(), res_ld=N,
+                   out32=out32.data_ptr(), ld32=N, out16=out16.data_ptr(), ld16=N)
+    L.gemm(d)
+    torch.cuda.synchronize()
+    ref = 0.5 * (a.double() @ w.double().t()) + bias.double() + res.double()
+    assert rel(out32, ref) < 2e-3
+    assert rel(out16.float(), ref) < 3e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 32), (2, 8, 8, 128, 48), (1, 64, 64, 64, 64),
+                                            (2, 4, 4, 128, 64), (2, 2, 2, 64, 32), (3, 32, 32, 192, 80),
+                                            (2, 24, 24, 64, 32)])
+def test_conv3x3(L, cuda, B, H, W, Cin, Cout):
+    g = torch.Generator(device="cpu").manual_seed(B * 131 + H)
+    x = torch.randn(B, H, W, Cin, generator=g).to(cuda).half()           # NHWC
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * 0.1).to(cuda).half()
+    bias = torch.randn(Cout, generator=g).to(cuda)
+    temb = torch.randn(B, Cout, generator=g).to(cuda)
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()       # [Cout][tap][Cin]
+    out32 = torch.zeros(B, H, W, Cout, device=cuda)
+    d = L.GemmDesc(A=x.data_ptr(), aC=Cin, aW=W, aH=H, aB=B, a_sw=Cin, a_sh=Cin * W, a_sb=Cin * W * H, taps=9,
+                   B=wp.data_ptr(), bI=9 * Cin, bR=Cout, b_sr=9 * Cin, N=Cout, Kc=Cin, bias=bias.data_ptr(),
+                   rowvec=temb.data_ptr(), rowvec_ld=Cout, relu=1, out32=out32.data_ptr(), ld32=Cout)
+    L.gemm(d)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double(), padding=1)
+    ref = torch.relu(ref + temb.double()[:, :, None, None]).permute(0, 2, 3, 1)
+    assert rel(out32, ref) < 2e-3
+
+
+def _attn_inputs(cuda, B, N, heads, d, dp, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    HP = heads * dp
+    qkv = torch.randn(B, N, 3, heads, dp, generator=g)
+    qkv[..., d:] = 0.0                      # head padding is zero in the real layout
+    return qkv.reshape(B, N, 3 * HP).to(cuda).half().contiguous(), HP
+
+
+@pytest.mark.parametrize("B,N,heads,d,dp", [(2, 256, 8, 40, 48), (2, 64, 8, 160, 160), (1, 1024, 4, 80, 80),
+                                            (2, 16, 4, 16, 16), (2, 4096, 2, 40, 48)])
+def test_attention_products(L, cuda, B, N, heads, d, dp):
+    qkv, HP = _attn_inputs(cuda, B, N, heads, d, dp, N + d)
+    Z = B * heads
+    ldS = (N + 3) // 4 * 4
+    ldP = (N + 7) // 8 * 8
+    scale = d ** -0.5
+    q = qkv.view(B, N, 3, heads, dp)[:, :, 0].permute(0, 2, 1, 3).reshape(Z, N, dp).double()
+    k = qkv.view(B, N, 3, heads, dp)[:, :, 1].permute(0, 2, 1, 3).reshape(Z, N, dp).double()
+    v = qkv.view(B, N, 3, heads, dp)[:, :, 2].permute(0, 2, 1, 3).reshape(Z, N, dp).double()
+
+    # S = scale * Q K^T  (K-major x K-major, head-sliced operands, K = dp not a multiple of 64)
+    S = torch.zeros(Z, N, ldS, device=cuda)
+    d1 = L.GemmDesc(A=qkv.data_ptr(), aC=3 * HP, aW=N, aB=B, a_sw=3 * HP, a_sb=N * 3 * HP, a_hoff=dp,
+                    B=qkv.data_ptr(), bI=3 * HP, bR=N, bZ=B, b_sr=3 * HP, b_sz=N * 3 * HP, b_c0=HP, b_hoff=dp,
+                    N=N, Kc=dp, Z=Z, zh=heads, alpha=scale, out32=S.data_ptr(), ld32=ldS,
+                    c_sb=heads * N * ldS, c_sh=N * ldS)
+    L.gemm(d1)
+    torch.cuda.synchronize()
+    Sref = scale * q @ k.transpose(1, 2)
+    assert rel(S[:, :, :N], Sref) < 2e-3
+
+    # O = P V  (K-major P with batch = z, MN-major V sliced per head)
+    P = torch.softmax(Sref, -1).half()
+    Pbuf = torch.zeros(Z, N, ldP, device=cuda, dtype=torch.float16)
+    Pbuf[:, :, :N] = P
+    O = torch.zeros(B, N, HP, device=cuda, dtype=torch.float16)
+    d2 = L.GemmDesc(A=Pbuf.data_ptr(), aC=N, aW=N, aB=Z, a_sw=ldP, a_sb=N * ldP, a_zmode=1,
+                    B=qkv.data_ptr(), b_mn=1, bI=3 * HP, bR=N, bZ=B, b_sr=3 * HP, b_sz=N * 3 * HP, b_c0=2 * HP,
+                    b_hoff=dp, N=dp, BN=dp, Kc=N, Z=Z, zh=heads, out16=O.data_ptr(), ld16=HP, c_sb=N * HP, c_sh=dp)
+    L.gemm(d2)
+    torch.cuda.synchronize()
+    Oref = (P.double() @ v).reshape(B, heads, N, dp).permute(0, 2, 1, 3).reshape(B, N, HP)
+    assert rel(O.float(), Oref) < 3e-3
+
+    # dV = P^T dO  (MN-major A and MN-major B)
+    dO = torch.randn(B, N, HP, device=cuda).half()
+    dV = torch.zeros(B, N, 3 * HP, device=cuda, dtype=torch.float16)
+    d3 = L.GemmDesc(A=Pbuf.data_ptr(), a_mn=1, aC=N, aW=N, aB=Z, a_sw=ldP, a_sb=N * ldP, a_zmode=1,
+                    B=dO.data_ptr(), b_mn=1, bI=HP, bR=N, bZ=B, b_sr=HP, b_sz=N * HP, b_hoff=dp,
+                    N=dp, BN=dp, Kc=N, Z=Z, zh=heads, out16=dV.data_ptr() + 2 * HP * 2, ld16=3 * HP,
+                    c_sb=N * 3 * HP, c_sh=dp)
+    L.gemm(d3)
+    torch.cuda.synchronize()
+    dOh = dO.view(B, N, heads, dp).permute(0, 2, 1, 3).reshape(Z, N, dp).double()
+    dVref = (P.double().transpose(1, 2) @ dOh).reshape(B, heads, N, dp).permute(0, 2, 1, 3).reshape(B, N, HP)
+    assert rel(dV[:, :, 2 * HP:].float(), dVref) < 3e-3
+
+    # dP = dO V^T (fp32 out) and dQ = dS K (MN-major B = K section)
+    dP = torch.zeros(Z, N, ldS, device=cuda)
+    d4 = L.GemmDesc(A=dO.data_ptr(), aC=HP, aW=N, aB=B, a_sw=HP, a_sb=N * HP, a_hoff=dp,
+                    B=qkv.data_ptr(), bI=3 * HP, bR=N, bZ=B, b_sr=3 * HP, b_sz=N * 3 * HP, b_c0=2 * HP, b_hoff=dp,
+                    N=N, Kc=dp, Z=Z, zh=heads, out32=dP.data_ptr(), ld32=ldS, c_sb=heads * N * ldS, c_sh=N * ldS)
+    L.gemm(d4)
+    torch.cuda.synchronize()
+    assert rel(dP[:, :, :N], dOh @ v.transpose(1, 2)) < 2e-3
+
+
+def test_cross_attention_shapes(L, cuda):
+    """Nk = 77 (text tokens): ragged K extent for PV and N extent for QK^T."""
+    B, N, heads, dp, Nk = 2, 256, 8, 48, 77
+    HP = heads * dp
+    g = torch.Generator(device="cpu").manual_seed(5)
+    q = torch.randn(B, N, HP, generator=g).to(cuda).half()
+    kv = torch.randn(B, Nk, 2 * HP, generator=g).to(cuda).half()
+    Z = B * heads
+    ldS, ldP = 80, 80
+    S = torch.full((Z, N, ldS), float("nan"), device=cuda)
+    d1 = L.GemmDesc(A=q.data_ptr(), aC=HP, aW=N, aB=B, a_sw=HP, a_sb=N * HP, a_hoff=dp,
+                    B=kv.data_ptr(), bI=2 * HP, bR=Nk, bZ=B, b_sr=2 * HP, b_sz=Nk * 2 * HP, b_hoff=dp,
+                    N=Nk, Kc=dp, Z=Z, zh=heads, out32=S.data_ptr(), ld32=ldS, c_sb=heads * N * ldS, c_sh=N * ldS)
+    L.gemm(d1)
+    torch.cuda.synchronize()
+    qh = q.view(B, N, heads, dp).permute(0, 2, 1, 3).reshape(Z, N, dp).double()
+    kh = kv[:, :, :HP].reshape(B, Nk, heads, dp).permute(0, 2, 1, 3).reshape(Z, Nk, dp).double()
+    vh = kv[:, :, HP:].reshape(B, Nk, heads, dp).permute(0, 2, 1, 3).reshape(Z, Nk, dp).double()
+    Sref = qh @ kh.transpose(1, 2)
+    assert rel(S[:, :, :Nk], Sref) < 2e-3
+    P = torch.softmax(Sref * 0.1, -1).half()
+    Pbuf = torch.full((Z, N, ldP), float("nan"), device=cuda, dtype=torch.float16)   # pad must never be read
+    Pbuf[:, :, :Nk] = P
+    O = torch.zeros(B, N, HP, device=cuda, dtype=torch.float16)
+    d2 = L.GemmDesc(A=Pbuf.data_ptr(), aC=Nk, aW=N, aB=Z, a_sw=ldP, a_sb=N * ldP, a_zmode=1,
+                    B=kv.data_ptr(), b_mn=1, bI=2 * HP, bR=Nk, bZ=B, b_sr=2 * HP, b_sz=Nk * 2 * HP, b_c0=HP, b_hoff=dp,
+                    N=dp, BN=dp, Kc=Nk, Z=Z, zh=heads, out16=O.data_ptr(), ld16=HP, c_sb=N * HP, c_sh=dp)
+    L.gemm(d2)
+    torch.cuda.synchronize()
+    Oref = (P.double() @ vh).reshape(B, heads, N, dp).permute(0, 2, 1, 3).reshape(B, N, HP)
+    assert rel(O.float(), Oref) < 3e-3
