@@ -43,9 +43,46 @@ typedef struct s2i_gemm_desc {
     const float* residual; long long res_ld;
     float* out32; long long ld32; void* out16; long long ld16; int out16_bf16;
     long long c_sb, c_sh; int relu;
+    float qscale;   /* != 0: round the result as fp16(v / qscale) * qscale (mimics unscaled fp16 autograd rounding) */
 } s2i_gemm_desc;
 
 int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream);
+
+
+/* ---------------------------------------------------------------------------------------------
+ * UNet2DCondition engine: replaces `self.unet(x, t, encoder_hidden_states=...)` (modules/pipeline.py:96),
+ * the 9 forward hooks of hook_unet (modules/latent_predictor.py:47-81) and the UNet part of
+ * `torch.autograd.grad(loss, latents_prev)` (modules/pipeline.py:159).
+ * Weights are passed once as host fp32 tensors under their diffusers state-dict names.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct s2i_unet_config {
+    int in_channels, out_channels;
+    int block_out_channels[4];
+    int num_heads[4];              /* diffusers `attention_head_dim` (= number of heads) per level */
+    int layers_per_block;
+    int cross_attention_dim;
+    int sample_size;
+    int ctx_len;                   /* text tokens (77) */
+} s2i_unet_config;
+
+typedef struct s2i_unet s2i_unet;
+
+int s2i_unet_create(const s2i_unet_config* cfg, s2i_unet** out);
+void s2i_unet_destroy(s2i_unet* u);
+/* shapes: n x 4 (unused dims = 1); host pointers must stay valid until the call returns */
+int s2i_unet_load(s2i_unet* u, int n, const char* const* names, const float* const* host_ptrs, const int* ndims,
+                  const long long* shapes);
+/* x, eps: NCHW fp32 device [B,C,H,W]; ctx: fp32 device [B,ctx_len,cross_attention_dim] */
+int s2i_unet_forward(s2i_unet* u, const float* x, int B, int H, int W, float t, const float* ctx, float* eps,
+                     int save_for_backward, void* cuda_stream);
+/* tap k of the last forward: NHWC fp32 device view owned by the engine (valid until the next forward) */
+int s2i_unet_tap(s2i_unet* u, int k, float** ptr, int* B, int* H, int* W, int* C);
+/* tap_grads[k]: NHWC fp32 device, shaped like tap k (NULL = no gradient); dx: NCHW fp32 device [B,C,H,W] */
+int s2i_unet_backward(s2i_unet* u, float* const* tap_grads, float* dx, void* cuda_stream);
+/* bisecting aid: keep named block outputs of the next forwards ("conv_in", "down0".., "mid", "up0"..) */
+int s2i_unet_debug(s2i_unet* u, int enable);
+int s2i_unet_debug_get(s2i_unet* u, const char* name, float** ptr, long long* ld, int* B, int* H, int* W, int* C);
+long long s2i_unet_arena_bytes(s2i_unet* u);
 
 #ifdef __cplusplus
 }

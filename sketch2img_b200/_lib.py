@@ -24,7 +24,7 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int),
         ("residual", C.c_void_p), ("res_ld", C.c_longlong),
         ("out32", C.c_void_p), ("ld32", C.c_longlong), ("out16", C.c_void_p), ("ld16", C.c_longlong),
-        ("out16_bf16", C.c_int), ("c_sb", C.c_longlong), ("c_sh", C.c_longlong), ("relu", C.c_int),
+        ("out16_bf16", C.c_int), ("c_sb", C.c_longlong), ("c_sh", C.c_longlong), ("relu", C.c_int), ("qscale", C.c_float),
     ]
 
     def __init__(self, **kw):
@@ -34,6 +34,13 @@ class GemmDesc(C.Structure):
         self.alpha = 1.0
         for k, v in kw.items():
             setattr(self, k, v)
+
+
+class UNetConfig(C.Structure):
+    """Mirror of ``s2i_unet_config`` (include/s2i.h)."""
+    _fields_ = [("in_channels", C.c_int), ("out_channels", C.c_int), ("block_out_channels", C.c_int * 4),
+                ("num_heads", C.c_int * 4), ("layers_per_block", C.c_int), ("cross_attention_dim", C.c_int),
+                ("sample_size", C.c_int), ("ctx_len", C.c_int)]
 
 
 def lib():
@@ -52,6 +59,18 @@ def lib():
     h.s2i_launch_count.restype = C.c_longlong
     h.s2i_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     h.s2i_gemm.restype = C.c_int
+    vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_void_p)
+    h.s2i_unet_create.argtypes = [C.POINTER(UNetConfig), C.POINTER(vp)]
+    h.s2i_unet_destroy.argtypes = [vp]
+    h.s2i_unet_destroy.restype = None
+    h.s2i_unet_load.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(vp), ip, C.POINTER(C.c_longlong)]
+    h.s2i_unet_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, C.c_int, vp]
+    h.s2i_unet_tap.argtypes = [vp, C.c_int, fp, ip, ip, ip, ip]
+    h.s2i_unet_backward.argtypes = [vp, C.POINTER(vp), vp, vp]
+    h.s2i_unet_debug.argtypes = [vp, C.c_int]
+    h.s2i_unet_debug_get.argtypes = [vp, C.c_char_p, fp, C.POINTER(C.c_longlong), ip, ip, ip, ip]
+    h.s2i_unet_arena_bytes.argtypes = [vp]
+    h.s2i_unet_arena_bytes.restype = C.c_longlong
     _lib = h
     return h
 

@@ -2,6 +2,11 @@
 #include "../../include/s2i.h"
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "unet.cuh"
+
+struct s2i_unet {
+    s2i::UNet* impl;
+};
 
 extern "C" {
 
@@ -12,5 +17,80 @@ int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream) {
     if (!d) return s2i::set_error(S2I_ERR_ARG, "s2i_gemm: null descriptor");
     return s2i::gemm_launch(s2i::GemmDesc(*d), static_cast<cudaStream_t>(cuda_stream));
 }
+
+
+int s2i_unet_create(const s2i_unet_config* c, s2i_unet** out) {
+    if (!c || !out) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_create: null argument");
+    s2i::UNetConfig cfg;
+    cfg.in_ch = c->in_channels;
+    cfg.out_ch = c->out_channels;
+    for (int i = 0; i < 4; ++i) {
+        cfg.boc[i] = c->block_out_channels[i];
+        cfg.heads[i] = c->num_heads[i];
+        if (cfg.boc[i] % 64 != 0) return s2i::set_error(S2I_ERR_ARG, "block_out_channels must be multiples of 64");
+        if (cfg.heads[i] <= 0 || cfg.boc[i] % cfg.heads[i] != 0) return s2i::set_error(S2I_ERR_ARG, "bad head count");
+    }
+    cfg.layers = c->layers_per_block;
+    cfg.cross_dim = c->cross_attention_dim;
+    cfg.sample_size = c->sample_size;
+    cfg.ctx_len = c->ctx_len;
+    if (cfg.cross_dim % 8 != 0) return s2i::set_error(S2I_ERR_ARG, "cross_attention_dim must be a multiple of 8");
+    *out = new s2i_unet{new s2i::UNet(cfg)};
+    return 0;
+}
+
+void s2i_unet_destroy(s2i_unet* u) {
+    if (!u) return;
+    delete u->impl;
+    delete u;
+}
+
+int s2i_unet_load(s2i_unet* u, int n, const char* const* names, const float* const* host_ptrs, const int* ndims,
+                  const long long* shapes) {
+    if (!u) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_load: null engine");
+    std::map<std::string, s2i::HostParam> params;
+    for (int i = 0; i < n; ++i) {
+        s2i::HostParam hp;
+        hp.data = host_ptrs[i];
+        for (int k = 0; k < ndims[i]; ++k) hp.shape.push_back((long)shapes[i * 4 + k]);
+        params[names[i]] = hp;
+    }
+    return u->impl->load(params);
+}
+
+int s2i_unet_forward(s2i_unet* u, const float* x, int B, int H, int W, float t, const float* ctx, float* eps,
+                     int save_for_backward, void* cuda_stream) {
+    if (!u || !x || !ctx || !eps) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_forward: null argument");
+    return u->impl->forward(x, B, H, W, t, ctx, eps, save_for_backward != 0, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int s2i_unet_tap(s2i_unet* u, int k, float** ptr, int* B, int* H, int* W, int* C) {
+    if (!u || k < 0 || k >= 9) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_tap: bad tap index");
+    const s2i::F32& t = u->impl->taps[k];
+    if (!t.p) return s2i::set_error(S2I_ERR_STATE, "s2i_unet_tap: no forward yet");
+    *ptr = t.p; *B = t.B; *H = t.H; *W = t.W; *C = t.C;
+    return 0;
+}
+
+int s2i_unet_backward(s2i_unet* u, float* const* tap_grads, float* dx, void* cuda_stream) {
+    if (!u || !tap_grads || !dx) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_backward: null argument");
+    return u->impl->backward(tap_grads, dx, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int s2i_unet_debug(s2i_unet* u, int enable) {
+    if (!u) return s2i::set_error(S2I_ERR_ARG, "null engine");
+    u->impl->keep_debug = enable != 0;
+    return 0;
+}
+
+int s2i_unet_debug_get(s2i_unet* u, const char* name, float** ptr, long long* ld, int* B, int* H, int* W, int* C) {
+    if (!u) return s2i::set_error(S2I_ERR_ARG, "null engine");
+    auto it = u->impl->debug.find(name);
+    if (it == u->impl->debug.end()) return s2i::set_error(S2I_ERR_ARG, "no debug tensor named %s", name);
+    *ptr = it->second.p; *ld = it->second.ld; *B = it->second.B; *H = it->second.H; *W = it->second.W; *C = it->second.C;
+    return 0;
+}
+
+long long s2i_unet_arena_bytes(s2i_unet* u) { return u ? (long long)u->impl->arena_bytes() : 0; }
 
 }  // extern "C"

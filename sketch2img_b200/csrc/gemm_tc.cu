@@ -43,6 +43,7 @@ struct __align__(64) GemmParams {
     int out16_bf16;
     long c_sb, c_sh;
     int relu;
+    float qscale, qinv;
 };
 
 __device__ __forceinline__ uint16_t to_half_bits(float v, int bf16) {
@@ -242,6 +243,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 if (p.relu) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (p.qscale != 0.f) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = __half2float(__float2half_rn(v[j] * p.qinv)) * p.qscale;
                 }
                 if (res) {
                     if (full4 && vecres && ((n & 3) == 0)) {
@@ -456,6 +461,8 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     p.c_sb = d.c_sb;
     p.c_sh = d.c_sh;
     p.relu = d.relu;
+    p.qscale = d.qscale;
+    p.qinv = d.qscale != 0.f ? 1.f / d.qscale : 0.f;
 
     // ---- tensor maps
     {

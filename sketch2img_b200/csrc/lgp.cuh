@@ -1,0 +1,81 @@
+// Latent Guidance Predictor: per-pixel MLP over the concatenated, bilinearly resized UNet taps
+// (reference: modules/latent_predictor.py:9-45 forward; modules/pipeline.py:145-159 feature build, edge loss and
+// autograd backward to the taps).  BatchNorm1d runs with per-sample batch statistics (train mode)
+// or running statistics (eval mode).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "unet.cuh"
+
+namespace s2i {
+
+struct LgpTap {
+    const float* p;   // NHWC fp32 [B][S][S][C]
+    int S, C;
+};
+
+class LGP {
+  public:
+    LGP(int input_dim, int output_dim, int num_pos_layers);
+    ~LGP();
+    int load(const std::map<std::string, HostParam>& params);
+
+    // Forward on B = 2*samples latents of side L.  noise: NCHW fp32 [samples,4,L,L]; lvl = sigma * noise is the
+    // "noise level" input shared by both CFG halves (pipeline.py:152-153).  Rows are ordered (b, h, w).
+    // out16: fp16 [B*L*L][8] (first output_dim columns valid).
+    int forward(const LgpTap taps[9], int B, int L, const float* noise, float sigma, bool train, cudaStream_t st);
+    // Edge loss on the cond half + backward to the taps.  target: NCHW fp32 [samples,4,L,L].
+    // tap_grads[k]: NHWC fp32 like tap k, multiplied by grad_scale(); loss: device float [samples].
+    int loss_backward(const float* target, float* const tap_grads[9], float* loss, cudaStream_t st);
+    float grad_scale() const { return gscale_; }
+    const __half* output() const { return out16_; }
+    // out_rows: fp32 [(b w h)][output_dim] in the reference's row order (latent_predictor.py:43)
+    int export_output(float* out_rows, cudaStream_t st);
+    // features from an already concatenated NCHW fp32 tensor x [B][input_dim-4-4*P][L][L] and t [B][4][L][L]
+    int forward_nchw(const float* x, const float* t, int B, int L, bool train, cudaStream_t st);
+
+    int input_dim() const { return D_; }
+
+  private:
+    int D_, O_, P_;
+    long ldX_ = 0;
+    int widths_[6];
+    Lin lin_[5];
+    Norm bn_[4];
+    float* bn_rm_[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* bn_rv_[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<void*> owned_;
+    bool loaded_ = false;
+
+    // per-call state
+    char* buf_ = nullptr;
+    size_t buf_cap_ = 0;
+    int B_ = 0, L_ = 0;
+    bool train_ = true;
+    LgpTap taps_[9];
+    __half* X_ = nullptr;        // [rows][ldX]
+    __half* h_[4] = {};          // ReLU outputs (BN inputs)   [rows][w]
+    __half* a_[4] = {};          // BN outputs (next GEMM operand)
+    double* bsum_[4] = {};       // per (sample, column) sum / sumsq
+    __half* out16_ = nullptr;    // [rows][8]
+    float gscale_ = 1.f;
+
+    int ensure(size_t bytes);
+    int mlp(cudaStream_t st);
+};
+
+// ---- scheduler / guidance update (modules/pipeline.py:100-104, :160-161; DDIM step per SURVEY A.6) -----------
+// eps: [2*S][n] ordered (uncond_s, cond_s); latents: [S][n].  prediction: 0 = epsilon, 1 = v_prediction.
+int cfg_ddim_step(const float* latents, const float* eps, int S, int n, float guidance, float sb_t, float sa_t,
+                  float sa_p, float sb_p, int prediction, float* out, cudaStream_t st);
+// x_new += beta * ||x_in - x_new||_F / ||g||_F * g with g = -dx[cond half]; norms per sample; x_in = [x_old, x_old].
+// dx: [2*S][n].  scratch: double [S][2] device.
+int guidance_update(const float* x_old, float* x_new, const float* dx, int S, int n, float beta, double* scratch,
+                    cudaStream_t st);
+
+}  // namespace s2i

@@ -1,0 +1,955 @@
+// UNet2DCondition forward (+9 taps) and tap->input backward.  See unet.cuh.
+#include "unet.cuh"
+
+#include <cmath>
+#include <cstring>
+
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace s2i {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ weight packing
+__device__ __forceinline__ long padmap(long x, int d, int dp) {
+    if (d == dp || dp == 0) return x;
+    const long h = x / dp, j = x - h * dp;
+    return j < d ? h * d + j : -1;
+}
+
+// out(r,c) = S(pm_r(r), pm_c(c))  (or S(pm_c(c), pm_r(r)) when transpose); S fp32 row-major with src_ld.
+__global__ void pack2d_kernel(const float* __restrict__ src, long src_ld, int transpose, long R, long Cc, int d_r,
+                              int dp_r, int d_c, int dp_c, __half* __restrict__ out, long out_ld) {
+    const long total = R * Cc;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long r = idx / Cc, c = idx - r * Cc;
+        const long i = padmap(r, d_r, dp_r), j = padmap(c, d_c, dp_c);
+        float v = 0.f;
+        if (i >= 0 && j >= 0) v = transpose ? src[j * src_ld + i] : src[i * src_ld + j];
+        out[r * out_ld + c] = __float2half_rn(v);
+    }
+}
+
+// src [Co][Ci][3][3] -> fwd out[co*out_ld + tap*Ci + ci]   |   dgrad out[ci*out_ld + tap*Co + co] with flipped taps
+__global__ void pack_conv_kernel(const float* __restrict__ src, int Co, int Ci, int dgrad, __half* __restrict__ out,
+                                 long out_ld) {
+    const long total = (long)Co * Ci * 9;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int kk = (int)(idx % 9);
+        const long rest = idx / 9;
+        const int ci = (int)(rest % Ci);
+        const int co = (int)(rest / Ci);
+        const float v = src[idx];
+        if (!dgrad) {
+            out[(long)co * out_ld + (long)kk * Ci + ci] = __float2half_rn(v);
+        } else {
+            out[(long)ci * out_ld + (long)(8 - kk) * Co + co] = __float2half_rn(v);
+        }
+    }
+}
+
+inline long rup(long a, long b) { return (a + b - 1) / b * b; }
+
+}  // namespace
+
+// ================================================================================================== loading
+UNet::~UNet() {
+    for (void* p : owned_) cudaFree(p);
+    if (arena_.base) cudaFree(arena_.base);
+}
+
+struct Loader {
+    const std::map<std::string, HostParam>& params;
+    std::vector<void*>& owned;
+    float* staging = nullptr;
+    size_t staging_elems = 0;
+    std::string err;
+
+    const HostParam* find(const std::string& name, size_t expect_elems) {
+        auto it = params.find(name);
+        if (it == params.end()) {
+            err = "missing parameter " + name;
+            return nullptr;
+        }
+        size_t n = 1;
+        for (long s : it->second.shape) n *= (size_t)s;
+        if (n != expect_elems) {
+            err = "parameter " + name + " has " + std::to_string(n) + " elements, expected " + std::to_string(expect_elems);
+            return nullptr;
+        }
+        return &it->second;
+    }
+    template <class T>
+    T* dmalloc(size_t n, bool zero = false) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) {
+            err = "cudaMalloc failed for weights";
+            return nullptr;
+        }
+        if (zero) cudaMemset(p, 0, n * sizeof(T));
+        owned.push_back(p);
+        return static_cast<T*>(p);
+    }
+    const float* stage(const HostParam* hp, size_t n) {
+        if (n > staging_elems) {
+            if (staging) cudaFree(staging);
+            staging_elems = n;
+            if (cudaMalloc(&staging, n * sizeof(float)) != cudaSuccess) {
+                err = "cudaMalloc failed for staging";
+                return nullptr;
+            }
+        }
+        if (cudaMemcpy(staging, hp->data, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            err = "H2D copy failed";
+            return nullptr;
+        }
+        return staging;
+    }
+    float* vec(const std::string& name, size_t n) {
+        const HostParam* hp = find(name, n);
+        if (!hp) return nullptr;
+        float* d = dmalloc<float>(n);
+        if (!d) return nullptr;
+        cudaMemcpy(d, hp->data, n * sizeof(float), cudaMemcpyHostToDevice);
+        return d;
+    }
+    bool norm(const std::string& pre, int C, float eps, Norm& n) {
+        n.C = C;
+        n.eps = eps;
+        n.g = vec(pre + ".weight", C);
+        n.b = vec(pre + ".bias", C);
+        return n.g && n.b;
+    }
+    // Plain / head-padded linear.  pad_n: output features are (heads x d) -> (heads x dp); pad_k likewise for inputs.
+    bool linear_into(const std::string& wname, int N, int K, int d, int dp, bool pad_n, bool pad_k, __half* w, long w_ld,
+                     long w_row0, __half* wd, long wd_ld, long wd_col0, bool want_dgrad) {
+        const HostParam* hp = find(wname, (size_t)N * K);
+        if (!hp) return false;
+        const float* s = stage(hp, (size_t)N * K);
+        if (!s) return false;
+        const long Np = pad_n ? (long)N / d * dp : N;
+        const long Kp = pad_k ? (long)K / d * dp : K;
+        pack2d_kernel<<<1024, 256>>>(s, K, 0, Np, Kp, pad_n ? d : 0, pad_n ? dp : 0, pad_k ? d : 0, pad_k ? dp : 0,
+                                     w + w_row0 * w_ld, w_ld);
+        if (want_dgrad)
+            pack2d_kernel<<<1024, 256>>>(s, K, 1, Kp, Np, pad_k ? d : 0, pad_k ? dp : 0, pad_n ? d : 0, pad_n ? dp : 0,
+                                         wd + wd_col0, wd_ld);
+        return cudaDeviceSynchronize() == cudaSuccess;
+    }
+    bool linear(const std::string& pre, int N, int K, bool bias, Lin& l, bool want_dgrad = true) {
+        l.N = N;
+        l.K = K;
+        l.w = dmalloc<__half>((size_t)N * K);
+        if (want_dgrad) l.wd = dmalloc<__half>((size_t)N * K);
+        if (!l.w || (want_dgrad && !l.wd)) return false;
+        if (!linear_into(pre + ".weight", N, K, 0, 0, false, false, l.w, K, 0, l.wd, N, 0, want_dgrad)) return false;
+        if (bias) {
+            l.b = vec(pre + ".bias", N);
+            if (!l.b) return false;
+        }
+        return true;
+    }
+    bool conv3(const std::string& pre, int Co, int Ci, Conv3& c, bool want_dgrad = true, bool want_fwd = true) {
+        c.Cin = Ci;
+        c.Cout = Co;
+        const size_t n = (size_t)Co * Ci * 9;
+        const HostParam* hp = find(pre + ".weight", n);
+        if (!hp) return false;
+        const float* s = stage(hp, n);
+        if (!s) return false;
+        if (want_fwd) {
+            c.w = dmalloc<__half>(n);
+            if (!c.w) return false;
+            pack_conv_kernel<<<2048, 256>>>(s, Co, Ci, 0, c.w, 9L * Ci);
+        }
+        if (want_dgrad) {
+            c.wd = dmalloc<__half>(n);
+            if (!c.wd) return false;
+            pack_conv_kernel<<<2048, 256>>>(s, Co, Ci, 1, c.wd, 9L * Co);
+        }
+        if (cudaDeviceSynchronize() != cudaSuccess) {
+            err = "pack_conv failed";
+            return false;
+        }
+        c.b = vec(pre + ".bias", Co);
+        return c.b != nullptr;
+    }
+};
+
+int UNet::load(const std::map<std::string, HostParam>& params) {
+    Loader L{params, owned_};
+    const int* boc = cfg.boc;
+    const int temb_dim = boc[0] * 4;
+    int temb_total = 0;
+    struct TembSrc { std::string name; int C; };
+    std::vector<TembSrc> temb_srcs;
+
+    auto fail = [&](const char* what) {
+        if (L.staging) cudaFree(L.staging);
+        return set_error(S2I_ERR_ARG, "unet load (%s): %s", what, L.err.c_str());
+    };
+
+    auto load_res = [&](const std::string& pre, int Cin, int Cout) -> bool {
+        ResBlock r;
+        r.Cin = Cin;
+        r.Cout = Cout;
+        if (!L.norm(pre + ".norm1", Cin, 1e-5f, r.n1)) return false;
+        if (!L.conv3(pre + ".conv1", Cout, Cin, r.c1)) return false;
+        if (!L.norm(pre + ".norm2", Cout, 1e-5f, r.n2)) return false;
+        if (!L.conv3(pre + ".conv2", Cout, Cout, r.c2)) return false;
+        r.has_sc = Cin != Cout;
+        if (r.has_sc && !L.linear(pre + ".conv_shortcut", Cout, Cin, true, r.sc)) return false;
+        r.temb_off = temb_total;
+        temb_total += Cout;
+        temb_srcs.push_back({pre + ".time_emb_proj", Cout});
+        res_.push_back(r);
+        return true;
+    };
+    auto load_tfm = [&](const std::string& pre, int C, int heads) -> bool {
+        Transformer T;
+        T.C = C;
+        T.heads = heads;
+        T.d = C / heads;
+        T.dp = (int)rup(T.d, 16);
+        T.HP = heads * T.dp;
+        const int D = cfg.cross_dim;
+        const std::string tb = pre + ".transformer_blocks.0";
+        if (!L.norm(pre + ".norm", C, 1e-6f, T.gn)) return false;
+        if (!L.linear(pre + ".proj_in", C, C, true, T.proj_in)) return false;
+        if (!L.linear(pre + ".proj_out", C, C, true, T.proj_out)) return false;
+        if (!L.norm(tb + ".norm1", C, 1e-5f, T.ln1) || !L.norm(tb + ".norm2", C, 1e-5f, T.ln2) ||
+            !L.norm(tb + ".norm3", C, 1e-5f, T.ln3))
+            return false;
+        // fused, head-padded self-attention projection
+        T.qkv.N = 3 * T.HP;
+        T.qkv.K = C;
+        T.qkv.w = L.dmalloc<__half>((size_t)3 * T.HP * C, true);
+        T.qkv.wd = L.dmalloc<__half>((size_t)3 * T.HP * C, true);
+        if (!T.qkv.w || !T.qkv.wd) return false;
+        const char* names[3] = {".attn1.to_q", ".attn1.to_k", ".attn1.to_v"};
+        for (int s = 0; s < 3; ++s)
+            if (!L.linear_into(tb + names[s] + ".weight", C, C, T.d, T.dp, true, false, T.qkv.w, C, (long)s * T.HP,
+                               T.qkv.wd, 3L * T.HP, (long)s * T.HP, true))
+                return false;
+        auto out_proj = [&](const std::string& p, Lin& l) -> bool {
+            l.N = C;
+            l.K = T.HP;
+            l.w = L.dmalloc<__half>((size_t)C * T.HP, true);
+            l.wd = L.dmalloc<__half>((size_t)C * T.HP, true);
+            if (!l.w || !l.wd) return false;
+            if (!L.linear_into(p + ".weight", C, C, T.d, T.dp, false, true, l.w, T.HP, 0, l.wd, C, 0, true)) return false;
+            l.b = L.vec(p + ".bias", C);
+            return l.b != nullptr;
+        };
+        if (!out_proj(tb + ".attn1.to_out.0", T.o1)) return false;
+        T.q2.N = T.HP;
+        T.q2.K = C;
+        T.q2.w = L.dmalloc<__half>((size_t)T.HP * C, true);
+        T.q2.wd = L.dmalloc<__half>((size_t)T.HP * C, true);
+        if (!T.q2.w || !T.q2.wd) return false;
+        if (!L.linear_into(tb + ".attn2.to_q.weight", C, C, T.d, T.dp, true, false, T.q2.w, C, 0, T.q2.wd, T.HP, 0, true))
+            return false;
+        T.kv2.N = 2 * T.HP;
+        T.kv2.K = D;
+        T.kv2.w = L.dmalloc<__half>((size_t)2 * T.HP * D, true);
+        if (!T.kv2.w) return false;
+        if (!L.linear_into(tb + ".attn2.to_k.weight", C, D, T.d, T.dp, true, false, T.kv2.w, D, 0, nullptr, 0, 0, false))
+            return false;
+        if (!L.linear_into(tb + ".attn2.to_v.weight", C, D, T.d, T.dp, true, false, T.kv2.w, D, T.HP, nullptr, 0, 0, false))
+            return false;
+        if (!out_proj(tb + ".attn2.to_out.0", T.o2)) return false;
+        if (!L.linear(tb + ".ff.net.0.proj", 8 * C, C, true, T.ff1)) return false;
+        if (!L.linear(tb + ".ff.net.2", C, 4 * C, true, T.ff2)) return false;
+        tfm_.push_back(T);
+        return true;
+    };
+
+    // conv_in: forward as an im2col GEMM (K = 9*in_ch padded to 64), backward as a 3x3 dgrad conv
+    {
+        const int Ci = cfg.in_ch, Co = boc[0];
+        const HostParam* hp = L.find("conv_in.weight", (size_t)Co * Ci * 9);
+        if (!hp) return fail("conv_in");
+        const float* s = L.stage(hp, (size_t)Co * Ci * 9);
+        conv_in_.N = Co;
+        conv_in_.K = 64;
+        conv_in_.w = L.dmalloc<__half>((size_t)Co * 64, true);
+        if (!s || !conv_in_.w) return fail("conv_in");
+        pack_conv_kernel<<<64, 256>>>(s, Co, Ci, 0, conv_in_.w, 64);
+        conv_in_d_.Cin = Ci;
+        conv_in_d_.Cout = Co;
+        conv_in_d_.wd = L.dmalloc<__half>((size_t)Co * Ci * 9);
+        if (!conv_in_d_.wd) return fail("conv_in");
+        pack_conv_kernel<<<64, 256>>>(s, Co, Ci, 1, conv_in_d_.wd, 9L * Co);
+        cudaDeviceSynchronize();
+        conv_in_.b = L.vec("conv_in.bias", Co);
+        if (!conv_in_.b) return fail("conv_in");
+    }
+    if (!L.linear("time_embedding.linear_1", temb_dim, boc[0], true, time1_, false)) return fail("time_embedding");
+    if (!L.linear("time_embedding.linear_2", temb_dim, temb_dim, true, time2_, false)) return fail("time_embedding");
+
+    // down path
+    int ch = boc[0];
+    for (int i = 0; i < 4; ++i) {
+        const std::string pre = "down_blocks." + std::to_string(i);
+        for (int j = 0; j < cfg.layers; ++j) {
+            if (!load_res(pre + ".resnets." + std::to_string(j), j == 0 ? ch : boc[i], boc[i])) return fail("down resnet");
+            if (i < 3 && !load_tfm(pre + ".attentions." + std::to_string(j), boc[i], cfg.heads[i])) return fail("down attn");
+        }
+        ch = boc[i];
+        if (i < 3) {
+            Conv3 c;
+            if (!L.conv3(pre + ".downsamplers.0.conv", ch, ch, c)) return fail("downsample");
+            down_.push_back(c);
+        }
+    }
+    // mid
+    if (!load_res("mid_block.resnets.0", boc[3], boc[3])) return fail("mid");
+    if (!load_tfm("mid_block.attentions.0", boc[3], cfg.heads[3])) return fail("mid");
+    if (!load_res("mid_block.resnets.1", boc[3], boc[3])) return fail("mid");
+    // up path
+    {
+        int rev[4] = {boc[3], boc[2], boc[1], boc[0]};
+        int out_c = rev[0];
+        for (int i = 0; i < 4; ++i) {
+            const std::string pre = "up_blocks." + std::to_string(i);
+            const int prev = out_c;
+            out_c = rev[i];
+            const int in_c = rev[i + 1 < 4 ? i + 1 : 3];
+            for (int j = 0; j < cfg.layers + 1; ++j) {
+                const int skip = (j == cfg.layers) ? in_c : out_c;
+                const int first = (j == 0) ? prev : out_c;
+                if (!load_res(pre + ".resnets." + std::to_string(j), first + skip, out_c)) return fail("up resnet");
+                if (i > 0 && !load_tfm(pre + ".attentions." + std::to_string(j), out_c, cfg.heads[3 - i]))
+                    return fail("up attn");
+            }
+            if (i < 3) {
+                Conv3 c;
+                if (!L.conv3(pre + ".upsamplers.0.conv", out_c, out_c, c)) return fail("upsample");
+                up_.push_back(c);
+            }
+        }
+    }
+    if (!L.norm("conv_norm_out", boc[0], 1e-5f, norm_out_)) return fail("conv_norm_out");
+    if (!L.conv3("conv_out", cfg.out_ch, boc[0], conv_out_, false, true)) return fail("conv_out");
+
+    // fused time_emb_proj of every resnet: [sum Cout][temb_dim]
+    temb_all_.N = temb_total;
+    temb_all_.K = temb_dim;
+    temb_all_.w = L.dmalloc<__half>((size_t)temb_total * temb_dim);
+    temb_all_.b = L.dmalloc<float>(temb_total);
+    if (!temb_all_.w || !temb_all_.b) return fail("temb");
+    {
+        long row = 0;
+        for (auto& ts : temb_srcs) {
+            if (!L.linear_into(ts.name + ".weight", ts.C, temb_dim, 0, 0, false, false, temb_all_.w, temb_dim, row, nullptr,
+                               0, 0, false))
+                return fail("time_emb_proj");
+            const HostParam* hb = L.find(ts.name + ".bias", ts.C);
+            if (!hb) return fail("time_emb_proj");
+            cudaMemcpy(temb_all_.b + row, hb->data, ts.C * sizeof(float), cudaMemcpyHostToDevice);
+            row += ts.C;
+        }
+    }
+    if (L.staging) cudaFree(L.staging);
+    if (cudaDeviceSynchronize() != cudaSuccess) return set_error(S2I_ERR_CUDA, "unet load: %s", cudaGetErrorString(cudaGetLastError()));
+    rsave_.resize(res_.size());
+    tsave_.resize(tfm_.size());
+    loaded_ = true;
+    return 0;
+}
+
+// ================================================================================================== helpers
+#define RUN(call)                  \
+    do {                           \
+        if (!dry_) S2I_TRY(call);  \
+    } while (0)
+
+F32 UNet::new32(int B, int H, int W, int C) {
+    F32 t;
+    t.B = B; t.H = H; t.W = W; t.C = C;
+    t.ld = C;
+    t.p = static_cast<float*>(arena_.alloc((size_t)B * H * W * C * sizeof(float)));
+    return t;
+}
+H16 UNet::new16(int B, int H, int W, int C) {
+    H16 t;
+    t.B = B; t.H = H; t.W = W; t.C = C;
+    t.ld = C;
+    t.p = static_cast<__half*>(arena_.alloc((size_t)B * H * W * C * sizeof(__half)));
+    return t;
+}
+template <class T>
+T* UNet::dalloc(size_t n) {
+    return static_cast<T*>(arena_.alloc(n * sizeof(T)));
+}
+double* UNet::new_stats() {
+    const size_t n = (size_t)B_ * kGroups * 2;
+    double* p = stats_ + stats_off_;
+    stats_off_ += n;
+    return p;
+}
+
+int UNet::gemm(const H16& a, bool spatial, int taps, const __half* w, long w_ld, int N, int Kc, const float* bias,
+               const float* rowvec, const F32* residual, F32* out32, H16* out16) {
+    if (dry_) return 0;
+    GemmDesc d;
+    d.A = a.p;
+    d.aC = Kc;
+    if (spatial) {
+        d.aW = a.W; d.aH = a.H; d.aB = a.B;
+        d.a_sw = a.ld; d.a_sh = a.ld * a.W; d.a_sb = a.ld * a.W * a.H;
+    } else {
+        d.aW = (int)a.rows(); d.aH = 1; d.aB = 1;
+        d.a_sw = a.ld;
+    }
+    d.taps = taps;
+    d.B = w;
+    d.bI = taps * Kc;
+    d.bR = N;
+    d.b_sr = w_ld;
+    d.N = N;
+    d.Kc = Kc;
+    d.bias = bias;
+    d.rowvec = rowvec;
+    d.rowvec_ld = 0;
+    if (residual) {
+        d.residual = residual->p;
+        d.res_ld = residual->ld;
+    }
+    if (out32) {
+        d.out32 = out32->p;
+        d.ld32 = out32->ld;
+    }
+    if (out16) {
+        d.out16 = out16->p;
+        d.ld16 = out16->ld;
+    }
+    return gemm_launch(d, st_);
+}
+
+int UNet::accumulate(F32& acc, const F32& g) {
+    if (!g.p) return 0;
+    if (!acc.p) {
+        acc = g;
+        return 0;
+    }
+    F32 out = new32(acc.B, acc.H, acc.W, acc.C);
+    RUN(add2d(acc.p, acc.ld, g.p, g.ld, acc.rows(), acc.C, out.p, out.ld, nullptr, 0, st_));
+    acc = out;
+    return 0;
+}
+
+// ================================================================================================== ResnetBlock2D
+int UNet::resblock(int idx, const F32& x, F32& out) {
+    const ResBlock& R = res_[idx];
+    const int B = x.B, H = x.H, W = x.W, HW = H * W;
+    double* s1 = new_stats();
+    RUN(gn_stats(x.p, x.ld, B, HW, R.Cin, s1, st_));
+    H16 a1 = new16(B, H, W, R.Cin);
+    H16 x16;
+    if (R.has_sc) x16 = new16(B, H, W, R.Cin);
+    RUN(gn_apply(x.p, x.ld, B, HW, R.Cin, s1, R.n1.g, R.n1.b, R.n1.eps, 1, a1.p, a1.ld, R.has_sc ? x16.p : nullptr,
+                 R.has_sc ? x16.ld : 0, st_));
+    F32 h1 = new32(B, H, W, R.Cout);
+    S2I_TRY(gemm(a1, true, 9, R.c1.w, 9L * R.Cin, R.Cout, R.Cin, R.c1.b, temb_ + R.temb_off, nullptr, &h1, nullptr));
+    double* s2 = new_stats();
+    RUN(gn_stats(h1.p, h1.ld, B, HW, R.Cout, s2, st_));
+    H16 a2 = new16(B, H, W, R.Cout);
+    RUN(gn_apply(h1.p, h1.ld, B, HW, R.Cout, s2, R.n2.g, R.n2.b, R.n2.eps, 1, a2.p, a2.ld, nullptr, 0, st_));
+    F32 res = x;
+    if (R.has_sc) {
+        F32 sc = new32(B, H, W, R.Cout);
+        S2I_TRY(gemm(x16, false, 1, R.sc.w, R.Cin, R.Cout, R.Cin, R.sc.b, nullptr, nullptr, &sc, nullptr));
+        res = sc;
+    }
+    out = new32(B, H, W, R.Cout);
+    S2I_TRY(gemm(a2, true, 9, R.c2.w, 9L * R.Cout, R.Cout, R.Cout, R.c2.b, nullptr, &res, &out, nullptr));
+    if (save_) {
+        rsave_[idx].x = x;
+        rsave_[idx].h1 = h1;
+        rsave_[idx].s1 = s1;
+        rsave_[idx].s2 = s2;
+    }
+    return 0;
+}
+
+int UNet::resblock_bwd(int idx, const F32& dout, F32& dx) {
+    const ResBlock& R = res_[idx];
+    const ResSave& S = rsave_[idx];
+    const int B = dout.B, H = dout.H, W = dout.W, HW = H * W;
+    H16 d16 = new16(B, H, W, R.Cout);
+    RUN(cast2d(dout.p, dout.ld, dout.rows(), R.Cout, 1.f, d16.p, d16.ld, st_));
+    F32 da2 = new32(B, H, W, R.Cout);
+    S2I_TRY(gemm(d16, true, 9, R.c2.wd, 9L * R.Cout, R.Cout, R.Cout, nullptr, nullptr, nullptr, &da2, nullptr));
+    double* bs2 = new_stats();
+    RUN(gn_bwd_stats(da2.p, da2.ld, S.h1.p, S.h1.ld, B, HW, R.Cout, S.s2, R.n2.g, R.n2.b, R.n2.eps, 1, bs2, st_));
+    H16 dh1 = new16(B, H, W, R.Cout);
+    RUN(gn_bwd_apply(da2.p, da2.ld, S.h1.p, S.h1.ld, B, HW, R.Cout, S.s2, bs2, R.n2.g, R.n2.b, R.n2.eps, 1, nullptr, 0,
+                     nullptr, 0, dh1.p, dh1.ld, st_));
+    F32 da1 = new32(B, H, W, R.Cin);
+    S2I_TRY(gemm(dh1, true, 9, R.c1.wd, 9L * R.Cout, R.Cin, R.Cout, nullptr, nullptr, nullptr, &da1, nullptr));
+    double* bs1 = new_stats();
+    RUN(gn_bwd_stats(da1.p, da1.ld, S.x.p, S.x.ld, B, HW, R.Cin, S.s1, R.n1.g, R.n1.b, R.n1.eps, 1, bs1, st_));
+    dx = new32(B, H, W, R.Cin);
+    if (R.has_sc) {
+        F32 tmp = new32(B, H, W, R.Cin);
+        RUN(gn_bwd_apply(da1.p, da1.ld, S.x.p, S.x.ld, B, HW, R.Cin, S.s1, bs1, R.n1.g, R.n1.b, R.n1.eps, 1, nullptr, 0,
+                         tmp.p, tmp.ld, nullptr, 0, st_));
+        S2I_TRY(gemm(d16, false, 1, R.sc.wd, R.Cout, R.Cin, R.Cout, nullptr, nullptr, &tmp, &dx, nullptr));
+    } else {
+        RUN(gn_bwd_apply(da1.p, da1.ld, S.x.p, S.x.ld, B, HW, R.Cin, S.s1, bs1, R.n1.g, R.n1.b, R.n1.eps, 1, dout.p,
+                         dout.ld, dx.p, dx.ld, nullptr, 0, st_));
+    }
+    return 0;
+}
+
+// ================================================================================================== attention
+// q: [B*Nq][q.ld] with this attention's Q heads at column q_c0; kv: [B*Nk][kv.ld] with K heads at k_c0, V at v_c0.
+int UNet::attention(const Transformer& T, const H16& q, long q_c0, const H16& kv, long k_c0, long v_c0, int Nk, H16& P,
+                    H16& o) {
+    const int B = q.B, Nq = q.H * q.W, Z = B * T.heads;
+    const long ldS = rup(Nk, 4), ldP = rup(Nk, 8);
+    float* S = dalloc<float>((size_t)Z * Nq * ldS);
+    P = H16();
+    P.B = Z; P.H = 1; P.W = Nq; P.C = Nk; P.ld = ldP;
+    P.p = dalloc<__half>((size_t)Z * Nq * ldP);
+    o = new16(q.B, q.H, q.W, T.HP);
+    if (dry_) return 0;
+    GemmDesc d;
+    d.A = q.p; d.aC = (int)q.ld; d.aW = Nq; d.aB = B; d.a_sw = q.ld; d.a_sb = (long)Nq * q.ld;
+    d.a_c0 = (int)q_c0; d.a_hoff = T.dp;
+    d.B = kv.p; d.bI = (int)kv.ld; d.bR = Nk; d.bZ = B; d.b_sr = kv.ld; d.b_sz = (long)Nk * kv.ld;
+    d.b_c0 = (int)k_c0; d.b_hoff = T.dp;
+    d.N = Nk; d.Kc = T.dp; d.Z = Z; d.zh = T.heads;
+    d.alpha = 1.f / sqrtf((float)T.d);
+    d.out32 = S; d.ld32 = ldS; d.c_sb = (long)T.heads * Nq * ldS; d.c_sh = (long)Nq * ldS;
+    S2I_TRY(gemm_launch(d, st_));
+    S2I_TRY(softmax_fwd(S, ldS, (long)Z * Nq, Nk, P.p, ldP, st_));
+    GemmDesc e;
+    e.A = P.p; e.aC = Nk; e.aW = Nq; e.aB = Z; e.a_sw = ldP; e.a_sb = (long)Nq * ldP; e.a_zmode = 1;
+    e.B = kv.p; e.b_mn = 1; e.bI = (int)kv.ld; e.bR = Nk; e.bZ = B; e.b_sr = kv.ld; e.b_sz = (long)Nk * kv.ld;
+    e.b_c0 = (int)v_c0; e.b_hoff = T.dp;
+    e.N = T.dp; e.BN = T.dp; e.Kc = Nk; e.Z = Z; e.zh = T.heads;
+    e.out16 = o.p; e.ld16 = o.ld; e.c_sb = (long)Nq * o.ld; e.c_sh = T.dp;
+    S2I_TRY(gemm_launch(e, st_));
+    return 0;
+}
+
+int UNet::attention_bwd(const Transformer& T, const H16& dO, const H16& q, long q_c0, const H16& kv, long k_c0,
+                        long v_c0, int Nk, const H16& P, H16& dq, long dq_c0, H16* dkv, long dk_c0, long dv_c0) {
+    const int B = q.B, Nq = q.H * q.W, Z = B * T.heads;
+    const long ldS = rup(Nk, 4), ldP = P.ld;
+    float* dP = dalloc<float>((size_t)Z * Nq * ldS);
+    __half* dS = dalloc<__half>((size_t)Z * Nq * ldP);
+    if (dry_) return 0;
+    const float scale = 1.f / sqrtf((float)T.d);
+    {   // dP = dO V^T
+        GemmDesc d;
+        d.A = dO.p; d.aC = (int)dO.ld; d.aW = Nq; d.aB = B; d.a_sw = dO.ld; d.a_sb = (long)Nq * dO.ld; d.a_hoff = T.dp;
+        d.B = kv.p; d.bI = (int)kv.ld; d.bR = Nk; d.bZ = B; d.b_sr = kv.ld; d.b_sz = (long)Nk * kv.ld;
+        d.b_c0 = (int)v_c0; d.b_hoff = T.dp;
+        d.N = Nk; d.Kc = T.dp; d.Z = Z; d.zh = T.heads;
+        d.out32 = dP; d.ld32 = ldS; d.c_sb = (long)T.heads * Nq * ldS; d.c_sh = (long)Nq * ldS;
+        S2I_TRY(gemm_launch(d, st_));
+    }
+    S2I_TRY(softmax_bwd(P.p, ldP, dP, ldS, (long)Z * Nq, Nk, scale, dS, ldP, st_));
+    {   // dQ = dS K
+        GemmDesc d;
+        d.A = dS; d.aC = Nk; d.aW = Nq; d.aB = Z; d.a_sw = ldP; d.a_sb = (long)Nq * ldP; d.a_zmode = 1;
+        d.B = kv.p; d.b_mn = 1; d.bI = (int)kv.ld; d.bR = Nk; d.bZ = B; d.b_sr = kv.ld; d.b_sz = (long)Nk * kv.ld;
+        d.b_c0 = (int)k_c0; d.b_hoff = T.dp;
+        d.N = T.dp; d.BN = T.dp; d.Kc = Nk; d.Z = Z; d.zh = T.heads;
+        d.out16 = dq.p + dq_c0; d.ld16 = dq.ld; d.c_sb = (long)Nq * dq.ld; d.c_sh = T.dp;
+        S2I_TRY(gemm_launch(d, st_));
+    }
+    if (dkv) {
+        {   // dV = P^T dO
+            GemmDesc d;
+            d.A = P.p; d.a_mn = 1; d.aC = Nk; d.aW = Nq; d.aB = Z; d.a_sw = ldP; d.a_sb = (long)Nq * ldP; d.a_zmode = 1;
+            d.B = dO.p; d.b_mn = 1; d.bI = (int)dO.ld; d.bR = Nq; d.bZ = B; d.b_sr = dO.ld; d.b_sz = (long)Nq * dO.ld;
+            d.b_hoff = T.dp;
+            d.N = T.dp; d.BN = T.dp; d.Kc = Nq; d.Z = Z; d.zh = T.heads;
+            d.out16 = dkv->p + dv_c0; d.ld16 = dkv->ld; d.c_sb = (long)Nk * dkv->ld; d.c_sh = T.dp;
+            S2I_TRY(gemm_launch(d, st_));
+        }
+        {   // dK = dS^T Q
+            GemmDesc d;
+            d.A = dS; d.a_mn = 1; d.aC = Nk; d.aW = Nq; d.aB = Z; d.a_sw = ldP; d.a_sb = (long)Nq * ldP; d.a_zmode = 1;
+            d.B = q.p; d.b_mn = 1; d.bI = (int)q.ld; d.bR = Nq; d.bZ = B; d.b_sr = q.ld; d.b_sz = (long)Nq * q.ld;
+            d.b_c0 = (int)q_c0; d.b_hoff = T.dp;
+            d.N = T.dp; d.BN = T.dp; d.Kc = Nq; d.Z = Z; d.zh = T.heads;
+            d.out16 = dkv->p + dk_c0; d.ld16 = dkv->ld; d.c_sb = (long)Nk * dkv->ld; d.c_sh = T.dp;
+            S2I_TRY(gemm_launch(d, st_));
+        }
+    }
+    return 0;
+}
+
+// ================================================================================================== Transformer2D
+int UNet::transformer(int idx, const F32& x, F32& out) {
+    const Transformer& T = tfm_[idx];
+    const int B = x.B, H = x.H, W = x.W, HW = H * W, C = T.C;
+    const long rows = x.rows();
+    TfmSave sv;
+    sv.x = x;
+    sv.gs = new_stats();
+    RUN(gn_stats(x.p, x.ld, B, HW, C, sv.gs, st_));
+    H16 n16 = new16(B, H, W, C);
+    RUN(gn_apply(x.p, x.ld, B, HW, C, sv.gs, T.gn.g, T.gn.b, T.gn.eps, 0, n16.p, n16.ld, nullptr, 0, st_));
+    sv.t0 = new32(B, H, W, C);
+    S2I_TRY(gemm(n16, false, 1, T.proj_in.w, C, C, C, T.proj_in.b, nullptr, nullptr, &sv.t0, nullptr));
+    // --- self attention
+    H16 l16 = new16(B, H, W, C);
+    sv.l1 = dalloc<float>(rows * 2);
+    RUN(ln_fwd(sv.t0.p, sv.t0.ld, rows, C, T.ln1.g, T.ln1.b, T.ln1.eps, l16.p, l16.ld, sv.l1, st_));
+    sv.qkv = new16(B, H, W, 3 * T.HP);
+    S2I_TRY(gemm(l16, false, 1, T.qkv.w, C, 3 * T.HP, C, nullptr, nullptr, nullptr, nullptr, &sv.qkv));
+    H16 o1;
+    S2I_TRY(attention(T, sv.qkv, 0, sv.qkv, T.HP, 2L * T.HP, HW, sv.P1, o1));
+    sv.t1 = new32(B, H, W, C);
+    S2I_TRY(gemm(o1, false, 1, T.o1.w, T.HP, C, T.HP, T.o1.b, nullptr, &sv.t0, &sv.t1, nullptr));
+    // --- cross attention (K/V from the text context)
+    H16 l16b = new16(B, H, W, C);
+    sv.l2 = dalloc<float>(rows * 2);
+    RUN(ln_fwd(sv.t1.p, sv.t1.ld, rows, C, T.ln2.g, T.ln2.b, T.ln2.eps, l16b.p, l16b.ld, sv.l2, st_));
+    sv.q2 = new16(B, H, W, T.HP);
+    S2I_TRY(gemm(l16b, false, 1, T.q2.w, C, T.HP, C, nullptr, nullptr, nullptr, nullptr, &sv.q2));
+    sv.kv2 = new16(B, 1, cfg.ctx_len, 2 * T.HP);
+    S2I_TRY(gemm(ctx16_, false, 1, T.kv2.w, cfg.cross_dim, 2 * T.HP, cfg.cross_dim, nullptr, nullptr, nullptr, nullptr,
+                 &sv.kv2));
+    H16 o2;
+    S2I_TRY(attention(T, sv.q2, 0, sv.kv2, 0, T.HP, cfg.ctx_len, sv.P2, o2));
+    sv.t2 = new32(B, H, W, C);
+    S2I_TRY(gemm(o2, false, 1, T.o2.w, T.HP, C, T.HP, T.o2.b, nullptr, &sv.t1, &sv.t2, nullptr));
+    // --- GEGLU feed-forward
+    H16 l16c = new16(B, H, W, C);
+    sv.l3 = dalloc<float>(rows * 2);
+    RUN(ln_fwd(sv.t2.p, sv.t2.ld, rows, C, T.ln3.g, T.ln3.b, T.ln3.eps, l16c.p, l16c.ld, sv.l3, st_));
+    sv.ff = new32(B, H, W, 8 * C);
+    S2I_TRY(gemm(l16c, false, 1, T.ff1.w, C, 8 * C, C, T.ff1.b, nullptr, nullptr, &sv.ff, nullptr));
+    H16 g16 = new16(B, H, W, 4 * C);
+    RUN(geglu_fwd(sv.ff.p, sv.ff.ld, rows, 4 * C, g16.p, g16.ld, st_));
+    H16 t3 = new16(B, H, W, C);
+    S2I_TRY(gemm(g16, false, 1, T.ff2.w, 4 * C, C, 4 * C, T.ff2.b, nullptr, &sv.t2, nullptr, &t3));
+    out = new32(B, H, W, C);
+    S2I_TRY(gemm(t3, false, 1, T.proj_out.w, C, C, C, T.proj_out.b, nullptr, &x, &out, nullptr));
+    if (save_) tsave_[idx] = sv;
+    return 0;
+}
+
+int UNet::transformer_bwd(int idx, const F32& dout, F32& dx) {
+    const Transformer& T = tfm_[idx];
+    const TfmSave& S = tsave_[idx];
+    const int B = dout.B, H = dout.H, W = dout.W, HW = H * W, C = T.C;
+    const long rows = dout.rows();
+    H16 d16 = new16(B, H, W, C);
+    RUN(cast2d(dout.p, dout.ld, rows, C, 1.f, d16.p, d16.ld, st_));
+    F32 dt3 = new32(B, H, W, C);
+    H16 dt3h = new16(B, H, W, C);
+    S2I_TRY(gemm(d16, false, 1, T.proj_out.wd, C, C, C, nullptr, nullptr, nullptr, &dt3, &dt3h));
+    // feed-forward
+    F32 dg = new32(B, H, W, 4 * C);
+    S2I_TRY(gemm(dt3h, false, 1, T.ff2.wd, C, 4 * C, C, nullptr, nullptr, nullptr, &dg, nullptr));
+    H16 dff = new16(B, H, W, 8 * C);
+    RUN(geglu_bwd(dg.p, dg.ld, S.ff.p, S.ff.ld, rows, 4 * C, dff.p, dff.ld, st_));
+    F32 dl3 = new32(B, H, W, C);
+    S2I_TRY(gemm(dff, false, 1, T.ff1.wd, 8 * C, C, 8 * C, nullptr, nullptr, nullptr, &dl3, nullptr));
+    F32 dt2 = new32(B, H, W, C);
+    H16 dt2h = new16(B, H, W, C);
+    RUN(ln_bwd(dl3.p, dl3.ld, S.t2.p, S.t2.ld, rows, C, T.ln3.g, S.l3, dt3.p, dt3.ld, dt2.p, dt2.ld, dt2h.p, dt2h.ld, st_));
+    // cross attention (only dQ: the text context needs no gradient)
+    H16 dO2 = new16(B, H, W, T.HP);
+    S2I_TRY(gemm(dt2h, false, 1, T.o2.wd, C, T.HP, C, nullptr, nullptr, nullptr, nullptr, &dO2));
+    H16 dq2 = new16(B, H, W, T.HP);
+    S2I_TRY(attention_bwd(T, dO2, S.q2, 0, S.kv2, 0, T.HP, cfg.ctx_len, S.P2, dq2, 0, nullptr, 0, 0));
+    F32 dl2 = new32(B, H, W, C);
+    S2I_TRY(gemm(dq2, false, 1, T.q2.wd, T.HP, C, T.HP, nullptr, nullptr, nullptr, &dl2, nullptr));
+    F32 dt1 = new32(B, H, W, C);
+    H16 dt1h = new16(B, H, W, C);
+    RUN(ln_bwd(dl2.p, dl2.ld, S.t1.p, S.t1.ld, rows, C, T.ln2.g, S.l2, dt2.p, dt2.ld, dt1.p, dt1.ld, dt1h.p, dt1h.ld, st_));
+    // self attention
+    H16 dO1 = new16(B, H, W, T.HP);
+    S2I_TRY(gemm(dt1h, false, 1, T.o1.wd, C, T.HP, C, nullptr, nullptr, nullptr, nullptr, &dO1));
+    H16 dqkv = new16(B, H, W, 3 * T.HP);
+    S2I_TRY(attention_bwd(T, dO1, S.qkv, 0, S.qkv, T.HP, 2L * T.HP, HW, S.P1, dqkv, 0, &dqkv, T.HP, 2L * T.HP));
+    F32 dl1 = new32(B, H, W, C);
+    S2I_TRY(gemm(dqkv, false, 1, T.qkv.wd, 3 * T.HP, C, 3 * T.HP, nullptr, nullptr, nullptr, &dl1, nullptr));
+    H16 dt0h = new16(B, H, W, C);
+    RUN(ln_bwd(dl1.p, dl1.ld, S.t0.p, S.t0.ld, rows, C, T.ln1.g, S.l1, dt1.p, dt1.ld, nullptr, 0, dt0h.p, dt0h.ld, st_));
+    F32 dn = new32(B, H, W, C);
+    S2I_TRY(gemm(dt0h, false, 1, T.proj_in.wd, C, C, C, nullptr, nullptr, nullptr, &dn, nullptr));
+    double* bs = new_stats();
+    RUN(gn_bwd_stats(dn.p, dn.ld, S.x.p, S.x.ld, B, HW, C, S.gs, T.gn.g, T.gn.b, T.gn.eps, 0, bs, st_));
+    dx = new32(B, H, W, C);
+    RUN(gn_bwd_apply(dn.p, dn.ld, S.x.p, S.x.ld, B, HW, C, S.gs, bs, T.gn.g, T.gn.b, T.gn.eps, 0, dout.p, dout.ld, dx.p,
+                     dx.ld, nullptr, 0, st_));
+    return 0;
+}
+
+// ================================================================================================== whole network
+static const int kStatsSlots = 192;
+
+int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
+    const int B = B_, H = H_, W = W_;
+    const int* boc = cfg.boc;
+    arena_.reset();
+    stats_off_ = 0;
+    stats_cap_ = (size_t)kStatsSlots * B * kGroups * 2;
+    stats_ = dalloc<double>(stats_cap_);
+    if (!dry_) S2I_CUDA(cudaMemsetAsync(stats_, 0, stats_cap_ * sizeof(double), st_));
+    debug.clear();
+
+    // time embedding -> fused per-resnet projections
+    const int temb_dim = boc[0] * 4;
+    float* e0 = dalloc<float>(boc[0]);
+    float* e1 = dalloc<float>(temb_dim);
+    float* e2 = dalloc<float>(temb_dim);
+    temb_ = dalloc<float>(temb_all_.N);
+    RUN(timestep_embedding(t, boc[0], e0, st_));
+    RUN(gemv(e0, boc[0], time1_.w, time1_.b, temb_dim, 0, e1, st_));
+    RUN(gemv(e1, temb_dim, time2_.w, time2_.b, temb_dim, 1, e2, st_));
+    RUN(gemv(e2, temb_dim, temb_all_.w, temb_all_.b, temb_all_.N, 1, temb_, st_));
+
+    // text context as fp16 GEMM operand
+    ctx16_ = new16(B, 1, cfg.ctx_len, cfg.cross_dim);
+    RUN(cast2d(ctx_, cfg.cross_dim, (long)B * cfg.ctx_len, cfg.cross_dim, 1.f, ctx16_.p, ctx16_.ld, st_));
+
+    // conv_in (im2col GEMM, K = 9*in_ch padded to 64)
+    F32 x = new32(B, H, W, cfg.in_ch);
+    RUN(nchw_to_nhwc(x_nchw, B, cfg.in_ch, H, W, x.p, x.ld, st_));
+    H16 col = new16(B, H, W, 64);
+    RUN(im2col3x3(x.p, x.ld, B, H, W, cfg.in_ch, 1, col.p, col.ld, st_));
+    F32 h = new32(B, H, W, boc[0]);
+    S2I_TRY(gemm(col, false, 1, conv_in_.w, 64, boc[0], 64, conv_in_.b, nullptr, nullptr, &h, nullptr));
+    if (keep_debug) debug["conv_in"] = h;
+
+    skips_.clear();
+    skips_.push_back(h);
+    int ri = 0, ti = 0;
+    // ---- down
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < cfg.layers; ++j) {
+            F32 o;
+            S2I_TRY(resblock(ri++, h, o));
+            h = o;
+            if (i < 3) {
+                S2I_TRY(transformer(ti++, h, o));
+                h = o;
+            }
+            skips_.push_back(h);
+        }
+        if (i < 3) {
+            const int Ho = h.H / 2, Wo = h.W / 2, C = h.C;
+            H16 c2 = new16(B, Ho, Wo, 9 * C);
+            RUN(im2col3x3(h.p, h.ld, B, h.H, h.W, C, 2, c2.p, c2.ld, st_));
+            F32 o = new32(B, Ho, Wo, C);
+            S2I_TRY(gemm(c2, false, 1, down_[i].w, 9L * C, C, 9 * C, down_[i].b, nullptr, nullptr, &o, nullptr));
+            h = o;
+            skips_.push_back(h);
+            taps[i] = h;
+        }
+        if (keep_debug) debug["down" + std::to_string(i)] = h;
+    }
+    // ---- mid
+    {
+        F32 o;
+        S2I_TRY(resblock(ri++, h, o));
+        h = o;
+        taps[4] = h;
+        S2I_TRY(transformer(ti++, h, o));
+        h = o;
+        taps[3] = h;
+        S2I_TRY(resblock(ri++, h, o));
+        h = o;
+        taps[5] = h;
+        if (keep_debug) debug["mid"] = h;
+    }
+    // ---- up
+    int sp = (int)skips_.size();
+    up_cat_.clear();
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < cfg.layers + 1; ++j) {
+            const F32& sk = skips_[--sp];
+            F32 cat = new32(B, h.H, h.W, h.C + sk.C);
+            RUN(add2d(h.p, h.ld, nullptr, 0, h.rows(), h.C, cat.p, cat.ld, nullptr, 0, st_));
+            RUN(add2d(sk.p, sk.ld, nullptr, 0, sk.rows(), sk.C, cat.p + h.C, cat.ld, nullptr, 0, st_));
+            up_cat_.push_back({h.C, sp});
+            F32 o;
+            S2I_TRY(resblock(ri++, cat, o));
+            h = o;
+            if (i > 0) {
+                S2I_TRY(transformer(ti++, h, o));
+                h = o;
+            }
+        }
+        if (i < 3) {
+            H16 u = new16(B, 2 * h.H, 2 * h.W, h.C);
+            RUN(upsample2x(h.p, h.ld, B, h.H, h.W, h.C, u.p, u.ld, st_));
+            F32 o = new32(B, 2 * h.H, 2 * h.W, h.C);
+            S2I_TRY(gemm(u, true, 9, up_[i].w, 9L * h.C, h.C, h.C, up_[i].b, nullptr, nullptr, &o, nullptr));
+            h = o;
+            taps[6 + i] = h;
+        }
+        if (keep_debug) debug["up" + std::to_string(i)] = h;
+    }
+    // ---- out
+    double* so = new_stats();
+    RUN(gn_stats(h.p, h.ld, B, H * W, boc[0], so, st_));
+    H16 a = new16(B, H, W, boc[0]);
+    RUN(gn_apply(h.p, h.ld, B, H * W, boc[0], so, norm_out_.g, norm_out_.b, norm_out_.eps, 1, a.p, a.ld, nullptr, 0, st_));
+    F32 eps = new32(B, H, W, cfg.out_ch);
+    S2I_TRY(gemm(a, true, 9, conv_out_.w, 9L * boc[0], cfg.out_ch, boc[0], conv_out_.b, nullptr, nullptr, &eps, nullptr));
+    RUN(nhwc_to_nchw(eps.p, eps.ld, B, cfg.out_ch, H, W, eps_nchw, st_));
+    if (stats_off_ > stats_cap_) return set_error(S2I_ERR_STATE, "GroupNorm statistics arena overflow");
+    return 0;
+}
+
+int UNet::run_backward(float* const tap_grads[9], float* dx_nchw) {
+    const int B = B_;
+    const size_t bstat_cap = (size_t)kStatsSlots * B * kGroups * 2;
+    double* save_stats = stats_;
+    size_t save_off = stats_off_;
+    stats_ = dalloc<double>(bstat_cap);
+    stats_off_ = 0;
+    if (!dry_) S2I_CUDA(cudaMemsetAsync(stats_, 0, bstat_cap * sizeof(double), st_));
+
+    auto tapg = [&](int k) {
+        F32 g = taps[k];
+        g.p = tap_grads ? tap_grads[k] : nullptr;
+        if (dry_) g.p = reinterpret_cast<float*>(256);
+        g.ld = g.C;
+        return g;
+    };
+    std::vector<F32> dskip(skips_.size());
+    F32 d;
+    const int nres = (int)res_.size(), ntf = (int)tfm_.size();
+    // forward order: res: down (8), mid (2), up (12); tfm: down (6), mid (1), up (9)
+    int ri = nres - (cfg.layers + 1);   // first resnet of up block 3 (off the backward path)
+    int ti = ntf - (cfg.layers + 1);
+    int ci = (int)up_cat_.size() - (cfg.layers + 1);
+    for (int i = 2; i >= 0; --i) {
+        S2I_TRY(accumulate(d, tapg(6 + i)));
+        {   // upsampler backward: conv dgrad then 2x2 sum-pool
+            H16 d16 = new16(B, d.H, d.W, d.C);
+            RUN(cast2d(d.p, d.ld, d.rows(), d.C, 1.f, d16.p, d16.ld, st_));
+            F32 du = new32(B, d.H, d.W, d.C);
+            S2I_TRY(gemm(d16, true, 9, up_[i].wd, 9L * d.C, d.C, d.C, nullptr, nullptr, nullptr, &du, nullptr));
+            F32 dn = new32(B, d.H / 2, d.W / 2, d.C);
+            RUN(sumpool2x(du.p, du.ld, B, dn.H, dn.W, dn.C, dn.p, dn.ld, st_));
+            d = dn;
+        }
+        for (int j = cfg.layers; j >= 0; --j) {
+            F32 o;
+            if (i > 0) {
+                S2I_TRY(transformer_bwd(--ti, d, o));
+                d = o;
+            }
+            S2I_TRY(resblock_bwd(--ri, d, o));
+            const UpCat& uc = up_cat_[--ci];
+            F32 dsk = o;
+            dsk.p = o.p + uc.ch;
+            dsk.C = o.C - uc.ch;
+            dskip[uc.skip] = dsk;
+            d = o;
+            d.C = uc.ch;
+        }
+    }
+    // mid
+    S2I_TRY(accumulate(d, tapg(5)));
+    {
+        F32 o;
+        S2I_TRY(resblock_bwd(--ri, d, o));
+        d = o;
+        S2I_TRY(accumulate(d, tapg(3)));
+        S2I_TRY(transformer_bwd(--ti, d, o));
+        d = o;
+        S2I_TRY(accumulate(d, tapg(4)));
+        S2I_TRY(resblock_bwd(--ri, d, o));
+        d = o;
+    }
+    // down
+    int sk = (int)skips_.size() - 1;
+    for (int i = 3; i >= 0; --i) {
+        if (i < 3) {
+            S2I_TRY(accumulate(d, dskip[sk--]));
+            S2I_TRY(accumulate(d, tapg(i)));
+            H16 z = new16(B, 2 * d.H, 2 * d.W, d.C);
+            RUN(zero_insert2x(d.p, d.ld, B, d.H, d.W, d.C, z.p, z.ld, st_));
+            F32 o = new32(B, 2 * d.H, 2 * d.W, d.C);
+            S2I_TRY(gemm(z, true, 9, down_[i].wd, 9L * d.C, d.C, d.C, nullptr, nullptr, nullptr, &o, nullptr));
+            d = o;
+        }
+        for (int j = cfg.layers - 1; j >= 0; --j) {
+            S2I_TRY(accumulate(d, dskip[sk--]));
+            F32 o;
+            if (i < 3) {
+                S2I_TRY(transformer_bwd(--ti, d, o));
+                d = o;
+            }
+            S2I_TRY(resblock_bwd(--ri, d, o));
+            d = o;
+        }
+    }
+    S2I_TRY(accumulate(d, dskip[0]));
+    // conv_in backward
+    H16 d16 = new16(B, d.H, d.W, d.C);
+    RUN(cast2d(d.p, d.ld, d.rows(), d.C, 1.f, d16.p, d16.ld, st_));
+    F32 dx = new32(B, d.H, d.W, cfg.in_ch);
+    S2I_TRY(gemm(d16, true, 9, conv_in_d_.wd, 9L * d.C, cfg.in_ch, d.C, nullptr, nullptr, nullptr, &dx, nullptr));
+    RUN(nhwc_to_nchw(dx.p, dx.ld, B, cfg.in_ch, d.H, d.W, dx_nchw, st_));
+    if (ri != 0 || ti != 0) return set_error(S2I_ERR_STATE, "backward walk out of sync (ri=%d ti=%d)", ri, ti);
+    if (stats_off_ > bstat_cap) return set_error(S2I_ERR_STATE, "GroupNorm backward statistics arena overflow");
+    stats_ = save_stats;
+    stats_off_ = save_off;
+    return 0;
+}
+
+int UNet::forward(const float* x_nchw, int B, int H, int W, float t, const float* ctx, float* eps_nchw,
+                  bool save_for_backward, cudaStream_t st) {
+    if (!loaded_) return set_error(S2I_ERR_STATE, "unet: weights not loaded");
+    if (H % 8 || W % 8) return set_error(S2I_ERR_ARG, "unet: latent H, W must be multiples of 8 (got %d x %d)", H, W);
+    st_ = st;
+    B_ = B; H_ = H; W_ = W;
+    ctx_ = ctx;
+    save_ = save_for_backward;
+    have_saved_ = false;
+    const long key = ((long)B << 40) ^ ((long)H << 24) ^ ((long)W << 8) ^ (save_ ? 1 : 0);
+    if (key != arena_key_) {
+        // measure the footprint of this configuration with a dry run, then (re)allocate
+        Arena real = arena_;
+        arena_ = Arena();
+        dry_ = true;
+        int rc = run_forward(nullptr, t, nullptr);
+        if (rc == 0 && save_) rc = run_backward(nullptr, nullptr);
+        dry_ = false;
+        const size_t need = arena_.peak + (64u << 20);
+        arena_ = real;
+        if (rc != 0) return rc;
+        if (need > arena_.cap) {
+            if (arena_.base) cudaFree(arena_.base);
+            arena_.base = nullptr;
+            arena_.cap = 0;
+            void* p = nullptr;
+            if (cudaMalloc(&p, need) != cudaSuccess) {
+                cudaGetLastError();
+                return set_error(S2I_ERR_OOM, "unet: cannot allocate %.1f GB activation arena", need / 1e9);
+            }
+            arena_.base = static_cast<char*>(p);
+            arena_.cap = need;
+        }
+        arena_key_ = key;
+    }
+    int rc = run_forward(x_nchw, t, eps_nchw);
+    if (rc == 0 && save_) have_saved_ = true;
+    return rc;
+}
+
+int UNet::backward(float* const tap_grads[9], float* dx_nchw, cudaStream_t st) {
+    if (!have_saved_) return set_error(S2I_ERR_STATE, "unet backward: no forward with save_for_backward precedes it");
+    st_ = st;
+    have_saved_ = false;
+    return run_backward(tap_grads, dx_nchw);
+}
+
+}  // namespace s2i

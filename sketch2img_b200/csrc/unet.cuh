@@ -156,6 +156,10 @@ class UNet {
     std::vector<ResSave> rsave_;
     std::vector<TfmSave> tsave_;
     std::vector<F32> skips_;
+    struct UpCat { int ch; int skip; };   // per up-path resnet: width of the `h` half of its concat input, skip index
+    std::vector<UpCat> up_cat_;
+    H16 ctx16_;
+    long arena_key_ = -1;
     bool have_saved_ = false;
 
     int run_forward(const float* x_nchw, float t, float* eps_nchw);
