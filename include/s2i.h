@@ -84,6 +84,58 @@ int s2i_unet_debug(s2i_unet* u, int enable);
 int s2i_unet_debug_get(s2i_unet* u, const char* name, float** ptr, long long* ld, int* B, int* H, int* W, int* C);
 long long s2i_unet_arena_bytes(s2i_unet* u);
 
+/* ---------------------------------------------------------------------------------------------
+ * Latent Guidance Predictor: replaces LatentEdgePredictor.forward (modules/latent_predictor.py:37-45), the
+ * resize + concat of the taps (modules/pipeline.py:145-151), the edge loss (:155-157) and the LGP part of
+ * autograd.grad (:159).  State-dict keys: layers.{0,3,6,9,12}.{weight,bias},
+ * layers.{2,5,8,11}.{weight,bias,running_mean,running_var}.  Batches hold (uncond, cond) pairs; BatchNorm
+ * statistics are per pair (train) or the running ones (eval).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct s2i_lgp s2i_lgp;
+
+int s2i_lgp_create(int input_dim, int output_dim, int num_pos_layers, s2i_lgp** out);
+void s2i_lgp_destroy(s2i_lgp* l);
+int s2i_lgp_load(s2i_lgp* l, int n, const char* const* names, const float* const* host_ptrs, const int* ndims,
+                 const long long* shapes);
+/* taps[k]: NHWC fp32 device [B][sizes[k]][sizes[k]][channels[k]]; noise: NCHW fp32 [B/2][4][L][L];
+ * the noise-level input is sigma * noise for both halves of a pair (modules/pipeline.py:152-153) */
+int s2i_lgp_forward_taps(s2i_lgp* l, const float* const* taps, const int* sizes, const int* channels, int B, int L,
+                         const float* noise, float sigma, int train, void* cuda_stream);
+/* x: NCHW fp32 [B][input_dim-4-4P][L][L] (already resized + concatenated), t: NCHW fp32 [B][4][L][L] */
+int s2i_lgp_forward_nchw(s2i_lgp* l, const float* x, const float* t, int B, int L, int train, void* cuda_stream);
+/* out_rows: fp32 device [(b w h)][output_dim] -- the reference's row order (latent_predictor.py:43) */
+int s2i_lgp_output(s2i_lgp* l, float* out_rows, void* cuda_stream);
+/* target: NCHW fp32 [B/2][output_dim][L][L]; tap_grads[k]: NHWC fp32 like tap k (scaled by *grad_scale);
+ * loss: device float [B/2] (MSE on the cond half, modules/pipeline.py:157) */
+int s2i_lgp_loss_backward(s2i_lgp* l, const float* target, float* const* tap_grads, float* loss, float* grad_scale,
+                          void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CFG combine + DDIM step (modules/pipeline.py:100-104; diffusers DDIMScheduler.step, eta = 0) and the
+ * norm-ratio guidance update (modules/pipeline.py:160-161).  eps / dx: [2S][n] ordered (uncond_s, cond_s).
+ * prediction: 0 = epsilon, 1 = v_prediction.
+ * --------------------------------------------------------------------------------------------- */
+int s2i_cfg_ddim_step(const float* latents, const float* eps, int S, int n, float guidance_scale, float sqrt_one_minus_a_t,
+                      float sqrt_a_t, float sqrt_a_prev, float sqrt_one_minus_a_prev, int prediction, float* out,
+                      void* cuda_stream);
+/* x_new += beta * ||[x_old,x_old] - x_new||_F / ||g||_F * g,  g = -dx[cond]; scratch: device double [S][2] */
+int s2i_guidance_update(const float* x_old, float* x_new, const float* dx, int S, int n, float beta, double* scratch,
+                        void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One whole denoising step on the device = the loop body of AntiGradientPipeline.__call__
+ * (modules/pipeline.py:83-115) for S independent samples (SURVEY Q1 batch semantics).
+ * latents [S][4][L][L] in/out; noise = the initial latents (:75); ctx [2S][ctx_len][D] ordered (uncond, cond);
+ * target [S][4][L][L] or NULL (guidance skipped, :142-143); sigma = sqrt(1 - alpha_bar_t) (:133).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct s2i_sampler s2i_sampler;
+int s2i_sampler_create(s2i_unet* u, s2i_lgp* l, s2i_sampler** out);
+void s2i_sampler_destroy(s2i_sampler* s);
+int s2i_sampler_step(s2i_sampler* s, float* latents, const float* noise, const float* ctx, const float* target, int S,
+                     int L, float t, float guidance_scale, float sqrt_a_t, float sqrt_one_minus_a_t, float sqrt_a_prev,
+                     float sqrt_one_minus_a_prev, int prediction, int guided, float sigma, float beta, int lgp_train,
+                     float* loss_out, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,22 @@ def lib():
     h.s2i_unet_debug_get.argtypes = [vp, C.c_char_p, fp, C.POINTER(C.c_longlong), ip, ip, ip, ip]
     h.s2i_unet_arena_bytes.argtypes = [vp]
     h.s2i_unet_arena_bytes.restype = C.c_longlong
+    ll, f = C.POINTER(C.c_longlong), C.c_float
+    h.s2i_lgp_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    h.s2i_lgp_destroy.argtypes = [vp]
+    h.s2i_lgp_destroy.restype = None
+    h.s2i_lgp_load.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(vp), ip, ll]
+    h.s2i_lgp_forward_taps.argtypes = [vp, C.POINTER(vp), ip, ip, C.c_int, C.c_int, vp, f, C.c_int, vp]
+    h.s2i_lgp_forward_nchw.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    h.s2i_lgp_output.argtypes = [vp, vp, vp]
+    h.s2i_lgp_loss_backward.argtypes = [vp, vp, C.POINTER(vp), vp, C.POINTER(f), vp]
+    h.s2i_cfg_ddim_step.argtypes = [vp, vp, C.c_int, C.c_int, f, f, f, f, f, C.c_int, vp, vp]
+    h.s2i_guidance_update.argtypes = [vp, vp, vp, C.c_int, C.c_int, f, vp, vp]
+    h.s2i_sampler_create.argtypes = [vp, vp, C.POINTER(vp)]
+    h.s2i_sampler_destroy.argtypes = [vp]
+    h.s2i_sampler_destroy.restype = None
+    h.s2i_sampler_step.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, f, f, f, f, f, f, C.c_int, C.c_int, f, f,
+                                   C.c_int, vp, vp]
     _lib = h
     return h
 

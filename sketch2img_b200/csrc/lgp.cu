@@ -1,0 +1,691 @@
+// Latent Guidance Predictor engine + scheduler/guidance-update kernels.  See lgp.cuh.
+#include "lgp.cuh"
+
+#include <cmath>
+
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace s2i {
+
+int pack_linear_host(const float* host, int N, int K, __half* w, long w_ld, __half* wd, long wd_ld);   // unet.cu
+
+namespace {
+
+constexpr float kBnEps = 1e-5f;
+constexpr float kTwoPi = 6.2831855f;   // float(2 * math.pi), as torch promotes the python scalar
+
+struct TapTable {
+    const float* p[9];
+    int S[9], C[9], off[10];
+};
+
+__device__ __forceinline__ void src_index(int dst, float scale, int S, int& i0, int& i1, float& l1) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;      // align_corners=False
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    if (i0 > S - 1) i0 = S - 1;
+    i1 = i0 + (i0 < S - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+}
+
+// X[(b,h,w)][col] = fp16( bilinear(tap_k)[b][:, h, w] | sigma*noise | sin(2 pi lvl 2^-l) ), zero padded to ldX
+__global__ void __launch_bounds__(256) lgp_features_kernel(TapTable tt, int B, int L, const float* __restrict__ noise,
+                                                           float sigma, int P, int D, __half* __restrict__ X,
+                                                           long ldX) {
+    const int chunks = (int)(ldX >> 3);
+    const long total = (long)B * L * L * chunks;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long row = idx / chunks;
+        const int col = (int)(idx - row * chunks) << 3;
+        const int w = (int)(row % L), h = (int)((row / L) % L), b = (int)(row / ((long)L * L));
+        float v[8];
+        if (col < tt.off[9]) {
+            int k = 0;
+            while (col >= tt.off[k + 1]) ++k;
+            const int S = tt.S[k], C = tt.C[k], c = col - tt.off[k];
+            const float* base = tt.p[k] + (long)b * S * S * C + c;
+            if (S == L) {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(base + ((long)h * S + w) * C));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(base + ((long)h * S + w) * C + 4));
+                v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+            } else {
+                const float scale = (float)S / (float)L;
+                int y0, y1, x0, x1;
+                float ly, lx;
+                src_index(h, scale, S, y0, y1, ly);
+                src_index(w, scale, S, x0, x1, lx);
+                const float hy = 1.f - ly, hx = 1.f - lx;
+                const float* p00 = base + ((long)y0 * S + x0) * C;
+                const float* p01 = base + ((long)y0 * S + x1) * C;
+                const float* p10 = base + ((long)y1 * S + x0) * C;
+                const float* p11 = base + ((long)y1 * S + x1) * C;
+#pragma unroll
+                for (int j = 0; j < 8; j += 4) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(p00 + j));
+                    const float4 bq = __ldg(reinterpret_cast<const float4*>(p01 + j));
+                    const float4 cq = __ldg(reinterpret_cast<const float4*>(p10 + j));
+                    const float4 dq = __ldg(reinterpret_cast<const float4*>(p11 + j));
+                    v[j + 0] = __fadd_rn(__fmul_rn(hy, __fadd_rn(__fmul_rn(hx, a.x), __fmul_rn(lx, bq.x))),
+                                         __fmul_rn(ly, __fadd_rn(__fmul_rn(hx, cq.x), __fmul_rn(lx, dq.x))));
+                    v[j + 1] = __fadd_rn(__fmul_rn(hy, __fadd_rn(__fmul_rn(hx, a.y), __fmul_rn(lx, bq.y))),
+                                         __fmul_rn(ly, __fadd_rn(__fmul_rn(hx, cq.y), __fmul_rn(lx, dq.y))));
+                    v[j + 2] = __fadd_rn(__fmul_rn(hy, __fadd_rn(__fmul_rn(hx, a.z), __fmul_rn(lx, bq.z))),
+                                         __fmul_rn(ly, __fadd_rn(__fmul_rn(hx, cq.z), __fmul_rn(lx, dq.z))));
+                    v[j + 3] = __fadd_rn(__fmul_rn(hy, __fadd_rn(__fmul_rn(hx, a.w), __fmul_rn(lx, bq.w))),
+                                         __fmul_rn(ly, __fadd_rn(__fmul_rn(hx, cq.w), __fmul_rn(lx, dq.w))));
+                }
+            }
+        } else {
+            const int s = b >> 1;     // both CFG halves share the sample's noise level
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int cc = col + j - tt.off[9];
+                float val = 0.f;
+                if (col + j < D) {
+                    const int ch = cc & 3;
+                    const float lvl = __fmul_rn(sigma, noise[(((long)s * 4 + ch) * L + h) * L + w]);
+                    if (cc < 4) {
+                        val = lvl;
+                    } else {
+                        const int l = (cc - 4) >> 2;
+                        val = sinf(__fmul_rn(__fmul_rn(kTwoPi, lvl), exp2f(-(float)l)));
+                    }
+                }
+                v[j] = val;
+            }
+        }
+        uint4 o;
+        __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+        __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(X + row * ldX + col) = o;
+    }
+}
+
+// features from concatenated NCHW x [B][Cx][L][L] and t [B][4][L][L]  (LatentEdgePredictor.forward surface)
+__global__ void __launch_bounds__(256) lgp_features_nchw_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                                int B, int L, int Cx, int P, int D,
+                                                                __half* __restrict__ X, long ldX) {
+    const long total = (long)B * L * L * ldX;
+    const long hw = (long)L * L;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long row = idx / ldX;
+        const int col = (int)(idx - row * ldX);
+        const long b = row / hw, pix = row - b * hw;
+        float val = 0.f;
+        if (col < Cx) {
+            val = x[(b * Cx + col) * hw + pix];
+        } else if (col < D) {
+            const int cc = col - Cx, ch = cc & 3;
+            const float lvl = t[(b * 4 + ch) * hw + pix];
+            val = cc < 4 ? lvl : sinf(__fmul_rn(__fmul_rn(kTwoPi, lvl), exp2f(-(float)((cc - 4) >> 2))));
+        }
+        X[idx] = __float2half_rn(val);
+    }
+}
+
+// per (sample, column) sums over R rows.  MODE 0: (h, h^2).  MODE 1: (dy, dy*xhat).
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const __half* __restrict__ h, const __half* __restrict__ dy,
+                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                        long R, int N, int chunk, double* __restrict__ out) {
+    const int s = blockIdx.y;
+    const long r0 = (long)blockIdx.x * chunk;
+    const long r1 = min(R, r0 + chunk);
+    for (int c = threadIdx.x * 2; c < N; c += blockDim.x * 2) {
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+        float m0 = 0.f, m1 = 0.f, q0 = 0.f, q1 = 0.f;
+        if (MODE == 1) {
+            m0 = mean[(long)s * N + c]; m1 = mean[(long)s * N + c + 1];
+            q0 = rstd[(long)s * N + c]; q1 = rstd[(long)s * N + c + 1];
+        }
+        for (long r = r0; r < r1; ++r) {
+            const long row = (long)s * R + r;
+            const float2 hv = __half22float2(*reinterpret_cast<const __half2*>(h + row * N + c));
+            if (MODE == 0) {
+                a0 += hv.x; a1 += hv.y;
+                b0 += hv.x * hv.x; b1 += hv.y * hv.y;
+            } else {
+                const float2 dv = __half22float2(*reinterpret_cast<const __half2*>(dy + row * N + c));
+                a0 += dv.x; a1 += dv.y;
+                b0 += dv.x * (hv.x - m0) * q0; b1 += dv.y * (hv.y - m1) * q1;
+            }
+        }
+        double* o = out + ((long)s * N + c) * 2;
+        atomicAdd(o + 0, (double)a0);
+        atomicAdd(o + 1, (double)b0);
+        atomicAdd(o + 2, (double)a1);
+        atomicAdd(o + 3, (double)b1);
+    }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ rm,
+                                   const float* __restrict__ rv, int train, long R, int N, int S, float* __restrict__ mean,
+                                   float* __restrict__ rstd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S * N) return;
+    const int c = i % N;
+    if (train) {
+        const double m = sums[2L * i] / (double)R;
+        double var = sums[2L * i + 1] / (double)R - m * m;
+        if (var < 0.0) var = 0.0;
+        mean[i] = (float)m;
+        rstd[i] = (float)(1.0 / sqrt(var + (double)kBnEps));
+    } else {
+        mean[i] = rm[c];
+        rstd[i] = rsqrtf(rv[c] + kBnEps);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __half* __restrict__ h, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, long R, int N, long rows,
+                                                       __half* __restrict__ out) {
+    const long total = rows * (N >> 1);
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long row = idx / (N >> 1);
+        const int c = (int)(idx - row * (N >> 1)) << 1;
+        const long s = row / R;
+        const float2 hv = __half22float2(*reinterpret_cast<const __half2*>(h + row * N + c));
+        const float y0 = (hv.x - mean[s * N + c]) * rstd[s * N + c] * gamma[c] + beta[c];
+        const float y1 = (hv.y - mean[s * N + c + 1]) * rstd[s * N + c + 1] * gamma[c + 1] + beta[c + 1];
+        *reinterpret_cast<__half2*>(out + row * N + c) = __floats2half2_rn(y0, y1);
+    }
+}
+
+// dprev = relu_mask(h) * q( gamma*rstd*(dy - m1 - xhat*m2) ), q = fp16 rounding in unscaled units
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half* __restrict__ h,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ gamma,
+                                                           const double* __restrict__ bsums, int train, long R, int N,
+                                                           long rows, float qscale, __half* __restrict__ out) {
+    const long total = rows * (N >> 1);
+    const float qinv = 1.f / qscale;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long row = idx / (N >> 1);
+        const int c = (int)(idx - row * (N >> 1)) << 1;
+        const long s = row / R;
+        const float2 hv = __half22float2(*reinterpret_cast<const __half2*>(h + row * N + c));
+        const float2 dv = __half22float2(*reinterpret_cast<const __half2*>(dy + row * N + c));
+        float o[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const long sc = s * N + c + j;
+            const float hh = j ? hv.y : hv.x, dd = j ? dv.y : dv.x;
+            float g;
+            if (train) {
+                const float m1 = (float)(bsums[2 * sc] / (double)R), m2 = (float)(bsums[2 * sc + 1] / (double)R);
+                const float xh = (hh - mean[sc]) * rstd[sc];
+                g = gamma[c + j] * rstd[sc] * (dd - m1 - xh * m2);
+            } else {
+                g = gamma[c + j] * rstd[sc] * dd;
+            }
+            g = __half2float(__float2half_rn(g * qinv)) * qscale;
+            o[j] = hh > 0.f ? g : 0.f;
+        }
+        *reinterpret_cast<__half2*>(out + row * N + c) = __floats2half2_rn(o[0], o[1]);
+    }
+}
+
+// dOut (scaled, fp16-rounded in true units) of the MSE edge loss on the cond half; loss[s] accumulated.
+__global__ void __launch_bounds__(256) lgp_loss_kernel(const __half* __restrict__ out16, const float* __restrict__ target,
+                                                       int B, int L, int O, float inv_n, float gscale,
+                                                       __half* __restrict__ dout, float* __restrict__ loss) {
+    const long rows = (long)B * L * L;
+    const long hw = (long)L * L;
+    for (long row = (long)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (long)gridDim.x * blockDim.x) {
+        const long b = row / hw, pix = row - b * hw;
+        __align__(16) __half d8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d8[j] = __float2half_rn(0.f);
+        if (b & 1) {
+            const long s = b >> 1;
+            float acc = 0.f;
+            for (int c = 0; c < O; ++c) {
+                const float diff = __half2float(out16[row * 8 + c]) - target[(s * O + c) * hw + pix];
+                acc += diff * diff;
+                const float g = __half2float(__float2half_rn(2.f * diff * inv_n));   // unscaled fp16 rounding
+                d8[c] = __float2half_rn(g * gscale);
+            }
+            atomicAdd(loss + s, acc * inv_n);
+        }
+        *reinterpret_cast<uint4*>(dout + row * 8) = *reinterpret_cast<uint4*>(d8);
+    }
+}
+
+// tap_grad[b][y][x][c] = sum_{h,w} wy(h,y) wx(w,x) dX[(b,h,w)][off + c]   (adjoint of the bilinear resize)
+__global__ void __launch_bounds__(256) interp_bwd_kernel(const __half* __restrict__ dX, long ldX, int off, int B, int L,
+                                                         int S, int C, float* __restrict__ g) {
+    const int chunks = C >> 3;
+    const long total = (long)B * S * S * chunks;
+    const float scale = (float)S / (float)L, f = (float)L / (float)S;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long pix = idx / chunks;
+        const int c = (int)(idx - pix * chunks) << 3;
+        const int x = (int)(pix % S), y = (int)((pix / S) % S), b = (int)(pix / ((long)S * S));
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int h_lo, h_hi, w_lo, w_hi;
+        if (S == L) {
+            h_lo = h_hi = y;
+            w_lo = w_hi = x;
+        } else {
+            h_lo = max(0, (int)floorf(f * ((float)y - 0.5f) - 0.5f));
+            h_hi = min(L - 1, (int)ceilf(f * ((float)y + 1.5f) - 0.5f));
+            w_lo = max(0, (int)floorf(f * ((float)x - 0.5f) - 0.5f));
+            w_hi = min(L - 1, (int)ceilf(f * ((float)x + 1.5f) - 0.5f));
+        }
+        for (int h = h_lo; h <= h_hi; ++h) {
+            float wy = 1.f;
+            if (S != L) {
+                int i0, i1;
+                float l1;
+                src_index(h, scale, S, i0, i1, l1);
+                wy = (i0 == y ? 1.f - l1 : 0.f) + (i1 == y ? l1 : 0.f);
+            }
+            if (wy == 0.f) continue;
+            for (int w = w_lo; w <= w_hi; ++w) {
+                float wx = 1.f;
+                if (S != L) {
+                    int i0, i1;
+                    float l1;
+                    src_index(w, scale, S, i0, i1, l1);
+                    wx = (i0 == x ? 1.f - l1 : 0.f) + (i1 == x ? l1 : 0.f);
+                }
+                if (wx == 0.f) continue;
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(dX + (((long)b * L + h) * L + w) * ldX + off + c));
+                const __half2* hp = reinterpret_cast<const __half2*>(&q);
+                const float ww = wy * wx;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 v = __half22float2(hp[j]);
+                    acc[2 * j] += ww * v.x;
+                    acc[2 * j + 1] += ww * v.y;
+                }
+            }
+        }
+        float* o = g + pix * C + c;
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
+
+__global__ void lgp_export_kernel(const __half* __restrict__ out16, int B, int L, int O, float* __restrict__ dst) {
+    const long total = (long)B * L * L * O;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % O);
+        const long r = idx / O;               // destination row in (b, w, h) order
+        const int h = (int)(r % L), w = (int)((r / L) % L), b = (int)(r / ((long)L * L));
+        dst[idx] = __half2float(out16[((((long)b * L + h) * L + w)) * 8 + c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ scheduler / update
+__global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eps, int S,
+                                                       int n, float g, float sb_t, float sa_t, float sa_p, float sb_p,
+                                                       int prediction, float* __restrict__ out) {
+    const long total = (long)S * n;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long s = idx / n, i = idx - s * n;
+        const float eu = eps[(2 * s) * (long)n + i], ec = eps[(2 * s + 1) * (long)n + i];
+        // no FMA contraction: each torch op rounds separately
+        float e = __fadd_rn(eu, __fmul_rn(g, __fsub_rn(ec, eu)));
+        const float xv = x[idx];
+        float x0;
+        if (prediction == 0) {
+            x0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(sb_t, e)), sa_t);
+        } else {
+            x0 = __fsub_rn(__fmul_rn(sa_t, xv), __fmul_rn(sb_t, e));
+            e = __fadd_rn(__fmul_rn(sa_t, e), __fmul_rn(sb_t, xv));
+        }
+        out[idx] = __fadd_rn(__fmul_rn(sa_p, x0), __fmul_rn(sb_p, e));
+    }
+}
+
+__global__ void __launch_bounds__(256) guidance_norms_kernel(const float* __restrict__ x_old,
+                                                             const float* __restrict__ x_new,
+                                                             const float* __restrict__ dx, int n,
+                                                             double* __restrict__ scratch) {
+    const int s = blockIdx.y;
+    float a = 0.f, b = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float d = x_old[(long)s * n + i] - x_new[(long)s * n + i];
+        const float gq = dx[(2L * s + 1) * n + i];
+        a += d * d;
+        b += gq * gq;
+    }
+    __shared__ float sa[8], sb[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sa[threadIdx.x >> 5] = a;
+        sb[threadIdx.x >> 5] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ta = 0.f, tb = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+            ta += sa[i];
+            tb += sb[i];
+        }
+        atomicAdd(scratch + 2 * s, (double)ta);
+        atomicAdd(scratch + 2 * s + 1, (double)tb);
+    }
+}
+
+__global__ void __launch_bounds__(256) guidance_apply_kernel(float* __restrict__ x_new, const float* __restrict__ dx,
+                                                             int n, float beta, const double* __restrict__ scratch) {
+    const int s = blockIdx.y;
+    // ||x_in - latents|| runs over both CFG copies of x_in (pipeline.py:160): sqrt(2 * sum d^2)
+    const float num = (float)sqrt(2.0 * scratch[2 * s]);
+    const float den = (float)sqrt(scratch[2 * s + 1]);
+    const float alpha = num / den * beta;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float gq = -dx[(2L * s + 1) * n + i];
+        x_new[(long)s * n + i] = __fadd_rn(x_new[(long)s * n + i], __fmul_rn(alpha, gq));
+    }
+}
+
+inline int grid1d(long work, int block = 256, int cap = 148 * 16) {
+    long g = (work + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+}  // namespace
+
+// ================================================================================================== LGP
+LGP::LGP(int input_dim, int output_dim, int num_pos_layers) : D_(input_dim), O_(output_dim), P_(num_pos_layers) {
+    widths_[0] = input_dim;
+    widths_[1] = 512; widths_[2] = 256; widths_[3] = 128; widths_[4] = 64;
+    widths_[5] = output_dim;
+    ldX_ = (input_dim + 63) / 64 * 64;
+}
+
+LGP::~LGP() {
+    for (void* p : owned_) cudaFree(p);
+    if (buf_) cudaFree(buf_);
+}
+
+int LGP::load(const std::map<std::string, HostParam>& params) {
+    if (D_ % 8 != 0) return set_error(S2I_ERR_ARG, "lgp: input_dim must be a multiple of 8 (got %d)", D_);
+    if (O_ > 8) return set_error(S2I_ERR_ARG, "lgp: output_dim must be <= 8");
+    auto get = [&](const std::string& name, size_t n) -> const float* {
+        auto it = params.find(name);
+        if (it == params.end()) return nullptr;
+        size_t e = 1;
+        for (long s : it->second.shape) e *= (size_t)s;
+        return e == n ? it->second.data : nullptr;
+    };
+    auto dvec = [&](const float* host, size_t n) -> float* {
+        void* p = nullptr;
+        if (!host || cudaMalloc(&p, n * sizeof(float)) != cudaSuccess) return nullptr;
+        owned_.push_back(p);
+        cudaMemcpy(p, host, n * sizeof(float), cudaMemcpyHostToDevice);
+        return static_cast<float*>(p);
+    };
+    for (int l = 0; l < 5; ++l) {
+        const std::string pre = "layers." + std::to_string(3 * l);
+        const int K = widths_[l], N = widths_[l + 1];
+        const float* w = get(pre + ".weight", (size_t)N * K);
+        if (!w) return set_error(S2I_ERR_ARG, "lgp load: missing or mis-shaped %s.weight (expect [%d,%d])", pre.c_str(), N, K);
+        const long wd_ld = (N + 7) / 8 * 8;
+        void *pw = nullptr, *pwd = nullptr;
+        if (cudaMalloc(&pw, (size_t)N * K * 2) != cudaSuccess || cudaMalloc(&pwd, (size_t)K * wd_ld * 2) != cudaSuccess)
+            return set_error(S2I_ERR_OOM, "lgp load: cudaMalloc");
+        owned_.push_back(pw);
+        owned_.push_back(pwd);
+        cudaMemset(pwd, 0, (size_t)K * wd_ld * 2);
+        lin_[l].N = N;
+        lin_[l].K = K;
+        lin_[l].w = static_cast<__half*>(pw);
+        lin_[l].wd = static_cast<__half*>(pwd);
+        S2I_TRY(pack_linear_host(w, N, K, lin_[l].w, K, lin_[l].wd, wd_ld));
+        lin_[l].b = dvec(get(pre + ".bias", N), N);
+        if (!lin_[l].b) return set_error(S2I_ERR_ARG, "lgp load: missing %s.bias", pre.c_str());
+        if (l < 4) {
+            const std::string bp = "layers." + std::to_string(3 * l + 2);
+            bn_[l].C = N;
+            bn_[l].g = dvec(get(bp + ".weight", N), N);
+            bn_[l].b = dvec(get(bp + ".bias", N), N);
+            bn_rm_[l] = dvec(get(bp + ".running_mean", N), N);
+            bn_rv_[l] = dvec(get(bp + ".running_var", N), N);
+            if (!bn_[l].g || !bn_[l].b || !bn_rm_[l] || !bn_rv_[l])
+                return set_error(S2I_ERR_ARG, "lgp load: missing BatchNorm tensors under %s", bp.c_str());
+        }
+    }
+    loaded_ = true;
+    return 0;
+}
+
+int LGP::ensure(size_t bytes) {
+    if (bytes <= buf_cap_) return 0;
+    if (buf_) cudaFree(buf_);
+    buf_ = nullptr;
+    buf_cap_ = 0;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(S2I_ERR_OOM, "lgp: cannot allocate %.2f GB workspace", bytes / 1e9);
+    }
+    buf_ = static_cast<char*>(p);
+    buf_cap_ = bytes;
+    return 0;
+}
+
+// Workspace layout (bump): X | h0..h3 | a0..a3 | out16 | dOut | dbuf A/B | sums | mean/rstd
+struct LgpWs {
+    size_t off = 0;
+    char* base;
+    explicit LgpWs(char* b) : base(b) {}
+    template <class T>
+    T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* p = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+static size_t lgp_ws_bytes(long rows, long ldX, int S) {
+    size_t b = (size_t)rows * ldX * 2;
+    b += (size_t)rows * (512 + 256 + 128 + 64) * 2 * 2;
+    b += (size_t)rows * 8 * 2 * 2;
+    b += (size_t)rows * 512 * 2 * 2;
+    b += (size_t)S * 512 * 2 * 8 * 8 + (size_t)S * 512 * 4 * 8;
+    return b + (1u << 20);
+}
+
+int LGP::mlp(cudaStream_t st) {
+    const long rows = (long)B_ * L_ * L_;
+    const int S = groups_;
+    const long R = rows / groups_;
+    LgpWs ws(buf_);
+    X_ = ws.take<__half>((size_t)rows * ldX_);
+    for (int l = 0; l < 4; ++l) h_[l] = ws.take<__half>((size_t)rows * widths_[l + 1]);
+    for (int l = 0; l < 4; ++l) a_[l] = ws.take<__half>((size_t)rows * widths_[l + 1]);
+    out16_ = ws.take<__half>((size_t)rows * 8);
+    dout_ = ws.take<__half>((size_t)rows * 8);
+    dA_ = ws.take<__half>((size_t)rows * 512);
+    dB_ = ws.take<__half>((size_t)rows * 512);
+    double* sums = ws.take<double>((size_t)S * 960 * 2 * 2);
+    S2I_CUDA(cudaMemsetAsync(sums, 0, (size_t)S * 960 * 2 * 2 * sizeof(double), st));
+    size_t so = 0;
+    for (int l = 0; l < 4; ++l) {
+        bsum_[l] = sums + so;
+        so += (size_t)S * widths_[l + 1] * 2;
+    }
+    for (int l = 0; l < 4; ++l) {
+        bbsum_[l] = sums + so;
+        so += (size_t)S * widths_[l + 1] * 2;
+    }
+    for (int l = 0; l < 4; ++l) {
+        mean_[l] = ws.take<float>((size_t)S * widths_[l + 1]);
+        rstd_[l] = ws.take<float>((size_t)S * widths_[l + 1]);
+    }
+    S2I_CUDA(cudaMemsetAsync(out16_, 0, (size_t)rows * 8 * 2, st));
+
+    for (int l = 0; l < 5; ++l) {
+        const int K = widths_[l], N = widths_[l + 1];
+        GemmDesc d;
+        d.A = l == 0 ? X_ : a_[l - 1];
+        d.aC = K; d.aW = (int)rows; d.a_sw = l == 0 ? ldX_ : K;
+        d.B = lin_[l].w; d.bI = K; d.bR = N; d.b_sr = K;
+        d.N = N; d.Kc = K;
+        d.bias = lin_[l].b;
+        if (l < 4) {
+            d.relu = 1;
+            d.out16 = h_[l]; d.ld16 = N;
+        } else {
+            d.out16 = out16_; d.ld16 = 8;
+        }
+        S2I_TRY(gemm_launch(d, st));
+        if (l < 4) {
+            if (train_) {
+                dim3 grid((unsigned)ceil_div_l(R, 128), S);
+                bn_reduce_kernel<0><<<grid, min(256, N / 2), 0, st>>>(h_[l], nullptr, nullptr, nullptr, R, N, 128, bsum_[l]);
+                S2I_LAUNCH_CHECK();
+            }
+            bn_finalize_kernel<<<ceil_div(S * N, 256), 256, 0, st>>>(bsum_[l], bn_rm_[l], bn_rv_[l], train_ ? 1 : 0, R, N, S,
+                                                                     mean_[l], rstd_[l]);
+            S2I_LAUNCH_CHECK();
+            bn_apply_kernel<<<grid1d(rows * (N / 2)), 256, 0, st>>>(h_[l], mean_[l], rstd_[l], bn_[l].g, bn_[l].b, R, N, rows,
+                                                                    a_[l]);
+            S2I_LAUNCH_CHECK();
+        }
+    }
+    have_fwd_ = true;
+    return 0;
+}
+
+int LGP::forward(const LgpTap taps[9], int B, int L, const float* noise, float sigma, bool train, cudaStream_t st) {
+    if (!loaded_) return set_error(S2I_ERR_STATE, "lgp: weights not loaded");
+    if (B % 2 != 0) return set_error(S2I_ERR_ARG, "lgp: batch must hold (uncond, cond) pairs");
+    TapTable tt;
+    int off = 0;
+    for (int k = 0; k < 9; ++k) {
+        taps_[k] = taps[k];
+        tt.p[k] = taps[k].p;
+        tt.S[k] = taps[k].S;
+        tt.C[k] = taps[k].C;
+        tt.off[k] = off;
+        if (taps[k].C % 8 != 0) return set_error(S2I_ERR_ARG, "lgp: tap channels must be multiples of 8");
+        off += taps[k].C;
+    }
+    tt.off[9] = off;
+    if (off + 4 + 4 * P_ != D_)
+        return set_error(S2I_ERR_ARG, "lgp: taps give %d channels (+%d) but input_dim is %d", off, 4 + 4 * P_, D_);
+    B_ = B; L_ = L; train_ = train;
+    const long rows = (long)B * L * L;
+    groups_ = B / 2;
+    S2I_TRY(ensure(lgp_ws_bytes(rows, ldX_, B / 2)));
+    X_ = reinterpret_cast<__half*>(buf_);   // first workspace slot (see mlp())
+    lgp_features_kernel<<<grid1d(rows * (ldX_ / 8)), 256, 0, st>>>(tt, B, L, noise, sigma, P_, D_, X_, ldX_);
+    S2I_LAUNCH_CHECK();
+    return mlp(st);
+}
+
+int LGP::forward_nchw(const float* x, const float* t, int B, int L, bool train, cudaStream_t st) {
+    if (!loaded_) return set_error(S2I_ERR_STATE, "lgp: weights not loaded");
+    groups_ = 1;   // LatentEdgePredictor.forward: BatchNorm statistics over every row of the call
+    B_ = B; L_ = L; train_ = train;
+    const long rows = (long)B * L * L;
+    S2I_TRY(ensure(lgp_ws_bytes(rows, ldX_, 1)));
+    X_ = reinterpret_cast<__half*>(buf_);
+    lgp_features_nchw_kernel<<<grid1d(rows * ldX_), 256, 0, st>>>(x, t, B, L, D_ - 4 - 4 * P_, P_, D_, X_, ldX_);
+    S2I_LAUNCH_CHECK();
+    for (int k = 0; k < 9; ++k) taps_[k] = LgpTap{nullptr, 0, 0};
+    return mlp(st);
+}
+
+int LGP::export_output(float* out_rows, cudaStream_t st) {
+    if (!have_fwd_) return set_error(S2I_ERR_STATE, "lgp: no forward yet");
+    lgp_export_kernel<<<grid1d((long)B_ * L_ * L_ * O_), 256, 0, st>>>(out16_, B_, L_, O_, out_rows);
+    S2I_LAUNCH_CHECK();
+    return 0;
+}
+
+int LGP::loss_backward(const float* target, float* const tap_grads[9], float* loss, cudaStream_t st) {
+    if (!have_fwd_) return set_error(S2I_ERR_STATE, "lgp: loss_backward needs a preceding forward");
+    have_fwd_ = false;
+    const long rows = (long)B_ * L_ * L_;
+    const int S = B_ / 2;
+    if (groups_ != S) return set_error(S2I_ERR_STATE, "lgp: loss_backward needs the per-pair (tap) forward");
+    const long R = 2L * L_ * L_;
+    const long n_elem = (long)O_ * L_ * L_;
+    gscale_ = exp2f(ceilf(log2f((float)n_elem)));
+    S2I_CUDA(cudaMemsetAsync(loss, 0, S * sizeof(float), st));
+    lgp_loss_kernel<<<grid1d(rows), 256, 0, st>>>(out16_, target, B_, L_, O_, 1.f / (float)n_elem, gscale_, dout_, loss);
+    S2I_LAUNCH_CHECK();
+
+    const __half* d = dout_;
+    long d_ld = 8;
+    __half* bufs[2] = {dA_, dB_};
+    int flip = 0;
+    for (int l = 4; l >= 0; --l) {
+        const int K = widths_[l + 1];   // contraction: this layer's output width
+        const int N = widths_[l];       // result: this layer's input width
+        GemmDesc g;
+        g.A = d; g.aC = K; g.aW = (int)rows; g.a_sw = d_ld;
+        g.B = lin_[l].wd; g.bI = K; g.bR = N; g.b_sr = (K + 7) / 8 * 8;
+        g.N = N; g.Kc = K;
+        g.qscale = gscale_;
+        __half* o = l == 0 ? X_ : bufs[flip];
+        g.out16 = o; g.ld16 = l == 0 ? ldX_ : N;
+        S2I_TRY(gemm_launch(g, st));
+        if (l == 0) break;
+        // BatchNorm(l-1) + ReLU backward
+        const int bl = l - 1;
+        if (train_) {
+            dim3 grid((unsigned)ceil_div_l(R, 128), S);
+            bn_reduce_kernel<1><<<grid, min(256, N / 2), 0, st>>>(h_[bl], o, mean_[bl], rstd_[bl], R, N, 128, bbsum_[bl]);
+            S2I_LAUNCH_CHECK();
+        }
+        __half* o2 = bufs[flip ^ 1];
+        bn_bwd_apply_kernel<<<grid1d(rows * (N / 2)), 256, 0, st>>>(o, h_[bl], mean_[bl], rstd_[bl], bn_[bl].g, bbsum_[bl],
+                                                                    train_ ? 1 : 0, R, N, rows, gscale_, o2);
+        S2I_LAUNCH_CHECK();
+        d = o2;
+        d_ld = N;
+        // next GEMM writes into bufs[flip] again (its previous content, the BN input gradient, is dead)
+    }
+    // adjoint of resize + concat: gather each tap's gradient from dX (now in X_)
+    int off = 0;
+    for (int k = 0; k < 9; ++k) {
+        if (!taps_[k].S) return set_error(S2I_ERR_STATE, "lgp: backward to taps needs the tap-based forward");
+        if (tap_grads[k]) {
+            interp_bwd_kernel<<<grid1d((long)B_ * taps_[k].S * taps_[k].S * (taps_[k].C / 8)), 256, 0, st>>>(
+                X_, ldX_, off, B_, L_, taps_[k].S, taps_[k].C, tap_grads[k]);
+            S2I_LAUNCH_CHECK();
+        }
+        off += taps_[k].C;
+    }
+    return 0;
+}
+
+// ================================================================================================== step
+int cfg_ddim_step(const float* latents, const float* eps, int S, int n, float guidance, float sb_t, float sa_t,
+                  float sa_p, float sb_p, int prediction, float* out, cudaStream_t st) {
+    cfg_ddim_kernel<<<grid1d((long)S * n), 256, 0, st>>>(latents, eps, S, n, guidance, sb_t, sa_t, sa_p, sb_p, prediction,
+                                                         out);
+    S2I_LAUNCH_CHECK();
+    return 0;
+}
+
+int guidance_update(const float* x_old, float* x_new, const float* dx, int S, int n, float beta, double* scratch,
+                    cudaStream_t st) {
+    S2I_CUDA(cudaMemsetAsync(scratch, 0, (size_t)S * 2 * sizeof(double), st));
+    dim3 grid(grid1d(n, 256, 64), S);
+    guidance_norms_kernel<<<grid, 256, 0, st>>>(x_old, x_new, dx, n, scratch);
+    S2I_LAUNCH_CHECK();
+    guidance_apply_kernel<<<grid, 256, 0, st>>>(x_new, dx, n, beta, scratch);
+    S2I_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace s2i

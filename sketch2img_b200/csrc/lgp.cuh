@@ -63,6 +63,13 @@ class LGP {
     __half* a_[4] = {};          // BN outputs (next GEMM operand)
     double* bsum_[4] = {};       // per (sample, column) sum / sumsq
     __half* out16_ = nullptr;    // [rows][8]
+    __half* dout_ = nullptr;     // [rows][8] scaled loss gradient
+    __half *dA_ = nullptr, *dB_ = nullptr;   // backward ping-pong [rows][512]
+    double* bbsum_[4] = {};      // backward per (sample, column) sums
+    float* mean_[4] = {};
+    float* rstd_[4] = {};
+    bool have_fwd_ = false;
+    int groups_ = 1;             // BatchNorm statistic groups (pairs on the sampling path, 1 for forward())
     float gscale_ = 1.f;
 
     int ensure(size_t bytes);

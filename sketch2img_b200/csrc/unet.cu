@@ -53,6 +53,19 @@ inline long rup(long a, long b) { return (a + b - 1) / b * b; }
 
 }  // namespace
 
+// Standalone helper (LGP): stage a host fp32 [N][K] matrix and pack fp16 forward [N][K] / transposed [K][N] copies.
+int pack_linear_host(const float* host, int N, int K, __half* w, long w_ld, __half* wd, long wd_ld) {
+    float* stg = nullptr;
+    S2I_CUDA(cudaMalloc(&stg, (size_t)N * K * sizeof(float)));
+    cudaMemcpy(stg, host, (size_t)N * K * sizeof(float), cudaMemcpyHostToDevice);
+    pack2d_kernel<<<1024, 256>>>(stg, K, 0, N, K, 0, 0, 0, 0, w, w_ld);
+    if (wd) pack2d_kernel<<<1024, 256>>>(stg, K, 1, K, N, 0, 0, 0, 0, wd, wd_ld);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(stg);
+    if (e != cudaSuccess) return set_error(S2I_ERR_CUDA, "pack_linear_host: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // ================================================================================================== loading
 UNet::~UNet() {
     for (void* p : owned_) cudaFree(p);

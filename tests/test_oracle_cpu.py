@@ -1,0 +1,67 @@
+"""CPU tests of the oracle (test infrastructure): the port restates the reference loop bit-exactly, matches the
+committed golden fixtures, and the reference's own files still agree when /root/reference is present."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _run_port(name, steps):
+    from oracle import port
+    unet = port.make_unet(name)
+    lgp = port.make_lgp(unet)
+    lat, emb, tgt = port.make_inputs(unet)
+    got = {}
+    out = port.guided_sample(unet, lgp, port.make_scheduler(), emb, lat.clone(), tgt, num_steps=steps,
+                             callback=lambda i, t, l: got.__setitem__(int(i), l.detach().clone()))
+    return out, got
+
+
+@pytest.mark.parametrize("steps", [4, 50])
+def test_port_matches_golden_tiny(steps):
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    gold = torch.load(os.path.join(GOLD, f"tiny_{steps}step.pt"))
+    out, got = _run_port("tiny", steps)
+    for i, ref in gold["latents"].items():
+        assert torch.equal(got[i], ref), f"step {i} differs from the fixture made by the reference files"
+    assert abs(out.norm().item() - gold["norms"][-1].item()) < 1e-3 * gold["norms"][-1].item()
+
+
+def test_golden_fixture_metadata():
+    for name in ["tiny_4step", "tiny_50step", "sd15_4step", "sd15_50step"]:
+        g = torch.load(os.path.join(GOLD, name + ".pt"))
+        assert g["source"].startswith("reference modules/pipeline.py")
+        assert g["steps"] - 1 in g["latents"]
+        assert torch.isfinite(g["norms"]).all()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/modules"), reason="reference sources only exist in the authoring container")
+def test_reference_files_over_shim_equal_port():
+    """The reference's pipeline.py + latent_predictor.py, imported UNMODIFIED over oracle/diffusers_shim, give
+    bit-identical per-step latents to oracle/port.py."""
+    from oracle import port
+    from oracle.make_golden import run_reference
+    ref_steps, _ = run_reference("tiny", 4)
+    _, got = _run_port("tiny", 4)
+    for i in range(4):
+        assert torch.equal(ref_steps[i], got[i])
+
+
+def test_reference_quirks_restated():
+    """train-mode BatchNorm, 3-of-4 guided steps, noise level from the initial noise."""
+    from oracle import port
+    unet = port.make_unet("tiny")
+    lgp = port.make_lgp(unet)
+    assert lgp.training and all(p.dtype == torch.float16 for p in lgp.parameters())
+    assert port.lgp_input_dim(unet) == 64 + 128 + 256 * 3 + 256 + 256 + 256 + 128 + 40
+    sch = port.make_scheduler()
+    sch.set_timesteps(4)
+    assert sch.timesteps.tolist() == [751, 501, 251, 1]
+    sch.set_timesteps(50)
+    assert sch.timesteps[:2].tolist() == [981, 961] and sch.timesteps[-1].item() == 1
+    assert abs(sch.alphas_cumprod[981].item() - 0.0057755) < 1e-6
+    assert sum(1 for i in range(50) if i <= 0.5 * 50) == 26
