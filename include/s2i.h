@@ -24,6 +24,12 @@ extern "C" {
 const char* s2i_last_error(void);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 long long s2i_launch_count(void);
+/* Opt-in per-launch device timing (bench.py's roofline numbers; no reference counterpart -- the reference ships no
+ * profiling).  Between begin and end every kernel this library launches on `cuda_stream` is
+ * bracketed by CUDA events; end synchronises the stream and writes one text line per kernel class:
+ * "<class> <launches> <ms> <flops> <bytes>".  Returns the number of characters written, or a negative code. */
+int s2i_profile_begin(void* cuda_stream);
+int s2i_profile_end(char* report, int capacity);
 
 /* ---------------------------------------------------------------------------------------------
  * tcgen05 + TMA implicit GEMM:  C[z] = alpha * A[z] * B[z]^T (+ bias, per-sample vector, ReLU, residual).

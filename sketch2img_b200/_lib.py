@@ -57,6 +57,8 @@ def lib():
         raise S2IError(f"cannot load {_LIB_PATH}: {e}. The sketch-guided path has no CPU fallback.") from e
     h.s2i_last_error.restype = C.c_char_p
     h.s2i_launch_count.restype = C.c_longlong
+    h.s2i_profile_begin.argtypes = [C.c_void_p]
+    h.s2i_profile_end.argtypes = [C.c_char_p, C.c_int]
     h.s2i_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     h.s2i_gemm.restype = C.c_int
     vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_void_p)
@@ -107,3 +109,21 @@ def gemm(desc):
 
 def launch_count():
     return int(lib().s2i_launch_count())
+
+
+def profile_begin():
+    """Start per-launch device timing of every libs2i kernel on the current stream."""
+    check(lib().s2i_profile_begin(stream_ptr()))
+
+
+def profile_end():
+    """-> {kernel class: {"launches", "ms", "flops", "bytes"}} since profile_begin()."""
+    buf = C.create_string_buffer(1 << 16)
+    n = lib().s2i_profile_end(buf, len(buf))
+    if n < 0:
+        check(n)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        tag, cnt, ms, fl, by = line.split()
+        out[tag] = {"launches": int(cnt), "ms": float(ms), "flops": float(fl), "bytes": float(by)}
+    return out

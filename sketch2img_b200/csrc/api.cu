@@ -12,6 +12,11 @@ extern "C" {
 
 const char* s2i_last_error(void) { return s2i::last_error(); }
 long long s2i_launch_count(void) { return s2i::g_launches; }
+int s2i_profile_begin(void* cuda_stream) { return s2i::prof_begin(static_cast<cudaStream_t>(cuda_stream)); }
+int s2i_profile_end(char* report, int capacity) {
+    if (!report || capacity <= 0) return s2i::set_error(S2I_ERR_ARG, "s2i_profile_end: no report buffer");
+    return s2i::prof_end(report, capacity);
+}
 
 int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream) {
     if (!d) return s2i::set_error(S2I_ERR_ARG, "s2i_gemm: null descriptor");

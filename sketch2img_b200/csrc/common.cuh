@@ -20,6 +20,14 @@ const char* last_error();
 extern long g_launches;  // kernels launched by this library since load
 inline void count_launch(int n = 1) { g_launches += n; }
 
+// Opt-in per-launch device timing (bench.py's roofline figures): while a profile is open every launch site drops a
+// CUDA event on the profiled stream; the gap to the previous event is attributed to the launch's tag.
+extern bool g_prof_on;
+void prof_mark(const char* tag, double flops, double bytes);
+int prof_begin(cudaStream_t st);
+// Text report, one line per tag: "tag launches ms flops bytes".  Returns the number of bytes written (or < 0).
+int prof_end(char* buf, int cap);
+
 #define S2I_CUDA(call)                                                                                       \
     do {                                                                                                     \
         cudaError_t e__ = (call);                                                                            \
@@ -35,6 +43,17 @@ inline void count_launch(int n = 1) { g_launches += n; }
             return ::s2i::set_error(S2I_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__,           \
                                     cudaGetErrorString(e__));                                                \
         ::s2i::count_launch();                                                                               \
+        if (::s2i::g_prof_on) ::s2i::prof_mark(__func__, 0.0, 0.0);                                          \
+    } while (0)
+
+#define S2I_LAUNCH_CHECK_TAG(tag, flops, bytes)                                                              \
+    do {                                                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                                \
+        if (e__ != cudaSuccess)                                                                              \
+            return ::s2i::set_error(S2I_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__,           \
+                                    cudaGetErrorString(e__));                                                \
+        ::s2i::count_launch();                                                                               \
+        if (::s2i::g_prof_on) ::s2i::prof_mark((tag), (flops), (bytes));                                     \
     } while (0)
 
 #define S2I_TRY(expr)                  \

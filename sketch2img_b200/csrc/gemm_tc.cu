@@ -500,7 +500,8 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     }
     dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)Z);
     gemm_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
-    S2I_LAUNCH_CHECK();
+    const double m_rows = d.a_mn ? (double)d.aC : (double)d.aW * d.aH * (d.Z > 1 ? 1 : d.aB);
+    S2I_LAUNCH_CHECK_TAG(d.tag, 2.0 * m_rows * d.N * d.Kc * d.taps * Z, 0.0);
     return 0;
 }
 

@@ -20,6 +20,7 @@ namespace s2i {
 // A operand, MN-major: the same 4-D tensor read as [K rows = W][M = C contiguous] (H = 1), batch on B.
 // B operand: 3-D tensor (I, R, Z) with I contiguous.  K-major: R = N rows, I = K.  MN-major: R = K rows, I = N.
 struct GemmDesc : s2i_gemm_desc {
+    const char* tag = "gemm";   // profiler class of this launch (gemm_conv3x3 / gemm_linear / gemm_attn / gemm_lgp)
     GemmDesc() {
         memset(static_cast<s2i_gemm_desc*>(this), 0, sizeof(s2i_gemm_desc));
         taps = 1; aH = 1; aB = 1; bZ = 1; Z = 1; zh = 1; alpha = 1.f;

@@ -533,6 +533,7 @@ int LGP::mlp(cudaStream_t st) {
     for (int l = 0; l < 5; ++l) {
         const int K = widths_[l], N = widths_[l + 1];
         GemmDesc d;
+        d.tag = "gemm_lgp";
         d.A = l == 0 ? X_ : a_[l - 1];
         d.aC = K; d.aW = (int)rows; d.a_sw = l == 0 ? ldX_ : K;
         d.B = lin_[l].w; d.bI = K; d.bR = N; d.b_sr = K;
@@ -631,6 +632,7 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
         const int K = widths_[l + 1];   // contraction: this layer's output width
         const int N = widths_[l];       // result: this layer's input width
         GemmDesc g;
+        g.tag = "gemm_lgp";
         g.A = d; g.aC = K; g.aW = (int)rows; g.a_sw = d_ld;
         g.B = lin_[l].wd; g.bI = K; g.bR = N; g.b_sr = (K + 7) / 8 * 8;
         g.N = N; g.Kc = K;

@@ -417,6 +417,7 @@ int UNet::gemm(const H16& a, bool spatial, int taps, const __half* w, long w_ld,
         d.a_sw = a.ld;
     }
     d.taps = taps;
+    d.tag = taps == 9 ? "gemm_conv3x3" : "gemm_linear";
     d.B = w;
     d.bI = taps * Kc;
     d.bR = N;
@@ -530,6 +531,7 @@ int UNet::attention(const Transformer& T, const H16& q, long q_c0, const H16& kv
     o = new16(q.B, q.H, q.W, T.HP);
     if (dry_) return 0;
     GemmDesc d;
+    d.tag = "gemm_attn";
     d.A = q.p; d.aC = (int)q.ld; d.aW = Nq; d.aB = B; d.a_sw = q.ld; d.a_sb = (long)Nq * q.ld;
     d.a_c0 = (int)q_c0; d.a_hoff = T.dp;
     d.B = kv.p; d.bI = (int)kv.ld; d.bR = Nk; d.bZ = B; d.b_sr = kv.ld; d.b_sz = (long)Nk * kv.ld;
@@ -540,6 +542,7 @@ int UNet::attention(const Transformer& T, const H16& q, long q_c0, const H16& kv
     S2I_TRY(gemm_launch(d, st_));
     S2I_TRY(softmax_fwd(S, ldS, (long)Z * Nq, Nk, P.p, ldP, st_));
     GemmDesc e;
+    e.tag = "gemm_attn";
     e.A = P.p; e.aC = Nk; e.aW = Nq; e.aB = Z; e.a_sw = ldP; e.a_sb = (long)Nq * ldP; e.a_zmode = 1;
     e.B = kv.p; e.b_mn = 1; e.bI = (int)kv.ld; e.bR = Nk; e.bZ = B; e.b_sr = kv.ld; e.b_sz = (long)Nk * kv.ld;
     e.b_c0 = (int)v_c0; e.b_hoff = T.dp;
@@ -559,6 +562,7 @@ int UNet::attention_bwd(const Transformer& T, const H16& dO, const H16& q, long 
     const float scale = 1.f / sqrtf((float)T.d);
     {   // dP = dO V^T
         GemmDesc d;
+            d.tag = "gemm_attn_bwd";
         d.A = dO.p; d.aC = (int)dO.ld; d.aW = Nq; d.aB = B; d.a_sw = dO.ld; d.a_sb = (long)Nq * dO.ld; d.a_hoff = T.dp;
         d.B = kv.p; d.bI = (int)kv.ld; d.bR = Nk; d.bZ = B; d.b_sr = kv.ld; d.b_sz = (long)Nk * kv.ld;
         d.b_c0 = (int)v_c0; d.b_hoff = T.dp;
@@ -569,6 +573,7 @@ int UNet::attention_bwd(const Transformer& T, const H16& dO, const H16& q, long 
     S2I_TRY(softmax_bwd(P.p, ldP, dP, ldS, (long)Z * Nq, Nk, scale, dS, ldP, st_));
     {   // dQ = dS K
         GemmDesc d;
+            d.tag = "gemm_attn_bwd";
         d.A = dS; d.aC = Nk; d.aW = Nq; d.aB = Z; d.a_sw = ldP; d.a_sb = (long)Nq * ldP; d.a_zmode = 1;
         d.B = kv.p; d.b_mn = 1; d.bI = (int)kv.ld; d.bR = Nk; d.bZ = B; d.b_sr = kv.ld; d.b_sz = (long)Nk * kv.ld;
         d.b_c0 = (int)k_c0; d.b_hoff = T.dp;
@@ -579,6 +584,7 @@ int UNet::attention_bwd(const Transformer& T, const H16& dO, const H16& q, long 
     if (dkv) {
         {   // dV = P^T dO
             GemmDesc d;
+            d.tag = "gemm_attn_bwd";
             d.A = P.p; d.a_mn = 1; d.aC = Nk; d.aW = Nq; d.aB = Z; d.a_sw = ldP; d.a_sb = (long)Nq * ldP; d.a_zmode = 1;
             d.B = dO.p; d.b_mn = 1; d.bI = (int)dO.ld; d.bR = Nq; d.bZ = B; d.b_sr = dO.ld; d.b_sz = (long)Nq * dO.ld;
             d.b_hoff = T.dp;
@@ -588,6 +594,7 @@ int UNet::attention_bwd(const Transformer& T, const H16& dO, const H16& q, long 
         }
         {   // dK = dS^T Q
             GemmDesc d;
+            d.tag = "gemm_attn_bwd";
             d.A = dS; d.a_mn = 1; d.aC = Nk; d.aW = Nq; d.aB = Z; d.a_sw = ldP; d.a_sb = (long)Nq * ldP; d.a_zmode = 1;
             d.B = q.p; d.b_mn = 1; d.bI = (int)q.ld; d.bR = Nq; d.bZ = B; d.b_sr = q.ld; d.b_sz = (long)Nq * q.ld;
             d.b_c0 = (int)q_c0; d.b_hoff = T.dp;
