@@ -44,7 +44,7 @@ int s2i_profile_end(char* report, int capacity);
 typedef struct s2i_gemm_desc {
     const void* A; int a_mn; int aC, aW, aH, aB; long long a_sw, a_sh, a_sb; int taps; int a_c0, a_hoff, a_zmode;
     const void* B; int b_mn; int bI, bR, bZ; long long b_sr, b_sz; int b_c0, b_hoff, b_zmode;
-    int N, Kc, Z, zh; int bf16; int BN;
+    int N, Kc, Z, zh; int bf16; int BN; int splits;   /* BN / splits: 0 = chosen by the library; splits < 0 = never split K */
     float alpha; const float* bias; const float* rowvec; int rowvec_ld;
     const float* residual; long long res_ld;
     float* out32; long long ld32; void* out16; long long ld16; int out16_bf16;
@@ -107,6 +107,9 @@ int s2i_lgp_load(s2i_lgp* l, int n, const char* const* names, const float* const
  * the noise-level input is sigma * noise for both halves of a pair (modules/pipeline.py:152-153) */
 int s2i_lgp_forward_taps(s2i_lgp* l, const float* const* taps, const int* sizes, const int* channels, int B, int L,
                          const float* noise, float sigma, int train, void* cuda_stream);
+/* emulate != 0 (default): round the back-propagated gradients like the reference's unscaled fp16 autograd
+ * (latent_predictor.py:43 casts to fp16, so torch's backward runs in fp16); 0: loss-scaled, no extra rounding */
+int s2i_lgp_set_grad_rounding(s2i_lgp* l, int emulate);
 /* x: NCHW fp32 [B][input_dim-4-4P][L][L] (already resized + concatenated), t: NCHW fp32 [B][4][L][L] */
 int s2i_lgp_forward_nchw(s2i_lgp* l, const float* x, const float* t, int B, int L, int train, void* cuda_stream);
 /* out_rows: fp32 device [(b w h)][output_dim] -- the reference's row order (latent_predictor.py:43) */

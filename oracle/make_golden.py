@@ -21,7 +21,7 @@ from oracle import port  # noqa: E402
 REF = "/root/reference"
 
 
-def run_reference(name, steps, guidance_scale=7.5, seed=port.SAMPLE_SEED):
+def run_reference(name, steps, guidance_scale=7.5, seed=port.SAMPLE_SEED, guided=True, latent_scale=1.0):
     if REF not in sys.path:
         sys.path.insert(0, REF)
     from modules.latent_predictor import LatentEdgePredictor
@@ -38,8 +38,8 @@ def run_reference(name, steps, guidance_scale=7.5, seed=port.SAMPLE_SEED):
     pipe.setup_lgp(lgp)
     per_step = {}
     t0 = time.perf_counter()
-    pipe("synthetic", num_inference_steps=steps, guidance_scale=guidance_scale, latents=lat.clone(),
-         sketch_image=tgt, output_type="np",
+    pipe("synthetic", num_inference_steps=steps, guidance_scale=guidance_scale, latents=lat.clone() * latent_scale,
+         sketch_image=tgt if guided else None, output_type="np",
          callback=lambda i, t, l: per_step.__setitem__(int(i), l.detach().clone().float()))
     dt = time.perf_counter() - t0
     return per_step, dt
@@ -54,7 +54,16 @@ def main(argv):
         steps = int(steps)
         per_step, dt = run_reference(name, steps)
         keep = sorted(set(list(range(0, steps, max(1, steps // 10))) + [steps - 1]))
+        # The guided loop is chaotic (DESIGN.md "Conditioning"): the SAME reference files, started from latents scaled
+        # by (1 + 1e-6), drift away from the run above.  That drift is the noise floor any other implementation is
+        # measured against.  The unguided run (sketch_image=None: plain CFG + DDIM) is smooth and pins the UNet +
+        # scheduler over the full schedule.
+        pert, _ = run_reference(name, steps, latent_scale=1.0 + 1e-6)
+        rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()
+        unguided, dt_u = run_reference(name, steps, guided=False)
         blob = {
+            "self_sensitivity": torch.tensor([rel(pert[i], per_step[i]) for i in range(steps)]),
+            "unguided_latents": {i: unguided[i] for i in keep}, "unguided_cpu_seconds": dt_u,
             "config": name, "steps": steps, "guidance_scale": 7.5, "beta": 1.6,
             "weight_seed": port.WEIGHT_SEED, "sample_seed": port.SAMPLE_SEED,
             "latents": {i: per_step[i] for i in keep},

@@ -68,6 +68,24 @@ class LatentEdgePredictorOracle(nn.Module):
         return self.layers(z)
 
 
+class LatentEdgePredictorOracle32(nn.Module):
+    """NOT the reference: the same MLP evaluated in fp32 end to end (no ``.to(float16)`` cast, fp32 weights copied
+    from an fp16 oracle LGP).  Used by the tests to separate implementation error from the reference's own fp16
+    rounding noise (its unscaled fp16 gradients sit in the subnormal range)."""
+
+    def __init__(self, lgp16):
+        super().__init__()
+        import copy
+        self.num_layers = lgp16.num_layers
+        self.layers = copy.deepcopy(lgp16.layers).float()
+
+    def forward(self, x, t):
+        pos = torch.cat([torch.sin(2 * math.pi * t * (2 ** -l)) for l in range(self.num_layers)], dim=1)
+        z = torch.cat((x, t, pos), dim=1)
+        b, c, h, w = z.shape
+        return self.layers(z.permute(0, 3, 2, 1).reshape(b * w * h, c))
+
+
 def tap_modules(unet):
     """The 9 tapped sub-modules in hook order (latent_predictor.py:63-80): down_blocks[0..2],
     mid attentions then mid resnets, up_blocks[0..2]."""

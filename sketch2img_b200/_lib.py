@@ -20,7 +20,7 @@ class GemmDesc(C.Structure):
         ("a_c0", C.c_int), ("a_hoff", C.c_int), ("a_zmode", C.c_int),
         ("B", C.c_void_p), ("b_mn", C.c_int), ("bI", C.c_int), ("bR", C.c_int), ("bZ", C.c_int),
         ("b_sr", C.c_longlong), ("b_sz", C.c_longlong), ("b_c0", C.c_int), ("b_hoff", C.c_int), ("b_zmode", C.c_int),
-        ("N", C.c_int), ("Kc", C.c_int), ("Z", C.c_int), ("zh", C.c_int), ("bf16", C.c_int), ("BN", C.c_int),
+        ("N", C.c_int), ("Kc", C.c_int), ("Z", C.c_int), ("zh", C.c_int), ("bf16", C.c_int), ("BN", C.c_int), ("splits", C.c_int),
         ("alpha", C.c_float), ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int),
         ("residual", C.c_void_p), ("res_ld", C.c_longlong),
         ("out32", C.c_void_p), ("ld32", C.c_longlong), ("out16", C.c_void_p), ("ld16", C.c_longlong),
@@ -78,6 +78,7 @@ def lib():
     h.s2i_lgp_destroy.argtypes = [vp]
     h.s2i_lgp_destroy.restype = None
     h.s2i_lgp_load.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(vp), ip, ll]
+    h.s2i_lgp_set_grad_rounding.argtypes = [vp, C.c_int]
     h.s2i_lgp_forward_taps.argtypes = [vp, C.POINTER(vp), ip, ip, C.c_int, C.c_int, vp, f, C.c_int, vp]
     h.s2i_lgp_forward_nchw.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     h.s2i_lgp_output.argtypes = [vp, vp, vp]

@@ -44,7 +44,16 @@ struct __align__(64) GemmParams {
     long c_sb, c_sh;
     int relu;
     float qscale, qinv;
+    int fast_epi;            // aligned operands: coalesced (smem-transposed) epilogue
+    int splits, iters_per_split;
+    float* ws;               // split-K partial tiles [split][tile][128][BN] fp32
+    unsigned int* counters;  // one arrival counter per output tile (self-resetting)
 };
+
+constexpr int kEpiLd = 36;   // floats per row of the per-warp 32x32 transpose buffer (16-byte aligned, conflict-free)
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldcg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 __device__ __forceinline__ uint16_t to_half_bits(float v, int bf16) {
     if (bf16) {
@@ -70,7 +79,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
     const int mt = blockIdx.x;
     const int n0 = blockIdx.y * p.BN;
-    const int z = blockIdx.z;
+    const int z = blockIdx.z / p.splits;
+    const int split = blockIdx.z - z * p.splits;
     const int zb = z / p.zh, zhd = z - zb * p.zh;
     int x0 = 0, y0 = 0, b0 = 0, m0 = 0;
     if (!p.a_mn) {
@@ -106,7 +116,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_iters = p.taps * p.k_chunks;
+    const int total_iters = p.taps * p.k_chunks;
+    const int it_begin = split * p.iters_per_split;
+    const int it_end = min(total_iters, it_begin + p.iters_per_split);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -116,9 +128,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const int b_inner = p.b_c0 + (p.b_zmode ? 0 : zhd * p.b_hoff);
             const int b_bz = p.b_zmode ? z : zb;
             const int nchunks_b = (p.BN + 63) >> 6;
-            for (int it = 0; it < num_iters; ++it) {
-                const int stage = it % p.stages;
-                const uint32_t phase = (it / p.stages) & 1;
+            for (int it = it_begin; it < it_end; ++it) {
+                const int li = it - it_begin;
+                const int stage = li % p.stages;
+                const uint32_t phase = (li / p.stages) & 1;
                 ptx::mbar_wait(&empty[stage], phase ^ 1);
                 ptx::mbar_expect_tx(&full[stage], p.tx_bytes);
                 uint8_t* sa = smem + stage * stage_bytes;
@@ -152,9 +165,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
             const uint32_t a_lbo = p.a_mn ? (uint32_t)kChunkBytes : 16u;
             const uint32_t b_lbo = p.b_mn ? (uint32_t)kChunkBytes : 16u;
-            for (int it = 0; it < num_iters; ++it) {
-                const int stage = it % p.stages;
-                const uint32_t phase = (it / p.stages) & 1;
+            for (int it = it_begin; it < it_end; ++it) {
+                const int li = it - it_begin;
+                const int stage = li % p.stages;
+                const uint32_t phase = (li / p.stages) & 1;
                 ptx::mbar_wait(&full[stage], phase);
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
@@ -164,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 for (int k = 0; k < ksteps; ++k) {
                     const uint64_t adesc = ptx::make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024u);
                     const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024u);
-                    ptx::umma_f16(tmem_base, adesc, bdesc, p.idesc, (it | k) != 0 ? 1u : 0u);
+                    ptx::umma_f16(tmem_base, adesc, bdesc, p.idesc, (li | k) != 0 ? 1u : 0u);
                 }
                 ptx::umma_commit(&empty[stage]);   // frees the smem stage once these MMAs have read it
             }
@@ -173,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     } else {
         // ---------------------------------------------------- epilogue (warps 2..5)
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int r = q * 32 + lane;            // tile row
+        const int r = q * 32 + lane;            // tile row owned by this thread in the TMEM layout
         bool valid;
         long row;
         int sample = 0;
@@ -189,98 +203,189 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             row = m0 + r;
         }
         const long zoff = (long)zb * p.c_sb + (long)zhd * p.c_sh;
-        float* o32 = p.out32 ? p.out32 + zoff + row * p.ld32 : nullptr;
-        uint16_t* o16 = p.out16 ? reinterpret_cast<uint16_t*>(p.out16) + zoff + row * p.ld16 : nullptr;
-        const float* res = p.residual ? p.residual + zoff + row * p.res_ld : nullptr;
-        const float* rvec = p.rowvec ? p.rowvec + (long)sample * p.rowvec_ld : nullptr;
-        const bool vec32 = o32 && ((p.ld32 & 3) == 0) && ((zoff & 3) == 0) &&
-                           ((reinterpret_cast<uintptr_t>(p.out32) & 15) == 0);
-        const bool vec16 = o16 && ((p.ld16 & 7) == 0) && ((zoff & 7) == 0) &&
-                           ((reinterpret_cast<uintptr_t>(p.out16) & 15) == 0);
-        const bool vecres = res && ((p.res_ld & 3) == 0) && ((zoff & 3) == 0) &&
-                            ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
 
         ptx::mbar_wait(accum_full, 0);
         ptx::tc_fence_after();
 
-        for (int c = 0; c < p.BN; c += 32) {
-            uint32_t raw[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
-            if (c + 32 <= p.BN) {
-                ptx::tmem_ld_32x32(taddr, raw);
-            } else {   // BN is a multiple of 16: 16-column tail
-                uint32_t lo[16];
-                ptx::tmem_ld_32x16(taddr, lo);
+        if (p.fast_epi) {
+            // Coalesced path.  TMEM hands each thread one ROW (32 consecutive columns per load); global memory wants
+            // a warp instruction to cover whole 128-byte row segments.  Each warp therefore transposes its 32x32 block
+            // through shared memory (the pipeline stages are idle once the accumulator is complete) and then works with
+            // lane -> (row i*4 + lane/8, columns 4*(lane%8)..+3): 8 lanes cover one 128-byte segment.  Bias / residual
+            // loads for a chunk are issued before the TMEM data is needed, so their latency overlaps the tcgen05.ld.
+            float* sT = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kEpiLd);
+            const int cq = (lane & 7) * 4;
+            const int rsub = lane >> 3;
+            const long my_row = valid ? row : -1;
+            long rows8[8];
+            int smp8[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    raw[j] = lo[j];
-                    raw[16 + j] = 0u;
+            for (int i = 0; i < 8; ++i) {
+                rows8[i] = __shfl_sync(0xffffffffu, my_row, i * 4 + rsub);
+                smp8[i] = __shfl_sync(0xffffffffu, sample, i * 4 + rsub);
+            }
+            const int tile_id = blockIdx.x + gridDim.x * blockIdx.y;
+            const int num_tiles = gridDim.x * gridDim.y;
+            float* wsT = p.splits > 1
+                             ? p.ws + ((long)(split * num_tiles + tile_id) * kBlockM + q * 32) * p.BN
+                             : nullptr;
+
+            // applies alpha / bias / per-sample vector / ReLU / fp16-rounding emulation / residual and stores 4 columns
+            auto finish4 = [&](float4 v, const float4& b4, const float4& rs, long ro, int smp, int n) {
+                v.x = v.x * p.alpha + b4.x; v.y = v.y * p.alpha + b4.y; v.z = v.z * p.alpha + b4.z; v.w = v.w * p.alpha + b4.w;
+                if (p.rowvec && p.rowvec_ld != 0) {
+                    const float4 rv = ldg_f4(p.rowvec + (long)smp * p.rowvec_ld + n);
+                    v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                }
+                if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                if (p.qscale != 0.f) {
+                    v.x = __half2float(__float2half_rn(v.x * p.qinv)) * p.qscale;
+                    v.y = __half2float(__float2half_rn(v.y * p.qinv)) * p.qscale;
+                    v.z = __half2float(__float2half_rn(v.z * p.qinv)) * p.qscale;
+                    v.w = __half2float(__float2half_rn(v.w * p.qinv)) * p.qscale;
+                }
+                v.x += rs.x; v.y += rs.y; v.z += rs.z; v.w += rs.w;
+                if (p.out32) *reinterpret_cast<float4*>(p.out32 + zoff + ro * p.ld32 + n) = v;
+                if (p.out16) {
+                    uint2 pk;
+                    pk.x = (uint32_t)to_half_bits(v.x, p.out16_bf16) | ((uint32_t)to_half_bits(v.y, p.out16_bf16) << 16);
+                    pk.y = (uint32_t)to_half_bits(v.z, p.out16_bf16) | ((uint32_t)to_half_bits(v.w, p.out16_bf16) << 16);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out16) + zoff + ro * p.ld16 + n) = pk;
+                }
+            };
+            auto load_b4 = [&](int n, bool colok) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (colok && p.bias) b4 = ldg_f4(p.bias + n);
+                if (colok && p.rowvec && p.rowvec_ld == 0) {
+                    const float4 t = ldg_f4(p.rowvec + n);
+                    b4.x += t.x; b4.y += t.y; b4.z += t.z; b4.w += t.w;
+                }
+                return b4;
+            };
+
+            for (int c = 0; c < p.BN; c += 32) {
+                const int ncols = min(min(32, p.BN - c), p.N - (n0 + c));     // multiple of 4 on this path
+                if (ncols <= 0) break;
+                uint32_t raw[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+                if (c + 32 <= p.BN) {
+                    ptx::tmem_ld_32x32(taddr, raw);
+                } else {   // BN is a multiple of 16: 16-column tail
+                    uint32_t lo[16];
+                    ptx::tmem_ld_32x16(taddr, lo);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        raw[j] = lo[j];
+                        raw[16 + j] = 0u;
+                    }
+                }
+                const bool colok = cq < ncols;
+                const int n = n0 + c + cq;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 rs[8];
+                if (p.splits == 1) {
+                    b4 = load_b4(n, colok);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.residual && colok && rows8[i] >= 0) rs[i] = ldg_f4(p.residual + zoff + rows8[i] * p.res_ld + n);
+                    }
+                }
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(sT + lane * kEpiLd + 4 * j) =
+                        make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                    __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v = *reinterpret_cast<const float4*>(sT + (i * 4 + rsub) * kEpiLd + cq);
+                    if (p.splits == 1) {
+                        if (colok && rows8[i] >= 0) finish4(v, b4, rs[i], rows8[i], smp8[i], n);
+                    } else if (colok) {
+                        *reinterpret_cast<float4*>(wsT + (long)(i * 4 + rsub) * p.BN + c + cq) = v;   // raw partial sums
+                    }
+                }
+                __syncwarp();
+            }
+
+            if (p.splits > 1) {
+                // The last CTA to arrive for this output tile reduces every split's partial tile (in split order, so the
+                // result does not depend on arrival order) and runs the real epilogue.
+                uint32_t* flag = reinterpret_cast<uint32_t*>(sT + 4 * 32 * kEpiLd - (warp - 2) * (32 * kEpiLd));
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (warp == 2 && lane == 0) {
+                    const unsigned int old = atomicAdd(p.counters + tile_id, 1u);
+                    const bool last = (old == (unsigned int)(p.splits - 1));
+                    if (last) p.counters[tile_id] = 0u;      // self-reset for the next launch
+                    *flag = last ? 1u : 0u;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (*flag) {
+                    __threadfence();
+                    const float* ws0 = p.ws + ((long)tile_id * kBlockM + q * 32) * p.BN;
+                    const long split_stride = (long)num_tiles * kBlockM * p.BN;
+                    for (int c = 0; c < p.BN; c += 32) {
+                        const int ncols = min(min(32, p.BN - c), p.N - (n0 + c));
+                        if (ncols <= 0) break;
+                        const bool colok = cq < ncols;
+                        const int n = n0 + c + cq;
+                        if (!colok) continue;
+                        const float4 b4 = load_b4(n, true);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (rows8[i] < 0) continue;
+                            float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.residual) rs = ldg_f4(p.residual + zoff + rows8[i] * p.res_ld + n);
+                            const float* src = ws0 + (long)(i * 4 + rsub) * p.BN + c + cq;
+                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int sp = 0; sp < p.splits; ++sp) {
+                                const float4 t = ldcg_f4(src + sp * split_stride);
+                                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                            }
+                            finish4(acc, b4, rs, rows8[i], smp8[i], n);
+                        }
+                    }
                 }
             }
-            ptx::tmem_ld_wait();
-            if (!valid) continue;
-            const int nbase = n0 + c;
-            const int ncols = min(min(32, p.BN - c), p.N - nbase);
-            if (ncols <= 0) continue;
+        } else {
+            // Generic path (odd widths / unaligned outputs, e.g. N not a multiple of 4): one thread per row.
+            float* o32 = p.out32 ? p.out32 + zoff + row * p.ld32 : nullptr;
+            uint16_t* o16 = p.out16 ? reinterpret_cast<uint16_t*>(p.out16) + zoff + row * p.ld16 : nullptr;
+            const float* res = p.residual ? p.residual + zoff + row * p.res_ld : nullptr;
+            const float* rvec = p.rowvec ? p.rowvec + (long)sample * p.rowvec_ld : nullptr;
+            for (int c = 0; c < p.BN; c += 32) {
+                uint32_t raw[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+                if (c + 32 <= p.BN) {
+                    ptx::tmem_ld_32x32(taddr, raw);
+                } else {
+                    uint32_t lo[16];
+                    ptx::tmem_ld_32x16(taddr, lo);
 #pragma unroll
-            for (int j4 = 0; j4 < 32; j4 += 4) {
-                if (j4 >= ncols) break;
-                float v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(raw[j4 + j]) * p.alpha;
-                const int n = nbase + j4;
-                const bool full4 = (j4 + 4 <= ncols);
-                if (p.bias) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j4 + j < ncols) v[j] += __ldg(p.bias + n + j);
-                }
-                if (rvec) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j4 + j < ncols) v[j] += __ldg(rvec + n + j);
-                }
-                if (p.relu) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
-                }
-                if (p.qscale != 0.f) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = __half2float(__float2half_rn(v[j] * p.qinv)) * p.qscale;
-                }
-                if (res) {
-                    if (full4 && vecres && ((n & 3) == 0)) {
-                        const float4 rr = *reinterpret_cast<const float4*>(res + n);
-                        v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j4 + j < ncols) v[j] += res[n + j];
+                    for (int j = 0; j < 16; ++j) {
+                        raw[j] = lo[j];
+                        raw[16 + j] = 0u;
                     }
                 }
-                if (o32) {
-                    if (full4 && vec32 && ((n & 3) == 0)) {
-                        *reinterpret_cast<float4*>(o32 + n) = make_float4(v[0], v[1], v[2], v[3]);
-                    } else {
+                ptx::tmem_ld_wait();
+                if (!valid) continue;
+                const int nbase = n0 + c;
+                const int ncols = min(min(32, p.BN - c), p.N - nbase);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j4 + j < ncols) o32[n + j] = v[j];
-                    }
-                }
-                if (o16) {
-                    uint16_t h[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) h[j] = to_half_bits(v[j], p.out16_bf16);
-                    if (full4 && vec16 && ((n & 3) == 0)) {
-                        uint2 pk;
-                        pk.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
-                        pk.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
-                        *reinterpret_cast<uint2*>(o16 + n) = pk;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j4 + j < ncols) o16[n + j] = h[j];
-                    }
+                for (int j = 0; j < 32; ++j) {
+                    if (j >= ncols) break;
+                    const int n = nbase + j;
+                    float v = __uint_as_float(raw[j]) * p.alpha;
+                    if (p.bias) v += __ldg(p.bias + n);
+                    if (rvec) v += __ldg(rvec + n);
+                    if (p.relu) v = fmaxf(v, 0.f);
+                    if (p.qscale != 0.f) v = __half2float(__float2half_rn(v * p.qinv)) * p.qscale;
+                    if (res) v += res[n];
+                    if (o32) o32[n] = v;
+                    if (o16) o16[n] = to_half_bits(v, p.out16_bf16);
                 }
             }
         }
@@ -331,25 +436,78 @@ int pow2_floor(int v) {
     return p;
 }
 
-int choose_bn(int N, long ctas_mz) {
+// ---- tile-shape / split-K selection ------------------------------------------------------------------------------
+// Rough per-CTA cycle model (B300_MICROARCH.md pacing law: one 128 x BN x 16 MMA takes ~BN/2 cycles; L2 -> SM operand
+// traffic at ~64 B/clk/SM when every SM pulls; ~6 k cycles of fixed launch / prologue / first-load latency; epilogue
+// ~8 cycles per column).  The problem sizes on this path are at most a few waves, so filling the 148 SMs (x2 resident
+// CTAs when shared memory allows) matters as much as the inner-loop rate.
+struct TileChoice {
+    int BN, splits;
+};
+
+double model_cycles(int N, long tiles_m, int Z, int iters, int BN, int splits) {
+    const int tiles_n = ceil_div(N, BN);
+    const long ctas = tiles_m * tiles_n * Z * splits;
+    const int stage_bytes = kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
+    const int occ = (3 * stage_bytes <= 100 * 1024) ? 2 : 1;
+    const long slots = (long)kNumSMs * occ;
+    const long waves = ceil_div_l(ctas, slots);
+    const int it = ceil_div(iters, splits);
+    const double resident = (double)(ctas < slots ? ceil_div_l(ctas, kNumSMs) : occ);   // CTAs sharing one SM
+    const double mma = 2.0 * BN * resident;                                  // cycles per 64-wide K chunk, SM shared
+    const double tma = (double)stage_bytes / 64.0 * resident;
+    const double per_iter = mma > tma ? mma : tma;
+    double fixed = 6000.0 + 8.0 * BN;
+    if (splits > 1) fixed += 1500.0 + 2.0 * BN * splits;                     // partial store + last-CTA reduction
+    return (double)waves * (it * per_iter + fixed);
+}
+
+TileChoice choose_tiles(int N, long tiles_m, int Z, int iters, bool allow_split) {
     const int nr = (int)round_up_l(N, 16);
-    if (nr <= 32) return nr;
-    static const int cands[] = {256, 192, 160, 128, 96, 80, 64, 48, 32};
-    int best = 0;
-    double best_score = -1.0;
+    static const int cands[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
+    TileChoice best{nr <= 256 ? nr : 128, 1};
+    double best_c = 1e30;
     for (int c : cands) {
-        const int tiles = ceil_div(N, c);
-        const double eff = (double)N / ((double)tiles * c);          // useful fraction of MMA columns
-        const long ctas = ctas_mz * tiles;
-        const double fill = ctas >= kNumSMs ? 1.0 : (double)ctas / kNumSMs;
-        const double width = 0.6 + 0.4 * ((double)c / 256.0);         // wider tiles re-read A less
-        const double score = eff * fill * width;
-        if (score > best_score) {
-            best_score = score;
-            best = c;
+        if (c > nr && c != 16) {
+            if (nr > 256 || c != cands[0]) continue;
+        }
+        const int bn = c > nr ? nr : c;
+        const long base = tiles_m * ceil_div(N, bn) * Z;
+        for (int sp = 1; sp <= 32; sp *= 2) {
+            if (sp > 1 && (!allow_split || base >= kNumSMs || iters / sp < 4)) break;
+            if ((long)(sp - 1) * ceil_div(iters, sp) >= iters) continue;     // an empty split
+            const double cyc = model_cycles(N, tiles_m, Z, iters, bn, sp);
+            if (cyc < best_c) {
+                best_c = cyc;
+                best = TileChoice{bn, sp};
+            }
         }
     }
     return best;
+}
+
+// split-K scratch: partial tiles + per-tile arrival counters (one stream at a time uses the library)
+constexpr size_t kWsBytes = 96u << 20;
+constexpr int kMaxSplitTiles = 4096;
+float* g_ws = nullptr;
+unsigned int* g_counters = nullptr;
+int g_ws_device = -1;
+
+int ensure_ws() {
+    int dev = 0;
+    S2I_CUDA(cudaGetDevice(&dev));
+    if (g_ws && dev == g_ws_device) return 0;
+    void* a = nullptr;
+    void* b = nullptr;
+    if (cudaMalloc(&a, kWsBytes) != cudaSuccess || cudaMalloc(&b, kMaxSplitTiles * sizeof(unsigned int)) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(S2I_ERR_OOM, "gemm: cannot allocate the split-K workspace");
+    }
+    S2I_CUDA(cudaMemset(b, 0, kMaxSplitTiles * sizeof(unsigned int)));
+    g_ws = static_cast<float*>(a);
+    g_counters = static_cast<unsigned int*>(b);
+    g_ws_device = dev;
+    return 0;
 }
 
 }  // namespace
@@ -419,22 +577,53 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     }
     const int Z = d.Z > 0 ? d.Z : 1;
 
-    int BN = d.BN > 0 ? d.BN : choose_bn(d.N, tiles_m * Z);
+    const int num_iters = p.taps * p.k_chunks;
+    // coalesced epilogue needs 16-byte aligned rows; everything on the sampling path qualifies
+    const long zo_align = (d.c_sb | d.c_sh);
+    bool fast = (d.N % 4 == 0) && (zo_align % 4 == 0);
+    if (d.out32) fast = fast && (d.ld32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.out32) & 15) == 0);
+    if (d.out16) fast = fast && (d.ld16 % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.out16) & 7) == 0);
+    if (d.residual) fast = fast && (d.res_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.residual) & 15) == 0);
+    if (d.bias) fast = fast && ((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0);
+    if (d.rowvec) fast = fast && (d.rowvec_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.rowvec) & 15) == 0);
+    p.fast_epi = fast ? 1 : 0;
+
+    TileChoice tc = choose_tiles(d.N, tiles_m, Z, num_iters, fast && Z == 1 && d.splits >= 0);
+    if (d.BN > 0) tc.BN = d.BN;
+    if (d.splits > 0) tc.splits = d.splits;
+    if (!fast || Z != 1) tc.splits = 1;
+    int BN = tc.BN;
     if (BN % 16 != 0 || BN < 16 || BN > 256) return set_error(S2I_ERR_ARG, "gemm: BN %d invalid", BN);
     p.BN = BN;
+    if (tc.splits > 1) {
+        const long tiles = tiles_m * ceil_div(d.N, BN);
+        while (tc.splits > 1 && ((long)(tc.splits - 1) * ceil_div(num_iters, tc.splits) >= num_iters ||
+                                 (size_t)tc.splits * tiles * kBlockM * BN * sizeof(float) > kWsBytes ||
+                                 tiles > kMaxSplitTiles))
+            --tc.splits;
+    }
+    p.splits = tc.splits;
+    p.iters_per_split = ceil_div(num_iters, tc.splits);
+    if (tc.splits > 1) {
+        S2I_TRY(ensure_ws());
+        p.ws = g_ws;
+        p.counters = g_counters;
+    }
     const int tiles_n = ceil_div(d.N, BN);
     p.tmem_cols = 32;
     while (p.tmem_cols < BN) p.tmem_cols *= 2;
 
     const int b_stage_bytes = ceil_div(BN, 64) * kChunkBytes;
     const int stage_bytes = kAStageBytes + b_stage_bytes;
-    const int num_iters = p.taps * p.k_chunks;
     int stages = (100 * 1024) / stage_bytes;   // <= ~100 KB so two CTAs can share an SM
     if (stages < 3) stages = 3;
     if (stages > 6) stages = 6;
-    if (stages > num_iters) stages = num_iters < 1 ? 1 : num_iters;
+    if (stages > p.iters_per_split) stages = p.iters_per_split < 1 ? 1 : p.iters_per_split;
     p.stages = stages;
-    const size_t smem_bytes = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+    // the epilogue reuses stage memory for its 4 x (32 x 36) fp32 transpose buffers (+ flag): keep at least 19 KB
+    size_t pipe_bytes = (size_t)stages * stage_bytes;
+    if (pipe_bytes < 19 * 1024) pipe_bytes = 19 * 1024;
+    const size_t smem_bytes = pipe_bytes + (2 * stages + 1) * 8 + 16 + 1024;
 
     p.a_c0 = d.a_c0;
     p.a_hoff = d.a_hoff;
@@ -498,7 +687,7 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
         S2I_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)Z);
+    dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)(Z * p.splits));
     gemm_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
     const double m_rows = d.a_mn ? (double)d.aC : (double)d.aW * d.aH * (d.Z > 1 ? 1 : d.aB);
     S2I_LAUNCH_CHECK_TAG(d.tag, 2.0 * m_rows * d.N * d.Kc * d.taps * Z, 0.0);

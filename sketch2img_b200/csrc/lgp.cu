@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
                                                            const double* __restrict__ bsums, int train, long R, int N,
                                                            long rows, float qscale, __half* __restrict__ out) {
     const long total = rows * (N >> 1);
-    const float qinv = 1.f / qscale;
+    const float qinv = qscale != 0.f ? 1.f / qscale : 0.f;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const long row = idx / (N >> 1);
         const int c = (int)(idx - row * (N >> 1)) << 1;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
             } else {
                 g = gamma[c + j] * rstd[sc] * dd;
             }
-            g = __half2float(__float2half_rn(g * qinv)) * qscale;
+            if (qscale != 0.f) g = __half2float(__float2half_rn(g * qinv)) * qscale;
             o[j] = hh > 0.f ? g : 0.f;
         }
         *reinterpret_cast<__half2*>(out + row * N + c) = __floats2half2_rn(o[0], o[1]);
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
 
 // dOut (scaled, fp16-rounded in true units) of the MSE edge loss on the cond half; loss[s] accumulated.
 __global__ void __launch_bounds__(256) lgp_loss_kernel(const __half* __restrict__ out16, const float* __restrict__ target,
-                                                       int B, int L, int O, float inv_n, float gscale,
+                                                       int B, int L, int O, float inv_n, float gscale, int emulate,
                                                        __half* __restrict__ dout, float* __restrict__ loss) {
     const long rows = (long)B * L * L;
     const long hw = (long)L * L;
@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(256) lgp_loss_kernel(const __half* __restrict_
             for (int c = 0; c < O; ++c) {
                 const float diff = __half2float(out16[row * 8 + c]) - target[(s * O + c) * hw + pix];
                 acc += diff * diff;
-                const float g = __half2float(__float2half_rn(2.f * diff * inv_n));   // unscaled fp16 rounding
+                float g = 2.f * diff * inv_n;
+                if (emulate) g = __half2float(__float2half_rn(g));   // the reference's unscaled fp16 rounding
                 d8[c] = __float2half_rn(g * gscale);
             }
             atomicAdd(loss + s, acc * inv_n);
@@ -621,7 +622,9 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
     const long n_elem = (long)O_ * L_ * L_;
     gscale_ = exp2f(ceilf(log2f((float)n_elem)));
     S2I_CUDA(cudaMemsetAsync(loss, 0, S * sizeof(float), st));
-    lgp_loss_kernel<<<grid1d(rows), 256, 0, st>>>(out16_, target, B_, L_, O_, 1.f / (float)n_elem, gscale_, dout_, loss);
+    lgp_loss_kernel<<<grid1d(rows), 256, 0, st>>>(out16_, target, B_, L_, O_, 1.f / (float)n_elem, gscale_,
+                                                  emulate_fp16_grad ? 1 : 0, dout_, loss);
+    const float qs = emulate_fp16_grad ? gscale_ : 0.f;
     S2I_LAUNCH_CHECK();
 
     const __half* d = dout_;
@@ -636,7 +639,7 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
         g.A = d; g.aC = K; g.aW = (int)rows; g.a_sw = d_ld;
         g.B = lin_[l].wd; g.bI = K; g.bR = N; g.b_sr = (K + 7) / 8 * 8;
         g.N = N; g.Kc = K;
-        g.qscale = gscale_;
+        g.qscale = qs;
         __half* o = l == 0 ? X_ : bufs[flip];
         g.out16 = o; g.ld16 = l == 0 ? ldX_ : N;
         S2I_TRY(gemm_launch(g, st));
@@ -650,7 +653,7 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
         }
         __half* o2 = bufs[flip ^ 1];
         bn_bwd_apply_kernel<<<grid1d(rows * (N / 2)), 256, 0, st>>>(o, h_[bl], mean_[bl], rstd_[bl], bn_[bl].g, bbsum_[bl],
-                                                                    train_ ? 1 : 0, R, N, rows, gscale_, o2);
+                                                                    train_ ? 1 : 0, R, N, rows, qs, o2);
         S2I_LAUNCH_CHECK();
         d = o2;
         d_ld = N;

@@ -40,6 +40,9 @@ class LGP {
     int forward_nchw(const float* x, const float* t, int B, int L, bool train, cudaStream_t st);
 
     int input_dim() const { return D_; }
+    // true (default): gradients are rounded like the reference's unscaled fp16 autograd (latent_predictor.py:43 casts
+    // the activations to fp16, so torch back-propagates in fp16); false: loss-scaled gradients, no extra rounding.
+    bool emulate_fp16_grad = true;
 
   private:
     int D_, O_, P_;

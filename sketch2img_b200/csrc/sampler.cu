@@ -141,6 +141,12 @@ int s2i_lgp_load(s2i_lgp* l, int n, const char* const* names, const float* const
     return l->impl->load(collect(n, names, host_ptrs, ndims, shapes));
 }
 
+int s2i_lgp_set_grad_rounding(s2i_lgp* l, int emulate) {
+    if (!l) return s2i::set_error(S2I_ERR_ARG, "s2i_lgp_set_grad_rounding: null handle");
+    l->impl->emulate_fp16_grad = emulate != 0;
+    return 0;
+}
+
 int s2i_lgp_forward_taps(s2i_lgp* l, const float* const* taps, const int* sizes, const int* channels, int B, int L,
                          const float* noise, float sigma, int train, void* cuda_stream) {
     if (!l || !taps || !sizes || !channels || !noise) return s2i::set_error(S2I_ERR_ARG, "s2i_lgp_forward_taps: null argument");

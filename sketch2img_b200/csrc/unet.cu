@@ -479,6 +479,10 @@ int UNet::resblock(int idx, const F32& x, F32& out) {
     }
     out = new32(B, H, W, R.Cout);
     S2I_TRY(gemm(a2, true, 9, R.c2.w, 9L * R.Cout, R.Cout, R.Cout, R.c2.b, nullptr, &res, &out, nullptr));
+    if (keep_debug) {
+        debug["r" + std::to_string(idx) + ".h1"] = h1;
+        debug["r" + std::to_string(idx) + ".out"] = out;
+    }
     if (save_) {
         rsave_[idx].x = x;
         rsave_[idx].h1 = h1;
@@ -654,6 +658,14 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     S2I_TRY(gemm(g16, false, 1, T.ff2.w, 4 * C, C, 4 * C, T.ff2.b, nullptr, &sv.t2, nullptr, &t3));
     out = new32(B, H, W, C);
     S2I_TRY(gemm(t3, false, 1, T.proj_out.w, C, C, C, T.proj_out.b, nullptr, &x, &out, nullptr));
+    if (keep_debug) {
+        const std::string pre = "t" + std::to_string(idx);
+        debug[pre + ".t0"] = sv.t0;
+        debug[pre + ".t1"] = sv.t1;
+        debug[pre + ".t2"] = sv.t2;
+        debug[pre + ".ff"] = sv.ff;
+        debug[pre + ".out"] = out;
+    }
     if (save_) tsave_[idx] = sv;
     return 0;
 }

@@ -91,6 +91,10 @@ class LGPEngine:
     def handle(self):
         return self._h
 
+    def set_grad_rounding(self, emulate_fp16=True):
+        """True (default): mimic the reference's unscaled fp16 autograd rounding; False: loss-scaled gradients."""
+        _lib.check(self.lib.s2i_lgp_set_grad_rounding(self._h, int(bool(emulate_fp16))))
+
     def forward_nchw(self, x, t, B, L, train):
         _lib.check(self.lib.s2i_lgp_forward_nchw(self._h, x.data_ptr(), t.data_ptr(), B, L, int(train), _lib.stream_ptr()))
         return self.output(B, L, x.device)

@@ -163,3 +163,47 @@ def test_cross_attention_shapes(L, cuda):
     torch.cuda.synchronize()
     Oref = (P.double() @ vh).reshape(B, heads, N, dp).permute(0, 2, 1, 3).reshape(B, N, HP)
     assert rel(O.float(), Oref) < 3e-3
+
+
+@pytest.mark.parametrize("M,N,K,splits,BN", [(128, 1280, 2048, 8, 128), (512, 1280, 1280, 0, 0), (128, 320, 4096, 16, 64),
+                                             (100, 64, 1024, 4, 0), (128, 10240, 1280, 0, 0), (2048, 640, 640, 0, 0)])
+def test_split_k_linear(L, cuda, M, N, K, splits, BN):
+    """Small-M GEMMs (the 8x8 / 16x16 levels) split K across CTAs; the last CTA per tile reduces the partial tiles in
+    split order and applies the full epilogue (bias, residual, fp32 + fp16 stores)."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda).half()
+    w = (torch.randn(N, K, generator=g) * 0.05).to(cuda).half()
+    bias = torch.randn(N, generator=g).to(cuda)
+    res = torch.randn(M, N, generator=g).to(cuda)
+    ref = a.double() @ w.double().t() + bias.double() + res.double()
+    outs = []
+    for rep in range(3):            # the arrival counters reset themselves: repeated launches stay correct
+        out32 = torch.full((M, N), float("nan"), device=cuda)
+        out16 = torch.zeros(M, N, device=cuda, dtype=torch.float16)
+        d = L.GemmDesc(A=a.data_ptr(), aC=K, aW=M, a_sw=K, B=w.data_ptr(), bI=K, bR=N, b_sr=K, N=N, Kc=K, BN=BN,
+                       splits=splits, bias=bias.data_ptr(), residual=res.data_ptr(), res_ld=N,
+                       out32=out32.data_ptr(), ld32=N, out16=out16.data_ptr(), ld16=N)
+        L.gemm(d)
+        torch.cuda.synchronize()
+        assert rel(out32, ref) < 2e-3
+        assert rel(out16.float(), ref) < 3e-3
+        outs.append(out32.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])     # reduction order is fixed
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,splits", [(2, 8, 8, 1280, 1280, 0), (2, 16, 16, 640, 1280, 0), (2, 8, 8, 256, 64, 6)])
+def test_split_k_conv3x3(L, cuda, B, H, W, Cin, Cout, splits):
+    g = torch.Generator(device="cpu").manual_seed(B * 7 + Cin)
+    x = torch.randn(B, H, W, Cin, generator=g).to(cuda).half()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * 0.02).to(cuda).half()
+    bias = torch.randn(Cout, generator=g).to(cuda)
+    temb = torch.randn(Cout, generator=g).to(cuda)
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    out32 = torch.full((B, H, W, Cout), float("nan"), device=cuda)
+    d = L.GemmDesc(A=x.data_ptr(), aC=Cin, aW=W, aH=H, aB=B, a_sw=Cin, a_sh=Cin * W, a_sb=Cin * W * H, taps=9,
+                   B=wp.data_ptr(), bI=9 * Cin, bR=Cout, b_sr=9 * Cin, N=Cout, Kc=Cin, splits=splits, bias=bias.data_ptr(),
+                   rowvec=temb.data_ptr(), rowvec_ld=0, out32=out32.data_ptr(), ld32=Cout)
+    L.gemm(d)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double() + temb.double(), padding=1).permute(0, 2, 3, 1)
+    assert rel(out32, ref) < 2e-3
