@@ -56,6 +56,19 @@ int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream);
 
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused attention forward (tcgen05 + TMA; scores stay on chip): replaces the xformers / CrossAttention call inside
+ * the UNet (app.py:43, modules/pipeline.py:96) wherever the probabilities are not needed by a later backward.
+ *   out[b, i, h*dp .. h*dp+dp) = softmax_j(scale * <Q[b,i,h], K[b,j,h]>) V[b,j,h]
+ *   q : fp16 device [B][Nq][ldq], head h of Q at columns q_c0 + h*dp
+ *   kv: fp16 device [B][Nk][ldkv], head h of K at k_c0 + h*dp, of V at v_c0 + h*dp
+ *   dp = head dim padded to a multiple of 16 (padding columns zero); Nq >= 128, Nk >= 64
+ *   lse (optional): fp32 device [B*heads][Nq] = log-sum-exp of the scaled scores
+ * --------------------------------------------------------------------------------------------- */
+int s2i_attention(const void* q, long long ldq, int q_c0, const void* kv, long long ldkv, int k_c0, int v_c0, int B,
+                  int heads, int Nq, int Nk, int dp, int d_true, float scale, void* out, long long ldo, float* lse,
+                  void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------
  * UNet2DCondition engine: replaces `self.unet(x, t, encoder_hidden_states=...)` (modules/pipeline.py:96),
  * the 9 forward hooks of hook_unet (modules/latent_predictor.py:47-81) and the UNet part of
  * `torch.autograd.grad(loss, latents_prev)` (modules/pipeline.py:159).

@@ -1,8 +1,11 @@
 // extern "C" surface of libs2i (declarations: include/s2i.h).
 #include "../../include/s2i.h"
 #include "common.cuh"
+#include "attn.cuh"
 #include "gemm_tc.cuh"
 #include "unet.cuh"
+
+#include <cstdlib>
 
 struct s2i_unet {
     s2i::UNet* impl;
@@ -24,6 +27,19 @@ int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream) {
 }
 
 
+int s2i_attention(const void* q, long long ldq, int q_c0, const void* kv, long long ldkv, int k_c0, int v_c0, int B,
+                  int heads, int Nq, int Nk, int dp, int d_true, float scale, void* out, long long ldo, float* lse,
+                  void* cuda_stream) {
+    if (!q || !kv || !out) return s2i::set_error(S2I_ERR_ARG, "s2i_attention: null argument");
+    s2i::AttnDesc a;
+    a.q = static_cast<const __half*>(q); a.ldq = ldq; a.q_c0 = q_c0;
+    a.kv = static_cast<const __half*>(kv); a.ldkv = ldkv; a.k_c0 = k_c0; a.v_c0 = v_c0;
+    a.B = B; a.heads = heads; a.Nq = Nq; a.Nk = Nk; a.dp = dp; a.d_true = d_true;
+    a.scale = scale;
+    a.out = static_cast<__half*>(out); a.ldo = ldo; a.lse = lse;
+    return s2i::attn_fwd_launch(a, static_cast<cudaStream_t>(cuda_stream));
+}
+
 int s2i_unet_create(const s2i_unet_config* c, s2i_unet** out) {
     if (!c || !out) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_create: null argument");
     s2i::UNetConfig cfg;
@@ -41,6 +57,7 @@ int s2i_unet_create(const s2i_unet_config* c, s2i_unet** out) {
     cfg.ctx_len = c->ctx_len;
     if (cfg.cross_dim % 8 != 0) return s2i::set_error(S2I_ERR_ARG, "cross_attention_dim must be a multiple of 8");
     *out = new s2i_unet{new s2i::UNet(cfg)};
+    if (const char* e = getenv("S2I_NO_FLASH")) (*out)->impl->use_flash_ = !(e[0] == '1');
     return 0;
 }
 

@@ -1,0 +1,360 @@
+// Fused attention forward  O = softmax(scale * Q K^T) V  on tcgen05 + TMA (reference: the xformers /
+// diffusers CrossAttention call inside `self.unet(...)`, modules/pipeline.py:96, app.py:43).
+//
+// One CTA = one (batch, head, 128-query tile).  S = Q K_j^T lands in TMEM (128 lanes x 128 fp32 columns); four
+// softmax warps (one query row per thread) read it with tcgen05.ld, exponentiate, and write P as fp16 into shared
+// memory in the 128B-swizzled K-major layout the tensor core reads; O += P V_j accumulates in TMEM (V is the
+// MN-major B operand straight from its [tokens][channels] layout).  The scores never touch HBM.
+//
+// Two passes over the key tiles keep the accumulator free of rescaling: pass 1 computes the exact row maximum
+// (QK^T only -- the tensor pipe is otherwise idle: the kernel is exp-bound for SD's small head dims), pass 2
+// recomputes S, forms p = exp2((s - max) * scale * log2 e), the row sum, and O.  Final O / rowsum is written fp16.
+//
+//   warp 0      TMA producer (Q once, then K tiles for pass 1 and K+V tiles for pass 2 through a stage ring)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5  softmax + epilogue (TMEM lane quarter = warp & 3)
+#include "attn.cuh"
+
+#include <cudaTypedefs.h>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace s2i {
+
+int encode_tmap_f16(CUtensorMap* m, int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);   // gemm_tc.cu
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kTileQ = 128;
+constexpr int kTileK = 64;               // keys per tile: one 64-row TMA box serves as K (K-major) and V (MN-major)
+constexpr int kChunk16 = 128 * 64 * 2;   // 16 KB: 128 rows x 64 fp16 (one swizzle-128B K-major chunk of Q or P)
+constexpr int kChunk8 = 64 * 64 * 2;     // 8 KB: 64 rows x 64 fp16 (one chunk of a K or V tile)
+constexpr int kMaxStages = 4;
+
+struct __align__(64) AttnParams {
+    CUtensorMap mapQ, mapKV;
+    int Nq, Nk, heads, dp;
+    int q_c0, k_c0, v_c0;
+    int nkc;            // 64-wide chunks covering dp
+    int stages, pbufs, tmem_cols;
+    uint32_t idesc_s, idesc_o;
+    float scale_log2;   // softmax scale * log2(e)
+    float scale;
+    __half* out;
+    long ldo;
+    float* lse;         // optional [B*heads][Nq]: scale * max + ln(rowsum)
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int q_bytes = p.nkc * kChunk16;
+    const int k_bytes = p.nkc * kChunk8;
+    const int stage_bytes = 2 * k_bytes;          // K tile + V tile
+    uint8_t* sQ = smem;
+    uint8_t* sP = sQ + q_bytes;                   // pbufs x 16 KB
+    uint8_t* sKV = sP + p.pbufs * kChunk16;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + p.stages * stage_bytes);
+    uint64_t* q_full = bars;
+    uint64_t* o_full = bars + 1;
+    uint64_t* s_full = bars + 2;     // [2]
+    uint64_t* s_empty = bars + 4;    // [2]
+    uint64_t* p_full = bars + 6;     // [2]
+    uint64_t* p_empty = bars + 8;    // [2]
+    uint64_t* kv_full = bars + 10;   // [kMaxStages]
+    uint64_t* kv_empty = kv_full + kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + kMaxStages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kTileQ;
+    const int z = blockIdx.y;
+    const int b = z / p.heads, h = z - b * p.heads;
+    const int T = (p.Nk + kTileK - 1) / kTileK;      // key tiles
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&p.mapQ);
+        ptx::prefetch_tmap(&p.mapKV);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            ptx::mbar_init(q_full, 1);
+            ptx::mbar_init(o_full, 1);
+            for (int i = 0; i < 2; ++i) {
+                ptx::mbar_init(&s_full[i], 1);
+                ptx::mbar_init(&s_empty[i], 4);
+                ptx::mbar_init(&p_full[i], 4);
+                ptx::mbar_init(&p_empty[i], 1);
+            }
+            for (int s = 0; s < p.stages; ++s) {
+                ptx::mbar_init(&kv_full[s], 1);
+                ptx::mbar_init(&kv_empty[s], 1);
+            }
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_O = tmem_base + 128u;        // S buffers: columns [0,64) and [64,128)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            ptx::mbar_expect_tx(q_full, (uint32_t)q_bytes);
+            for (int c = 0; c < p.nkc; ++c)
+                ptx::tma_load_3d(sQ + c * kChunk16, &p.mapQ, q_full, p.q_c0 + h * p.dp + c * 64, q0, b);
+            for (int g = 0; g < 2 * T; ++g) {
+                const int j = g < T ? g : g - T;
+                const bool with_v = g >= T;
+                const int stage = g % p.stages;
+                const uint32_t phase = (g / p.stages) & 1;
+                ptx::mbar_wait(&kv_empty[stage], phase ^ 1);
+                ptx::mbar_expect_tx(&kv_full[stage], (uint32_t)(with_v ? stage_bytes : k_bytes));
+                uint8_t* sK = sKV + stage * stage_bytes;
+                uint8_t* sV = sK + k_bytes;
+                for (int c = 0; c < p.nkc; ++c)
+                    ptx::tma_load_3d(sK + c * kChunk8, &p.mapKV, &kv_full[stage], p.k_c0 + h * p.dp + c * 64, j * kTileK, b);
+                if (with_v)
+                    for (int c = 0; c < p.nkc; ++c)
+                        ptx::tma_load_3d(sV + c * kChunk8, &p.mapKV, &kv_full[stage], p.v_c0 + h * p.dp + c * 64,
+                                         j * kTileK, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer
+            const int nks = p.dp >> 4;             // K steps of the QK^T product
+            const uint32_t aQ = ptx::smem_u32(sQ);
+            // S[g & 1] = Q K_g^T once the tile has landed and the softmax warps have drained that S buffer
+            auto issue_S = [&](int g) {
+                const int stage = g % p.stages;
+                ptx::mbar_wait(&kv_full[stage], (g / p.stages) & 1);
+                ptx::mbar_wait(&s_empty[g & 1], ((g >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t aK = ptx::smem_u32(sKV + stage * stage_bytes);
+                const uint32_t tS = tmem_base + (uint32_t)(g & 1) * 64u;
+                for (int k = 0; k < nks; ++k) {
+                    const uint32_t kq = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3) * 32u;
+                    ptx::umma_f16(tS, ptx::make_smem_desc_sw128(aQ + kq * kChunk16 + ks, 16u, 1024u),
+                                  ptx::make_smem_desc_sw128(aK + kq * kChunk8 + ks, 16u, 1024u), p.idesc_s,
+                                  k != 0 ? 1u : 0u);
+                }
+            };
+            ptx::mbar_wait(q_full, 0);
+            // pass 1: row maxima (the issuer may run two tiles ahead of the softmax warps)
+            for (int g = 0; g < T; ++g) {
+                issue_S(g);
+                ptx::umma_commit(&kv_empty[g % p.stages]);
+                ptx::umma_commit(&s_full[g & 1]);
+            }
+            // pass 2: probabilities and output; S_{j+1} is issued before P_j V_j so the softmax warps never starve
+            issue_S(T);
+            ptx::umma_commit(&s_full[T & 1]);
+            for (int j = 0; j < T; ++j) {
+                const int g = T + j;
+                if (j + 1 < T) {
+                    issue_S(g + 1);
+                    ptx::umma_commit(&s_full[(g + 1) & 1]);
+                }
+                ptx::mbar_wait(&p_full[j % p.pbufs], (j / p.pbufs) & 1);
+                ptx::tc_fence_after();
+                const int stage = g % p.stages;
+                const uint32_t aV = ptx::smem_u32(sKV + stage * stage_bytes + k_bytes);
+                const uint32_t aP = ptx::smem_u32(sP + (j % p.pbufs) * kChunk16);
+                for (int kk = 0; kk < 4; ++kk) {
+                    ptx::umma_f16(tmem_O, ptx::make_smem_desc_sw128(aP + (uint32_t)kk * 32u, 16u, 1024u),
+                                  ptx::make_smem_desc_sw128(aV + (uint32_t)kk * 2048u, (uint32_t)kChunk8, 1024u),
+                                  p.idesc_o, (j | kk) != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(&kv_empty[stage]);
+                ptx::umma_commit(&p_empty[j % p.pbufs]);
+            }
+            ptx::umma_commit(o_full);
+        }
+    } else {
+        // ---------------------------------------------------- softmax + epilogue (one query row per thread)
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const bool row_ok = (q0 + r) < p.Nq;
+        float m = -INFINITY;
+        // pass 1
+        for (int g = 0; g < T; ++g) {
+            ptx::mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+            ptx::tc_fence_after();
+            const int kvalid = p.Nk - g * kTileK;      // columns >= kvalid are padding
+            const uint32_t tS = tmem_base + (uint32_t)(g & 1) * 64u + lane_addr;
+#pragma unroll
+            for (int c = 0; c < kTileK; c += 32) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(tS + (uint32_t)c, raw);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c + i < kvalid) m = fmaxf(m, __uint_as_float(raw[i]));
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&s_empty[g & 1]);
+        }
+        const float mneg = (m == -INFINITY) ? 0.f : -m * p.scale_log2;
+        float l = 0.f;
+        // pass 2
+        for (int j = 0; j < T; ++j) {
+            const int g = T + j;
+            ptx::mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t tS = tmem_base + (uint32_t)(g & 1) * 64u + lane_addr;
+            uint32_t s[kTileK];
+#pragma unroll
+            for (int c = 0; c < kTileK; c += 32) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(tS + (uint32_t)c, raw);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) s[c + i] = raw[i];
+            }
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&s_empty[g & 1]);     // S is in registers: TMEM buffer may be overwritten
+
+            const int kvalid = p.Nk - j * kTileK;
+            uint32_t pk[kTileK / 2];
+#pragma unroll
+            for (int i = 0; i < kTileK; i += 2) {
+                float e0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, mneg));
+                float e1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, mneg));
+                if (i >= kvalid) e0 = 0.f;
+                if (i + 1 >= kvalid) e1 = 0.f;
+                const __half2 h2 = __floats2half2_rn(e0, e1);
+                const float2 back = __half22float2(h2);       // the row sum uses what the tensor core multiplies
+                l += back.x + back.y;
+                pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            const int pb = j % p.pbufs;
+            ptx::mbar_wait(&p_empty[pb], ((j / p.pbufs) & 1) ^ 1);    // the P V product that read this buffer is done
+            // row r of the K-major swizzled tile: 16-byte unit u lives at r * 128 + ((u ^ (r & 7)) * 16)
+            uint8_t* prow = sP + pb * kChunk16 + r * 128;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                *reinterpret_cast<uint4*>(prow + ((u ^ (r & 7)) << 4)) =
+                    make_uint4(pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
+            ptx::fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&p_full[pb]);
+        }
+        // epilogue: O / rowsum -> fp16
+        ptx::mbar_wait(o_full, 0);
+        ptx::tc_fence_after();
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        __half* orow = p.out + ((long)b * p.Nq + q0 + r) * p.ldo + h * p.dp;
+        for (int c = 0; c < p.dp; c += 16) {
+            uint32_t raw[16];
+            ptx::tmem_ld_32x16(tmem_O + lane_addr + (uint32_t)c, raw);
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+                uint32_t o[8];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const __half2 h2 = __floats2half2_rn(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv);
+                    o[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                *reinterpret_cast<uint4*>(orow + c) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+        }
+        if (p.lse && row_ok) p.lse[(long)z * p.Nq + q0 + r] = m * p.scale + logf(l);
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace
+
+bool attn_fwd_supported(int Nq, int Nk, int dp) {
+    return Nq >= kTileQ && Nk >= kTileK && dp % 16 == 0 && dp >= 16 && dp <= 256;   // TMA boxes never exceed the tensor
+}
+
+int attn_fwd_launch(const AttnDesc& d, cudaStream_t stream) {
+    if (!attn_fwd_supported(d.Nq, d.Nk, d.dp)) return set_error(S2I_ERR_ARG, "attn_fwd: unsupported shape Nq=%d Nk=%d dp=%d", d.Nq, d.Nk, d.dp);
+    if ((d.ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(d.out) & 15) != 0 || (d.dp % 8) != 0)
+        return set_error(S2I_ERR_ARG, "attn_fwd: output must be 16-byte aligned per head");
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.Nq = d.Nq; p.Nk = d.Nk; p.heads = d.heads; p.dp = d.dp;
+    p.q_c0 = d.q_c0; p.k_c0 = d.k_c0; p.v_c0 = d.v_c0;
+    p.nkc = (d.dp + 63) / 64;
+    p.scale = d.scale;
+    p.scale_log2 = d.scale * 1.4426950408889634f;
+    p.out = d.out; p.ldo = d.ldo; p.lse = d.lse;
+    p.idesc_s = ptx::make_idesc_f16(128, kTileK, 0, 0, 0);
+    p.idesc_o = ptx::make_idesc_f16(128, (uint32_t)d.dp, 0, 0, 1);
+    p.tmem_cols = (128 + d.dp) <= 256 ? 256 : 512;
+
+    // shared memory: Q | P buffers | (K tile + V tile) stages | barriers.  Prefer a footprint that lets two CTAs share
+    // an SM (the kernel is exp- and latency-bound for SD's head dims: a second CTA fills the handshake bubbles).
+    const int q_bytes = p.nkc * kChunk16, stage_bytes = 2 * p.nkc * kChunk8;
+    const int overhead = 256 + 1024;     // barriers + alignment slack
+    const int half_sm = 113 * 1024, full_sm = 226 * 1024;
+    int pbufs = 0, stages = 0;
+    const int tries[4][2] = {{2, 3}, {2, 2}, {1, 2}, {0, 0}};
+    for (int i = 0; tries[i][0]; ++i) {
+        if (q_bytes + tries[i][0] * kChunk16 + tries[i][1] * stage_bytes + overhead <= half_sm) {
+            pbufs = tries[i][0];
+            stages = tries[i][1];
+            break;
+        }
+    }
+    if (!pbufs) {
+        pbufs = 2;
+        stages = (full_sm - overhead - q_bytes - pbufs * kChunk16) / stage_bytes;
+        if (stages > kMaxStages) stages = kMaxStages;
+        if (stages < 2) return set_error(S2I_ERR_ARG, "attn_fwd: head dim %d does not fit shared memory", d.dp);
+    }
+    p.stages = stages;
+    p.pbufs = pbufs;
+    const size_t smem_bytes = (size_t)q_bytes + (size_t)pbufs * kChunk16 + (size_t)stages * stage_bytes + overhead;
+
+    {
+        uint64_t dims[3] = {(uint64_t)d.ldq, (uint64_t)d.Nq, (uint64_t)d.B};
+        uint64_t str[2] = {(uint64_t)d.ldq * 2, (uint64_t)d.Nq * d.ldq * 2};
+        uint32_t box[3] = {64, (uint32_t)kTileQ, 1};
+        S2I_TRY(encode_tmap_f16(&p.mapQ, 3, d.q, dims, str, box));
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)d.ldkv, (uint64_t)d.Nk, (uint64_t)d.B};
+        uint64_t str[2] = {(uint64_t)d.ldkv * 2, (uint64_t)d.Nk * d.ldkv * 2};
+        uint32_t box[3] = {64, (uint32_t)kTileK, 1};
+        S2I_TRY(encode_tmap_f16(&p.mapKV, 3, d.kv, dims, str, box));
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        S2I_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((d.Nq + kTileQ - 1) / kTileQ), (unsigned)(d.B * d.heads), 1);
+    attn_fwd_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+    // algorithmic work: QK^T + PV at the true head dim
+    S2I_LAUNCH_CHECK_TAG("attn_fwd", 4.0 * d.B * d.heads * (double)d.Nq * d.Nk * d.d_true, 0.0);
+    return 0;
+}
+
+}  // namespace s2i

@@ -512,6 +512,11 @@ int ensure_ws() {
 
 }  // namespace
 
+int encode_tmap_f16(CUtensorMap* m, int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+    return encode_map(m, 0, rank, ptr, dims, strides_bytes, box);
+}
+
 long g_launches = 0;
 long gemm_launch_count() { return g_launches; }
 

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "attn.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
@@ -525,8 +526,21 @@ int UNet::resblock_bwd(int idx, const F32& dout, F32& dx) {
 // ================================================================================================== attention
 // q: [B*Nq][q.ld] with this attention's Q heads at column q_c0; kv: [B*Nk][kv.ld] with K heads at k_c0, V at v_c0.
 int UNet::attention(const Transformer& T, const H16& q, long q_c0, const H16& kv, long k_c0, long v_c0, int Nk, H16& P,
-                    H16& o) {
+                    H16& o, bool need_P) {
     const int B = q.B, Nq = q.H * q.W, Z = B * T.heads;
+    if (!need_P && use_flash_ && attn_fwd_supported(Nq, Nk, T.dp)) {
+        // fused path: the scores stay in TMEM / shared memory (no backward will ask for P)
+        P = H16();
+        o = new16(q.B, q.H, q.W, T.HP);
+        if (dry_) return 0;
+        AttnDesc a;
+        a.q = q.p; a.ldq = q.ld; a.q_c0 = (int)q_c0;
+        a.kv = kv.p; a.ldkv = kv.ld; a.k_c0 = (int)k_c0; a.v_c0 = (int)v_c0;
+        a.B = B; a.heads = T.heads; a.Nq = Nq; a.Nk = Nk; a.dp = T.dp; a.d_true = T.d;
+        a.scale = 1.f / sqrtf((float)T.d);
+        a.out = o.p; a.ldo = o.ld;
+        return attn_fwd_launch(a, st_);
+    }
     const long ldS = rup(Nk, 4), ldP = rup(Nk, 8);
     float* S = dalloc<float>((size_t)Z * Nq * ldS);
     P = H16();
@@ -629,8 +643,10 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     RUN(ln_fwd(sv.t0.p, sv.t0.ld, rows, C, T.ln1.g, T.ln1.b, T.ln1.eps, l16.p, l16.ld, sv.l1, st_));
     sv.qkv = new16(B, H, W, 3 * T.HP);
     S2I_TRY(gemm(l16, false, 1, T.qkv.w, C, 3 * T.HP, C, nullptr, nullptr, nullptr, nullptr, &sv.qkv));
+    // P is only kept for the input-gradient pass, and up_blocks[3] (the last layers+1 transformers) is not on it
+    const bool need_P = save_ && idx < (int)tfm_.size() - (cfg.layers + 1);
     H16 o1;
-    S2I_TRY(attention(T, sv.qkv, 0, sv.qkv, T.HP, 2L * T.HP, HW, sv.P1, o1));
+    S2I_TRY(attention(T, sv.qkv, 0, sv.qkv, T.HP, 2L * T.HP, HW, sv.P1, o1, need_P));
     sv.t1 = new32(B, H, W, C);
     S2I_TRY(gemm(o1, false, 1, T.o1.w, T.HP, C, T.HP, T.o1.b, nullptr, &sv.t0, &sv.t1, nullptr));
     // --- cross attention (K/V from the text context)
@@ -643,7 +659,7 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     S2I_TRY(gemm(ctx16_, false, 1, T.kv2.w, cfg.cross_dim, 2 * T.HP, cfg.cross_dim, nullptr, nullptr, nullptr, nullptr,
                  &sv.kv2));
     H16 o2;
-    S2I_TRY(attention(T, sv.q2, 0, sv.kv2, 0, T.HP, cfg.ctx_len, sv.P2, o2));
+    S2I_TRY(attention(T, sv.q2, 0, sv.kv2, 0, T.HP, cfg.ctx_len, sv.P2, o2, need_P));
     sv.t2 = new32(B, H, W, C);
     S2I_TRY(gemm(o2, false, 1, T.o2.w, T.HP, C, T.HP, T.o2.b, nullptr, &sv.t1, &sv.t2, nullptr));
     // --- GEGLU feed-forward

@@ -127,6 +127,7 @@ class UNet {
     // Named intermediates of the last forward (debugging / parity bisecting).
     std::map<std::string, F32> debug;
     bool keep_debug = false;
+    bool use_flash_ = true;   // fused attention forward wherever P is not needed afterwards (S2I_NO_FLASH=1 disables)
 
     size_t arena_bytes() const { return arena_.cap; }
 
@@ -178,7 +179,7 @@ class UNet {
     int transformer(int idx, const F32& x, F32& out);
     int transformer_bwd(int idx, const F32& dout, F32& dx);
     int attention(const Transformer& T, const H16& q, long q_c0, const H16& kv, long k_c0, long v_c0, int Nk, H16& P,
-                  H16& o);
+                  H16& o, bool need_P);
     int attention_bwd(const Transformer& T, const H16& dO, const H16& q, long q_c0, const H16& kv, long k_c0, long v_c0,
                       int Nk, const H16& P, H16& dq, long dq_c0, H16* dkv, long dk_c0, long dv_c0);
     int accumulate(F32& acc, const F32& g);
