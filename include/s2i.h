@@ -53,6 +53,9 @@ typedef struct s2i_gemm_desc {
 } s2i_gemm_desc;
 
 int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream);
+/* Bisecting / A-B switch (no reference counterpart): 1 (default) = eligible GEMMs run gemm_tma_kernel (residual tile in,
+ * result tiles out through cp.async.bulk.tensor), 0 = every GEMM runs gemm_tc_kernel (per-thread epilogue). */
+int s2i_gemm_set_tma_epilogue(int on);
 
 
 /* ---------------------------------------------------------------------------------------------
@@ -67,6 +70,18 @@ int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream);
 int s2i_attention(const void* q, long long ldq, int q_c0, const void* kv, long long ldkv, int k_c0, int v_c0, int B,
                   int heads, int Nq, int Nk, int dp, int d_true, float scale, void* out, long long ldo, float* lse,
                   void* cuda_stream);
+
+/* Fused attention backward (tcgen05 + TMA; scores / probabilities recomputed on chip from the forward's log-sum-exp):
+ * the attention part of `torch.autograd.grad(loss, latents_prev)` (modules/pipeline.py:159).
+ *   d_out, out: fp16 device [B][Nq][ldo] (gradient of / value of the forward output), head h at columns h*dp
+ *   lse: the forward's log-sum-exp; delta_scratch: fp32 device [B*heads][Nq]
+ *   dq : fp16 device [B][Nq][lddq], head h at dq_c0 + h*dp
+ *   dkv: fp16 device [B][Nk][lddkv] or NULL (cross-attention to a constant context: only dQ); dK heads at dk_c0 + h*dp,
+ *        dV heads at dv_c0 + h*dp.   Nq >= 128, Nk >= 64, dp a multiple of 16 and <= 128. */
+int s2i_attention_backward(const void* q, long long ldq, int q_c0, const void* kv, long long ldkv, int k_c0, int v_c0,
+                           const void* d_out, const void* out, long long ldo, const float* lse, float* delta_scratch, int B,
+                           int heads, int Nq, int Nk, int dp, int d_true, float scale, void* dq, long long lddq, int dq_c0,
+                           void* dkv, long long lddkv, int dk_c0, int dv_c0, void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------
  * UNet2DCondition engine: replaces `self.unet(x, t, encoder_hidden_states=...)` (modules/pipeline.py:96),

@@ -61,9 +61,13 @@ def lib():
     h.s2i_profile_end.argtypes = [C.c_char_p, C.c_int]
     h.s2i_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     h.s2i_gemm.restype = C.c_int
+    h.s2i_gemm_set_tma_epilogue.argtypes = [C.c_int]
     vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_void_p)
     h.s2i_attention.argtypes = [vp, C.c_longlong, C.c_int, vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_longlong, vp, vp]
+    h.s2i_attention_backward.argtypes = [vp, C.c_longlong, C.c_int, vp, C.c_longlong, C.c_int, C.c_int, vp, vp, C.c_longlong,
+                                         vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp,
+                                         C.c_longlong, C.c_int, vp, C.c_longlong, C.c_int, C.c_int, vp]
     h.s2i_unet_create.argtypes = [C.POINTER(UNetConfig), C.POINTER(vp)]
     h.s2i_unet_destroy.argtypes = [vp]
     h.s2i_unet_destroy.restype = None

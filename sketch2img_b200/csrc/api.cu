@@ -21,6 +21,11 @@ int s2i_profile_end(char* report, int capacity) {
     return s2i::prof_end(report, capacity);
 }
 
+int s2i_gemm_set_tma_epilogue(int on) {
+    s2i::gemm_set_tma_epilogue(on);
+    return 0;
+}
+
 int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream) {
     if (!d) return s2i::set_error(S2I_ERR_ARG, "s2i_gemm: null descriptor");
     return s2i::gemm_launch(s2i::GemmDesc(*d), static_cast<cudaStream_t>(cuda_stream));
@@ -38,6 +43,24 @@ int s2i_attention(const void* q, long long ldq, int q_c0, const void* kv, long l
     a.scale = scale;
     a.out = static_cast<__half*>(out); a.ldo = ldo; a.lse = lse;
     return s2i::attn_fwd_launch(a, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int s2i_attention_backward(const void* q, long long ldq, int q_c0, const void* kv, long long ldkv, int k_c0, int v_c0,
+                           const void* d_out, const void* out, long long ldo, const float* lse, float* delta_scratch, int B,
+                           int heads, int Nq, int Nk, int dp, int d_true, float scale, void* dq, long long lddq, int dq_c0,
+                           void* dkv, long long lddkv, int dk_c0, int dv_c0, void* cuda_stream) {
+    if (!q || !kv || !d_out || !out || !lse || !delta_scratch || !dq)
+        return s2i::set_error(S2I_ERR_ARG, "s2i_attention_backward: null argument");
+    s2i::AttnBwdDesc a;
+    a.q = static_cast<const __half*>(q); a.ldq = ldq; a.q_c0 = q_c0;
+    a.kv = static_cast<const __half*>(kv); a.ldkv = ldkv; a.k_c0 = k_c0; a.v_c0 = v_c0;
+    a.dO = static_cast<const __half*>(d_out); a.lddo = ldo;
+    a.o = static_cast<const __half*>(out); a.ldo = ldo;
+    a.lse = lse; a.delta = delta_scratch;
+    a.B = B; a.heads = heads; a.Nq = Nq; a.Nk = Nk; a.dp = dp; a.d_true = d_true; a.scale = scale;
+    a.dq = static_cast<__half*>(dq); a.lddq = lddq; a.dq_c0 = dq_c0;
+    a.dk = a.dv = static_cast<__half*>(dkv); a.lddkv = lddkv; a.dk_c0 = dk_c0; a.dv_c0 = dv_c0;
+    return s2i::attn_bwd_launch(a, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int s2i_unet_create(const s2i_unet_config* c, s2i_unet** out) {

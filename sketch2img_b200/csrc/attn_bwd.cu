@@ -1,0 +1,412 @@
+// Fused attention backward on tcgen05 + TMA: dQ, dK, dV from (Q, K, V, dO, log-sum-exp, delta) with the scores and
+// probabilities RECOMPUTED on chip -- nothing of size Nq x Nk touches HBM.  Replaces, for the UNet's attention blocks,
+// the part of `torch.autograd.grad(loss, latents_prev)` (modules/pipeline.py:159) that flows through
+// softmax(scale Q K^T) V of diffusers' CrossAttention (app.py:43 / SURVEY A.4).
+//
+// One kernel, two modes; a CTA owns 128 "row" tokens and streams 64-token "column" tiles:
+//   MODE_DQ   rows = queries (Q_i, dO_i resident), columns = keys   (K_j, V_j streamed):
+//             S = Q K^T, dP = dO V^T, P = exp(scale S - lse_row), dS = scale P (dP - delta_row);  dQ_i += dS K_j
+//   MODE_DKV  rows = keys    (K_j, V_j resident), columns = queries (Q_i, dO_i streamed):
+//             S^T = K Q^T, dP^T = V dO^T, P^T = exp(scale S^T - lse_col), dS^T likewise;  dV_j += P^T dO_i, dK_j += dS^T Q_i
+// Both products of a tile land in TMEM (2 x 64 fp32 columns each, double buffered); four softmax warps (one row per
+// thread) turn them into fp16 P / dS tiles in 128B-swizzled shared memory, which the tensor core reads back as the
+// A operand of the accumulating products (accumulators: TMEM columns 256.., fp32).
+//   warp 0      TMA producer      warp 1  TMEM allocator + tcgen05.mma issuer      warps 2..5  softmax + epilogue
+#include "attn.cuh"
+
+#include <cudaTypedefs.h>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace s2i {
+
+int encode_tmap_f16(CUtensorMap* m, int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);   // gemm_tc.cu
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kRows = 128;               // resident ("row") tokens per CTA
+constexpr int kCols = 64;                // streamed ("column") tokens per tile
+constexpr int kChunk16 = 128 * 64 * 2;   // 16 KB: 128 rows x 64 fp16 (one swizzle-128B K-major chunk)
+constexpr int kChunk8 = 64 * 64 * 2;     //  8 KB:  64 rows x 64 fp16
+constexpr int kStages = 2;
+
+struct __align__(64) BwdParams {
+    CUtensorMap mapR1, mapR2, mapC1, mapC2;   // resident (box 64 x 128) and streamed (box 64 x 64) operands
+    int mode;                                 // 0 = dQ, 1 = dK/dV
+    int Nrow, Ncol, heads, dp, nkc;
+    int r1_c0, r2_c0, c1_c0, c2_c0;           // column of head 0 in each operand tensor
+    int sbufs;                                // staging buffers per staged matrix (1 or 2)
+    uint32_t idesc_t, idesc_acc;
+    float scale, scale_log2;
+    const float* lse;                         // [B*heads][Nq]
+    const float* delta;                       // [B*heads][Nq]
+    int Nq;
+    __half* out0; long ld0; int o0_c0;        // dQ (mode 0) or dV (mode 1)
+    __half* out1; long ld1; int o1_c0;        // dK (mode 1)
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) attn_bwd_kernel(const __grid_constant__ BwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int r_bytes = p.nkc * kChunk16;          // one resident operand tile
+    const int c_bytes = p.nkc * kChunk8;           // one streamed operand tile
+    const int stage_bytes = 2 * c_bytes;
+    const int nstaged = p.mode ? 2 : 1;            // staged A operands per tile: dS (mode 0); P^T and dS^T (mode 1)
+    uint8_t* sR1 = smem;
+    uint8_t* sR2 = sR1 + r_bytes;
+    uint8_t* sSt = sR2 + r_bytes;                  // [sbufs][nstaged] x 16 KB
+    uint8_t* sC = sSt + p.sbufs * nstaged * kChunk16;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sC + kStages * stage_bytes);
+    uint64_t* r_full = bars;            // resident operands landed
+    uint64_t* acc_full = bars + 1;      // accumulators complete
+    uint64_t* t_full = bars + 2;        // [2] both tile products complete
+    uint64_t* t_empty = bars + 4;       // [2] softmax warps drained the TMEM tile buffers
+    uint64_t* st_full = bars + 6;       // [2] staging written
+    uint64_t* st_empty = bars + 8;      // [2] accumulating MMAs done with the staging buffer
+    uint64_t* c_full = bars + 10;       // [kStages]
+    uint64_t* c_empty = bars + 12;      // [kStages]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    float* sStat = reinterpret_cast<float*>(bars + 16);   // mode 1: [2][2][64] per-column (lse*log2e, delta)
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * kRows;
+    const int z = blockIdx.y;
+    const int b = z / p.heads, h = z - b * p.heads;
+    const int T = (p.Ncol + kCols - 1) / kCols;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&p.mapR1);
+        ptx::prefetch_tmap(&p.mapR2);
+        ptx::prefetch_tmap(&p.mapC1);
+        ptx::prefetch_tmap(&p.mapC2);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            ptx::mbar_init(r_full, 1);
+            ptx::mbar_init(acc_full, 1);
+            for (int i = 0; i < 2; ++i) {
+                ptx::mbar_init(&t_full[i], 1);
+                ptx::mbar_init(&t_empty[i], 4);
+                ptx::mbar_init(&st_full[i], 4);
+                ptx::mbar_init(&st_empty[i], 1);
+            }
+            for (int s = 0; s < kStages; ++s) {
+                ptx::mbar_init(&c_full[s], 1);
+                ptx::mbar_init(&c_empty[s], 1);
+            }
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_acc0 = tmem_base + 256u;
+    const uint32_t tmem_acc1 = tmem_acc0 + (uint32_t)p.dp;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            ptx::mbar_expect_tx(r_full, (uint32_t)(2 * r_bytes));
+            for (int c = 0; c < p.nkc; ++c) {
+                ptx::tma_load_3d(sR1 + c * kChunk16, &p.mapR1, r_full, p.r1_c0 + h * p.dp + c * 64, row0, b);
+                ptx::tma_load_3d(sR2 + c * kChunk16, &p.mapR2, r_full, p.r2_c0 + h * p.dp + c * 64, row0, b);
+            }
+            for (int j = 0; j < T; ++j) {
+                const int stage = j % kStages;
+                ptx::mbar_wait(&c_empty[stage], ((j / kStages) & 1) ^ 1);
+                ptx::mbar_expect_tx(&c_full[stage], (uint32_t)stage_bytes);
+                uint8_t* s1 = sC + stage * stage_bytes;
+                uint8_t* s2 = s1 + c_bytes;
+                for (int c = 0; c < p.nkc; ++c) {
+                    ptx::tma_load_3d(s1 + c * kChunk8, &p.mapC1, &c_full[stage], p.c1_c0 + h * p.dp + c * 64, j * kCols, b);
+                    ptx::tma_load_3d(s2 + c * kChunk8, &p.mapC2, &c_full[stage], p.c2_c0 + h * p.dp + c * 64, j * kCols, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer
+            const int nks = p.dp >> 4;
+            const uint32_t aR1 = ptx::smem_u32(sR1), aR2 = ptx::smem_u32(sR2);
+            // T1[g&1] = R1 C1_g^T, T2[g&1] = R2 C2_g^T
+            auto issue_T = [&](int g) {
+                const int stage = g % kStages;
+                ptx::mbar_wait(&c_full[stage], (g / kStages) & 1);
+                ptx::mbar_wait(&t_empty[g & 1], ((g >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t aC1 = ptx::smem_u32(sC + stage * stage_bytes);
+                const uint32_t aC2 = aC1 + (uint32_t)c_bytes;
+                const uint32_t t1 = tmem_base + (uint32_t)(g & 1) * 64u;
+                const uint32_t t2 = tmem_base + 128u + (uint32_t)(g & 1) * 64u;
+                for (int k = 0; k < nks; ++k) {
+                    const uint32_t kq = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3) * 32u;
+                    ptx::umma_f16(t1, ptx::make_smem_desc_sw128(aR1 + kq * kChunk16 + ks, 16u, 1024u),
+                                  ptx::make_smem_desc_sw128(aC1 + kq * kChunk8 + ks, 16u, 1024u), p.idesc_t, k != 0 ? 1u : 0u);
+                }
+                for (int k = 0; k < nks; ++k) {
+                    const uint32_t kq = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3) * 32u;
+                    ptx::umma_f16(t2, ptx::make_smem_desc_sw128(aR2 + kq * kChunk16 + ks, 16u, 1024u),
+                                  ptx::make_smem_desc_sw128(aC2 + kq * kChunk8 + ks, 16u, 1024u), p.idesc_t, k != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(&t_full[g & 1]);
+            };
+            ptx::mbar_wait(r_full, 0);
+            issue_T(0);
+            for (int j = 0; j < T; ++j) {
+                if (j + 1 < T) issue_T(j + 1);      // keep the softmax warps fed while tile j's staging is produced
+                const int sb = j % p.sbufs;
+                ptx::mbar_wait(&st_full[sb], (j / p.sbufs) & 1);
+                ptx::tc_fence_after();
+                const int stage = j % kStages;
+                const uint32_t aC1 = ptx::smem_u32(sC + stage * stage_bytes);
+                const uint32_t aC2 = aC1 + (uint32_t)c_bytes;
+                const uint32_t aSt = ptx::smem_u32(sSt + sb * nstaged * kChunk16);
+                if (p.mode == 0) {
+                    // dQ += dS K_j   (B = K_j read MN-major: N = head channels, K = keys)
+                    for (int kk = 0; kk < 4; ++kk)
+                        ptx::umma_f16(tmem_acc0, ptx::make_smem_desc_sw128(aSt + (uint32_t)kk * 32u, 16u, 1024u),
+                                      ptx::make_smem_desc_sw128(aC1 + (uint32_t)kk * 2048u, (uint32_t)kChunk8, 1024u),
+                                      p.idesc_acc, (j | kk) != 0 ? 1u : 0u);
+                } else {
+                    // dV += P^T dO_i ; dK += dS^T Q_i
+                    for (int kk = 0; kk < 4; ++kk)
+                        ptx::umma_f16(tmem_acc0, ptx::make_smem_desc_sw128(aSt + (uint32_t)kk * 32u, 16u, 1024u),
+                                      ptx::make_smem_desc_sw128(aC2 + (uint32_t)kk * 2048u, (uint32_t)kChunk8, 1024u),
+                                      p.idesc_acc, (j | kk) != 0 ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk)
+                        ptx::umma_f16(tmem_acc1, ptx::make_smem_desc_sw128(aSt + kChunk16 + (uint32_t)kk * 32u, 16u, 1024u),
+                                      ptx::make_smem_desc_sw128(aC1 + (uint32_t)kk * 2048u, (uint32_t)kChunk8, 1024u),
+                                      p.idesc_acc, (j | kk) != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(&c_empty[stage]);
+                ptx::umma_commit(&st_empty[sb]);
+            }
+            ptx::umma_commit(acc_full);
+        }
+    } else {
+        // ---------------------------------------------------- softmax warps: thread <-> row token
+        const int e = threadIdx.x - 64;
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const bool row_ok = (row0 + r) < p.Nrow;
+        const float kLog2e = 1.4426950408889634f;
+        float lse_r = 0.f, delta_r = 0.f;
+        if (p.mode == 0 && row_ok) {
+            lse_r = p.lse[(long)z * p.Nq + row0 + r] * kLog2e;
+            delta_r = p.delta[(long)z * p.Nq + row0 + r];
+        }
+        for (int j = 0; j < T; ++j) {
+            const int col0 = j * kCols;
+            if (p.mode == 1) {
+                // per-column statistics of this query tile -> shared memory (double buffered by tile parity)
+                float* st = sStat + (j & 1) * 128;
+                const int c = e & 63;
+                const bool ok = (col0 + c) < p.Ncol;
+                const long idx = (long)z * p.Nq + col0 + c;
+                st[e] = ok ? (e < 64 ? p.lse[idx] * kLog2e : p.delta[idx]) : 0.f;
+                ptx::named_bar_sync(1, 128);
+            }
+            ptx::mbar_wait(&t_full[j & 1], (j >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t t1 = tmem_base + (uint32_t)(j & 1) * 64u + lane_addr;
+            const uint32_t t2 = t1 + 128u;
+            const int nvalid = p.Ncol - col0;          // columns >= nvalid are padding
+            const float* stl = sStat + (j & 1) * 128;
+            const int sb = j % p.sbufs;
+            ptx::mbar_wait(&st_empty[sb], ((j / p.sbufs) & 1) ^ 1);   // the MMAs that read this staging buffer are done
+            // K-major 128B-swizzled tile: 16-byte unit u of row r lives at r * 128 + ((u ^ (r & 7)) * 16)
+            uint8_t* st0 = sSt + sb * nstaged * kChunk16 + r * 128;
+#pragma unroll
+            for (int c0 = 0; c0 < kCols; c0 += 32) {
+                uint32_t s[32], d[32];
+                ptx::tmem_ld_32x32(t1 + (uint32_t)c0, s);
+                ptx::tmem_ld_32x32(t2 + (uint32_t)c0, d);
+                ptx::tmem_ld_wait();
+                if (c0 + 32 == kCols) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&t_empty[j & 1]);      // both tile products are in registers
+                }
+                uint32_t pk[16], dk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float l0 = lse_r, l1 = lse_r, d0 = delta_r, d1 = delta_r;
+                    if (p.mode == 1) {
+                        l0 = stl[c0 + i]; l1 = stl[c0 + i + 1];
+                        d0 = stl[64 + c0 + i]; d1 = stl[64 + c0 + i + 1];
+                    }
+                    float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, -l0));
+                    float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -l1));
+                    if (c0 + i >= nvalid) p0 = 0.f;
+                    if (c0 + i + 1 >= nvalid) p1 = 0.f;
+                    const float g0 = p0 * (__uint_as_float(d[i]) - d0) * p.scale;
+                    const float g1 = p1 * (__uint_as_float(d[i + 1]) - d1) * p.scale;
+                    const __half2 ph = __floats2half2_rn(p0, p1);
+                    const __half2 gh = __floats2half2_rn(g0, g1);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&ph);
+                    dk[i >> 1] = *reinterpret_cast<const uint32_t*>(&gh);
+                }
+                const int u0 = c0 >> 3;      // first 16-byte unit of this half (8 fp16 per unit)
+                if (p.mode == 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        *reinterpret_cast<uint4*>(st0 + (((u0 + u) ^ (r & 7)) << 4)) =
+                            make_uint4(dk[u * 4], dk[u * 4 + 1], dk[u * 4 + 2], dk[u * 4 + 3]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        *reinterpret_cast<uint4*>(st0 + (((u0 + u) ^ (r & 7)) << 4)) =
+                            make_uint4(pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
+                        *reinterpret_cast<uint4*>(st0 + kChunk16 + (((u0 + u) ^ (r & 7)) << 4)) =
+                            make_uint4(dk[u * 4], dk[u * 4 + 1], dk[u * 4 + 2], dk[u * 4 + 3]);
+                    }
+                }
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&st_full[sb]);
+        }
+        // epilogue: accumulators -> fp16
+        ptx::mbar_wait(acc_full, 0);
+        ptx::tc_fence_after();
+        const int nout = p.mode ? 2 : 1;
+        for (int o = 0; o < nout; ++o) {
+            __half* base = o == 0 ? p.out0 : p.out1;
+            const long ld = o == 0 ? p.ld0 : p.ld1;
+            const int c0 = o == 0 ? p.o0_c0 : p.o1_c0;
+            __half* orow = base + ((long)b * p.Nrow + row0 + r) * ld + c0 + h * p.dp;
+            const uint32_t tacc = (o == 0 ? tmem_acc0 : tmem_acc1) + lane_addr;
+            for (int c = 0; c < p.dp; c += 16) {
+                uint32_t raw[16];
+                ptx::tmem_ld_32x16(tacc + (uint32_t)c, raw);
+                ptx::tmem_ld_wait();
+                if (row_ok) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const __half2 h2 = __floats2half2_rn(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+                        w[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                    }
+                    *reinterpret_cast<uint4*>(orow + c) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// delta[z][i] = sum_c dO[b,i,h,c] * O[b,i,h,c]   (one warp per (z, i) row)
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __half* __restrict__ o, long ldo, const __half* __restrict__ dO,
+                                                         long lddo, int B, int heads, int Nq, int dp, float* __restrict__ delta) {
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const long total = (long)B * heads * Nq;
+    if (row >= total) return;
+    const int i = (int)(row % Nq);
+    const int z = (int)(row / Nq);
+    const int b = z / heads, h = z - b * heads;
+    const __half2* po = reinterpret_cast<const __half2*>(o + ((long)b * Nq + i) * ldo + h * dp);
+    const __half2* pd = reinterpret_cast<const __half2*>(dO + ((long)b * Nq + i) * lddo + h * dp);
+    float acc = 0.f;
+    for (int c = lane; c < dp / 2; c += 32) {
+        const float2 a = __half22float2(po[c]), g = __half22float2(pd[c]);
+        acc += a.x * g.x + a.y * g.y;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) delta[row] = acc;
+}
+
+int make_map(CUtensorMap* m, const __half* ptr, long ld, int N, int B, int box_rows) {
+    uint64_t dims[3] = {(uint64_t)ld, (uint64_t)N, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)N * ld * 2};
+    uint32_t box[3] = {64, (uint32_t)box_rows, 1};
+    return encode_tmap_f16(m, 3, ptr, dims, str, box);
+}
+
+}  // namespace
+
+bool attn_bwd_supported(int Nq, int Nk, int dp) {
+    // both modes keep 256 + 2*dp TMEM columns and (2 resident + 2x2 streamed + staging) tiles in shared memory
+    return Nq >= kRows && Nk >= kCols && dp % 16 == 0 && dp >= 16 && dp <= 128;
+}
+
+int attn_bwd_launch(const AttnBwdDesc& d, cudaStream_t stream) {
+    if (!attn_bwd_supported(d.Nq, d.Nk, d.dp)) return set_error(S2I_ERR_ARG, "attn_bwd: unsupported shape Nq=%d Nk=%d dp=%d", d.Nq, d.Nk, d.dp);
+    if (!d.q || !d.kv || !d.dO || !d.o || !d.lse || !d.delta || !d.dq) return set_error(S2I_ERR_ARG, "attn_bwd: null argument");
+    const int Z = d.B * d.heads;
+    {   // delta = rowsum(dO * O)
+        const long rows = (long)Z * d.Nq;
+        attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(d.o, d.ldo, d.dO, d.lddo, d.B, d.heads, d.Nq, d.dp, d.delta);
+        S2I_LAUNCH_CHECK_TAG("attn_bwd_delta", 0.0, 0.0);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        S2I_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int nkc = (d.dp + 63) / 64;
+    for (int mode = 0; mode < 2; ++mode) {
+        if (mode == 1 && !d.dk) break;
+        BwdParams p;
+        memset(&p, 0, sizeof(p));
+        p.mode = mode;
+        p.heads = d.heads; p.dp = d.dp; p.nkc = nkc; p.Nq = d.Nq;
+        p.scale = d.scale;
+        p.scale_log2 = d.scale * 1.4426950408889634f;
+        p.lse = d.lse; p.delta = d.delta;
+        p.idesc_t = ptx::make_idesc_f16(128, kCols, 0, 0, 0);
+        p.idesc_acc = ptx::make_idesc_f16(128, (uint32_t)d.dp, 0, 0, 1);
+        if (mode == 0) {
+            p.Nrow = d.Nq; p.Ncol = d.Nk;
+            S2I_TRY(make_map(&p.mapR1, d.q, d.ldq, d.Nq, d.B, kRows));   p.r1_c0 = d.q_c0;
+            S2I_TRY(make_map(&p.mapR2, d.dO, d.lddo, d.Nq, d.B, kRows)); p.r2_c0 = 0;
+            S2I_TRY(make_map(&p.mapC1, d.kv, d.ldkv, d.Nk, d.B, kCols)); p.c1_c0 = d.k_c0;
+            S2I_TRY(make_map(&p.mapC2, d.kv, d.ldkv, d.Nk, d.B, kCols)); p.c2_c0 = d.v_c0;
+            p.out0 = d.dq; p.ld0 = d.lddq; p.o0_c0 = d.dq_c0;
+        } else {
+            p.Nrow = d.Nk; p.Ncol = d.Nq;
+            S2I_TRY(make_map(&p.mapR1, d.kv, d.ldkv, d.Nk, d.B, kRows)); p.r1_c0 = d.k_c0;
+            S2I_TRY(make_map(&p.mapR2, d.kv, d.ldkv, d.Nk, d.B, kRows)); p.r2_c0 = d.v_c0;
+            S2I_TRY(make_map(&p.mapC1, d.q, d.ldq, d.Nq, d.B, kCols));   p.c1_c0 = d.q_c0;
+            S2I_TRY(make_map(&p.mapC2, d.dO, d.lddo, d.Nq, d.B, kCols)); p.c2_c0 = 0;
+            p.out0 = d.dv; p.ld0 = d.lddkv; p.o0_c0 = d.dv_c0;
+            p.out1 = d.dk; p.ld1 = d.lddkv; p.o1_c0 = d.dk_c0;
+        }
+        const int nstaged = mode ? 2 : 1;
+        const int fixed = 2 * nkc * kChunk16 + kStages * 2 * nkc * kChunk8 + 2048 + 1024;   // operands + barriers/stats + slack
+        p.sbufs = (fixed + 2 * nstaged * kChunk16 <= 227 * 1024) ? 2 : 1;
+        // prefer two co-resident CTAs when a single staging buffer makes the footprint fit half an SM
+        if (fixed + 2 * nstaged * kChunk16 > 113 * 1024 && fixed + nstaged * kChunk16 <= 113 * 1024) p.sbufs = 1;
+        const size_t smem_bytes = (size_t)fixed + (size_t)p.sbufs * nstaged * kChunk16;
+        if (smem_bytes > 227u * 1024u) return set_error(S2I_ERR_ARG, "attn_bwd: head dim %d does not fit shared memory", d.dp);
+        dim3 grid((unsigned)((p.Nrow + kRows - 1) / kRows), (unsigned)Z, 1);
+        attn_bwd_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+        // algorithmic work of the reference's backward: dP, dQ (mode 0) and dV, dK (mode 1) products at the true head dim
+        S2I_LAUNCH_CHECK_TAG("attn_bwd", 4.0 * Z * (double)d.Nq * d.Nk * d.d_true, 0.0);
+    }
+    return 0;
+}
+
+}  // namespace s2i

@@ -8,6 +8,7 @@
 #include "ptx.cuh"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -48,6 +49,12 @@ struct __align__(64) GemmParams {
     int splits, iters_per_split;
     float* ws;               // split-K partial tiles [split][tile][128][BN] fp32
     unsigned int* counters;  // one arrival counter per output tile (self-resetting)
+    // ---- TMA epilogue (gemm_tma_kernel): residual tile in, result tiles out through cp.async.bulk.tensor
+    CUtensorMap mapRes;      // fp32 residual  (N, W, H, B), box (32, tw, th, tb), 128B swizzle
+    CUtensorMap mapO32;      // fp32 output, same geometry
+    CUtensorMap mapO16;      // fp16 output, box (32, tw, th, tb), 64B swizzle
+    int has_res, has_o32, has_o16;
+    int split_add;           // split-K by fp32 reduce-add into a zeroed output (split 0 carries bias + residual)
 };
 
 constexpr int kEpiLd = 36;   // floats per row of the per-warp 32x32 transpose buffer (16-byte aligned, conflict-free)
@@ -64,6 +71,247 @@ __device__ __forceinline__ uint16_t to_half_bits(float v, int bf16) {
     return *reinterpret_cast<uint16_t*>(&h);
 }
 
+struct TileCtx {
+    int x0, y0, b0, m0, n0, z, zb, zhd, split, it_begin, it_end;
+};
+
+__device__ __forceinline__ TileCtx tile_ctx(const GemmParams& p) {
+    TileCtx t;
+    const int mt = blockIdx.x;
+    t.n0 = blockIdx.y * p.BN;
+    t.z = blockIdx.z / p.splits;
+    t.split = blockIdx.z - t.z * p.splits;
+    t.zb = t.z / p.zh;
+    t.zhd = t.z - t.zb * p.zh;
+    t.x0 = t.y0 = t.b0 = t.m0 = 0;
+    if (!p.a_mn) {
+        const int tx = mt % p.tiles_x;
+        const int ty = (mt / p.tiles_x) % p.tiles_y;
+        const int tbi = mt / (p.tiles_x * p.tiles_y);
+        t.x0 = tx * p.tw;
+        t.y0 = ty * p.th;
+        t.b0 = tbi * p.tb;
+    } else {
+        t.m0 = mt * kBlockM;
+    }
+    const int total_iters = p.taps * p.k_chunks;
+    t.it_begin = t.split * p.iters_per_split;
+    t.it_end = min(total_iters, t.it_begin + p.iters_per_split);
+    return t;
+}
+
+// One thread: stream the A / B operand tiles of this CTA's K range through the stage ring.
+__device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx& t, uint8_t* smem, int stage_bytes,
+                                              uint64_t* full, uint64_t* empty) {
+    const int a_inner = p.a_c0 + (p.a_zmode ? 0 : t.zhd * p.a_hoff);
+    const int a_bz = p.a_zmode ? t.z : t.zb;
+    const int b_inner = p.b_c0 + (p.b_zmode ? 0 : t.zhd * p.b_hoff);
+    const int b_bz = p.b_zmode ? t.z : t.zb;
+    const int nchunks_b = (p.BN + 63) >> 6;
+    for (int it = t.it_begin; it < t.it_end; ++it) {
+        const int li = it - t.it_begin;
+        const int stage = li % p.stages;
+        const uint32_t phase = (li / p.stages) & 1;
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&full[stage], p.tx_bytes);
+        uint8_t* sa = smem + stage * stage_bytes;
+        uint8_t* sb = sa + kAStageBytes;
+        if (!p.a_mn) {
+            const int tap = it / p.k_chunks;
+            const int kc = it - tap * p.k_chunks;
+            int dx = 0, dy = 0;
+            if (p.taps == 9) {
+                dy = tap / 3 - 1;
+                dx = tap % 3 - 1;
+            }
+            ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + kc * kBlockK, t.x0 + dx, t.y0 + dy, t.b0 + a_bz);
+        } else {
+            ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + t.m0, it * kBlockK, 0, a_bz);
+            ptx::tma_load_4d(sa + kChunkBytes, &p.mapA, &full[stage], a_inner + t.m0 + 64, it * kBlockK, 0, a_bz);
+        }
+        if (!p.b_mn) {
+            ptx::tma_load_3d(sb, &p.mapB, &full[stage], b_inner + it * kBlockK, t.n0, b_bz);
+        } else {
+            for (int j = 0; j < nchunks_b; ++j)
+                ptx::tma_load_3d(sb + j * kChunkBytes, &p.mapB, &full[stage], b_inner + t.n0 + j * 64, it * kBlockK, b_bz);
+        }
+    }
+}
+
+// One thread: issue the tcgen05.mma stream of this CTA's K range; accum_full fires when the accumulator is complete.
+__device__ __forceinline__ void mma_loop(const GemmParams& p, const TileCtx& t, uint8_t* smem, int stage_bytes,
+                                         uint64_t* full, uint64_t* empty, uint64_t* accum_full, uint32_t tmem_base) {
+    const uint32_t a_kstep = p.a_mn ? 2048u : 32u;   // bytes per UMMA_K = 16 elements
+    const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
+    const uint32_t a_lbo = p.a_mn ? (uint32_t)kChunkBytes : 16u;
+    const uint32_t b_lbo = p.b_mn ? (uint32_t)kChunkBytes : 16u;
+    for (int it = t.it_begin; it < t.it_end; ++it) {
+        const int li = it - t.it_begin;
+        const int stage = li % p.stages;
+        const uint32_t phase = (li / p.stages) & 1;
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
+        const uint32_t sb = sa + kAStageBytes;
+        // The last K chunk of a tap may be partial: head-sliced operands must not read past Kc.
+        const int ksteps = ((it + 1) % p.k_chunks == 0) ? p.k_last_steps : kBlockK / 16;
+        for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024u);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024u);
+            ptx::umma_f16(tmem_base, adesc, bdesc, p.idesc, (li | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[stage]);   // frees the smem stage once these MMAs have read it
+    }
+    ptx::umma_commit(accum_full);          // accumulator complete
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// gemm_tma_kernel: same mainloop, epilogue entirely through TMA.  Per 32-column chunk each epilogue thread (one tile
+// row) does: tcgen05.ld -> + bias (staged in smem) -> + residual (tile loaded by TMA into the idle pipeline stages,
+// 128B-swizzled, read and overwritten in place) -> fp32 / fp16 staging -> one thread issues the bulk tensor store.
+// No per-thread global addressing, no predicates: ~100 instructions per chunk instead of ~1000 in gemm_tc_kernel.
+// Supports K-major operands, Z = 1, N % 32 == 0, alpha = 1, no ReLU / rounding emulation.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kChunk32Bytes = kBlockM * 32 * 4;   // 16 KB: 128 rows x 32 fp32 columns
+constexpr int kChunk16Bytes = kBlockM * 32 * 2;   //  8 KB: 128 rows x 32 fp16 columns
+constexpr int kMaxChunks = 8;
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_stage_bytes = ((p.BN + 63) >> 6) * kChunkBytes;
+    const int stage_bytes = kAStageBytes + b_stage_bytes;
+    const int nch = p.BN >> 5;
+    const int use32 = p.has_res | p.has_o32;
+    int pipe_bytes = p.stages * stage_bytes;
+    const int epi_bytes = (use32 ? nch * kChunk32Bytes : 0) + (p.has_o16 ? nch * kChunk16Bytes : 0);
+    if (pipe_bytes < epi_bytes) pipe_bytes = epi_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + pipe_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* accum_full = empty + p.stages;
+    uint64_t* r_full = accum_full + 1;                      // [kMaxChunks]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + kMaxChunks);
+    float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [BN]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const TileCtx t = tile_ctx(p);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&p.mapA);
+        ptx::prefetch_tmap(&p.mapB);
+        if (p.has_res) ptx::prefetch_tmap(&p.mapRes);
+        if (p.has_o32) ptx::prefetch_tmap(&p.mapO32);
+        if (p.has_o16) ptx::prefetch_tmap(&p.mapO16);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < p.stages; ++s) {
+                ptx::mbar_init(&full[s], 1);
+                ptx::mbar_init(&empty[s], 1);
+            }
+            ptx::mbar_init(accum_full, 1);
+            for (int c = 0; c < kMaxChunks; ++c) ptx::mbar_init(&r_full[c], 1);
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const bool add_res = p.has_res && (!p.split_add || t.split == 0);
+    const bool add_bias = !p.split_add || t.split == 0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            producer_loop(p, t, smem, stage_bytes, full, empty);
+            if (add_res) {
+                // the pipeline stages are idle once the accumulator is complete: land the residual tile there
+                ptx::mbar_wait(accum_full, 0);
+                for (int c = 0; c < nch; ++c) {
+                    if (t.n0 + c * 32 >= p.N) break;
+                    ptx::mbar_expect_tx(&r_full[c], (uint32_t)(p.tw * p.th * p.tb * 128));
+                    ptx::tma_load_4d(smem + c * kChunk32Bytes, &p.mapRes, &r_full[c], t.n0 + c * 32, t.x0, t.y0, t.b0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) mma_loop(p, t, smem, stage_bytes, full, empty, accum_full, tmem_base);
+    } else {
+        // ---------------------------------------------------- epilogue (warps 2..5), thread <-> tile row
+        const int e = threadIdx.x - 64;
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;
+        for (int i = e; i < p.BN; i += 128) {
+            const int n = t.n0 + i;
+            float b = 0.f;
+            if (add_bias && n < p.N) {
+                if (p.bias) b = __ldg(p.bias + n);
+                if (p.rowvec) b += __ldg(p.rowvec + n);
+            }
+            bias_s[i] = b;
+        }
+        ptx::named_bar_sync(1, 128);
+        ptx::mbar_wait(accum_full, 0);
+        ptx::tc_fence_after();
+        const uint32_t sw128 = (uint32_t)(r & 7);
+        const uint32_t sw64 = (uint32_t)((r >> 1) & 3);
+        uint8_t* base16 = smem + (use32 ? nch * kChunk32Bytes : 0);
+        for (int c = 0; c < nch; ++c) {
+            if (t.n0 + c * 32 >= p.N) break;
+            uint32_t raw[32];
+            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
+            if (add_res) ptx::mbar_wait(&r_full[c], 0);
+            ptx::tmem_ld_wait();
+            uint8_t* row32 = smem + c * kChunk32Bytes + r * 128;
+            uint32_t hp[16];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + u * 4);
+                float4 v = make_float4(__uint_as_float(raw[4 * u]) + b4.x, __uint_as_float(raw[4 * u + 1]) + b4.y,
+                                       __uint_as_float(raw[4 * u + 2]) + b4.z, __uint_as_float(raw[4 * u + 3]) + b4.w);
+                float4* slot = reinterpret_cast<float4*>(row32 + ((u ^ sw128) << 4));
+                if (add_res) {
+                    const float4 x = *slot;
+                    v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+                }
+                if (p.has_o32) *slot = v;
+                if (p.has_o16) {
+                    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                    hp[2 * u] = *reinterpret_cast<const uint32_t*>(&h0);
+                    hp[2 * u + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+                }
+            }
+            if (p.has_o16) {
+                uint8_t* row16 = base16 + c * kChunk16Bytes + r * 64;
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    *reinterpret_cast<uint4*>(row16 + ((w ^ sw64) << 4)) =
+                        make_uint4(hp[4 * w], hp[4 * w + 1], hp[4 * w + 2], hp[4 * w + 3]);
+            }
+            ptx::fence_proxy_async();              // generic-proxy smem writes -> visible to the bulk-copy engine
+            ptx::named_bar_sync(1, 128);
+            if (e == 0) {
+                const int nc = t.n0 + c * 32;
+                if (p.has_o32) {
+                    if (p.split_add) ptx::tma_reduce_add_4d(&p.mapO32, smem + c * kChunk32Bytes, nc, t.x0, t.y0, t.b0);
+                    else ptx::tma_store_4d(&p.mapO32, smem + c * kChunk32Bytes, nc, t.x0, t.y0, t.b0);
+                }
+                if (p.has_o16) ptx::tma_store_4d(&p.mapO16, base16 + c * kChunk16Bytes, nc, t.x0, t.y0, t.b0);
+                ptx::tma_store_commit();
+            }
+        }
+        if (e == 0) ptx::tma_store_wait_read0();   // shared memory stays valid until the stores have read it
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -77,22 +325,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int mt = blockIdx.x;
-    const int n0 = blockIdx.y * p.BN;
-    const int z = blockIdx.z / p.splits;
-    const int split = blockIdx.z - z * p.splits;
-    const int zb = z / p.zh, zhd = z - zb * p.zh;
-    int x0 = 0, y0 = 0, b0 = 0, m0 = 0;
-    if (!p.a_mn) {
-        const int tx = mt % p.tiles_x;
-        const int ty = (mt / p.tiles_x) % p.tiles_y;
-        const int tbi = mt / (p.tiles_x * p.tiles_y);
-        x0 = tx * p.tw;
-        y0 = ty * p.th;
-        b0 = tbi * p.tb;
-    } else {
-        m0 = mt * kBlockM;
-    }
+    const TileCtx t = tile_ctx(p);
+    const int n0 = t.n0, zb = t.zb, zhd = t.zhd, split = t.split;
+    const int x0 = t.x0, y0 = t.y0, b0 = t.b0, m0 = t.m0;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&p.mapA);
@@ -116,74 +351,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_iters = p.taps * p.k_chunks;
-    const int it_begin = split * p.iters_per_split;
-    const int it_end = min(total_iters, it_begin + p.iters_per_split);
-
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------ TMA producer
-            const int a_inner = p.a_c0 + (p.a_zmode ? 0 : zhd * p.a_hoff);
-            const int a_bz = p.a_zmode ? z : zb;
-            const int b_inner = p.b_c0 + (p.b_zmode ? 0 : zhd * p.b_hoff);
-            const int b_bz = p.b_zmode ? z : zb;
-            const int nchunks_b = (p.BN + 63) >> 6;
-            for (int it = it_begin; it < it_end; ++it) {
-                const int li = it - it_begin;
-                const int stage = li % p.stages;
-                const uint32_t phase = (li / p.stages) & 1;
-                ptx::mbar_wait(&empty[stage], phase ^ 1);
-                ptx::mbar_expect_tx(&full[stage], p.tx_bytes);
-                uint8_t* sa = smem + stage * stage_bytes;
-                uint8_t* sb = sa + kAStageBytes;
-                if (!p.a_mn) {
-                    const int tap = it / p.k_chunks;
-                    const int kc = it - tap * p.k_chunks;
-                    int dx = 0, dy = 0;
-                    if (p.taps == 9) {
-                        dy = tap / 3 - 1;
-                        dx = tap % 3 - 1;
-                    }
-                    ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + kc * kBlockK, x0 + dx, y0 + dy, b0 + a_bz);
-                } else {
-                    ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + m0, it * kBlockK, 0, a_bz);
-                    ptx::tma_load_4d(sa + kChunkBytes, &p.mapA, &full[stage], a_inner + m0 + 64, it * kBlockK, 0, a_bz);
-                }
-                if (!p.b_mn) {
-                    ptx::tma_load_3d(sb, &p.mapB, &full[stage], b_inner + it * kBlockK, n0, b_bz);
-                } else {
-                    for (int j = 0; j < nchunks_b; ++j)
-                        ptx::tma_load_3d(sb + j * kChunkBytes, &p.mapB, &full[stage], b_inner + n0 + j * 64,
-                                         it * kBlockK, b_bz);
-                }
-            }
-        }
+        if (lane == 0) producer_loop(p, t, smem, stage_bytes, full, empty);
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer
-            const uint32_t a_kstep = p.a_mn ? 2048u : 32u;   // bytes per UMMA_K = 16 elements
-            const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
-            const uint32_t a_lbo = p.a_mn ? (uint32_t)kChunkBytes : 16u;
-            const uint32_t b_lbo = p.b_mn ? (uint32_t)kChunkBytes : 16u;
-            for (int it = it_begin; it < it_end; ++it) {
-                const int li = it - it_begin;
-                const int stage = li % p.stages;
-                const uint32_t phase = (li / p.stages) & 1;
-                ptx::mbar_wait(&full[stage], phase);
-                ptx::tc_fence_after();
-                const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
-                const uint32_t sb = sa + kAStageBytes;
-                // The last K chunk of a tap may be partial: head-sliced operands must not read past Kc.
-                const int ksteps = ((it + 1) % p.k_chunks == 0) ? p.k_last_steps : kBlockK / 16;
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t adesc = ptx::make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024u);
-                    const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024u);
-                    ptx::umma_f16(tmem_base, adesc, bdesc, p.idesc, (li | k) != 0 ? 1u : 0u);
-                }
-                ptx::umma_commit(&empty[stage]);   // frees the smem stage once these MMAs have read it
-            }
-            ptx::umma_commit(accum_full);          // accumulator complete
-        }
+        if (lane == 0) mma_loop(p, t, smem, stage_bytes, full, empty, accum_full, tmem_base);
     } else {
         // ---------------------------------------------------- epilogue (warps 2..5)
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -410,14 +581,16 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-int encode_map(CUtensorMap* m, int bf16, int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box) {
+int encode_map(CUtensorMap* m, int dtype, int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, int swizzle_bytes = 128) {
     auto fn = get_encode_fn();
     if (!fn) return set_error(S2I_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     uint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
-                    const_cast<void*>(ptr), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUtensorMapDataType dt = dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                   : dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(S2I_ERR_CUDA,
                          "cuTensorMapEncodeTiled failed (%d): rank %d ptr %p dims [%llu %llu %llu %llu] strides [%llu %llu "
@@ -486,6 +659,61 @@ TileChoice choose_tiles(int N, long tiles_m, int Z, int iters, bool allow_split)
     return best;
 }
 
+// ---- gemm_tma_kernel tile choice ----------------------------------------------------------------------------------
+// Same pacing model with this kernel's constants: prologue + first-load latency ~4.5 k cycles, ~450 cycles per
+// 32-column epilogue chunk (+ the residual tile's L2 round trip), operands arriving at ~48 B/clk per SM when every SM
+// pulls from L2.  Split-K partial tiles are reduce-added into the (zeroed) output by the bulk-copy engine.
+double model_cycles_tma(int N, long tiles_m, int iters, int BN, int splits, bool residual) {
+    // Calibrated on B200 with tools/gemm_bench.py (profiles/r1_gemm_bench_v2.txt): every CTA pays ~9 k cycles of launch,
+    // prologue, first-load and drain latency, so small problems want MANY short CTAs (two co-resident CTAs per SM hide
+    // each other's latencies); operand tiles arrive from L2 at ~40 B/clk per SM when the whole chip pulls.
+    const int tiles_n = ceil_div(N, BN);
+    const long ctas = tiles_m * tiles_n * splits;
+    const int stage_bytes = kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
+    const int occ = (2 * stage_bytes <= 100 * 1024) ? 2 : 1;
+    const long slots = (long)kNumSMs * occ;
+    const long waves = ceil_div_l(ctas, slots);
+    const int it = ceil_div(iters, splits);
+    const double resident = (double)(ctas <= kNumSMs ? 1 : occ);
+    const double mma = 2.0 * BN * resident;
+    // measured operand arrival: ~31 B/clk for a CTA alone on its SM, ~42 B/clk shared by two co-resident CTAs
+    const double tma = (double)(kAStageBytes + BN * 128) / (resident > 1.0 ? 21.0 : 31.0);
+    const double per_iter = mma > tma ? mma : tma;
+    double fixed = 9000.0 + 350.0 * (BN / 32) + (residual ? 900.0 : 0.0);
+    double total = (double)waves * (it * per_iter + fixed);
+    if (splits > 1) total += 4500.0;      // zero-fill node + reduce-add traffic
+    return total;
+}
+
+TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, bool residual) {
+    static const int cands[] = {256, 192, 160, 128, 96, 64, 32};
+    TileChoice best{N >= 128 ? 128 : N, 1};
+    double best_c = 1e30;
+    for (int c : cands) {
+        if (c > N && c != 32) continue;
+        const long base = tiles_m * ceil_div(N, c);
+        for (int sp = 1; sp <= 32; sp *= 2) {
+            if (sp > 1 && (!allow_split || base * sp > 2 * kNumSMs + 64 || iters / sp < 2)) break;
+            if ((long)(sp - 1) * ceil_div(iters, sp) >= iters) continue;
+            const double cyc = model_cycles_tma(N, tiles_m, iters, c, sp, residual);
+            if (cyc < best_c) {
+                best_c = cyc;
+                best = TileChoice{c, sp};
+            }
+        }
+    }
+    return best;
+}
+
+int g_tma_epi = -1;
+bool tma_epilogue_enabled() {
+    if (g_tma_epi < 0) {
+        const char* e = getenv("S2I_GEMM_TMA_EPI");
+        g_tma_epi = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_tma_epi != 0;
+}
+
 // split-K scratch: partial tiles + per-tile arrival counters (one stream at a time uses the library)
 constexpr size_t kWsBytes = 96u << 20;
 constexpr int kMaxSplitTiles = 4096;
@@ -510,6 +738,145 @@ int ensure_ws() {
     return 0;
 }
 
+int build_operand_maps(GemmParams& p, const GemmDesc& d, int BN) {
+    {
+        const long sw = d.a_sw > 0 ? d.a_sw : d.aC;
+        const long sh = d.a_sh > 0 ? d.a_sh : sw * d.aW;
+        const long sb = d.a_sb > 0 ? d.a_sb : sh * d.aH;
+        uint64_t dims[4] = {(uint64_t)d.aC, (uint64_t)d.aW, (uint64_t)d.aH, (uint64_t)d.aB};
+        uint64_t str[3] = {(uint64_t)sw * 2, (uint64_t)sh * 2, (uint64_t)sb * 2};
+        uint32_t box[4];
+        if (!d.a_mn) {
+            box[0] = kBlockK; box[1] = (uint32_t)p.tw; box[2] = (uint32_t)p.th; box[3] = (uint32_t)p.tb;
+        } else {
+            box[0] = 64; box[1] = kBlockK; box[2] = 1; box[3] = 1;
+        }
+        S2I_TRY(encode_map(&p.mapA, d.bf16, 4, d.A, dims, str, box));
+    }
+    {
+        const long sr = d.b_sr > 0 ? d.b_sr : d.bI;
+        const long sz = d.b_sz > 0 ? d.b_sz : sr * d.bR;
+        uint64_t dims[3] = {(uint64_t)d.bI, (uint64_t)d.bR, (uint64_t)(d.bZ > 0 ? d.bZ : 1)};
+        uint64_t str[2] = {(uint64_t)sr * 2, (uint64_t)sz * 2};
+        uint32_t box[3];
+        if (!d.b_mn) {
+            box[0] = kBlockK; box[1] = (uint32_t)BN; box[2] = 1;
+        } else {
+            box[0] = 64; box[1] = kBlockK; box[2] = 1;
+        }
+        S2I_TRY(encode_map(&p.mapB, d.bf16, 3, d.B, dims, str, box));
+    }
+    return 0;
+}
+
+// Output-side map: [rows...][N] tensor with the A operand's pixel geometry, 32-column boxes.
+int build_out_map(CUtensorMap* m, const GemmParams& p, const GemmDesc& d, const void* ptr, long ld, int dtype) {
+    const int esz = dtype == 2 ? 4 : 2;
+    uint64_t dims[4] = {(uint64_t)d.N, (uint64_t)d.aW, (uint64_t)d.aH, (uint64_t)d.aB};
+    uint64_t str[3] = {(uint64_t)ld * esz, (uint64_t)ld * d.aW * esz, (uint64_t)ld * d.aW * d.aH * esz};
+    uint32_t box[4] = {32, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tb};
+    return encode_map(m, dtype, 4, ptr, dims, str, box, dtype == 2 ? 128 : 64);
+}
+
+// fp32 [rows][N] (row pitch lds) -> fp16 [rows][N] (row pitch ldd); N % 4 == 0
+__global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ src, long lds, __half* __restrict__ dst,
+                                                        long ldd, long rows, int n4) {
+    const long total = rows * n4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / n4;
+        const int c = (int)(i - r * n4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + r * lds + c);
+        const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&a);
+        pk.y = *reinterpret_cast<const uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(dst + r * ldd + c) = pk;
+    }
+}
+
+int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters, cudaStream_t stream) {
+    GemmDesc d = d_in;
+    const long rows_total = (long)d.aW * d.aH * d.aB;
+    bool can_split = d.splits >= 0 && d.out32 && !d.out16;
+    bool via_scratch = false;
+    TileChoice tc = choose_tiles_tma(d.N, tiles_m, num_iters, can_split, d.residual != nullptr);
+    if (d.splits >= 0 && d.out16 && !d.out32 && (size_t)rows_total * d.N * sizeof(float) <= kWsBytes) {
+        // fp16-only output of a K-heavy small problem: split K into an fp32 scratch tile matrix, then convert
+        const TileChoice ts = choose_tiles_tma(d.N, tiles_m, num_iters, true, d.residual != nullptr);
+        if (ts.splits > 1 && model_cycles_tma(d.N, tiles_m, num_iters, ts.BN, ts.splits, d.residual != nullptr) + 5000.0 <
+                                 model_cycles_tma(d.N, tiles_m, num_iters, tc.BN, 1, d.residual != nullptr)) {
+            S2I_TRY(ensure_ws());
+            tc = ts;
+            via_scratch = can_split = true;
+            d.out32 = g_ws;
+            d.ld32 = d.N;
+            d.out16 = nullptr;
+        }
+    }
+    if (d.BN > 0) tc.BN = d.BN;
+    if (d.splits > 0 && can_split) tc.splits = d.splits;
+    while (tc.splits > 1 && (long)(tc.splits - 1) * ceil_div(num_iters, tc.splits) >= num_iters) --tc.splits;
+    const int BN = tc.BN;
+    p.BN = BN;
+    p.splits = tc.splits;
+    p.split_add = tc.splits > 1 ? 1 : 0;
+    p.iters_per_split = ceil_div(num_iters, tc.splits);
+    p.has_res = d.residual ? 1 : 0;
+    p.has_o32 = d.out32 ? 1 : 0;
+    p.has_o16 = d.out16 ? 1 : 0;
+    const int tiles_n = ceil_div(d.N, BN);
+    p.tmem_cols = 32;
+    while (p.tmem_cols < BN) p.tmem_cols *= 2;
+
+    const int stage_bytes = kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
+    const int nch = BN / 32;
+    const size_t epi_bytes = (size_t)((p.has_res || p.has_o32) ? nch * kChunk32Bytes : 0) + (p.has_o16 ? nch * kChunk16Bytes : 0);
+    const long ctas = tiles_m * tiles_n * tc.splits;
+    const size_t tail = (size_t)(2 * 8 + 1 + kMaxChunks) * 8 + 16 + (size_t)BN * 4 + 1024 + 64;
+    const size_t budget = (ctas > kNumSMs ? 112u : 220u) * 1024u - tail;
+    int stages = (int)(budget / stage_bytes);
+    if (stages < 2) stages = 2;
+    if (stages > 8) stages = 8;
+    if (stages > p.iters_per_split) stages = p.iters_per_split < 1 ? 1 : p.iters_per_split;
+    p.stages = stages;
+    size_t pipe_bytes = (size_t)stages * stage_bytes;
+    if (pipe_bytes < epi_bytes) pipe_bytes = epi_bytes;
+    const size_t smem_bytes = pipe_bytes + tail;
+    if (smem_bytes > 227u * 1024u) return set_error(S2I_ERR_ARG, "gemm(tma): %zu bytes of shared memory needed (BN %d)", smem_bytes, BN);
+
+    p.a_c0 = d.a_c0; p.a_hoff = d.a_hoff; p.a_zmode = d.a_zmode;
+    p.b_c0 = d.b_c0; p.b_hoff = d.b_hoff; p.b_zmode = d.b_zmode;
+    p.idesc = ptx::make_idesc_f16(kBlockM, BN, d.bf16, 0, 0);
+    p.tx_bytes = (uint32_t)(p.tw * p.th * p.tb * kBlockK * 2) + (uint32_t)(BN * kBlockK * 2);
+    p.alpha = 1.f;
+    p.bias = d.bias;
+    p.rowvec = d.rowvec;
+    S2I_TRY(build_operand_maps(p, d, BN));
+    if (d.residual) S2I_TRY(build_out_map(&p.mapRes, p, d, d.residual, d.res_ld, 2));
+    if (d.out32) S2I_TRY(build_out_map(&p.mapO32, p, d, d.out32, d.ld32, 2));
+    if (d.out16) S2I_TRY(build_out_map(&p.mapO16, p, d, d.out16, d.ld16, 0));
+    if (p.split_add) {
+        const long rows = (long)d.aW * d.aH * d.aB;
+        S2I_CUDA(cudaMemset2DAsync(d.out32, (size_t)d.ld32 * 4, 0, (size_t)d.N * 4, (size_t)rows, stream));
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)tc.splits);
+    gemm_tma_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+    const double m_rows = (double)d.aW * d.aH * d.aB;
+    S2I_LAUNCH_CHECK_TAG(d.tag, 2.0 * m_rows * d.N * d.Kc * d.taps, 0.0);
+    if (via_scratch) {
+        const long total = rows_total * (d.N / 4);
+        cast_rows_kernel<<<(unsigned)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048), 256, 0, stream>>>(
+            g_ws, d.N, static_cast<__half*>(d_in.out16), d_in.ld16, rows_total, d.N / 4);
+        S2I_LAUNCH_CHECK_TAG("gemm_split_cast", 0.0, 0.0);
+    }
+    return 0;
+}
+
 }  // namespace
 
 int encode_tmap_f16(CUtensorMap* m, int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -519,6 +886,7 @@ int encode_tmap_f16(CUtensorMap* m, int rank, const void* ptr, const uint64_t* d
 
 long g_launches = 0;
 long gemm_launch_count() { return g_launches; }
+void gemm_set_tma_epilogue(int on) { g_tma_epi = on ? 1 : 0; }
 
 int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     if (!d.A || !d.B) return set_error(S2I_ERR_ARG, "gemm: null operand");
@@ -593,6 +961,16 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     if (d.rowvec) fast = fast && (d.rowvec_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.rowvec) & 15) == 0);
     p.fast_epi = fast ? 1 : 0;
 
+    // Epilogue through TMA (gemm_tma_kernel) whenever the shape allows: K-major operands, one problem, plain
+    // bias / shared per-column vector / fp32 residual epilogue, 32-column boxes, 16-byte aligned rows.
+    bool tma = tma_epilogue_enabled() && !d.a_mn && !d.b_mn && Z == 1 && d.alpha == 1.f && !d.relu && d.qscale == 0.f &&
+               d.N % 32 == 0 && !d.out16_bf16 && !(d.rowvec && d.rowvec_ld != 0) && d.c_sb == 0 && d.c_sh == 0 &&
+               d.a_hoff == 0 && d.b_hoff == 0;
+    if (d.out32) tma = tma && (d.ld32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.out32) & 15) == 0);
+    if (d.out16) tma = tma && (d.ld16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(d.out16) & 15) == 0);
+    if (d.residual) tma = tma && (d.res_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.residual) & 15) == 0);
+    if (tma) return launch_tma(p, d, tiles_m, num_iters, stream);
+
     TileChoice tc = choose_tiles(d.N, tiles_m, Z, num_iters, fast && Z == 1 && d.splits >= 0);
     if (d.BN > 0) tc.BN = d.BN;
     if (d.splits > 0) tc.splits = d.splits;
@@ -658,34 +1036,7 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     p.qscale = d.qscale;
     p.qinv = d.qscale != 0.f ? 1.f / d.qscale : 0.f;
 
-    // ---- tensor maps
-    {
-        const long sw = d.a_sw > 0 ? d.a_sw : d.aC;
-        const long sh = d.a_sh > 0 ? d.a_sh : sw * d.aW;
-        const long sb = d.a_sb > 0 ? d.a_sb : sh * d.aH;
-        uint64_t dims[4] = {(uint64_t)d.aC, (uint64_t)d.aW, (uint64_t)d.aH, (uint64_t)d.aB};
-        uint64_t str[3] = {(uint64_t)sw * 2, (uint64_t)sh * 2, (uint64_t)sb * 2};
-        uint32_t box[4];
-        if (!d.a_mn) {
-            box[0] = kBlockK; box[1] = (uint32_t)p.tw; box[2] = (uint32_t)p.th; box[3] = (uint32_t)p.tb;
-        } else {
-            box[0] = 64; box[1] = kBlockK; box[2] = 1; box[3] = 1;
-        }
-        S2I_TRY(encode_map(&p.mapA, d.bf16, 4, d.A, dims, str, box));
-    }
-    {
-        const long sr = d.b_sr > 0 ? d.b_sr : d.bI;
-        const long sz = d.b_sz > 0 ? d.b_sz : sr * d.bR;
-        uint64_t dims[3] = {(uint64_t)d.bI, (uint64_t)d.bR, (uint64_t)(d.bZ > 0 ? d.bZ : 1)};
-        uint64_t str[2] = {(uint64_t)sr * 2, (uint64_t)sz * 2};
-        uint32_t box[3];
-        if (!d.b_mn) {
-            box[0] = kBlockK; box[1] = (uint32_t)BN; box[2] = 1;
-        } else {
-            box[0] = 64; box[1] = kBlockK; box[2] = 1;
-        }
-        S2I_TRY(encode_map(&p.mapB, d.bf16, 3, d.B, dims, str, box));
-    }
+    S2I_TRY(build_operand_maps(p, d, BN));
 
     static bool attr_set = false;
     if (!attr_set) {

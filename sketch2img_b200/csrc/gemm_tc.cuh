@@ -31,6 +31,10 @@ struct GemmDesc : s2i_gemm_desc {
 // Enqueue on `stream`.  Returns 0 or a negative s2i error code (message via s2i_last_error()).
 int gemm_launch(const GemmDesc& d, cudaStream_t stream);
 
+// Bisecting switch: 0 routes every GEMM through gemm_tc_kernel (per-thread epilogue), 1 (default) lets eligible shapes
+// use gemm_tma_kernel (epilogue through TMA).  Also settable with S2I_GEMM_TMA_EPI=0 in the environment.
+void gemm_set_tma_epilogue(int on);
+
 // Number of kernel launches issued through gemm_launch since process start (bench.py's gpu_launches).
 long gemm_launch_count();
 

@@ -17,11 +17,15 @@ def _dt(bf16):
     return torch.bfloat16 if bf16 else torch.float16
 
 
-@pytest.fixture(scope="module")
-def L(cuda):
+@pytest.fixture(scope="module", params=["tma_epilogue", "thread_epilogue"])
+def L(cuda, request):
+    """Every GEMM test runs twice: eligible shapes through gemm_tma_kernel (default), and everything through
+    gemm_tc_kernel (the per-thread epilogue, still used for batched / MN-major / scaled / ReLU GEMMs)."""
     from sketch2img_b200 import _lib
-    _lib.lib()
-    return _lib
+    _lib.lib().s2i_gemm_set_tma_epilogue(1 if request.param == "tma_epilogue" else 0)
+    _lib.tma_epilogue = request.param == "tma_epilogue"
+    yield _lib
+    _lib.lib().s2i_gemm_set_tma_epilogue(1)
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 150, 200), (2048, 320, 320), (77, 96, 768), (8192, 16, 320)])
@@ -189,6 +193,60 @@ def test_split_k_linear(L, cuda, M, N, K, splits, BN):
         assert rel(out16.float(), ref) < 3e-3
         outs.append(out32.clone())
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])     # reduction order is fixed
+
+
+@pytest.mark.parametrize("M,N,K,splits,BN,res,o32,o16", [
+    (8192, 320, 320, 0, 0, 1, 1, 0), (8192, 1152, 320, 0, 0, 0, 0, 1), (2048, 640, 2560, 0, 0, 1, 0, 1),
+    (300, 96, 200, 0, 0, 1, 1, 1), (154, 768, 768, 0, 0, 0, 0, 1), (512, 1280, 1280, 4, 0, 1, 1, 0),
+    (128, 1280, 5120, 0, 0, 1, 1, 0), (128, 320, 4096, 16, 64, 0, 1, 0), (8192, 2560, 320, 0, 256, 0, 1, 0),
+    (1000, 32, 64, 0, 0, 1, 1, 1), (4096, 640, 1920, 0, 160, 1, 1, 1)])
+def test_linear_plain_epilogue(L, cuda, M, N, K, splits, BN, res, o32, o16):
+    """alpha = 1, bias + shared column vector (+ fp32 residual), fp32 and/or fp16 outputs: the shapes of the sampling
+    path that take the TMA epilogue (ragged M, ragged last N tile, fp16-only output, split-K by reduce-add)."""
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N + K)
+    a = torch.randn(M, K, generator=g).to(cuda).half()
+    w = (torch.randn(N, K, generator=g) * 0.05).to(cuda).half()
+    bias = torch.randn(N, generator=g).to(cuda)
+    vec = torch.randn(N, generator=g).to(cuda)
+    r = torch.randn(M, N, generator=g).to(cuda)
+    ref = a.double() @ w.double().t() + bias.double() + vec.double() + (r.double() if res else 0.0)
+    for rep in range(2):
+        out32 = torch.full((M, N), float("nan"), device=cuda)
+        out16 = torch.full((M, N), float("nan"), device=cuda, dtype=torch.float16)
+        d = L.GemmDesc(A=a.data_ptr(), aC=K, aW=M, a_sw=K, B=w.data_ptr(), bI=K, bR=N, b_sr=K, N=N, Kc=K, BN=BN,
+                       splits=splits, bias=bias.data_ptr(), rowvec=vec.data_ptr(), rowvec_ld=0,
+                       residual=r.data_ptr() if res else None, res_ld=N,
+                       out32=out32.data_ptr() if o32 else None, ld32=N, out16=out16.data_ptr() if o16 else None, ld16=N)
+        L.gemm(d)
+        torch.cuda.synchronize()
+        if o32:
+            assert rel(out32, ref) < 2e-3
+        if o16:
+            assert rel(out16.float(), ref) < 3e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 320, 320), (2, 32, 32, 640, 640), (2, 16, 16, 1280, 1280),
+                                            (2, 8, 8, 1280, 1280), (2, 24, 24, 64, 96), (3, 4, 4, 128, 64), (2, 2, 2, 64, 32)])
+def test_conv3x3_plain_epilogue(L, cuda, B, H, W, Cin, Cout):
+    """ResBlock conv with bias + time-embedding column vector + fp32 residual into a strided (wider) output."""
+    g = torch.Generator(device="cpu").manual_seed(B * 17 + Cin + H)
+    x = torch.randn(B, H, W, Cin, generator=g).to(cuda).half()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * 0.02).to(cuda).half()
+    bias = torch.randn(Cout, generator=g).to(cuda)
+    temb = torch.randn(Cout, generator=g).to(cuda)
+    r = torch.randn(B, H, W, Cout + 32, generator=g).to(cuda)              # residual rows wider than N
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    out32 = torch.full((B, H, W, Cout + 64), float("nan"), device=cuda)    # output rows wider than N
+    d = L.GemmDesc(A=x.data_ptr(), aC=Cin, aW=W, aH=H, aB=B, a_sw=Cin, a_sh=Cin * W, a_sb=Cin * W * H, taps=9,
+                   B=wp.data_ptr(), bI=9 * Cin, bR=Cout, b_sr=9 * Cin, N=Cout, Kc=Cin, bias=bias.data_ptr(),
+                   rowvec=temb.data_ptr(), rowvec_ld=0, residual=r.data_ptr(), res_ld=Cout + 32,
+                   out32=out32.data_ptr(), ld32=Cout + 64)
+    L.gemm(d)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double() + temb.double(), padding=1).permute(0, 2, 3, 1)
+    ref = ref + r[..., :Cout].double()
+    assert rel(out32[..., :Cout], ref) < 2e-3
+    assert torch.isnan(out32[..., Cout:]).all()                            # nothing written outside the N columns
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,splits", [(2, 8, 8, 1280, 1280, 0), (2, 16, 16, 640, 1280, 0), (2, 8, 8, 256, 64, 6)])
