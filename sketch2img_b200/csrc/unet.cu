@@ -526,12 +526,15 @@ int UNet::resblock_bwd(int idx, const F32& dout, F32& dx) {
 // ================================================================================================== attention
 // q: [B*Nq][q.ld] with this attention's Q heads at column q_c0; kv: [B*Nk][kv.ld] with K heads at k_c0, V at v_c0.
 int UNet::attention(const Transformer& T, const H16& q, long q_c0, const H16& kv, long k_c0, long v_c0, int Nk, H16& P,
-                    H16& o, bool need_P) {
+                    H16& o, bool need_bwd, float** lse) {
     const int B = q.B, Nq = q.H * q.W, Z = B * T.heads;
-    if (!need_P && use_flash_ && attn_fwd_supported(Nq, Nk, T.dp)) {
-        // fused path: the scores stay in TMEM / shared memory (no backward will ask for P)
+    *lse = nullptr;
+    const bool fused_bwd = need_bwd && attn_bwd_supported(Nq, Nk, T.dp);
+    if ((!need_bwd || fused_bwd) && use_flash_ && attn_fwd_supported(Nq, Nk, T.dp)) {
+        // fused path: the scores stay in TMEM / shared memory; a later backward recomputes them from the log-sum-exp
         P = H16();
         o = new16(q.B, q.H, q.W, T.HP);
+        if (fused_bwd) *lse = dalloc<float>((size_t)Z * Nq);
         if (dry_) return 0;
         AttnDesc a;
         a.q = q.p; a.ldq = q.ld; a.q_c0 = (int)q_c0;
@@ -539,6 +542,7 @@ int UNet::attention(const Transformer& T, const H16& q, long q_c0, const H16& kv
         a.B = B; a.heads = T.heads; a.Nq = Nq; a.Nk = Nk; a.dp = T.dp; a.d_true = T.d;
         a.scale = 1.f / sqrtf((float)T.d);
         a.out = o.p; a.ldo = o.ld;
+        a.lse = *lse;
         return attn_fwd_launch(a, st_);
     }
     const long ldS = rup(Nk, 4), ldP = rup(Nk, 8);
@@ -571,8 +575,27 @@ int UNet::attention(const Transformer& T, const H16& q, long q_c0, const H16& kv
 }
 
 int UNet::attention_bwd(const Transformer& T, const H16& dO, const H16& q, long q_c0, const H16& kv, long k_c0,
-                        long v_c0, int Nk, const H16& P, H16& dq, long dq_c0, H16* dkv, long dk_c0, long dv_c0) {
+                        long v_c0, int Nk, const H16& P, const H16& o, const float* lse, H16& dq, long dq_c0, H16* dkv,
+                        long dk_c0, long dv_c0) {
     const int B = q.B, Nq = q.H * q.W, Z = B * T.heads;
+    if (lse) {
+        // fused: dQ (and dK, dV) with S / P / dP / dS recomputed on chip
+        float* delta = dalloc<float>((size_t)Z * Nq);
+        if (dry_) return 0;
+        AttnBwdDesc a;
+        a.q = q.p; a.ldq = q.ld; a.q_c0 = (int)q_c0;
+        a.kv = kv.p; a.ldkv = kv.ld; a.k_c0 = (int)k_c0; a.v_c0 = (int)v_c0;
+        a.dO = dO.p; a.lddo = dO.ld;
+        a.o = o.p; a.ldo = o.ld;
+        a.lse = lse; a.delta = delta;
+        a.B = B; a.heads = T.heads; a.Nq = Nq; a.Nk = Nk; a.dp = T.dp; a.d_true = T.d;
+        a.scale = 1.f / sqrtf((float)T.d);
+        a.dq = dq.p; a.lddq = dq.ld; a.dq_c0 = (int)dq_c0;
+        if (dkv) {
+            a.dk = a.dv = dkv->p; a.lddkv = dkv->ld; a.dk_c0 = (int)dk_c0; a.dv_c0 = (int)dv_c0;
+        }
+        return attn_bwd_launch(a, st_);
+    }
     const long ldS = rup(Nk, 4), ldP = P.ld;
     float* dP = dalloc<float>((size_t)Z * Nq * ldS);
     __half* dS = dalloc<__half>((size_t)Z * Nq * ldP);
@@ -644,11 +667,10 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     sv.qkv = new16(B, H, W, 3 * T.HP);
     S2I_TRY(gemm(l16, false, 1, T.qkv.w, C, 3 * T.HP, C, nullptr, nullptr, nullptr, nullptr, &sv.qkv));
     // P is only kept for the input-gradient pass, and up_blocks[3] (the last layers+1 transformers) is not on it
-    const bool need_P = save_ && idx < (int)tfm_.size() - (cfg.layers + 1);
-    H16 o1;
-    S2I_TRY(attention(T, sv.qkv, 0, sv.qkv, T.HP, 2L * T.HP, HW, sv.P1, o1, need_P));
+    const bool need_bwd = save_ && idx < (int)tfm_.size() - (cfg.layers + 1);
+    S2I_TRY(attention(T, sv.qkv, 0, sv.qkv, T.HP, 2L * T.HP, HW, sv.P1, sv.o1, need_bwd, &sv.lse1));
     sv.t1 = new32(B, H, W, C);
-    S2I_TRY(gemm(o1, false, 1, T.o1.w, T.HP, C, T.HP, T.o1.b, nullptr, &sv.t0, &sv.t1, nullptr));
+    S2I_TRY(gemm(sv.o1, false, 1, T.o1.w, T.HP, C, T.HP, T.o1.b, nullptr, &sv.t0, &sv.t1, nullptr));
     // --- cross attention (K/V from the text context)
     H16 l16b = new16(B, H, W, C);
     sv.l2 = dalloc<float>(rows * 2);
@@ -658,10 +680,9 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     sv.kv2 = new16(B, 1, cfg.ctx_len, 2 * T.HP);
     S2I_TRY(gemm(ctx16_, false, 1, T.kv2.w, cfg.cross_dim, 2 * T.HP, cfg.cross_dim, nullptr, nullptr, nullptr, nullptr,
                  &sv.kv2));
-    H16 o2;
-    S2I_TRY(attention(T, sv.q2, 0, sv.kv2, 0, T.HP, cfg.ctx_len, sv.P2, o2, need_P));
+    S2I_TRY(attention(T, sv.q2, 0, sv.kv2, 0, T.HP, cfg.ctx_len, sv.P2, sv.o2, need_bwd, &sv.lse2));
     sv.t2 = new32(B, H, W, C);
-    S2I_TRY(gemm(o2, false, 1, T.o2.w, T.HP, C, T.HP, T.o2.b, nullptr, &sv.t1, &sv.t2, nullptr));
+    S2I_TRY(gemm(sv.o2, false, 1, T.o2.w, T.HP, C, T.HP, T.o2.b, nullptr, &sv.t1, &sv.t2, nullptr));
     // --- GEGLU feed-forward
     H16 l16c = new16(B, H, W, C);
     sv.l3 = dalloc<float>(rows * 2);
@@ -710,7 +731,7 @@ int UNet::transformer_bwd(int idx, const F32& dout, F32& dx) {
     H16 dO2 = new16(B, H, W, T.HP);
     S2I_TRY(gemm(dt2h, false, 1, T.o2.wd, C, T.HP, C, nullptr, nullptr, nullptr, nullptr, &dO2));
     H16 dq2 = new16(B, H, W, T.HP);
-    S2I_TRY(attention_bwd(T, dO2, S.q2, 0, S.kv2, 0, T.HP, cfg.ctx_len, S.P2, dq2, 0, nullptr, 0, 0));
+    S2I_TRY(attention_bwd(T, dO2, S.q2, 0, S.kv2, 0, T.HP, cfg.ctx_len, S.P2, S.o2, S.lse2, dq2, 0, nullptr, 0, 0));
     F32 dl2 = new32(B, H, W, C);
     S2I_TRY(gemm(dq2, false, 1, T.q2.wd, T.HP, C, T.HP, nullptr, nullptr, nullptr, &dl2, nullptr));
     F32 dt1 = new32(B, H, W, C);
@@ -720,7 +741,7 @@ int UNet::transformer_bwd(int idx, const F32& dout, F32& dx) {
     H16 dO1 = new16(B, H, W, T.HP);
     S2I_TRY(gemm(dt1h, false, 1, T.o1.wd, C, T.HP, C, nullptr, nullptr, nullptr, nullptr, &dO1));
     H16 dqkv = new16(B, H, W, 3 * T.HP);
-    S2I_TRY(attention_bwd(T, dO1, S.qkv, 0, S.qkv, T.HP, 2L * T.HP, HW, S.P1, dqkv, 0, &dqkv, T.HP, 2L * T.HP));
+    S2I_TRY(attention_bwd(T, dO1, S.qkv, 0, S.qkv, T.HP, 2L * T.HP, HW, S.P1, S.o1, S.lse1, dqkv, 0, &dqkv, T.HP, 2L * T.HP));
     F32 dl1 = new32(B, H, W, C);
     S2I_TRY(gemm(dqkv, false, 1, T.qkv.wd, 3 * T.HP, C, 3 * T.HP, nullptr, nullptr, nullptr, &dl1, nullptr));
     H16 dt0h = new16(B, H, W, C);

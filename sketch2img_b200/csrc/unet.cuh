@@ -90,6 +90,9 @@ struct TfmSave {
     double* gs = nullptr;
     float *l1 = nullptr, *l2 = nullptr, *l3 = nullptr;
     H16 qkv, P1, q2, kv2, P2;
+    // fused attention backward (attn_bwd.cu): the forward keeps its output and log-sum-exp instead of P
+    H16 o1, o2;
+    float *lse1 = nullptr, *lse2 = nullptr;
 };
 
 class Arena {
@@ -178,10 +181,12 @@ class UNet {
     int resblock_bwd(int idx, const F32& dout, F32& dx);
     int transformer(int idx, const F32& x, F32& out);
     int transformer_bwd(int idx, const F32& dout, F32& dx);
+    // need_bwd: a backward through this attention follows -- keep the log-sum-exp (*lse, fused backward) or P (unfused)
     int attention(const Transformer& T, const H16& q, long q_c0, const H16& kv, long k_c0, long v_c0, int Nk, H16& P,
-                  H16& o, bool need_P);
+                  H16& o, bool need_bwd, float** lse);
     int attention_bwd(const Transformer& T, const H16& dO, const H16& q, long q_c0, const H16& kv, long k_c0, long v_c0,
-                      int Nk, const H16& P, H16& dq, long dq_c0, H16* dkv, long dk_c0, long dv_c0);
+                      int Nk, const H16& P, const H16& o, const float* lse, H16& dq, long dq_c0, H16* dkv, long dk_c0,
+                      long dv_c0);
     int accumulate(F32& acc, const F32& g);
 };
 
