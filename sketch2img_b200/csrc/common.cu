@@ -21,6 +21,7 @@ const char* last_error() { return g_err; }
 
 // ------------------------------------------------------------------------------------------------ profiler
 bool g_prof_on = false;
+long g_alloc_gen = 0;
 namespace {
 struct ProfRec {
     const char* tag;

@@ -18,6 +18,9 @@ int set_error(int code, const char* fmt, ...);
 const char* last_error();
 
 extern long g_launches;  // kernels launched by this library since load
+// Bumped whenever a scratch buffer that kernels address directly (activation arena, LGP workspace, split-K / GroupNorm
+// scratch) is (re)allocated: a captured CUDA graph is only valid for the generation it was captured in.
+extern long g_alloc_gen;
 inline void count_launch(int n = 1) { g_launches += n; }
 
 // Opt-in per-launch device timing (bench.py's roofline figures): while a profile is open every launch site drops a

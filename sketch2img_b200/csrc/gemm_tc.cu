@@ -732,6 +732,7 @@ int ensure_ws() {
         return set_error(S2I_ERR_OOM, "gemm: cannot allocate the split-K workspace");
     }
     S2I_CUDA(cudaMemset(b, 0, kMaxSplitTiles * sizeof(unsigned int)));
+    ++g_alloc_gen;
     g_ws = static_cast<float*>(a);
     g_counters = static_cast<unsigned int*>(b);
     g_ws_device = dev;

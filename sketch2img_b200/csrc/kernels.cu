@@ -5,6 +5,7 @@
 
 #include <cuda_fp16.h>
 #include <math.h>
+#include <cstring>
 
 namespace s2i {
 
@@ -40,40 +41,45 @@ inline int grid_for(long work, int block, int cap = 148 * 16) {
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
+// Statistics slot of one GroupNorm call: per sample 512 bytes = float2[32] (mean, rstd) -- or, for the backward
+// reduction, (mean dxhat, mean dxhat*xhat) -- followed by the arrival counter of the reduction (zero between calls).
 struct GnStat {
     float mean[kGroups];
     float rstd[kGroups];
 };
+constexpr int kSlotDoubles = kGroups * 2;   // doubles per sample in the caller's slot (512 bytes)
 
-__device__ __forceinline__ void load_gn_stats(GnStat& s, const double* sums, int b, double n, float eps) {
+__device__ __forceinline__ void load_gn_stats(GnStat& s, const double* slot, int b) {
     if (threadIdx.x < kGroups) {
-        const double s1 = sums[((long)b * kGroups + threadIdx.x) * 2 + 0];
-        const double s2 = sums[((long)b * kGroups + threadIdx.x) * 2 + 1];
-        const double m = s1 / n;
-        double var = s2 / n - m * m;
-        if (var < 0.0) var = 0.0;
-        s.mean[threadIdx.x] = (float)m;
-        s.rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+        const float2 v = reinterpret_cast<const float2*>(slot + (long)b * kSlotDoubles)[threadIdx.x];
+        s.mean[threadIdx.x] = v.x;
+        s.rstd[threadIdx.x] = v.y;
     }
 }
 
-// MODE 0: accumulate (x, x^2).  MODE 1: accumulate (dxhat, dxhat*xhat) for the backward pass.
+// MODE 0: (sum x, sum x^2) -> (mean, rstd).  MODE 1: (sum dxhat, sum dxhat*xhat) -> their means (backward pass).
+// Each block reduces a slab of pixels of one sample (register partials, 8 loads in flight per thread), writes its
+// 32 x 2 group sums to `partial`; the last block of a sample to arrive adds the partials in block order (the result
+// does not depend on scheduling) and writes the finished statistics.
 template <int MODE>
 __global__ void __launch_bounds__(256) gn_reduce_kernel(const float* __restrict__ x, long ldx,
                                                         const float* __restrict__ dy, long ldd, int HW, int C, int P,
-                                                        const double* __restrict__ fsums,
+                                                        const double* __restrict__ fslot,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float eps, int silu, double* __restrict__ out) {
+                                                        float eps, int silu, double* __restrict__ partial,
+                                                        double* __restrict__ slot) {
     __shared__ float s1[kGroups], s2[kGroups];
     __shared__ GnStat st;
+    __shared__ int is_last;
     const int b = blockIdx.y;
+    const int nblk = gridDim.x;
     const int Cg = C / kGroups;
     const int t = threadIdx.x;
     if (t < kGroups) {
         s1[t] = 0.f;
         s2[t] = 0.f;
     }
-    if (MODE == 1) load_gn_stats(st, fsums, b, (double)Cg * HW, eps);
+    if (MODE == 1) load_gn_stats(st, fslot, b);
     __syncthreads();
     const int p0 = blockIdx.x * P;
     const int p1 = min(HW, p0 + P);
@@ -82,6 +88,7 @@ __global__ void __launch_bounds__(256) gn_reduce_kernel(const float* __restrict_
     const int prow = max(1, (int)blockDim.x / vec);
     const int r = t / qstride;
     const int q0 = t - r * qstride;
+    constexpr int U = 8;
     if (r < prow) {
         for (int q = q0; q < vec; q += qstride) {
             const int c = q << 2;
@@ -96,45 +103,108 @@ __global__ void __launch_bounds__(256) gn_reduce_kernel(const float* __restrict_
                     rs[j] = st.rstd[(c + j) / Cg];
                 }
             }
-            for (int p = p0 + r; p < p1; p += prow) {
-                const long row = (long)b * HW + p;
-                const float4 xv = ldg4(x + row * ldx + c);
-                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-                if (MODE == 0) {
+            for (int pb = p0 + r; pb < p1; pb += U * prow) {
+                float4 xv[U], dv[U];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        a1[j] += xs[j];
-                        a2[j] += xs[j] * xs[j];
-                    }
-                } else {
-                    const float4 dv = ldg4(dy + row * ldd + c);
-                    const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
+                for (int u = 0; u < U; ++u) {
+                    const int pp = pb + u * prow;
+                    const long row = (long)b * HW + (pp < p1 ? pp : p0);
+                    xv[u] = ldg4(x + row * ldx + c);
+                    if (MODE == 1) dv[u] = ldg4(dy + row * ldd + c);
+                }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float xh = (xs[j] - mu[j]) * rs[j];
-                        float d = ds[j];
-                        if (silu) {
-                            const float y = xh * g4[j] + b4[j];
-                            const float sg = sigmoidf_(y);
-                            d *= sg * (1.f + y * (1.f - sg));
+                for (int u = 0; u < U; ++u) {
+                    if (pb + u * prow >= p1) break;
+                    const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                    if (MODE == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            a1[j] += xs[j];
+                            a2[j] += xs[j] * xs[j];
                         }
-                        const float dxh = d * g4[j];
-                        a1[j] += dxh;
-                        a2[j] += dxh * xh;
+                    } else {
+                        const float ds[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float xh = (xs[j] - mu[j]) * rs[j];
+                            float d = ds[j];
+                            if (silu) {
+                                const float y = xh * g4[j] + b4[j];
+                                const float sg = sigmoidf_(y);
+                                d *= sg * (1.f + y * (1.f - sg));
+                            }
+                            const float dxh = d * g4[j];
+                            a1[j] += dxh;
+                            a2[j] += dxh * xh;
+                        }
                     }
                 }
             }
+            if (Cg < 2) {   // degenerate: one channel per group
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    atomicAdd(&s1[c + j], a1[j]);
+                    atomicAdd(&s2[c + j], a2[j]);
+                }
+                continue;
+            }
+            // channels c..c+3 fall in at most two groups: merge before touching shared memory
+            const int ga = c / Cg, gb = (c + 3) / Cg;
+            float sa1 = 0.f, sa2 = 0.f, sb1 = 0.f, sb2 = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                atomicAdd(&s1[(c + j) / Cg], a1[j]);
-                atomicAdd(&s2[(c + j) / Cg], a2[j]);
+                if ((c + j) / Cg == ga) {
+                    sa1 += a1[j];
+                    sa2 += a2[j];
+                } else {
+                    sb1 += a1[j];
+                    sb2 += a2[j];
+                }
+            }
+            atomicAdd(&s1[ga], sa1);
+            atomicAdd(&s2[ga], sa2);
+            if (gb != ga) {
+                atomicAdd(&s1[gb], sb1);
+                atomicAdd(&s2[gb], sb2);
             }
         }
     }
     __syncthreads();
+    double* mine = partial + ((long)b * nblk + blockIdx.x) * (2 * kGroups);
     if (t < kGroups) {
-        atomicAdd(&out[((long)b * kGroups + t) * 2 + 0], (double)s1[t]);
-        atomicAdd(&out[((long)b * kGroups + t) * 2 + 1], (double)s2[t]);
+        mine[2 * t] = (double)s1[t];
+        mine[2 * t + 1] = (double)s2[t];
+    }
+    __threadfence();
+    __syncthreads();
+    unsigned int* counter = reinterpret_cast<unsigned int*>(slot + (long)b * kSlotDoubles + kGroups);
+    if (t == 0) {
+        const unsigned int old = atomicAdd(counter, 1u);
+        is_last = (old == (unsigned int)(nblk - 1));
+        if (is_last) *counter = 0u;     // ready for the next launch that reuses this slot
+    }
+    __syncthreads();
+    if (is_last && t < kGroups) {
+        __threadfence();
+        const double* base = partial + (long)b * nblk * (2 * kGroups);
+        double t1 = 0.0, t2 = 0.0;
+        for (int k = 0; k < nblk; ++k) {
+            t1 += __ldcg(base + (long)k * (2 * kGroups) + 2 * t);
+            t2 += __ldcg(base + (long)k * (2 * kGroups) + 2 * t + 1);
+        }
+        const double n = (double)Cg * HW;
+        float2 o;
+        if (MODE == 0) {
+            const double m = t1 / n;
+            double var = t2 / n - m * m;
+            if (var < 0.0) var = 0.0;
+            o.x = (float)m;
+            o.y = (float)(1.0 / sqrt(var + (double)eps));
+        } else {
+            o.x = (float)(t1 / n);
+            o.y = (float)(t2 / n);
+        }
+        reinterpret_cast<float2*>(slot + (long)b * kSlotDoubles)[t] = o;
     }
 }
 
@@ -146,7 +216,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     __shared__ GnStat st;
     const int b = blockIdx.y;
     const int Cg = C / kGroups;
-    load_gn_stats(st, sums, b, (double)Cg * HW, eps);
+    load_gn_stats(st, sums, b);
     __syncthreads();
     const int vec = C >> 2;
     const long total = (long)HW * vec;
@@ -182,11 +252,11 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restri
     __shared__ float m1[kGroups], m2[kGroups];
     const int b = blockIdx.y;
     const int Cg = C / kGroups;
-    const double n = (double)Cg * HW;
-    load_gn_stats(st, sums, b, n, eps);
+    load_gn_stats(st, sums, b);
     if (threadIdx.x < kGroups) {
-        m1[threadIdx.x] = (float)(bsums[((long)b * kGroups + threadIdx.x) * 2 + 0] / n);
-        m2[threadIdx.x] = (float)(bsums[((long)b * kGroups + threadIdx.x) * 2 + 1] / n);
+        const float2 v = reinterpret_cast<const float2*>(bsums + (long)b * kSlotDoubles)[threadIdx.x];
+        m1[threadIdx.x] = v.x;
+        m2[threadIdx.x] = v.y;
     }
     __syncthreads();
     const int vec = C >> 2;
@@ -219,6 +289,243 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restri
         }
         if (dx32) *reinterpret_cast<float4*>(dx32 + row * ld32 + c) = make_float4(o[0], o[1], o[2], o[3]);
         if (dx16) *reinterpret_cast<uint2*>(dx16 + row * ld16 + c) = pack_half4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ---- fused statistics + apply -------------------------------------------------------------------------------------
+// One launch per GroupNorm (forward: stats -> normalise/affine/SiLU -> fp16; backward: the two reduction terms -> dx).
+// grid = (nblk, B) with nblk * B <= #SMs, so every block is resident and a grid-wide arrival counter (in the call's
+// statistics slot, zeroed once per pass by the caller) can separate the reduction from the apply phase.  Each block
+// reduces its slab of pixels, publishes 32 x 2 partial sums, waits for the grid, adds its sample's partials in block
+// order (deterministic) and applies to the same slab (second read comes from L2).
+struct GnFusedArgs {
+    const float* x; long ldx;
+    const float* dy; long ldd;               // backward only
+    int HW, C, P;
+    const double* fslot;                     // backward: the forward statistics slot
+    const float* gamma; const float* beta;
+    float eps; int silu;
+    double* partial; double* slot;
+    __half* out16; long ld16; __half* raw16; long ldraw;            // forward outputs
+    const float* add; long ldadd; float* dx32; long ld32;           // backward outputs (dx16 = out16 / ld16)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(512) gn_fused_kernel(const GnFusedArgs a) {
+    __shared__ float s1[kGroups], s2[kGroups];
+    __shared__ GnStat st;            // forward statistics (MODE 0: computed here; MODE 1: loaded)
+    __shared__ float m1[kGroups], m2[kGroups];
+    __shared__ double red[8][2 * kGroups];
+    __shared__ __align__(16) float cs[5120];     // [2][prow][C] channel partials, prow * C <= max(2048, C) <= 2560
+    const int b = blockIdx.y;
+    const int nblk = gridDim.x;
+    const int C = a.C, HW = a.HW;
+    const int Cg = C / kGroups;
+    const int t = threadIdx.x;
+    if (t < kGroups) {
+        s1[t] = 0.f;
+        s2[t] = 0.f;
+    }
+    if (MODE == 1) load_gn_stats(st, a.fslot, b);
+    __syncthreads();
+    const int p0 = blockIdx.x * a.P;
+    const int p1 = min(HW, p0 + a.P);
+    const int vec = C >> 2;
+    {   // ---------------- phase 1: slab reduction
+        const int qstride = min(vec, (int)blockDim.x);
+        const int prow = max(1, (int)blockDim.x / vec);
+        const int r = t / qstride;
+        const int q0 = t - r * qstride;
+        constexpr int U = 8;
+        if (r < prow) {
+            for (int q = q0; q < vec; q += qstride) {
+                const int c = q << 2;
+                float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+                float g4[4], b4[4], mu[4], rs[4];
+                if (MODE == 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        g4[j] = a.gamma[c + j];
+                        b4[j] = a.beta[c + j];
+                        mu[j] = st.mean[(c + j) / Cg];
+                        rs[j] = st.rstd[(c + j) / Cg];
+                    }
+                }
+                for (int pb = p0 + r; pb < p1; pb += U * prow) {
+                    float4 xv[U], dv[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int pp = pb + u * prow;
+                        const long row = (long)b * HW + (pp < p1 ? pp : p0);
+                        xv[u] = ldg4(a.x + row * a.ldx + c);
+                        if (MODE == 1) dv[u] = ldg4(a.dy + row * a.ldd + c);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (pb + u * prow >= p1) break;
+                        const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                        if (MODE == 0) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                a1[j] += xs[j];
+                                a2[j] += xs[j] * xs[j];
+                            }
+                        } else {
+                            const float ds[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float xh = (xs[j] - mu[j]) * rs[j];
+                                float d = ds[j];
+                                if (a.silu) {
+                                    const float y = xh * g4[j] + b4[j];
+                                    const float sg = sigmoidf_(y);
+                                    d *= sg * (1.f + y * (1.f - sg));
+                                }
+                                const float dxh = d * g4[j];
+                                a1[j] += dxh;
+                                a2[j] += dxh * xh;
+                            }
+                        }
+                    }
+                }
+                // per-(pixel-row, channel) partials -> shared memory (no atomics); reduced per group below
+                *reinterpret_cast<float4*>(cs + ((long)r * C + c)) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+                *reinterpret_cast<float4*>(cs + ((long)(prow + r) * C + c)) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+            }
+        }
+        __syncthreads();
+        if (t < 2 * kGroups) {
+            const int g = t >> 1, which = t & 1;
+            float acc = 0.f;
+            for (int rr = 0; rr < prow; ++rr) {
+                const float* src = cs + ((long)(which * prow + rr) * C + g * Cg);
+                for (int j = 0; j < Cg; ++j) acc += src[j];
+            }
+            if (which) s2[g] = acc; else s1[g] = acc;
+        }
+    }
+    __syncthreads();
+    double* mine = a.partial + ((long)b * nblk + blockIdx.x) * (2 * kGroups);
+    if (t < kGroups) {
+        mine[2 * t] = (double)s1[t];
+        mine[2 * t + 1] = (double)s2[t];
+    }
+    __syncthreads();
+    // ---------------- grid-wide arrival (all blocks are resident: grid <= #SMs)
+    if (t == 0) {
+        unsigned int* counter = reinterpret_cast<unsigned int*>(a.slot + kGroups);
+        const unsigned int total = gridDim.x * gridDim.y;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < total);
+    }
+    __syncthreads();
+    {   // ---------------- this sample's totals: 8 thread groups x 64 values, block order
+        const int v = t & 63, k0 = t >> 6;
+        const double* base = a.partial + (long)b * nblk * (2 * kGroups) + v;
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        int k = k0;
+        for (; k + 24 < nblk; k += 32) {      // four independent loads in flight
+            const double v0 = __ldcg(base + (long)k * (2 * kGroups));
+            const double v1 = __ldcg(base + (long)(k + 8) * (2 * kGroups));
+            const double v2 = __ldcg(base + (long)(k + 16) * (2 * kGroups));
+            const double v3 = __ldcg(base + (long)(k + 24) * (2 * kGroups));
+            acc0 += v0; acc1 += v1; acc2 += v2; acc3 += v3;
+        }
+        for (; k < nblk; k += 8) acc0 += __ldcg(base + (long)k * (2 * kGroups));
+        red[k0][v] = (acc0 + acc1) + (acc2 + acc3);
+    }
+    __syncthreads();
+    if (t < kGroups) {
+        double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            t1 += red[k][2 * t];
+            t2 += red[k][2 * t + 1];
+        }
+        const double n = (double)Cg * HW;
+        float2 o;
+        if (MODE == 0) {
+            const double m = t1 / n;
+            double var = t2 / n - m * m;
+            if (var < 0.0) var = 0.0;
+            o.x = (float)m;
+            o.y = (float)(1.0 / sqrt(var + (double)a.eps));
+            st.mean[t] = o.x;
+            st.rstd[t] = o.y;
+        } else {
+            o.x = (float)(t1 / n);
+            o.y = (float)(t2 / n);
+            m1[t] = o.x;
+            m2[t] = o.y;
+        }
+        if (blockIdx.x == 0) {
+            // slot layout: float2[32] per sample; sample 0's upper half holds the arrival counter (left untouched)
+            reinterpret_cast<float2*>(a.slot + (long)b * kSlotDoubles)[t] = o;
+        }
+    }
+    __syncthreads();
+    // ---------------- phase 2: apply to the same slab (4 independent float4 per thread in flight)
+    const long total = (long)(p1 - p0) * vec;
+    constexpr int U2 = 4;
+    for (long i0 = t; i0 < total; i0 += (long)U2 * blockDim.x) {
+        float4 xv[U2], dv[U2], av[U2];
+        long rowu[U2];
+        int cu[U2];
+#pragma unroll
+        for (int u = 0; u < U2; ++u) {
+            const long idx = i0 + (long)u * blockDim.x;
+            const long id2 = idx < total ? idx : (long)t;
+            const int p = p0 + (int)(id2 / vec);
+            cu[u] = (int)(id2 % vec) << 2;
+            rowu[u] = (long)b * HW + p;
+            xv[u] = ldg4(a.x + rowu[u] * a.ldx + cu[u]);
+            if (MODE == 1) {
+                dv[u] = ldg4(a.dy + rowu[u] * a.ldd + cu[u]);
+                av[u] = a.add ? ldg4(a.add + rowu[u] * a.ldadd + cu[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U2; ++u) {
+            if (i0 + (long)u * blockDim.x >= total) break;
+            const long row = rowu[u];
+            const int c = cu[u];
+            const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+            if (MODE == 0) {
+                float y[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int g = (c + j) / Cg;
+                    float v = (xs[j] - st.mean[g]) * st.rstd[g] * __ldg(a.gamma + c + j) + __ldg(a.beta + c + j);
+                    if (a.silu) v = v * sigmoidf_(v);
+                    y[j] = v;
+                }
+                *reinterpret_cast<uint2*>(a.out16 + row * a.ld16 + c) = pack_half4(y[0], y[1], y[2], y[3]);
+                if (a.raw16) *reinterpret_cast<uint2*>(a.raw16 + row * a.ldraw + c) = pack_half4(xs[0], xs[1], xs[2], xs[3]);
+            } else {
+                const float ds[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int g = (c + j) / Cg;
+                    const float gm = __ldg(a.gamma + c + j);
+                    const float xh = (xs[j] - st.mean[g]) * st.rstd[g];
+                    float d = ds[j];
+                    if (a.silu) {
+                        const float yv = xh * gm + __ldg(a.beta + c + j);
+                        const float sg = sigmoidf_(yv);
+                        d *= sg * (1.f + yv * (1.f - sg));
+                    }
+                    o[j] = st.rstd[g] * (d * gm - m1[g] - xh * m2[g]);
+                }
+                o[0] += av[u].x; o[1] += av[u].y; o[2] += av[u].z; o[3] += av[u].w;
+                if (a.dx32) *reinterpret_cast<float4*>(a.dx32 + row * a.ld32 + c) = make_float4(o[0], o[1], o[2], o[3]);
+                if (a.out16) *reinterpret_cast<uint2*>(a.out16 + row * a.ld16 + c) = pack_half4(o[0], o[1], o[2], o[3]);
+            }
+        }
     }
 }
 
@@ -565,18 +872,49 @@ __global__ void timestep_embedding_kernel(float t, int dim, float* __restrict__ 
         if (!(cond)) return set_error(S2I_ERR_ARG, "%s", msg);   \
     } while (0)
 
+// pixels per reduction block: ~2 blocks per SM over the whole batch, at least 4 pixels each
 static int gn_chunk(int B, int HW) {
-    int P = (int)(((long)HW * B) / 512);
+    int nblk = (2 * kNumSMs) / (B > 0 ? B : 1);
+    if (nblk < 1) nblk = 1;
+    int P = ceil_div(HW, nblk);
     if (P < 4) P = 4;
-    if (P > 128) P = 128;
     return P;
 }
 
-int gn_stats(const float* x, long ldx, int B, int HW, int C, double* sums, cudaStream_t st) {
+// per-block partial sums of the running reduction (one stream at a time uses the library)
+static double* g_gn_partial = nullptr;
+static size_t g_gn_partial_cap = 0;
+static int g_gn_partial_dev = -1;
+static int gn_partial(size_t doubles, double** out) {
+    int dev = 0;
+    S2I_CUDA(cudaGetDevice(&dev));
+    if (dev != g_gn_partial_dev || doubles > g_gn_partial_cap) {
+        if (g_gn_partial && dev == g_gn_partial_dev) {
+            S2I_CUDA(cudaDeviceSynchronize());
+            cudaFree(g_gn_partial);
+        }
+        size_t cap = doubles < (size_t)(1u << 18) ? (size_t)(1u << 18) : doubles * 2;
+        void* p = nullptr;
+        if (cudaMalloc(&p, cap * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(S2I_ERR_OOM, "gn: cannot allocate the partial-sum scratch");
+        }
+        ++g_alloc_gen;
+        g_gn_partial = static_cast<double*>(p);
+        g_gn_partial_cap = cap;
+        g_gn_partial_dev = dev;
+    }
+    *out = g_gn_partial;
+    return 0;
+}
+
+int gn_stats(const float* x, long ldx, int B, int HW, int C, float eps, double* sums, cudaStream_t st) {
     S2I_REQ(C % (4 * 1) == 0 && C % kGroups == 0 && (ldx & 3) == 0, "gn_stats: C must be a multiple of 32 and ld of 4");
     const int P = gn_chunk(B, HW);
     dim3 grid(ceil_div(HW, P), B);
-    gn_reduce_kernel<0><<<grid, 256, 0, st>>>(x, ldx, nullptr, 0, HW, C, P, nullptr, nullptr, nullptr, 0.f, 0, sums);
+    double* partial = nullptr;
+    S2I_TRY(gn_partial((size_t)B * grid.x * 2 * kGroups, &partial));
+    gn_reduce_kernel<0><<<grid, 256, 0, st>>>(x, ldx, nullptr, 0, HW, C, P, nullptr, nullptr, nullptr, eps, 0, partial, sums);
     S2I_LAUNCH_CHECK();
     return 0;
 }
@@ -596,7 +934,9 @@ int gn_bwd_stats(const float* dy, long ldd, const float* x, long ldx, int B, int
     S2I_REQ(C % kGroups == 0 && (ldx & 3) == 0 && (ldd & 3) == 0, "gn_bwd_stats: alignment");
     const int P = gn_chunk(B, HW);
     dim3 grid(ceil_div(HW, P), B);
-    gn_reduce_kernel<1><<<grid, 256, 0, st>>>(x, ldx, dy, ldd, HW, C, P, sums, gamma, beta, eps, silu, bsums);
+    double* partial = nullptr;
+    S2I_TRY(gn_partial((size_t)B * grid.x * 2 * kGroups, &partial));
+    gn_reduce_kernel<1><<<grid, 256, 0, st>>>(x, ldx, dy, ldd, HW, C, P, sums, gamma, beta, eps, silu, partial, bsums);
     S2I_LAUNCH_CHECK();
     return 0;
 }
@@ -609,6 +949,62 @@ int gn_bwd_apply(const float* dy, long ldd, const float* x, long ldx, int B, int
     dim3 grid(grid_for((long)HW * (C >> 2), 256, 148 * 8), B);
     gn_bwd_apply_kernel<<<grid, 256, 0, st>>>(dy, ldd, x, ldx, HW, C, sums, bsums, gamma, beta, eps, silu, add, ldadd,
                                              dx32, ld32, (__half*)dx16, ld16);
+    S2I_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- fused launchers (see gn_fused_kernel); fall back to the two-kernel form when the batch exceeds the SM count
+static bool gn_fused_geometry(int B, int HW, int C, int* nblk, int* P) {
+    if (B > kNumSMs || C > 2560) return false;
+    int n = kNumSMs / B;
+    int p = ceil_div(HW, n);
+    if (p < 4) p = 4;
+    n = ceil_div(HW, p);
+    *nblk = n;
+    *P = p;
+    return true;
+}
+
+int gn_forward(const float* x, long ldx, int B, int HW, int C, double* slot, const float* gamma, const float* beta, float eps,
+               int silu, void* out16, long ld16, void* raw16, long ldraw, cudaStream_t st) {
+    S2I_REQ(C % 4 == 0 && C % kGroups == 0 && (ldx & 3) == 0 && (ld16 & 3) == 0 && (ldraw & 3) == 0, "gn_forward: alignment");
+    int nblk, P;
+    if (!gn_fused_geometry(B, HW, C, &nblk, &P)) {
+        S2I_TRY(gn_stats(x, ldx, B, HW, C, eps, slot, st));
+        return gn_apply(x, ldx, B, HW, C, slot, gamma, beta, eps, silu, out16, ld16, raw16, ldraw, st);
+    }
+    GnFusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.ldx = ldx; a.HW = HW; a.C = C; a.P = P;
+    a.gamma = gamma; a.beta = beta; a.eps = eps; a.silu = silu;
+    S2I_TRY(gn_partial((size_t)B * nblk * 2 * kGroups, &a.partial));
+    a.slot = slot;
+    a.out16 = (__half*)out16; a.ld16 = ld16; a.raw16 = (__half*)raw16; a.ldraw = ldraw;
+    gn_fused_kernel<0><<<dim3(nblk, B), 512, 0, st>>>(a);
+    S2I_LAUNCH_CHECK();
+    return 0;
+}
+
+int gn_backward(const float* dy, long ldd, const float* x, long ldx, int B, int HW, int C, const double* fslot, double* bslot,
+                const float* gamma, const float* beta, float eps, int silu, const float* add, long ldadd, float* dx32,
+                long ld32, void* dx16, long ld16, cudaStream_t st) {
+    S2I_REQ(C % 4 == 0 && C % kGroups == 0 && (ldx & 3) == 0 && (ldd & 3) == 0 && (ldadd & 3) == 0 && (ld32 & 3) == 0 &&
+                (ld16 & 3) == 0, "gn_backward: alignment");
+    int nblk, P;
+    if (!gn_fused_geometry(B, HW, C, &nblk, &P)) {
+        S2I_TRY(gn_bwd_stats(dy, ldd, x, ldx, B, HW, C, fslot, gamma, beta, eps, silu, bslot, st));
+        return gn_bwd_apply(dy, ldd, x, ldx, B, HW, C, fslot, bslot, gamma, beta, eps, silu, add, ldadd, dx32, ld32, dx16,
+                            ld16, st);
+    }
+    GnFusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.ldx = ldx; a.dy = dy; a.ldd = ldd; a.HW = HW; a.C = C; a.P = P;
+    a.fslot = fslot;
+    a.gamma = gamma; a.beta = beta; a.eps = eps; a.silu = silu;
+    S2I_TRY(gn_partial((size_t)B * nblk * 2 * kGroups, &a.partial));
+    a.slot = bslot;
+    a.add = add; a.ldadd = ldadd; a.dx32 = dx32; a.ld32 = ld32; a.out16 = (__half*)dx16; a.ld16 = ld16;
+    gn_fused_kernel<1><<<dim3(nblk, B), 512, 0, st>>>(a);
     S2I_LAUNCH_CHECK();
     return 0;
 }

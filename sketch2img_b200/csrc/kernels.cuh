@@ -9,18 +9,26 @@ namespace s2i {
 constexpr int kGroups = 32;   // GroupNorm groups (norm_num_groups of every SD UNet)
 
 // ---- GroupNorm (per sample, per group over (C/32) x HW), optionally fused with SiLU ------------------------
-// sums: double [B][32][2] = (sum x, sum x^2); must be zero on entry to gn_stats.
-int gn_stats(const float* x, long ldx, int B, int HW, int C, double* sums, cudaStream_t st);
+// sums: the call's statistics slot, 64 doubles (512 bytes) per sample, zero-initialised once by the caller:
+// gn_stats leaves float2[32] = (mean, rstd) per sample in it (the rest is the reduction's self-resetting arrival counter).
+int gn_stats(const float* x, long ldx, int B, int HW, int C, float eps, double* sums, cudaStream_t st);
 // out16 = fp16( act( (x-mean)*rstd*gamma + beta ) ); raw16 (optional) = fp16(x)
 int gn_apply(const float* x, long ldx, int B, int HW, int C, const double* sums, const float* gamma, const float* beta,
              float eps, int silu, void* out16, long ld16, void* raw16, long ldraw, cudaStream_t st);
-// Backward.  bsums: double [B][32][2] = (sum dxhat, sum dxhat*xhat); zero on entry to gn_bwd_stats.
+// Backward.  bsums: a second slot of the same shape; receives float2[32] = (mean dxhat, mean dxhat*xhat) per sample.
 int gn_bwd_stats(const float* dy, long ldd, const float* x, long ldx, int B, int HW, int C, const double* sums,
                  const float* gamma, const float* beta, float eps, int silu, double* bsums, cudaStream_t st);
 // dx = rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)) (+ add);  written as fp32 (dx32) and/or fp16 (dx16)
 int gn_bwd_apply(const float* dy, long ldd, const float* x, long ldx, int B, int HW, int C, const double* sums,
                  const double* bsums, const float* gamma, const float* beta, float eps, int silu, const float* add,
                  long ldadd, float* dx32, long ld32, void* dx16, long ld16, cudaStream_t st);
+
+// Fused forms (one launch: reduction, grid-wide arrival, apply); same slot convention as above.
+int gn_forward(const float* x, long ldx, int B, int HW, int C, double* slot, const float* gamma, const float* beta, float eps,
+               int silu, void* out16, long ld16, void* raw16, long ldraw, cudaStream_t st);
+int gn_backward(const float* dy, long ldd, const float* x, long ldx, int B, int HW, int C, const double* fslot, double* bslot,
+                const float* gamma, const float* beta, float eps, int silu, const float* add, long ldadd, float* dx32,
+                long ld32, void* dx16, long ld16, cudaStream_t st);
 
 // ---- LayerNorm over the last dim (one warp per row) --------------------------------------------------------
 int ln_fwd(const float* x, long ldx, long rows, int C, const float* gamma, const float* beta, float eps, void* out16,

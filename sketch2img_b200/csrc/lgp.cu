@@ -31,8 +31,9 @@ __device__ __forceinline__ void src_index(int dst, float scale, int S, int& i0, 
 
 // X[(b,h,w)][col] = fp16( bilinear(tap_k)[b][:, h, w] | sigma*noise | sin(2 pi lvl 2^-l) ), zero padded to ldX
 __global__ void __launch_bounds__(256) lgp_features_kernel(TapTable tt, int B, int L, const float* __restrict__ noise,
-                                                           float sigma, int P, int D, __half* __restrict__ X,
-                                                           long ldX) {
+                                                           float sigma, const float* __restrict__ dsigma, int P, int D,
+                                                           __half* __restrict__ X, long ldX) {
+    if (dsigma) sigma = __ldg(dsigma);      // graph-replayed steps read the step's scalars from device memory
     const int chunks = (int)(ldX >> 3);
     const long total = (long)B * L * L * chunks;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -325,7 +326,14 @@ __global__ void lgp_export_kernel(const __half* __restrict__ out16, int B, int L
 // ------------------------------------------------------------------------------------------ scheduler / update
 __global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eps, int S,
                                                        int n, float g, float sb_t, float sa_t, float sa_p, float sb_p,
-                                                       int prediction, float* __restrict__ out) {
+                                                       const float* __restrict__ dparams, int prediction,
+                                                       float* __restrict__ out) {
+    if (dparams) {      // graph-replayed steps read the step's scalars from device memory
+        sb_t = __ldg(dparams + 0);
+        sa_t = __ldg(dparams + 1);
+        sa_p = __ldg(dparams + 2);
+        sb_p = __ldg(dparams + 3);
+    }
     const long total = (long)S * n;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const long s = idx / n, i = idx - s * n;
@@ -474,6 +482,7 @@ int LGP::ensure(size_t bytes) {
         cudaGetLastError();
         return set_error(S2I_ERR_OOM, "lgp: cannot allocate %.2f GB workspace", bytes / 1e9);
     }
+    ++g_alloc_gen;
     buf_ = static_cast<char*>(p);
     buf_cap_ = bytes;
     return 0;
@@ -565,7 +574,8 @@ int LGP::mlp(cudaStream_t st) {
     return 0;
 }
 
-int LGP::forward(const LgpTap taps[9], int B, int L, const float* noise, float sigma, bool train, cudaStream_t st) {
+int LGP::forward(const LgpTap taps[9], int B, int L, const float* noise, float sigma, bool train, cudaStream_t st,
+                 const float* dsigma) {
     if (!loaded_) return set_error(S2I_ERR_STATE, "lgp: weights not loaded");
     if (B % 2 != 0) return set_error(S2I_ERR_ARG, "lgp: batch must hold (uncond, cond) pairs");
     TapTable tt;
@@ -587,7 +597,7 @@ int LGP::forward(const LgpTap taps[9], int B, int L, const float* noise, float s
     groups_ = B / 2;
     S2I_TRY(ensure(lgp_ws_bytes(rows, ldX_, B / 2)));
     X_ = reinterpret_cast<__half*>(buf_);   // first workspace slot (see mlp())
-    lgp_features_kernel<<<grid1d(rows * (ldX_ / 8)), 256, 0, st>>>(tt, B, L, noise, sigma, P_, D_, X_, ldX_);
+    lgp_features_kernel<<<grid1d(rows * (ldX_ / 8)), 256, 0, st>>>(tt, B, L, noise, sigma, dsigma, P_, D_, X_, ldX_);
     S2I_LAUNCH_CHECK();
     return mlp(st);
 }
@@ -675,9 +685,9 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
 
 // ================================================================================================== step
 int cfg_ddim_step(const float* latents, const float* eps, int S, int n, float guidance, float sb_t, float sa_t,
-                  float sa_p, float sb_p, int prediction, float* out, cudaStream_t st) {
-    cfg_ddim_kernel<<<grid1d((long)S * n), 256, 0, st>>>(latents, eps, S, n, guidance, sb_t, sa_t, sa_p, sb_p, prediction,
-                                                         out);
+                  float sa_p, float sb_p, int prediction, float* out, cudaStream_t st, const float* dparams) {
+    cfg_ddim_kernel<<<grid1d((long)S * n), 256, 0, st>>>(latents, eps, S, n, guidance, sb_t, sa_t, sa_p, sb_p, dparams,
+                                                         prediction, out);
     S2I_LAUNCH_CHECK();
     return 0;
 }

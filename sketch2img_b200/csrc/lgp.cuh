@@ -28,7 +28,9 @@ class LGP {
     // Forward on B = 2*samples latents of side L.  noise: NCHW fp32 [samples,4,L,L]; lvl = sigma * noise is the
     // "noise level" input shared by both CFG halves (pipeline.py:152-153).  Rows are ordered (b, h, w).
     // out16: fp16 [B*L*L][8] (first output_dim columns valid).
-    int forward(const LgpTap taps[9], int B, int L, const float* noise, float sigma, bool train, cudaStream_t st);
+    // dsigma (optional, device): overrides `sigma` at run time (graph-replayed steps).
+    int forward(const LgpTap taps[9], int B, int L, const float* noise, float sigma, bool train, cudaStream_t st,
+                const float* dsigma = nullptr);
     // Edge loss on the cond half + backward to the taps.  target: NCHW fp32 [samples,4,L,L].
     // tap_grads[k]: NHWC fp32 like tap k, multiplied by grad_scale(); loss: device float [samples].
     int loss_backward(const float* target, float* const tap_grads[9], float* loss, cudaStream_t st);
@@ -81,8 +83,9 @@ class LGP {
 
 // ---- scheduler / guidance update (modules/pipeline.py:100-104, :160-161; DDIM step per SURVEY A.6) -----------
 // eps: [2*S][n] ordered (uncond_s, cond_s); latents: [S][n].  prediction: 0 = epsilon, 1 = v_prediction.
+// dparams (optional, device float[4] = sb_t, sa_t, sa_p, sb_p): overrides the by-value coefficients (graph-replayed steps).
 int cfg_ddim_step(const float* latents, const float* eps, int S, int n, float guidance, float sb_t, float sa_t,
-                  float sa_p, float sb_p, int prediction, float* out, cudaStream_t st);
+                  float sa_p, float sb_p, int prediction, float* out, cudaStream_t st, const float* dparams = nullptr);
 // x_new += beta * ||x_in - x_new||_F / ||g||_F * g with g = -dx[cond half]; norms per sample; x_in = [x_old, x_old].
 // dx: [2*S][n].  scratch: double [S][2] device.
 int guidance_update(const float* x_old, float* x_new, const float* dx, int S, int n, float beta, double* scratch,

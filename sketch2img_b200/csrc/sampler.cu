@@ -7,6 +7,9 @@
 #include "lgp.cuh"
 #include "unet.cuh"
 
+#include <cstdlib>
+#include <vector>
+
 struct s2i_unet {
     s2i::UNet* impl;
 };
@@ -20,23 +23,146 @@ class Sampler {
   public:
     UNet* unet;
     LGP* lgp;
-    Sampler(UNet* u, LGP* l) : unet(u), lgp(l) {}
+    bool use_graphs = true;      // S2I_NO_GRAPH=1 disables
+    Sampler(UNet* u, LGP* l) : unet(u), lgp(l) {
+        if (const char* e = getenv("S2I_NO_GRAPH")) use_graphs = !(e[0] == '1');
+    }
     ~Sampler() {
+        drop_graphs();
         if (buf_) cudaFree(buf_);
+        if (d_sp_) cudaFree(d_sp_);
+        if (h_sp_) cudaFreeHost(h_sp_);
+        if (cap_stream_) cudaStreamDestroy(cap_stream_);
     }
 
+    // One denoising step.  Everything that depends on the timestep is done up front, outside the replayed part: the
+    // time embedding (UNet::prepare_time, cached per t) and the step's scalars (DDIM coefficients, noise level), which
+    // the kernels read from a small device buffer.  The remaining ~400 (unguided) / ~900 (guided) launches are identical
+    // from step to step -- same kernels, same arena addresses -- so the second call with the same arguments captures
+    // them into a CUDA graph and later calls replay it (no host launch cost, no inter-kernel gaps).
     int step(float* latents, const float* noise, const float* ctx, const float* target, int S, int L, float t,
              float guidance, float sa_t, float sb_t, float sa_p, float sb_p, int prediction, int guided, float sigma,
              float beta, int lgp_train, float* loss_out, cudaStream_t st) {
-        const int C = unet->cfg.in_ch;
-        const int n = C * L * L;
-        const int B = 2 * S;
-        // scratch: x_in [B][n] | eps [B][n] | dx [B][n] | x_new [S][n] | loss [S] | norms double [S][2] | tap grads
+        const bool do_guide = guided && target != nullptr && lgp != nullptr;
+        S2I_TRY(ensure_params());
+        float* hp = h_sp_ + (ring_++ % kRing) * 8;
+        hp[0] = sb_t; hp[1] = sa_t; hp[2] = sa_p; hp[3] = sb_p; hp[4] = sigma;
+        S2I_CUDA(cudaMemcpyAsync(d_sp_, hp, 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+        S2I_TRY(unet->prepare_time(t, st));
+
+        Key key{S, L, prediction, do_guide ? 1 : 0, lgp_train, guidance, beta};
+        // The replayed part works on sampler-owned copies of the caller's tensors, so one graph serves every image.
+        S2I_TRY(layout(key));
+        const size_t nb = (size_t)S * unet->cfg.in_ch * L * L * sizeof(float);
+        S2I_CUDA(cudaMemcpyAsync(own_lat_, latents, nb, cudaMemcpyDeviceToDevice, st));
+        S2I_CUDA(cudaMemcpyAsync(own_ctx_, ctx, (size_t)2 * S * unet->cfg.ctx_len * unet->cfg.cross_dim * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+        if (do_guide) {
+            S2I_CUDA(cudaMemcpyAsync(own_noise_, noise, nb, cudaMemcpyDeviceToDevice, st));
+            S2I_CUDA(cudaMemcpyAsync(own_target_, target, nb, cudaMemcpyDeviceToDevice, st));
+        }
+        S2I_TRY(run(key, st));
+        S2I_CUDA(cudaMemcpyAsync(latents, own_lat_, nb, cudaMemcpyDeviceToDevice, st));
+        if (do_guide && loss_out) S2I_CUDA(cudaMemcpyAsync(loss_out, own_loss_, S * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+
+  private:
+    struct Key {
+        int S, L, prediction, guided, train;
+        float guidance, beta;
+        bool operator==(const Key& o) const {
+            return S == o.S && L == o.L && prediction == o.prediction && guided == o.guided && train == o.train &&
+                   guidance == o.guidance && beta == o.beta;
+        }
+    };
+    struct Entry {
+        Key key;
+        cudaGraphExec_t exec;
+        long launches;
+        long alloc_gen;
+    };
+
+    int run(const Key& key, cudaStream_t st) {
+        if (!use_graphs || g_prof_on) return body(key, st);
+        Entry* e = nullptr;
+        for (auto& c : graphs_)
+            if (c.key == key) e = &c;
+        if (!e) {
+            // first sighting: run eagerly (sizes every arena / scratch buffer; allocations are illegal during capture)
+            if (graphs_.size() >= 8) drop_graphs();
+            graphs_.push_back(Entry{key, nullptr, 0, g_alloc_gen});
+            return body(key, st);
+        }
+        if (e->exec && e->alloc_gen != g_alloc_gen) {     // some scratch buffer moved since the capture: stale addresses
+            cudaGraphExecDestroy(e->exec);
+            e->exec = nullptr;
+        }
+        if (!e->exec) {
+            if (!cap_stream_) S2I_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
+            const long l0 = g_launches;
+            S2I_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
+            const int rc = body(key, cap_stream_);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(cap_stream_, &graph);
+            if (rc != 0 || ce != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                use_graphs = false;                     // fall back to plain launches for good
+                return body(key, st);
+            }
+            e->launches = g_launches - l0;
+            g_launches = l0;
+            const cudaError_t ie = cudaGraphInstantiate(&e->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) {
+                cudaGetLastError();
+                e->exec = nullptr;
+                use_graphs = false;
+                return body(key, st);
+            }
+            e->alloc_gen = g_alloc_gen;
+        }
+        S2I_CUDA(cudaGraphLaunch(e->exec, st));
+        g_launches += e->launches;
+        return 0;
+    }
+
+    static constexpr int kRing = 256;
+    std::vector<Entry> graphs_;
+    cudaStream_t cap_stream_ = nullptr;
+    float* d_sp_ = nullptr;      // device: sb_t, sa_t, sa_p, sb_p, sigma
+    float* h_sp_ = nullptr;      // pinned ring of the same
+    unsigned ring_ = 0;
+    char* buf_ = nullptr;
+    size_t cap_ = 0;
+
+    void drop_graphs() {
+        for (auto& c : graphs_)
+            if (c.exec) cudaGraphExecDestroy(c.exec);
+        graphs_.clear();
+    }
+    int ensure_params() {
+        if (d_sp_) return 0;
+        S2I_CUDA(cudaMalloc(&d_sp_, 8 * sizeof(float)));
+        S2I_CUDA(cudaMallocHost(&h_sp_, kRing * 8 * sizeof(float)));
+        return 0;
+    }
+
+    // scratch layout for a key: caller copies | x_in [B][n] | eps | dx | x_new [S][n] | loss | norms | tap gradients
+    float *own_lat_ = nullptr, *own_noise_ = nullptr, *own_ctx_ = nullptr, *own_target_ = nullptr, *own_loss_ = nullptr;
+    float *x_in_ = nullptr, *eps_ = nullptr, *dx_ = nullptr, *x_new_ = nullptr;
+    double* norms_ = nullptr;
+    float* tg_[9] = {};
+    int layout(const Key& k) {
+        const int S = k.S, L = k.L, B = 2 * S;
+        const int n = unet->cfg.in_ch * L * L;
         const int* boc = unet->cfg.boc;
         const int tapS[9] = {L / 2, L / 4, L / 8, L / 8, L / 8, L / 8, L / 4, L / 2, L};
         const int tapC[9] = {boc[0], boc[1], boc[2], boc[3], boc[3], boc[3], boc[3], boc[2], boc[1]};
-        size_t need = (size_t)(3 * B + S) * n * sizeof(float) + (size_t)S * 20 + 16 * 256;
-        for (int k = 0; k < 9; ++k) need += (size_t)B * tapS[k] * tapS[k] * tapC[k] * 4 + 256;
+        const size_t ctx_bytes = (size_t)B * unet->cfg.ctx_len * unet->cfg.cross_dim * sizeof(float);
+        size_t need = (size_t)(3 * B + 4 * S) * n * sizeof(float) + ctx_bytes + (size_t)S * 20 + 32 * 256;
+        for (int q = 0; q < 9; ++q) need += (size_t)B * tapS[q] * tapS[q] * tapC[q] * 4 + 256;
         S2I_TRY(ensure(need));
         char* p = buf_;
         auto take = [&](size_t bytes) {
@@ -44,45 +170,50 @@ class Sampler {
             p += (bytes + 255) & ~size_t(255);
             return q;
         };
-        float* x_in = (float*)take((size_t)B * n * 4);
-        float* eps = (float*)take((size_t)B * n * 4);
-        float* dx = (float*)take((size_t)B * n * 4);
-        float* x_new = (float*)take((size_t)S * n * 4);
-        float* loss = (float*)take((size_t)S * 4);
-        double* norms = (double*)take((size_t)S * 16);
-
-        // x_in = cat([latents] * 2) per sample, ordered (uncond_s, cond_s)   (pipeline.py:85)
-        for (int s = 0; s < S; ++s) {
-            S2I_CUDA(cudaMemcpyAsync(x_in + (size_t)(2 * s) * n, latents + (size_t)s * n, n * 4, cudaMemcpyDeviceToDevice, st));
-            S2I_CUDA(cudaMemcpyAsync(x_in + (size_t)(2 * s + 1) * n, latents + (size_t)s * n, n * 4, cudaMemcpyDeviceToDevice, st));
-        }
-        const bool do_guide = guided && target != nullptr && lgp != nullptr;
-        S2I_TRY(unet->forward(x_in, B, L, L, t, ctx, eps, do_guide, st));                          // :96
-        S2I_TRY(cfg_ddim_step(latents, eps, S, n, guidance, sb_t, sa_t, sa_p, sb_p, prediction, x_new, st));   // :100-104
-        if (do_guide) {
-            // taps -> LGP -> edge loss -> tap gradients   (:145-159, LGP part)
-            LgpTap taps[9];
-            for (int k = 0; k < 9; ++k) {
-                const F32& tp = unet->taps[k];
-                if (tp.H != tp.W) return set_error(S2I_ERR_ARG, "guided sampling needs square latents (pipeline.py:147)");
-                taps[k] = LgpTap{tp.p, tp.H, tp.C};
-                if (tp.H != tapS[k] || tp.C != tapC[k]) return set_error(S2I_ERR_STATE, "sampler: unexpected tap %d geometry", k);
-            }
-            float* tg[9];
-            for (int k = 0; k < 9; ++k) tg[k] = (float*)take((size_t)unet->taps[k].rows() * unet->taps[k].C * 4);
-            S2I_TRY(lgp->forward(taps, B, L, noise, sigma, lgp_train != 0, st));
-            S2I_TRY(lgp->loss_backward(target, tg, loss, st));
-            S2I_TRY(unet->backward(tg, dx, st));                                                     // :159 (UNet part)
-            S2I_TRY(guidance_update(latents, x_new, dx, S, n, beta, norms, st));                     // :160-161
-            if (loss_out) S2I_CUDA(cudaMemcpyAsync(loss_out, loss, S * 4, cudaMemcpyDeviceToDevice, st));
-        }
-        S2I_CUDA(cudaMemcpyAsync(latents, x_new, (size_t)S * n * 4, cudaMemcpyDeviceToDevice, st));
+        own_lat_ = (float*)take((size_t)S * n * 4);
+        own_noise_ = (float*)take((size_t)S * n * 4);
+        own_target_ = (float*)take((size_t)S * n * 4);
+        own_ctx_ = (float*)take(ctx_bytes);
+        own_loss_ = (float*)take((size_t)S * 4);
+        x_in_ = (float*)take((size_t)B * n * 4);
+        eps_ = (float*)take((size_t)B * n * 4);
+        dx_ = (float*)take((size_t)B * n * 4);
+        x_new_ = (float*)take((size_t)S * n * 4);
+        norms_ = (double*)take((size_t)S * 16);
+        for (int q = 0; q < 9; ++q) tg_[q] = (float*)take((size_t)B * tapS[q] * tapS[q] * tapC[q] * 4);
         return 0;
     }
 
-  private:
-    char* buf_ = nullptr;
-    size_t cap_ = 0;
+    // the timestep-independent part of the step (reads the step's scalars from d_sp_; works on the owned copies)
+    int body(const Key& k, cudaStream_t st) {
+        const int S = k.S, L = k.L;
+        const int n = unet->cfg.in_ch * L * L;
+        const int B = 2 * S;
+        // x_in = cat([latents] * 2) per sample, ordered (uncond_s, cond_s)   (pipeline.py:85)
+        for (int s = 0; s < S; ++s) {
+            S2I_CUDA(cudaMemcpyAsync(x_in_ + (size_t)(2 * s) * n, own_lat_ + (size_t)s * n, n * 4, cudaMemcpyDeviceToDevice, st));
+            S2I_CUDA(cudaMemcpyAsync(x_in_ + (size_t)(2 * s + 1) * n, own_lat_ + (size_t)s * n, n * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        const bool do_guide = k.guided != 0;
+        S2I_TRY(unet->forward(x_in_, B, L, L, 0.f, own_ctx_, eps_, do_guide, st, /*time_ready=*/true));    // :96
+        S2I_TRY(cfg_ddim_step(own_lat_, eps_, S, n, k.guidance, 0.f, 1.f, 1.f, 0.f, k.prediction, x_new_, st, d_sp_));   // :100-104
+        if (do_guide) {
+            // taps -> LGP -> edge loss -> tap gradients   (:145-159, LGP part)
+            LgpTap taps[9];
+            for (int q = 0; q < 9; ++q) {
+                const F32& tp = unet->taps[q];
+                if (tp.H != tp.W) return set_error(S2I_ERR_ARG, "guided sampling needs square latents (pipeline.py:147)");
+                taps[q] = LgpTap{tp.p, tp.H, tp.C};
+            }
+            S2I_TRY(lgp->forward(taps, B, L, own_noise_, 0.f, k.train != 0, st, d_sp_ + 4));
+            S2I_TRY(lgp->loss_backward(own_target_, tg_, own_loss_, st));
+            S2I_TRY(unet->backward(tg_, dx_, st));                                                   // :159 (UNet part)
+            S2I_TRY(guidance_update(own_lat_, x_new_, dx_, S, n, k.beta, norms_, st));               // :160-161
+        }
+        S2I_CUDA(cudaMemcpyAsync(own_lat_, x_new_, (size_t)S * n * 4, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+
     int ensure(size_t bytes) {
         if (bytes <= cap_) return 0;
         if (buf_) {
@@ -91,11 +222,13 @@ class Sampler {
         }
         buf_ = nullptr;
         cap_ = 0;
+        drop_graphs();
         void* q = nullptr;
         if (cudaMalloc(&q, bytes) != cudaSuccess) {
             cudaGetLastError();
             return set_error(S2I_ERR_OOM, "sampler: cannot allocate %.2f GB scratch", bytes / 1e9);
         }
+        ++g_alloc_gen;
         buf_ = static_cast<char*>(q);
         cap_ = bytes;
         return 0;

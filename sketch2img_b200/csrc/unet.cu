@@ -367,6 +367,15 @@ int UNet::load(const std::map<std::string, HostParam>& params) {
     }
     if (L.staging) cudaFree(L.staging);
     if (cudaDeviceSynchronize() != cudaSuccess) return set_error(S2I_ERR_CUDA, "unet load: %s", cudaGetErrorString(cudaGetLastError()));
+    {
+        const int temb_dim = boc[0] * 4;
+        Loader L2{params, owned_};
+        temb_ = L2.dmalloc<float>(temb_all_.N);
+        te0_ = L2.dmalloc<float>(boc[0]);
+        te1_ = L2.dmalloc<float>(temb_dim);
+        te2_ = L2.dmalloc<float>(temb_dim);
+        if (!temb_ || !te0_ || !te1_ || !te2_) return set_error(S2I_ERR_OOM, "unet load: time-embedding buffers");
+    }
     rsave_.resize(res_.size());
     tsave_.resize(tfm_.size());
     loaded_ = true;
@@ -460,18 +469,16 @@ int UNet::resblock(int idx, const F32& x, F32& out) {
     const ResBlock& R = res_[idx];
     const int B = x.B, H = x.H, W = x.W, HW = H * W;
     double* s1 = new_stats();
-    RUN(gn_stats(x.p, x.ld, B, HW, R.Cin, s1, st_));
     H16 a1 = new16(B, H, W, R.Cin);
     H16 x16;
     if (R.has_sc) x16 = new16(B, H, W, R.Cin);
-    RUN(gn_apply(x.p, x.ld, B, HW, R.Cin, s1, R.n1.g, R.n1.b, R.n1.eps, 1, a1.p, a1.ld, R.has_sc ? x16.p : nullptr,
-                 R.has_sc ? x16.ld : 0, st_));
+    RUN(gn_forward(x.p, x.ld, B, HW, R.Cin, s1, R.n1.g, R.n1.b, R.n1.eps, 1, a1.p, a1.ld, R.has_sc ? x16.p : nullptr,
+                   R.has_sc ? x16.ld : 0, st_));
     F32 h1 = new32(B, H, W, R.Cout);
     S2I_TRY(gemm(a1, true, 9, R.c1.w, 9L * R.Cin, R.Cout, R.Cin, R.c1.b, temb_ + R.temb_off, nullptr, &h1, nullptr));
     double* s2 = new_stats();
-    RUN(gn_stats(h1.p, h1.ld, B, HW, R.Cout, s2, st_));
     H16 a2 = new16(B, H, W, R.Cout);
-    RUN(gn_apply(h1.p, h1.ld, B, HW, R.Cout, s2, R.n2.g, R.n2.b, R.n2.eps, 1, a2.p, a2.ld, nullptr, 0, st_));
+    RUN(gn_forward(h1.p, h1.ld, B, HW, R.Cout, s2, R.n2.g, R.n2.b, R.n2.eps, 1, a2.p, a2.ld, nullptr, 0, st_));
     F32 res = x;
     if (R.has_sc) {
         F32 sc = new32(B, H, W, R.Cout);
@@ -502,23 +509,21 @@ int UNet::resblock_bwd(int idx, const F32& dout, F32& dx) {
     F32 da2 = new32(B, H, W, R.Cout);
     S2I_TRY(gemm(d16, true, 9, R.c2.wd, 9L * R.Cout, R.Cout, R.Cout, nullptr, nullptr, nullptr, &da2, nullptr));
     double* bs2 = new_stats();
-    RUN(gn_bwd_stats(da2.p, da2.ld, S.h1.p, S.h1.ld, B, HW, R.Cout, S.s2, R.n2.g, R.n2.b, R.n2.eps, 1, bs2, st_));
     H16 dh1 = new16(B, H, W, R.Cout);
-    RUN(gn_bwd_apply(da2.p, da2.ld, S.h1.p, S.h1.ld, B, HW, R.Cout, S.s2, bs2, R.n2.g, R.n2.b, R.n2.eps, 1, nullptr, 0,
-                     nullptr, 0, dh1.p, dh1.ld, st_));
+    RUN(gn_backward(da2.p, da2.ld, S.h1.p, S.h1.ld, B, HW, R.Cout, S.s2, bs2, R.n2.g, R.n2.b, R.n2.eps, 1, nullptr, 0,
+                    nullptr, 0, dh1.p, dh1.ld, st_));
     F32 da1 = new32(B, H, W, R.Cin);
     S2I_TRY(gemm(dh1, true, 9, R.c1.wd, 9L * R.Cout, R.Cin, R.Cout, nullptr, nullptr, nullptr, &da1, nullptr));
     double* bs1 = new_stats();
-    RUN(gn_bwd_stats(da1.p, da1.ld, S.x.p, S.x.ld, B, HW, R.Cin, S.s1, R.n1.g, R.n1.b, R.n1.eps, 1, bs1, st_));
     dx = new32(B, H, W, R.Cin);
     if (R.has_sc) {
         F32 tmp = new32(B, H, W, R.Cin);
-        RUN(gn_bwd_apply(da1.p, da1.ld, S.x.p, S.x.ld, B, HW, R.Cin, S.s1, bs1, R.n1.g, R.n1.b, R.n1.eps, 1, nullptr, 0,
-                         tmp.p, tmp.ld, nullptr, 0, st_));
+        RUN(gn_backward(da1.p, da1.ld, S.x.p, S.x.ld, B, HW, R.Cin, S.s1, bs1, R.n1.g, R.n1.b, R.n1.eps, 1, nullptr, 0,
+                        tmp.p, tmp.ld, nullptr, 0, st_));
         S2I_TRY(gemm(d16, false, 1, R.sc.wd, R.Cout, R.Cin, R.Cout, nullptr, nullptr, &tmp, &dx, nullptr));
     } else {
-        RUN(gn_bwd_apply(da1.p, da1.ld, S.x.p, S.x.ld, B, HW, R.Cin, S.s1, bs1, R.n1.g, R.n1.b, R.n1.eps, 1, dout.p,
-                         dout.ld, dx.p, dx.ld, nullptr, 0, st_));
+        RUN(gn_backward(da1.p, da1.ld, S.x.p, S.x.ld, B, HW, R.Cin, S.s1, bs1, R.n1.g, R.n1.b, R.n1.eps, 1, dout.p,
+                        dout.ld, dx.p, dx.ld, nullptr, 0, st_));
     }
     return 0;
 }
@@ -655,9 +660,8 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     TfmSave sv;
     sv.x = x;
     sv.gs = new_stats();
-    RUN(gn_stats(x.p, x.ld, B, HW, C, sv.gs, st_));
     H16 n16 = new16(B, H, W, C);
-    RUN(gn_apply(x.p, x.ld, B, HW, C, sv.gs, T.gn.g, T.gn.b, T.gn.eps, 0, n16.p, n16.ld, nullptr, 0, st_));
+    RUN(gn_forward(x.p, x.ld, B, HW, C, sv.gs, T.gn.g, T.gn.b, T.gn.eps, 0, n16.p, n16.ld, nullptr, 0, st_));
     sv.t0 = new32(B, H, W, C);
     S2I_TRY(gemm(n16, false, 1, T.proj_in.w, C, C, C, T.proj_in.b, nullptr, nullptr, &sv.t0, nullptr));
     // --- self attention
@@ -749,9 +753,8 @@ int UNet::transformer_bwd(int idx, const F32& dout, F32& dx) {
     F32 dn = new32(B, H, W, C);
     S2I_TRY(gemm(dt0h, false, 1, T.proj_in.wd, C, C, C, nullptr, nullptr, nullptr, &dn, nullptr));
     double* bs = new_stats();
-    RUN(gn_bwd_stats(dn.p, dn.ld, S.x.p, S.x.ld, B, HW, C, S.gs, T.gn.g, T.gn.b, T.gn.eps, 0, bs, st_));
     dx = new32(B, H, W, C);
-    RUN(gn_bwd_apply(dn.p, dn.ld, S.x.p, S.x.ld, B, HW, C, S.gs, bs, T.gn.g, T.gn.b, T.gn.eps, 0, dout.p, dout.ld, dx.p,
+    RUN(gn_backward(dn.p, dn.ld, S.x.p, S.x.ld, B, HW, C, S.gs, bs, T.gn.g, T.gn.b, T.gn.eps, 0, dout.p, dout.ld, dx.p,
                      dx.ld, nullptr, 0, st_));
     return 0;
 }
@@ -769,16 +772,8 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
     if (!dry_) S2I_CUDA(cudaMemsetAsync(stats_, 0, stats_cap_ * sizeof(double), st_));
     debug.clear();
 
-    // time embedding -> fused per-resnet projections
-    const int temb_dim = boc[0] * 4;
-    float* e0 = dalloc<float>(boc[0]);
-    float* e1 = dalloc<float>(temb_dim);
-    float* e2 = dalloc<float>(temb_dim);
-    temb_ = dalloc<float>(temb_all_.N);
-    RUN(timestep_embedding(t, boc[0], e0, st_));
-    RUN(gemv(e0, boc[0], time1_.w, time1_.b, temb_dim, 0, e1, st_));
-    RUN(gemv(e1, temb_dim, time2_.w, time2_.b, temb_dim, 1, e2, st_));
-    RUN(gemv(e2, temb_dim, temb_all_.w, temb_all_.b, temb_all_.N, 1, temb_, st_));
+    // time embedding -> fused per-resnet projections (persistent buffer; see prepare_time)
+    if (!dry_ && !time_ready_) S2I_TRY(prepare_time(t, st_));
 
     // text context as fp16 GEMM operand
     ctx16_ = new16(B, 1, cfg.ctx_len, cfg.cross_dim);
@@ -864,9 +859,8 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
     }
     // ---- out
     double* so = new_stats();
-    RUN(gn_stats(h.p, h.ld, B, H * W, boc[0], so, st_));
     H16 a = new16(B, H, W, boc[0]);
-    RUN(gn_apply(h.p, h.ld, B, H * W, boc[0], so, norm_out_.g, norm_out_.b, norm_out_.eps, 1, a.p, a.ld, nullptr, 0, st_));
+    RUN(gn_forward(h.p, h.ld, B, H * W, boc[0], so, norm_out_.g, norm_out_.b, norm_out_.eps, 1, a.p, a.ld, nullptr, 0, st_));
     F32 eps = new32(B, H, W, cfg.out_ch);
     S2I_TRY(gemm(a, true, 9, conv_out_.w, 9L * boc[0], cfg.out_ch, boc[0], conv_out_.b, nullptr, nullptr, &eps, nullptr));
     RUN(nhwc_to_nchw(eps.p, eps.ld, B, cfg.out_ch, H, W, eps_nchw, st_));
@@ -974,9 +968,40 @@ int UNet::run_backward(float* const tap_grads[9], float* dx_nchw) {
     return 0;
 }
 
-int UNet::forward(const float* x_nchw, int B, int H, int W, float t, const float* ctx, float* eps_nchw,
-                  bool save_for_backward, cudaStream_t st) {
+int UNet::prepare_time(float t, cudaStream_t st) {
     if (!loaded_) return set_error(S2I_ERR_STATE, "unet: weights not loaded");
+    const int* boc = cfg.boc;
+    const int temb_dim = boc[0] * 4;
+    const size_t bytes = (size_t)temb_all_.N * sizeof(float);
+    const bool integral = t == (float)(int)t && t >= 0.f && t < 100000.f;
+    if (integral) {
+        auto it = temb_cache_.find((int)t);
+        if (it != temb_cache_.end()) {
+            S2I_CUDA(cudaMemcpyAsync(temb_, it->second, bytes, cudaMemcpyDeviceToDevice, st));
+            return 0;
+        }
+    }
+    S2I_TRY(timestep_embedding(t, boc[0], te0_, st));
+    S2I_TRY(gemv(te0_, boc[0], time1_.w, time1_.b, temb_dim, 0, te1_, st));
+    S2I_TRY(gemv(te1_, temb_dim, time2_.w, time2_.b, temb_dim, 1, te2_, st));
+    S2I_TRY(gemv(te2_, temb_dim, temb_all_.w, temb_all_.b, temb_all_.N, 1, temb_, st));
+    if (integral && temb_cache_.size() < 1024) {
+        void* c = nullptr;
+        if (cudaMalloc(&c, bytes) == cudaSuccess) {
+            owned_.push_back(c);
+            temb_cache_[(int)t] = static_cast<float*>(c);
+            S2I_CUDA(cudaMemcpyAsync(c, temb_, bytes, cudaMemcpyDeviceToDevice, st));
+        } else {
+            cudaGetLastError();
+        }
+    }
+    return 0;
+}
+
+int UNet::forward(const float* x_nchw, int B, int H, int W, float t, const float* ctx, float* eps_nchw,
+                  bool save_for_backward, cudaStream_t st, bool time_ready) {
+    if (!loaded_) return set_error(S2I_ERR_STATE, "unet: weights not loaded");
+    time_ready_ = time_ready;
     if (H % 8 || W % 8) return set_error(S2I_ERR_ARG, "unet: latent H, W must be multiples of 8 (got %d x %d)", H, W);
     st_ = st;
     B_ = B; H_ = H; W_ = W;
@@ -1004,6 +1029,7 @@ int UNet::forward(const float* x_nchw, int B, int H, int W, float t, const float
                 cudaGetLastError();
                 return set_error(S2I_ERR_OOM, "unet: cannot allocate %.1f GB activation arena", need / 1e9);
             }
+            ++g_alloc_gen;
             arena_.base = static_cast<char*>(p);
             arena_.cap = need;
         }

@@ -121,7 +121,11 @@ class UNet {
     // eps[B,4,H,W] (NCHW fp32, device) = unet(x[B,4,H,W], t, ctx[B,ctx_len,cross_dim]).  With save_for_backward the
     // activations needed by backward() stay resident until the next forward().
     int forward(const float* x_nchw, int B, int H, int W, float t, const float* ctx, float* eps_nchw,
-                bool save_for_backward, cudaStream_t st);
+                bool save_for_backward, cudaStream_t st, bool time_ready = false);
+    // The timestep-dependent part of the forward (sinusoidal embedding -> 2 Linear -> every ResBlock's time_emb_proj),
+    // into a persistent buffer; results are cached per timestep.  forward(..., time_ready = true) then skips it, so the
+    // rest of the step does not depend on t (the sampler replays it from a CUDA graph).
+    int prepare_time(float t, cudaStream_t st);
     // dx[B,4,H,W] (NCHW fp32) = sum_k J_k^T tap_grad[k]; tap_grad[k] is NHWC fp32 shaped like tap(k).
     int backward(float* const tap_grads[9], float* dx_nchw, cudaStream_t st);
 
@@ -154,7 +158,9 @@ class UNet {
     cudaStream_t st_ = nullptr;
     int B_ = 0, H_ = 0, W_ = 0;
     const float* ctx_ = nullptr;
-    float* temb_ = nullptr;      // fused time_emb_proj output [sum Cout]
+    float* temb_ = nullptr;      // fused time_emb_proj output [sum Cout] (persistent)
+    float *te0_ = nullptr, *te1_ = nullptr, *te2_ = nullptr;
+    std::map<int, float*> temb_cache_;   // timestep -> cached temb_ contents
     double* stats_ = nullptr;    // GroupNorm sums arena (zeroed once per pass)
     size_t stats_off_ = 0, stats_cap_ = 0;
     std::vector<ResSave> rsave_;
@@ -165,6 +171,7 @@ class UNet {
     H16 ctx16_;
     long arena_key_ = -1;
     bool have_saved_ = false;
+    bool time_ready_ = false;
 
     int run_forward(const float* x_nchw, float t, float* eps_nchw);
     int run_backward(float* const tap_grads[9], float* dx_nchw);
