@@ -6,11 +6,13 @@
 // memory in the 128B-swizzled K-major layout the tensor core reads; O += P V_j accumulates in TMEM (V is the
 // MN-major B operand straight from its [tokens][channels] layout).  The scores never touch HBM.
 //
-// Two passes over the key tiles keep the accumulator free of rescaling: pass 1 computes the exact row maximum
-// (QK^T only -- the tensor pipe is otherwise idle: the kernel is exp-bound for SD's small head dims), pass 2
-// recomputes S, forms p = exp2((s - max) * scale * log2 e), the row sum, and O.  Final O / rowsum is written fp16.
+// One pass over the key tiles with an online softmax whose reference maximum moves lazily: probabilities are formed as
+// p = exp2(s * scale * log2 e - m_ref); m_ref is only raised (and the TMEM accumulator and row sum rescaled by
+// exp2(m_old - m_new)) when a tile's maximum exceeds it by more than 8 (p stays <= 2^8, exact in fp16 / fp32).  After the
+// first tiles this almost never happens, so the accumulator is free of per-tile rescaling.  S tiles are issued up to
+// nS - 1 tiles ahead of the softmax warps (TMEM: nS x 64 score columns + dp output columns).  Final O / rowsum -> fp16.
 //
-//   warp 0      TMA producer (Q once, then K tiles for pass 1 and K+V tiles for pass 2 through a stage ring)
+//   warp 0      TMA producer (Q once, then K+V tiles through a stage ring)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
 //   warps 2..5  softmax + epilogue (TMEM lane quarter = warp & 3)
 #include "attn.cuh"
@@ -35,13 +37,14 @@ constexpr int kTileK = 64;               // keys per tile: one 64-row TMA box se
 constexpr int kChunk16 = 128 * 64 * 2;   // 16 KB: 128 rows x 64 fp16 (one swizzle-128B K-major chunk of Q or P)
 constexpr int kChunk8 = 64 * 64 * 2;     // 8 KB: 64 rows x 64 fp16 (one chunk of a K or V tile)
 constexpr int kMaxStages = 4;
+constexpr int kMaxS = 4;
 
 struct __align__(64) AttnParams {
     CUtensorMap mapQ, mapKV;
     int Nq, Nk, heads, dp;
     int q_c0, k_c0, v_c0;
     int nkc;            // 64-wide chunks covering dp
-    int stages, pbufs, tmem_cols;
+    int stages, pbufs, tmem_cols, nS;
     uint32_t idesc_s, idesc_o;
     float scale_log2;   // softmax scale * log2(e)
     float scale;
@@ -68,11 +71,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_cons
     uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + p.stages * stage_bytes);
     uint64_t* q_full = bars;
     uint64_t* o_full = bars + 1;
-    uint64_t* s_full = bars + 2;     // [2]
-    uint64_t* s_empty = bars + 4;    // [2]
-    uint64_t* p_full = bars + 6;     // [2]
-    uint64_t* p_empty = bars + 8;    // [2]
-    uint64_t* kv_full = bars + 10;   // [kMaxStages]
+    uint64_t* p_full = bars + 2;     // [2]
+    uint64_t* p_empty = bars + 4;    // [2]
+    uint64_t* s_full = bars + 6;     // [kMaxS]
+    uint64_t* s_empty = bars + 10;   // [kMaxS]
+    uint64_t* kv_full = bars + 14;   // [kMaxStages]
     uint64_t* kv_empty = kv_full + kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + kMaxStages);
 
@@ -92,10 +95,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_cons
             ptx::mbar_init(q_full, 1);
             ptx::mbar_init(o_full, 1);
             for (int i = 0; i < 2; ++i) {
-                ptx::mbar_init(&s_full[i], 1);
-                ptx::mbar_init(&s_empty[i], 4);
                 ptx::mbar_init(&p_full[i], 4);
                 ptx::mbar_init(&p_empty[i], 1);
+            }
+            for (int i = 0; i < kMaxS; ++i) {
+                ptx::mbar_init(&s_full[i], 1);
+                ptx::mbar_init(&s_empty[i], 4);
             }
             for (int s = 0; s < p.stages; ++s) {
                 ptx::mbar_init(&kv_full[s], 1);
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_O = tmem_base + 128u;        // S buffers: columns [0,64) and [64,128)
+    const uint32_t tmem_O = tmem_base + (uint32_t)p.nS * 64u;        // S buffers: nS x 64 columns, then O
 
     if (warp == 0) {
         if (lane == 0) {
@@ -119,21 +124,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_cons
             ptx::mbar_expect_tx(q_full, (uint32_t)q_bytes);
             for (int c = 0; c < p.nkc; ++c)
                 ptx::tma_load_3d(sQ + c * kChunk16, &p.mapQ, q_full, p.q_c0 + h * p.dp + c * 64, q0, b);
-            for (int g = 0; g < 2 * T; ++g) {
-                const int j = g < T ? g : g - T;
-                const bool with_v = g >= T;
-                const int stage = g % p.stages;
-                const uint32_t phase = (g / p.stages) & 1;
+            for (int j = 0; j < T; ++j) {
+                const int stage = j % p.stages;
+                const uint32_t phase = (j / p.stages) & 1;
                 ptx::mbar_wait(&kv_empty[stage], phase ^ 1);
-                ptx::mbar_expect_tx(&kv_full[stage], (uint32_t)(with_v ? stage_bytes : k_bytes));
+                ptx::mbar_expect_tx(&kv_full[stage], (uint32_t)stage_bytes);
                 uint8_t* sK = sKV + stage * stage_bytes;
                 uint8_t* sV = sK + k_bytes;
-                for (int c = 0; c < p.nkc; ++c)
+                for (int c = 0; c < p.nkc; ++c) {
                     ptx::tma_load_3d(sK + c * kChunk8, &p.mapKV, &kv_full[stage], p.k_c0 + h * p.dp + c * 64, j * kTileK, b);
-                if (with_v)
-                    for (int c = 0; c < p.nkc; ++c)
-                        ptx::tma_load_3d(sV + c * kChunk8, &p.mapKV, &kv_full[stage], p.v_c0 + h * p.dp + c * 64,
-                                         j * kTileK, b);
+                    ptx::tma_load_3d(sV + c * kChunk8, &p.mapKV, &kv_full[stage], p.v_c0 + h * p.dp + c * 64, j * kTileK, b);
+                }
             }
         }
     } else if (warp == 1) {
@@ -141,40 +142,31 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_cons
             // ------------------------------------------------ MMA issuer
             const int nks = p.dp >> 4;             // K steps of the QK^T product
             const uint32_t aQ = ptx::smem_u32(sQ);
-            // S[g & 1] = Q K_g^T once the tile has landed and the softmax warps have drained that S buffer
+            // S[g % nS] = Q K_g^T once the tile has landed and the softmax warps have drained that S buffer
             auto issue_S = [&](int g) {
                 const int stage = g % p.stages;
+                const int sb = g % p.nS;
                 ptx::mbar_wait(&kv_full[stage], (g / p.stages) & 1);
-                ptx::mbar_wait(&s_empty[g & 1], ((g >> 1) & 1) ^ 1);
+                ptx::mbar_wait(&s_empty[sb], ((g / p.nS) & 1) ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t aK = ptx::smem_u32(sKV + stage * stage_bytes);
-                const uint32_t tS = tmem_base + (uint32_t)(g & 1) * 64u;
+                const uint32_t tS = tmem_base + (uint32_t)sb * 64u;
                 for (int k = 0; k < nks; ++k) {
                     const uint32_t kq = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3) * 32u;
                     ptx::umma_f16(tS, ptx::make_smem_desc_sw128(aQ + kq * kChunk16 + ks, 16u, 1024u),
                                   ptx::make_smem_desc_sw128(aK + kq * kChunk8 + ks, 16u, 1024u), p.idesc_s,
                                   k != 0 ? 1u : 0u);
                 }
+                ptx::umma_commit(&s_full[sb]);
             };
             ptx::mbar_wait(q_full, 0);
-            // pass 1: row maxima (the issuer may run two tiles ahead of the softmax warps)
-            for (int g = 0; g < T; ++g) {
-                issue_S(g);
-                ptx::umma_commit(&kv_empty[g % p.stages]);
-                ptx::umma_commit(&s_full[g & 1]);
-            }
-            // pass 2: probabilities and output; S_{j+1} is issued before P_j V_j so the softmax warps never starve
-            issue_S(T);
-            ptx::umma_commit(&s_full[T & 1]);
+            int next_s = 0;
             for (int j = 0; j < T; ++j) {
-                const int g = T + j;
-                if (j + 1 < T) {
-                    issue_S(g + 1);
-                    ptx::umma_commit(&s_full[(g + 1) & 1]);
-                }
+                // keep score tiles issued up to nS - 1 tiles ahead of the P V products (nS <= stages: no deadlock)
+                while (next_s < T && next_s <= j + p.nS - 1) issue_S(next_s++);
                 ptx::mbar_wait(&p_full[j % p.pbufs], (j / p.pbufs) & 1);
                 ptx::tc_fence_after();
-                const int stage = g % p.stages;
+                const int stage = j % p.stages;
                 const uint32_t aV = ptx::smem_u32(sKV + stage * stage_bytes + k_bytes);
                 const uint32_t aP = ptx::smem_u32(sP + (j % p.pbufs) * kChunk16);
                 for (int kk = 0; kk < 4; ++kk) {
@@ -193,34 +185,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_cons
         const int r = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const bool row_ok = (q0 + r) < p.Nq;
-        float m = -INFINITY;
-        // pass 1
-        for (int g = 0; g < T; ++g) {
-            ptx::mbar_wait(&s_full[g & 1], (g >> 1) & 1);
-            ptx::tc_fence_after();
-            const int kvalid = p.Nk - g * kTileK;      // columns >= kvalid are padding
-            const uint32_t tS = tmem_base + (uint32_t)(g & 1) * 64u + lane_addr;
-#pragma unroll
-            for (int c = 0; c < kTileK; c += 32) {
-                uint32_t raw[32];
-                ptx::tmem_ld_32x32(tS + (uint32_t)c, raw);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c + i < kvalid) m = fmaxf(m, __uint_as_float(raw[i]));
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&s_empty[g & 1]);
-        }
-        const float mneg = (m == -INFINITY) ? 0.f : -m * p.scale_log2;
-        float l = 0.f;
-        // pass 2
+        float mref = 0.f;       // reference maximum of this row, in log2 units (score * scale * log2 e)
+        float l = 0.f;          // sum of p relative to mref
         for (int j = 0; j < T; ++j) {
-            const int g = T + j;
-            ptx::mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+            const int sbuf = j % p.nS;
+            ptx::mbar_wait(&s_full[sbuf], (j / p.nS) & 1);
             ptx::tc_fence_after();
-            const uint32_t tS = tmem_base + (uint32_t)(g & 1) * 64u + lane_addr;
+            const uint32_t tS = tmem_base + (uint32_t)sbuf * 64u + lane_addr;
             uint32_t s[kTileK];
 #pragma unroll
             for (int c = 0; c < kTileK; c += 32) {
@@ -232,9 +203,43 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_cons
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&s_empty[g & 1]);     // S is in registers: TMEM buffer may be overwritten
+            if (lane == 0) ptx::mbar_arrive(&s_empty[sbuf]);     // S is in registers: TMEM buffer may be overwritten
 
-            const int kvalid = p.Nk - j * kTileK;
+            const int kvalid = p.Nk - j * kTileK;                // columns >= kvalid are padding (last tile only)
+            float mx = -INFINITY;
+            if (kvalid >= kTileK) {
+#pragma unroll
+                for (int i = 0; i < kTileK; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < kTileK; ++i)
+                    if (i < kvalid) mx = fmaxf(mx, __uint_as_float(s[i]));
+            }
+            const float mt = mx * p.scale_log2;
+            // lazy reference update: only when this tile would push p above 2^8 (always on the first tile)
+            const bool need = (j == 0) || (mt > mref + 8.f);
+            if (__any_sync(0xffffffffu, need)) {
+                const float mnew = need ? mt : mref;
+                const float factor = (j == 0) ? 0.f : ex2_approx(mref - mnew);     // 1 for rows that keep their reference
+                l *= factor;
+                mref = mnew;
+                if (j > 0) {
+                    // every P V product issued so far must have landed before the accumulator rows are rescaled
+                    ptx::mbar_wait(&p_empty[(j - 1) % p.pbufs], ((j - 1) / p.pbufs) & 1);
+                    ptx::tc_fence_after();
+                    for (int c = 0; c < p.dp; c += 16) {
+                        uint32_t o[16];
+                        ptx::tmem_ld_32x16(tmem_O + lane_addr + (uint32_t)c, o);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                        ptx::tmem_st_32x16(tmem_O + lane_addr + (uint32_t)c, o);
+                    }
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                }
+            }
+            const float mneg = -mref;
             uint32_t pk[kTileK / 2];
 #pragma unroll
             for (int i = 0; i < kTileK; i += 2) {
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_cons
                 *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(o[4], o[5], o[6], o[7]);
             }
         }
-        if (p.lse && row_ok) p.lse[(long)z * p.Nq + q0 + r] = m * p.scale + logf(l);
+        if (p.lse && row_ok) p.lse[(long)z * p.Nq + q0 + r] = mref * 0.6931471805599453f + logf(l);
     }
 
     ptx::tc_fence_before();
@@ -307,12 +312,12 @@ int attn_fwd_launch(const AttnDesc& d, cudaStream_t stream) {
     p.out = d.out; p.ldo = d.ldo; p.lse = d.lse;
     p.idesc_s = ptx::make_idesc_f16(128, kTileK, 0, 0, 0);
     p.idesc_o = ptx::make_idesc_f16(128, (uint32_t)d.dp, 0, 0, 1);
-    p.tmem_cols = (128 + d.dp) <= 256 ? 256 : 512;
+    p.tmem_cols = d.dp <= 128 ? 256 : 512;      // 256 columns let two CTAs share an SM
 
     // shared memory: Q | P buffers | (K tile + V tile) stages | barriers.  Prefer a footprint that lets two CTAs share
     // an SM (the kernel is exp- and latency-bound for SD's head dims: a second CTA fills the handshake bubbles).
     const int q_bytes = p.nkc * kChunk16, stage_bytes = 2 * p.nkc * kChunk8;
-    const int overhead = 256 + 1024;     // barriers + alignment slack
+    const int overhead = 512 + 1024;     // barriers + alignment slack
     const int half_sm = 113 * 1024, full_sm = 226 * 1024;
     int pbufs = 0, stages = 0;
     const int tries[4][2] = {{2, 3}, {2, 2}, {1, 2}, {0, 0}};
@@ -331,6 +336,10 @@ int attn_fwd_launch(const AttnDesc& d, cudaStream_t stream) {
     }
     p.stages = stages;
     p.pbufs = pbufs;
+    p.nS = (p.tmem_cols - d.dp) / 64;
+    if (p.nS > kMaxS) p.nS = kMaxS;
+    if (p.nS > stages) p.nS = stages;           // score tiles run at most `stages` key tiles ahead (see the issuer)
+    if (p.nS < 1) return set_error(S2I_ERR_ARG, "attn_fwd: head dim %d leaves no TMEM for the score tiles", d.dp);
     const size_t smem_bytes = (size_t)q_bytes + (size_t)pbufs * kChunk16 + (size_t)stages * stage_bytes + overhead;
 
     {
