@@ -56,6 +56,10 @@ int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream);
 /* Bisecting / A-B switch (no reference counterpart): 1 (default) = eligible GEMMs run gemm_tma_kernel (residual tile in,
  * result tiles out through cp.async.bulk.tensor), 0 = every GEMM runs gemm_tc_kernel (per-thread epilogue). */
 int s2i_gemm_set_tma_epilogue(int on);
+/* Debugging: device buffer of [ctas][16] uint64 that gemm_tma_kernel fills with %globaltimer stamps of its phases
+ * (entry, setup done, loads issued, MMAs issued, epilogue start, accumulator ready, residual ready, chunks done, stores
+ * read, exit); NULL switches it off. */
+int s2i_gemm_set_trace(void* device_buf);
 
 
 /* ---------------------------------------------------------------------------------------------

@@ -26,6 +26,11 @@ int s2i_gemm_set_tma_epilogue(int on) {
     return 0;
 }
 
+int s2i_gemm_set_trace(void* device_buf) {
+    s2i::gemm_set_trace(static_cast<unsigned long long*>(device_buf));
+    return 0;
+}
+
 int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream) {
     if (!d) return s2i::set_error(S2I_ERR_ARG, "s2i_gemm: null descriptor");
     return s2i::gemm_launch(s2i::GemmDesc(*d), static_cast<cudaStream_t>(cuda_stream));

@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();       // everything above is local setup; global memory of earlier kernels is touched only below
+    pdl_launch();     // TMEM is held: dependents may become resident
     const uint32_t tmem_O = tmem_base + (uint32_t)p.nS * 64u;        // S buffers: nS x 64 columns, then O
 
     if (warp == 0) {
@@ -360,7 +362,7 @@ int attn_fwd_launch(const AttnDesc& d, cudaStream_t stream) {
         attr_set = true;
     }
     dim3 grid((unsigned)((d.Nq + kTileQ - 1) / kTileQ), (unsigned)(d.B * d.heads), 1);
-    attn_fwd_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+    S2I_LAUNCH((attn_fwd_kernel), grid, kThreads, smem_bytes, stream, p);
     // algorithmic work: QK^T + PV at the true head dim
     S2I_LAUNCH_CHECK_TAG("attn_fwd", 4.0 * d.B * d.heads * (double)d.Nq * d.Nk * d.d_true, 0.0);
     return 0;

@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_kernel(const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();       // everything above is local setup; global memory of earlier kernels is touched only below
+    pdl_launch();     // TMEM is held: dependents may become resident
     const uint32_t tmem_acc0 = tmem_base + 256u;
     const uint32_t tmem_acc1 = tmem_acc0 + (uint32_t)p.dp;
 
@@ -319,6 +321,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_kernel(const __grid_cons
 // delta[z][i] = sum_c dO[b,i,h,c] * O[b,i,h,c]   (one warp per (z, i) row)
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __half* __restrict__ o, long ldo, const __half* __restrict__ dO,
                                                          long lddo, int B, int heads, int Nq, int dp, float* __restrict__ delta) {
+    pdl_wait();
+    pdl_launch();
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const long total = (long)B * heads * Nq;
@@ -358,7 +362,7 @@ int attn_bwd_launch(const AttnBwdDesc& d, cudaStream_t stream) {
     const int Z = d.B * d.heads;
     {   // delta = rowsum(dO * O)
         const long rows = (long)Z * d.Nq;
-        attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(d.o, d.ldo, d.dO, d.lddo, d.B, d.heads, d.Nq, d.dp, d.delta);
+        S2I_LAUNCH((attn_delta_kernel), (unsigned)((rows + 7) / 8), 256, 0, stream, d.o, d.ldo, d.dO, d.lddo, d.B, d.heads, d.Nq, d.dp, d.delta);
         S2I_LAUNCH_CHECK_TAG("attn_bwd_delta", 0.0, 0.0);
     }
     static bool attr_set = false;
@@ -402,7 +406,7 @@ int attn_bwd_launch(const AttnBwdDesc& d, cudaStream_t stream) {
         const size_t smem_bytes = (size_t)fixed + (size_t)p.sbufs * nstaged * kChunk16;
         if (smem_bytes > 227u * 1024u) return set_error(S2I_ERR_ARG, "attn_bwd: head dim %d does not fit shared memory", d.dp);
         dim3 grid((unsigned)((p.Nrow + kRows - 1) / kRows), (unsigned)Z, 1);
-        attn_bwd_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+        S2I_LAUNCH((attn_bwd_kernel), grid, kThreads, smem_bytes, stream, p);
         // algorithmic work of the reference's backward: dP, dQ (mode 0) and dV, dK (mode 1) products at the true head dim
         S2I_LAUNCH_CHECK_TAG("attn_bwd", 4.0 * Z * (double)d.Nq * d.Nk * d.d_true, 0.0);
     }

@@ -1,5 +1,6 @@
 #include "common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -22,6 +23,11 @@ const char* last_error() { return g_err; }
 // ------------------------------------------------------------------------------------------------ profiler
 bool g_prof_on = false;
 long g_alloc_gen = 0;
+bool g_prev_kernel = false;
+bool g_pdl = [] {
+    const char* e = getenv("S2I_NO_PDL");
+    return !(e && e[0] == '1');
+}();
 namespace {
 struct ProfRec {
     const char* tag;

@@ -59,6 +59,43 @@ int prof_end(char* buf, int cap);
         if (::s2i::g_prof_on) ::s2i::prof_mark((tag), (flops), (bytes));                                     \
     } while (0)
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// Every kernel of the sampling path is launched with programmatic stream serialization: its CTAs may become resident
+// (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) while the previous kernel drains.
+// Each kernel therefore executes pdl_wait() before it first touches memory written by earlier kernels, and
+// pdl_launch() once it holds its own scarce resources (TMEM), so dependents never starve a still-starting primary.
+// S2I_NO_PDL=1 in the environment turns the launch attribute off (the device-side instructions become no-ops).
+extern bool g_pdl;
+// True while the last operation enqueued by the library was one of its kernels: only then is the next kernel launched
+// as a programmatic dependent (a copy / memset / graph launch in between gets an ordinary full dependency).
+extern bool g_prev_kernel;
+#define S2I_MEMOP(call)                \
+    do {                               \
+        ::s2i::g_prev_kernel = false;  \
+        S2I_CUDA(call);                \
+    } while (0)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (g_pdl && g_prev_kernel) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    g_prev_kernel = true;
+}
+#define S2I_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    ::s2i::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
+#endif
+
 #define S2I_TRY(expr)                  \
     do {                               \
         int rc__ = (expr);             \

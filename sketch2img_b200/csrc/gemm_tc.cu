@@ -55,7 +55,17 @@ struct __align__(64) GemmParams {
     CUtensorMap mapO16;      // fp16 output, box (32, tw, th, tb), 64B swizzle
     int has_res, has_o32, has_o16;
     int split_add;           // split-K by fp32 reduce-add into a zeroed output (split 0 carries bias + residual)
+    unsigned long long* trace;   // optional [ctas][16] %globaltimer stamps of the kernel's phases (tools/gemm_trace.py)
 };
+
+__device__ __forceinline__ void stamp(const GemmParams& p, int slot) {
+    if (p.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        p.trace[(long)cta * 16 + slot] = t;
+    }
+}
 
 constexpr int kEpiLd = 36;   // floats per row of the per-warp 32x32 transpose buffer (16-byte aligned, conflict-free)
 
@@ -135,6 +145,7 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx
             for (int j = 0; j < nchunks_b; ++j)
                 ptx::tma_load_3d(sb + j * kChunkBytes, &p.mapB, &full[stage], b_inner + t.n0 + j * 64, it * kBlockK, b_bz);
         }
+        if (li < 3) stamp(p, 10 + li);
     }
 }
 
@@ -196,6 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const TileCtx t = tile_ctx(p);
+    if (threadIdx.x == 0) stamp(p, 0);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&p.mapA);
@@ -222,12 +234,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();       // everything above is local setup; global memory of earlier kernels is touched only below
+    pdl_launch();     // TMEM is held: dependents may become resident
+    if (threadIdx.x == 0) stamp(p, 1);
     const bool add_res = p.has_res && (!p.split_add || t.split == 0);
     const bool add_bias = !p.split_add || t.split == 0;
 
     if (warp == 0) {
         if (lane == 0) {
             producer_loop(p, t, smem, stage_bytes, full, empty);
+            stamp(p, 2);
             if (add_res) {
                 // the pipeline stages are idle once the accumulator is complete: land the residual tile there
                 ptx::mbar_wait(accum_full, 0);
@@ -239,7 +255,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) mma_loop(p, t, smem, stage_bytes, full, empty, accum_full, tmem_base);
+        if (lane == 0) {
+            mma_loop(p, t, smem, stage_bytes, full, empty, accum_full, tmem_base);
+            stamp(p, 3);
+        }
     } else {
         // ---------------------------------------------------- epilogue (warps 2..5), thread <-> tile row
         const int e = threadIdx.x - 64;
@@ -255,8 +274,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
             bias_s[i] = b;
         }
         ptx::named_bar_sync(1, 128);
+        if (e == 0) stamp(p, 4);
         ptx::mbar_wait(accum_full, 0);
         ptx::tc_fence_after();
+        if (e == 0) stamp(p, 5);
         const uint32_t sw128 = (uint32_t)(r & 7);
         const uint32_t sw64 = (uint32_t)((r >> 1) & 3);
         uint8_t* base16 = smem + (use32 ? nch * kChunk32Bytes : 0);
@@ -266,6 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
             ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
             if (add_res) ptx::mbar_wait(&r_full[c], 0);
             ptx::tmem_ld_wait();
+            if (e == 0 && c == 0) stamp(p, 6);
             uint8_t* row32 = smem + c * kChunk32Bytes + r * 128;
             uint32_t hp[16];
 #pragma unroll
@@ -292,6 +314,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
                     *reinterpret_cast<uint4*>(row16 + ((w ^ sw64) << 4)) =
                         make_uint4(hp[4 * w], hp[4 * w + 1], hp[4 * w + 2], hp[4 * w + 3]);
             }
+            // the chunk's bulk store overlaps the next chunk's arithmetic (the copy engine, like the loads, runs at the
+            // chip's ~10 TB/s L2 rate: a late burst of all stores would only lengthen the tail)
             ptx::fence_proxy_async();              // generic-proxy smem writes -> visible to the bulk-copy engine
             ptx::named_bar_sync(1, 128);
             if (e == 0) {
@@ -302,13 +326,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
                 }
                 if (p.has_o16) ptx::tma_store_4d(&p.mapO16, base16 + c * kChunk16Bytes, nc, t.x0, t.y0, t.b0);
                 ptx::tma_store_commit();
+                if (c < 3) stamp(p, 13 + c);
             }
         }
-        if (e == 0) ptx::tma_store_wait_read0();   // shared memory stays valid until the stores have read it
+        if (e == 0) {
+            stamp(p, 7);
+            ptx::tma_store_wait_read0();   // shared memory stays valid until the stores have read it
+            stamp(p, 8);
+        }
     }
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp(p, 9);
     if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
@@ -350,6 +380,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();       // everything above is local setup; global memory of earlier kernels is touched only below
+    pdl_launch();     // TMEM is held: dependents may become resident
 
     if (warp == 0) {
         if (lane == 0) producer_loop(p, t, smem, stage_bytes, full, empty);
@@ -705,6 +737,7 @@ TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, bo
     return best;
 }
 
+unsigned long long* g_trace = nullptr;
 int g_tma_epi = -1;
 bool tma_epilogue_enabled() {
     if (g_tma_epi < 0) {
@@ -782,6 +815,8 @@ int build_out_map(CUtensorMap* m, const GemmParams& p, const GemmDesc& d, const 
 // fp32 [rows][N] (row pitch lds) -> fp16 [rows][N] (row pitch ldd); N % 4 == 0
 __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ src, long lds, __half* __restrict__ dst,
                                                         long ldd, long rows, int n4) {
+    pdl_wait();
+    pdl_launch();
     const long total = rows * n4;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long r = i / n4;
@@ -858,7 +893,7 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     if (d.out16) S2I_TRY(build_out_map(&p.mapO16, p, d, d.out16, d.ld16, 0));
     if (p.split_add) {
         const long rows = (long)d.aW * d.aH * d.aB;
-        S2I_CUDA(cudaMemset2DAsync(d.out32, (size_t)d.ld32 * 4, 0, (size_t)d.N * 4, (size_t)rows, stream));
+        S2I_MEMOP(cudaMemset2DAsync(d.out32, (size_t)d.ld32 * 4, 0, (size_t)d.N * 4, (size_t)rows, stream));
     }
     static bool attr_set = false;
     if (!attr_set) {
@@ -866,12 +901,13 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
         attr_set = true;
     }
     dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)tc.splits);
-    gemm_tma_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+    p.trace = g_trace;
+    S2I_LAUNCH((gemm_tma_kernel), grid, kThreads, smem_bytes, stream, p);
     const double m_rows = (double)d.aW * d.aH * d.aB;
     S2I_LAUNCH_CHECK_TAG(d.tag, 2.0 * m_rows * d.N * d.Kc * d.taps, 0.0);
     if (via_scratch) {
         const long total = rows_total * (d.N / 4);
-        cast_rows_kernel<<<(unsigned)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048), 256, 0, stream>>>(
+        S2I_LAUNCH((cast_rows_kernel), (unsigned)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048), 256, 0, stream, 
             g_ws, d.N, static_cast<__half*>(d_in.out16), d_in.ld16, rows_total, d.N / 4);
         S2I_LAUNCH_CHECK_TAG("gemm_split_cast", 0.0, 0.0);
     }
@@ -888,6 +924,7 @@ int encode_tmap_f16(CUtensorMap* m, int rank, const void* ptr, const uint64_t* d
 long g_launches = 0;
 long gemm_launch_count() { return g_launches; }
 void gemm_set_tma_epilogue(int on) { g_tma_epi = on ? 1 : 0; }
+void gemm_set_trace(unsigned long long* buf) { g_trace = buf; }
 
 int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     if (!d.A || !d.B) return set_error(S2I_ERR_ARG, "gemm: null operand");
@@ -1045,7 +1082,7 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
         attr_set = true;
     }
     dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)(Z * p.splits));
-    gemm_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+    S2I_LAUNCH((gemm_tc_kernel), grid, kThreads, smem_bytes, stream, p);
     const double m_rows = d.a_mn ? (double)d.aC : (double)d.aW * d.aH * (d.Z > 1 ? 1 : d.aB);
     S2I_LAUNCH_CHECK_TAG(d.tag, 2.0 * m_rows * d.N * d.Kc * d.taps * Z, 0.0);
     return 0;

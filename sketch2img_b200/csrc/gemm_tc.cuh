@@ -35,6 +35,9 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream);
 // use gemm_tma_kernel (epilogue through TMA).  Also settable with S2I_GEMM_TMA_EPI=0 in the environment.
 void gemm_set_tma_epilogue(int on);
 
+// Debugging: when set, gemm_tma_kernel stamps %globaltimer at its phase boundaries into buf[cta][16] (tools/gemm_trace.py).
+void gemm_set_trace(unsigned long long* buf);
+
 // Number of kernel launches issued through gemm_launch since process start (bench.py's gpu_launches).
 long gemm_launch_count();
 

@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(256) gn_reduce_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, int silu, double* __restrict__ partial,
                                                         double* __restrict__ slot) {
+    pdl_wait();
+    pdl_launch();
     __shared__ float s1[kGroups], s2[kGroups];
     __shared__ GnStat st;
     __shared__ int is_last;
@@ -213,6 +215,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float eps, int silu, __half* __restrict__ out16, long ld16,
                                                        __half* __restrict__ raw16, long ldraw) {
+    pdl_wait();
+    pdl_launch();
     __shared__ GnStat st;
     const int b = blockIdx.y;
     const int Cg = C / kGroups;
@@ -248,6 +252,8 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ add, long ldadd,
                                                            float* __restrict__ dx32, long ld32,
                                                            __half* __restrict__ dx16, long ld16) {
+    pdl_wait();
+    pdl_launch();
     __shared__ GnStat st;
     __shared__ float m1[kGroups], m2[kGroups];
     const int b = blockIdx.y;
@@ -312,6 +318,8 @@ struct GnFusedArgs {
 
 template <int MODE>
 __global__ void __launch_bounds__(512) gn_fused_kernel(const GnFusedArgs a) {
+    pdl_wait();
+    pdl_launch();
     __shared__ float s1[kGroups], s2[kGroups];
     __shared__ GnStat st;            // forward statistics (MODE 0: computed here; MODE 1: loaded)
     __shared__ float m1[kGroups], m2[kGroups];
@@ -534,6 +542,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float eps, __half* __restrict__ out16, long ld16,
                                                      float* __restrict__ stats) {
+    pdl_wait();
+    pdl_launch();
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -572,6 +582,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      const float* __restrict__ add, long ldadd,
                                                      float* __restrict__ dx32, long ld32, __half* __restrict__ dx16,
                                                      long ld16) {
+    pdl_wait();
+    pdl_launch();
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -609,6 +621,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 // ------------------------------------------------------------------------------------------------ softmax
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ s, long lds, long rows, int n,
                                                           __half* __restrict__ p16, long ldp) {
+    pdl_wait();
+    pdl_launch();
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -649,6 +663,8 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __half* __restrict__ p16, long ldp,
                                                           const float* __restrict__ dp, long lddp, long rows, int n,
                                                           float scale, __half* __restrict__ ds16, long ldds) {
+    pdl_wait();
+    pdl_launch();
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -669,6 +685,8 @@ __device__ __forceinline__ float gelu_grad(float x) {
 
 __global__ void __launch_bounds__(256) geglu_fwd_kernel(const float* __restrict__ ff, long ldf, long rows, int F,
                                                         __half* __restrict__ out16, long ld16) {
+    pdl_wait();
+    pdl_launch();
     const int vec = F >> 2;
     const long total = rows * vec;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -684,6 +702,8 @@ __global__ void __launch_bounds__(256) geglu_fwd_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) geglu_bwd_kernel(const float* __restrict__ dg, long ldg,
                                                         const float* __restrict__ ff, long ldf, long rows, int F,
                                                         __half* __restrict__ dff16, long ld16) {
+    pdl_wait();
+    pdl_launch();
     const int vec = F >> 2;
     const long total = rows * vec;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -704,6 +724,8 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) add2d_kernel(const float* __restrict__ a, long lda, const float* __restrict__ b,
                                                     long ldb, long rows, int cols, float* __restrict__ d32, long ld32,
                                                     __half* __restrict__ d16, long ld16) {
+    pdl_wait();
+    pdl_launch();
     const int vec = cols >> 2;
     const long total = rows * vec;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -721,6 +743,8 @@ __global__ void __launch_bounds__(256) add2d_kernel(const float* __restrict__ a,
 
 __global__ void __launch_bounds__(256) cast2d_kernel(const float* __restrict__ a, long lda, long rows, int cols,
                                                      float mul, __half* __restrict__ d16, long ld16) {
+    pdl_wait();
+    pdl_launch();
     const int vec = cols >> 2;
     const long total = rows * vec;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -733,6 +757,8 @@ __global__ void __launch_bounds__(256) cast2d_kernel(const float* __restrict__ a
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ x, long ldx, int B, int H, int W,
                                                          int C, __half* __restrict__ out16, long ld16) {
+    pdl_wait();
+    pdl_launch();
     const int vec = C >> 2;
     const long total = (long)B * 2 * H * 2 * W * vec;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -749,6 +775,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) sumpool2x_kernel(const float* __restrict__ d, long ldd, int B, int H, int W,
                                                         int C, float* __restrict__ dx, long ldx) {
+    pdl_wait();
+    pdl_launch();
     const int vec = C >> 2;
     const long total = (long)B * H * W * vec;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -770,6 +798,8 @@ __global__ void __launch_bounds__(256) sumpool2x_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) zero_insert2x_kernel(const float* __restrict__ d, long ldd, int B, int Ho,
                                                             int Wo, int C, __half* __restrict__ out16, long ld16) {
+    pdl_wait();
+    pdl_launch();
     const int vec = C >> 2;
     const long total = (long)B * 2 * Ho * 2 * Wo * vec;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -791,6 +821,8 @@ __global__ void __launch_bounds__(256) zero_insert2x_kernel(const float* __restr
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict__ x, long ldx, int B, int H, int W,
                                                         int C, int stride, int Ho, int Wo, __half* __restrict__ col,
                                                         long ldcol) {
+    pdl_wait();
+    pdl_launch();
     const long total = (long)B * Ho * Wo * ldcol;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const long pix = idx / ldcol;
@@ -811,6 +843,8 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict_
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int B, int C, int H, int W, float* __restrict__ dst,
                                     long ldn) {
+    pdl_wait();
+    pdl_launch();
     const long total = (long)B * H * W * ldn;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const long pix = idx / ldn;
@@ -822,6 +856,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int B, int C,
 }
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, long ldn, int B, int C, int H, int W,
                                     float* __restrict__ dst) {
+    pdl_wait();
+    pdl_launch();
     const long hw = (long)H * W;
     const long total = (long)B * C * hw;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -836,6 +872,8 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, long ldn, int
 __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, int K, const __half* __restrict__ w,
                                                    const float* __restrict__ bias, int N, int silu_in,
                                                    float* __restrict__ out) {
+    pdl_wait();
+    pdl_launch();
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (n >= N) return;
@@ -855,6 +893,8 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, 
 }
 
 __global__ void timestep_embedding_kernel(float t, int dim, float* __restrict__ out) {
+    pdl_wait();
+    pdl_launch();
     const int half = dim / 2;
     for (int i = threadIdx.x; i < half; i += blockDim.x) {
         const float freq = expf(-logf(10000.f) * (float)i / (float)half);
@@ -914,7 +954,7 @@ int gn_stats(const float* x, long ldx, int B, int HW, int C, float eps, double* 
     dim3 grid(ceil_div(HW, P), B);
     double* partial = nullptr;
     S2I_TRY(gn_partial((size_t)B * grid.x * 2 * kGroups, &partial));
-    gn_reduce_kernel<0><<<grid, 256, 0, st>>>(x, ldx, nullptr, 0, HW, C, P, nullptr, nullptr, nullptr, eps, 0, partial, sums);
+    S2I_LAUNCH((gn_reduce_kernel<0>), grid, 256, 0, st, x, ldx, nullptr, 0, HW, C, P, nullptr, nullptr, nullptr, eps, 0, partial, sums);
     S2I_LAUNCH_CHECK();
     return 0;
 }
@@ -923,7 +963,7 @@ int gn_apply(const float* x, long ldx, int B, int HW, int C, const double* sums,
              float eps, int silu, void* out16, long ld16, void* raw16, long ldraw, cudaStream_t st) {
     S2I_REQ(C % kGroups == 0 && (ldx & 3) == 0 && (ld16 & 3) == 0 && (ldraw & 3) == 0, "gn_apply: alignment");
     dim3 grid(grid_for((long)HW * (C >> 2), 256, 148 * 8), B);
-    gn_apply_kernel<<<grid, 256, 0, st>>>(x, ldx, HW, C, sums, gamma, beta, eps, silu, (__half*)out16, ld16,
+    S2I_LAUNCH((gn_apply_kernel), grid, 256, 0, st, x, ldx, HW, C, sums, gamma, beta, eps, silu, (__half*)out16, ld16,
                                          (__half*)raw16, ldraw);
     S2I_LAUNCH_CHECK();
     return 0;
@@ -936,7 +976,7 @@ int gn_bwd_stats(const float* dy, long ldd, const float* x, long ldx, int B, int
     dim3 grid(ceil_div(HW, P), B);
     double* partial = nullptr;
     S2I_TRY(gn_partial((size_t)B * grid.x * 2 * kGroups, &partial));
-    gn_reduce_kernel<1><<<grid, 256, 0, st>>>(x, ldx, dy, ldd, HW, C, P, sums, gamma, beta, eps, silu, partial, bsums);
+    S2I_LAUNCH((gn_reduce_kernel<1>), grid, 256, 0, st, x, ldx, dy, ldd, HW, C, P, sums, gamma, beta, eps, silu, partial, bsums);
     S2I_LAUNCH_CHECK();
     return 0;
 }
@@ -947,7 +987,7 @@ int gn_bwd_apply(const float* dy, long ldd, const float* x, long ldx, int B, int
     S2I_REQ(C % kGroups == 0 && (ldx & 3) == 0 && (ldd & 3) == 0 && (ldadd & 3) == 0 && (ld32 & 3) == 0 && (ld16 & 3) == 0,
             "gn_bwd_apply: alignment");
     dim3 grid(grid_for((long)HW * (C >> 2), 256, 148 * 8), B);
-    gn_bwd_apply_kernel<<<grid, 256, 0, st>>>(dy, ldd, x, ldx, HW, C, sums, bsums, gamma, beta, eps, silu, add, ldadd,
+    S2I_LAUNCH((gn_bwd_apply_kernel), grid, 256, 0, st, dy, ldd, x, ldx, HW, C, sums, bsums, gamma, beta, eps, silu, add, ldadd,
                                              dx32, ld32, (__half*)dx16, ld16);
     S2I_LAUNCH_CHECK();
     return 0;
@@ -980,7 +1020,7 @@ int gn_forward(const float* x, long ldx, int B, int HW, int C, double* slot, con
     S2I_TRY(gn_partial((size_t)B * nblk * 2 * kGroups, &a.partial));
     a.slot = slot;
     a.out16 = (__half*)out16; a.ld16 = ld16; a.raw16 = (__half*)raw16; a.ldraw = ldraw;
-    gn_fused_kernel<0><<<dim3(nblk, B), 512, 0, st>>>(a);
+    S2I_LAUNCH((gn_fused_kernel<0>), dim3(nblk, B), 512, 0, st, a);
     S2I_LAUNCH_CHECK();
     return 0;
 }
@@ -1004,7 +1044,7 @@ int gn_backward(const float* dy, long ldd, const float* x, long ldx, int B, int 
     S2I_TRY(gn_partial((size_t)B * nblk * 2 * kGroups, &a.partial));
     a.slot = bslot;
     a.add = add; a.ldadd = ldadd; a.dx32 = dx32; a.ld32 = ld32; a.out16 = (__half*)dx16; a.ld16 = ld16;
-    gn_fused_kernel<1><<<dim3(nblk, B), 512, 0, st>>>(a);
+    S2I_LAUNCH((gn_fused_kernel<1>), dim3(nblk, B), 512, 0, st, a);
     S2I_LAUNCH_CHECK();
     return 0;
 }
@@ -1012,7 +1052,7 @@ int gn_backward(const float* dy, long ldd, const float* x, long ldx, int B, int 
 int ln_fwd(const float* x, long ldx, long rows, int C, const float* gamma, const float* beta, float eps, void* out16,
            long ld16, float* stats, cudaStream_t st) {
     S2I_REQ((C & 3) == 0 && (ldx & 3) == 0 && (ld16 & 3) == 0, "ln_fwd: alignment");
-    ln_fwd_kernel<<<(unsigned)ceil_div_l(rows, 8), 256, 0, st>>>(x, ldx, rows, C, gamma, beta, eps, (__half*)out16, ld16,
+    S2I_LAUNCH((ln_fwd_kernel), (unsigned)ceil_div_l(rows, 8), 256, 0, st, x, ldx, rows, C, gamma, beta, eps, (__half*)out16, ld16,
                                                                 stats);
     S2I_LAUNCH_CHECK();
     return 0;
@@ -1023,21 +1063,21 @@ int ln_bwd(const float* dy, long ldd, const float* x, long ldx, long rows, int C
            cudaStream_t st) {
     S2I_REQ((C & 3) == 0 && (ldx & 3) == 0 && (ldd & 3) == 0 && (ldadd & 3) == 0 && (ld32 & 3) == 0 && (ld16 & 3) == 0,
             "ln_bwd: alignment");
-    ln_bwd_kernel<<<(unsigned)ceil_div_l(rows, 8), 256, 0, st>>>(dy, ldd, x, ldx, rows, C, gamma, stats, add, ldadd, dx32,
+    S2I_LAUNCH((ln_bwd_kernel), (unsigned)ceil_div_l(rows, 8), 256, 0, st, dy, ldd, x, ldx, rows, C, gamma, stats, add, ldadd, dx32,
                                                                 ld32, (__half*)dx16, ld16);
     S2I_LAUNCH_CHECK();
     return 0;
 }
 
 int softmax_fwd(const float* s, long lds, long rows, int n, void* p16, long ldp, cudaStream_t st) {
-    softmax_fwd_kernel<<<(unsigned)ceil_div_l(rows, 8), 256, 0, st>>>(s, lds, rows, n, (__half*)p16, ldp);
+    S2I_LAUNCH((softmax_fwd_kernel), (unsigned)ceil_div_l(rows, 8), 256, 0, st, s, lds, rows, n, (__half*)p16, ldp);
     S2I_LAUNCH_CHECK();
     return 0;
 }
 
 int softmax_bwd(const void* p16, long ldp, const float* dp, long lddp, long rows, int n, float scale, void* ds16,
                 long ldds, cudaStream_t st) {
-    softmax_bwd_kernel<<<(unsigned)ceil_div_l(rows, 8), 256, 0, st>>>((const __half*)p16, ldp, dp, lddp, rows, n, scale,
+    S2I_LAUNCH((softmax_bwd_kernel), (unsigned)ceil_div_l(rows, 8), 256, 0, st, (const __half*)p16, ldp, dp, lddp, rows, n, scale,
                                                                      (__half*)ds16, ldds);
     S2I_LAUNCH_CHECK();
     return 0;
@@ -1045,7 +1085,7 @@ int softmax_bwd(const void* p16, long ldp, const float* dp, long lddp, long rows
 
 int geglu_fwd(const float* ff, long ldf, long rows, int F, void* out16, long ld16, cudaStream_t st) {
     S2I_REQ((F & 3) == 0 && (ldf & 3) == 0 && (ld16 & 3) == 0, "geglu_fwd: alignment");
-    geglu_fwd_kernel<<<grid_for(rows * (F >> 2), 256), 256, 0, st>>>(ff, ldf, rows, F, (__half*)out16, ld16);
+    S2I_LAUNCH((geglu_fwd_kernel), grid_for(rows * (F >> 2), 256), 256, 0, st, ff, ldf, rows, F, (__half*)out16, ld16);
     S2I_LAUNCH_CHECK();
     return 0;
 }
@@ -1053,7 +1093,7 @@ int geglu_fwd(const float* ff, long ldf, long rows, int F, void* out16, long ld1
 int geglu_bwd(const float* dg, long ldg, const float* ff, long ldf, long rows, int F, void* dff16, long ld16,
               cudaStream_t st) {
     S2I_REQ((F & 3) == 0 && (ldf & 3) == 0 && (ldg & 3) == 0 && (ld16 & 3) == 0, "geglu_bwd: alignment");
-    geglu_bwd_kernel<<<grid_for(rows * (F >> 2), 256), 256, 0, st>>>(dg, ldg, ff, ldf, rows, F, (__half*)dff16, ld16);
+    S2I_LAUNCH((geglu_bwd_kernel), grid_for(rows * (F >> 2), 256), 256, 0, st, dg, ldg, ff, ldf, rows, F, (__half*)dff16, ld16);
     S2I_LAUNCH_CHECK();
     return 0;
 }
@@ -1061,7 +1101,7 @@ int geglu_bwd(const float* dg, long ldg, const float* ff, long ldf, long rows, i
 int add2d(const float* a, long lda, const float* b, long ldb, long rows, int cols, float* dst32, long ld32, void* dst16,
           long ld16, cudaStream_t st) {
     S2I_REQ((cols & 3) == 0 && (lda & 3) == 0 && (ldb & 3) == 0 && (ld32 & 3) == 0 && (ld16 & 3) == 0, "add2d: alignment");
-    add2d_kernel<<<grid_for(rows * (cols >> 2), 256), 256, 0, st>>>(a, lda, b, ldb, rows, cols, dst32, ld32,
+    S2I_LAUNCH((add2d_kernel), grid_for(rows * (cols >> 2), 256), 256, 0, st, a, lda, b, ldb, rows, cols, dst32, ld32,
                                                                    (__half*)dst16, ld16);
     S2I_LAUNCH_CHECK();
     return 0;
@@ -1069,14 +1109,14 @@ int add2d(const float* a, long lda, const float* b, long ldb, long rows, int col
 
 int cast2d(const float* a, long lda, long rows, int cols, float mul, void* dst16, long ld16, cudaStream_t st) {
     S2I_REQ((cols & 3) == 0 && (lda & 3) == 0 && (ld16 & 3) == 0, "cast2d: alignment");
-    cast2d_kernel<<<grid_for(rows * (cols >> 2), 256), 256, 0, st>>>(a, lda, rows, cols, mul, (__half*)dst16, ld16);
+    S2I_LAUNCH((cast2d_kernel), grid_for(rows * (cols >> 2), 256), 256, 0, st, a, lda, rows, cols, mul, (__half*)dst16, ld16);
     S2I_LAUNCH_CHECK();
     return 0;
 }
 
 int upsample2x(const float* x, long ldx, int B, int H, int W, int C, void* out16, long ld16, cudaStream_t st) {
     S2I_REQ((C & 3) == 0 && (ldx & 3) == 0 && (ld16 & 3) == 0, "upsample2x: alignment");
-    upsample2x_kernel<<<grid_for((long)B * 4 * H * W * (C >> 2), 256), 256, 0, st>>>(x, ldx, B, H, W, C, (__half*)out16,
+    S2I_LAUNCH((upsample2x_kernel), grid_for((long)B * 4 * H * W * (C >> 2), 256), 256, 0, st, x, ldx, B, H, W, C, (__half*)out16,
                                                                                     ld16);
     S2I_LAUNCH_CHECK();
     return 0;
@@ -1084,14 +1124,14 @@ int upsample2x(const float* x, long ldx, int B, int H, int W, int C, void* out16
 
 int sumpool2x(const float* d, long ldd, int B, int H, int W, int C, float* dx, long ldx, cudaStream_t st) {
     S2I_REQ((C & 3) == 0 && (ldx & 3) == 0 && (ldd & 3) == 0, "sumpool2x: alignment");
-    sumpool2x_kernel<<<grid_for((long)B * H * W * (C >> 2), 256), 256, 0, st>>>(d, ldd, B, H, W, C, dx, ldx);
+    S2I_LAUNCH((sumpool2x_kernel), grid_for((long)B * H * W * (C >> 2), 256), 256, 0, st, d, ldd, B, H, W, C, dx, ldx);
     S2I_LAUNCH_CHECK();
     return 0;
 }
 
 int zero_insert2x(const float* d, long ldd, int B, int Ho, int Wo, int C, void* out16, long ld16, cudaStream_t st) {
     S2I_REQ((C & 3) == 0 && (ldd & 3) == 0 && (ld16 & 3) == 0, "zero_insert2x: alignment");
-    zero_insert2x_kernel<<<grid_for((long)B * 4 * Ho * Wo * (C >> 2), 256), 256, 0, st>>>(d, ldd, B, Ho, Wo, C,
+    S2I_LAUNCH((zero_insert2x_kernel), grid_for((long)B * 4 * Ho * Wo * (C >> 2), 256), 256, 0, st, d, ldd, B, Ho, Wo, C,
                                                                                          (__half*)out16, ld16);
     S2I_LAUNCH_CHECK();
     return 0;
@@ -1102,33 +1142,33 @@ int im2col3x3(const float* x, long ldx, int B, int H, int W, int C, int stride, 
     S2I_REQ(stride == 1 || stride == 2, "im2col3x3: stride");
     const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
     S2I_REQ(ldcol >= 9L * C, "im2col3x3: ldcol too small");
-    im2col3x3_kernel<<<grid_for((long)B * Ho * Wo * ldcol, 256), 256, 0, st>>>(x, ldx, B, H, W, C, stride, Ho, Wo,
+    S2I_LAUNCH((im2col3x3_kernel), grid_for((long)B * Ho * Wo * ldcol, 256), 256, 0, st, x, ldx, B, H, W, C, stride, Ho, Wo,
                                                                               (__half*)col16, ldcol);
     S2I_LAUNCH_CHECK();
     return 0;
 }
 
 int nchw_to_nhwc(const float* src, int B, int C, int H, int W, float* dst, long ldn, cudaStream_t st) {
-    nchw_to_nhwc_kernel<<<grid_for((long)B * H * W * ldn, 256), 256, 0, st>>>(src, B, C, H, W, dst, ldn);
+    S2I_LAUNCH((nchw_to_nhwc_kernel), grid_for((long)B * H * W * ldn, 256), 256, 0, st, src, B, C, H, W, dst, ldn);
     S2I_LAUNCH_CHECK();
     return 0;
 }
 
 int nhwc_to_nchw(const float* src, long ldn, int B, int C, int H, int W, float* dst, cudaStream_t st) {
-    nhwc_to_nchw_kernel<<<grid_for((long)B * C * H * W, 256), 256, 0, st>>>(src, ldn, B, C, H, W, dst);
+    S2I_LAUNCH((nhwc_to_nchw_kernel), grid_for((long)B * C * H * W, 256), 256, 0, st, src, ldn, B, C, H, W, dst);
     S2I_LAUNCH_CHECK();
     return 0;
 }
 
 int gemv(const float* x, int K, const void* w16, const float* bias, int N, int silu_in, float* out, cudaStream_t st) {
     S2I_REQ((K & 1) == 0, "gemv: K must be even");
-    gemv_kernel<<<ceil_div(N, 8), 256, 0, st>>>(x, K, (const __half*)w16, bias, N, silu_in, out);
+    S2I_LAUNCH((gemv_kernel), ceil_div(N, 8), 256, 0, st, x, K, (const __half*)w16, bias, N, silu_in, out);
     S2I_LAUNCH_CHECK();
     return 0;
 }
 
 int timestep_embedding(float t, int dim, float* out, cudaStream_t st) {
-    timestep_embedding_kernel<<<1, 256, 0, st>>>(t, dim, out);
+    S2I_LAUNCH((timestep_embedding_kernel), 1, 256, 0, st, t, dim, out);
     S2I_LAUNCH_CHECK();
     return 0;
 }

@@ -33,6 +33,8 @@ __device__ __forceinline__ void src_index(int dst, float scale, int S, int& i0, 
 __global__ void __launch_bounds__(256) lgp_features_kernel(TapTable tt, int B, int L, const float* __restrict__ noise,
                                                            float sigma, const float* __restrict__ dsigma, int P, int D,
                                                            __half* __restrict__ X, long ldX) {
+    pdl_wait();
+    pdl_launch();
     if (dsigma) sigma = __ldg(dsigma);      // graph-replayed steps read the step's scalars from device memory
     const int chunks = (int)(ldX >> 3);
     const long total = (long)B * L * L * chunks;
@@ -109,6 +111,8 @@ __global__ void __launch_bounds__(256) lgp_features_kernel(TapTable tt, int B, i
 __global__ void __launch_bounds__(256) lgp_features_nchw_kernel(const float* __restrict__ x, const float* __restrict__ t,
                                                                 int B, int L, int Cx, int P, int D,
                                                                 __half* __restrict__ X, long ldX) {
+    pdl_wait();
+    pdl_launch();
     const long total = (long)B * L * L * ldX;
     const long hw = (long)L * L;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -132,6 +136,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const __half* __restrict__ h, const __half* __restrict__ dy,
                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
                                                         long R, int N, int chunk, double* __restrict__ out) {
+    pdl_wait();
+    pdl_launch();
     const int s = blockIdx.y;
     const long r0 = (long)blockIdx.x * chunk;
     const long r1 = min(R, r0 + chunk);
@@ -165,6 +171,8 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __half* __restrict
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ rm,
                                    const float* __restrict__ rv, int train, long R, int N, int S, float* __restrict__ mean,
                                    float* __restrict__ rstd) {
+    pdl_wait();
+    pdl_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S * N) return;
     const int c = i % N;
@@ -184,6 +192,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __half* __restrict_
                                                        const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, long R, int N, long rows,
                                                        __half* __restrict__ out) {
+    pdl_wait();
+    pdl_launch();
     const long total = rows * (N >> 1);
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const long row = idx / (N >> 1);
@@ -202,6 +212,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
                                                            const float* __restrict__ gamma,
                                                            const double* __restrict__ bsums, int train, long R, int N,
                                                            long rows, float qscale, __half* __restrict__ out) {
+    pdl_wait();
+    pdl_launch();
     const long total = rows * (N >> 1);
     const float qinv = qscale != 0.f ? 1.f / qscale : 0.f;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -234,6 +246,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
 __global__ void __launch_bounds__(256) lgp_loss_kernel(const __half* __restrict__ out16, const float* __restrict__ target,
                                                        int B, int L, int O, float inv_n, float gscale, int emulate,
                                                        __half* __restrict__ dout, float* __restrict__ loss) {
+    pdl_wait();
+    pdl_launch();
     const long rows = (long)B * L * L;
     const long hw = (long)L * L;
     for (long row = (long)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (long)gridDim.x * blockDim.x) {
@@ -260,6 +274,8 @@ __global__ void __launch_bounds__(256) lgp_loss_kernel(const __half* __restrict_
 // tap_grad[b][y][x][c] = sum_{h,w} wy(h,y) wx(w,x) dX[(b,h,w)][off + c]   (adjoint of the bilinear resize)
 __global__ void __launch_bounds__(256) interp_bwd_kernel(const __half* __restrict__ dX, long ldX, int off, int B, int L,
                                                          int S, int C, float* __restrict__ g) {
+    pdl_wait();
+    pdl_launch();
     const int chunks = C >> 3;
     const long total = (long)B * S * S * chunks;
     const float scale = (float)S / (float)L, f = (float)L / (float)S;
@@ -314,6 +330,8 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(const __half* __restric
 }
 
 __global__ void lgp_export_kernel(const __half* __restrict__ out16, int B, int L, int O, float* __restrict__ dst) {
+    pdl_wait();
+    pdl_launch();
     const long total = (long)B * L * L * O;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % O);
@@ -328,6 +346,8 @@ __global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* __restrict__
                                                        int n, float g, float sb_t, float sa_t, float sa_p, float sb_p,
                                                        const float* __restrict__ dparams, int prediction,
                                                        float* __restrict__ out) {
+    pdl_wait();
+    pdl_launch();
     if (dparams) {      // graph-replayed steps read the step's scalars from device memory
         sb_t = __ldg(dparams + 0);
         sa_t = __ldg(dparams + 1);
@@ -356,6 +376,8 @@ __global__ void __launch_bounds__(256) guidance_norms_kernel(const float* __rest
                                                              const float* __restrict__ x_new,
                                                              const float* __restrict__ dx, int n,
                                                              double* __restrict__ scratch) {
+    pdl_wait();
+    pdl_launch();
     const int s = blockIdx.y;
     float a = 0.f, b = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -388,6 +410,8 @@ __global__ void __launch_bounds__(256) guidance_norms_kernel(const float* __rest
 
 __global__ void __launch_bounds__(256) guidance_apply_kernel(float* __restrict__ x_new, const float* __restrict__ dx,
                                                              int n, float beta, const double* __restrict__ scratch) {
+    pdl_wait();
+    pdl_launch();
     const int s = blockIdx.y;
     // ||x_in - latents|| runs over both CFG copies of x_in (pipeline.py:160): sqrt(2 * sum d^2)
     const float num = (float)sqrt(2.0 * scratch[2 * s]);
@@ -524,7 +548,7 @@ int LGP::mlp(cudaStream_t st) {
     dA_ = ws.take<__half>((size_t)rows * 512);
     dB_ = ws.take<__half>((size_t)rows * 512);
     double* sums = ws.take<double>((size_t)S * 960 * 2 * 2);
-    S2I_CUDA(cudaMemsetAsync(sums, 0, (size_t)S * 960 * 2 * 2 * sizeof(double), st));
+    S2I_MEMOP(cudaMemsetAsync(sums, 0, (size_t)S * 960 * 2 * 2 * sizeof(double), st));
     size_t so = 0;
     for (int l = 0; l < 4; ++l) {
         bsum_[l] = sums + so;
@@ -538,7 +562,7 @@ int LGP::mlp(cudaStream_t st) {
         mean_[l] = ws.take<float>((size_t)S * widths_[l + 1]);
         rstd_[l] = ws.take<float>((size_t)S * widths_[l + 1]);
     }
-    S2I_CUDA(cudaMemsetAsync(out16_, 0, (size_t)rows * 8 * 2, st));
+    S2I_MEMOP(cudaMemsetAsync(out16_, 0, (size_t)rows * 8 * 2, st));
 
     for (int l = 0; l < 5; ++l) {
         const int K = widths_[l], N = widths_[l + 1];
@@ -559,13 +583,13 @@ int LGP::mlp(cudaStream_t st) {
         if (l < 4) {
             if (train_) {
                 dim3 grid((unsigned)ceil_div_l(R, 128), S);
-                bn_reduce_kernel<0><<<grid, min(256, N / 2), 0, st>>>(h_[l], nullptr, nullptr, nullptr, R, N, 128, bsum_[l]);
+                S2I_LAUNCH((bn_reduce_kernel<0>), grid, min(256, N / 2), 0, st, h_[l], nullptr, nullptr, nullptr, R, N, 128, bsum_[l]);
                 S2I_LAUNCH_CHECK();
             }
-            bn_finalize_kernel<<<ceil_div(S * N, 256), 256, 0, st>>>(bsum_[l], bn_rm_[l], bn_rv_[l], train_ ? 1 : 0, R, N, S,
+            S2I_LAUNCH((bn_finalize_kernel), ceil_div(S * N, 256), 256, 0, st, bsum_[l], bn_rm_[l], bn_rv_[l], train_ ? 1 : 0, R, N, S,
                                                                      mean_[l], rstd_[l]);
             S2I_LAUNCH_CHECK();
-            bn_apply_kernel<<<grid1d(rows * (N / 2)), 256, 0, st>>>(h_[l], mean_[l], rstd_[l], bn_[l].g, bn_[l].b, R, N, rows,
+            S2I_LAUNCH((bn_apply_kernel), grid1d(rows * (N / 2)), 256, 0, st, h_[l], mean_[l], rstd_[l], bn_[l].g, bn_[l].b, R, N, rows,
                                                                     a_[l]);
             S2I_LAUNCH_CHECK();
         }
@@ -597,7 +621,7 @@ int LGP::forward(const LgpTap taps[9], int B, int L, const float* noise, float s
     groups_ = B / 2;
     S2I_TRY(ensure(lgp_ws_bytes(rows, ldX_, B / 2)));
     X_ = reinterpret_cast<__half*>(buf_);   // first workspace slot (see mlp())
-    lgp_features_kernel<<<grid1d(rows * (ldX_ / 8)), 256, 0, st>>>(tt, B, L, noise, sigma, dsigma, P_, D_, X_, ldX_);
+    S2I_LAUNCH((lgp_features_kernel), grid1d(rows * (ldX_ / 8)), 256, 0, st, tt, B, L, noise, sigma, dsigma, P_, D_, X_, ldX_);
     S2I_LAUNCH_CHECK();
     return mlp(st);
 }
@@ -609,7 +633,7 @@ int LGP::forward_nchw(const float* x, const float* t, int B, int L, bool train, 
     const long rows = (long)B * L * L;
     S2I_TRY(ensure(lgp_ws_bytes(rows, ldX_, 1)));
     X_ = reinterpret_cast<__half*>(buf_);
-    lgp_features_nchw_kernel<<<grid1d(rows * ldX_), 256, 0, st>>>(x, t, B, L, D_ - 4 - 4 * P_, P_, D_, X_, ldX_);
+    S2I_LAUNCH((lgp_features_nchw_kernel), grid1d(rows * ldX_), 256, 0, st, x, t, B, L, D_ - 4 - 4 * P_, P_, D_, X_, ldX_);
     S2I_LAUNCH_CHECK();
     for (int k = 0; k < 9; ++k) taps_[k] = LgpTap{nullptr, 0, 0};
     return mlp(st);
@@ -617,7 +641,7 @@ int LGP::forward_nchw(const float* x, const float* t, int B, int L, bool train, 
 
 int LGP::export_output(float* out_rows, cudaStream_t st) {
     if (!have_fwd_) return set_error(S2I_ERR_STATE, "lgp: no forward yet");
-    lgp_export_kernel<<<grid1d((long)B_ * L_ * L_ * O_), 256, 0, st>>>(out16_, B_, L_, O_, out_rows);
+    S2I_LAUNCH((lgp_export_kernel), grid1d((long)B_ * L_ * L_ * O_), 256, 0, st, out16_, B_, L_, O_, out_rows);
     S2I_LAUNCH_CHECK();
     return 0;
 }
@@ -631,8 +655,8 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
     const long R = 2L * L_ * L_;
     const long n_elem = (long)O_ * L_ * L_;
     gscale_ = exp2f(ceilf(log2f((float)n_elem)));
-    S2I_CUDA(cudaMemsetAsync(loss, 0, S * sizeof(float), st));
-    lgp_loss_kernel<<<grid1d(rows), 256, 0, st>>>(out16_, target, B_, L_, O_, 1.f / (float)n_elem, gscale_,
+    S2I_MEMOP(cudaMemsetAsync(loss, 0, S * sizeof(float), st));
+    S2I_LAUNCH((lgp_loss_kernel), grid1d(rows), 256, 0, st, out16_, target, B_, L_, O_, 1.f / (float)n_elem, gscale_,
                                                   emulate_fp16_grad ? 1 : 0, dout_, loss);
     const float qs = emulate_fp16_grad ? gscale_ : 0.f;
     S2I_LAUNCH_CHECK();
@@ -658,11 +682,11 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
         const int bl = l - 1;
         if (train_) {
             dim3 grid((unsigned)ceil_div_l(R, 128), S);
-            bn_reduce_kernel<1><<<grid, min(256, N / 2), 0, st>>>(h_[bl], o, mean_[bl], rstd_[bl], R, N, 128, bbsum_[bl]);
+            S2I_LAUNCH((bn_reduce_kernel<1>), grid, min(256, N / 2), 0, st, h_[bl], o, mean_[bl], rstd_[bl], R, N, 128, bbsum_[bl]);
             S2I_LAUNCH_CHECK();
         }
         __half* o2 = bufs[flip ^ 1];
-        bn_bwd_apply_kernel<<<grid1d(rows * (N / 2)), 256, 0, st>>>(o, h_[bl], mean_[bl], rstd_[bl], bn_[bl].g, bbsum_[bl],
+        S2I_LAUNCH((bn_bwd_apply_kernel), grid1d(rows * (N / 2)), 256, 0, st, o, h_[bl], mean_[bl], rstd_[bl], bn_[bl].g, bbsum_[bl],
                                                                     train_ ? 1 : 0, R, N, rows, qs, o2);
         S2I_LAUNCH_CHECK();
         d = o2;
@@ -674,7 +698,7 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
     for (int k = 0; k < 9; ++k) {
         if (!taps_[k].S) return set_error(S2I_ERR_STATE, "lgp: backward to taps needs the tap-based forward");
         if (tap_grads[k]) {
-            interp_bwd_kernel<<<grid1d((long)B_ * taps_[k].S * taps_[k].S * (taps_[k].C / 8)), 256, 0, st>>>(
+            S2I_LAUNCH((interp_bwd_kernel), grid1d((long)B_ * taps_[k].S * taps_[k].S * (taps_[k].C / 8)), 256, 0, st, 
                 X_, ldX_, off, B_, L_, taps_[k].S, taps_[k].C, tap_grads[k]);
             S2I_LAUNCH_CHECK();
         }
@@ -686,7 +710,7 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
 // ================================================================================================== step
 int cfg_ddim_step(const float* latents, const float* eps, int S, int n, float guidance, float sb_t, float sa_t,
                   float sa_p, float sb_p, int prediction, float* out, cudaStream_t st, const float* dparams) {
-    cfg_ddim_kernel<<<grid1d((long)S * n), 256, 0, st>>>(latents, eps, S, n, guidance, sb_t, sa_t, sa_p, sb_p, dparams,
+    S2I_LAUNCH((cfg_ddim_kernel), grid1d((long)S * n), 256, 0, st, latents, eps, S, n, guidance, sb_t, sa_t, sa_p, sb_p, dparams,
                                                          prediction, out);
     S2I_LAUNCH_CHECK();
     return 0;
@@ -694,11 +718,11 @@ int cfg_ddim_step(const float* latents, const float* eps, int S, int n, float gu
 
 int guidance_update(const float* x_old, float* x_new, const float* dx, int S, int n, float beta, double* scratch,
                     cudaStream_t st) {
-    S2I_CUDA(cudaMemsetAsync(scratch, 0, (size_t)S * 2 * sizeof(double), st));
+    S2I_MEMOP(cudaMemsetAsync(scratch, 0, (size_t)S * 2 * sizeof(double), st));
     dim3 grid(grid1d(n, 256, 64), S);
-    guidance_norms_kernel<<<grid, 256, 0, st>>>(x_old, x_new, dx, n, scratch);
+    S2I_LAUNCH((guidance_norms_kernel), grid, 256, 0, st, x_old, x_new, dx, n, scratch);
     S2I_LAUNCH_CHECK();
-    guidance_apply_kernel<<<grid, 256, 0, st>>>(x_new, dx, n, beta, scratch);
+    S2I_LAUNCH((guidance_apply_kernel), grid, 256, 0, st, x_new, dx, n, beta, scratch);
     S2I_LAUNCH_CHECK();
     return 0;
 }

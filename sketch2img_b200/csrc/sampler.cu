@@ -47,23 +47,23 @@ class Sampler {
         S2I_TRY(ensure_params());
         float* hp = h_sp_ + (ring_++ % kRing) * 8;
         hp[0] = sb_t; hp[1] = sa_t; hp[2] = sa_p; hp[3] = sb_p; hp[4] = sigma;
-        S2I_CUDA(cudaMemcpyAsync(d_sp_, hp, 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+        S2I_MEMOP(cudaMemcpyAsync(d_sp_, hp, 8 * sizeof(float), cudaMemcpyHostToDevice, st));
         S2I_TRY(unet->prepare_time(t, st));
 
         Key key{S, L, prediction, do_guide ? 1 : 0, lgp_train, guidance, beta};
         // The replayed part works on sampler-owned copies of the caller's tensors, so one graph serves every image.
         S2I_TRY(layout(key));
         const size_t nb = (size_t)S * unet->cfg.in_ch * L * L * sizeof(float);
-        S2I_CUDA(cudaMemcpyAsync(own_lat_, latents, nb, cudaMemcpyDeviceToDevice, st));
-        S2I_CUDA(cudaMemcpyAsync(own_ctx_, ctx, (size_t)2 * S * unet->cfg.ctx_len * unet->cfg.cross_dim * sizeof(float),
+        S2I_MEMOP(cudaMemcpyAsync(own_lat_, latents, nb, cudaMemcpyDeviceToDevice, st));
+        S2I_MEMOP(cudaMemcpyAsync(own_ctx_, ctx, (size_t)2 * S * unet->cfg.ctx_len * unet->cfg.cross_dim * sizeof(float),
                                  cudaMemcpyDeviceToDevice, st));
         if (do_guide) {
-            S2I_CUDA(cudaMemcpyAsync(own_noise_, noise, nb, cudaMemcpyDeviceToDevice, st));
-            S2I_CUDA(cudaMemcpyAsync(own_target_, target, nb, cudaMemcpyDeviceToDevice, st));
+            S2I_MEMOP(cudaMemcpyAsync(own_noise_, noise, nb, cudaMemcpyDeviceToDevice, st));
+            S2I_MEMOP(cudaMemcpyAsync(own_target_, target, nb, cudaMemcpyDeviceToDevice, st));
         }
         S2I_TRY(run(key, st));
-        S2I_CUDA(cudaMemcpyAsync(latents, own_lat_, nb, cudaMemcpyDeviceToDevice, st));
-        if (do_guide && loss_out) S2I_CUDA(cudaMemcpyAsync(loss_out, own_loss_, S * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        S2I_MEMOP(cudaMemcpyAsync(latents, own_lat_, nb, cudaMemcpyDeviceToDevice, st));
+        if (do_guide && loss_out) S2I_MEMOP(cudaMemcpyAsync(loss_out, own_loss_, S * sizeof(float), cudaMemcpyDeviceToDevice, st));
         return 0;
     }
 
@@ -123,7 +123,7 @@ class Sampler {
             }
             e->alloc_gen = g_alloc_gen;
         }
-        S2I_CUDA(cudaGraphLaunch(e->exec, st));
+        S2I_MEMOP(cudaGraphLaunch(e->exec, st));
         g_launches += e->launches;
         return 0;
     }
@@ -191,8 +191,8 @@ class Sampler {
         const int B = 2 * S;
         // x_in = cat([latents] * 2) per sample, ordered (uncond_s, cond_s)   (pipeline.py:85)
         for (int s = 0; s < S; ++s) {
-            S2I_CUDA(cudaMemcpyAsync(x_in_ + (size_t)(2 * s) * n, own_lat_ + (size_t)s * n, n * 4, cudaMemcpyDeviceToDevice, st));
-            S2I_CUDA(cudaMemcpyAsync(x_in_ + (size_t)(2 * s + 1) * n, own_lat_ + (size_t)s * n, n * 4, cudaMemcpyDeviceToDevice, st));
+            S2I_MEMOP(cudaMemcpyAsync(x_in_ + (size_t)(2 * s) * n, own_lat_ + (size_t)s * n, n * 4, cudaMemcpyDeviceToDevice, st));
+            S2I_MEMOP(cudaMemcpyAsync(x_in_ + (size_t)(2 * s + 1) * n, own_lat_ + (size_t)s * n, n * 4, cudaMemcpyDeviceToDevice, st));
         }
         const bool do_guide = k.guided != 0;
         S2I_TRY(unet->forward(x_in_, B, L, L, 0.f, own_ctx_, eps_, do_guide, st, /*time_ready=*/true));    // :96
@@ -210,7 +210,7 @@ class Sampler {
             S2I_TRY(unet->backward(tg_, dx_, st));                                                   // :159 (UNet part)
             S2I_TRY(guidance_update(own_lat_, x_new_, dx_, S, n, k.beta, norms_, st));               // :160-161
         }
-        S2I_CUDA(cudaMemcpyAsync(own_lat_, x_new_, (size_t)S * n * 4, cudaMemcpyDeviceToDevice, st));
+        S2I_MEMOP(cudaMemcpyAsync(own_lat_, x_new_, (size_t)S * n * 4, cudaMemcpyDeviceToDevice, st));
         return 0;
     }
 

@@ -769,7 +769,7 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
     stats_off_ = 0;
     stats_cap_ = (size_t)kStatsSlots * B * kGroups * 2;
     stats_ = dalloc<double>(stats_cap_);
-    if (!dry_) S2I_CUDA(cudaMemsetAsync(stats_, 0, stats_cap_ * sizeof(double), st_));
+    if (!dry_) S2I_MEMOP(cudaMemsetAsync(stats_, 0, stats_cap_ * sizeof(double), st_));
     debug.clear();
 
     // time embedding -> fused per-resnet projections (persistent buffer; see prepare_time)
@@ -875,7 +875,7 @@ int UNet::run_backward(float* const tap_grads[9], float* dx_nchw) {
     size_t save_off = stats_off_;
     stats_ = dalloc<double>(bstat_cap);
     stats_off_ = 0;
-    if (!dry_) S2I_CUDA(cudaMemsetAsync(stats_, 0, bstat_cap * sizeof(double), st_));
+    if (!dry_) S2I_MEMOP(cudaMemsetAsync(stats_, 0, bstat_cap * sizeof(double), st_));
 
     auto tapg = [&](int k) {
         F32 g = taps[k];
@@ -977,7 +977,7 @@ int UNet::prepare_time(float t, cudaStream_t st) {
     if (integral) {
         auto it = temb_cache_.find((int)t);
         if (it != temb_cache_.end()) {
-            S2I_CUDA(cudaMemcpyAsync(temb_, it->second, bytes, cudaMemcpyDeviceToDevice, st));
+            S2I_MEMOP(cudaMemcpyAsync(temb_, it->second, bytes, cudaMemcpyDeviceToDevice, st));
             return 0;
         }
     }
@@ -990,7 +990,7 @@ int UNet::prepare_time(float t, cudaStream_t st) {
         if (cudaMalloc(&c, bytes) == cudaSuccess) {
             owned_.push_back(c);
             temb_cache_[(int)t] = static_cast<float*>(c);
-            S2I_CUDA(cudaMemcpyAsync(c, temb_, bytes, cudaMemcpyDeviceToDevice, st));
+            S2I_MEMOP(cudaMemcpyAsync(c, temb_, bytes, cudaMemcpyDeviceToDevice, st));
         } else {
             cudaGetLastError();
         }

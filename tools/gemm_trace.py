@@ -1,0 +1,46 @@
+"""GPU box: phase timeline of gemm_tma_kernel for a few shapes (median over CTAs, ns from kernel entry of the first CTA)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sketch2img_b200 import _lib as L  # noqa: E402
+from tools.gemm_bench import SHAPES, make  # noqa: E402
+
+NAMES = ["entry", "setup", "loads_issued", "mmas_issued", "epi_start", "accum_ready", "res_ready", "chunks_done", "stores_read", "exit",
+         "load0", "load1", "load2", "chunk0", "chunk1", "chunk2"]
+
+
+def main():
+    lib = L.lib()
+    lib.s2i_gemm_set_trace.argtypes = [C.c_void_p]
+    buf = torch.zeros(4096 * 16, dtype=torch.int64, device="cuda")
+    for shape in SHAPES:
+        if shape[0] not in ("lin 320->320 @64 res", "conv 320@64", "qkv 320->1152 @64", "lin 1280->1280 @16 res", "lin 1280->1280 @8 res"):
+            continue
+        kw, keep = make(shape)
+        d = L.GemmDesc(**kw)
+        for _ in range(3):
+            L.gemm(d)
+        torch.cuda.synchronize()
+        buf.zero_()
+        lib.s2i_gemm_set_trace(buf.data_ptr())
+        L.gemm(d)
+        torch.cuda.synchronize()
+        lib.s2i_gemm_set_trace(None)
+        t = buf.view(-1, 16).cpu()
+        t = t[t[:, 0] > 0][:, :16].double()
+        t0 = t[:, 0].min()
+        rel = t - t0
+        med = rel.median(dim=0).values
+        mx = rel.max(dim=0).values
+        print(f"{shape[0]}: {t.shape[0]} CTAs; first entry -> last exit {mx[9]:.0f} ns")
+        print("   median ns from first entry: " + ", ".join(f"{n}={v:.0f}" for n, v in zip(NAMES, med.tolist())))
+        print("   per-CTA medians (from own entry): " + ", ".join(f"{n}={v:.0f}" for n, v in zip(NAMES, (t - t[:, :1]).median(dim=0).values.tolist())))
+
+
+if __name__ == "__main__":
+    main()
