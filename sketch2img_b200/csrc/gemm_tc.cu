@@ -695,14 +695,17 @@ TileChoice choose_tiles(int N, long tiles_m, int Z, int iters, bool allow_split)
 // Same pacing model with this kernel's constants: prologue + first-load latency ~4.5 k cycles, ~450 cycles per
 // 32-column epilogue chunk (+ the residual tile's L2 round trip), operands arriving at ~48 B/clk per SM when every SM
 // pulls from L2.  Split-K partial tiles are reduce-added into the (zeroed) output by the bulk-copy engine.
-double model_cycles_tma(int N, long tiles_m, int iters, int BN, int splits, bool residual) {
+double model_cycles_tma(int N, long tiles_m, int iters, int BN, int splits, int epi) {
+    const bool residual = (epi & 1) != 0;
     // Calibrated on B200 with tools/gemm_bench.py (profiles/r1_gemm_bench_v2.txt): every CTA pays ~9 k cycles of launch,
     // prologue, first-load and drain latency, so small problems want MANY short CTAs (two co-resident CTAs per SM hide
     // each other's latencies); operand tiles arrive from L2 at ~40 B/clk per SM when the whole chip pulls.
     const int tiles_n = ceil_div(N, BN);
     const long ctas = tiles_m * tiles_n * splits;
     const int stage_bytes = kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
-    const int occ = (2 * stage_bytes <= 100 * 1024) ? 2 : 1;
+    // two CTAs share an SM only if the pipeline (>= 2 stages) AND the epilogue staging that aliases it fit half of it
+    const int epi_bytes = (BN / 32) * (((epi & 2) ? 16384 : 0) + ((epi & 4) ? 8192 : 0));
+    const int occ = (2 * stage_bytes <= 100 * 1024 && epi_bytes <= 100 * 1024) ? 2 : 1;
     const long slots = (long)kNumSMs * occ;
     const long waves = ceil_div_l(ctas, slots);
     const int it = ceil_div(iters, splits);
@@ -717,7 +720,7 @@ double model_cycles_tma(int N, long tiles_m, int iters, int BN, int splits, bool
     return total;
 }
 
-TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, bool residual) {
+TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, int epi) {
     static const int cands[] = {256, 192, 160, 128, 96, 64, 32};
     TileChoice best{N >= 128 ? 128 : N, 1};
     double best_c = 1e30;
@@ -727,7 +730,7 @@ TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, bo
         for (int sp = 1; sp <= 32; sp *= 2) {
             if (sp > 1 && (!allow_split || base * sp > 2 * kNumSMs + 64 || iters / sp < 2)) break;
             if ((long)(sp - 1) * ceil_div(iters, sp) >= iters) continue;
-            const double cyc = model_cycles_tma(N, tiles_m, iters, c, sp, residual);
+            const double cyc = model_cycles_tma(N, tiles_m, iters, c, sp, epi);
             if (cyc < best_c) {
                 best_c = cyc;
                 best = TileChoice{c, sp};
@@ -835,12 +838,14 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     const long rows_total = (long)d.aW * d.aH * d.aB;
     bool can_split = d.splits >= 0 && d.out32 && !d.out16;
     bool via_scratch = false;
-    TileChoice tc = choose_tiles_tma(d.N, tiles_m, num_iters, can_split, d.residual != nullptr);
+    const int epi = (d.residual ? 1 : 0) | ((d.residual || d.out32) ? 2 : 0) | (d.out16 ? 4 : 0);
+    TileChoice tc = choose_tiles_tma(d.N, tiles_m, num_iters, can_split, epi);
     if (d.splits >= 0 && d.out16 && !d.out32 && (size_t)rows_total * d.N * sizeof(float) <= kWsBytes) {
         // fp16-only output of a K-heavy small problem: split K into an fp32 scratch tile matrix, then convert
-        const TileChoice ts = choose_tiles_tma(d.N, tiles_m, num_iters, true, d.residual != nullptr);
-        if (ts.splits > 1 && model_cycles_tma(d.N, tiles_m, num_iters, ts.BN, ts.splits, d.residual != nullptr) + 5000.0 <
-                                 model_cycles_tma(d.N, tiles_m, num_iters, tc.BN, 1, d.residual != nullptr)) {
+        const int epi_s = (d.residual ? 1 : 0) | 2;
+        const TileChoice ts = choose_tiles_tma(d.N, tiles_m, num_iters, true, epi_s);
+        if (ts.splits > 1 && model_cycles_tma(d.N, tiles_m, num_iters, ts.BN, ts.splits, epi_s) + 5000.0 <
+                                 model_cycles_tma(d.N, tiles_m, num_iters, tc.BN, 1, epi)) {
             S2I_TRY(ensure_ws());
             tc = ts;
             via_scratch = can_split = true;

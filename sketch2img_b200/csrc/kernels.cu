@@ -683,7 +683,14 @@ __device__ __forceinline__ float gelu_grad(float x) {
     return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
-__global__ void __launch_bounds__(256) geglu_fwd_kernel(const float* __restrict__ ff, long ldf, long rows, int F,
+__device__ __forceinline__ float4 ldh4(const __half* p) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+__global__ void __launch_bounds__(256) geglu_fwd_kernel(const __half* __restrict__ ff, long ldf, long rows, int F,
                                                         __half* __restrict__ out16, long ld16) {
     pdl_wait();
     pdl_launch();
@@ -692,15 +699,15 @@ __global__ void __launch_bounds__(256) geglu_fwd_kernel(const float* __restrict_
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const long r = idx / vec;
         const int c = (int)(idx - r * vec) << 2;
-        const float4 a = ldg4(ff + r * ldf + c);
-        const float4 g = ldg4(ff + r * ldf + F + c);
+        const float4 a = ldh4(ff + r * ldf + c);
+        const float4 g = ldh4(ff + r * ldf + F + c);
         *reinterpret_cast<uint2*>(out16 + r * ld16 + c) =
             pack_half4(a.x * gelu_exact(g.x), a.y * gelu_exact(g.y), a.z * gelu_exact(g.z), a.w * gelu_exact(g.w));
     }
 }
 
 __global__ void __launch_bounds__(256) geglu_bwd_kernel(const float* __restrict__ dg, long ldg,
-                                                        const float* __restrict__ ff, long ldf, long rows, int F,
+                                                        const __half* __restrict__ ff, long ldf, long rows, int F,
                                                         __half* __restrict__ dff16, long ld16) {
     pdl_wait();
     pdl_launch();
@@ -710,8 +717,8 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const float* __restrict_
         const long r = idx / vec;
         const int c = (int)(idx - r * vec) << 2;
         const float4 d = ldg4(dg + r * ldg + c);
-        const float4 a = ldg4(ff + r * ldf + c);
-        const float4 g = ldg4(ff + r * ldf + F + c);
+        const float4 a = ldh4(ff + r * ldf + c);
+        const float4 g = ldh4(ff + r * ldf + F + c);
         *reinterpret_cast<uint2*>(dff16 + r * ld16 + c) =
             pack_half4(d.x * gelu_exact(g.x), d.y * gelu_exact(g.y), d.z * gelu_exact(g.z), d.w * gelu_exact(g.w));
         *reinterpret_cast<uint2*>(dff16 + r * ld16 + F + c) =
@@ -1083,15 +1090,17 @@ int softmax_bwd(const void* p16, long ldp, const float* dp, long lddp, long rows
     return 0;
 }
 
-int geglu_fwd(const float* ff, long ldf, long rows, int F, void* out16, long ld16, cudaStream_t st) {
+int geglu_fwd(const void* ff16, long ldf, long rows, int F, void* out16, long ld16, cudaStream_t st) {
+    const __half* ff = static_cast<const __half*>(ff16);
     S2I_REQ((F & 3) == 0 && (ldf & 3) == 0 && (ld16 & 3) == 0, "geglu_fwd: alignment");
     S2I_LAUNCH((geglu_fwd_kernel), grid_for(rows * (F >> 2), 256), 256, 0, st, ff, ldf, rows, F, (__half*)out16, ld16);
     S2I_LAUNCH_CHECK();
     return 0;
 }
 
-int geglu_bwd(const float* dg, long ldg, const float* ff, long ldf, long rows, int F, void* dff16, long ld16,
+int geglu_bwd(const float* dg, long ldg, const void* ff16, long ldf, long rows, int F, void* dff16, long ld16,
               cudaStream_t st) {
+    const __half* ff = static_cast<const __half*>(ff16);
     S2I_REQ((F & 3) == 0 && (ldf & 3) == 0 && (ldg & 3) == 0 && (ld16 & 3) == 0, "geglu_bwd: alignment");
     S2I_LAUNCH((geglu_bwd_kernel), grid_for(rows * (F >> 2), 256), 256, 0, st, dg, ldg, ff, ldf, rows, F, (__half*)dff16, ld16);
     S2I_LAUNCH_CHECK();

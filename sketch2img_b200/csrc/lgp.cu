@@ -329,6 +329,71 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(const __half* __restric
     }
 }
 
+// Separable form of the same adjoint for the low-resolution taps (the direct gather above visits a (2f+2)^2 window per
+// output, 289 strided loads at f = 8): horizontal pass dX [B][L][L][.] -> T [B][L][S][C] fp32, vertical pass T -> g [B][S][S][C].
+__global__ void __launch_bounds__(256) interp_bwd_h_kernel(const __half* __restrict__ dX, long ldX, int off, int B, int L,
+                                                           int S, int C, float* __restrict__ T) {
+    pdl_wait();
+    pdl_launch();
+    const int chunks = C >> 3;
+    const long total = (long)B * L * S * chunks;
+    const float scale = (float)S / (float)L, f = (float)L / (float)S;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long pix = idx / chunks;                    // (b, h, x)
+        const int c = (int)(idx - pix * chunks) << 3;
+        const int x = (int)(pix % S);
+        const long bh = pix / S;                          // b * L + h
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int w_lo = max(0, (int)floorf(f * ((float)x - 0.5f) - 0.5f));
+        const int w_hi = min(L - 1, (int)ceilf(f * ((float)x + 1.5f) - 0.5f));
+        for (int w = w_lo; w <= w_hi; ++w) {
+            int i0, i1;
+            float l1;
+            src_index(w, scale, S, i0, i1, l1);
+            const float wx = (i0 == x ? 1.f - l1 : 0.f) + (i1 == x ? l1 : 0.f);
+            if (wx == 0.f) continue;
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(dX + (bh * L + w) * ldX + off + c));
+            const __half2* hp = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 v = __half22float2(hp[j]);
+                acc[2 * j] += wx * v.x;
+                acc[2 * j + 1] += wx * v.y;
+            }
+        }
+        float* o = T + pix * C + c;
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
+
+__global__ void __launch_bounds__(256) interp_bwd_v_kernel(const float* __restrict__ T, int B, int L, int S, int C,
+                                                           float* __restrict__ g) {
+    pdl_wait();
+    pdl_launch();
+    const int chunks = C >> 2;
+    const long total = (long)B * S * S * chunks;
+    const float scale = (float)S / (float)L, f = (float)L / (float)S;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long pix = idx / chunks;                    // (b, y, x)
+        const int c = (int)(idx - pix * chunks) << 2;
+        const int x = (int)(pix % S), y = (int)((pix / S) % S), b = (int)(pix / ((long)S * S));
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int h_lo = max(0, (int)floorf(f * ((float)y - 0.5f) - 0.5f));
+        const int h_hi = min(L - 1, (int)ceilf(f * ((float)y + 1.5f) - 0.5f));
+        for (int h = h_lo; h <= h_hi; ++h) {
+            int i0, i1;
+            float l1;
+            src_index(h, scale, S, i0, i1, l1);
+            const float wy = (i0 == y ? 1.f - l1 : 0.f) + (i1 == y ? l1 : 0.f);
+            if (wy == 0.f) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(T + (((long)b * L + h) * S + x) * C + c));
+            acc.x += wy * v.x; acc.y += wy * v.y; acc.z += wy * v.z; acc.w += wy * v.w;
+        }
+        *reinterpret_cast<float4*>(g + pix * C + c) = acc;
+    }
+}
+
 __global__ void lgp_export_kernel(const __half* __restrict__ out16, int B, int L, int O, float* __restrict__ dst) {
     pdl_wait();
     pdl_launch();
@@ -441,6 +506,7 @@ LGP::LGP(int input_dim, int output_dim, int num_pos_layers) : D_(input_dim), O_(
 }
 
 LGP::~LGP() {
+    if (interp_tmp_) cudaFree(interp_tmp_);
     for (void* p : owned_) cudaFree(p);
     if (buf_) cudaFree(buf_);
 }
@@ -694,13 +760,45 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
         // next GEMM writes into bufs[flip] again (its previous content, the BN input gradient, is dead)
     }
     // adjoint of resize + concat: gather each tap's gradient from dX (now in X_)
+    {
+        size_t need = 0;
+        for (int k = 0; k < 9; ++k)
+            if (tap_grads[k] && taps_[k].S * 4 <= L_) {
+                const size_t n = (size_t)B_ * L_ * taps_[k].S * taps_[k].C * sizeof(float);
+                if (n > need) need = n;
+            }
+        if (need > interp_cap_) {
+            if (interp_tmp_) cudaFree(interp_tmp_);
+            interp_tmp_ = nullptr;
+            interp_cap_ = 0;
+            void* q = nullptr;
+            if (cudaMalloc(&q, need) != cudaSuccess) {
+                cudaGetLastError();
+                return set_error(S2I_ERR_OOM, "lgp: cannot allocate the resize-adjoint scratch");
+            }
+            ++g_alloc_gen;
+            interp_tmp_ = static_cast<float*>(q);
+            interp_cap_ = need;
+        }
+    }
     int off = 0;
     for (int k = 0; k < 9; ++k) {
         if (!taps_[k].S) return set_error(S2I_ERR_STATE, "lgp: backward to taps needs the tap-based forward");
         if (tap_grads[k]) {
-            S2I_LAUNCH((interp_bwd_kernel), grid1d((long)B_ * taps_[k].S * taps_[k].S * (taps_[k].C / 8)), 256, 0, st, 
-                X_, ldX_, off, B_, L_, taps_[k].S, taps_[k].C, tap_grads[k]);
-            S2I_LAUNCH_CHECK();
+            const int Sk = taps_[k].S, Ck = taps_[k].C;
+            if (Sk * 4 <= L_) {
+                // resize factor >= 4: separable adjoint through a [B][L][S][C] fp32 intermediate
+                S2I_LAUNCH((interp_bwd_h_kernel), grid1d((long)B_ * L_ * Sk * (Ck / 8)), 256, 0, st, X_, ldX_, off, B_, L_, Sk, Ck,
+                           interp_tmp_);
+                S2I_LAUNCH_CHECK();
+                S2I_LAUNCH((interp_bwd_v_kernel), grid1d((long)B_ * Sk * Sk * (Ck / 4)), 256, 0, st, interp_tmp_, B_, L_, Sk, Ck,
+                           tap_grads[k]);
+                S2I_LAUNCH_CHECK();
+            } else {
+                S2I_LAUNCH((interp_bwd_kernel), grid1d((long)B_ * Sk * Sk * (Ck / 8)), 256, 0, st, X_, ldX_, off, B_, L_, Sk, Ck,
+                           tap_grads[k]);
+                S2I_LAUNCH_CHECK();
+            }
         }
         off += taps_[k].C;
     }

@@ -76,6 +76,8 @@ class LGP {
     bool have_fwd_ = false;
     int groups_ = 1;             // BatchNorm statistic groups (pairs on the sampling path, 1 for forward())
     float gscale_ = 1.f;
+    float* interp_tmp_ = nullptr;    // [B][L][S][C] intermediate of the separable resize adjoint
+    size_t interp_cap_ = 0;
 
     int ensure(size_t bytes);
     int mlp(cudaStream_t st);

@@ -691,8 +691,8 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     H16 l16c = new16(B, H, W, C);
     sv.l3 = dalloc<float>(rows * 2);
     RUN(ln_fwd(sv.t2.p, sv.t2.ld, rows, C, T.ln3.g, T.ln3.b, T.ln3.eps, l16c.p, l16c.ld, sv.l3, st_));
-    sv.ff = new32(B, H, W, 8 * C);
-    S2I_TRY(gemm(l16c, false, 1, T.ff1.w, C, 8 * C, C, T.ff1.b, nullptr, nullptr, &sv.ff, nullptr));
+    sv.ff = new16(B, H, W, 8 * C);
+    S2I_TRY(gemm(l16c, false, 1, T.ff1.w, C, 8 * C, C, T.ff1.b, nullptr, nullptr, nullptr, &sv.ff));
     H16 g16 = new16(B, H, W, 4 * C);
     RUN(geglu_fwd(sv.ff.p, sv.ff.ld, rows, 4 * C, g16.p, g16.ld, st_));
     H16 t3 = new16(B, H, W, C);
@@ -704,7 +704,6 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
         debug[pre + ".t0"] = sv.t0;
         debug[pre + ".t1"] = sv.t1;
         debug[pre + ".t2"] = sv.t2;
-        debug[pre + ".ff"] = sv.ff;
         debug[pre + ".out"] = out;
     }
     if (save_) tsave_[idx] = sv;

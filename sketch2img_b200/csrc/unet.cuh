@@ -86,7 +86,8 @@ struct ResSave {
     double *s1 = nullptr, *s2 = nullptr;
 };
 struct TfmSave {
-    F32 x, t0, t1, t2, ff;
+    F32 x, t0, t1, t2;
+    H16 ff;      // GEGLU projection [rows][8C] (fp16: only ever consumed as a * gelu(gate) and its derivative)
     double* gs = nullptr;
     float *l1 = nullptr, *l2 = nullptr, *l3 = nullptr;
     H16 qkv, P1, q2, kv2, P2;

@@ -14,17 +14,17 @@ SHAPES = [
     ("conv 320@64", 64, 8192, 320, 320, 9, 1, 1, 0),
     ("lin 320->320 @64 res", None, 8192, 320, 320, 1, 1, 1, 0),
     ("qkv 320->1152 @64", None, 8192, 1152, 320, 1, 0, 0, 1),
-    ("ff1 320->2560 @64", None, 8192, 2560, 320, 1, 0, 1, 0),
+    ("ff1 320->2560 @64", None, 8192, 2560, 320, 1, 0, 0, 1),
     ("ff2 1280->320 @64", None, 8192, 320, 1280, 1, 1, 0, 1),
     ("conv 960->320@64", 64, 8192, 320, 960, 9, 1, 1, 0),
     ("conv 640@32", 32, 2048, 640, 640, 9, 1, 1, 0),
     ("lin 640->640 @32 res", None, 2048, 640, 640, 1, 1, 1, 0),
-    ("ff1 640->5120 @32", None, 2048, 5120, 640, 1, 0, 1, 0),
+    ("ff1 640->5120 @32", None, 2048, 5120, 640, 1, 0, 0, 1),
     ("ff2 2560->640 @32", None, 2048, 640, 2560, 1, 1, 0, 1),
     ("conv 1280@16", 16, 512, 1280, 1280, 9, 1, 1, 0),
     ("conv 2560->1280@16", 16, 512, 1280, 2560, 9, 1, 1, 0),
     ("lin 1280->1280 @16 res", None, 512, 1280, 1280, 1, 1, 1, 0),
-    ("ff1 1280->10240 @16", None, 512, 10240, 1280, 1, 0, 1, 0),
+    ("ff1 1280->10240 @16", None, 512, 10240, 1280, 1, 0, 0, 1),
     ("ff2 5120->1280 @16", None, 512, 1280, 5120, 1, 1, 0, 1),
     ("conv 1280@8", 8, 128, 1280, 1280, 9, 1, 1, 0),
     ("conv 2560->1280@8", 8, 128, 1280, 2560, 9, 1, 1, 0),

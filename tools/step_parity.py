@@ -37,7 +37,7 @@ def main(name="tiny", t=981, B=2):
     xb = torch.randn(B, 4, L, L, generator=g).cuda()
     eb = torch.randn(B, 77, emb.shape[2], generator=g).cuda()
     eng.set_debug(True)
-    names = ["conv_in", "r0.h1", "r0.out", "t0.t0", "t0.t1", "t0.t2", "t0.ff", "t0.out", "r1.h1", "r1.out", "t1.out",
+    names = ["conv_in", "r0.h1", "r0.out", "t0.t0", "t0.t1", "t0.t2", "t0.out", "r1.h1", "r1.out", "t1.out",
              "down0", "down1", "down2", "down3", "mid", "up0", "up1", "up2", "up3"]
     runs = []
     for _ in range(3):
