@@ -117,6 +117,19 @@ int s2i_unet_forward(s2i_unet* u, const float* x, int B, int H, int W, float t, 
 int s2i_unet_tap(s2i_unet* u, int k, float** ptr, int* B, int* H, int* W, int* C);
 /* tap_grads[k]: NHWC fp32 device, shaped like tap k (NULL = no gradient); dx: NCHW fp32 device [B,C,H,W] */
 int s2i_unet_backward(s2i_unet* u, float* const* tap_grads, float* dx, void* cuda_stream);
+/* Injected sketch attention (modules/sketch_guided_attn.py:8-161, SatMixin / AttnModule; forward only).
+ * load_sat: host fp32 tensors under the reference's parameter names
+ *   "sketch_attn_<block path, '.' -> '_'>_transformer_blocks_0.{sketch_norm.{weight,bias}, sketch_attn.to_{q,k,v}.weight,
+ *    sketch_attn.to_out.0.{weight,bias}, sketch_conv.{weight,bias}}"  for each of the 16 transformer blocks.
+ * set_sat_feature: the sketch-encoder feature of one block (AttnModule.set_res_sample), NCHW fp32 device [B,C,H,W] with B =
+ *   the forward batch and (C, H*W) = the block's width and token count; block_path e.g. "down_blocks.0.attentions.1";
+ *   NULL removes it (the block then runs unmodified, sketch_guided_attn.py:120).  K / V are projected once here.
+ * set_sat_scale: AttnModule.set_scale for every block. */
+int s2i_unet_load_sat(s2i_unet* u, int n, const char* const* names, const float* const* host_ptrs, const int* ndims,
+                      const long long* shapes);
+int s2i_unet_set_sat_feature(s2i_unet* u, const char* block_path, const float* feature_nchw, int B, int C, int H, int W,
+                             void* cuda_stream);
+int s2i_unet_set_sat_scale(s2i_unet* u, float scale, void* cuda_stream);
 /* bisecting aid: keep named block outputs of the next forwards ("conv_in", "down0".., "mid", "up0"..) */
 int s2i_unet_debug(s2i_unet* u, int enable);
 int s2i_unet_debug_get(s2i_unet* u, const char* name, float** ptr, long long* ld, int* B, int* H, int* W, int* C);

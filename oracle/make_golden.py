@@ -45,8 +45,42 @@ def run_reference(name, steps, guidance_scale=7.5, seed=port.SAMPLE_SEED, guided
     return per_step, dt
 
 
+def run_reference_sat(name="tiny21", steps=4, guidance_scale=7.5, scale=0.7, seed=port.SAMPLE_SEED):
+    """Config 4: the reference's OWN SatMixin (modules/sketch_guided_attn.py, unmodified) injected into the shim UNet,
+    sampled with plain CFG + v-prediction DDIM (the reference's pipeline with sketch_image=None: pipeline.py:142-143)."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from modules.pipeline import AntiGradientPipeline
+    from modules.sketch_guided_attn import SatMixin
+
+    unet = port.make_unet(name)
+    sat = port.make_sat(unet, SatMixin)
+    lat, emb, _ = port.make_inputs(unet, seed)
+    res = port.make_res_samples(unet, 2)
+    sat.set_res_samples(res)
+    sat.set_scale(scale)
+    with torch.no_grad():
+        eps = unet(torch.cat([lat] * 2), torch.tensor(501), encoder_hidden_states=emb).sample
+    pipe = AntiGradientPipeline(unet=unet, scheduler=port.make_scheduler("v_prediction"))
+    pipe.set_prompt_embeds(emb)
+    from modules.latent_predictor import LatentEdgePredictor
+    pipe.setup_lgp(LatentEdgePredictor(port.lgp_input_dim(unet), 4, port.NUM_POS_LAYERS).half())   # required by :38, unused
+    per_step = {}
+    pipe("synthetic", num_inference_steps=steps, guidance_scale=guidance_scale, latents=lat.clone(), sketch_image=None,
+         output_type="np", callback=lambda i, t, l: per_step.__setitem__(int(i), l.detach().clone().float()))
+    return {"config": name, "steps": steps, "guidance_scale": guidance_scale, "sat_scale": scale, "eps_t501": eps,
+            "latents": per_step, "weight_seed": port.WEIGHT_SEED, "sat_seed": port.WEIGHT_SEED + 2, "sample_seed": seed,
+            "source": "reference modules/sketch_guided_attn.py (SatMixin) + modules/pipeline.py over oracle/diffusers_shim"}
+
+
 def main(argv):
     torch.set_num_threads(os.cpu_count())
+    if argv and argv[0] == "sat":
+        blob = run_reference_sat()
+        path = os.path.join(ROOT, "tests", "golden", "tiny21_sat_4step.pt")
+        torch.save(blob, path)
+        print("sat fixture ->", path, "final norm", blob["latents"][blob["steps"] - 1].norm().item())
+        return
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     pairs = list(zip(argv[0::2], argv[1::2]))

@@ -185,7 +185,9 @@ def guided_sample(unet, lgp, scheduler, text_emb, latents, target, num_steps=50,
 # --------------------------------------------------------------------------------------------------
 # Seeded synthetic models / inputs shared by the oracle, the tests and bench.py
 # --------------------------------------------------------------------------------------------------
-CONFIGS = {"sd15": SD15_CONFIG, "sd21": SD21_CONFIG, "tiny": TINY_CONFIG}
+# SD2.1-shaped small topology (linear projections, d_head = 64, upcast attention) for the injected-attention path
+TINY21_CONFIG = dict(TINY_CONFIG, attention_head_dim=(1, 2, 4, 4), use_linear_projection=True, upcast_attention=True)
+CONFIGS = {"sd15": SD15_CONFIG, "sd21": SD21_CONFIG, "tiny": TINY_CONFIG, "tiny21": TINY21_CONFIG}
 WEIGHT_SEED = 1138
 SAMPLE_SEED = 1139
 
@@ -227,3 +229,112 @@ def make_inputs(unet, seed=SAMPLE_SEED):
 
 def make_scheduler(prediction_type="epsilon"):
     return DDIMScheduler(prediction_type=prediction_type)
+
+
+# --------------------------------------------------------------------------------------------------
+# Injected sketch attention  (/root/reference/modules/sketch_guided_attn.py:8-161)
+# --------------------------------------------------------------------------------------------------
+class SatAttnOracle(nn.Module):
+    """AttnModule restated (sketch_guided_attn.py:46-161): same sub-module / parameter names; rebinding the wrapped
+    BasicTransformerBlock's forward like :74-79."""
+
+    def __init__(self, sat_name, base_layer):
+        super().__init__()
+        from diffusers.models.attention import CrossAttention
+        self.name = sat_name
+        attn1 = base_layer.attn1
+        dim = attn1.to_q.in_features
+        heads = attn1.heads
+        dim_head = attn1.to_q.out_features // heads
+        self.sketch_norm = nn.LayerNorm(dim)
+        self.sketch_attn = CrossAttention(query_dim=dim, heads=heads, dim_head=dim_head, dropout=0.0, bias=False,
+                                          upcast_attention=attn1.upcast_attention)
+        self.sketch_conv = nn.Conv1d(dim, dim, 1)
+        self.sketch_scale = 1.0
+        self.res_sample = None
+        outer = self
+
+        def forward(blk, hidden_states, encoder_hidden_states=None, timestep=None, attention_mask=None,
+                    cross_attention_kwargs=None, class_labels=None):
+            return outer.block_forward(blk, hidden_states, encoder_hidden_states, attention_mask)
+
+        base_layer.forward = forward.__get__(base_layer, type(base_layer))
+
+    def set_res_sample(self, res_sample):
+        b, c, h, w = res_sample.shape
+        self.res_sample = res_sample.permute(0, 2, 3, 1).reshape(b, h * w, c)          # "b c h w -> b (h w) c" (:82)
+
+    def set_scale(self, scale):
+        self.sketch_scale = scale
+
+    def block_forward(self, blk, hidden_states, encoder_hidden_states, attention_mask):
+        # :99-118 self-attention + residual
+        attn_output = blk.attn1(blk.norm1(hidden_states),
+                                encoder_hidden_states=encoder_hidden_states if blk.only_cross_attention else None,
+                                attention_mask=attention_mask)
+        hidden_states = attn_output + hidden_states
+        if self.res_sample is not None:
+            # :126-132 LayerNorm -> cross-attention to the sketch tokens -> slice (no-op) -> Conv1d 1x1 -> scale -> residual
+            a = self.sketch_attn(self.sketch_norm(hidden_states), encoder_hidden_states=self.res_sample)
+            a = a[:, :attn_output.shape[1], :attn_output.shape[2]].permute(0, 2, 1)
+            a = self.sketch_scale * self.sketch_conv(a)
+            hidden_states = a.permute(0, 2, 1) + hidden_states
+        # :134-159 text cross-attention and feed-forward
+        hidden_states = blk.attn2(blk.norm2(hidden_states), encoder_hidden_states=encoder_hidden_states,
+                                  attention_mask=attention_mask) + hidden_states
+        return blk.ff(blk.norm3(hidden_states)) + hidden_states
+
+
+class SatMixinOracle(nn.Module):
+    """SatMixin restated (sketch_guided_attn.py:8-44)."""
+
+    def __init__(self, unet):
+        super().__init__()
+        self.blocks = []
+        for name, module in unet.named_modules():
+            if module.__class__.__name__ == "BasicTransformerBlock":
+                blk = SatAttnOracle(("sketch_attn." + name).replace(".", "_"), module)
+                self.blocks.append(blk)
+        for blk in self.blocks:
+            self.add_module(blk.name, blk)
+
+    def set_res_samples(self, res_samples):
+        down_blocks, up_blocks = (), ()
+        mid_block = (res_samples[-1][-1],)
+        for mid_layers in res_samples:
+            if len(mid_layers) == 3:
+                down_blocks += (mid_layers[0], mid_layers[1])
+                up_blocks += (mid_layers[0], mid_layers[1], mid_layers[1])
+        total_blocks = down_blocks + up_blocks[::-1] + mid_block
+        for idx in range(len(self.blocks)):
+            self.blocks[idx].set_res_sample(total_blocks[idx])
+
+    def set_scale(self, scale):
+        for blk in self.blocks:
+            blk.set_scale(scale)
+
+
+def make_sat(unet, cls=SatMixinOracle, seed=WEIGHT_SEED + 2):
+    """Seeded SatMixin over `unet` (rebinds its transformer blocks' forward!).  cls: the port's restatement or the
+    reference's own class (same constructor)."""
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    sat = cls(unet)
+    torch.random.set_rng_state(g)
+    return sat
+
+
+def make_res_samples(unet, batch, seed=SAMPLE_SEED + 7, size=None):
+    """Synthetic SketchEncoder output (modules/sketch_encoder.py:93-98): one tuple of feature maps per down block --
+    (resnet/attn out) x layers_per_block (+ the downsampled map for all but the last block)."""
+    gen = torch.Generator().manual_seed(seed)
+    boc = unet.config.block_out_channels
+    L = size or unet.config.sample_size
+    out = []
+    for i, c in enumerate(boc):
+        maps = [torch.randn(batch, c, L, L, generator=gen) for _ in range(unet.config.layers_per_block)]
+        if i < len(boc) - 1:
+            L //= 2
+            maps.append(torch.randn(batch, c, L, L, generator=gen))
+        out.append(tuple(maps))
+    return out

@@ -75,6 +75,9 @@ def lib():
     h.s2i_unet_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, C.c_int, vp]
     h.s2i_unet_tap.argtypes = [vp, C.c_int, fp, ip, ip, ip, ip]
     h.s2i_unet_backward.argtypes = [vp, C.POINTER(vp), vp, vp]
+    h.s2i_unet_load_sat.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(vp), ip, C.POINTER(C.c_longlong)]
+    h.s2i_unet_set_sat_feature.argtypes = [vp, C.c_char_p, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    h.s2i_unet_set_sat_scale.argtypes = [vp, C.c_float, vp]
     h.s2i_unet_debug.argtypes = [vp, C.c_int]
     h.s2i_unet_debug_get.argtypes = [vp, C.c_char_p, fp, C.POINTER(C.c_longlong), ip, ip, ip, ip]
     h.s2i_unet_arena_bytes.argtypes = [vp]

@@ -127,6 +127,30 @@ int s2i_unet_backward(s2i_unet* u, float* const* tap_grads, float* dx, void* cud
     return u->impl->backward(tap_grads, dx, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int s2i_unet_load_sat(s2i_unet* u, int n, const char* const* names, const float* const* host_ptrs, const int* ndims,
+                      const long long* shapes) {
+    if (!u || !names || !host_ptrs || !ndims || !shapes) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_load_sat: null argument");
+    std::map<std::string, s2i::HostParam> params;
+    for (int i = 0; i < n; ++i) {
+        s2i::HostParam hp;
+        hp.data = host_ptrs[i];
+        for (int k = 0; k < ndims[i]; ++k) hp.shape.push_back((long)shapes[i * 4 + k]);
+        params[names[i]] = hp;
+    }
+    return u->impl->load_sat(params);
+}
+
+int s2i_unet_set_sat_feature(s2i_unet* u, const char* block_path, const float* feature_nchw, int B, int C, int H, int W,
+                             void* cuda_stream) {
+    if (!u || !block_path) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_set_sat_feature: null argument");
+    return u->impl->set_sat_feature(block_path, feature_nchw, B, C, H, W, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int s2i_unet_set_sat_scale(s2i_unet* u, float scale, void* cuda_stream) {
+    if (!u) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_set_sat_scale: null engine");
+    return u->impl->set_sat_scale(scale, static_cast<cudaStream_t>(cuda_stream));
+}
+
 int s2i_unet_debug(s2i_unet* u, int enable) {
     if (!u) return s2i::set_error(S2I_ERR_ARG, "null engine");
     u->impl->keep_debug = enable != 0;

@@ -52,6 +52,26 @@ __global__ void pack_conv_kernel(const float* __restrict__ src, int Co, int Ci, 
 
 inline long rup(long a, long b) { return (a + b - 1) / b * b; }
 
+// dst16 = fp16(scale * src32) (n elements); dstb = scale * srcb (nb elements)
+__global__ void scale_pack_kernel(const float* __restrict__ src, long n, float scale, __half* __restrict__ dst,
+                                  const float* __restrict__ srcb, int nb, float* __restrict__ dstb) {
+    const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long i = i0; i < n; i += (long)gridDim.x * blockDim.x) dst[i] = __float2half_rn(scale * src[i]);
+    for (long i = i0; i < nb; i += (long)gridDim.x * blockDim.x) dstb[i] = scale * srcb[i];
+}
+
+// NCHW fp32 -> token-major fp16 [B][H*W][C]
+__global__ void nchw_to_tokens16_kernel(const float* __restrict__ src, int B, int C, int HW, __half* __restrict__ dst) {
+    const long total = (long)B * HW * C;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        const long t = idx / C;
+        const int p = (int)(t % HW);
+        const int b = (int)(t / HW);
+        dst[idx] = __float2half_rn(src[((long)b * C + c) * HW + p]);
+    }
+}
+
 }  // namespace
 
 // Standalone helper (LGP): stage a host fp32 [N][K] matrix and pack fp16 forward [N][K] / transposed [K][N] copies.
@@ -222,6 +242,7 @@ int UNet::load(const std::map<std::string, HostParam>& params) {
     };
     auto load_tfm = [&](const std::string& pre, int C, int heads) -> bool {
         Transformer T;
+        T.path = pre;
         T.C = C;
         T.heads = heads;
         T.d = C / heads;
@@ -379,6 +400,105 @@ int UNet::load(const std::map<std::string, HostParam>& params) {
     rsave_.resize(res_.size());
     tsave_.resize(tfm_.size());
     loaded_ = true;
+    return 0;
+}
+
+// ================================================================================================== injected sketch attention
+int UNet::load_sat(const std::map<std::string, HostParam>& params) {
+    if (!loaded_) return set_error(S2I_ERR_STATE, "unet: load the UNet weights before the sketch-attention weights");
+    Loader L{params, owned_};
+    auto fail = [&](const std::string& what) {
+        if (L.staging) cudaFree(L.staging);
+        return set_error(S2I_ERR_ARG, "sketch attention load (%s): %s", what.c_str(), L.err.c_str());
+    };
+    for (auto& T : tfm_) {
+        std::string name = "sketch_attn_" + T.path + ".transformer_blocks.0";
+        for (char& ch : name)
+            if (ch == '.') ch = '_';
+        const int C = T.C;
+        SatBlock& S = T.sat;
+        if (!L.norm(name + ".sketch_norm", C, 1e-5f, S.ln)) return fail(name);
+        S.q.N = T.HP; S.q.K = C;
+        S.q.w = L.dmalloc<__half>((size_t)T.HP * C, true);
+        S.kv.N = 2 * T.HP; S.kv.K = C;
+        S.kv.w = L.dmalloc<__half>((size_t)2 * T.HP * C, true);
+        S.o.N = C; S.o.K = T.HP;
+        S.o.w = L.dmalloc<__half>((size_t)C * T.HP, true);
+        if (!S.q.w || !S.kv.w || !S.o.w) return fail(name);
+        if (!L.linear_into(name + ".sketch_attn.to_q.weight", C, C, T.d, T.dp, true, false, S.q.w, C, 0, nullptr, 0, 0, false) ||
+            !L.linear_into(name + ".sketch_attn.to_k.weight", C, C, T.d, T.dp, true, false, S.kv.w, C, 0, nullptr, 0, 0, false) ||
+            !L.linear_into(name + ".sketch_attn.to_v.weight", C, C, T.d, T.dp, true, false, S.kv.w, C, T.HP, nullptr, 0, 0, false) ||
+            !L.linear_into(name + ".sketch_attn.to_out.0.weight", C, C, T.d, T.dp, false, true, S.o.w, T.HP, 0, nullptr, 0, 0, false))
+            return fail(name);
+        S.o.b = L.vec(name + ".sketch_attn.to_out.0.bias", C);
+        S.conv_w32 = L.vec(name + ".sketch_conv.weight", (size_t)C * C);     // [C][C][1]
+        S.conv_b32 = L.vec(name + ".sketch_conv.bias", C);
+        S.conv.N = C; S.conv.K = C;
+        S.conv.w = L.dmalloc<__half>((size_t)C * C);
+        S.conv.b = L.dmalloc<float>(C);
+        if (!S.o.b || !S.conv_w32 || !S.conv_b32 || !S.conv.w || !S.conv.b) return fail(name);
+        S.loaded = true;
+    }
+    if (L.staging) cudaFree(L.staging);
+    return set_sat_scale(sat_scale_, nullptr);
+}
+
+int UNet::set_sat_scale(float scale, cudaStream_t st) {
+    sat_scale_ = scale;
+    for (auto& T : tfm_) {
+        SatBlock& S = T.sat;
+        if (!S.loaded) continue;
+        scale_pack_kernel<<<256, 256, 0, st>>>(S.conv_w32, (long)T.C * T.C, scale, S.conv.w, S.conv_b32, T.C, S.conv.b);
+    }
+    S2I_CUDA(cudaGetLastError());
+    g_prev_kernel = false;
+    return 0;
+}
+
+int UNet::set_sat_feature(const char* block_path, const float* nchw, int B, int C, int H, int W, cudaStream_t st) {
+    Transformer* T = nullptr;
+    for (auto& t : tfm_)
+        if (t.path == block_path) T = &t;
+    if (!T) return set_error(S2I_ERR_ARG, "sketch attention: no transformer block at '%s'", block_path);
+    SatBlock& S = T->sat;
+    if (!nchw) {
+        S.fB = S.fN = 0;
+        return 0;
+    }
+    if (!S.loaded) return set_error(S2I_ERR_STATE, "sketch attention: weights not loaded");
+    if (C != T->C) return set_error(S2I_ERR_ARG, "sketch attention: block %s has %d channels, feature has %d", block_path, T->C, C);
+    const int N = H * W;
+    const size_t need = (size_t)B * N * 2 * T->HP * sizeof(__half);
+    if (need > S.kv_cap) {
+        if (S.kv16) cudaFree(S.kv16);
+        S.kv16 = nullptr;
+        S.kv_cap = 0;
+        void* q = nullptr;
+        if (cudaMalloc(&q, need) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(S2I_ERR_OOM, "sketch attention: cannot allocate the K/V cache");
+        }
+        ++g_alloc_gen;
+        S.kv16 = static_cast<__half*>(q);
+        S.kv_cap = need;
+    }
+    // tokens "b c h w -> b (h w) c" (sketch_guided_attn.py:82) in fp16, then K | V = tokens [to_k | to_v]^T once per feature
+    __half* tok = nullptr;
+    S2I_CUDA(cudaMalloc(reinterpret_cast<void**>(&tok), (size_t)B * N * C * sizeof(__half)));
+    nchw_to_tokens16_kernel<<<1024, 256, 0, st>>>(nchw, B, C, N, tok);
+    g_prev_kernel = false;
+    GemmDesc g;
+    g.tag = "gemm_linear";
+    g.A = tok; g.aC = C; g.aW = B * N; g.a_sw = C;
+    g.B = S.kv.w; g.bI = C; g.bR = 2 * T->HP; g.b_sr = C;
+    g.N = 2 * T->HP; g.Kc = C;
+    g.out16 = S.kv16; g.ld16 = 2 * T->HP;
+    int rc = gemm_launch(g, st);
+    cudaStreamSynchronize(st);
+    cudaFree(tok);
+    if (rc != 0) return rc;
+    S.fB = B;
+    S.fN = N;
     return 0;
 }
 
@@ -675,6 +795,29 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     S2I_TRY(attention(T, sv.qkv, 0, sv.qkv, T.HP, 2L * T.HP, HW, sv.P1, sv.o1, need_bwd, &sv.lse1));
     sv.t1 = new32(B, H, W, C);
     S2I_TRY(gemm(sv.o1, false, 1, T.o1.w, T.HP, C, T.HP, T.o1.b, nullptr, &sv.t0, &sv.t1, nullptr));
+    // --- injected sketch attention (sketch_guided_attn.py:120-132), when a feature is set for this block
+    if (T.sat.loaded && T.sat.fN > 0) {
+        const SatBlock& S = T.sat;
+        if (save_) return set_error(S2I_ERR_STATE, "sketch attention has no backward (the reference runs it under no_grad)");
+        if (S.fB != B || S.fN != HW)
+            return set_error(S2I_ERR_ARG, "sketch attention: block %s expects a [%d, %d, %d x %d tokens] feature, has [%d, %d tokens]",
+                             T.path.c_str(), B, C, H, W, S.fB, S.fN);
+        H16 ls = new16(B, H, W, C);
+        float* lst = dalloc<float>(rows * 2);
+        RUN(ln_fwd(sv.t1.p, sv.t1.ld, rows, C, S.ln.g, S.ln.b, S.ln.eps, ls.p, ls.ld, lst, st_));
+        H16 qs = new16(B, H, W, T.HP);
+        S2I_TRY(gemm(ls, false, 1, S.q.w, C, T.HP, C, nullptr, nullptr, nullptr, nullptr, &qs));
+        H16 kvs;
+        kvs.p = S.kv16; kvs.B = B; kvs.H = 1; kvs.W = HW; kvs.C = 2 * T.HP; kvs.ld = 2 * T.HP;
+        H16 Ps, os;
+        float* lse_s = nullptr;
+        S2I_TRY(attention(T, qs, 0, kvs, 0, T.HP, HW, Ps, os, false, &lse_s));
+        H16 u = new16(B, H, W, C);
+        S2I_TRY(gemm(os, false, 1, S.o.w, T.HP, C, T.HP, S.o.b, nullptr, nullptr, nullptr, &u));
+        F32 t1s = new32(B, H, W, C);
+        S2I_TRY(gemm(u, false, 1, S.conv.w, C, C, C, S.conv.b, nullptr, &sv.t1, &t1s, nullptr));
+        sv.t1 = t1s;
+    }
     // --- cross attention (K/V from the text context)
     H16 l16b = new16(B, H, W, C);
     sv.l2 = dalloc<float>(rows * 2);

@@ -68,7 +68,24 @@ struct ResBlock {
     int temb_off = 0;  // offset of this block's time_emb_proj slice in the fused projection
     int Cin = 0, Cout = 0;
 };
+// Injected sketch attention of one transformer block (reference: AttnModule, modules/sketch_guided_attn.py:46-132):
+// after the self-attention residual,  h += scale * Conv1d_1x1( to_out( softmax(Q K^T / sqrt(d)) V ) ),
+// Q = to_q(LayerNorm(h)), K / V = to_k / to_v of the sketch-encoder feature tokens of this block.
+struct SatBlock {
+    bool loaded = false;
+    Norm ln;                   // sketch_norm
+    Lin q, kv, o;              // to_q [HP][C]; to_k | to_v fused [2*HP][C]; to_out.0 [C][HP] + bias
+    Lin conv;                  // sketch_conv as a Linear [C][C] + bias, multiplied by `scale` (fp16 weight, fp32 bias)
+    float* conv_w32 = nullptr; // unscaled masters
+    float* conv_b32 = nullptr;
+    __half* kv16 = nullptr;    // cached K | V projections of the current feature tokens [B][N][2*HP]
+    size_t kv_cap = 0;
+    int fB = 0, fN = 0;        // batch / tokens of the cached feature (0 = no feature set: block runs unmodified)
+};
+
 struct Transformer {
+    std::string path;          // diffusers module path, e.g. "down_blocks.0.attentions.1"
+    SatBlock sat;
     Norm gn, ln1, ln2, ln3;
     Lin proj_in, proj_out;
     Lin qkv;   // fused self-attention q|k|v, head-padded: [3*HP][C]
@@ -130,6 +147,13 @@ class UNet {
     // dx[B,4,H,W] (NCHW fp32) = sum_k J_k^T tap_grad[k]; tap_grad[k] is NHWC fp32 shaped like tap(k).
     int backward(float* const tap_grads[9], float* dx_nchw, cudaStream_t st);
 
+    // Injected sketch attention (SatMixin): weights under the reference's names
+    // "sketch_attn_<block path with '.' -> '_'>_transformer_blocks_0.{sketch_norm,sketch_attn.to_q,...,sketch_conv}.*",
+    // one feature map (NCHW fp32 [B,C,H,W], B = the forward's batch) per transformer block, and the residual scale.
+    int load_sat(const std::map<std::string, HostParam>& params);
+    int set_sat_feature(const char* block_path, const float* nchw, int B, int C, int H, int W, cudaStream_t st);
+    int set_sat_scale(float scale, cudaStream_t st);
+
     // The 9 taps of the last forward (NHWC fp32), hook order of latent_predictor.py:63-80.
     F32 taps[9];
     // Named intermediates of the last forward (debugging / parity bisecting).
@@ -173,6 +197,7 @@ class UNet {
     long arena_key_ = -1;
     bool have_saved_ = false;
     bool time_ready_ = false;
+    float sat_scale_ = 1.f;
 
     int run_forward(const float* x_nchw, float t, float* eps_nchw);
     int run_backward(float* const tap_grads[9], float* dx_nchw);

@@ -99,3 +99,21 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), f"{fn} references the oracle"
+
+
+def test_satmixin_state_dict_contract():
+    """Same sub-module names, order (down, up, mid) and parameter names/shapes as the reference's SatMixin
+    (sketch_guided_attn.py:14-27, :62-72), so its checkpoints load into the drop-in unchanged."""
+    from types import SimpleNamespace
+    from oracle import port
+    from sketch2img_b200.sketch_guided_attn import SatMixin, transformer_block_paths
+    o_unet = port.make_unet("tiny21")
+    o_sat = port.make_sat(o_unet)
+    fake = SimpleNamespace(config=o_unet.config, engine=None)
+    sat = SatMixin(fake)
+    assert len(sat.blocks) == 16 and [b.name for b in sat.blocks] == [b.name for b in o_sat.blocks]
+    want = {k: tuple(v.shape) for k, v in o_sat.state_dict().items()}
+    got = {k: tuple(v.shape) for k, v in sat.state_dict().items()}
+    assert got == want
+    sat.load_state_dict(o_sat.state_dict())
+    assert transformer_block_paths(fake)[6] == "up_blocks.1.attentions.0" and transformer_block_paths(fake)[-1] == "mid_block.attentions.0"

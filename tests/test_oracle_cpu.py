@@ -65,3 +65,49 @@ def test_reference_quirks_restated():
     assert sch.timesteps[:2].tolist() == [981, 961] and sch.timesteps[-1].item() == 1
     assert abs(sch.alphas_cumprod[981].item() - 0.0057755) < 1e-6
     assert sum(1 for i in range(50) if i <= 0.5 * 50) == 26
+
+
+# ------------------------------------------------------------------------------------------------ injected sketch attention
+def _port_sat_run(steps=4):
+    from oracle import port
+    unet = port.make_unet("tiny21")
+    sat = port.make_sat(unet)
+    lat, emb, _ = port.make_inputs(unet)
+    sat.set_res_samples(port.make_res_samples(unet, 2))
+    sat.set_scale(0.7)
+    with torch.no_grad():
+        eps = unet(torch.cat([lat] * 2), torch.tensor(501), encoder_hidden_states=emb).sample
+    got = {}
+    port.guided_sample(unet, None, port.make_scheduler("v_prediction"), emb, lat.clone(), None, num_steps=steps,
+                       callback=lambda i, t, l: got.__setitem__(int(i), l.detach().clone()))
+    return eps, got, sat
+
+
+def test_port_sat_matches_golden():
+    """oracle/port.py's SatMixin restatement + plain CFG / v-prediction DDIM reproduce the fixture made by the reference's
+    own sketch_guided_attn.py + pipeline.py bit for bit."""
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    gold = torch.load(os.path.join(GOLD, "tiny21_sat_4step.pt"))
+    eps, got, sat = _port_sat_run(gold["steps"])
+    assert torch.equal(eps, gold["eps_t501"])
+    for i, ref in gold["latents"].items():
+        assert torch.equal(got[i], ref), f"step {i}"
+    assert len(sat.blocks) == 16 and sat.blocks[6].name == "sketch_attn_up_blocks_1_attentions_0_transformer_blocks_0"
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/modules"), reason="reference sources only exist in the authoring container")
+def test_reference_satmixin_over_shim_equals_port():
+    from oracle import port
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    from modules.sketch_guided_attn import SatMixin
+    unet = port.make_unet("tiny21")
+    sat = port.make_sat(unet, SatMixin)
+    lat, emb, _ = port.make_inputs(unet)
+    sat.set_res_samples(port.make_res_samples(unet, 2))
+    sat.set_scale(0.7)
+    with torch.no_grad():
+        eps_ref = unet(torch.cat([lat] * 2), torch.tensor(501), encoder_hidden_states=emb).sample
+    eps, _, sat_port = _port_sat_run(1)
+    assert torch.equal(eps, eps_ref)
+    assert list(sat.state_dict().keys()) == list(sat_port.state_dict().keys())
