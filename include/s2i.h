@@ -56,6 +56,9 @@ int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream);
 /* Bisecting / A-B switch (no reference counterpart): 1 (default) = eligible GEMMs run gemm_tma_kernel (residual tile in,
  * result tiles out through cp.async.bulk.tensor), 0 = every GEMM runs gemm_tc_kernel (per-thread epilogue). */
 int s2i_gemm_set_tma_epilogue(int on);
+/* Tools / tests: 2 forces gemm_tma_kernel's two-sub-tile form (256 x BN per CTA: two A tiles share each B tile, two TMEM
+ * accumulators) wherever it is legal, 1 forbids it, 0 (default) lets the cost model choose. */
+int s2i_gemm_force_msub(int msub);
 /* Debugging: device buffer of [ctas][16] uint64 that gemm_tma_kernel fills with %globaltimer stamps of its phases
  * (entry, setup done, loads issued, MMAs issued, epilogue start, accumulator ready, residual ready, chunks done, stores
  * read, exit); NULL switches it off. */

@@ -26,6 +26,11 @@ int s2i_gemm_set_tma_epilogue(int on) {
     return 0;
 }
 
+int s2i_gemm_force_msub(int msub) {
+    s2i::gemm_force_msub(msub);
+    return 0;
+}
+
 int s2i_gemm_set_trace(void* device_buf) {
     s2i::gemm_set_trace(static_cast<unsigned long long*>(device_buf));
     return 0;

@@ -55,6 +55,8 @@ struct __align__(64) GemmParams {
     CUtensorMap mapO16;      // fp16 output, box (32, tw, th, tb), 64B swizzle
     int has_res, has_o32, has_o16;
     int split_add;           // split-K by fp32 reduce-add into a zeroed output (split 0 carries bias + residual)
+    int msub;                // M sub-tiles per CTA (1 or 2): two 128-row A tiles share every B tile (two TMEM accumulators)
+    int tiles_m;             // number of 128-row M tiles of the problem
     unsigned long long* trace;   // optional [ctas][16] %globaltimer stamps of the kernel's phases (tools/gemm_trace.py)
 };
 
@@ -83,24 +85,34 @@ __device__ __forceinline__ uint16_t to_half_bits(float v, int bf16) {
 
 struct TileCtx {
     int x0, y0, b0, m0, n0, z, zb, zhd, split, it_begin, it_end;
+    int x1, y1, b1;          // second M sub-tile (msub == 2)
+    int mt0;                 // index of the first M tile of this CTA
 };
+
+__device__ __forceinline__ void tile_xyb(const GemmParams& p, int mt, int& x0, int& y0, int& b0) {
+    const int tx = mt % p.tiles_x;
+    const int ty = (mt / p.tiles_x) % p.tiles_y;
+    const int tbi = mt / (p.tiles_x * p.tiles_y);
+    x0 = tx * p.tw;
+    y0 = ty * p.th;
+    b0 = tbi * p.tb;
+}
 
 __device__ __forceinline__ TileCtx tile_ctx(const GemmParams& p) {
     TileCtx t;
-    const int mt = blockIdx.x;
+    const int msub = p.msub > 1 ? p.msub : 1;
+    const int mt = blockIdx.x * msub;
+    t.mt0 = mt;
     t.n0 = blockIdx.y * p.BN;
     t.z = blockIdx.z / p.splits;
     t.split = blockIdx.z - t.z * p.splits;
     t.zb = t.z / p.zh;
     t.zhd = t.z - t.zb * p.zh;
     t.x0 = t.y0 = t.b0 = t.m0 = 0;
+    t.x1 = t.y1 = t.b1 = 0;
     if (!p.a_mn) {
-        const int tx = mt % p.tiles_x;
-        const int ty = (mt / p.tiles_x) % p.tiles_y;
-        const int tbi = mt / (p.tiles_x * p.tiles_y);
-        t.x0 = tx * p.tw;
-        t.y0 = ty * p.th;
-        t.b0 = tbi * p.tb;
+        tile_xyb(p, mt, t.x0, t.y0, t.b0);
+        if (msub > 1) tile_xyb(p, mt + 1, t.x1, t.y1, t.b1);
     } else {
         t.m0 = mt * kBlockM;
     }
@@ -125,7 +137,7 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx
         ptx::mbar_wait(&empty[stage], phase ^ 1);
         ptx::mbar_expect_tx(&full[stage], p.tx_bytes);
         uint8_t* sa = smem + stage * stage_bytes;
-        uint8_t* sb = sa + kAStageBytes;
+        uint8_t* sb = sa + (p.msub > 1 ? 2 : 1) * kAStageBytes;
         if (!p.a_mn) {
             const int tap = it / p.k_chunks;
             const int kc = it - tap * p.k_chunks;
@@ -135,6 +147,9 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx
                 dx = tap % 3 - 1;
             }
             ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + kc * kBlockK, t.x0 + dx, t.y0 + dy, t.b0 + a_bz);
+            if (p.msub > 1)
+                ptx::tma_load_4d(sa + kAStageBytes, &p.mapA, &full[stage], a_inner + kc * kBlockK, t.x1 + dx, t.y1 + dy,
+                                 t.b1 + a_bz);
         } else {
             ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + t.m0, it * kBlockK, 0, a_bz);
             ptx::tma_load_4d(sa + kChunkBytes, &p.mapA, &full[stage], a_inner + t.m0 + 64, it * kBlockK, 0, a_bz);
@@ -163,13 +178,17 @@ __device__ __forceinline__ void mma_loop(const GemmParams& p, const TileCtx& t, 
         ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
-        const uint32_t sb = sa + kAStageBytes;
+        const uint32_t sb = sa + (p.msub > 1 ? 2u : 1u) * kAStageBytes;
         // The last K chunk of a tap may be partial: head-sliced operands must not read past Kc.
         const int ksteps = ((it + 1) % p.k_chunks == 0) ? p.k_last_steps : kBlockK / 16;
         for (int k = 0; k < ksteps; ++k) {
             const uint64_t adesc = ptx::make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024u);
             const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024u);
             ptx::umma_f16(tmem_base, adesc, bdesc, p.idesc, (li | k) != 0 ? 1u : 0u);
+            if (p.msub > 1) {     // second 128-row sub-tile against the same B tile -> second accumulator
+                const uint64_t adesc1 = ptx::make_smem_desc_sw128(sa + kAStageBytes + k * a_kstep, a_lbo, 1024u);
+                ptx::umma_f16(tmem_base + (uint32_t)p.BN, adesc1, bdesc, p.idesc, (li | k) != 0 ? 1u : 0u);
+            }
         }
         ptx::umma_commit(&empty[stage]);   // frees the smem stage once these MMAs have read it
     }
@@ -191,7 +210,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_stage_bytes = ((p.BN + 63) >> 6) * kChunkBytes;
-    const int stage_bytes = kAStageBytes + b_stage_bytes;
+    const int msub = p.msub > 1 ? 2 : 1;
+    const int stage_bytes = msub * kAStageBytes + b_stage_bytes;
     const int nch = p.BN >> 5;
     const int use32 = p.has_res | p.has_o32;
     int pipe_bytes = p.stages * stage_bytes;
@@ -281,52 +301,71 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
         const uint32_t sw128 = (uint32_t)(r & 7);
         const uint32_t sw64 = (uint32_t)((r >> 1) & 3);
         uint8_t* base16 = smem + (use32 ? nch * kChunk32Bytes : 0);
-        for (int c = 0; c < nch; ++c) {
-            if (t.n0 + c * 32 >= p.N) break;
-            uint32_t raw[32];
-            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
-            if (add_res) ptx::mbar_wait(&r_full[c], 0);
-            ptx::tmem_ld_wait();
-            if (e == 0 && c == 0) stamp(p, 6);
-            uint8_t* row32 = smem + c * kChunk32Bytes + r * 128;
-            uint32_t hp[16];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + u * 4);
-                float4 v = make_float4(__uint_as_float(raw[4 * u]) + b4.x, __uint_as_float(raw[4 * u + 1]) + b4.y,
-                                       __uint_as_float(raw[4 * u + 2]) + b4.z, __uint_as_float(raw[4 * u + 3]) + b4.w);
-                float4* slot = reinterpret_cast<float4*>(row32 + ((u ^ sw128) << 4));
-                if (add_res) {
-                    const float4 x = *slot;
-                    v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+        for (int sub = 0; sub < msub; ++sub) {
+            if (t.mt0 + sub >= p.tiles_m) break;          // odd tile count: the last CTA has one sub-tile
+            const int xs = sub ? t.x1 : t.x0, ys = sub ? t.y1 : t.y0, bs = sub ? t.b1 : t.b0;
+            if (sub > 0) {
+                // the staging buffers are reused: the first sub-tile's stores must have read them; its residual tile
+                // is then loaded over them by this thread (second phase of the r_full barriers)
+                if (e == 0) {
+                    ptx::tma_store_wait_read0();
+                    if (add_res) {
+                        for (int c = 0; c < nch; ++c) {
+                            if (t.n0 + c * 32 >= p.N) break;
+                            ptx::mbar_expect_tx(&r_full[c], (uint32_t)(p.tw * p.th * p.tb * 128));
+                            ptx::tma_load_4d(smem + c * kChunk32Bytes, &p.mapRes, &r_full[c], t.n0 + c * 32, xs, ys, bs);
+                        }
+                    }
                 }
-                if (p.has_o32) *slot = v;
+                ptx::named_bar_sync(1, 128);
+            }
+            for (int c = 0; c < nch; ++c) {
+                if (t.n0 + c * 32 >= p.N) break;
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * p.BN + c * 32), raw);
+                if (add_res) ptx::mbar_wait(&r_full[c], (uint32_t)(sub & 1));
+                ptx::tmem_ld_wait();
+                if (e == 0 && c == 0) stamp(p, 6);
+                uint8_t* row32 = smem + c * kChunk32Bytes + r * 128;
+                uint32_t hp[16];
+    #pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + u * 4);
+                    float4 v = make_float4(__uint_as_float(raw[4 * u]) + b4.x, __uint_as_float(raw[4 * u + 1]) + b4.y,
+                                           __uint_as_float(raw[4 * u + 2]) + b4.z, __uint_as_float(raw[4 * u + 3]) + b4.w);
+                    float4* slot = reinterpret_cast<float4*>(row32 + ((u ^ sw128) << 4));
+                    if (add_res) {
+                        const float4 x = *slot;
+                        v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+                    }
+                    if (p.has_o32) *slot = v;
+                    if (p.has_o16) {
+                        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                        hp[2 * u] = *reinterpret_cast<const uint32_t*>(&h0);
+                        hp[2 * u + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+                    }
+                }
                 if (p.has_o16) {
-                    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-                    hp[2 * u] = *reinterpret_cast<const uint32_t*>(&h0);
-                    hp[2 * u + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+                    uint8_t* row16 = base16 + c * kChunk16Bytes + r * 64;
+    #pragma unroll
+                    for (int w = 0; w < 4; ++w)
+                        *reinterpret_cast<uint4*>(row16 + ((w ^ sw64) << 4)) =
+                            make_uint4(hp[4 * w], hp[4 * w + 1], hp[4 * w + 2], hp[4 * w + 3]);
                 }
-            }
-            if (p.has_o16) {
-                uint8_t* row16 = base16 + c * kChunk16Bytes + r * 64;
-#pragma unroll
-                for (int w = 0; w < 4; ++w)
-                    *reinterpret_cast<uint4*>(row16 + ((w ^ sw64) << 4)) =
-                        make_uint4(hp[4 * w], hp[4 * w + 1], hp[4 * w + 2], hp[4 * w + 3]);
-            }
-            // the chunk's bulk store overlaps the next chunk's arithmetic (the copy engine, like the loads, runs at the
-            // chip's ~10 TB/s L2 rate: a late burst of all stores would only lengthen the tail)
-            ptx::fence_proxy_async();              // generic-proxy smem writes -> visible to the bulk-copy engine
-            ptx::named_bar_sync(1, 128);
-            if (e == 0) {
-                const int nc = t.n0 + c * 32;
-                if (p.has_o32) {
-                    if (p.split_add) ptx::tma_reduce_add_4d(&p.mapO32, smem + c * kChunk32Bytes, nc, t.x0, t.y0, t.b0);
-                    else ptx::tma_store_4d(&p.mapO32, smem + c * kChunk32Bytes, nc, t.x0, t.y0, t.b0);
+                // the chunk's bulk store overlaps the next chunk's arithmetic (the copy engine, like the loads, runs at the
+                // chip's ~10 TB/s L2 rate: a late burst of all stores would only lengthen the tail)
+                ptx::fence_proxy_async();              // generic-proxy smem writes -> visible to the bulk-copy engine
+                ptx::named_bar_sync(1, 128);
+                if (e == 0) {
+                    const int nc = t.n0 + c * 32;
+                    if (p.has_o32) {
+                        if (p.split_add) ptx::tma_reduce_add_4d(&p.mapO32, smem + c * kChunk32Bytes, nc, xs, ys, bs);
+                        else ptx::tma_store_4d(&p.mapO32, smem + c * kChunk32Bytes, nc, xs, ys, bs);
+                    }
+                    if (p.has_o16) ptx::tma_store_4d(&p.mapO16, base16 + c * kChunk16Bytes, nc, xs, ys, bs);
+                    ptx::tma_store_commit();
+                    if (c < 3) stamp(p, 13 + c);
                 }
-                if (p.has_o16) ptx::tma_store_4d(&p.mapO16, base16 + c * kChunk16Bytes, nc, t.x0, t.y0, t.b0);
-                ptx::tma_store_commit();
-                if (c < 3) stamp(p, 13 + c);
             }
         }
         if (e == 0) {
@@ -648,6 +687,7 @@ int pow2_floor(int v) {
 // CTAs when shared memory allows) matters as much as the inner-loop rate.
 struct TileChoice {
     int BN, splits;
+    int msub = 1;
 };
 
 double model_cycles(int N, long tiles_m, int Z, int iters, int BN, int splits) {
@@ -695,30 +735,38 @@ TileChoice choose_tiles(int N, long tiles_m, int Z, int iters, bool allow_split)
 // Same pacing model with this kernel's constants: prologue + first-load latency ~4.5 k cycles, ~450 cycles per
 // 32-column epilogue chunk (+ the residual tile's L2 round trip), operands arriving at ~48 B/clk per SM when every SM
 // pulls from L2.  Split-K partial tiles are reduce-added into the (zeroed) output by the bulk-copy engine.
-double model_cycles_tma(int N, long tiles_m, int iters, int BN, int splits, int epi) {
+double model_cycles_tma(int N, long tiles_m_all, int iters, int BN, int splits, int epi, int msub = 1) {
     const bool residual = (epi & 1) != 0;
+    const long tiles_m = ceil_div_l(tiles_m_all, msub);
     // Calibrated on B200 with tools/gemm_bench.py (profiles/r1_gemm_bench_v2.txt): every CTA pays ~9 k cycles of launch,
     // prologue, first-load and drain latency, so small problems want MANY short CTAs (two co-resident CTAs per SM hide
     // each other's latencies); operand tiles arrive from L2 at ~40 B/clk per SM when the whole chip pulls.
     const int tiles_n = ceil_div(N, BN);
     const long ctas = tiles_m * tiles_n * splits;
-    const int stage_bytes = kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
-    // two CTAs share an SM only if the pipeline (>= 2 stages) AND the epilogue staging that aliases it fit half of it
+    const int stage_bytes = msub * kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
+    // two CTAs share an SM only if the pipeline (>= 2 stages) AND the epilogue staging that aliases it fit half of it,
+    // and their accumulators fit the 512 TMEM columns together
     const int epi_bytes = (BN / 32) * (((epi & 2) ? 16384 : 0) + ((epi & 4) ? 8192 : 0));
-    const int occ = (2 * stage_bytes <= 100 * 1024 && epi_bytes <= 100 * 1024) ? 2 : 1;
+    const int occ = (2 * stage_bytes <= 100 * 1024 && epi_bytes <= 100 * 1024 && msub * BN <= 256) ? 2 : 1;
     const long slots = (long)kNumSMs * occ;
     const long waves = ceil_div_l(ctas, slots);
     const int it = ceil_div(iters, splits);
     const double resident = (double)(ctas <= kNumSMs ? 1 : occ);
-    const double mma = 2.0 * BN * resident;
+    const double mma = 2.0 * BN * resident * msub;
     // measured operand arrival: ~31 B/clk for a CTA alone on its SM, ~42 B/clk shared by two co-resident CTAs
-    const double tma = (double)(kAStageBytes + BN * 128) / (resident > 1.0 ? 21.0 : 31.0);
+    // (the chip-wide L2 rate: what matters is bytes per FLOP, hence the two-sub-tile form for K-heavy problems)
+    const double tma = (double)(msub * kAStageBytes + BN * 128) / (resident > 1.0 ? 21.0 : 31.0);
     const double per_iter = mma > tma ? mma : tma;
-    double fixed = 9000.0 + 350.0 * (BN / 32) + (residual ? 900.0 : 0.0);
+    double fixed = 9000.0 + msub * 350.0 * (BN / 32) + (residual ? 900.0 * msub : 0.0) + (msub - 1) * 500.0;
     double total = (double)waves * (it * per_iter + fixed);
     if (splits > 1) total += 4500.0;      // zero-fill node + reduce-add traffic
     return total;
 }
+
+bool g_allow_msub = [] {
+    const char* e = getenv("S2I_GEMM_MSUB");
+    return !(e && e[0] == '0');
+}();
 
 TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, int epi) {
     static const int cands[] = {256, 192, 160, 128, 96, 64, 32};
@@ -726,14 +774,17 @@ TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, in
     double best_c = 1e30;
     for (int c : cands) {
         if (c > N && c != 32) continue;
-        const long base = tiles_m * ceil_div(N, c);
-        for (int sp = 1; sp <= 32; sp *= 2) {
-            if (sp > 1 && (!allow_split || base * sp > 2 * kNumSMs + 64 || iters / sp < 2)) break;
-            if ((long)(sp - 1) * ceil_div(iters, sp) >= iters) continue;
-            const double cyc = model_cycles_tma(N, tiles_m, iters, c, sp, epi);
-            if (cyc < best_c) {
-                best_c = cyc;
-                best = TileChoice{c, sp};
+        for (int ms = 1; ms <= 2; ++ms) {
+            if (ms == 2 && (tiles_m < 2 || ms * c > 512 || !g_allow_msub)) break;
+            const long base = ceil_div_l(tiles_m, ms) * ceil_div(N, c);
+            for (int sp = 1; sp <= 32; sp *= 2) {
+                if (sp > 1 && (!allow_split || base * sp > 2 * kNumSMs + 64 || iters / sp < 2)) break;
+                if ((long)(sp - 1) * ceil_div(iters, sp) >= iters) continue;
+                const double cyc = model_cycles_tma(N, tiles_m, iters, c, sp, epi, ms);
+                if (cyc < best_c) {
+                    best_c = cyc;
+                    best = TileChoice{c, sp, ms};
+                }
             }
         }
     }
@@ -741,6 +792,7 @@ TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, in
 }
 
 unsigned long long* g_trace = nullptr;
+int g_force_msub = 0;      // tools / tests: 1 or 2 forces the M sub-tile count of gemm_tma_kernel, 0 = model's choice
 int g_tma_epi = -1;
 bool tma_epilogue_enabled() {
     if (g_tma_epi < 0) {
@@ -844,8 +896,8 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
         // fp16-only output of a K-heavy small problem: split K into an fp32 scratch tile matrix, then convert
         const int epi_s = (d.residual ? 1 : 0) | 2;
         const TileChoice ts = choose_tiles_tma(d.N, tiles_m, num_iters, true, epi_s);
-        if (ts.splits > 1 && model_cycles_tma(d.N, tiles_m, num_iters, ts.BN, ts.splits, epi_s) + 5000.0 <
-                                 model_cycles_tma(d.N, tiles_m, num_iters, tc.BN, 1, epi)) {
+        if (ts.splits > 1 && model_cycles_tma(d.N, tiles_m, num_iters, ts.BN, ts.splits, epi_s, ts.msub) + 5000.0 <
+                                 model_cycles_tma(d.N, tiles_m, num_iters, tc.BN, 1, epi, tc.msub)) {
             S2I_TRY(ensure_ws());
             tc = ts;
             via_scratch = can_split = true;
@@ -856,8 +908,12 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     }
     if (d.BN > 0) tc.BN = d.BN;
     if (d.splits > 0 && can_split) tc.splits = d.splits;
+    if (g_force_msub > 0) tc.msub = (g_force_msub == 2 && tiles_m >= 2 && 2 * tc.BN <= 512) ? 2 : 1;
     while (tc.splits > 1 && (long)(tc.splits - 1) * ceil_div(num_iters, tc.splits) >= num_iters) --tc.splits;
     const int BN = tc.BN;
+    const int msub = tc.msub;
+    p.msub = msub;
+    p.tiles_m = (int)tiles_m;
     p.BN = BN;
     p.splits = tc.splits;
     p.split_add = tc.splits > 1 ? 1 : 0;
@@ -867,14 +923,17 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     p.has_o16 = d.out16 ? 1 : 0;
     const int tiles_n = ceil_div(d.N, BN);
     p.tmem_cols = 32;
-    while (p.tmem_cols < BN) p.tmem_cols *= 2;
+    while (p.tmem_cols < msub * BN) p.tmem_cols *= 2;
 
-    const int stage_bytes = kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
+    const int stage_bytes = msub * kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
     const int nch = BN / 32;
     const size_t epi_bytes = (size_t)((p.has_res || p.has_o32) ? nch * kChunk32Bytes : 0) + (p.has_o16 ? nch * kChunk16Bytes : 0);
-    const long ctas = tiles_m * tiles_n * tc.splits;
+    const long grid_m = ceil_div_l(tiles_m, msub);
+    const long ctas = grid_m * tiles_n * tc.splits;
     const size_t tail = (size_t)(2 * 8 + 1 + kMaxChunks) * 8 + 16 + (size_t)BN * 4 + 1024 + 64;
-    const size_t budget = (ctas > kNumSMs ? 112u : 220u) * 1024u - tail;
+    // aim for two co-resident CTAs (<= 112 KB each) when more than one wave is coming and they can actually share an SM
+    const bool can_pair = 2 * (size_t)stage_bytes + tail <= 112u * 1024u && epi_bytes + tail <= 112u * 1024u && msub * BN <= 256;
+    const size_t budget = ((ctas > kNumSMs && can_pair) ? 112u : 220u) * 1024u - tail;
     int stages = (int)(budget / stage_bytes);
     if (stages < 2) stages = 2;
     if (stages > 8) stages = 8;
@@ -888,7 +947,7 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     p.a_c0 = d.a_c0; p.a_hoff = d.a_hoff; p.a_zmode = d.a_zmode;
     p.b_c0 = d.b_c0; p.b_hoff = d.b_hoff; p.b_zmode = d.b_zmode;
     p.idesc = ptx::make_idesc_f16(kBlockM, BN, d.bf16, 0, 0);
-    p.tx_bytes = (uint32_t)(p.tw * p.th * p.tb * kBlockK * 2) + (uint32_t)(BN * kBlockK * 2);
+    p.tx_bytes = (uint32_t)(msub * p.tw * p.th * p.tb * kBlockK * 2) + (uint32_t)(BN * kBlockK * 2);
     p.alpha = 1.f;
     p.bias = d.bias;
     p.rowvec = d.rowvec;
@@ -905,7 +964,7 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
         S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)tc.splits);
+    dim3 grid((unsigned)grid_m, (unsigned)tiles_n, (unsigned)tc.splits);
     p.trace = g_trace;
     S2I_LAUNCH((gemm_tma_kernel), grid, kThreads, smem_bytes, stream, p);
     const double m_rows = (double)d.aW * d.aH * d.aB;
@@ -930,6 +989,7 @@ long g_launches = 0;
 long gemm_launch_count() { return g_launches; }
 void gemm_set_tma_epilogue(int on) { g_tma_epi = on ? 1 : 0; }
 void gemm_set_trace(unsigned long long* buf) { g_trace = buf; }
+void gemm_force_msub(int msub) { g_force_msub = msub; }
 
 int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     if (!d.A || !d.B) return set_error(S2I_ERR_ARG, "gemm: null operand");

@@ -38,6 +38,9 @@ void gemm_set_tma_epilogue(int on);
 // Debugging: when set, gemm_tma_kernel stamps %globaltimer at its phase boundaries into buf[cta][16] (tools/gemm_trace.py).
 void gemm_set_trace(unsigned long long* buf);
 
+// Tools / tests: force one (1) or two (2) 128-row M sub-tiles per CTA in gemm_tma_kernel; 0 = the cost model decides.
+void gemm_force_msub(int msub);
+
 // Number of kernel launches issued through gemm_launch since process start (bench.py's gpu_launches).
 long gemm_launch_count();
 

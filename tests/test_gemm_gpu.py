@@ -265,3 +265,58 @@ def test_split_k_conv3x3(L, cuda, B, H, W, Cin, Cout, splits):
     torch.cuda.synchronize()
     ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double() + temb.double(), padding=1).permute(0, 2, 3, 1)
     assert rel(out32, ref) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K,res,o32,o16,splits", [
+    (8192, 320, 320, 1, 1, 0, 0), (300, 96, 200, 1, 1, 1, 0), (2048, 640, 2560, 1, 0, 1, 0), (512, 1280, 1280, 1, 1, 0, 4),
+    (8192, 1152, 320, 0, 0, 1, 0), (384, 256, 512, 0, 1, 0, 0), (1000, 512, 4096, 1, 1, 0, 2)])
+def test_two_subtile_linear(L, cuda, M, N, K, res, o32, o16, splits):
+    """gemm_tma_kernel with two 128-row A tiles per CTA sharing each B tile (two TMEM accumulators, staging reused between
+    the sub-tiles): ragged M (odd tile counts, partial last tile), residual reload in the second phase, split-K."""
+    if not L.tma_epilogue:
+        pytest.skip("two-sub-tile form belongs to the TMA-epilogue kernel")
+    g = torch.Generator(device="cpu").manual_seed(M + 5 * N + K)
+    a = torch.randn(M, K, generator=g).to(cuda).half()
+    w = (torch.randn(N, K, generator=g) * 0.05).to(cuda).half()
+    bias = torch.randn(N, generator=g).to(cuda)
+    r = torch.randn(M, N, generator=g).to(cuda)
+    ref = a.double() @ w.double().t() + bias.double() + (r.double() if res else 0.0)
+    L.lib().s2i_gemm_force_msub(2)
+    try:
+        out32 = torch.full((M, N), float("nan"), device=cuda)
+        out16 = torch.full((M, N), float("nan"), device=cuda, dtype=torch.float16)
+        d = L.GemmDesc(A=a.data_ptr(), aC=K, aW=M, a_sw=K, B=w.data_ptr(), bI=K, bR=N, b_sr=K, N=N, Kc=K, splits=splits,
+                       bias=bias.data_ptr(), residual=r.data_ptr() if res else None, res_ld=N,
+                       out32=out32.data_ptr() if o32 else None, ld32=N, out16=out16.data_ptr() if o16 else None, ld16=N)
+        L.gemm(d)
+        torch.cuda.synchronize()
+    finally:
+        L.lib().s2i_gemm_force_msub(0)
+    if o32:
+        assert rel(out32, ref) < 2e-3
+    if o16:
+        assert rel(out16.float(), ref) < 3e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 320, 320), (2, 16, 16, 1280, 1280), (3, 8, 8, 256, 64), (2, 24, 24, 64, 96)])
+def test_two_subtile_conv3x3(L, cuda, B, H, W, Cin, Cout):
+    if not L.tma_epilogue:
+        pytest.skip("two-sub-tile form belongs to the TMA-epilogue kernel")
+    g = torch.Generator(device="cpu").manual_seed(B * 19 + Cin + H)
+    x = torch.randn(B, H, W, Cin, generator=g).to(cuda).half()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * 0.02).to(cuda).half()
+    bias = torch.randn(Cout, generator=g).to(cuda)
+    r = torch.randn(B, H, W, Cout, generator=g).to(cuda)
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    out32 = torch.full((B, H, W, Cout), float("nan"), device=cuda)
+    L.lib().s2i_gemm_force_msub(2)
+    try:
+        d = L.GemmDesc(A=x.data_ptr(), aC=Cin, aW=W, aH=H, aB=B, a_sw=Cin, a_sh=Cin * W, a_sb=Cin * W * H, taps=9,
+                       B=wp.data_ptr(), bI=9 * Cin, bR=Cout, b_sr=9 * Cin, N=Cout, Kc=Cin, bias=bias.data_ptr(),
+                       residual=r.data_ptr(), res_ld=Cout, out32=out32.data_ptr(), ld32=Cout)
+        L.gemm(d)
+        torch.cuda.synchronize()
+    finally:
+        L.lib().s2i_gemm_force_msub(0)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1) + r.double()
+    assert rel(out32, ref) < 2e-3

@@ -87,22 +87,30 @@ def main():
         t0 = time_desc(kw)
         lib.s2i_gemm_set_tma_epilogue(1)
         t1 = time_desc(kw)
-        print(f"{name:28s} {gf:7.2f} {t0:13.1f} {t1:11.1f} {gf / t1:7.1f}", flush=True)
+        lib.s2i_gemm_force_msub(1)
+        t1a = time_desc(kw)
+        lib.s2i_gemm_force_msub(2)
+        t1b = time_desc(kw)
+        lib.s2i_gemm_force_msub(0)
+        print(f"{name:28s} {gf:7.2f} {t0:13.1f} {t1:11.1f} {gf / t1:7.1f}   msub1 {t1a:6.1f}  msub2 {t1b:6.1f}", flush=True)
         if sweep:
             best = []
-            for bn in (32, 64, 96, 128, 160, 192, 256):
-                if bn > N:
-                    continue
-                for sp in (-1, 2, 4, 8, 16):
-                    if sp > 1 and shape[8]:
+            for ms in (1, 2):
+                lib.s2i_gemm_force_msub(ms)
+                for bn in (64, 96, 128, 160, 192, 256):
+                    if bn > N:
                         continue
-                    try:
-                        t = time_desc(kw, reps=10, BN=bn, splits=sp)
-                    except L.S2IError:
-                        continue
-                    best.append((t, bn, sp))
+                    for sp in (-1, 2, 4, 8, 16, 32):
+                        if sp > 1 and shape[8]:
+                            continue
+                        try:
+                            t = time_desc(kw, reps=10, BN=bn, splits=sp)
+                        except L.S2IError:
+                            continue
+                        best.append((t, ms, bn, sp))
+            lib.s2i_gemm_force_msub(0)
             best.sort()
-            print("      best (us, BN, splits):", [(round(t, 1), bn, sp) for t, bn, sp in best[:4]], flush=True)
+            print("      best (us, msub, BN, splits):", [(round(t, 1), ms, bn, sp) for t, ms, bn, sp in best[:5]], flush=True)
         del keep
 
 
