@@ -19,6 +19,7 @@
 
 #include <cudaTypedefs.h>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -36,7 +37,7 @@ constexpr int kTileQ = 128;
 constexpr int kTileK = 64;               // keys per tile: one 64-row TMA box serves as K (K-major) and V (MN-major)
 constexpr int kChunk16 = 128 * 64 * 2;   // 16 KB: 128 rows x 64 fp16 (one swizzle-128B K-major chunk of Q or P)
 constexpr int kChunk8 = 64 * 64 * 2;     // 8 KB: 64 rows x 64 fp16 (one chunk of a K or V tile)
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kMaxS = 4;
 
 struct __align__(64) AttnParams {
@@ -243,17 +244,34 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_cons
             }
             const float mneg = -mref;
             uint32_t pk[kTileK / 2];
+            // The softmax warps are issue-bound (one warp per scheduler): keep the per-element work at FFMA + EX2 + half
+            // a pack + one add.  Padding columns only exist in the last tile; four independent partial row sums.
+            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+            if (kvalid >= kTileK) {
 #pragma unroll
-            for (int i = 0; i < kTileK; i += 2) {
-                float e0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, mneg));
-                float e1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, mneg));
-                if (i >= kvalid) e0 = 0.f;
-                if (i + 1 >= kvalid) e1 = 0.f;
-                const __half2 h2 = __floats2half2_rn(e0, e1);
-                const float2 back = __half22float2(h2);       // the row sum uses what the tensor core multiplies
-                l += back.x + back.y;
-                pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                for (int i = 0; i < kTileK; i += 4) {
+                    const float e0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, mneg));
+                    const float e1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, mneg));
+                    const float e2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), p.scale_log2, mneg));
+                    const float e3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), p.scale_log2, mneg));
+                    l0 += e0; l1 += e1; l2 += e2; l3 += e3;
+                    const __half2 ha = __floats2half2_rn(e0, e1), hb = __floats2half2_rn(e2, e3);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&ha);
+                    pk[(i >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&hb);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kTileK; i += 2) {
+                    float e0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, mneg));
+                    float e1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, mneg));
+                    if (i >= kvalid) e0 = 0.f;
+                    if (i + 1 >= kvalid) e1 = 0.f;
+                    l0 += e0; l1 += e1;
+                    const __half2 h2 = __floats2half2_rn(e0, e1);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
             }
+            l += (l0 + l1) + (l2 + l3);
             const int pb = j % p.pbufs;
             ptx::mbar_wait(&p_empty[pb], ((j / p.pbufs) & 1) ^ 1);    // the P V product that read this buffer is done
             // row r of the K-major swizzled tile: 16-byte unit u lives at r * 128 + ((u ^ (r & 7)) * 16)
@@ -314,28 +332,42 @@ int attn_fwd_launch(const AttnDesc& d, cudaStream_t stream) {
     p.out = d.out; p.ldo = d.ldo; p.lse = d.lse;
     p.idesc_s = ptx::make_idesc_f16(128, kTileK, 0, 0, 0);
     p.idesc_o = ptx::make_idesc_f16(128, (uint32_t)d.dp, 0, 0, 1);
-    p.tmem_cols = d.dp <= 128 ? 256 : 512;      // 256 columns let two CTAs share an SM
-
-    // shared memory: Q | P buffers | (K tile + V tile) stages | barriers.  Prefer a footprint that lets two CTAs share
-    // an SM (the kernel is exp- and latency-bound for SD's head dims: a second CTA fills the handshake bubbles).
+    // Two configurations.  Long key sequences (self-attention): ONE CTA per SM with a deep K/V ring -- a stage is only
+    // recycled after its P V product, a full load -> S -> softmax -> P V round trip (~4 k cycles) later, so keeping the
+    // softmax warps fed at ~600 cycles per tile takes 6+ stages -- and up to four score tiles in flight (512 TMEM columns).
+    // Short ones (cross-attention to 77 tokens): the small footprint that lets two CTAs share an SM.
     const int q_bytes = p.nkc * kChunk16, stage_bytes = 2 * p.nkc * kChunk8;
     const int overhead = 512 + 1024;     // barriers + alignment slack
     const int half_sm = 113 * 1024, full_sm = 226 * 1024;
+    const int T = (d.Nk + kTileK - 1) / kTileK;
+    static const int deep_mode = [] {
+        const char* e = getenv("S2I_ATTN_DEEP");
+        return e ? atoi(e) : 0;      // measured on B200: two co-resident shallow CTAs beat one deep CTA (212 vs 353 us at N=4096)
+    }();
     int pbufs = 0, stages = 0;
-    const int tries[4][2] = {{2, 3}, {2, 2}, {1, 2}, {0, 0}};
-    for (int i = 0; tries[i][0]; ++i) {
-        if (q_bytes + tries[i][0] * kChunk16 + tries[i][1] * stage_bytes + overhead <= half_sm) {
-            pbufs = tries[i][0];
-            stages = tries[i][1];
-            break;
+    if (deep_mode && T >= 8) {
+        pbufs = 2;
+        stages = (full_sm - overhead - q_bytes - pbufs * kChunk16) / stage_bytes;
+        if (stages > kMaxStages) stages = kMaxStages;
+        if (stages > T) stages = T;
+        p.tmem_cols = 512;
+    } else {
+        p.tmem_cols = d.dp <= 128 ? 256 : 512;      // 256 columns let two CTAs share an SM
+        const int tries[4][2] = {{2, 3}, {2, 2}, {1, 2}, {0, 0}};
+        for (int i = 0; tries[i][0]; ++i) {
+            if (q_bytes + tries[i][0] * kChunk16 + tries[i][1] * stage_bytes + overhead <= half_sm) {
+                pbufs = tries[i][0];
+                stages = tries[i][1];
+                break;
+            }
         }
     }
     if (!pbufs) {
         pbufs = 2;
         stages = (full_sm - overhead - q_bytes - pbufs * kChunk16) / stage_bytes;
         if (stages > kMaxStages) stages = kMaxStages;
-        if (stages < 2) return set_error(S2I_ERR_ARG, "attn_fwd: head dim %d does not fit shared memory", d.dp);
     }
+    if (stages < 2) return set_error(S2I_ERR_ARG, "attn_fwd: head dim %d does not fit shared memory", d.dp);
     p.stages = stages;
     p.pbufs = pbufs;
     p.nS = (p.tmem_cols - d.dp) / 64;

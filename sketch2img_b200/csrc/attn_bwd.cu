@@ -41,6 +41,7 @@ struct __align__(64) BwdParams {
     int Nrow, Ncol, heads, dp, nkc;
     int r1_c0, r2_c0, c1_c0, c2_c0;           // column of head 0 in each operand tensor
     int sbufs;                                // staging buffers per staged matrix (1 or 2)
+    int nT, tmem_cols;                        // tile-product buffers in TMEM (1 or 2) and the allocation that holds them
     uint32_t idesc_t, idesc_acc;
     float scale, scale_log2;
     const float* lse;                         // [B*heads][Nq]
@@ -56,7 +57,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) attn_bwd_kernel(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_constant__ BwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int r_bytes = p.nkc * kChunk16;          // one resident operand tile
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_kernel(const __grid_cons
     uint64_t* c_full = bars + 10;       // [kStages]
     uint64_t* c_empty = bars + 12;      // [kStages]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-    float* sStat = reinterpret_cast<float*>(bars + 16);   // mode 1: [2][2][64] per-column (lse*log2e, delta)
+    float* sStat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 16) + 15) & ~uintptr_t(15));   // mode 1: [2][2][64] (lse*log2e, delta)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_kernel(const __grid_cons
             ptx::fence_mbar_init();
         }
         __syncwarp();
-        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_kernel(const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();       // everything above is local setup; global memory of earlier kernels is touched only below
     pdl_launch();     // TMEM is held: dependents may become resident
-    const uint32_t tmem_acc0 = tmem_base + 256u;
+    const uint32_t tmem_acc0 = tmem_base + (uint32_t)p.nT * 128u;    // T1 buffers | T2 buffers | accumulators
     const uint32_t tmem_acc1 = tmem_acc0 + (uint32_t)p.dp;
 
     if (warp == 0) {
@@ -150,12 +151,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_kernel(const __grid_cons
             auto issue_T = [&](int g) {
                 const int stage = g % kStages;
                 ptx::mbar_wait(&c_full[stage], (g / kStages) & 1);
-                ptx::mbar_wait(&t_empty[g & 1], ((g >> 1) & 1) ^ 1);
+                const int tb = g % p.nT;
+                ptx::mbar_wait(&t_empty[tb], ((g / p.nT) & 1) ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t aC1 = ptx::smem_u32(sC + stage * stage_bytes);
                 const uint32_t aC2 = aC1 + (uint32_t)c_bytes;
-                const uint32_t t1 = tmem_base + (uint32_t)(g & 1) * 64u;
-                const uint32_t t2 = tmem_base + 128u + (uint32_t)(g & 1) * 64u;
+                const uint32_t t1 = tmem_base + (uint32_t)tb * 64u;
+                const uint32_t t2 = tmem_base + (uint32_t)p.nT * 64u + (uint32_t)tb * 64u;
                 for (int k = 0; k < nks; ++k) {
                     const uint32_t kq = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3) * 32u;
                     ptx::umma_f16(t1, ptx::make_smem_desc_sw128(aR1 + kq * kChunk16 + ks, 16u, 1024u),
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_kernel(const __grid_cons
                     ptx::umma_f16(t2, ptx::make_smem_desc_sw128(aR2 + kq * kChunk16 + ks, 16u, 1024u),
                                   ptx::make_smem_desc_sw128(aC2 + kq * kChunk8 + ks, 16u, 1024u), p.idesc_t, k != 0 ? 1u : 0u);
                 }
-                ptx::umma_commit(&t_full[g & 1]);
+                ptx::umma_commit(&t_full[tb]);
             };
             ptx::mbar_wait(r_full, 0);
             issue_T(0);
@@ -225,10 +227,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_kernel(const __grid_cons
                 st[e] = ok ? (e < 64 ? p.lse[idx] * kLog2e : p.delta[idx]) : 0.f;
                 ptx::named_bar_sync(1, 128);
             }
-            ptx::mbar_wait(&t_full[j & 1], (j >> 1) & 1);
+            const int tb = j % p.nT;
+            ptx::mbar_wait(&t_full[tb], (j / p.nT) & 1);
             ptx::tc_fence_after();
-            const uint32_t t1 = tmem_base + (uint32_t)(j & 1) * 64u + lane_addr;
-            const uint32_t t2 = t1 + 128u;
+            const uint32_t t1 = tmem_base + (uint32_t)tb * 64u + lane_addr;
+            const uint32_t t2 = t1 + (uint32_t)p.nT * 64u;
             const int nvalid = p.Ncol - col0;          // columns >= nvalid are padding
             const float* stl = sStat + (j & 1) * 128;
             const int sb = j % p.sbufs;
@@ -244,26 +247,40 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_kernel(const __grid_cons
                 if (c0 + 32 == kCols) {
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&t_empty[j & 1]);      // both tile products are in registers
+                    if (lane == 0) ptx::mbar_arrive(&t_empty[tb]);      // both tile products are in registers
                 }
                 uint32_t pk[16], dk[16];
+                // issue-bound loop (one warp per scheduler): 4 elements per iteration, column statistics (mode 1) fetched
+                // as two 128-bit shared loads, padding handled only in the last tile
+                const bool ragged = (c0 + 32) > nvalid;
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float l0 = lse_r, l1 = lse_r, d0 = delta_r, d1 = delta_r;
+                for (int i = 0; i < 32; i += 4) {
+                    float4 l4 = make_float4(lse_r, lse_r, lse_r, lse_r), d4 = make_float4(delta_r, delta_r, delta_r, delta_r);
                     if (p.mode == 1) {
-                        l0 = stl[c0 + i]; l1 = stl[c0 + i + 1];
-                        d0 = stl[64 + c0 + i]; d1 = stl[64 + c0 + i + 1];
+                        l4 = *reinterpret_cast<const float4*>(stl + c0 + i);
+                        d4 = *reinterpret_cast<const float4*>(stl + 64 + c0 + i);
                     }
-                    float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, -l0));
-                    float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -l1));
-                    if (c0 + i >= nvalid) p0 = 0.f;
-                    if (c0 + i + 1 >= nvalid) p1 = 0.f;
-                    const float g0 = p0 * (__uint_as_float(d[i]) - d0) * p.scale;
-                    const float g1 = p1 * (__uint_as_float(d[i + 1]) - d1) * p.scale;
-                    const __half2 ph = __floats2half2_rn(p0, p1);
-                    const __half2 gh = __floats2half2_rn(g0, g1);
-                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&ph);
-                    dk[i >> 1] = *reinterpret_cast<const uint32_t*>(&gh);
+                    float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, -l4.x));
+                    float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -l4.y));
+                    float p2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), p.scale_log2, -l4.z));
+                    float p3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), p.scale_log2, -l4.w));
+                    if (ragged) {
+                        if (c0 + i >= nvalid) p0 = 0.f;
+                        if (c0 + i + 1 >= nvalid) p1 = 0.f;
+                        if (c0 + i + 2 >= nvalid) p2 = 0.f;
+                        if (c0 + i + 3 >= nvalid) p3 = 0.f;
+                    }
+                    const float ps0 = p0 * p.scale, ps1 = p1 * p.scale, ps2 = p2 * p.scale, ps3 = p3 * p.scale;
+                    const float g0 = ps0 * (__uint_as_float(d[i]) - d4.x);
+                    const float g1 = ps1 * (__uint_as_float(d[i + 1]) - d4.y);
+                    const float g2 = ps2 * (__uint_as_float(d[i + 2]) - d4.z);
+                    const float g3 = ps3 * (__uint_as_float(d[i + 3]) - d4.w);
+                    const __half2 pa = __floats2half2_rn(p0, p1), pb = __floats2half2_rn(p2, p3);
+                    const __half2 ga = __floats2half2_rn(g0, g1), gb = __floats2half2_rn(g2, g3);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pa);
+                    pk[(i >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&pb);
+                    dk[i >> 1] = *reinterpret_cast<const uint32_t*>(&ga);
+                    dk[(i >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&gb);
                 }
                 const int u0 = c0 >> 3;      // first 16-byte unit of this half (8 fp16 per unit)
                 if (p.mode == 0) {
@@ -315,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_kernel(const __grid_cons
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // delta[z][i] = sum_c dO[b,i,h,c] * O[b,i,h,c]   (one warp per (z, i) row)
@@ -399,6 +416,12 @@ int attn_bwd_launch(const AttnBwdDesc& d, cudaStream_t stream) {
             p.out1 = d.dk; p.ld1 = d.lddkv; p.o1_c0 = d.dk_c0;
         }
         const int nstaged = mode ? 2 : 1;
+        // TMEM: double-buffered tile products need 256 + nacc*dp columns (512 allocation, one CTA per SM); single-buffered
+        // they fit 256 columns and two CTAs share the SM -- the softmax warps are issue-bound, so a second CTA's warps
+        // on every scheduler are worth more than overlapping this CTA's own tile products
+        const int nacc = mode ? 2 : 1;
+        p.nT = (128 + nacc * d.dp <= 256) ? 1 : 2;
+        p.tmem_cols = (p.nT * 128 + nacc * d.dp <= 256) ? 256 : 512;
         const int fixed = 2 * nkc * kChunk16 + kStages * 2 * nkc * kChunk8 + 2048 + 1024;   // operands + barriers/stats + slack
         p.sbufs = (fixed + 2 * nstaged * kChunk16 <= 227 * 1024) ? 2 : 1;
         // prefer two co-resident CTAs when a single staging buffer makes the footprint fit half an SM
