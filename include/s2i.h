@@ -188,6 +188,9 @@ int s2i_guidance_update(const float* x_old, float* x_new, const float* dx, int S
 typedef struct s2i_sampler s2i_sampler;
 int s2i_sampler_create(s2i_unet* u, s2i_lgp* l, s2i_sampler** out);
 void s2i_sampler_destroy(s2i_sampler* s);
+/* The sampler reuses the text context's cross-attention K/V projections from step to step.  Call this whenever the VALUES
+ * behind `ctx` change (a new prompt / image); a new ctx pointer or sample count is noticed by itself. */
+int s2i_sampler_context_changed(s2i_sampler* s);
 int s2i_sampler_step(s2i_sampler* s, float* latents, const float* noise, const float* ctx, const float* target, int S,
                      int L, float t, float guidance_scale, float sqrt_a_t, float sqrt_one_minus_a_t, float sqrt_a_prev,
                      float sqrt_one_minus_a_prev, int prediction, int guided, float sigma, float beta, int lgp_train,

@@ -96,6 +96,7 @@ def lib():
     h.s2i_cfg_ddim_step.argtypes = [vp, vp, C.c_int, C.c_int, f, f, f, f, f, C.c_int, vp, vp]
     h.s2i_guidance_update.argtypes = [vp, vp, vp, C.c_int, C.c_int, f, vp, vp]
     h.s2i_sampler_create.argtypes = [vp, vp, C.POINTER(vp)]
+    h.s2i_sampler_context_changed.argtypes = [vp]
     h.s2i_sampler_destroy.argtypes = [vp]
     h.s2i_sampler_destroy.restype = None
     h.s2i_sampler_step.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, f, f, f, f, f, f, C.c_int, C.c_int, f, f,

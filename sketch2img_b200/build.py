@@ -22,13 +22,19 @@ def _nvcc():
     return exe
 
 
+def _flags():
+    """NVCC_FLAGS plus S2I_EXTRA_NVCC_FLAGS from the environment (tuning experiments, e.g. -DS2I_SPIN_NS=32)."""
+    extra = os.environ.get("S2I_EXTRA_NVCC_FLAGS", "").split()
+    return NVCC_FLAGS + extra
+
+
 def _digest(paths):
     h = hashlib.sha256()
     for p in sorted(paths):
         h.update(p.encode())
         with open(p, "rb") as f:
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     return h.hexdigest()
 
 
@@ -45,7 +51,7 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(HERE, "build", os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = [nvcc] + _flags() + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()

@@ -60,7 +60,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int q_bytes = p.nkc * kChunk16;
@@ -165,8 +166,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_cons
             ptx::mbar_wait(q_full, 0);
             int next_s = 0;
             for (int j = 0; j < T; ++j) {
-                // keep score tiles issued up to nS - 1 tiles ahead of the P V products (nS <= stages: no deadlock)
-                while (next_s < T && next_s <= j + p.nS - 1) issue_S(next_s++);
+                // keep score tiles issued up to nS tiles ahead of the P V products: buffer (j + nS) % nS is the one the
+                // softmax warps drained for tile j (before P_j exists), and its K tile's stage was freed by P V (j + nS -
+                // stages) <= j - 1 because nS <= stages - 1 -- no wait below depends on a later step of this loop
+                while (next_s < T && next_s <= j + p.nS) issue_S(next_s++);
                 ptx::mbar_wait(&p_full[j % p.pbufs], (j / p.pbufs) & 1);
                 ptx::tc_fence_after();
                 const int stage = j % p.stages;
@@ -344,8 +347,21 @@ int attn_fwd_launch(const AttnDesc& d, cudaStream_t stream) {
         const char* e = getenv("S2I_ATTN_DEEP");
         return e ? atoi(e) : 0;      // measured on B200: two co-resident shallow CTAs beat one deep CTA (212 vs 353 us at N=4096)
     }();
+    static const int triple_mode = [] {
+        const char* e = getenv("S2I_ATTN_TRIPLE");
+        return e ? atoi(e) : -1;      // -1: automatic
+    }();
     int pbufs = 0, stages = 0;
-    if (deep_mode && T >= 8) {
+    bool triple = false;
+    // measured (tools/attn_bench.py): three CTAs per SM win for 64-wide heads (N = 9216: 530 vs 728 us), lose for 48 (234 vs 220)
+    const bool want_triple = triple_mode > 0 || (triple_mode < 0 && d.dp > 48 && T >= 32);
+    if (want_triple && T >= 8 && d.dp <= 64 && q_bytes + kChunk16 + 2 * stage_bytes + overhead <= 75 * 1024) {
+        // three CTAs per SM (128 TMEM columns each: one score tile + O): three softmax warps per scheduler
+        triple = true;
+        pbufs = 1;
+        stages = 2;
+        p.tmem_cols = 128;
+    } else if (deep_mode && T >= 8) {
         pbufs = 2;
         stages = (full_sm - overhead - q_bytes - pbufs * kChunk16) / stage_bytes;
         if (stages > kMaxStages) stages = kMaxStages;
@@ -372,7 +388,7 @@ int attn_fwd_launch(const AttnDesc& d, cudaStream_t stream) {
     p.pbufs = pbufs;
     p.nS = (p.tmem_cols - d.dp) / 64;
     if (p.nS > kMaxS) p.nS = kMaxS;
-    if (p.nS > stages) p.nS = stages;           // score tiles run at most `stages` key tiles ahead (see the issuer)
+    if (p.nS > stages - 1) p.nS = stages - 1;   // score tiles run nS key tiles ahead of the P V products (see the issuer)
     if (p.nS < 1) return set_error(S2I_ERR_ARG, "attn_fwd: head dim %d leaves no TMEM for the score tiles", d.dp);
     const size_t smem_bytes = (size_t)q_bytes + (size_t)pbufs * kChunk16 + (size_t)stages * stage_bytes + overhead;
 
@@ -390,11 +406,13 @@ int attn_fwd_launch(const AttnDesc& d, cudaStream_t stream) {
     }
     static bool attr_set = false;
     if (!attr_set) {
-        S2I_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        S2I_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        S2I_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     dim3 grid((unsigned)((d.Nq + kTileQ - 1) / kTileQ), (unsigned)(d.B * d.heads), 1);
-    S2I_LAUNCH((attn_fwd_kernel), grid, kThreads, smem_bytes, stream, p);
+    if (triple) S2I_LAUNCH((attn_fwd_kernel<3>), grid, kThreads, smem_bytes, stream, p);
+    else S2I_LAUNCH((attn_fwd_kernel<1>), grid, kThreads, smem_bytes, stream, p);
     // algorithmic work: QK^T + PV at the true head dim
     S2I_LAUNCH_CHECK_TAG("attn_fwd", 4.0 * d.B * d.heads * (double)d.Nq * d.Nk * d.d_true, 0.0);
     return 0;

@@ -51,10 +51,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (kernel fault, surfaced as a CUDA error) instead of hanging the GPU.
+#ifndef S2I_SPIN_NS
+#define S2I_SPIN_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // The spinning single-thread roles share warp schedulers with the epilogue / softmax warps, and every failed
+    // try_wait they issue is an issue slot those warps do not get (measured: the tighter the spin, the slower the
+    // attention kernels).  Back off between polls.
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+#if S2I_SPIN_NS > 0
+        __nanosleep(S2I_SPIN_NS);
+#endif
         if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
             __trap();
         }

@@ -24,6 +24,7 @@ class Sampler {
     UNet* unet;
     LGP* lgp;
     bool use_graphs = true;      // S2I_NO_GRAPH=1 disables
+    void context_changed() { ctx_fresh_ = true; }
     Sampler(UNet* u, LGP* l) : unet(u), lgp(l) {
         if (const char* e = getenv("S2I_NO_GRAPH")) use_graphs = !(e[0] == '1');
     }
@@ -50,7 +51,14 @@ class Sampler {
         S2I_MEMOP(cudaMemcpyAsync(d_sp_, hp, 8 * sizeof(float), cudaMemcpyHostToDevice, st));
         S2I_TRY(unet->prepare_time(t, st));
 
-        Key key{S, L, prediction, do_guide ? 1 : 0, lgp_train, guidance, beta};
+        // The text context is constant over the steps of an image: after the first step that saw it (context_changed()
+        // or a new ctx pointer / sample count marks a new one) the cross-attention K/V projections are reused.
+        if (ctx != last_ctx_ || S != last_S_) ctx_fresh_ = true;
+        last_ctx_ = ctx;
+        last_S_ = S;
+        const int reuse = ctx_fresh_ ? 0 : 1;
+        ctx_fresh_ = false;
+        Key key{S, L, prediction, do_guide ? 1 : 0, lgp_train, reuse, guidance, beta};
         // The replayed part works on sampler-owned copies of the caller's tensors, so one graph serves every image.
         S2I_TRY(layout(key));
         const size_t nb = (size_t)S * unet->cfg.in_ch * L * L * sizeof(float);
@@ -69,11 +77,11 @@ class Sampler {
 
   private:
     struct Key {
-        int S, L, prediction, guided, train;
+        int S, L, prediction, guided, train, reuse_kv;
         float guidance, beta;
         bool operator==(const Key& o) const {
             return S == o.S && L == o.L && prediction == o.prediction && guided == o.guided && train == o.train &&
-                   guidance == o.guidance && beta == o.beta;
+                   reuse_kv == o.reuse_kv && guidance == o.guidance && beta == o.beta;
         }
     };
     struct Entry {
@@ -128,6 +136,9 @@ class Sampler {
         return 0;
     }
 
+    bool ctx_fresh_ = true;
+    const void* last_ctx_ = nullptr;
+    int last_S_ = 0;
     static constexpr int kRing = 256;
     std::vector<Entry> graphs_;
     cudaStream_t cap_stream_ = nullptr;
@@ -195,7 +206,7 @@ class Sampler {
             S2I_MEMOP(cudaMemcpyAsync(x_in_ + (size_t)(2 * s + 1) * n, own_lat_ + (size_t)s * n, n * 4, cudaMemcpyDeviceToDevice, st));
         }
         const bool do_guide = k.guided != 0;
-        S2I_TRY(unet->forward(x_in_, B, L, L, 0.f, own_ctx_, eps_, do_guide, st, /*time_ready=*/true));    // :96
+        S2I_TRY(unet->forward(x_in_, B, L, L, 0.f, own_ctx_, eps_, do_guide, st, /*time_ready=*/true, k.reuse_kv != 0));    // :96
         S2I_TRY(cfg_ddim_step(own_lat_, eps_, S, n, k.guidance, 0.f, 1.f, 1.f, 0.f, k.prediction, x_new_, st, d_sp_));   // :100-104
         if (do_guide) {
             // taps -> LGP -> edge loss -> tap gradients   (:145-159, LGP part)
@@ -323,6 +334,12 @@ int s2i_guidance_update(const float* x_old, float* x_new, const float* dx, int S
 int s2i_sampler_create(s2i_unet* u, s2i_lgp* l, s2i_sampler** out) {
     if (!u || !out) return s2i::set_error(S2I_ERR_ARG, "s2i_sampler_create: null argument");
     *out = new s2i_sampler{new s2i::Sampler(u->impl, l ? l->impl : nullptr)};
+    return 0;
+}
+
+int s2i_sampler_context_changed(s2i_sampler* s) {
+    if (!s) return s2i::set_error(S2I_ERR_ARG, "s2i_sampler_context_changed: null handle");
+    s->impl->context_changed();
     return 0;
 }
 

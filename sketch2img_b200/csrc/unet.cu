@@ -89,6 +89,10 @@ int pack_linear_host(const float* host, int N, int K, __half* w, long w_ld, __ha
 
 // ================================================================================================== loading
 UNet::~UNet() {
+    for (auto& T : tfm_) {
+        if (T.kv2_cache) cudaFree(T.kv2_cache);
+        if (T.sat.kv16) cudaFree(T.sat.kv16);
+    }
     for (void* p : owned_) cudaFree(p);
     if (arena_.base) cudaFree(arena_.base);
 }
@@ -824,9 +828,30 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     RUN(ln_fwd(sv.t1.p, sv.t1.ld, rows, C, T.ln2.g, T.ln2.b, T.ln2.eps, l16b.p, l16b.ld, sv.l2, st_));
     sv.q2 = new16(B, H, W, T.HP);
     S2I_TRY(gemm(l16b, false, 1, T.q2.w, C, T.HP, C, nullptr, nullptr, nullptr, nullptr, &sv.q2));
-    sv.kv2 = new16(B, 1, cfg.ctx_len, 2 * T.HP);
-    S2I_TRY(gemm(ctx16_, false, 1, T.kv2.w, cfg.cross_dim, 2 * T.HP, cfg.cross_dim, nullptr, nullptr, nullptr, nullptr,
-                 &sv.kv2));
+    {
+        // persistent (not arena) so it survives to the next steps of the image
+        Transformer& Tm = tfm_[idx];
+        const size_t need = (size_t)B * cfg.ctx_len * 2 * T.HP * sizeof(__half);
+        if (!dry_ && need > Tm.kv2_cap) {
+            if (Tm.kv2_cache) cudaFree(Tm.kv2_cache);
+            Tm.kv2_cache = nullptr;
+            Tm.kv2_cap = 0;
+            void* q = nullptr;
+            if (cudaMalloc(&q, need) != cudaSuccess) {
+                cudaGetLastError();
+                return set_error(S2I_ERR_OOM, "unet: cannot allocate the context K/V cache");
+            }
+            ++g_alloc_gen;
+            Tm.kv2_cache = static_cast<__half*>(q);
+            Tm.kv2_cap = need;
+        }
+        sv.kv2 = H16();
+        sv.kv2.B = B; sv.kv2.H = 1; sv.kv2.W = cfg.ctx_len; sv.kv2.C = 2 * T.HP; sv.kv2.ld = 2 * T.HP;
+        sv.kv2.p = Tm.kv2_cache;
+        if (!reuse_kv_)
+            S2I_TRY(gemm(ctx16_, false, 1, T.kv2.w, cfg.cross_dim, 2 * T.HP, cfg.cross_dim, nullptr, nullptr, nullptr, nullptr,
+                         &sv.kv2));
+    }
     S2I_TRY(attention(T, sv.q2, 0, sv.kv2, 0, T.HP, cfg.ctx_len, sv.P2, sv.o2, need_bwd, &sv.lse2));
     sv.t2 = new32(B, H, W, C);
     S2I_TRY(gemm(sv.o2, false, 1, T.o2.w, T.HP, C, T.HP, T.o2.b, nullptr, &sv.t1, &sv.t2, nullptr));
@@ -919,7 +944,7 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
 
     // text context as fp16 GEMM operand
     ctx16_ = new16(B, 1, cfg.ctx_len, cfg.cross_dim);
-    RUN(cast2d(ctx_, cfg.cross_dim, (long)B * cfg.ctx_len, cfg.cross_dim, 1.f, ctx16_.p, ctx16_.ld, st_));
+    if (!reuse_kv_) RUN(cast2d(ctx_, cfg.cross_dim, (long)B * cfg.ctx_len, cfg.cross_dim, 1.f, ctx16_.p, ctx16_.ld, st_));
 
     // conv_in (im2col GEMM, K = 9*in_ch padded to 64)
     F32 x = new32(B, H, W, cfg.in_ch);
@@ -1141,9 +1166,11 @@ int UNet::prepare_time(float t, cudaStream_t st) {
 }
 
 int UNet::forward(const float* x_nchw, int B, int H, int W, float t, const float* ctx, float* eps_nchw,
-                  bool save_for_backward, cudaStream_t st, bool time_ready) {
+                  bool save_for_backward, cudaStream_t st, bool time_ready, bool reuse_ctx_kv) {
     if (!loaded_) return set_error(S2I_ERR_STATE, "unet: weights not loaded");
     time_ready_ = time_ready;
+    reuse_kv_ = reuse_ctx_kv && kv_cache_B_ == B;      // a cache filled for another batch size is not reusable
+    kv_cache_B_ = B;
     if (H % 8 || W % 8) return set_error(S2I_ERR_ARG, "unet: latent H, W must be multiples of 8 (got %d x %d)", H, W);
     st_ = st;
     B_ = B; H_ = H; W_ = W;

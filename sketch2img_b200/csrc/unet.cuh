@@ -96,6 +96,10 @@ struct Transformer {
     Lin ff1;   // [8C][C]
     Lin ff2;   // [C][4C]
     int C = 0, heads = 0, d = 0, dp = 0, HP = 0;
+    // K | V projections of the text context [B][ctx_len][2*HP]: the context is the same at every denoising step of an
+    // image, so they are computed on the first step and reused (UNet::forward's reuse_ctx_kv)
+    __half* kv2_cache = nullptr;
+    size_t kv2_cap = 0;
 };
 
 struct ResSave {
@@ -138,8 +142,10 @@ class UNet {
 
     // eps[B,4,H,W] (NCHW fp32, device) = unet(x[B,4,H,W], t, ctx[B,ctx_len,cross_dim]).  With save_for_backward the
     // activations needed by backward() stay resident until the next forward().
+    // reuse_ctx_kv: `ctx` holds the same values as in the previous forward of the same batch size -- skip the 16
+    // cross-attention K/V projections and reuse the cached ones.
     int forward(const float* x_nchw, int B, int H, int W, float t, const float* ctx, float* eps_nchw,
-                bool save_for_backward, cudaStream_t st, bool time_ready = false);
+                bool save_for_backward, cudaStream_t st, bool time_ready = false, bool reuse_ctx_kv = false);
     // The timestep-dependent part of the forward (sinusoidal embedding -> 2 Linear -> every ResBlock's time_emb_proj),
     // into a persistent buffer; results are cached per timestep.  forward(..., time_ready = true) then skips it, so the
     // rest of the step does not depend on t (the sampler replays it from a CUDA graph).
@@ -197,6 +203,8 @@ class UNet {
     long arena_key_ = -1;
     bool have_saved_ = false;
     bool time_ready_ = false;
+    bool reuse_kv_ = false;
+    int kv_cache_B_ = 0;
     float sat_scale_ = 1.f;
 
     int run_forward(const float* x_nchw, float t, float* eps_nchw);

@@ -173,6 +173,7 @@ class AntiGradientPipeline:
                 target = target.expand(S, -1, -1, -1)
             target = target.contiguous()
         sampler = self._get_sampler()
+        _lib.check(lib.s2i_sampler_context_changed(sampler))       # new prompt embeddings: re-project the context K/V
         train = int(self.lgp_model.training) if self.lgp_model is not None else 1
         loss = torch.zeros(S, device=device, dtype=torch.float32)
         stream = _lib.stream_ptr()
