@@ -334,6 +334,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
                     float4 v = make_float4(__uint_as_float(raw[4 * u]) + b4.x, __uint_as_float(raw[4 * u + 1]) + b4.y,
                                            __uint_as_float(raw[4 * u + 2]) + b4.z, __uint_as_float(raw[4 * u + 3]) + b4.w);
                     float4* slot = reinterpret_cast<float4*>(row32 + ((u ^ sw128) << 4));
+                    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (p.qscale != 0.f) {      // mimic unscaled fp16 autograd rounding (LGP backward)
+                        v.x = __half2float(__float2half_rn(v.x * p.qinv)) * p.qscale;
+                        v.y = __half2float(__float2half_rn(v.y * p.qinv)) * p.qscale;
+                        v.z = __half2float(__float2half_rn(v.z * p.qinv)) * p.qscale;
+                        v.w = __half2float(__float2half_rn(v.w * p.qinv)) * p.qscale;
+                    }
                     if (add_res) {
                         const float4 x = *slot;
                         v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
@@ -888,11 +895,12 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict_
 int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters, cudaStream_t stream) {
     GemmDesc d = d_in;
     const long rows_total = (long)d.aW * d.aH * d.aB;
-    bool can_split = d.splits >= 0 && d.out32 && !d.out16;
+    const bool nonlinear = d.relu || d.qscale != 0.f;      // ReLU / rounding emulation: the epilogue needs the full K sum
+    bool can_split = d.splits >= 0 && d.out32 && !d.out16 && !nonlinear;
     bool via_scratch = false;
     const int epi = (d.residual ? 1 : 0) | ((d.residual || d.out32) ? 2 : 0) | (d.out16 ? 4 : 0);
     TileChoice tc = choose_tiles_tma(d.N, tiles_m, num_iters, can_split, epi);
-    if (d.splits >= 0 && d.out16 && !d.out32 && (size_t)rows_total * d.N * sizeof(float) <= kWsBytes) {
+    if (d.splits >= 0 && !nonlinear && d.out16 && !d.out32 && (size_t)rows_total * d.N * sizeof(float) <= kWsBytes) {
         // fp16-only output of a K-heavy small problem: split K into an fp32 scratch tile matrix, then convert
         const int epi_s = (d.residual ? 1 : 0) | 2;
         const TileChoice ts = choose_tiles_tma(d.N, tiles_m, num_iters, true, epi_s);
@@ -951,6 +959,9 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     p.alpha = 1.f;
     p.bias = d.bias;
     p.rowvec = d.rowvec;
+    p.relu = d.relu;
+    p.qscale = d.qscale;
+    p.qinv = d.qscale != 0.f ? 1.f / d.qscale : 0.f;
     S2I_TRY(build_operand_maps(p, d, BN));
     if (d.residual) S2I_TRY(build_out_map(&p.mapRes, p, d, d.residual, d.res_ld, 2));
     if (d.out32) S2I_TRY(build_out_map(&p.mapO32, p, d, d.out32, d.ld32, 2));
@@ -1066,8 +1077,7 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
 
     // Epilogue through TMA (gemm_tma_kernel) whenever the shape allows: K-major operands, one problem, plain
     // bias / shared per-column vector / fp32 residual epilogue, 32-column boxes, 16-byte aligned rows.
-    bool tma = tma_epilogue_enabled() && !d.a_mn && !d.b_mn && Z == 1 && d.alpha == 1.f && !d.relu && d.qscale == 0.f &&
-               d.N % 32 == 0 && !d.out16_bf16 && !(d.rowvec && d.rowvec_ld != 0) && d.c_sb == 0 && d.c_sh == 0 &&
+    bool tma = tma_epilogue_enabled() && !d.a_mn && !d.b_mn && Z == 1 && d.alpha == 1.f && d.N % 32 == 0 && !d.out16_bf16 && !(d.rowvec && d.rowvec_ld != 0) && d.c_sb == 0 && d.c_sh == 0 &&
                d.a_hoff == 0 && d.b_hoff == 0;
     if (d.out32) tma = tma && (d.ld32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.out32) & 15) == 0);
     if (d.out16) tma = tma && (d.ld16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(d.out16) & 15) == 0);

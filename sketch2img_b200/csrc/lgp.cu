@@ -739,6 +739,9 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
         g.A = d; g.aC = K; g.aW = (int)rows; g.a_sw = d_ld;
         g.B = lin_[l].wd; g.bI = K; g.bR = N; g.b_sr = (K + 7) / 8 * 8;
         g.N = N; g.Kc = K;
+        // layer 0 writes the whole padded feature row (columns >= input_dim come from out-of-bounds weight rows: zeros),
+        // which makes the width a multiple of 32 and the GEMM eligible for the TMA-epilogue kernel
+        if (l == 0) g.N = (int)ldX_;
         g.qscale = qs;
         __half* o = l == 0 ? X_ : bufs[flip];
         g.out16 = o; g.ld16 = l == 0 ? ldX_ : N;

@@ -320,3 +320,35 @@ def test_two_subtile_conv3x3(L, cuda, B, H, W, Cin, Cout):
         L.lib().s2i_gemm_force_msub(0)
     ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1) + r.double()
     assert rel(out32, ref) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(8192, 512, 9320), (8192, 256, 512), (1000, 64, 128)])
+def test_relu_and_fp16_rounding_epilogues(L, cuda, M, N, K):
+    """The LGP MLP's epilogues: ReLU on the forward Linear, and the backward's emulation of unscaled fp16 autograd
+    rounding  v -> fp16(v / q) * q  (both also on the TMA-epilogue kernel)."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    Kp = (K + 7) // 8 * 8
+    a = torch.zeros(M, Kp)
+    a[:, :K] = torch.randn(M, K, generator=g)
+    a = a.to(cuda).half()
+    w = torch.zeros(N, Kp)
+    w[:, :K] = torch.randn(N, K, generator=g) * 0.02
+    w = w.to(cuda).half()
+    bias = torch.randn(N, generator=g).to(cuda)
+    ref = a.double() @ w.double().t() + bias.double()
+    out16 = torch.full((M, N), float("nan"), device=cuda, dtype=torch.float16)
+    d = L.GemmDesc(A=a.data_ptr(), aC=K, aW=M, a_sw=Kp, B=w.data_ptr(), bI=K, bR=N, b_sr=Kp, N=N, Kc=K, bias=bias.data_ptr(),
+                   relu=1, out16=out16.data_ptr(), ld16=N)
+    L.gemm(d)
+    torch.cuda.synchronize()
+    assert rel(out16.float(), torch.relu(ref)) < 3e-3
+    q = 2.0 ** 14
+    out32 = torch.full((M, N), float("nan"), device=cuda)
+    d = L.GemmDesc(A=a.data_ptr(), aC=K, aW=M, a_sw=Kp, B=w.data_ptr(), bI=K, bR=N, b_sr=Kp, N=N, Kc=K, qscale=q,
+                   out32=out32.data_ptr(), ld32=N)
+    L.gemm(d)
+    torch.cuda.synchronize()
+    want = ((a.double() @ w.double().t()) / q).half().double() * q
+    # identical up to the rare value whose fp32 accumulation-order noise crosses an fp16 rounding boundary
+    assert rel(out32, want) < 2e-3
+    assert torch.equal(out32, (out32 / q).half().float() * q)              # every output is an fp16 multiple of q
