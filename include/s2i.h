@@ -120,6 +120,9 @@ int s2i_unet_forward(s2i_unet* u, const float* x, int B, int H, int W, float t, 
 int s2i_unet_tap(s2i_unet* u, int k, float** ptr, int* B, int* H, int* W, int* C);
 /* tap_grads[k]: NHWC fp32 device, shaped like tap k (NULL = no gradient); dx: NCHW fp32 device [B,C,H,W] */
 int s2i_unet_backward(s2i_unet* u, float* const* tap_grads, float* dx, void* cuda_stream);
+/* The same walk over the samples [b0, b0 + nb) of the forward's batch only: tap_grads[k] and dx hold nb samples.
+ * Samples are independent computations, and modules/pipeline.py:159 keeps only the cond half of the gradient. */
+int s2i_unet_backward_samples(s2i_unet* u, float* const* tap_grads, float* dx, int b0, int nb, void* cuda_stream);
 /* Injected sketch attention (modules/sketch_guided_attn.py:8-161, SatMixin / AttnModule; forward only).
  * load_sat: host fp32 tensors under the reference's parameter names
  *   "sketch_attn_<block path, '.' -> '_'>_transformer_blocks_0.{sketch_norm.{weight,bias}, sketch_attn.to_{q,k,v}.weight,
@@ -166,6 +169,10 @@ int s2i_lgp_output(s2i_lgp* l, float* out_rows, void* cuda_stream);
  * loss: device float [B/2] (MSE on the cond half, modules/pipeline.py:157) */
 int s2i_lgp_loss_backward(s2i_lgp* l, const float* target, float* const* tap_grads, float* loss, float* grad_scale,
                           void* cuda_stream);
+/* Same loss; tap_grads[k] holds only the B/2 cond samples' gradients (sample s = batch entry 2s+1), which is all
+ * modules/pipeline.py:159 keeps.  The BatchNorm backward still covers both halves. */
+int s2i_lgp_loss_backward_cond(s2i_lgp* l, const float* target, float* const* tap_grads, float* loss, float* grad_scale,
+                               void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------
  * CFG combine + DDIM step (modules/pipeline.py:100-104; diffusers DDIMScheduler.step, eta = 0) and the

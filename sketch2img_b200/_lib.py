@@ -76,6 +76,7 @@ def lib():
     h.s2i_unet_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, C.c_int, vp]
     h.s2i_unet_tap.argtypes = [vp, C.c_int, fp, ip, ip, ip, ip]
     h.s2i_unet_backward.argtypes = [vp, C.POINTER(vp), vp, vp]
+    h.s2i_unet_backward_samples.argtypes = [vp, C.POINTER(vp), vp, C.c_int, C.c_int, vp]
     h.s2i_unet_load_sat.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(vp), ip, C.POINTER(C.c_longlong)]
     h.s2i_unet_set_sat_feature.argtypes = [vp, C.c_char_p, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     h.s2i_unet_set_sat_scale.argtypes = [vp, C.c_float, vp]
@@ -93,6 +94,7 @@ def lib():
     h.s2i_lgp_forward_nchw.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     h.s2i_lgp_output.argtypes = [vp, vp, vp]
     h.s2i_lgp_loss_backward.argtypes = [vp, vp, C.POINTER(vp), vp, C.POINTER(f), vp]
+    h.s2i_lgp_loss_backward_cond.argtypes = [vp, vp, C.POINTER(vp), vp, C.POINTER(f), vp]
     h.s2i_cfg_ddim_step.argtypes = [vp, vp, C.c_int, C.c_int, f, f, f, f, f, C.c_int, vp, vp]
     h.s2i_guidance_update.argtypes = [vp, vp, vp, C.c_int, C.c_int, f, vp, vp]
     h.s2i_sampler_create.argtypes = [vp, vp, C.POINTER(vp)]

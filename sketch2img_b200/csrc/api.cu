@@ -132,6 +132,12 @@ int s2i_unet_backward(s2i_unet* u, float* const* tap_grads, float* dx, void* cud
     return u->impl->backward(tap_grads, dx, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int s2i_unet_backward_samples(s2i_unet* u, float* const* tap_grads, float* dx, int b0, int nb, void* cuda_stream) {
+    if (!u || !tap_grads || !dx) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_backward_samples: null argument");
+    if (nb < 1) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_backward_samples: nb must be positive");
+    return u->impl->backward(tap_grads, dx, static_cast<cudaStream_t>(cuda_stream), b0, nb);
+}
+
 int s2i_unet_load_sat(s2i_unet* u, int n, const char* const* names, const float* const* host_ptrs, const int* ndims,
                       const long long* shapes) {
     if (!u || !names || !host_ptrs || !ndims || !shapes) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_load_sat: null argument");

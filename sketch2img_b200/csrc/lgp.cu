@@ -272,8 +272,9 @@ __global__ void __launch_bounds__(256) lgp_loss_kernel(const __half* __restrict_
 }
 
 // tap_grad[b][y][x][c] = sum_{h,w} wy(h,y) wx(w,x) dX[(b,h,w)][off + c]   (adjoint of the bilinear resize)
+// Source sample of output sample b is  b * bmul + badd  (cond-only gradients: bmul = 2, badd = 1); g holds B samples.
 __global__ void __launch_bounds__(256) interp_bwd_kernel(const __half* __restrict__ dX, long ldX, int off, int B, int L,
-                                                         int S, int C, float* __restrict__ g) {
+                                                         int S, int C, float* __restrict__ g, int bmul, int badd) {
     pdl_wait();
     pdl_launch();
     const int chunks = C >> 3;
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(const __half* __restric
                     wx = (i0 == x ? 1.f - l1 : 0.f) + (i1 == x ? l1 : 0.f);
                 }
                 if (wx == 0.f) continue;
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(dX + (((long)b * L + h) * L + w) * ldX + off + c));
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(dX + (((long)(b * bmul + badd) * L + h) * L + w) * ldX + off + c));
                 const __half2* hp = reinterpret_cast<const __half2*>(&q);
                 const float ww = wy * wx;
 #pragma unroll
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(const __half* __restric
 // Separable form of the same adjoint for the low-resolution taps (the direct gather above visits a (2f+2)^2 window per
 // output, 289 strided loads at f = 8): horizontal pass dX [B][L][L][.] -> T [B][L][S][C] fp32, vertical pass T -> g [B][S][S][C].
 __global__ void __launch_bounds__(256) interp_bwd_h_kernel(const __half* __restrict__ dX, long ldX, int off, int B, int L,
-                                                           int S, int C, float* __restrict__ T) {
+                                                           int S, int C, float* __restrict__ T, int bmul, int badd) {
     pdl_wait();
     pdl_launch();
     const int chunks = C >> 3;
@@ -342,7 +343,8 @@ __global__ void __launch_bounds__(256) interp_bwd_h_kernel(const __half* __restr
         const long pix = idx / chunks;                    // (b, h, x)
         const int c = (int)(idx - pix * chunks) << 3;
         const int x = (int)(pix % S);
-        const long bh = pix / S;                          // b * L + h
+        const long bh0 = pix / S;                         // b * L + h
+        const long bh = ((bh0 / L) * bmul + badd) * L + bh0 % L;    // the source row of that (sample, h)
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const int w_lo = max(0, (int)floorf(f * ((float)x - 0.5f) - 0.5f));
         const int w_hi = min(L - 1, (int)ceilf(f * ((float)x + 1.5f) - 0.5f));
@@ -440,14 +442,14 @@ __global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) guidance_norms_kernel(const float* __restrict__ x_old,
                                                              const float* __restrict__ x_new,
                                                              const float* __restrict__ dx, int n,
-                                                             double* __restrict__ scratch) {
+                                                             double* __restrict__ scratch, int dmul, int dadd) {
     pdl_wait();
     pdl_launch();
     const int s = blockIdx.y;
     float a = 0.f, b = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float d = x_old[(long)s * n + i] - x_new[(long)s * n + i];
-        const float gq = dx[(2L * s + 1) * n + i];
+        const float gq = dx[((long)s * dmul + dadd) * n + i];
         a += d * d;
         b += gq * gq;
     }
@@ -474,7 +476,8 @@ __global__ void __launch_bounds__(256) guidance_norms_kernel(const float* __rest
 }
 
 __global__ void __launch_bounds__(256) guidance_apply_kernel(float* __restrict__ x_new, const float* __restrict__ dx,
-                                                             int n, float beta, const double* __restrict__ scratch) {
+                                                             int n, float beta, const double* __restrict__ scratch,
+                                                             int dmul, int dadd) {
     pdl_wait();
     pdl_launch();
     const int s = blockIdx.y;
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(256) guidance_apply_kernel(float* __restrict__
     const float den = (float)sqrt(scratch[2 * s + 1]);
     const float alpha = num / den * beta;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float gq = -dx[(2L * s + 1) * n + i];
+        const float gq = -dx[((long)s * dmul + dadd) * n + i];
         x_new[(long)s * n + i] = __fadd_rn(x_new[(long)s * n + i], __fmul_rn(alpha, gq));
     }
 }
@@ -712,7 +715,7 @@ int LGP::export_output(float* out_rows, cudaStream_t st) {
     return 0;
 }
 
-int LGP::loss_backward(const float* target, float* const tap_grads[9], float* loss, cudaStream_t st) {
+int LGP::loss_backward(const float* target, float* const tap_grads[9], float* loss, cudaStream_t st, bool cond_only) {
     if (!have_fwd_) return set_error(S2I_ERR_STATE, "lgp: loss_backward needs a preceding forward");
     have_fwd_ = false;
     const long rows = (long)B_ * L_ * L_;
@@ -745,6 +748,18 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
         g.qscale = qs;
         __half* o = l == 0 ? X_ : bufs[flip];
         g.out16 = o; g.ld16 = l == 0 ? ldX_ : N;
+        if (l == 0 && cond_only) {
+            // the feature gradient of the uncond rows is never read: one GEMM per cond sample (rows (2s+1) L^2 ...)
+            const long LL = (long)L_ * L_;
+            for (int s = 0; s < S; ++s) {
+                GemmDesc gs = g;
+                gs.A = d + (2 * s + 1) * LL * d_ld;
+                gs.aW = (int)LL;
+                gs.out16 = X_ + (2 * s + 1) * LL * ldX_;
+                S2I_TRY(gemm_launch(gs, st));
+            }
+            break;
+        }
         S2I_TRY(gemm_launch(g, st));
         if (l == 0) break;
         // BatchNorm(l-1) + ReLU backward
@@ -767,7 +782,7 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
         size_t need = 0;
         for (int k = 0; k < 9; ++k)
             if (tap_grads[k] && taps_[k].S * 4 <= L_) {
-                const size_t n = (size_t)B_ * L_ * taps_[k].S * taps_[k].C * sizeof(float);
+                const size_t n = (size_t)(cond_only ? S : B_) * L_ * taps_[k].S * taps_[k].C * sizeof(float);
                 if (n > need) need = n;
             }
         if (need > interp_cap_) {
@@ -785,21 +800,22 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
         }
     }
     int off = 0;
+    const int Bg = cond_only ? S : B_, bmul = cond_only ? 2 : 1, badd = cond_only ? 1 : 0;
     for (int k = 0; k < 9; ++k) {
         if (!taps_[k].S) return set_error(S2I_ERR_STATE, "lgp: backward to taps needs the tap-based forward");
         if (tap_grads[k]) {
             const int Sk = taps_[k].S, Ck = taps_[k].C;
             if (Sk * 4 <= L_) {
                 // resize factor >= 4: separable adjoint through a [B][L][S][C] fp32 intermediate
-                S2I_LAUNCH((interp_bwd_h_kernel), grid1d((long)B_ * L_ * Sk * (Ck / 8)), 256, 0, st, X_, ldX_, off, B_, L_, Sk, Ck,
-                           interp_tmp_);
+                S2I_LAUNCH((interp_bwd_h_kernel), grid1d((long)Bg * L_ * Sk * (Ck / 8)), 256, 0, st, X_, ldX_, off, Bg, L_, Sk, Ck,
+                           interp_tmp_, bmul, badd);
                 S2I_LAUNCH_CHECK();
-                S2I_LAUNCH((interp_bwd_v_kernel), grid1d((long)B_ * Sk * Sk * (Ck / 4)), 256, 0, st, interp_tmp_, B_, L_, Sk, Ck,
+                S2I_LAUNCH((interp_bwd_v_kernel), grid1d((long)Bg * Sk * Sk * (Ck / 4)), 256, 0, st, interp_tmp_, Bg, L_, Sk, Ck,
                            tap_grads[k]);
                 S2I_LAUNCH_CHECK();
             } else {
-                S2I_LAUNCH((interp_bwd_kernel), grid1d((long)B_ * Sk * Sk * (Ck / 8)), 256, 0, st, X_, ldX_, off, B_, L_, Sk, Ck,
-                           tap_grads[k]);
+                S2I_LAUNCH((interp_bwd_kernel), grid1d((long)Bg * Sk * Sk * (Ck / 8)), 256, 0, st, X_, ldX_, off, Bg, L_, Sk, Ck,
+                           tap_grads[k], bmul, badd);
                 S2I_LAUNCH_CHECK();
             }
         }
@@ -818,12 +834,13 @@ int cfg_ddim_step(const float* latents, const float* eps, int S, int n, float gu
 }
 
 int guidance_update(const float* x_old, float* x_new, const float* dx, int S, int n, float beta, double* scratch,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool dx_cond_only) {
+    const int dmul = dx_cond_only ? 1 : 2, dadd = dx_cond_only ? 0 : 1;
     S2I_MEMOP(cudaMemsetAsync(scratch, 0, (size_t)S * 2 * sizeof(double), st));
     dim3 grid(grid1d(n, 256, 64), S);
-    S2I_LAUNCH((guidance_norms_kernel), grid, 256, 0, st, x_old, x_new, dx, n, scratch);
+    S2I_LAUNCH((guidance_norms_kernel), grid, 256, 0, st, x_old, x_new, dx, n, scratch, dmul, dadd);
     S2I_LAUNCH_CHECK();
-    S2I_LAUNCH((guidance_apply_kernel), grid, 256, 0, st, x_new, dx, n, beta, scratch);
+    S2I_LAUNCH((guidance_apply_kernel), grid, 256, 0, st, x_new, dx, n, beta, scratch, dmul, dadd);
     S2I_LAUNCH_CHECK();
     return 0;
 }

@@ -33,7 +33,11 @@ class LGP {
                 const float* dsigma = nullptr);
     // Edge loss on the cond half + backward to the taps.  target: NCHW fp32 [samples,4,L,L].
     // tap_grads[k]: NHWC fp32 like tap k, multiplied by grad_scale(); loss: device float [samples].
-    int loss_backward(const float* target, float* const tap_grads[9], float* loss, cudaStream_t st);
+    // cond_only: only the cond samples' tap gradients are produced (tap_grads[k] then holds `samples` maps, sample s =
+    // gradient of batch entry 2s+1) -- the sampler discards the uncond half of the latent gradient (pipeline.py:159) and
+    // the UNet is per-sample, so the uncond taps' gradients are never needed.  The BatchNorm backward still runs over
+    // both halves (train-mode statistics couple them).
+    int loss_backward(const float* target, float* const tap_grads[9], float* loss, cudaStream_t st, bool cond_only = false);
     float grad_scale() const { return gscale_; }
     const __half* output() const { return out16_; }
     // out_rows: fp32 [(b w h)][output_dim] in the reference's row order (latent_predictor.py:43)
@@ -89,8 +93,8 @@ class LGP {
 int cfg_ddim_step(const float* latents, const float* eps, int S, int n, float guidance, float sb_t, float sa_t,
                   float sa_p, float sb_p, int prediction, float* out, cudaStream_t st, const float* dparams = nullptr);
 // x_new += beta * ||x_in - x_new||_F / ||g||_F * g with g = -dx[cond half]; norms per sample; x_in = [x_old, x_old].
-// dx: [2*S][n].  scratch: double [S][2] device.
+// dx: [2*S][n], or [S][n] holding only the cond halves (dx_cond_only).  scratch: double [S][2] device.
 int guidance_update(const float* x_old, float* x_new, const float* dx, int S, int n, float beta, double* scratch,
-                    cudaStream_t st);
+                    cudaStream_t st, bool dx_cond_only = false);
 
 }  // namespace s2i

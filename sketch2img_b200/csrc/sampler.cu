@@ -217,9 +217,16 @@ class Sampler {
                 taps[q] = LgpTap{tp.p, tp.H, tp.C};
             }
             S2I_TRY(lgp->forward(taps, B, L, own_noise_, 0.f, k.train != 0, st, d_sp_ + 4));
-            S2I_TRY(lgp->loss_backward(own_target_, tg_, own_loss_, st));
-            S2I_TRY(unet->backward(tg_, dx_, st));                                                   // :159 (UNet part)
-            S2I_TRY(guidance_update(own_lat_, x_new_, dx_, S, n, k.beta, norms_, st));               // :160-161
+            // Only the cond half of the latent gradient is kept (:159) and the UNet is a per-sample computation, so the
+            // backward walks the cond sample alone (one image: batch entry 1); the LGP's BatchNorm backward still
+            // runs over both halves.  Several images per call keep the whole-batch walk (cond entries are interleaved).
+            const bool cond_only = S == 1;
+            S2I_TRY(lgp->loss_backward(own_target_, tg_, own_loss_, st, cond_only));
+            if (cond_only)
+                S2I_TRY(unet->backward(tg_, dx_, st, 1, 1));                                         // :159 (UNet part)
+            else
+                S2I_TRY(unet->backward(tg_, dx_, st));
+            S2I_TRY(guidance_update(own_lat_, x_new_, dx_, S, n, k.beta, norms_, st, cond_only));    // :160-161
         }
         S2I_MEMOP(cudaMemcpyAsync(own_lat_, x_new_, (size_t)S * n * 4, cudaMemcpyDeviceToDevice, st));
         return 0;
@@ -313,6 +320,14 @@ int s2i_lgp_loss_backward(s2i_lgp* l, const float* target, float* const* tap_gra
                           void* cuda_stream) {
     if (!l || !target || !tap_grads || !loss) return s2i::set_error(S2I_ERR_ARG, "s2i_lgp_loss_backward: null argument");
     int rc = l->impl->loss_backward(target, tap_grads, loss, static_cast<cudaStream_t>(cuda_stream));
+    if (rc == 0 && grad_scale) *grad_scale = l->impl->grad_scale();
+    return rc;
+}
+
+int s2i_lgp_loss_backward_cond(s2i_lgp* l, const float* target, float* const* tap_grads, float* loss, float* grad_scale,
+                               void* cuda_stream) {
+    if (!l || !target || !tap_grads || !loss) return s2i::set_error(S2I_ERR_ARG, "s2i_lgp_loss_backward_cond: null argument");
+    int rc = l->impl->loss_backward(target, tap_grads, loss, static_cast<cudaStream_t>(cuda_stream), /*cond_only=*/true);
     if (rc == 0 && grad_scale) *grad_scale = l->impl->grad_scale();
     return rc;
 }

@@ -624,9 +624,51 @@ int UNet::resblock(int idx, const F32& x, F32& out) {
     return 0;
 }
 
+// Views of what the forward saved, restricted to the samples [bb0_, bb0_ + bnb_) the backward runs on.
+F32 UNet::sub(const F32& t) const {
+    F32 v = t;
+    if (t.p) v.p = t.p + (size_t)bb0_ * t.H * t.W * t.ld;
+    v.B = bnb_;
+    return v;
+}
+H16 UNet::sub(const H16& t) const {
+    H16 v = t;
+    if (t.p) v.p = t.p + (size_t)bb0_ * t.H * t.W * t.ld;
+    v.B = bnb_;
+    return v;
+}
+ResSave UNet::sub(const ResSave& s) const {
+    ResSave v;
+    v.x = sub(s.x);
+    v.h1 = sub(s.h1);
+    v.s1 = s.s1 + (size_t)bb0_ * kGroups * 2;
+    v.s2 = s.s2 + (size_t)bb0_ * kGroups * 2;
+    return v;
+}
+TfmSave UNet::sub(const TfmSave& s, const Transformer& T) const {
+    TfmSave v;
+    v.x = sub(s.x); v.t0 = sub(s.t0); v.t1 = sub(s.t1); v.t2 = sub(s.t2);
+    v.ff = sub(s.ff); v.qkv = sub(s.qkv); v.q2 = sub(s.q2); v.kv2 = sub(s.kv2); v.o1 = sub(s.o1); v.o2 = sub(s.o2);
+    const size_t tok = (size_t)bb0_ * s.x.H * s.x.W;
+    v.gs = s.gs + (size_t)bb0_ * kGroups * 2;
+    v.l1 = s.l1 + tok * 2; v.l2 = s.l2 + tok * 2; v.l3 = s.l3 + tok * 2;
+    v.lse1 = s.lse1 ? s.lse1 + tok * T.heads : nullptr;
+    v.lse2 = s.lse2 ? s.lse2 + tok * T.heads : nullptr;
+    // unfused attention keeps P as [B * heads][Nq][ldP]
+    auto subP = [&](const H16& P) {
+        H16 w = P;
+        if (P.p) w.p = P.p + (size_t)bb0_ * T.heads * P.H * P.W * P.ld;
+        w.B = bnb_ * T.heads;
+        return w;
+    };
+    v.P1 = subP(s.P1);
+    v.P2 = subP(s.P2);
+    return v;
+}
+
 int UNet::resblock_bwd(int idx, const F32& dout, F32& dx) {
     const ResBlock& R = res_[idx];
-    const ResSave& S = rsave_[idx];
+    const ResSave S = sub(rsave_[idx]);
     const int B = dout.B, H = dout.H, W = dout.W, HW = H * W;
     H16 d16 = new16(B, H, W, R.Cout);
     RUN(cast2d(dout.p, dout.ld, dout.rows(), R.Cout, 1.f, d16.p, d16.ld, st_));
@@ -880,7 +922,7 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
 
 int UNet::transformer_bwd(int idx, const F32& dout, F32& dx) {
     const Transformer& T = tfm_[idx];
-    const TfmSave& S = tsave_[idx];
+    const TfmSave S = sub(tsave_[idx], T);
     const int B = dout.B, H = dout.H, W = dout.W, HW = H * W, C = T.C;
     const long rows = dout.rows();
     H16 d16 = new16(B, H, W, C);
@@ -1036,8 +1078,8 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
 }
 
 int UNet::run_backward(float* const tap_grads[9], float* dx_nchw) {
-    const int B = B_;
-    const size_t bstat_cap = (size_t)kStatsSlots * B * kGroups * 2;
+    const int B = bnb_;
+    const size_t bstat_cap = (size_t)kStatsSlots * B_ * kGroups * 2;   // new_stats() hands out B_-sample slots
     double* save_stats = stats_;
     size_t save_off = stats_off_;
     stats_ = dalloc<double>(bstat_cap);
@@ -1046,6 +1088,7 @@ int UNet::run_backward(float* const tap_grads[9], float* dx_nchw) {
 
     auto tapg = [&](int k) {
         F32 g = taps[k];
+        g.B = B;
         g.p = tap_grads ? tap_grads[k] : nullptr;
         if (dry_) g.p = reinterpret_cast<float*>(256);
         g.ld = g.C;
@@ -1184,6 +1227,8 @@ int UNet::forward(const float* x_nchw, int B, int H, int W, float t, const float
         arena_ = Arena();
         dry_ = true;
         int rc = run_forward(nullptr, t, nullptr);
+        bb0_ = 0;
+        bnb_ = B;      // sized for a backward over every sample (a sub-range needs less)
         if (rc == 0 && save_) rc = run_backward(nullptr, nullptr);
         dry_ = false;
         const size_t need = arena_.peak + (64u << 20);
@@ -1209,10 +1254,15 @@ int UNet::forward(const float* x_nchw, int B, int H, int W, float t, const float
     return rc;
 }
 
-int UNet::backward(float* const tap_grads[9], float* dx_nchw, cudaStream_t st) {
+int UNet::backward(float* const tap_grads[9], float* dx_nchw, cudaStream_t st, int b0, int nb) {
     if (!have_saved_) return set_error(S2I_ERR_STATE, "unet backward: no forward with save_for_backward precedes it");
+    if (nb < 0) nb = B_ - b0;
+    if (b0 < 0 || nb < 1 || b0 + nb > B_)
+        return set_error(S2I_ERR_ARG, "unet backward: samples [%d, %d) are not inside the forward's batch of %d", b0, b0 + nb, B_);
     st_ = st;
     have_saved_ = false;
+    bb0_ = b0;
+    bnb_ = nb;
     return run_backward(tap_grads, dx_nchw);
 }
 

@@ -151,7 +151,10 @@ class UNet {
     // rest of the step does not depend on t (the sampler replays it from a CUDA graph).
     int prepare_time(float t, cudaStream_t st);
     // dx[B,4,H,W] (NCHW fp32) = sum_k J_k^T tap_grad[k]; tap_grad[k] is NHWC fp32 shaped like tap(k).
-    int backward(float* const tap_grads[9], float* dx_nchw, cudaStream_t st);
+    // (b0, nb): walk only the samples [b0, b0 + nb) of the forward's batch (nb < 0: through the last one) -- samples are
+    // independent computations (GroupNorm per sample, LayerNorm per token, attention per sample), and the guided sampler
+    // only keeps the cond half of the gradient (pipeline.py:159).  tap_grads / dx then hold nb samples.
+    int backward(float* const tap_grads[9], float* dx_nchw, cudaStream_t st, int b0 = 0, int nb = -1);
 
     // Injected sketch attention (SatMixin): weights under the reference's names
     // "sketch_attn_<block path with '.' -> '_'>_transformer_blocks_0.{sketch_norm,sketch_attn.to_q,...,sketch_conv}.*",
@@ -188,6 +191,7 @@ class UNet {
     bool save_ = false;
     cudaStream_t st_ = nullptr;
     int B_ = 0, H_ = 0, W_ = 0;
+    int bb0_ = 0, bnb_ = 0;      // sample range of the current backward
     const float* ctx_ = nullptr;
     float* temb_ = nullptr;      // fused time_emb_proj output [sum Cout] (persistent)
     float *te0_ = nullptr, *te1_ = nullptr, *te2_ = nullptr;
@@ -229,6 +233,10 @@ class UNet {
                       int Nk, const H16& P, const H16& o, const float* lse, H16& dq, long dq_c0, H16* dkv, long dk_c0,
                       long dv_c0);
     int accumulate(F32& acc, const F32& g);
+    F32 sub(const F32& t) const;
+    H16 sub(const H16& t) const;
+    ResSave sub(const ResSave& s) const;
+    TfmSave sub(const TfmSave& s, const Transformer& T) const;
 };
 
 }  // namespace s2i

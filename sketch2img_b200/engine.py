@@ -108,14 +108,20 @@ class UNetEngine:
     def taps(self):
         return [self.tap(k) for k in range(9)]
 
-    def backward(self, tap_grads):
-        """tap_grads: 9 NHWC fp32 cuda tensors (or None) -> dx [B,4,H,W] fp32 (NCHW)."""
+    def backward(self, tap_grads, samples=None):
+        """tap_grads: 9 NHWC fp32 cuda tensors (or None) -> dx [B,4,H,W] fp32 (NCHW).
+        samples = (b0, nb): walk only the samples [b0, b0 + nb) of the forward's batch; tap_grads and dx hold nb samples."""
         x, _ = self._last
         gs = [None if g is None else g.to(self.device, torch.float32).contiguous() for g in tap_grads]
         arr = (C.c_void_p * 9)(*[None if g is None else g.data_ptr() for g in gs])
-        dx = torch.empty_like(x)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.s2i_unet_backward(self._h, arr, dx.data_ptr(), _lib.stream_ptr()))
+            if samples is None:
+                dx = torch.empty_like(x)
+                _lib.check(self.lib.s2i_unet_backward(self._h, arr, dx.data_ptr(), _lib.stream_ptr()))
+            else:
+                b0, nb = samples
+                dx = torch.empty((nb,) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+                _lib.check(self.lib.s2i_unet_backward_samples(self._h, arr, dx.data_ptr(), int(b0), int(nb), _lib.stream_ptr()))
         return dx
 
     def set_debug(self, on=True):

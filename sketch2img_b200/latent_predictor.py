@@ -112,14 +112,16 @@ class LGPEngine:
         _lib.check(self.lib.s2i_lgp_output(self._h, out.data_ptr(), _lib.stream_ptr()))
         return out
 
-    def loss_backward(self, target, taps):
-        """-> (loss [B/2], tap grads (9 NHWC fp32 tensors, scaled), grad_scale)."""
-        grads = [torch.empty_like(t) for t in taps]
+    def loss_backward(self, target, taps, cond_only=False):
+        """-> (loss [B/2], tap grads (9 NHWC fp32 tensors, scaled), grad_scale).  cond_only: the gradients of the B/2 cond
+        samples only (batch entries 1, 3, ...), which is all pipeline.py:159 keeps."""
         S = target.shape[0]
+        grads = [torch.empty_like(t[1::2]) if cond_only else torch.empty_like(t) for t in taps]
         loss = torch.empty(S, device=target.device, dtype=torch.float32)
         scale = C.c_float()
-        _lib.check(self.lib.s2i_lgp_loss_backward(self._h, target.data_ptr(), (C.c_void_p * 9)(*[g.data_ptr() for g in grads]),
-                                                  loss.data_ptr(), C.byref(scale), _lib.stream_ptr()))
+        fn = self.lib.s2i_lgp_loss_backward_cond if cond_only else self.lib.s2i_lgp_loss_backward
+        _lib.check(fn(self._h, target.data_ptr(), (C.c_void_p * 9)(*[g.data_ptr() for g in grads]),
+                      loss.data_ptr(), C.byref(scale), _lib.stream_ptr()))
         return loss, grads, scale.value
 
 

@@ -82,6 +82,38 @@ def test_unet_forward_taps_backward_match_oracle(tiny):
         eng.backward(Gd)
 
 
+def test_unet_backward_over_a_sample_range_equals_the_slice_of_the_whole_walk(tiny):
+    """pipeline.py:159 keeps only the cond half of the latent gradient, and samples are independent computations: the
+    sampler therefore walks the cond sample alone (s2i_unet_backward_samples).  It must equal that sample's slice of the
+    whole-batch walk, and the oracle's autograd gradient of that sample."""
+    port, o_unet, eng = tiny["port"], tiny["o_unet"], tiny["unet"].engine
+    lat, emb, _ = tiny["inputs"]
+    g = torch.Generator().manual_seed(13)
+    x = torch.cat([lat] * 2) + 0.05 * torch.randn(2, *lat.shape[1:], generator=g)
+    taps, handles = port.register_taps(o_unet)
+    xg = x.clone().requires_grad_(True)
+    with torch.enable_grad():
+        o_unet(xg, torch.tensor(501), encoder_hidden_states=emb)
+        tap_ref = [m.output for m in taps]
+        G = [torch.randn(t.shape, generator=g) for t in tap_ref]
+        dx_ref = torch.autograd.grad(sum((gg * t).sum() for gg, t in zip(G, tap_ref)), xg)[0]
+    for h in handles:
+        h.remove()
+    Gd = [gg.permute(0, 2, 3, 1).contiguous().cuda() for gg in G]
+    eng.forward(x.cuda(), 501, emb.cuda(), save_for_backward=True)
+    whole = eng.backward(Gd)
+    for b0 in (1, 0):
+        eng.forward(x.cuda(), 501, emb.cuda(), save_for_backward=True)
+        part = eng.backward([gg[b0:b0 + 1].contiguous() for gg in Gd], samples=(b0, 1))
+        assert tuple(part.shape) == (1,) + tuple(x.shape[1:])
+        assert rel(part, whole[b0:b0 + 1]) < 3e-3, f"sample {b0} vs whole-batch walk"
+        assert rel(part, dx_ref[b0:b0 + 1]) < 6e-3, f"sample {b0} vs oracle"
+    from sketch2img_b200._lib import S2IError
+    eng.forward(x.cuda(), 501, emb.cuda(), save_for_backward=True)
+    with pytest.raises(S2IError):
+        eng.backward([gg[:1].contiguous() for gg in Gd], samples=(2, 1))       # outside the forward's batch
+
+
 def test_unet_forward_is_reproducible_and_batch_independent(tiny):
     eng = tiny["unet"].engine
     lat, emb, _ = tiny["inputs"]
@@ -150,6 +182,14 @@ def test_lgp_forward_loss_backward_match_oracle(tiny):
         print("LGP tap gradients vs %s oracle: %s" % (key, " ".join("%.2e" % e for e in errs)))
         # on identical inputs the CUDA gradient is as close to either oracle as the two oracles are to each other
         assert max(errs) < 1.5 * yard + 1e-2, f"{key}: {errs}"
+        # cond-only form (what the sampler calls): the cond sample's gradients, same values
+        eng.forward_taps(taps_nhwc, 2, L, lat.cuda().contiguous(), sigma, True)
+        l2, gc, scale2 = eng.loss_backward(tgt.cuda().contiguous(), taps_nhwc, cond_only=True)
+        assert scale2 == scale and abs(l2.item() - l.item()) <= 1e-6 * abs(l.item())
+        for k in range(9):
+            assert tuple(gc[k].shape) == (1,) + tuple(grads[k].shape[1:])
+            # same arithmetic; the 4096-row layer-1 dgrad may pick another tile / split-K than the 8192-row one
+            assert rel(gc[k], grads[k][1:2]) < 2e-3, f"{key}: cond-only tap gradient {k} differs from the cond slice"
     eng.set_grad_rounding(True)
     # LatentEdgePredictor.forward surface (already resized + concatenated features), train-mode BN over all rows
     out2 = tiny["lgp"](ref["fp16"]["feats"].cuda(), torch.cat([lvl] * 2).cuda())
