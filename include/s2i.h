@@ -91,6 +91,25 @@ int s2i_attention_backward(const void* q, long long ldq, int q_c0, const void* k
                            void* dkv, long long lddkv, int dk_c0, int dv_c0, void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * GroupNorm(32 groups) [+ SiLU] of an NHWC fp32 tensor, statistics and apply in ONE launch (thread-block clusters own a
+ * few groups of a sample, exchange their partial sums through distributed shared memory, and apply from the slab they
+ * staged in shared memory): the `norm1/norm2 -> nonlinearity` of every diffusers ResnetBlock2D and the `norm` of every
+ * Transformer2DModel inside `self.unet(...)` (modules/pipeline.py:96), and their part of the autograd backward (:159).
+ *   x, dy, add, dx32: fp32 device [B][HW][ld*]; out16 / raw16 / dx16: fp16 device; gamma, beta: fp32 [C]
+ *   stats: device scratch of B * 512 bytes, zeroed before the forward; the backward reads the forward's and needs its own
+ *   forward : out16 = fp16(act(GN(x))), raw16 (optional) = fp16(x);  act = SiLU when silu != 0
+ *   backward: dx = dGN/dx applied to (dy * act'(GN(x))) (+ add), written as fp32 (dx32) and / or fp16 (dx16)
+ * C must be a multiple of 32 and of 4, every ld a multiple of 4.
+ * --------------------------------------------------------------------------------------------- */
+int s2i_groupnorm_forward(const float* x, long long ldx, int B, int HW, int C, const float* gamma, const float* beta,
+                          float eps, int silu, void* out16, long long ld16, void* raw16, long long ldraw, void* stats,
+                          void* cuda_stream);
+int s2i_groupnorm_backward(const float* dy, long long ldd, const float* x, long long ldx, int B, int HW, int C,
+                           const float* gamma, const float* beta, float eps, int silu, const void* fwd_stats,
+                           void* bwd_stats, const float* add, long long ldadd, float* dx32, long long ld32, void* dx16,
+                           long long ld16, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------
  * UNet2DCondition engine: replaces `self.unet(x, t, encoder_hidden_states=...)` (modules/pipeline.py:96),
  * the 9 forward hooks of hook_unet (modules/latent_predictor.py:47-81) and the UNet part of
  * `torch.autograd.grad(loss, latents_prev)` (modules/pipeline.py:159).

@@ -75,6 +75,10 @@ def lib():
     h.s2i_unet_load.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(vp), ip, C.POINTER(C.c_longlong)]
     h.s2i_unet_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, C.c_int, vp]
     h.s2i_unet_tap.argtypes = [vp, C.c_int, fp, ip, ip, ip, ip]
+    L = C.c_longlong
+    h.s2i_groupnorm_forward.argtypes = [vp, L, C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_int, vp, L, vp, L, vp, vp]
+    h.s2i_groupnorm_backward.argtypes = [vp, L, vp, L, C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp, vp, L,
+                                         vp, L, vp, L, vp]
     h.s2i_unet_backward.argtypes = [vp, C.POINTER(vp), vp, vp]
     h.s2i_unet_backward_samples.argtypes = [vp, C.POINTER(vp), vp, C.c_int, C.c_int, vp]
     h.s2i_unet_load_sat.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(vp), ip, C.POINTER(C.c_longlong)]

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "attn.cuh"
 #include "gemm_tc.cuh"
+#include "kernels.cuh"
 #include "unet.cuh"
 
 #include <cstdlib>
@@ -41,6 +42,26 @@ int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream) {
     return s2i::gemm_launch(s2i::GemmDesc(*d), static_cast<cudaStream_t>(cuda_stream));
 }
 
+
+int s2i_groupnorm_forward(const float* x, long long ldx, int B, int HW, int C, const float* gamma, const float* beta,
+                          float eps, int silu, void* out16, long long ld16, void* raw16, long long ldraw, void* stats,
+                          void* cuda_stream) {
+    if (!x || !gamma || !beta || !out16 || !stats) return s2i::set_error(S2I_ERR_ARG, "s2i_groupnorm_forward: null argument");
+    if (B < 1 || HW < 1 || C < 32) return s2i::set_error(S2I_ERR_ARG, "s2i_groupnorm_forward: empty tensor");
+    return s2i::gn_forward(x, ldx, B, HW, C, static_cast<double*>(stats), gamma, beta, eps, silu, out16, ld16, raw16, ldraw,
+                           static_cast<cudaStream_t>(cuda_stream));
+}
+
+int s2i_groupnorm_backward(const float* dy, long long ldd, const float* x, long long ldx, int B, int HW, int C,
+                           const float* gamma, const float* beta, float eps, int silu, const void* fwd_stats,
+                           void* bwd_stats, const float* add, long long ldadd, float* dx32, long long ld32, void* dx16,
+                           long long ld16, void* cuda_stream) {
+    if (!dy || !x || !gamma || !beta || !fwd_stats || !bwd_stats || (!dx32 && !dx16))
+        return s2i::set_error(S2I_ERR_ARG, "s2i_groupnorm_backward: null argument");
+    if (B < 1 || HW < 1 || C < 32) return s2i::set_error(S2I_ERR_ARG, "s2i_groupnorm_backward: empty tensor");
+    return s2i::gn_backward(dy, ldd, x, ldx, B, HW, C, static_cast<const double*>(fwd_stats), static_cast<double*>(bwd_stats),
+                            gamma, beta, eps, silu, add, ldadd, dx32, ld32, dx16, ld16, static_cast<cudaStream_t>(cuda_stream));
+}
 
 int s2i_attention(const void* q, long long ldq, int q_c0, const void* kv, long long ldkv, int k_c0, int v_c0, int B,
                   int heads, int Nq, int Nk, int dp, int d_true, float scale, void* out, long long ldo, float* lse,

@@ -92,6 +92,27 @@ inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
     g_prev_kernel = true;
 }
+// Same, as thread-block clusters of cluster_x CTAs along x (grid.x must be a multiple of cluster_x).
+template <typename... KArgs, typename... Args>
+inline void launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, int cluster_x, cudaStream_t st,
+                                  Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_x;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (g_pdl && g_prev_kernel) ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    g_prev_kernel = true;
+}
 #define S2I_LAUNCH(kernel, grid, block, smem, stream, ...) \
     ::s2i::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
 #endif

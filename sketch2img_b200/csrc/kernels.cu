@@ -5,7 +5,9 @@
 
 #include <cuda_fp16.h>
 #include <math.h>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 
 namespace s2i {
 
@@ -537,6 +539,281 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const GnFusedArgs a) {
     }
 }
 
+// ---- cluster form: statistics + apply in one launch, no grid-wide barrier --------------------------------------------
+// One thread-block CLUSTER owns `gpc` consecutive groups of one sample (W = gpc * C/32 channels, a column slab of the
+// NHWC tensor); its `cs` CTAs split the pixels.  Each CTA reduces its [P pixels][W channels] slab from registers
+// (float4 loads, 8 in flight per thread) while staging it in shared memory, the per-group sums are exchanged through
+// distributed shared memory in rank order (deterministic), and the apply phase reads the slab back from shared memory:
+// x (and dy) cross the L2 -> SM path once.  When the slab does not fit (cached = 0) the apply phase re-reads global.
+struct GnClArgs {
+    const float* x; long ldx;
+    const float* dy; long ldd;               // backward only
+    int HW, C, Cg, gpc, W, P, cs, cached;
+    const double* fslot;                     // backward: the forward statistics slot
+    const float* gamma; const float* beta;
+    float eps; int silu;
+    double* slot;
+    __half* out16; long ld16; __half* raw16; long ldraw;            // forward outputs
+    const float* add; long ldadd; float* dx32; long ld32;           // backward outputs (dx16 = out16 / ld16)
+};
+constexpr int kGnClT = 512;          // threads per CTA
+constexpr int kGnClColp = 4096;      // floats: [2][prow][W] per-(pixel-lane, channel) partials, prow * W <= 2048
+constexpr int kGnClRed = 2048;       // floats: [SUB][2 W] second-stage partials (W <= 1024)
+constexpr int kGnClMaxW = 1024;
+
+__device__ __forceinline__ void cluster_arrive_() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ double ld_cluster_f64(const double* local, uint32_t rank) {
+    const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
+    uint32_t ra;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kGnClT) gn_cluster_kernel(const GnClArgs a) {
+    extern __shared__ __align__(16) float gsm[];
+    float* colp = gsm;
+    float* red2 = gsm + kGnClColp;
+    float* slab = gsm + kGnClColp + kGnClRed;     // MODE 0: x [P][W];  MODE 1: xhat [P][W] then dxhat [P][W]
+    __shared__ double part[2 * kGroups];
+    __shared__ float s_mean[kGroups], s_rstd[kGroups], s_m1[kGroups], s_m2[kGroups];
+    pdl_wait();
+    pdl_launch();
+    const int t = threadIdx.x, b = blockIdx.y;
+    const int cs = a.cs;
+    const int rank = blockIdx.x % cs;             // == %cluster_ctarank (clusters are 1-D along x)
+    const int chunk = blockIdx.x / cs;
+    const int W = a.W, Wq = W >> 2, Cg = a.Cg, gpc = a.gpc;
+    const int c0 = chunk * W, g0 = chunk * gpc;
+    const int p0 = rank * a.P, p1 = min(a.HW, p0 + a.P);
+    const int prow = kGnClT / Wq;
+    const int r = t / Wq, q = t - r * Wq;
+    const bool active = r < prow;
+    const int c = c0 + 4 * q;
+    const long slabN = (long)a.P * W;
+    int gl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gl[j] = (4 * q + j) / Cg;
+    float gm[4], bt[4], mu[4], rs[4];
+    if (MODE == 1) {
+        if (t < gpc) {
+            const float2 v = reinterpret_cast<const float2*>(a.fslot + (long)b * kSlotDoubles)[g0 + t];
+            s_mean[t] = v.x;
+            s_rstd[t] = v.y;
+        }
+        __syncthreads();
+    }
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            gm[j] = __ldg(a.gamma + c + j);
+            bt[j] = __ldg(a.beta + c + j);
+            if (MODE == 1) {
+                mu[j] = s_mean[gl[j]];
+                rs[j] = s_rstd[gl[j]];
+            }
+        }
+    }
+    // ---------------- phase 1: slab reduction (and staging)
+    {
+        float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+        constexpr int U = MODE == 0 ? 8 : 4;
+        if (active) {
+            for (int pb = p0 + r; pb < p1; pb += U * prow) {
+                float4 xv[U], dv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int pp = pb + u * prow;
+                    const long row = (long)b * a.HW + (pp < p1 ? pp : pb);
+                    xv[u] = ldg4(a.x + row * a.ldx + c);
+                    if (MODE == 1) dv[u] = ldg4(a.dy + row * a.ldd + c);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int pp = pb + u * prow;
+                    if (pp < p1) {
+                        const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                        if (MODE == 0) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                a1[j] += xs[j];
+                                a2[j] += xs[j] * xs[j];
+                            }
+                            if (a.cached) *reinterpret_cast<float4*>(slab + (long)(pp - p0) * W + 4 * q) = xv[u];
+                        } else {
+                            const float ds[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+                            float xh[4], dxh[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                xh[j] = (xs[j] - mu[j]) * rs[j];
+                                float d = ds[j];
+                                if (a.silu) {
+                                    const float y = xh[j] * gm[j] + bt[j];
+                                    const float sg = sigmoidf_(y);
+                                    d *= sg * (1.f + y * (1.f - sg));
+                                }
+                                dxh[j] = d * gm[j];
+                                a1[j] += dxh[j];
+                                a2[j] += dxh[j] * xh[j];
+                            }
+                            if (a.cached) {
+                                float* sp = slab + (long)(pp - p0) * W + 4 * q;
+                                *reinterpret_cast<float4*>(sp) = make_float4(xh[0], xh[1], xh[2], xh[3]);
+                                *reinterpret_cast<float4*>(sp + slabN) = make_float4(dxh[0], dxh[1], dxh[2], dxh[3]);
+                            }
+                        }
+                    }
+                }
+            }
+            *reinterpret_cast<float4*>(colp + (long)r * W + 4 * q) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+            *reinterpret_cast<float4*>(colp + (long)(prow + r) * W + 4 * q) = make_float4(a2[0], a2[1], a2[2], a2[3]);
+        }
+    }
+    __syncthreads();
+    {   // per-channel sums over the pixel lanes (SUB threads per channel), then per-group sums
+        const int W2 = 2 * W;
+        const int SUB = max(1, kGnClT / W2);
+        for (int idx = t; idx < W2 * SUB; idx += kGnClT) {
+            const int sub = idx / W2, col = idx - sub * W2;
+            const int which = col >= W ? 1 : 0, cc = col - which * W;
+            float acc = 0.f;
+            for (int rr = sub; rr < prow; rr += SUB) acc += colp[(long)(which * prow + rr) * W + cc];
+            red2[idx] = acc;
+        }
+        __syncthreads();
+        if (t < 2 * gpc) {
+            const int g = t >> 1, which = t & 1;
+            float acc0 = 0.f, acc1 = 0.f;
+            for (int sub = 0; sub < SUB; ++sub) {
+                const float* src = red2 + (long)sub * W2 + which * W + g * Cg;
+                for (int j = 0; j + 1 < Cg; j += 2) {
+                    acc0 += src[j];
+                    acc1 += src[j + 1];
+                }
+                if (Cg & 1) acc0 += src[Cg - 1];
+            }
+            part[t] = (double)acc0 + (double)acc1;
+        }
+    }
+    // ---------------- cluster-wide totals through distributed shared memory, rank order
+    cluster_arrive_();
+    cluster_wait_();
+    if (t < 64) {
+        double tot = 0.0;
+        if (t < 2 * gpc)
+            for (int rk = 0; rk < cs; ++rk) tot += ld_cluster_f64(&part[t], (uint32_t)rk);
+        const double other = __shfl_down_sync(0xffffffffu, tot, 1);
+        if (t < 2 * gpc && !(t & 1)) {
+            const int g = t >> 1;
+            const double n = (double)Cg * a.HW;
+            float2 o;
+            if (MODE == 0) {
+                const double m = tot / n;
+                double var = other / n - m * m;
+                if (var < 0.0) var = 0.0;
+                o.x = (float)m;
+                o.y = (float)(1.0 / sqrt(var + (double)a.eps));
+                s_mean[g] = o.x;
+                s_rstd[g] = o.y;
+            } else {
+                o.x = (float)(tot / n);
+                o.y = (float)(other / n);
+                s_m1[g] = o.x;
+                s_m2[g] = o.y;
+            }
+            if (rank == 0) reinterpret_cast<float2*>(a.slot + (long)b * kSlotDoubles)[g0 + g] = o;
+        }
+    }
+    cluster_arrive_();        // this CTA is done reading its peers' shared memory (matching wait before exit)
+    __syncthreads();
+    // ---------------- phase 2: apply
+    if (active) {
+        constexpr int U2 = 4;
+        float k0[4], k1[4], k2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (MODE == 0) {
+                k0[j] = s_mean[gl[j]];
+                k1[j] = s_rstd[gl[j]] * gm[j];
+                k2[j] = bt[j];
+            } else {
+                k0[j] = s_m1[gl[j]];
+                k1[j] = s_m2[gl[j]];
+                k2[j] = rs[j];
+            }
+        }
+        for (int pb = p0 + r; pb < p1; pb += U2 * prow) {
+            float4 v0[U2], v1[U2], av[U2];
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+                const int pp = pb + u * prow;
+                const int pc = pp < p1 ? pp : pb;
+                const long row = (long)b * a.HW + pc;
+                if (a.cached) {
+                    const float* sp = slab + (long)(pc - p0) * W + 4 * q;
+                    v0[u] = *reinterpret_cast<const float4*>(sp);
+                    if (MODE == 1) v1[u] = *reinterpret_cast<const float4*>(sp + slabN);
+                } else {
+                    v0[u] = ldg4(a.x + row * a.ldx + c);
+                    if (MODE == 1) v1[u] = ldg4(a.dy + row * a.ldd + c);
+                }
+                if (MODE == 1) av[u] = a.add ? ldg4(a.add + row * a.ldadd + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+                const int pp = pb + u * prow;
+                if (pp >= p1) continue;
+                const long row = (long)b * a.HW + pp;
+                const float xs[4] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w};
+                if (MODE == 0) {
+                    float y[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v = (xs[j] - k0[j]) * k1[j] + k2[j];
+                        if (a.silu) v = v * sigmoidf_(v);
+                        y[j] = v;
+                    }
+                    *reinterpret_cast<uint2*>(a.out16 + row * a.ld16 + c) = pack_half4(y[0], y[1], y[2], y[3]);
+                    if (a.raw16) *reinterpret_cast<uint2*>(a.raw16 + row * a.ldraw + c) = pack_half4(xs[0], xs[1], xs[2], xs[3]);
+                } else {
+                    float xh[4], dxh[4];
+                    if (a.cached) {
+                        const float ds[4] = {v1[u].x, v1[u].y, v1[u].z, v1[u].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            xh[j] = xs[j];
+                            dxh[j] = ds[j];
+                        }
+                    } else {
+                        const float ds[4] = {v1[u].x, v1[u].y, v1[u].z, v1[u].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            xh[j] = (xs[j] - mu[j]) * rs[j];
+                            float d = ds[j];
+                            if (a.silu) {
+                                const float y = xh[j] * gm[j] + bt[j];
+                                const float sg = sigmoidf_(y);
+                                d *= sg * (1.f + y * (1.f - sg));
+                            }
+                            dxh[j] = d * gm[j];
+                        }
+                    }
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = k2[j] * (dxh[j] - k0[j] - xh[j] * k1[j]);
+                    o[0] += av[u].x; o[1] += av[u].y; o[2] += av[u].z; o[3] += av[u].w;
+                    if (a.dx32) *reinterpret_cast<float4*>(a.dx32 + row * a.ld32 + c) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (a.out16) *reinterpret_cast<uint2*>(a.out16 + row * a.ld16 + c) = pack_half4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+    cluster_wait_();
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, long ldx, long rows, int C,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -1000,6 +1277,107 @@ int gn_bwd_apply(const float* dy, long ldd, const float* x, long ldx, int B, int
     return 0;
 }
 
+// ---- cluster launchers (see gn_cluster_kernel)
+static int g_gn_cluster = -1;        // S2I_GN_CLUSTER=0 in the environment selects the grid-barrier form instead
+static const size_t kGnClSmemMax = 200 * 1024;
+static int gn_cluster_prepare();
+// How many clusters of `cs` CTAs with `smem` bytes each the device keeps resident at once (the launch's wave size).
+// Measured on B200: 8-CTA clusters of this kernel reach 15, 4-CTA clusters 32+ -- large clusters leave SMs idle.
+template <int MODE>
+static int gn_cluster_capacity(int cs, size_t smem) {
+    static std::map<long, int> cache;
+    const long key = ((long)cs << 32) | (long)(smem >> 10);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs * 64, 1, 1);
+    cfg.blockDim = dim3(kGnClT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gn_cluster_kernel<MODE>, &cfg) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = cs <= 4 ? 128 / cs : 8;      // what B200 gave when this was written
+    }
+    cache[key] = n;
+    return n;
+}
+// Picks groups per cluster (gpc), CTAs per cluster (cs) and whether the slab is staged in shared memory with a small
+// cost model fitted to tools/gn_bench.py --sweep:  waves x (fixed + slab elements per CTA, x1.25 when the apply phase
+// re-reads global memory), with rows shorter than 128 bytes charged for their wasted sectors.
+static bool gn_cluster_geometry(int B, int HW, int C, int mode, GnClArgs* out, size_t* smem) {
+    if (g_gn_cluster < 0) {
+        const char* e = getenv("S2I_GN_CLUSTER");
+        g_gn_cluster = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (!g_gn_cluster || C % kGroups) return false;
+    if (gn_cluster_prepare() != 0) return false;
+    // tools/gn_bench.py --sweep: S2I_GN_GEOM="gpc,cs" forces one geometry (ignored when it is not legal for the shape)
+    int f_gpc = 0, f_cs = 0;
+    if (const char* e = getenv("S2I_GN_GEOM")) sscanf(e, "%d,%d", &f_gpc, &f_cs);
+    struct Choice { GnClArgs a; size_t smem; bool ok; };
+    static std::map<long, Choice> decided;
+    const long key = ((long)B << 48) ^ ((long)HW << 24) ^ ((long)C << 4) ^ (long)mode;
+    if (!f_gpc && !f_cs) {
+        auto it = decided.find(key);
+        if (it != decided.end()) {
+            *out = it->second.a;
+            *smem = it->second.smem;
+            return it->second.ok;
+        }
+    }
+    const int Cg = C / kGroups;
+    double best = 1e30;
+    bool found = false;
+    const size_t fixed = (size_t)(kGnClColp + kGnClRed) * sizeof(float);
+    for (int gpc = 1; gpc <= kGroups; gpc *= 2) {
+        const int W = gpc * Cg;
+        if (W % 4 || W > kGnClMaxW) continue;
+        if (f_gpc && gpc != f_gpc) continue;
+        for (int cs = 1; cs <= 16; cs *= 2) {
+            if (f_cs ? cs != f_cs : cs > 8) continue;
+            const int P = ceil_div(HW, cs);
+            const double elems = (double)P * W * (mode ? 2 : 1);
+            const size_t slab = (size_t)P * W * sizeof(float) * (mode ? 2 : 1);
+            const bool fits = fixed + slab <= kGnClSmemMax;
+            const size_t need = fixed + (fits ? slab : 0);
+            const long clusters = (long)B * (kGroups / gpc);
+            const int cap = mode ? gn_cluster_capacity<1>(cs, need) : gn_cluster_capacity<0>(cs, need);
+            const double waves = (double)((clusters + cap - 1) / cap);
+            double cost = waves * (25000.0 + elems * (fits ? 1.0 : 1.25));
+            if (W * 4 < 128) cost *= 1.0 + (128 - W * 4) / 256.0;      // short rows waste sectors
+            if (cost < best) {
+                best = cost;
+                found = true;
+                memset(out, 0, sizeof(*out));
+                out->HW = HW; out->C = C; out->Cg = Cg; out->gpc = gpc; out->W = W; out->P = P; out->cs = cs;
+                out->cached = fits ? 1 : 0;
+                *smem = need;
+            }
+        }
+    }
+    if (!f_gpc && !f_cs) decided[key] = Choice{*out, *smem, found};
+    return found;
+}
+static int gn_cluster_prepare() {
+    static int dev_done = -1;
+    int dev = 0;
+    S2I_CUDA(cudaGetDevice(&dev));
+    if (dev_done == dev) return 0;
+    S2I_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnClSmemMax));
+    S2I_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGnClSmemMax));
+    S2I_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    S2I_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    dev_done = dev;
+    return 0;
+}
+
 // ---- fused launchers (see gn_fused_kernel); fall back to the two-kernel form when the batch exceeds the SM count
 static bool gn_fused_geometry(int B, int HW, int C, int* nblk, int* P) {
     if (B > kNumSMs || C > 2560) return false;
@@ -1015,6 +1393,17 @@ static bool gn_fused_geometry(int B, int HW, int C, int* nblk, int* P) {
 int gn_forward(const float* x, long ldx, int B, int HW, int C, double* slot, const float* gamma, const float* beta, float eps,
                int silu, void* out16, long ld16, void* raw16, long ldraw, cudaStream_t st) {
     S2I_REQ(C % 4 == 0 && C % kGroups == 0 && (ldx & 3) == 0 && (ld16 & 3) == 0 && (ldraw & 3) == 0, "gn_forward: alignment");
+    GnClArgs ca;
+    size_t csmem;
+    if (gn_cluster_geometry(B, HW, C, 0, &ca, &csmem)) {
+        ca.x = x; ca.ldx = ldx;
+        ca.gamma = gamma; ca.beta = beta; ca.eps = eps; ca.silu = silu;
+        ca.slot = slot;
+        ca.out16 = (__half*)out16; ca.ld16 = ld16; ca.raw16 = (__half*)raw16; ca.ldraw = ldraw;
+        launch_kernel_cluster(gn_cluster_kernel<0>, dim3((32 / ca.gpc) * ca.cs, B), dim3(kGnClT), csmem, ca.cs, st, ca);
+        S2I_LAUNCH_CHECK();
+        return 0;
+    }
     int nblk, P;
     if (!gn_fused_geometry(B, HW, C, &nblk, &P)) {
         S2I_TRY(gn_stats(x, ldx, B, HW, C, eps, slot, st));
@@ -1037,6 +1426,18 @@ int gn_backward(const float* dy, long ldd, const float* x, long ldx, int B, int 
                 long ld32, void* dx16, long ld16, cudaStream_t st) {
     S2I_REQ(C % 4 == 0 && C % kGroups == 0 && (ldx & 3) == 0 && (ldd & 3) == 0 && (ldadd & 3) == 0 && (ld32 & 3) == 0 &&
                 (ld16 & 3) == 0, "gn_backward: alignment");
+    GnClArgs ca;
+    size_t csmem;
+    if (gn_cluster_geometry(B, HW, C, 1, &ca, &csmem)) {
+        ca.x = x; ca.ldx = ldx; ca.dy = dy; ca.ldd = ldd;
+        ca.fslot = fslot;
+        ca.gamma = gamma; ca.beta = beta; ca.eps = eps; ca.silu = silu;
+        ca.slot = bslot;
+        ca.add = add; ca.ldadd = ldadd; ca.dx32 = dx32; ca.ld32 = ld32; ca.out16 = (__half*)dx16; ca.ld16 = ld16;
+        launch_kernel_cluster(gn_cluster_kernel<1>, dim3((32 / ca.gpc) * ca.cs, B), dim3(kGnClT), csmem, ca.cs, st, ca);
+        S2I_LAUNCH_CHECK();
+        return 0;
+    }
     int nblk, P;
     if (!gn_fused_geometry(B, HW, C, &nblk, &P)) {
         S2I_TRY(gn_bwd_stats(dy, ldd, x, ldx, B, HW, C, fslot, gamma, beta, eps, silu, bslot, st));
