@@ -201,6 +201,15 @@ int s2i_lgp_loss_backward_cond(s2i_lgp* l, const float* target, float* const* ta
 int s2i_cfg_ddim_step(const float* latents, const float* eps, int S, int n, float guidance_scale, float sqrt_one_minus_a_t,
                       float sqrt_a_t, float sqrt_a_prev, float sqrt_one_minus_a_prev, int prediction, float* out,
                       void* cuda_stream);
+/* CFG combine + one DPM-Solver++(2M, midpoint) update: diffusers DPMSolverMultistepScheduler.step as the reference's demo
+ * configures it (app.py:14-25; called at modules/pipeline.py:104).  The host passes the step's fp32 scalars
+ *   alpha_t, sigma_t (current timestep), c_x = sigma_prev / sigma_t, c_m0 = alpha_prev (exp(-h) - 1), c_d1 = 0.5 c_m0,
+ *   inv_r0 = 1 / r0,  h = lambda_prev - lambda_t, r0 = (lambda_t - lambda_before) / h, lambda = log alpha - log sigma;
+ *   m0 = x0 prediction; order 1: out = c_x x - c_m0 m0;  order 2: out = (c_x x - c_m0 m0) - c_d1 (inv_r0 (m0 - m1)).
+ * x0_history [S][n]: the previous step's x0 prediction on entry (read when order == 2), this step's on return. */
+int s2i_cfg_dpmpp_step(const float* latents, const float* eps, float* x0_history, int S, int n, float guidance_scale,
+                       float alpha_t, float sigma_t, float c_x, float c_m0, float c_d1, float inv_r0, int order, int prediction,
+                       float* out, void* cuda_stream);
 /* x_new += beta * ||[x_old,x_old] - x_new||_F / ||g||_F * g,  g = -dx[cond]; scratch: device double [S][2] */
 int s2i_guidance_update(const float* x_old, float* x_new, const float* dx, int S, int n, float beta, double* scratch,
                         void* cuda_stream);
@@ -221,6 +230,14 @@ int s2i_sampler_step(s2i_sampler* s, float* latents, const float* noise, const f
                      int L, float t, float guidance_scale, float sqrt_a_t, float sqrt_one_minus_a_t, float sqrt_a_prev,
                      float sqrt_one_minus_a_prev, int prediction, int guided, float sigma, float beta, int lgp_train,
                      float* loss_out, void* cuda_stream);
+/* The same loop body when `self.scheduler` is the demo's DPM-Solver++(2M) scheduler (app.py:14-25): the scheduler.step of
+ * modules/pipeline.py:104 becomes s2i_cfg_dpmpp_step (scalars as documented there; the LGP noise level of :133 is sigma_t);
+ * the guidance update of :109 edits the latents AFTER the solver update, exactly like the reference (the multistep history
+ * keeps the unedited x0 predictions).  x0_history [S][4][L][L]: caller-owned, carried from step to step of an image. */
+int s2i_sampler_step_dpmpp(s2i_sampler* s, float* latents, const float* noise, const float* ctx, const float* target,
+                           float* x0_history, int S, int L, float t, float guidance_scale, float alpha_t, float sigma_t,
+                           float c_x, float c_m0, float c_d1, float inv_r0, int order, int prediction, int guided, float beta,
+                           int lgp_train, float* loss_out, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,7 @@ top of oracle/diffusers_shim, on CPU, with the seeded synthetic weights/inputs o
 stores the per-step latents it reports through ``callback`` (pipeline.py:112-115).  Only runnable in the
 authoring container (needs /root/reference); the fixtures it writes travel with the repo.
 
-    python oracle/make_golden.py tiny 4 tiny 50 sd15 4 sd15 50
+    python oracle/make_golden.py tiny 4 tiny 50 sd15 4 sd15 50 tiny@dpmpp 4 tiny@dpmpp 20
 """
 import os
 import sys
@@ -21,7 +21,7 @@ from oracle import port  # noqa: E402
 REF = "/root/reference"
 
 
-def run_reference(name, steps, guidance_scale=7.5, seed=port.SAMPLE_SEED, guided=True, latent_scale=1.0):
+def run_reference(name, steps, guidance_scale=7.5, seed=port.SAMPLE_SEED, guided=True, latent_scale=1.0, kind="ddim"):
     if REF not in sys.path:
         sys.path.insert(0, REF)
     from modules.latent_predictor import LatentEdgePredictor
@@ -33,7 +33,16 @@ def run_reference(name, steps, guidance_scale=7.5, seed=port.SAMPLE_SEED, guided
     lgp = LatentEdgePredictor(port.lgp_input_dim(unet), 4, port.NUM_POS_LAYERS)
     lgp.load_state_dict(lgp_o.float().state_dict())
     lgp.half()
-    pipe = AntiGradientPipeline(unet=unet, scheduler=port.make_scheduler())
+    if kind == "dpmpp":
+        # the demo's scheduler, constructed with the reference's own keyword arguments (app.py:14-25)
+        from diffusers import DPMSolverMultistepScheduler
+        sched = DPMSolverMultistepScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                            num_train_timesteps=1000, trained_betas=None, predict_epsilon=True,
+                                            thresholding=False, algorithm_type="dpmsolver++", solver_type="midpoint",
+                                            lower_order_final=True)
+    else:
+        sched = port.make_scheduler()
+    pipe = AntiGradientPipeline(unet=unet, scheduler=sched)
     pipe.set_prompt_embeds(emb)
     pipe.setup_lgp(lgp)
     per_step = {}
@@ -86,26 +95,28 @@ def main(argv):
     pairs = list(zip(argv[0::2], argv[1::2]))
     for name, steps in pairs:
         steps = int(steps)
-        per_step, dt = run_reference(name, steps)
+        name, _, kind = name.partition("@")          # "tiny@dpmpp": the demo's DPM-Solver++(2M) instead of DDIM
+        kind = kind or "ddim"
+        per_step, dt = run_reference(name, steps, kind=kind)
         keep = sorted(set(list(range(0, steps, max(1, steps // 10))) + [steps - 1]))
         # The guided loop is chaotic (DESIGN.md "Conditioning"): the SAME reference files, started from latents scaled
         # by (1 + 1e-6), drift away from the run above.  That drift is the noise floor any other implementation is
         # measured against.  The unguided run (sketch_image=None: plain CFG + DDIM) is smooth and pins the UNet +
         # scheduler over the full schedule.
-        pert, _ = run_reference(name, steps, latent_scale=1.0 + 1e-6)
+        pert, _ = run_reference(name, steps, latent_scale=1.0 + 1e-6, kind=kind)
         rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()
-        unguided, dt_u = run_reference(name, steps, guided=False)
+        unguided, dt_u = run_reference(name, steps, guided=False, kind=kind)
         blob = {
             "self_sensitivity": torch.tensor([rel(pert[i], per_step[i]) for i in range(steps)]),
             "unguided_latents": {i: unguided[i] for i in keep}, "unguided_cpu_seconds": dt_u,
-            "config": name, "steps": steps, "guidance_scale": 7.5, "beta": 1.6,
+            "config": name, "steps": steps, "guidance_scale": 7.5, "beta": 1.6, "scheduler": kind,
             "weight_seed": port.WEIGHT_SEED, "sample_seed": port.SAMPLE_SEED,
             "latents": {i: per_step[i] for i in keep},
             "norms": torch.tensor([per_step[i].norm().item() for i in range(steps)]),
             "cpu_seconds": dt, "cpu_threads": torch.get_num_threads(),
             "source": "reference modules/pipeline.py + latent_predictor.py over oracle/diffusers_shim",
         }
-        path = os.path.join(out_dir, f"{name}_{steps}step.pt")
+        path = os.path.join(out_dir, f"{name}_{steps}step.pt" if kind == "ddim" else f"{name}_{kind}_{steps}step.pt")
         torch.save(blob, path)
         print(f"{name} {steps} steps: {dt:.1f}s  final norm {per_step[steps - 1].norm():.4f} -> {path}", flush=True)
 

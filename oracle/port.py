@@ -12,6 +12,7 @@ arithmetic of diffusers' UNet/DDIM lives in an un-vendored dependency restated i
 oracle/diffusers_shim from SURVEY.md Appendix A.  => pinned against the reference's own Python files
 run here; "parity unpinned" with respect to genuine diffusers + real checkpoints.
 """
+import inspect
 import math
 import os
 import sys
@@ -29,7 +30,7 @@ def add_shim_to_path():
 
 
 add_shim_to_path()
-from diffusers import DDIMScheduler, UNet2DConditionModel  # noqa: E402  (the shim)
+from diffusers import DDIMScheduler, DPMSolverMultistepScheduler, UNet2DConditionModel  # noqa: E402  (the shim)
 from diffusers.models.unet_2d_condition import SD15_CONFIG, SD21_CONFIG, TINY_CONFIG  # noqa: E402,F401
 
 LGP_HIDDEN = (512, 256, 128, 64)
@@ -173,7 +174,8 @@ def guided_sample(unet, lgp, scheduler, text_emb, latents, target, num_steps=50,
             eps = unet(x_in, t, encoder_hidden_states=text_emb).sample      # :96
         eps_u, eps_c = eps.chunk(2)                                         # :100
         eps = eps_u + guidance_scale * (eps_c - eps_u)                      # :101
-        latents = scheduler.step(eps, t, latents, eta=0.0).prev_sample      # :104
+        extra = {"eta": 0.0} if "eta" in inspect.signature(scheduler.step).parameters else {}           # :78
+        latents = scheduler.step(eps, t, latents, **extra).prev_sample      # :104
         if guided:
             with torch.enable_grad():
                 latents = anti_gradient(lgp, scheduler, taps, x_in, latents, noise, t, target, beta)  # :109
@@ -227,7 +229,14 @@ def make_inputs(unet, seed=SAMPLE_SEED):
     return latents, emb, target
 
 
-def make_scheduler(prediction_type="epsilon"):
+def make_scheduler(prediction_type="epsilon", kind="ddim"):
+    """kind "ddim": BASELINE.json's scheduler; "dpmpp": the demo's DPM-Solver++(2M) exactly as /root/reference/app.py:14-25
+    constructs it."""
+    if kind == "dpmpp":
+        return DPMSolverMultistepScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                           num_train_timesteps=1000, trained_betas=None, prediction_type=prediction_type,
+                                           thresholding=False, algorithm_type="dpmsolver++", solver_type="midpoint",
+                                           lower_order_final=True)
     return DDIMScheduler(prediction_type=prediction_type)
 
 

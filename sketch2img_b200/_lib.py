@@ -107,6 +107,9 @@ def lib():
     h.s2i_sampler_destroy.restype = None
     h.s2i_sampler_step.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, f, f, f, f, f, f, C.c_int, C.c_int, f, f,
                                    C.c_int, vp, vp]
+    h.s2i_cfg_dpmpp_step.argtypes = [vp, vp, vp, C.c_int, C.c_int, f, f, f, f, f, f, f, C.c_int, C.c_int, vp, vp]
+    h.s2i_sampler_step_dpmpp.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, f, f, f, f, f, f, f, f, C.c_int, C.c_int,
+                                         C.c_int, f, C.c_int, vp, vp]
     _lib = h
     return h
 

@@ -439,6 +439,44 @@ __global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* __restrict__
     }
 }
 
+// CFG combine + one DPM-Solver++ multistep update (diffusers DPMSolverMultistepScheduler.step, algorithm "dpmsolver++",
+// midpoint, thresholding off -- the scheduler the reference's demo constructs at app.py:14-25), in diffusers' rounding
+// order: m0 = x0 prediction; first order  x' = A x - Bc m0;  second order  x' = (A x - Bc m0) - Cc (R (m0 - m1)).
+// hist holds the previous step's x0 prediction (m1) on entry and this step's (m0) on exit.
+// dparams (device float[8]): sigma_t, alpha_t, A, Bc, (unused), Cc, R.
+__global__ void __launch_bounds__(256) cfg_dpmpp_kernel(const float* __restrict__ x, const float* __restrict__ eps, int S,
+                                                        int n, float g, float sigma_t, float alpha_t, float A, float Bc,
+                                                        float Cc, float R, const float* __restrict__ dparams, int prediction,
+                                                        int order, float* __restrict__ hist, float* __restrict__ out) {
+    pdl_wait();
+    pdl_launch();
+    if (dparams) {
+        sigma_t = __ldg(dparams + 0);
+        alpha_t = __ldg(dparams + 1);
+        A = __ldg(dparams + 2);
+        Bc = __ldg(dparams + 3);
+        Cc = __ldg(dparams + 5);
+        R = __ldg(dparams + 6);
+    }
+    const long total = (long)S * n;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long s = idx / n, i = idx - s * n;
+        const float eu = eps[(2 * s) * (long)n + i], ec = eps[(2 * s + 1) * (long)n + i];
+        const float e = __fadd_rn(eu, __fmul_rn(g, __fsub_rn(ec, eu)));
+        const float xv = x[idx];
+        float m0;
+        if (prediction == 0) m0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(sigma_t, e)), alpha_t);
+        else m0 = __fsub_rn(__fmul_rn(alpha_t, xv), __fmul_rn(sigma_t, e));
+        float r = __fsub_rn(__fmul_rn(A, xv), __fmul_rn(Bc, m0));
+        if (order == 2) {
+            const float d1 = __fmul_rn(R, __fsub_rn(m0, hist[idx]));
+            r = __fsub_rn(r, __fmul_rn(Cc, d1));
+        }
+        hist[idx] = m0;
+        out[idx] = r;
+    }
+}
+
 __global__ void __launch_bounds__(256) guidance_norms_kernel(const float* __restrict__ x_old,
                                                              const float* __restrict__ x_new,
                                                              const float* __restrict__ dx, int n,
@@ -829,6 +867,15 @@ int cfg_ddim_step(const float* latents, const float* eps, int S, int n, float gu
                   float sa_p, float sb_p, int prediction, float* out, cudaStream_t st, const float* dparams) {
     S2I_LAUNCH((cfg_ddim_kernel), grid1d((long)S * n), 256, 0, st, latents, eps, S, n, guidance, sb_t, sa_t, sa_p, sb_p, dparams,
                                                          prediction, out);
+    S2I_LAUNCH_CHECK();
+    return 0;
+}
+
+int cfg_dpmpp_step(const float* latents, const float* eps, float* x0_hist, int S, int n, float guidance, float sigma_t,
+                   float alpha_t, float A, float Bc, float Cc, float R, int prediction, int order, float* out, cudaStream_t st,
+                   const float* dparams) {
+    S2I_LAUNCH((cfg_dpmpp_kernel), grid1d((long)S * n), 256, 0, st, latents, eps, S, n, guidance, sigma_t, alpha_t, A, Bc, Cc, R,
+                                                          dparams, prediction, order, x0_hist, out);
     S2I_LAUNCH_CHECK();
     return 0;
 }

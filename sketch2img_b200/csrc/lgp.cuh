@@ -92,6 +92,13 @@ class LGP {
 // dparams (optional, device float[4] = sb_t, sa_t, sa_p, sb_p): overrides the by-value coefficients (graph-replayed steps).
 int cfg_ddim_step(const float* latents, const float* eps, int S, int n, float guidance, float sb_t, float sa_t,
                   float sa_p, float sb_p, int prediction, float* out, cudaStream_t st, const float* dparams = nullptr);
+// CFG combine + DPM-Solver++(2M, midpoint) update, the scheduler of the reference's demo (app.py:14-25).  The host supplies
+// the step's fp32 scalars: sigma_t / alpha_t of the current timestep, A = sigma_prev / sigma_t, Bc = alpha_prev (exp(-h) - 1),
+// Cc = 0.5 Bc, R = 1 / r0.  x0_hist [S][n]: previous x0 prediction in (second order), this step's out.  order: 1 | 2.
+// dparams (optional, device float[8] = sigma_t, alpha_t, A, Bc, -, Cc, R): overrides the by-value scalars.
+int cfg_dpmpp_step(const float* latents, const float* eps, float* x0_hist, int S, int n, float guidance, float sigma_t,
+                   float alpha_t, float A, float Bc, float Cc, float R, int prediction, int order, float* out, cudaStream_t st,
+                   const float* dparams = nullptr);
 // x_new += beta * ||x_in - x_new||_F / ||g||_F * g with g = -dx[cond half]; norms per sample; x_in = [x_old, x_old].
 // dx: [2*S][n], or [S][n] holding only the cond halves (dx_cond_only).  scratch: double [S][2] device.
 int guidance_update(const float* x_old, float* x_new, const float* dx, int S, int n, float beta, double* scratch,

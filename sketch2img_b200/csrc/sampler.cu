@@ -41,15 +41,26 @@ class Sampler {
     // the kernels read from a small device buffer.  The remaining ~400 (unguided) / ~900 (guided) launches are identical
     // from step to step -- same kernels, same arena addresses -- so the second call with the same arguments captures
     // them into a CUDA graph and later calls replay it (no host launch cost, no inter-kernel gaps).
-    int step(float* latents, const float* noise, const float* ctx, const float* target, int S, int L, float t,
-             float guidance, float sa_t, float sb_t, float sa_p, float sb_p, int prediction, int guided, float sigma,
-             float beta, int lgp_train, float* loss_out, cudaStream_t st) {
-        const bool do_guide = guided && target != nullptr && lgp != nullptr;
+    struct StepArgs {
+        int solver = 0;          // 0: DDIM (eta 0);  1: DPM-Solver++ multistep, midpoint (the demo's scheduler, app.py:14-25)
+        int order = 1;           // multistep: 1 = first-order update (first step / lower_order_final), 2 = second order
+        float t = 0.f, guidance = 1.f;
+        float sa_t = 1.f, sb_t = 0.f, sa_p = 1.f, sb_p = 0.f;   // sqrt(abar_t), sqrt(1 - abar_t) [= alpha_t, sigma_t], same at t_prev
+        float A = 0.f, Bc = 0.f, Cc = 0.f, R = 0.f;             // multistep scalars (see cfg_dpmpp_step)
+        int prediction = 0, guided = 0;
+        float sigma = 0.f, beta = 1.6f;
+        int lgp_train = 1;
+    };
+    int step(float* latents, const float* noise, const float* ctx, const float* target, float* x0_hist, int S, int L,
+             const StepArgs& a, float* loss_out, cudaStream_t st) {
+        const bool do_guide = a.guided && target != nullptr && lgp != nullptr;
+        if (a.solver == 1 && !x0_hist) return set_error(S2I_ERR_ARG, "sampler: the multistep solver needs its x0 history buffer");
         S2I_TRY(ensure_params());
         float* hp = h_sp_ + (ring_++ % kRing) * 8;
-        hp[0] = sb_t; hp[1] = sa_t; hp[2] = sa_p; hp[3] = sb_p; hp[4] = sigma;
+        hp[0] = a.sb_t; hp[1] = a.sa_t; hp[2] = a.solver ? a.A : a.sa_p; hp[3] = a.solver ? a.Bc : a.sb_p; hp[4] = a.sigma;
+        hp[5] = a.Cc; hp[6] = a.R; hp[7] = 0.f;
         S2I_MEMOP(cudaMemcpyAsync(d_sp_, hp, 8 * sizeof(float), cudaMemcpyHostToDevice, st));
-        S2I_TRY(unet->prepare_time(t, st));
+        S2I_TRY(unet->prepare_time(a.t, st));
 
         // The text context is constant over the steps of an image: after the first step that saw it (context_changed()
         // or a new ctx pointer / sample count marks a new one) the cross-attention K/V projections are reused.
@@ -58,30 +69,32 @@ class Sampler {
         last_S_ = S;
         const int reuse = ctx_fresh_ ? 0 : 1;
         ctx_fresh_ = false;
-        Key key{S, L, prediction, do_guide ? 1 : 0, lgp_train, reuse, guidance, beta};
+        Key key{S, L, a.prediction, do_guide ? 1 : 0, a.lgp_train, reuse, a.solver, a.solver ? a.order : 0, a.guidance, a.beta};
         // The replayed part works on sampler-owned copies of the caller's tensors, so one graph serves every image.
         S2I_TRY(layout(key));
         const size_t nb = (size_t)S * unet->cfg.in_ch * L * L * sizeof(float);
         S2I_MEMOP(cudaMemcpyAsync(own_lat_, latents, nb, cudaMemcpyDeviceToDevice, st));
         S2I_MEMOP(cudaMemcpyAsync(own_ctx_, ctx, (size_t)2 * S * unet->cfg.ctx_len * unet->cfg.cross_dim * sizeof(float),
                                  cudaMemcpyDeviceToDevice, st));
+        if (a.solver == 1 && a.order == 2) S2I_MEMOP(cudaMemcpyAsync(own_x0_, x0_hist, nb, cudaMemcpyDeviceToDevice, st));
         if (do_guide) {
             S2I_MEMOP(cudaMemcpyAsync(own_noise_, noise, nb, cudaMemcpyDeviceToDevice, st));
             S2I_MEMOP(cudaMemcpyAsync(own_target_, target, nb, cudaMemcpyDeviceToDevice, st));
         }
         S2I_TRY(run(key, st));
         S2I_MEMOP(cudaMemcpyAsync(latents, own_lat_, nb, cudaMemcpyDeviceToDevice, st));
+        if (a.solver == 1) S2I_MEMOP(cudaMemcpyAsync(x0_hist, own_x0_, nb, cudaMemcpyDeviceToDevice, st));
         if (do_guide && loss_out) S2I_MEMOP(cudaMemcpyAsync(loss_out, own_loss_, S * sizeof(float), cudaMemcpyDeviceToDevice, st));
         return 0;
     }
 
   private:
     struct Key {
-        int S, L, prediction, guided, train, reuse_kv;
+        int S, L, prediction, guided, train, reuse_kv, solver, order;
         float guidance, beta;
         bool operator==(const Key& o) const {
             return S == o.S && L == o.L && prediction == o.prediction && guided == o.guided && train == o.train &&
-                   reuse_kv == o.reuse_kv && guidance == o.guidance && beta == o.beta;
+                   reuse_kv == o.reuse_kv && solver == o.solver && order == o.order && guidance == o.guidance && beta == o.beta;
         }
     };
     struct Entry {
@@ -98,7 +111,7 @@ class Sampler {
             if (c.key == key) e = &c;
         if (!e) {
             // first sighting: run eagerly (sizes every arena / scratch buffer; allocations are illegal during capture)
-            if (graphs_.size() >= 8) drop_graphs();
+            if (graphs_.size() >= 12) drop_graphs();
             graphs_.push_back(Entry{key, nullptr, 0, g_alloc_gen});
             return body(key, st);
         }
@@ -162,7 +175,7 @@ class Sampler {
 
     // scratch layout for a key: caller copies | x_in [B][n] | eps | dx | x_new [S][n] | loss | norms | tap gradients
     float *own_lat_ = nullptr, *own_noise_ = nullptr, *own_ctx_ = nullptr, *own_target_ = nullptr, *own_loss_ = nullptr;
-    float *x_in_ = nullptr, *eps_ = nullptr, *dx_ = nullptr, *x_new_ = nullptr;
+    float *x_in_ = nullptr, *eps_ = nullptr, *dx_ = nullptr, *x_new_ = nullptr, *own_x0_ = nullptr;
     double* norms_ = nullptr;
     float* tg_[9] = {};
     int layout(const Key& k) {
@@ -172,7 +185,7 @@ class Sampler {
         const int tapS[9] = {L / 2, L / 4, L / 8, L / 8, L / 8, L / 8, L / 4, L / 2, L};
         const int tapC[9] = {boc[0], boc[1], boc[2], boc[3], boc[3], boc[3], boc[3], boc[2], boc[1]};
         const size_t ctx_bytes = (size_t)B * unet->cfg.ctx_len * unet->cfg.cross_dim * sizeof(float);
-        size_t need = (size_t)(3 * B + 4 * S) * n * sizeof(float) + ctx_bytes + (size_t)S * 20 + 32 * 256;
+        size_t need = (size_t)(3 * B + 5 * S) * n * sizeof(float) + ctx_bytes + (size_t)S * 20 + 32 * 256;
         for (int q = 0; q < 9; ++q) need += (size_t)B * tapS[q] * tapS[q] * tapC[q] * 4 + 256;
         S2I_TRY(ensure(need));
         char* p = buf_;
@@ -190,6 +203,7 @@ class Sampler {
         eps_ = (float*)take((size_t)B * n * 4);
         dx_ = (float*)take((size_t)B * n * 4);
         x_new_ = (float*)take((size_t)S * n * 4);
+        own_x0_ = (float*)take((size_t)S * n * 4);
         norms_ = (double*)take((size_t)S * 16);
         for (int q = 0; q < 9; ++q) tg_[q] = (float*)take((size_t)B * tapS[q] * tapS[q] * tapC[q] * 4);
         return 0;
@@ -207,7 +221,11 @@ class Sampler {
         }
         const bool do_guide = k.guided != 0;
         S2I_TRY(unet->forward(x_in_, B, L, L, 0.f, own_ctx_, eps_, do_guide, st, /*time_ready=*/true, k.reuse_kv != 0));    // :96
-        S2I_TRY(cfg_ddim_step(own_lat_, eps_, S, n, k.guidance, 0.f, 1.f, 1.f, 0.f, k.prediction, x_new_, st, d_sp_));   // :100-104
+        if (k.solver == 1)      // :100-104 with the demo's DPM-Solver++(2M) scheduler
+            S2I_TRY(cfg_dpmpp_step(own_lat_, eps_, own_x0_, S, n, k.guidance, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, k.prediction, k.order,
+                                   x_new_, st, d_sp_));
+        else
+            S2I_TRY(cfg_ddim_step(own_lat_, eps_, S, n, k.guidance, 0.f, 1.f, 1.f, 0.f, k.prediction, x_new_, st, d_sp_));   // :100-104
         if (do_guide) {
             // taps -> LGP -> edge loss -> tap gradients   (:145-159, LGP part)
             LgpTap taps[9];
@@ -370,9 +388,37 @@ int s2i_sampler_step(s2i_sampler* s, float* latents, const float* noise, const f
                      float* loss_out, void* cuda_stream) {
     if (!s || !latents || !ctx) return s2i::set_error(S2I_ERR_ARG, "s2i_sampler_step: null argument");
     if (guided && target && !noise) return s2i::set_error(S2I_ERR_ARG, "s2i_sampler_step: guided step needs the initial noise");
-    return s->impl->step(latents, noise, ctx, target, S, L, t, guidance_scale, sqrt_a_t, sqrt_one_minus_a_t, sqrt_a_prev,
-                         sqrt_one_minus_a_prev, prediction, guided, sigma, beta, lgp_train, loss_out,
-                         static_cast<cudaStream_t>(cuda_stream));
+    s2i::Sampler::StepArgs a;
+    a.t = t; a.guidance = guidance_scale;
+    a.sa_t = sqrt_a_t; a.sb_t = sqrt_one_minus_a_t; a.sa_p = sqrt_a_prev; a.sb_p = sqrt_one_minus_a_prev;
+    a.prediction = prediction; a.guided = guided; a.sigma = sigma; a.beta = beta; a.lgp_train = lgp_train;
+    return s->impl->step(latents, noise, ctx, target, nullptr, S, L, a, loss_out, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int s2i_sampler_step_dpmpp(s2i_sampler* s, float* latents, const float* noise, const float* ctx, const float* target,
+                           float* x0_history, int S, int L, float t, float guidance_scale, float alpha_t, float sigma_t,
+                           float c_x, float c_m0, float c_d1, float inv_r0, int order, int prediction, int guided, float beta,
+                           int lgp_train, float* loss_out, void* cuda_stream) {
+    if (!s || !latents || !ctx || !x0_history) return s2i::set_error(S2I_ERR_ARG, "s2i_sampler_step_dpmpp: null argument");
+    if (guided && target && !noise)
+        return s2i::set_error(S2I_ERR_ARG, "s2i_sampler_step_dpmpp: guided step needs the initial noise");
+    if (order != 1 && order != 2) return s2i::set_error(S2I_ERR_ARG, "s2i_sampler_step_dpmpp: order must be 1 or 2");
+    s2i::Sampler::StepArgs a;
+    a.solver = 1; a.order = order;
+    a.t = t; a.guidance = guidance_scale;
+    a.sa_t = alpha_t; a.sb_t = sigma_t;
+    a.A = c_x; a.Bc = c_m0; a.Cc = c_d1; a.R = inv_r0;
+    a.prediction = prediction; a.guided = guided; a.sigma = sigma_t; a.beta = beta; a.lgp_train = lgp_train;
+    return s->impl->step(latents, noise, ctx, target, x0_history, S, L, a, loss_out, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int s2i_cfg_dpmpp_step(const float* latents, const float* eps, float* x0_history, int S, int n, float guidance_scale,
+                       float alpha_t, float sigma_t, float c_x, float c_m0, float c_d1, float inv_r0, int order, int prediction,
+                       float* out, void* cuda_stream) {
+    if (!latents || !eps || !x0_history || !out) return s2i::set_error(S2I_ERR_ARG, "s2i_cfg_dpmpp_step: null argument");
+    if (order != 1 && order != 2) return s2i::set_error(S2I_ERR_ARG, "s2i_cfg_dpmpp_step: order must be 1 or 2");
+    return s2i::cfg_dpmpp_step(latents, eps, x0_history, S, n, guidance_scale, sigma_t, alpha_t, c_x, c_m0, c_d1, inv_r0,
+                               prediction, order, out, static_cast<cudaStream_t>(cuda_stream));
 }
 
 }  // extern "C"

@@ -143,7 +143,8 @@ class AntiGradientPipeline:
         device = self._execution_device
         if not guidance_scale > 1.0:
             raise NotImplementedError("the sketch-guided engine runs with classifier-free guidance on (guidance_scale > 1)")
-        if eta != 0.0:
+        multistep = hasattr(self.scheduler, "step_plan")        # DPM-Solver++(2M): the demo's scheduler (app.py:14-25)
+        if eta != 0.0 and not multistep:
             raise NotImplementedError("DDIM eta must be 0 on the fused step")
         if height != width and sketch_image is not None:
             raise RuntimeError("sketch guidance needs square latents (reference: pipeline.py:147 resizes to shape[2] only)")
@@ -180,10 +181,25 @@ class AntiGradientPipeline:
         chunk = max(1, int(self.max_samples_per_launch))
         step_stop = 0.5 * len(timesteps)                                            # pipeline.py:90
         self.last_losses = []
+        x0_hist = torch.zeros_like(latents) if multistep else None                  # the solver's x0-prediction history
         with self.progress_bar(total=num_inference_steps) as progress_bar:
             for i, t in enumerate(timesteps):
                 ti = int(t)
                 guided = int(i <= step_stop and target is not None)                 # pipeline.py:89-92, :108
+                if multistep:
+                    p = self.scheduler.step_plan(i)
+                    for s0 in range(0, S, chunk):
+                        s1 = min(S, s0 + chunk)
+                        _lib.check(lib.s2i_sampler_step_dpmpp(
+                            sampler, latents[s0:s1].data_ptr(), noise[s0:s1].data_ptr(), ctx[2 * s0:2 * s1].data_ptr(),
+                            target[s0:s1].data_ptr() if target is not None else None, x0_hist[s0:s1].data_ptr(), s1 - s0, L,
+                            float(ti), float(guidance_scale), p["alpha_t"], p["sigma_t"], p["c_x"], p["c_m0"], p["c_d1"],
+                            p["inv_r0"], p["order"], self.scheduler.prediction, guided, 1.6, train, loss[s0:s1].data_ptr(),
+                            stream))
+                    progress_bar.update()
+                    if callback is not None and i % callback_steps == 0:
+                        callback(i, t, latents)
+                    continue
                 sa_t, sb_t, sa_p, sb_p = self.scheduler.step_coefficients(ti)
                 sigma = self.scheduler.sigma(ti)
                 for s0 in range(0, S, chunk):

@@ -117,3 +117,40 @@ def test_satmixin_state_dict_contract():
     assert got == want
     sat.load_state_dict(o_sat.state_dict())
     assert transformer_block_paths(fake)[6] == "up_blocks.1.attentions.0" and transformer_block_paths(fake)[-1] == "mid_block.attentions.0"
+
+
+def test_dpmpp_host_scalars_reproduce_the_oracle_scheduler():
+    """sketch2img_b200.scheduler.DPMSolverMultistepScheduler (constructed with the reference's own keyword arguments,
+    app.py:14-25) hands the CUDA step the scalars of diffusers' first / second-order DPM-Solver++ updates: applied with the
+    kernel's rounding order on CPU they reproduce the oracle scheduler's ``step`` bit for bit, over whole schedules
+    (4 steps: first, second, second, lower-order-final first; 20 / 50 steps: first, then second order)."""
+    import torch
+    from oracle import port
+    from sketch2img_b200.scheduler import DPMSolverMultistepScheduler
+    o = port.make_scheduler(kind="dpmpp")
+    p = DPMSolverMultistepScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000,
+                                    trained_betas=None, predict_epsilon=True, thresholding=False, algorithm_type="dpmsolver++",
+                                    solver_type="midpoint", lower_order_final=True)
+    f = lambda v: torch.tensor(v, dtype=torch.float32)
+    for n, orders in ((4, [1, 2, 2, 1]), (20, [1] + [2] * 19), (50, [1] + [2] * 49)):
+        o.set_timesteps(n)
+        p.set_timesteps(n)
+        assert torch.equal(o.timesteps, p.timesteps)
+        assert [p.step_plan(i)["order"] for i in range(n)] == orders
+        g = torch.Generator().manual_seed(n)
+        x, m1 = torch.randn(1, 4, 8, 8, generator=g), None
+        for i, t in enumerate(o.timesteps):
+            e = torch.randn(1, 4, 8, 8, generator=g)
+            want = o.step(e, t, x).prev_sample
+            pl = p.step_plan(i)
+            m0 = (x - f(pl["sigma_t"]) * e) / f(pl["alpha_t"])
+            r = f(pl["c_x"]) * x - f(pl["c_m0"]) * m0
+            if pl["order"] == 2:
+                r = r - f(pl["c_d1"]) * (f(pl["inv_r0"]) * (m0 - m1))
+            assert torch.equal(r, want), f"{n}-step schedule, step {i}"
+            assert p.sigma(int(t)) == float((1 - o.alphas_cumprod[t]) ** 0.5)       # the LGP noise level of pipeline.py:133
+            x, m1 = want, m0
+    with pytest.raises(NotImplementedError):
+        DPMSolverMultistepScheduler(solver_order=3)
+    with pytest.raises(NotImplementedError):
+        DPMSolverMultistepScheduler(algorithm_type="dpmsolver")

@@ -31,8 +31,26 @@ def test_port_matches_golden_tiny(steps):
     assert abs(out.norm().item() - gold["norms"][-1].item()) < 1e-3 * gold["norms"][-1].item()
 
 
+@pytest.mark.parametrize("steps", [4, 20])
+def test_port_matches_golden_dpmpp(steps):
+    """The demo's scheduler (DPM-Solver++(2M), app.py:14-25): the port's loop over the shim scheduler reproduces the fixture
+    the unmodified reference pipeline wrote with that scheduler, bit for bit."""
+    from oracle import port
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    gold = torch.load(os.path.join(GOLD, f"tiny_dpmpp_{steps}step.pt"))
+    assert gold["scheduler"] == "dpmpp"
+    unet = port.make_unet("tiny")
+    lgp = port.make_lgp(unet)
+    lat, emb, tgt = port.make_inputs(unet)
+    got = {}
+    port.guided_sample(unet, lgp, port.make_scheduler(kind="dpmpp"), emb, lat.clone(), tgt, num_steps=steps,
+                       callback=lambda i, t, l: got.__setitem__(int(i), l.detach().clone()))
+    for i, ref in gold["latents"].items():
+        assert torch.equal(got[i], ref), f"step {i} differs from the fixture made by the reference files"
+
+
 def test_golden_fixture_metadata():
-    for name in ["tiny_4step", "tiny_50step", "sd15_4step", "sd15_50step"]:
+    for name in ["tiny_4step", "tiny_50step", "sd15_4step", "sd15_50step", "tiny_dpmpp_4step", "tiny_dpmpp_20step"]:
         g = torch.load(os.path.join(GOLD, name + ".pt"))
         assert g["source"].startswith("reference modules/pipeline.py")
         assert g["steps"] - 1 in g["latents"]

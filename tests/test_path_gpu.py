@@ -325,6 +325,71 @@ def test_pipeline_unguided_matches_reference_golden(tiny, steps):
     print("tiny %d-step unguided FINAL rel err %.3e" % (steps, final))
 
 
+# ---- the demo's scheduler: DPM-Solver++(2M), app.py:14-25 ---------------------------------------------------------
+def _dpmpp_pipe(tiny):
+    from sketch2img_b200.pipeline import AntiGradientPipeline
+    from sketch2img_b200.scheduler import DPMSolverMultistepScheduler
+    sch = DPMSolverMultistepScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000,
+                                      trained_betas=None, predict_epsilon=True, thresholding=False, algorithm_type="dpmsolver++",
+                                      solver_type="midpoint", lower_order_final=True)
+    pipe = AntiGradientPipeline(unet=tiny["unet"], scheduler=sch)
+    pipe.setup_lgp(tiny["lgp"])
+    return pipe
+
+
+@pytest.mark.parametrize("prediction", [0, 1])
+def test_cfg_dpmpp_step_bit_exact(cuda, prediction):
+    """s2i_cfg_dpmpp_step against the oracle scheduler's ``step`` on the same CFG-combined model output, over a whole
+    4-step (first / second / second / first order) and the head of a 50-step schedule: bit for bit."""
+    from oracle import port
+    from sketch2img_b200 import _lib
+    from sketch2img_b200.scheduler import DPMSolverMultistepScheduler
+    lib = _lib.lib()
+    ptype = "epsilon" if prediction == 0 else "v_prediction"
+    for n, upto in ((4, 4), (50, 5)):
+        o = port.make_scheduler(prediction_type=ptype, kind="dpmpp")
+        p = DPMSolverMultistepScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", prediction_type=ptype)
+        o.set_timesteps(n)
+        p.set_timesteps(n)
+        g = torch.Generator().manual_seed(31 + n)
+        S, nel = 3, 4 * 32 * 32
+        x = torch.randn(S, nel, generator=g)
+        hist = torch.full((S, nel), float("nan"), device=cuda)
+        xd = x.cuda()
+        for i in range(upto):
+            t = o.timesteps[i]
+            eps = torch.randn(2 * S, nel, generator=g)
+            e = eps[0::2] + 7.5 * (eps[1::2] - eps[0::2])
+            want = o.step(e, t, x).prev_sample
+            pl = p.step_plan(i)
+            out = torch.empty(S, nel, device=cuda)
+            _lib.check(lib.s2i_cfg_dpmpp_step(xd.data_ptr(), eps.cuda().data_ptr(), hist.data_ptr(), S, nel, 7.5, pl["alpha_t"],
+                                              pl["sigma_t"], pl["c_x"], pl["c_m0"], pl["c_d1"], pl["inv_r0"], pl["order"],
+                                              prediction, out.data_ptr(), _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            assert torch.equal(out.cpu(), want), f"{n}-step schedule, step {i} (order {pl['order']})"
+            assert torch.equal(hist.cpu(), o.model_outputs[-1]), "x0-prediction history"
+            x, xd = want, out
+
+
+@pytest.mark.parametrize("steps", [4, 20])
+def test_pipeline_dpmpp_unguided_matches_reference_golden(tiny, steps):
+    gold = torch.load(os.path.join(GOLD, f"tiny_dpmpp_{steps}step.pt"))
+    final = _check_unguided_against_golden(_dpmpp_pipe(tiny), tiny["inputs"], gold, f"tiny dpm++ {steps}-step")
+    print("tiny dpm++ %d-step unguided FINAL rel err %.3e" % (steps, final))
+
+
+@pytest.mark.parametrize("steps", [4, 20])
+def test_pipeline_dpmpp_guided_matches_reference_golden_at_noise_floor(tiny, steps):
+    gold = torch.load(os.path.join(GOLD, f"tiny_dpmpp_{steps}step.pt"))
+    lat, emb, tgt = tiny["inputs"]
+    got = {}
+    out = _dpmpp_pipe(tiny)("synthetic", num_inference_steps=steps, guidance_scale=7.5, latents=lat.cuda(), sketch_image=tgt.cuda(),
+                            prompt_embeds=emb.cuda(), output_type="latent",
+                            callback=lambda i, t, l: got.__setitem__(int(i), l.detach().float().cpu().clone()))
+    _check_guided_against_golden(got, out, gold, f"tiny dpm++ {steps}-step")
+
+
 def test_guided_step_stage_by_stage(tiny):
     """ONE guided step from identical state, stage by stage: CFG + DDIM latent, UNet adjoint applied to the ORACLE's
     tap gradients, and the update direction of the full CUDA chain."""
