@@ -383,12 +383,27 @@ int attn_fwd_launch(const AttnDesc& d, cudaStream_t stream) {
         stages = (full_sm - overhead - q_bytes - pbufs * kChunk16) / stage_bytes;
         if (stages > kMaxStages) stages = kMaxStages;
     }
+    int ns_force = 0;
+    if (const char* e = getenv("S2I_ATTN_CFG")) {       // tools/attn_bench.py --sweep: "pbufs,stages[,nS]" (two-CTA form only)
+        int fp = 0, fs = 0, fn = 0;
+        sscanf(e, "%d,%d,%d", &fp, &fs, &fn);
+        if (!triple && fp >= 1 && fp <= 2 && fs >= 2 && fs <= kMaxStages &&
+            q_bytes + fp * kChunk16 + fs * stage_bytes + overhead <= full_sm) {
+            pbufs = fp;
+            stages = fs;
+            ns_force = fn;
+        }
+    }
     if (stages < 2) return set_error(S2I_ERR_ARG, "attn_fwd: head dim %d does not fit shared memory", d.dp);
     p.stages = stages;
     p.pbufs = pbufs;
     p.nS = (p.tmem_cols - d.dp) / 64;
     if (p.nS > kMaxS) p.nS = kMaxS;
     if (p.nS > stages - 1) p.nS = stages - 1;   // score tiles run nS key tiles ahead of the P V products (see the issuer)
+    // measured (tools/attn_bench.py --sweep): a K/V stage is only reloaded after its P V product, so score tiles running
+    // more than stages - 2 ahead starve the loads (N = 4096, d = 40: 3 stages, nS 2 -> 1: 199 -> 182 us)
+    if (stages >= 3 && p.nS > stages - 2) p.nS = stages - 2;
+    if (ns_force >= 1 && ns_force <= kMaxS && ns_force <= stages - 1 && ns_force <= (p.tmem_cols - d.dp) / 64) p.nS = ns_force;
     if (p.nS < 1) return set_error(S2I_ERR_ARG, "attn_fwd: head dim %d leaves no TMEM for the score tiles", d.dp);
     const size_t smem_bytes = (size_t)q_bytes + (size_t)pbufs * kChunk16 + (size_t)stages * stage_bytes + overhead;
 

@@ -30,7 +30,9 @@ def _run(L, q, ldq, q_c0, kv, ldkv, k_c0, v_c0, B, heads, Nq, Nk, dp, d, scale, 
 
 @pytest.mark.parametrize("B,N,heads,d,dp", [(2, 256, 8, 40, 48), (1, 1024, 4, 80, 80), (2, 256, 8, 160, 160),
                                             (2, 4096, 2, 40, 48), (2, 256, 4, 16, 16), (1, 320, 5, 64, 64),
-                                            (3, 576, 2, 64, 64), (2, 128, 8, 40, 48)])
+                                            (3, 576, 2, 64, 64), (2, 128, 8, 40, 48),
+                                            # long, ragged key / query ranges with narrow heads
+                                            (1, 1024, 2, 64, 64), (2, 1100, 3, 40, 48), (1, 1030, 1, 16, 16)])
 def test_self_attention(L, cuda, B, N, heads, d, dp):
     """Q, K, V head-sliced out of one fused [B][N][3*heads*dp] projection (the UNet's qkv layout)."""
     g = torch.Generator(device="cpu").manual_seed(N + d)

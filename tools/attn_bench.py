@@ -9,6 +9,8 @@ sys.path.insert(0, ROOT)
 from sketch2img_b200 import _lib as L  # noqa: E402
 
 SHAPES = [("self N=4096 d=40", 2, 8, 4096, 4096, 40, 48), ("self N=1024 d=80", 2, 8, 1024, 1024, 80, 80),
+          ("self N=256 d=160", 2, 8, 256, 256, 160, 160), ("cross N=1024 Nk=77 d=80", 2, 8, 1024, 77, 80, 80),
+          ("self N=4096 d=40 B=1", 1, 8, 4096, 4096, 40, 48),
           ("cross N=4096 Nk=77 d=40", 2, 8, 4096, 77, 40, 48), ("self N=9216 d=64 (SD2.1)", 2, 5, 9216, 9216, 64, 64)]
 
 
@@ -33,8 +35,35 @@ def graph_time(fn, reps=10):
     return e0.elapsed_time(e1) / (3 * reps) * 1e3
 
 
+def sweep(lib):
+    """Forward only: shared-memory ring / score-tile configurations per shape."""
+    for name, B, heads, Nq, Nk, d, dp in SHAPES:
+        HP = heads * dp
+        gen = torch.Generator().manual_seed(1)
+        q = torch.randn(B, Nq, HP, generator=gen).cuda().half()
+        kv = torch.randn(B, Nk, 2 * HP, generator=gen).cuda().half()
+        out = torch.zeros(B, Nq, HP, device="cuda", dtype=torch.float16)
+        lse = torch.zeros(B * heads, Nq, device="cuda")
+
+        def fwd():
+            L.check(lib.s2i_attention(q.data_ptr(), HP, 0, kv.data_ptr(), 2 * HP, 0, HP, B, heads, Nq, Nk, dp, d, d ** -0.5,
+                                      out.data_ptr(), HP, lse.data_ptr(), L.stream_ptr()))
+
+        row = []
+        for cfg in ("", "2,3,2", "2,3,1", "2,2,1", "1,4,2", "1,4,1", "1,3,1", "1,2,1"):
+            if cfg:
+                os.environ["S2I_ATTN_CFG"] = cfg
+            else:
+                os.environ.pop("S2I_ATTN_CFG", None)
+            row.append("%s %.1f" % (cfg or "default", graph_time(fwd)))
+        print("%-28s (pbufs,stages,nS) us: %s" % (name, "   ".join(row)), flush=True)
+    os.environ.pop("S2I_ATTN_CFG", None)
+
+
 def main():
     lib = L.lib()
+    if "--sweep" in sys.argv:
+        return sweep(lib)
     for name, B, heads, Nq, Nk, d, dp in SHAPES:
         HP = heads * dp
         gen = torch.Generator().manual_seed(1)
@@ -58,8 +87,9 @@ def main():
                                                dkv.data_ptr() if with_kv else None, 2 * HP, 0, HP, L.stream_ptr()))
 
         tf = graph_time(fwd)
-        tq = graph_time(lambda: bwd(False))
-        tkv = graph_time(lambda: bwd(True)) if Nk >= 128 else float("nan")
+        bwd_ok = dp <= 128
+        tq = graph_time(lambda: bwd(False)) if bwd_ok else float("nan")
+        tkv = graph_time(lambda: bwd(True)) if Nk >= 128 and bwd_ok else float("nan")
         gf = 4.0 * B * heads * Nq * Nk * d / 1e9
         print(f"{name:28s} fwd {tf:7.1f} us ({gf / tf:6.1f} TF/s)   bwd dQ {tq:7.1f} us   bwd dQ+dK+dV {tkv:7.1f} us", flush=True)
 
