@@ -206,7 +206,11 @@ constexpr int kChunk32Bytes = kBlockM * 32 * 4;   // 16 KB: 128 rows x 32 fp32 c
 constexpr int kChunk16Bytes = kBlockM * 32 * 2;   //  8 KB: 128 rows x 32 fp16 columns
 constexpr int kMaxChunks = 8;
 
-__global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_constant__ GemmParams p) {
+// ESETS epilogue warp quartets (warps 2..5, and 6..9 when ESETS = 2) take the tile's 32-column chunks in turn: the chunks
+// are independent (own residual / staging region, own bulk store), and one quartet alone works through them at ~0.75 us
+// per chunk -- a latency chain (TMEM load, shared-memory round trips, proxy fence, barrier), not a bandwidth limit.
+template <int ESETS>
+__global__ void __launch_bounds__(64 + 128 * ESETS, ESETS == 2 ? 2 : 1) gemm_tma_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_stage_bytes = ((p.BN + 63) >> 6) * kChunkBytes;
@@ -282,9 +286,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
     } else {
         // ---------------------------------------------------- epilogue (warps 2..5), thread <-> tile row
         const int e = threadIdx.x - 64;
+        const int eset = e >> 7;                // warp quartet: chunks eset, eset + ESETS, ...
+        const int el = e & 127;
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;
-        for (int i = e; i < p.BN; i += 128) {
+        for (int i = e; i < p.BN; i += 128 * ESETS) {
             const int n = t.n0 + i;
             float b = 0.f;
             if (add_bias && n < p.N) {
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
             }
             bias_s[i] = b;
         }
-        ptx::named_bar_sync(1, 128);
+        ptx::named_bar_sync(1, 128 * ESETS);
         if (e == 0) stamp(p, 4);
         ptx::mbar_wait(accum_full, 0);
         ptx::tc_fence_after();
@@ -307,19 +313,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
             if (sub > 0) {
                 // the staging buffers are reused: the first sub-tile's stores must have read them; its residual tile
                 // is then loaded over them by this thread (second phase of the r_full barriers)
-                if (e == 0) {
-                    ptx::tma_store_wait_read0();
-                    if (add_res) {
-                        for (int c = 0; c < nch; ++c) {
-                            if (t.n0 + c * 32 >= p.N) break;
-                            ptx::mbar_expect_tx(&r_full[c], (uint32_t)(p.tw * p.th * p.tb * 128));
-                            ptx::tma_load_4d(smem + c * kChunk32Bytes, &p.mapRes, &r_full[c], t.n0 + c * 32, xs, ys, bs);
-                        }
+                if (el == 0) ptx::tma_store_wait_read0();      // each quartet's issuing thread waits for its own bulk groups
+                ptx::named_bar_sync(1, 128 * ESETS);
+                if (e == 0 && add_res) {
+                    for (int c = 0; c < nch; ++c) {
+                        if (t.n0 + c * 32 >= p.N) break;
+                        ptx::mbar_expect_tx(&r_full[c], (uint32_t)(p.tw * p.th * p.tb * 128));
+                        ptx::tma_load_4d(smem + c * kChunk32Bytes, &p.mapRes, &r_full[c], t.n0 + c * 32, xs, ys, bs);
                     }
                 }
-                ptx::named_bar_sync(1, 128);
             }
-            for (int c = 0; c < nch; ++c) {
+            for (int c = eset; c < nch; c += ESETS) {
                 if (t.n0 + c * 32 >= p.N) break;
                 uint32_t raw[32];
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * p.BN + c * 32), raw);
@@ -362,8 +366,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
                 // the chunk's bulk store overlaps the next chunk's arithmetic (the copy engine, like the loads, runs at the
                 // chip's ~10 TB/s L2 rate: a late burst of all stores would only lengthen the tail)
                 ptx::fence_proxy_async();              // generic-proxy smem writes -> visible to the bulk-copy engine
-                ptx::named_bar_sync(1, 128);
-                if (e == 0) {
+                ptx::named_bar_sync(2 + eset, 128);
+                if (el == 0) {
                     const int nc = t.n0 + c * 32;
                     if (p.has_o32) {
                         if (p.split_add) ptx::tma_reduce_add_4d(&p.mapO32, smem + c * kChunk32Bytes, nc, xs, ys, bs);
@@ -371,14 +375,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tma_kernel(const __grid_cons
                     }
                     if (p.has_o16) ptx::tma_store_4d(&p.mapO16, base16 + c * kChunk16Bytes, nc, xs, ys, bs);
                     ptx::tma_store_commit();
-                    if (c < 3) stamp(p, 13 + c);
+                    if (e == 0 && c < 3) stamp(p, 13 + c);
                 }
             }
         }
-        if (e == 0) {
-            stamp(p, 7);
+        if (el == 0) {
+            if (e == 0) stamp(p, 7);
             ptx::tma_store_wait_read0();   // shared memory stays valid until the stores have read it
-            stamp(p, 8);
+            if (e == 0) stamp(p, 8);
         }
     }
 
@@ -972,12 +976,18 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     }
     static bool attr_set = false;
     if (!attr_set) {
-        S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     dim3 grid((unsigned)grid_m, (unsigned)tiles_n, (unsigned)tc.splits);
     p.trace = g_trace;
-    S2I_LAUNCH((gemm_tma_kernel), grid, kThreads, smem_bytes, stream, p);
+    // two epilogue warp quartets whenever the tile has at least two 32-column chunks (S2I_GEMM_ESETS=1: always one);
+    // read per call so tools can A/B in one process
+    int esets = (BN >> 5) >= 2 ? 2 : 1;
+    if (const char* e = getenv("S2I_GEMM_ESETS")) esets = atoi(e) == 1 ? 1 : esets;
+    if (esets == 2) S2I_LAUNCH((gemm_tma_kernel<2>), grid, kThreads + 128, smem_bytes, stream, p);
+    else S2I_LAUNCH((gemm_tma_kernel<1>), grid, kThreads, smem_bytes, stream, p);
     const double m_rows = (double)d.aW * d.aH * d.aB;
     S2I_LAUNCH_CHECK_TAG(d.tag, 2.0 * m_rows * d.N * d.Kc * d.taps, 0.0);
     if (via_scratch) {
