@@ -166,7 +166,7 @@ def run_reference(args):
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- CUDA arm
@@ -329,14 +329,34 @@ def run_ours(args):
                 "value": images_per_sec_from_steps(tg, tu), "unit": "images/sec", "cores": threads, "kind": "port",
                 "sample": "1 guided + 1 unguided denoising step of the same job (%.2f s + %.2f s), extrapolated to "
                           "26 guided + 24 unguided steps" % (tg, tu)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return line
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout: libraries that write to fd 1 on their own (NCCL prints its version banner
+    there on the first collective) are pointed at stderr for the duration of the run."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
