@@ -30,9 +30,11 @@ __device__ __forceinline__ void src_index(int dst, float scale, int S, int& i0, 
 }
 
 // X[(b,h,w)][col] = fp16( bilinear(tap_k)[b][:, h, w] | sigma*noise | sin(2 pi lvl 2^-l) ), zero padded to ldX
+// smS > 0: the taps' batch is sample-major ([uncond_0 .. uncond_{smS-1}, cond_0 .. cond_{smS-1}], the sampler's order)
+// while the feature rows stay in (uncond_s, cond_s) pair order.
 __global__ void __launch_bounds__(256) lgp_features_kernel(TapTable tt, int B, int L, const float* __restrict__ noise,
                                                            float sigma, const float* __restrict__ dsigma, int P, int D,
-                                                           __half* __restrict__ X, long ldX) {
+                                                           __half* __restrict__ X, long ldX, int smS) {
     pdl_wait();
     pdl_launch();
     if (dsigma) sigma = __ldg(dsigma);      // graph-replayed steps read the step's scalars from device memory
@@ -47,7 +49,8 @@ __global__ void __launch_bounds__(256) lgp_features_kernel(TapTable tt, int B, i
             int k = 0;
             while (col >= tt.off[k + 1]) ++k;
             const int S = tt.S[k], C = tt.C[k], c = col - tt.off[k];
-            const float* base = tt.p[k] + (long)b * S * S * C + c;
+            const int bt = smS > 0 ? ((b & 1) ? smS + (b >> 1) : (b >> 1)) : b;     // batch entry of the tap tensors
+            const float* base = tt.p[k] + (long)bt * S * S * C + c;
             if (S == L) {
                 const float4 q0 = __ldg(reinterpret_cast<const float4*>(base + ((long)h * S + w) * C));
                 const float4 q1 = __ldg(reinterpret_cast<const float4*>(base + ((long)h * S + w) * C + 4));
@@ -412,7 +415,7 @@ __global__ void lgp_export_kernel(const __half* __restrict__ out16, int B, int L
 __global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eps, int S,
                                                        int n, float g, float sb_t, float sa_t, float sa_p, float sb_p,
                                                        const float* __restrict__ dparams, int prediction,
-                                                       float* __restrict__ out) {
+                                                       float* __restrict__ out, int sm) {
     pdl_wait();
     pdl_launch();
     if (dparams) {      // graph-replayed steps read the step's scalars from device memory
@@ -424,7 +427,8 @@ __global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* __restrict__
     const long total = (long)S * n;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const long s = idx / n, i = idx - s * n;
-        const float eu = eps[(2 * s) * (long)n + i], ec = eps[(2 * s + 1) * (long)n + i];
+        // eps: (uncond_s, cond_s) pairs, or sample-major [uncond..., cond...] (sm: the sampler's internal order)
+        const float eu = eps[(sm ? s : 2 * s) * (long)n + i], ec = eps[(sm ? S + s : 2 * s + 1) * (long)n + i];
         // no FMA contraction: each torch op rounds separately
         float e = __fadd_rn(eu, __fmul_rn(g, __fsub_rn(ec, eu)));
         const float xv = x[idx];
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) cfg_dpmpp_kernel(const float* __restrict__ x, const float* __restrict__ eps, int S,
                                                         int n, float g, float sigma_t, float alpha_t, float A, float Bc,
                                                         float Cc, float R, const float* __restrict__ dparams, int prediction,
-                                                        int order, float* __restrict__ hist, float* __restrict__ out) {
+                                                        int order, float* __restrict__ hist, float* __restrict__ out, int sm) {
     pdl_wait();
     pdl_launch();
     if (dparams) {
@@ -461,7 +465,7 @@ __global__ void __launch_bounds__(256) cfg_dpmpp_kernel(const float* __restrict_
     const long total = (long)S * n;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const long s = idx / n, i = idx - s * n;
-        const float eu = eps[(2 * s) * (long)n + i], ec = eps[(2 * s + 1) * (long)n + i];
+        const float eu = eps[(sm ? s : 2 * s) * (long)n + i], ec = eps[(sm ? S + s : 2 * s + 1) * (long)n + i];
         const float e = __fadd_rn(eu, __fmul_rn(g, __fsub_rn(ec, eu)));
         const float xv = x[idx];
         float m0;
@@ -706,7 +710,7 @@ int LGP::mlp(cudaStream_t st) {
 }
 
 int LGP::forward(const LgpTap taps[9], int B, int L, const float* noise, float sigma, bool train, cudaStream_t st,
-                 const float* dsigma) {
+                 const float* dsigma, bool taps_sample_major) {
     if (!loaded_) return set_error(S2I_ERR_STATE, "lgp: weights not loaded");
     if (B % 2 != 0) return set_error(S2I_ERR_ARG, "lgp: batch must hold (uncond, cond) pairs");
     TapTable tt;
@@ -728,7 +732,8 @@ int LGP::forward(const LgpTap taps[9], int B, int L, const float* noise, float s
     groups_ = B / 2;
     S2I_TRY(ensure(lgp_ws_bytes(rows, ldX_, B / 2)));
     X_ = reinterpret_cast<__half*>(buf_);   // first workspace slot (see mlp())
-    S2I_LAUNCH((lgp_features_kernel), grid1d(rows * (ldX_ / 8)), 256, 0, st, tt, B, L, noise, sigma, dsigma, P_, D_, X_, ldX_);
+    S2I_LAUNCH((lgp_features_kernel), grid1d(rows * (ldX_ / 8)), 256, 0, st, tt, B, L, noise, sigma, dsigma, P_, D_, X_, ldX_,
+                                                      taps_sample_major ? B / 2 : 0);
     S2I_LAUNCH_CHECK();
     return mlp(st);
 }
@@ -864,18 +869,18 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
 
 // ================================================================================================== step
 int cfg_ddim_step(const float* latents, const float* eps, int S, int n, float guidance, float sb_t, float sa_t,
-                  float sa_p, float sb_p, int prediction, float* out, cudaStream_t st, const float* dparams) {
+                  float sa_p, float sb_p, int prediction, float* out, cudaStream_t st, const float* dparams, bool sample_major) {
     S2I_LAUNCH((cfg_ddim_kernel), grid1d((long)S * n), 256, 0, st, latents, eps, S, n, guidance, sb_t, sa_t, sa_p, sb_p, dparams,
-                                                         prediction, out);
+                                                         prediction, out, sample_major ? 1 : 0);
     S2I_LAUNCH_CHECK();
     return 0;
 }
 
 int cfg_dpmpp_step(const float* latents, const float* eps, float* x0_hist, int S, int n, float guidance, float sigma_t,
                    float alpha_t, float A, float Bc, float Cc, float R, int prediction, int order, float* out, cudaStream_t st,
-                   const float* dparams) {
+                   const float* dparams, bool sample_major) {
     S2I_LAUNCH((cfg_dpmpp_kernel), grid1d((long)S * n), 256, 0, st, latents, eps, S, n, guidance, sigma_t, alpha_t, A, Bc, Cc, R,
-                                                          dparams, prediction, order, x0_hist, out);
+                                                          dparams, prediction, order, x0_hist, out, sample_major ? 1 : 0);
     S2I_LAUNCH_CHECK();
     return 0;
 }

@@ -29,8 +29,10 @@ class LGP {
     // "noise level" input shared by both CFG halves (pipeline.py:152-153).  Rows are ordered (b, h, w).
     // out16: fp16 [B*L*L][8] (first output_dim columns valid).
     // dsigma (optional, device): overrides `sigma` at run time (graph-replayed steps).
+    // taps_sample_major: the taps' batch is ordered [uncond_0.., cond_0..] (the sampler's internal order) instead of
+    // (uncond_s, cond_s) pairs; the LGP's own rows stay in pair order either way.
     int forward(const LgpTap taps[9], int B, int L, const float* noise, float sigma, bool train, cudaStream_t st,
-                const float* dsigma = nullptr);
+                const float* dsigma = nullptr, bool taps_sample_major = false);
     // Edge loss on the cond half + backward to the taps.  target: NCHW fp32 [samples,4,L,L].
     // tap_grads[k]: NHWC fp32 like tap k, multiplied by grad_scale(); loss: device float [samples].
     // cond_only: only the cond samples' tap gradients are produced (tap_grads[k] then holds `samples` maps, sample s =
@@ -90,15 +92,17 @@ class LGP {
 // ---- scheduler / guidance update (modules/pipeline.py:100-104, :160-161; DDIM step per SURVEY A.6) -----------
 // eps: [2*S][n] ordered (uncond_s, cond_s); latents: [S][n].  prediction: 0 = epsilon, 1 = v_prediction.
 // dparams (optional, device float[4] = sb_t, sa_t, sa_p, sb_p): overrides the by-value coefficients (graph-replayed steps).
+// sample_major: eps is ordered [uncond_0.., cond_0..] (the sampler's internal batch order) instead of pairs.
 int cfg_ddim_step(const float* latents, const float* eps, int S, int n, float guidance, float sb_t, float sa_t,
-                  float sa_p, float sb_p, int prediction, float* out, cudaStream_t st, const float* dparams = nullptr);
+                  float sa_p, float sb_p, int prediction, float* out, cudaStream_t st, const float* dparams = nullptr,
+                  bool sample_major = false);
 // CFG combine + DPM-Solver++(2M, midpoint) update, the scheduler of the reference's demo (app.py:14-25).  The host supplies
 // the step's fp32 scalars: sigma_t / alpha_t of the current timestep, A = sigma_prev / sigma_t, Bc = alpha_prev (exp(-h) - 1),
 // Cc = 0.5 Bc, R = 1 / r0.  x0_hist [S][n]: previous x0 prediction in (second order), this step's out.  order: 1 | 2.
 // dparams (optional, device float[8] = sigma_t, alpha_t, A, Bc, -, Cc, R): overrides the by-value scalars.
 int cfg_dpmpp_step(const float* latents, const float* eps, float* x0_hist, int S, int n, float guidance, float sigma_t,
                    float alpha_t, float A, float Bc, float Cc, float R, int prediction, int order, float* out, cudaStream_t st,
-                   const float* dparams = nullptr);
+                   const float* dparams = nullptr, bool sample_major = false);
 // x_new += beta * ||x_in - x_new||_F / ||g||_F * g with g = -dx[cond half]; norms per sample; x_in = [x_old, x_old].
 // dx: [2*S][n], or [S][n] holding only the cond halves (dx_cond_only).  scratch: double [S][2] device.
 int guidance_update(const float* x_old, float* x_new, const float* dx, int S, int n, float beta, double* scratch,

@@ -74,8 +74,13 @@ class Sampler {
         S2I_TRY(layout(key));
         const size_t nb = (size_t)S * unet->cfg.in_ch * L * L * sizeof(float);
         S2I_MEMOP(cudaMemcpyAsync(own_lat_, latents, nb, cudaMemcpyDeviceToDevice, st));
-        S2I_MEMOP(cudaMemcpyAsync(own_ctx_, ctx, (size_t)2 * S * unet->cfg.ctx_len * unet->cfg.cross_dim * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, st));
+        {   // the caller's context comes in (uncond_s, cond_s) pairs; the engine's batch is sample-major [uncond.., cond..]
+            const size_t cb = (size_t)unet->cfg.ctx_len * unet->cfg.cross_dim * sizeof(float);
+            const char* src = reinterpret_cast<const char*>(ctx);
+            char* dst = reinterpret_cast<char*>(own_ctx_);
+            S2I_MEMOP(cudaMemcpy2DAsync(dst, cb, src, 2 * cb, cb, S, cudaMemcpyDeviceToDevice, st));
+            S2I_MEMOP(cudaMemcpy2DAsync(dst + (size_t)S * cb, cb, src + cb, 2 * cb, cb, S, cudaMemcpyDeviceToDevice, st));
+        }
         if (a.solver == 1 && a.order == 2) S2I_MEMOP(cudaMemcpyAsync(own_x0_, x0_hist, nb, cudaMemcpyDeviceToDevice, st));
         if (do_guide) {
             S2I_MEMOP(cudaMemcpyAsync(own_noise_, noise, nb, cudaMemcpyDeviceToDevice, st));
@@ -214,18 +219,18 @@ class Sampler {
         const int S = k.S, L = k.L;
         const int n = unet->cfg.in_ch * L * L;
         const int B = 2 * S;
-        // x_in = cat([latents] * 2) per sample, ordered (uncond_s, cond_s)   (pipeline.py:85)
-        for (int s = 0; s < S; ++s) {
-            S2I_MEMOP(cudaMemcpyAsync(x_in_ + (size_t)(2 * s) * n, own_lat_ + (size_t)s * n, n * 4, cudaMemcpyDeviceToDevice, st));
-            S2I_MEMOP(cudaMemcpyAsync(x_in_ + (size_t)(2 * s + 1) * n, own_lat_ + (size_t)s * n, n * 4, cudaMemcpyDeviceToDevice, st));
-        }
+        // x_in = cat([latents] * 2) (pipeline.py:85); the engine's batch is sample-major: [uncond_0.., cond_0..], so the cond
+        // samples -- the only ones whose latent gradient is kept (:159) -- form the contiguous second half
+        S2I_MEMOP(cudaMemcpyAsync(x_in_, own_lat_, (size_t)S * n * 4, cudaMemcpyDeviceToDevice, st));
+        S2I_MEMOP(cudaMemcpyAsync(x_in_ + (size_t)S * n, own_lat_, (size_t)S * n * 4, cudaMemcpyDeviceToDevice, st));
         const bool do_guide = k.guided != 0;
         S2I_TRY(unet->forward(x_in_, B, L, L, 0.f, own_ctx_, eps_, do_guide, st, /*time_ready=*/true, k.reuse_kv != 0));    // :96
         if (k.solver == 1)      // :100-104 with the demo's DPM-Solver++(2M) scheduler
             S2I_TRY(cfg_dpmpp_step(own_lat_, eps_, own_x0_, S, n, k.guidance, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, k.prediction, k.order,
-                                   x_new_, st, d_sp_));
+                                   x_new_, st, d_sp_, /*sample_major=*/true));
         else
-            S2I_TRY(cfg_ddim_step(own_lat_, eps_, S, n, k.guidance, 0.f, 1.f, 1.f, 0.f, k.prediction, x_new_, st, d_sp_));   // :100-104
+            S2I_TRY(cfg_ddim_step(own_lat_, eps_, S, n, k.guidance, 0.f, 1.f, 1.f, 0.f, k.prediction, x_new_, st, d_sp_,
+                                  /*sample_major=*/true));                                                                  // :100-104
         if (do_guide) {
             // taps -> LGP -> edge loss -> tap gradients   (:145-159, LGP part)
             LgpTap taps[9];
@@ -234,17 +239,13 @@ class Sampler {
                 if (tp.H != tp.W) return set_error(S2I_ERR_ARG, "guided sampling needs square latents (pipeline.py:147)");
                 taps[q] = LgpTap{tp.p, tp.H, tp.C};
             }
-            S2I_TRY(lgp->forward(taps, B, L, own_noise_, 0.f, k.train != 0, st, d_sp_ + 4));
+            S2I_TRY(lgp->forward(taps, B, L, own_noise_, 0.f, k.train != 0, st, d_sp_ + 4, /*taps_sample_major=*/true));
             // Only the cond half of the latent gradient is kept (:159) and the UNet is a per-sample computation, so the
-            // backward walks the cond sample alone (one image: batch entry 1); the LGP's BatchNorm backward still
-            // runs over both halves.  Several images per call keep the whole-batch walk (cond entries are interleaved).
-            const bool cond_only = S == 1;
-            S2I_TRY(lgp->loss_backward(own_target_, tg_, own_loss_, st, cond_only));
-            if (cond_only)
-                S2I_TRY(unet->backward(tg_, dx_, st, 1, 1));                                         // :159 (UNet part)
-            else
-                S2I_TRY(unet->backward(tg_, dx_, st));
-            S2I_TRY(guidance_update(own_lat_, x_new_, dx_, S, n, k.beta, norms_, st, cond_only));    // :160-161
+            // backward walks the cond samples alone (batch entries S .. 2S-1); the LGP's BatchNorm backward still runs over
+            // both halves of every pair.
+            S2I_TRY(lgp->loss_backward(own_target_, tg_, own_loss_, st, /*cond_only=*/true));
+            S2I_TRY(unet->backward(tg_, dx_, st, S, S));                                             // :159 (UNet part)
+            S2I_TRY(guidance_update(own_lat_, x_new_, dx_, S, n, k.beta, norms_, st, /*dx_cond_only=*/true));   // :160-161
         }
         S2I_MEMOP(cudaMemcpyAsync(own_lat_, x_new_, (size_t)S * n * 4, cudaMemcpyDeviceToDevice, st));
         return 0;
