@@ -30,6 +30,10 @@ long long s2i_launch_count(void);
  * "<class> <launches> <ms> <flops> <bytes>".  Returns the number of characters written, or a negative code. */
 int s2i_profile_begin(void* cuda_stream);
 int s2i_profile_end(char* report, int capacity);
+/* Roofline denominators (dense fp16/bf16 TFLOP/s, HBM GB/s): with them set, each line of the report carries a sixth column,
+ * the sum over the class's launches of  max(FLOPs / peak, algorithmic bytes / bandwidth)  in ms -- the time the launches
+ * would take at their own roofline, whichever resource bounds each of them. */
+int s2i_profile_set_peaks(double tflops, double hbm_gbs);
 
 /* ---------------------------------------------------------------------------------------------
  * tcgen05 + TMA implicit GEMM:  C[z] = alpha * A[z] * B[z]^T (+ bias, per-sample vector, ReLU, residual).

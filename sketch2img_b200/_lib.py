@@ -59,6 +59,7 @@ def lib():
     h.s2i_launch_count.restype = C.c_longlong
     h.s2i_profile_begin.argtypes = [C.c_void_p]
     h.s2i_profile_end.argtypes = [C.c_char_p, C.c_int]
+    h.s2i_profile_set_peaks.argtypes = [C.c_double, C.c_double]
     h.s2i_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     h.s2i_gemm.restype = C.c_int
     h.s2i_gemm_set_tma_epilogue.argtypes = [C.c_int]
@@ -132,19 +133,21 @@ def launch_count():
     return int(lib().s2i_launch_count())
 
 
-def profile_begin():
-    """Start per-launch device timing of every libs2i kernel on the current stream."""
+def profile_begin(peak_tflops=0.0, peak_hbm_gbs=0.0):
+    """Start per-launch device timing of every libs2i kernel on the current stream.  With the roofline denominators given,
+    profile_end() also reports each class's time at its launches' own rooflines ("roof_ms")."""
+    check(lib().s2i_profile_set_peaks(float(peak_tflops), float(peak_hbm_gbs)))
     check(lib().s2i_profile_begin(stream_ptr()))
 
 
 def profile_end():
-    """-> {kernel class: {"launches", "ms", "flops", "bytes"}} since profile_begin()."""
+    """-> {kernel class: {"launches", "ms", "flops", "bytes", "roof_ms"}} since profile_begin()."""
     buf = C.create_string_buffer(1 << 16)
     n = lib().s2i_profile_end(buf, len(buf))
     if n < 0:
         check(n)
     out = {}
     for line in buf.value.decode().splitlines():
-        tag, cnt, ms, fl, by = line.split()
-        out[tag] = {"launches": int(cnt), "ms": float(ms), "flops": float(fl), "bytes": float(by)}
+        tag, cnt, ms, fl, by, roof = line.split()
+        out[tag] = {"launches": int(cnt), "ms": float(ms), "flops": float(fl), "bytes": float(by), "roof_ms": float(roof)}
     return out

@@ -22,6 +22,12 @@ int s2i_profile_end(char* report, int capacity) {
     return s2i::prof_end(report, capacity);
 }
 
+int s2i_profile_set_peaks(double tflops, double hbm_gbs) {
+    if (tflops < 0 || hbm_gbs < 0) return s2i::set_error(S2I_ERR_ARG, "s2i_profile_set_peaks: negative peak");
+    s2i::prof_set_peaks(tflops, hbm_gbs);
+    return 0;
+}
+
 int s2i_gemm_set_tma_epilogue(int on) {
     s2i::gemm_set_tma_epilogue(on);
     return 0;

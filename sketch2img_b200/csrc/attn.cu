@@ -429,7 +429,8 @@ int attn_fwd_launch(const AttnDesc& d, cudaStream_t stream) {
     if (triple) S2I_LAUNCH((attn_fwd_kernel<3>), grid, kThreads, smem_bytes, stream, p);
     else S2I_LAUNCH((attn_fwd_kernel<1>), grid, kThreads, smem_bytes, stream, p);
     // algorithmic work: QK^T + PV at the true head dim
-    S2I_LAUNCH_CHECK_TAG("attn_fwd", 4.0 * d.B * d.heads * (double)d.Nq * d.Nk * d.d_true, 0.0);
+    S2I_LAUNCH_CHECK_TAG("attn_fwd", 4.0 * d.B * d.heads * (double)d.Nq * d.Nk * d.d_true,
+                         2.0 * d.B * d.heads * d.d_true * (2.0 * d.Nq + 2.0 * d.Nk));      // Q, O, K, V once (fp16)
     return 0;
 }
 

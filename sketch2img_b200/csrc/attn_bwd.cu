@@ -431,7 +431,8 @@ int attn_bwd_launch(const AttnBwdDesc& d, cudaStream_t stream) {
         dim3 grid((unsigned)((p.Nrow + kRows - 1) / kRows), (unsigned)Z, 1);
         S2I_LAUNCH((attn_bwd_kernel), grid, kThreads, smem_bytes, stream, p);
         // algorithmic work of the reference's backward: dP, dQ (mode 0) and dV, dK (mode 1) products at the true head dim
-        S2I_LAUNCH_CHECK_TAG("attn_bwd", 4.0 * Z * (double)d.Nq * d.Nk * d.d_true, 0.0);
+        S2I_LAUNCH_CHECK_TAG("attn_bwd", 4.0 * Z * (double)d.Nq * d.Nk * d.d_true,
+                             2.0 * Z * d.d_true * (3.0 * d.Nq + 3.0 * d.Nk));      // Q, dO, dQ | K, V, dK/dV once (fp16)
     }
     return 0;
 }

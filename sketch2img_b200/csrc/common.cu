@@ -57,6 +57,13 @@ int prof_begin(cudaStream_t st) {
     return 0;
 }
 
+// Roofline denominators for the per-launch floor  max(FLOPs / peak_flops, bytes / peak_bw)  reported by prof_end (0: not set)
+static double g_peak_flops = 0.0, g_peak_bw = 0.0;
+void prof_set_peaks(double tflops, double gbs) {
+    g_peak_flops = tflops * 1e12;
+    g_peak_bw = gbs * 1e9;
+}
+
 void prof_mark(const char* tag, double flops, double bytes) {
     cudaEventRecord(prof_event(), g_prof_stream);
     g_prof_recs.push_back(ProfRec{tag, flops, bytes});
@@ -68,7 +75,7 @@ int prof_end(char* buf, int cap) {
         return set_error(S2I_ERR_CUDA, "prof_end: %s", cudaGetErrorString(cudaGetLastError()));
     struct Agg {
         long n = 0;
-        double ms = 0, flops = 0, bytes = 0;
+        double ms = 0, flops = 0, bytes = 0, roof_ms = 0;
     };
     std::map<std::string, Agg> agg;
     for (size_t i = 0; i < g_prof_recs.size(); ++i) {
@@ -79,11 +86,15 @@ int prof_end(char* buf, int cap) {
         a.ms += ms;
         a.flops += g_prof_recs[i].flops;
         a.bytes += g_prof_recs[i].bytes;
+        // this launch's roofline floor: whichever of the tensor pipe and HBM bounds it
+        double t_f = g_peak_flops > 0 ? g_prof_recs[i].flops / g_peak_flops : 0.0;
+        double t_b = g_peak_bw > 0 ? g_prof_recs[i].bytes / g_peak_bw : 0.0;
+        a.roof_ms += 1e3 * (t_f > t_b ? t_f : t_b);
     }
     int off = 0;
     for (auto& kv : agg) {
-        int w = snprintf(buf + off, cap - off > 0 ? cap - off : 0, "%s %ld %.6f %.6e %.6e\n", kv.first.c_str(), kv.second.n,
-                         kv.second.ms, kv.second.flops, kv.second.bytes);
+        int w = snprintf(buf + off, cap - off > 0 ? cap - off : 0, "%s %ld %.6f %.6e %.6e %.6f\n", kv.first.c_str(), kv.second.n,
+                         kv.second.ms, kv.second.flops, kv.second.bytes, kv.second.roof_ms);
         if (w < 0 || off + w >= cap) return set_error(S2I_ERR_ARG, "prof_end: report buffer too small");
         off += w;
     }

@@ -28,7 +28,9 @@ inline void count_launch(int n = 1) { g_launches += n; }
 extern bool g_prof_on;
 void prof_mark(const char* tag, double flops, double bytes);
 int prof_begin(cudaStream_t st);
-// Text report, one line per tag: "tag launches ms flops bytes".  Returns the number of bytes written (or < 0).
+void prof_set_peaks(double tflops, double gbs);
+// Text report, one line per tag: "tag launches ms flops bytes roof_ms" (roof_ms = sum over the tag's launches of
+// max(flops / peak_flops, bytes / peak_bw), see prof_set_peaks).  Returns the number of bytes written (or < 0).
 int prof_end(char* buf, int cap);
 
 #define S2I_CUDA(call)                                                                                       \

@@ -989,7 +989,10 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     if (esets == 2) S2I_LAUNCH((gemm_tma_kernel<2>), grid, kThreads + 128, smem_bytes, stream, p);
     else S2I_LAUNCH((gemm_tma_kernel<1>), grid, kThreads, smem_bytes, stream, p);
     const double m_rows = (double)d.aW * d.aH * d.aB;
-    S2I_LAUNCH_CHECK_TAG(d.tag, 2.0 * m_rows * d.N * d.Kc * d.taps, 0.0);
+    // algorithmic bytes: the activation operand and the weights once (fp16), the fp32 residual, the outputs
+    const double alg_bytes = 2.0 * (m_rows * d.Kc + (double)d.N * d.Kc * d.taps) + m_rows * d.N * ((d.residual ? 4.0 : 0.0) +
+                             (d_in.out32 ? 4.0 : 0.0) + (d_in.out16 ? 2.0 : 0.0));
+    S2I_LAUNCH_CHECK_TAG(d.tag, 2.0 * m_rows * d.N * d.Kc * d.taps, alg_bytes);
     if (via_scratch) {
         const long total = rows_total * (d.N / 4);
         S2I_LAUNCH((cast_rows_kernel), (unsigned)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048), 256, 0, stream, 
@@ -1169,7 +1172,9 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)(Z * p.splits));
     S2I_LAUNCH((gemm_tc_kernel), grid, kThreads, smem_bytes, stream, p);
     const double m_rows = d.a_mn ? (double)d.aC : (double)d.aW * d.aH * (d.Z > 1 ? 1 : d.aB);
-    S2I_LAUNCH_CHECK_TAG(d.tag, 2.0 * m_rows * d.N * d.Kc * d.taps * Z, 0.0);
+    const double alg_bytes = Z * (2.0 * (m_rows * d.Kc + (double)d.N * d.Kc * d.taps) + m_rows * d.N * ((d.residual ? 4.0 : 0.0) +
+                             (d.out32 ? 4.0 : 0.0) + (d.out16 ? 2.0 : 0.0)));
+    S2I_LAUNCH_CHECK_TAG(d.tag, 2.0 * m_rows * d.N * d.Kc * d.taps * Z, alg_bytes);
     return 0;
 }
 
