@@ -141,6 +141,8 @@ int s2i_unet_forward(s2i_unet* u, const float* x, int B, int H, int W, float t, 
                      int save_for_backward, void* cuda_stream);
 /* tap k of the last forward: NHWC fp32 device view owned by the engine (valid until the next forward) */
 int s2i_unet_tap(s2i_unet* u, int k, float** ptr, int* B, int* H, int* W, int* C);
+/* element stride between consecutive pixels of tap k (>= C: some taps are slices of the up path's concat buffers) */
+int s2i_unet_tap_stride(s2i_unet* u, int k, long long* pixel_stride);
 /* tap_grads[k]: NHWC fp32 device, shaped like tap k (NULL = no gradient); dx: NCHW fp32 device [B,C,H,W] */
 int s2i_unet_backward(s2i_unet* u, float* const* tap_grads, float* dx, void* cuda_stream);
 /* The same walk over the samples [b0, b0 + nb) of the forward's batch only: tap_grads[k] and dx hold nb samples.

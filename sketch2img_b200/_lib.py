@@ -76,6 +76,7 @@ def lib():
     h.s2i_unet_load.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(vp), ip, C.POINTER(C.c_longlong)]
     h.s2i_unet_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, C.c_int, vp]
     h.s2i_unet_tap.argtypes = [vp, C.c_int, fp, ip, ip, ip, ip]
+    h.s2i_unet_tap_stride.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
     L = C.c_longlong
     h.s2i_groupnorm_forward.argtypes = [vp, L, C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_int, vp, L, vp, L, vp, vp]
     h.s2i_groupnorm_backward.argtypes = [vp, L, vp, L, C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp, vp, L,

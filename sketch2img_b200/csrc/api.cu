@@ -154,6 +154,14 @@ int s2i_unet_tap(s2i_unet* u, int k, float** ptr, int* B, int* H, int* W, int* C
     return 0;
 }
 
+int s2i_unet_tap_stride(s2i_unet* u, int k, long long* pixel_stride) {
+    if (!u || k < 0 || k >= 9 || !pixel_stride) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_tap_stride: bad argument");
+    const s2i::F32& t = u->impl->taps[k];
+    if (!t.p) return s2i::set_error(S2I_ERR_STATE, "s2i_unet_tap_stride: no forward yet");
+    *pixel_stride = t.ld;
+    return 0;
+}
+
 int s2i_unet_backward(s2i_unet* u, float* const* tap_grads, float* dx, void* cuda_stream) {
     if (!u || !tap_grads || !dx) return s2i::set_error(S2I_ERR_ARG, "s2i_unet_backward: null argument");
     return u->impl->backward(tap_grads, dx, static_cast<cudaStream_t>(cuda_stream));

@@ -17,6 +17,7 @@ constexpr float kTwoPi = 6.2831855f;   // float(2 * math.pi), as torch promotes 
 
 struct TapTable {
     const float* p[9];
+    long ld[9];          // pixel stride (taps may be slices of the UNet's concat buffers)
     int S[9], C[9], off[10];
 };
 
@@ -50,10 +51,11 @@ __global__ void __launch_bounds__(256) lgp_features_kernel(TapTable tt, int B, i
             while (col >= tt.off[k + 1]) ++k;
             const int S = tt.S[k], C = tt.C[k], c = col - tt.off[k];
             const int bt = smS > 0 ? ((b & 1) ? smS + (b >> 1) : (b >> 1)) : b;     // batch entry of the tap tensors
-            const float* base = tt.p[k] + (long)bt * S * S * C + c;
+            const long ld = tt.ld[k];
+            const float* base = tt.p[k] + (long)bt * S * S * ld + c;
             if (S == L) {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(base + ((long)h * S + w) * C));
-                const float4 q1 = __ldg(reinterpret_cast<const float4*>(base + ((long)h * S + w) * C + 4));
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(base + ((long)h * S + w) * ld));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(base + ((long)h * S + w) * ld + 4));
                 v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
             } else {
                 const float scale = (float)S / (float)L;
@@ -62,10 +64,10 @@ __global__ void __launch_bounds__(256) lgp_features_kernel(TapTable tt, int B, i
                 src_index(h, scale, S, y0, y1, ly);
                 src_index(w, scale, S, x0, x1, lx);
                 const float hy = 1.f - ly, hx = 1.f - lx;
-                const float* p00 = base + ((long)y0 * S + x0) * C;
-                const float* p01 = base + ((long)y0 * S + x1) * C;
-                const float* p10 = base + ((long)y1 * S + x0) * C;
-                const float* p11 = base + ((long)y1 * S + x1) * C;
+                const float* p00 = base + ((long)y0 * S + x0) * ld;
+                const float* p01 = base + ((long)y0 * S + x1) * ld;
+                const float* p10 = base + ((long)y1 * S + x0) * ld;
+                const float* p11 = base + ((long)y1 * S + x1) * ld;
 #pragma unroll
                 for (int j = 0; j < 8; j += 4) {
                     const float4 a = __ldg(reinterpret_cast<const float4*>(p00 + j));
@@ -718,6 +720,8 @@ int LGP::forward(const LgpTap taps[9], int B, int L, const float* noise, float s
     for (int k = 0; k < 9; ++k) {
         taps_[k] = taps[k];
         tt.p[k] = taps[k].p;
+        tt.ld[k] = taps[k].ld > 0 ? taps[k].ld : taps[k].C;
+        if (tt.ld[k] % 4 != 0) return set_error(S2I_ERR_ARG, "lgp: tap pixel strides must be multiples of 4");
         tt.S[k] = taps[k].S;
         tt.C[k] = taps[k].C;
         tt.off[k] = off;
@@ -747,7 +751,7 @@ int LGP::forward_nchw(const float* x, const float* t, int B, int L, bool train, 
     X_ = reinterpret_cast<__half*>(buf_);
     S2I_LAUNCH((lgp_features_nchw_kernel), grid1d(rows * ldX_), 256, 0, st, x, t, B, L, D_ - 4 - 4 * P_, P_, D_, X_, ldX_);
     S2I_LAUNCH_CHECK();
-    for (int k = 0; k < 9; ++k) taps_[k] = LgpTap{nullptr, 0, 0};
+    for (int k = 0; k < 9; ++k) taps_[k] = LgpTap{nullptr, 0, 0, 0};
     return mlp(st);
 }
 

@@ -15,8 +15,9 @@
 namespace s2i {
 
 struct LgpTap {
-    const float* p;   // NHWC fp32 [B][S][S][C]
+    const float* p;   // NHWC fp32 [B][S][S][C], pixel stride ld (0 = C: dense)
     int S, C;
+    long ld = 0;
 };
 
 class LGP {

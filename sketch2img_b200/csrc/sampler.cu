@@ -237,7 +237,7 @@ class Sampler {
             for (int q = 0; q < 9; ++q) {
                 const F32& tp = unet->taps[q];
                 if (tp.H != tp.W) return set_error(S2I_ERR_ARG, "guided sampling needs square latents (pipeline.py:147)");
-                taps[q] = LgpTap{tp.p, tp.H, tp.C};
+                taps[q] = LgpTap{tp.p, tp.H, tp.C, tp.ld};
             }
             S2I_TRY(lgp->forward(taps, B, L, own_noise_, 0.f, k.train != 0, st, d_sp_ + 4, /*taps_sample_major=*/true));
             // Only the cond half of the latent gradient is kept (:159) and the UNet is a per-sample computation, so the
@@ -321,7 +321,7 @@ int s2i_lgp_forward_taps(s2i_lgp* l, const float* const* taps, const int* sizes,
                          const float* noise, float sigma, int train, void* cuda_stream) {
     if (!l || !taps || !sizes || !channels || !noise) return s2i::set_error(S2I_ERR_ARG, "s2i_lgp_forward_taps: null argument");
     s2i::LgpTap tp[9];
-    for (int k = 0; k < 9; ++k) tp[k] = s2i::LgpTap{taps[k], sizes[k], channels[k]};
+    for (int k = 0; k < 9; ++k) tp[k] = s2i::LgpTap{taps[k], sizes[k], channels[k], 0};
     return l->impl->forward(tp, B, L, noise, sigma, train != 0, static_cast<cudaStream_t>(cuda_stream));
 }
 

@@ -519,6 +519,19 @@ F32 UNet::new32(int B, int H, int W, int C) {
     t.p = static_cast<float*>(arena_.alloc((size_t)B * H * W * C * sizeof(float)));
     return t;
 }
+// The next layer output: a fresh arena tensor, or -- when the caller reserved a destination (the slice of an up-path
+// concat buffer this output is one half of) -- that slice, so torch.cat([h, skip], dim=1) never copies.
+F32 UNet::out32(int B, int H, int W, int C) {
+    if (!dest_set_) return new32(B, H, W, C);
+    dest_set_ = false;
+    return dest_;       // shape checked by reserve()
+}
+void UNet::reserve(const F32& cat, int c0, int C) {
+    dest_ = cat;
+    dest_.p = cat.p + c0;
+    dest_.C = C;
+    dest_set_ = true;
+}
 H16 UNet::new16(int B, int H, int W, int C) {
     H16 t;
     t.B = B; t.H = H; t.W = W; t.C = C;
@@ -609,7 +622,7 @@ int UNet::resblock(int idx, const F32& x, F32& out) {
         S2I_TRY(gemm(x16, false, 1, R.sc.w, R.Cin, R.Cout, R.Cin, R.sc.b, nullptr, nullptr, &sc, nullptr));
         res = sc;
     }
-    out = new32(B, H, W, R.Cout);
+    out = out32(B, H, W, R.Cout);
     S2I_TRY(gemm(a2, true, 9, R.c2.w, 9L * R.Cout, R.Cout, R.Cout, R.c2.b, nullptr, &res, &out, nullptr));
     if (keep_debug) {
         debug["r" + std::to_string(idx) + ".h1"] = h1;
@@ -907,7 +920,7 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     RUN(geglu_fwd(sv.ff.p, sv.ff.ld, rows, 4 * C, g16.p, g16.ld, st_));
     H16 t3 = new16(B, H, W, C);
     S2I_TRY(gemm(g16, false, 1, T.ff2.w, 4 * C, C, 4 * C, T.ff2.b, nullptr, &sv.t2, nullptr, &t3));
-    out = new32(B, H, W, C);
+    out = out32(B, H, W, C);
     S2I_TRY(gemm(t3, false, 1, T.proj_out.w, C, C, C, T.proj_out.b, nullptr, &x, &out, nullptr));
     if (keep_debug) {
         const std::string pre = "t" + std::to_string(idx);
@@ -975,6 +988,7 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
     const int B = B_, H = H_, W = W_;
     const int* boc = cfg.boc;
     arena_.reset();
+    dest_set_ = false;
     stats_off_ = 0;
     stats_cap_ = (size_t)kStatsSlots * B * kGroups * 2;
     stats_ = dalloc<double>(stats_cap_);
@@ -988,25 +1002,56 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
     ctx16_ = new16(B, 1, cfg.ctx_len, cfg.cross_dim);
     if (!reuse_kv_) RUN(cast2d(ctx_, cfg.cross_dim, (long)B * cfg.ctx_len, cfg.cross_dim, 1.f, ctx16_.p, ctx16_.ld, st_));
 
+    // Up-path concat buffers, planned before anything runs: the k-th up resnet reads cat([h, skip]) (diffusers
+    // UpBlock2D / CrossAttnUpBlock2D), skip = the (K-1-k)-th tensor the down path pushed.  Both producers write straight
+    // into their half of the buffer (row stride = the concatenated width), so the concat costs no launch.
+    const int K = 4 * (cfg.layers + 1);
+    std::vector<F32> cats(K);
+    std::vector<int> cat_h(K);
+    {
+        std::vector<int> sC, sH, sW;                  // skip channels / spatial size, push order
+        int hh = H, ww = W;
+        sC.push_back(boc[0]); sH.push_back(hh); sW.push_back(ww);
+        for (int i = 0; i < 4; ++i) {
+            for (int j = 0; j < cfg.layers; ++j) { sC.push_back(boc[i]); sH.push_back(hh); sW.push_back(ww); }
+            if (i < 3) { hh /= 2; ww /= 2; sC.push_back(boc[i]); sH.push_back(hh); sW.push_back(ww); }
+        }
+        if ((int)sC.size() != K) return set_error(S2I_ERR_STATE, "unet: skip plan out of sync (%d vs %d)", (int)sC.size(), K);
+        int hC = boc[3], sp0 = K;
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < cfg.layers + 1; ++j) {
+                const int k = i * (cfg.layers + 1) + j;
+                --sp0;
+                cat_h[k] = hC;
+                cats[k] = new32(B, sH[sp0], sW[sp0], hC + sC[sp0]);
+                hC = boc[3 - i];
+            }
+    }
+    // skip n (push order) is the second half of cats[K - 1 - n]
+    auto reserve_skip = [&](int n) { reserve(cats[K - 1 - n], cat_h[K - 1 - n], cats[K - 1 - n].C - cat_h[K - 1 - n]); };
+
     // conv_in (im2col GEMM, K = 9*in_ch padded to 64)
     F32 x = new32(B, H, W, cfg.in_ch);
     RUN(nchw_to_nhwc(x_nchw, B, cfg.in_ch, H, W, x.p, x.ld, st_));
     H16 col = new16(B, H, W, 64);
     RUN(im2col3x3(x.p, x.ld, B, H, W, cfg.in_ch, 1, col.p, col.ld, st_));
-    F32 h = new32(B, H, W, boc[0]);
+    skips_.clear();
+    reserve_skip(0);
+    F32 h = out32(B, H, W, boc[0]);
     S2I_TRY(gemm(col, false, 1, conv_in_.w, 64, boc[0], 64, conv_in_.b, nullptr, nullptr, &h, nullptr));
     if (keep_debug) debug["conv_in"] = h;
 
-    skips_.clear();
     skips_.push_back(h);
     int ri = 0, ti = 0;
     // ---- down
     for (int i = 0; i < 4; ++i) {
         for (int j = 0; j < cfg.layers; ++j) {
             F32 o;
+            if (i == 3) reserve_skip((int)skips_.size());        // no transformer follows: the resnet output is the skip
             S2I_TRY(resblock(ri++, h, o));
             h = o;
             if (i < 3) {
+                reserve_skip((int)skips_.size());
                 S2I_TRY(transformer(ti++, h, o));
                 h = o;
             }
@@ -1016,7 +1061,8 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
             const int Ho = h.H / 2, Wo = h.W / 2, C = h.C;
             H16 c2 = new16(B, Ho, Wo, 9 * C);
             RUN(im2col3x3(h.p, h.ld, B, h.H, h.W, C, 2, c2.p, c2.ld, st_));
-            F32 o = new32(B, Ho, Wo, C);
+            reserve_skip((int)skips_.size());
+            F32 o = out32(B, Ho, Wo, C);
             S2I_TRY(gemm(c2, false, 1, down_[i].w, 9L * C, C, 9 * C, down_[i].b, nullptr, nullptr, &o, nullptr));
             h = o;
             skips_.push_back(h);
@@ -1033,6 +1079,7 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
         S2I_TRY(transformer(ti++, h, o));
         h = o;
         taps[3] = h;
+        reserve(cats[0], 0, cat_h[0]);                           // the mid block's output is the first half of cats[0]
         S2I_TRY(resblock(ri++, h, o));
         h = o;
         taps[5] = h;
@@ -1043,15 +1090,20 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
     up_cat_.clear();
     for (int i = 0; i < 4; ++i) {
         for (int j = 0; j < cfg.layers + 1; ++j) {
+            const int k = i * (cfg.layers + 1) + j;
             const F32& sk = skips_[--sp];
-            F32 cat = new32(B, h.H, h.W, h.C + sk.C);
-            RUN(add2d(h.p, h.ld, nullptr, 0, h.rows(), h.C, cat.p, cat.ld, nullptr, 0, st_));
-            RUN(add2d(sk.p, sk.ld, nullptr, 0, sk.rows(), sk.C, cat.p + h.C, cat.ld, nullptr, 0, st_));
+            F32 cat = cats[k];
+            if (cat.C != h.C + sk.C || cat.H != h.H || h.p != cat.p || sk.p != cat.p + h.C)
+                return set_error(S2I_ERR_STATE, "unet: concat plan out of sync at up resnet %d", k);
             up_cat_.push_back({h.C, sp});
+            // whichever call ends this iteration produces the first half of the next concat buffer
+            const bool ups = j == cfg.layers && i < 3, tfm = i > 0, more = k + 1 < K;
             F32 o;
+            if (more && !tfm && !ups) reserve(cats[k + 1], 0, cat_h[k + 1]);
             S2I_TRY(resblock(ri++, cat, o));
             h = o;
-            if (i > 0) {
+            if (tfm) {
+                if (more && !ups) reserve(cats[k + 1], 0, cat_h[k + 1]);
                 S2I_TRY(transformer(ti++, h, o));
                 h = o;
             }
@@ -1059,7 +1111,8 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
         if (i < 3) {
             H16 u = new16(B, 2 * h.H, 2 * h.W, h.C);
             RUN(upsample2x(h.p, h.ld, B, h.H, h.W, h.C, u.p, u.ld, st_));
-            F32 o = new32(B, 2 * h.H, 2 * h.W, h.C);
+            reserve(cats[(i + 1) * (cfg.layers + 1)], 0, cat_h[(i + 1) * (cfg.layers + 1)]);
+            F32 o = out32(B, 2 * h.H, 2 * h.W, h.C);
             S2I_TRY(gemm(u, true, 9, up_[i].w, 9L * h.C, h.C, h.C, up_[i].b, nullptr, nullptr, &o, nullptr));
             h = o;
             taps[6 + i] = h;

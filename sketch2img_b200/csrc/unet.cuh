@@ -215,6 +215,10 @@ class UNet {
     int run_backward(float* const tap_grads[9], float* dx_nchw);
 
     F32 new32(int B, int H, int W, int C);
+    F32 out32(int B, int H, int W, int C);
+    void reserve(const F32& cat, int c0, int C);
+    F32 dest_;                   // reserved destination of the next layer output (see out32)
+    bool dest_set_ = false;
     H16 new16(int B, int H, int W, int C);
     double* new_stats();
     template <class T> T* dalloc(size_t n);

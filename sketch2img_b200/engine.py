@@ -103,7 +103,10 @@ class UNetEngine:
         """NHWC fp32 view [B,H,W,C] of tap k (hook order of latent_predictor.py:63-80)."""
         p, B, H, W, Cc = C.c_void_p(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _lib.check(self.lib.s2i_unet_tap(self._h, k, C.byref(p), C.byref(B), C.byref(H), C.byref(W), C.byref(Cc)))
-        return device_view(p.value, (B.value, H.value, W.value, Cc.value))
+        ld = C.c_longlong()
+        _lib.check(self.lib.s2i_unet_tap_stride(self._h, k, C.byref(ld)))
+        return device_view(p.value, (B.value, H.value, W.value, Cc.value),
+                           (H.value * W.value * ld.value, W.value * ld.value, ld.value, 1))
 
     def taps(self):
         return [self.tap(k) for k in range(9)]

@@ -101,6 +101,8 @@ class LGPEngine:
 
     def forward_taps(self, taps, B, L, noise, sigma, train):
         """taps: 9 NHWC fp32 cuda tensors; noise NCHW [B/2,4,L,L]."""
+        taps = [t.contiguous() for t in taps]      # engine taps may be strided slices of the UNet's concat buffers
+        self._taps_keepalive = taps
         ptrs = (C.c_void_p * 9)(*[t.data_ptr() for t in taps])
         sizes = (C.c_int * 9)(*[t.shape[1] for t in taps])
         chans = (C.c_int * 9)(*[t.shape[3] for t in taps])
@@ -116,7 +118,8 @@ class LGPEngine:
         """-> (loss [B/2], tap grads (9 NHWC fp32 tensors, scaled), grad_scale).  cond_only: the gradients of the B/2 cond
         samples only (batch entries 1, 3, ...), which is all pipeline.py:159 keeps."""
         S = target.shape[0]
-        grads = [torch.empty_like(t[1::2]) if cond_only else torch.empty_like(t) for t in taps]
+        grads = [torch.empty((t.shape[0] // 2 if cond_only else t.shape[0],) + tuple(t.shape[1:]), device=t.device,
+                             dtype=torch.float32) for t in taps]
         loss = torch.empty(S, device=target.device, dtype=torch.float32)
         scale = C.c_float()
         fn = self.lib.s2i_lgp_loss_backward_cond if cond_only else self.lib.s2i_lgp_loss_backward

@@ -83,6 +83,41 @@ def test_sat_sampling_matches_reference_fixture(cuda):
     assert max(errs.values()) < 5e-3
 
 
+def test_sat_sampling_two_images_per_call_matches_oracle(cuda):
+    """Two images per call (config 4 runs batches): the reference concatenates [uncond_0, uncond_1, cond_0, cond_1]
+    (pipeline.py:85) and its sketch features come in that order; the engine's batch is sample-major too, so the features
+    pass through unpermuted.  Oracle: oracle/port.py's loop with SatMixinOracle on the same batch, on CPU."""
+    from sketch2img_b200.pipeline import AntiGradientPipeline
+    from sketch2img_b200.scheduler import DDIMScheduler
+    port, o_unet, o_sat, unet, sat = _build("tiny21", cuda)
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    g = torch.Generator().manual_seed(77)
+    L, D = o_unet.config.sample_size, o_unet.config.cross_attention_dim
+    lat = torch.randn(2, 4, L, L, generator=g)
+    emb = torch.randn(4, 77, D, generator=g)                      # [uncond_0, uncond_1, cond_0, cond_1]
+    res = port.make_res_samples(o_unet, 4)
+    o_sat.set_res_samples(res)
+    o_sat.set_scale(0.7)
+    sat.set_res_samples([tuple(t.cuda() for t in tup) for tup in res])
+    sat.set_scale(0.7)
+    want = {}
+    port.guided_sample(o_unet, None, port.make_scheduler("v_prediction"), emb, lat.clone(), None, num_steps=4,
+                       callback=lambda i, t, l: want.__setitem__(int(i), l.detach().clone()))
+    pipe = AntiGradientPipeline(unet=unet, scheduler=DDIMScheduler(prediction_type="v_prediction"))
+    got = {}
+    pipe(["a", "b"], num_inference_steps=4, guidance_scale=7.5, latents=lat.cuda(), sketch_image=None, prompt_embeds=emb.cuda(),
+         output_type="latent", callback=lambda i, t, l: got.__setitem__(int(i), l.detach().float().cpu().clone()))
+    errs = {i: rel(got[i], want[i]) for i in want}
+    print("tiny21 + SatMixin, 2 images per call, per-step rel err vs oracle", {i: "%.2e" % e for i, e in errs.items()})
+    assert max(errs.values()) < 5e-3
+    # and each image equals its own single-image call (samples are closed computations)
+    for s in range(2):
+        sat.set_res_samples([tuple(t[[s, 2 + s]].cuda() for t in tup) for tup in res])
+        one = pipe("a", num_inference_steps=4, guidance_scale=7.5, latents=lat[s:s + 1].cuda(), sketch_image=None,
+                   prompt_embeds=emb[[s, 2 + s]].cuda(), output_type="latent")
+        assert rel(one, got[3][s:s + 1]) < 3e-3
+
+
 def test_sat_sd21_shape_forward_matches_oracle(cuda):
     """The real SD2.1 topology (320/640/1280 channels, 5/10/20/20 heads of 64, context 1024, linear projections) at a
     48 x 48 latent: every block through the fused attention kernel (N = 2304 .. 36 tokens)."""
