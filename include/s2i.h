@@ -88,7 +88,7 @@ int s2i_attention(const void* q, long long ldq, int q_c0, const void* kv, long l
  *   lse: the forward's log-sum-exp; delta_scratch: fp32 device [B*heads][Nq]
  *   dq : fp16 device [B][Nq][lddq], head h at dq_c0 + h*dp
  *   dkv: fp16 device [B][Nk][lddkv] or NULL (cross-attention to a constant context: only dQ); dK heads at dk_c0 + h*dp,
- *        dV heads at dv_c0 + h*dp.   Nq >= 128, Nk >= 64, dp a multiple of 16 and <= 128. */
+ *        dV heads at dv_c0 + h*dp.   Nq >= 128, Nk >= 64, dp a multiple of 16 and <= 192. */
 int s2i_attention_backward(const void* q, long long ldq, int q_c0, const void* kv, long long ldkv, int k_c0, int v_c0,
                            const void* d_out, const void* out, long long ldo, const float* lse, float* delta_scratch, int B,
                            int heads, int Nq, int Nk, int dp, int d_true, float scale, void* dq, long long lddq, int dq_c0,

@@ -369,8 +369,10 @@ int make_map(CUtensorMap* m, const __half* ptr, long ld, int N, int B, int box_r
 }  // namespace
 
 bool attn_bwd_supported(int Nq, int Nk, int dp) {
-    // both modes keep 256 + 2*dp TMEM columns and (2 resident + 2x2 streamed + staging) tiles in shared memory
-    return Nq >= kRows && Nk >= kCols && dp % 16 == 0 && dp >= 16 && dp <= 128;
+    // TMEM: the tile products (128 columns single-, 256 double-buffered) + dp (dQ) or 2 dp (dK | dV) accumulator columns must
+    // fit 512; shared memory: 2 resident + 2 x 2 streamed operand tiles of ceil(dp / 64) chunks + staging must fit 227 KB.
+    // dp = 160 (SD1.5's 16 x 16 level) runs the dK / dV mode single-buffered in 448 columns.
+    return Nq >= kRows && Nk >= kCols && dp % 16 == 0 && dp >= 16 && dp <= 192;
 }
 
 int attn_bwd_launch(const AttnBwdDesc& d, cudaStream_t stream) {
@@ -420,8 +422,9 @@ int attn_bwd_launch(const AttnBwdDesc& d, cudaStream_t stream) {
         // they fit 256 columns and two CTAs share the SM -- the softmax warps are issue-bound, so a second CTA's warps
         // on every scheduler are worth more than overlapping this CTA's own tile products
         const int nacc = mode ? 2 : 1;
-        p.nT = (128 + nacc * d.dp <= 256) ? 1 : 2;
+        p.nT = (128 + nacc * d.dp <= 256 || 256 + nacc * d.dp > 512) ? 1 : 2;
         p.tmem_cols = (p.nT * 128 + nacc * d.dp <= 256) ? 256 : 512;
+        if (p.nT * 128 + nacc * d.dp > 512) return set_error(S2I_ERR_ARG, "attn_bwd: head dim %d does not fit TMEM", d.dp);
         const int fixed = 2 * nkc * kChunk16 + kStages * 2 * nkc * kChunk8 + 2048 + 1024;   // operands + barriers/stats + slack
         p.sbufs = (fixed + 2 * nstaged * kChunk16 <= 227 * 1024) ? 2 : 1;
         // prefer two co-resident CTAs when a single staging buffer makes the footprint fit half an SM

@@ -111,7 +111,10 @@ def _bwd(L, q, ldq, q_c0, kv, ldkv, k_c0, v_c0, dO, out, lse, B, heads, Nq, Nk, 
 
 
 @pytest.mark.parametrize("B,N,heads,d,dp", [(2, 256, 8, 40, 48), (1, 1024, 4, 80, 80), (2, 4096, 2, 40, 48),
-                                            (1, 320, 5, 64, 64), (3, 576, 2, 64, 64), (2, 128, 8, 40, 48), (1, 200, 2, 16, 16)])
+                                            (1, 320, 5, 64, 64), (3, 576, 2, 64, 64), (2, 128, 8, 40, 48), (1, 200, 2, 16, 16),
+                                            # SD1.5's 16 x 16 level: 160-wide heads (three 64-column operand chunks, dK | dV
+                                            # accumulators in 320 TMEM columns next to single-buffered tile products)
+                                            (2, 256, 8, 160, 160), (1, 300, 2, 160, 160), (1, 256, 2, 192, 192)])
 def test_self_attention_backward(L, cuda, B, N, heads, d, dp):
     """dQ, dK, dV of softmax(scale Q K^T) V against fp64 autograd on the same fp16 operands (recompute from the
     forward's log-sum-exp; P and dS are rounded to fp16 before the accumulating products like the unfused path)."""
@@ -136,10 +139,11 @@ def test_self_attention_backward(L, cuda, B, N, heads, d, dp):
     assert rel(dkv[:, :, HP:].float(), back(gv)) < 5e-3
 
 
-@pytest.mark.parametrize("Nq,Nk", [(256, 77), (4096, 77), (128, 64), (256, 200)])
-def test_cross_attention_backward(L, cuda, Nq, Nk):
+@pytest.mark.parametrize("Nq,Nk,d,dp", [(256, 77, 40, 48), (4096, 77, 40, 48), (128, 64, 40, 48), (256, 200, 40, 48),
+                                        (256, 77, 160, 160)])
+def test_cross_attention_backward(L, cuda, Nq, Nk, d, dp):
     """Only dQ (the text context is a constant); ragged key count."""
-    B, heads, d, dp = 2, 8, 40, 48
+    B, heads = 2, 8
     HP = heads * dp
     g = torch.Generator(device="cpu").manual_seed(Nq * 5 + Nk)
     q = torch.randn(B, Nq, heads, dp, generator=g)
