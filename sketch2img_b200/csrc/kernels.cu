@@ -815,6 +815,9 @@ __global__ void __launch_bounds__(kGnClT) gn_cluster_kernel(const GnClArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
+// One warp per row; the row is read ONCE into registers (all loads in flight together: NV float4 per lane cover C <= 128 NV
+// channels), so the kernel is one memory round trip + two warp reductions instead of three dependent passes.
+template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, long ldx, long rows, int C,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float eps, __half* __restrict__ out16, long ld16,
@@ -826,33 +829,43 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     if (row >= rows) return;
     const float* xr = x + row * ldx;
     const int vec = C >> 2;
-    float s = 0.f;
-    for (int q = lane; q < vec; q += 32) {
-        const float4 v = ldg4(xr + 4 * q);
-        s += (v.x + v.y) + (v.z + v.w);
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int q = lane + 32 * i;
+        v[i] = q < vec ? ldg4(xr + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     const float mean = warp_sum(s) / C;
     float ss = 0.f;
-    for (int q = lane; q < vec; q += 32) {
-        const float4 v = ldg4(xr + 4 * q);
-        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-        ss += (a * a + b * b) + (c * c + d * d);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        if (lane + 32 * i < vec) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            ss += (a * a + b * b) + (c * c + d * d);
+        }
     }
     const float rstd = rsqrtf(warp_sum(ss) / C + eps);
     if (stats && lane == 0) {
         stats[row * 2 + 0] = mean;
         stats[row * 2 + 1] = rstd;
     }
-    for (int q = lane; q < vec; q += 32) {
-        const float4 v = ldg4(xr + 4 * q);
-        const float4 g = ldg4(gamma + 4 * q);
-        const float4 bb = ldg4(beta + 4 * q);
-        *reinterpret_cast<uint2*>(out16 + row * ld16 + 4 * q) =
-            pack_half4((v.x - mean) * rstd * g.x + bb.x, (v.y - mean) * rstd * g.y + bb.y,
-                       (v.z - mean) * rstd * g.z + bb.z, (v.w - mean) * rstd * g.w + bb.w);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int q = lane + 32 * i;
+        if (q < vec) {
+            const float4 g = ldg4(gamma + 4 * q);
+            const float4 bb = ldg4(beta + 4 * q);
+            *reinterpret_cast<uint2*>(out16 + row * ld16 + 4 * q) =
+                pack_half4((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y,
+                           (v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+        }
     }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, long ldd,
                                                      const float* __restrict__ x, long ldx, long rows, int C,
                                                      const float* __restrict__ gamma, const float* __restrict__ stats,
@@ -866,32 +879,42 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     if (row >= rows) return;
     const float* xr = x + row * ldx;
     const float* dr = dy + row * ldd;
-    const float mean = stats[row * 2 + 0], rstd = stats[row * 2 + 1];
     const int vec = C >> 2;
+    // xh = normalised input, hd = dy * gamma: both kept in registers between the reduction and the apply
+    float4 xh[NV], hd[NV];
+    const float mean = stats[row * 2 + 0], rstd = stats[row * 2 + 1];
     float a1 = 0.f, a2 = 0.f;
-    for (int q = lane; q < vec; q += 32) {
-        const float4 v = ldg4(xr + 4 * q);
-        const float4 d = ldg4(dr + 4 * q);
-        const float4 g = ldg4(gamma + 4 * q);
-        const float h0 = d.x * g.x, h1 = d.y * g.y, h2 = d.z * g.z, h3 = d.w * g.w;
-        a1 += (h0 + h1) + (h2 + h3);
-        a2 += h0 * (v.x - mean) * rstd + h1 * (v.y - mean) * rstd + h2 * (v.z - mean) * rstd + h3 * (v.w - mean) * rstd;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int q = lane + 32 * i;
+        if (q < vec) {
+            const float4 v = ldg4(xr + 4 * q);
+            const float4 d = ldg4(dr + 4 * q);
+            const float4 g = ldg4(gamma + 4 * q);
+            hd[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+            xh[i] = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+            a1 += (hd[i].x + hd[i].y) + (hd[i].z + hd[i].w);
+            a2 += hd[i].x * xh[i].x + hd[i].y * xh[i].y + hd[i].z * xh[i].z + hd[i].w * xh[i].w;
+        } else {
+            hd[i] = xh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     const float m1 = warp_sum(a1) / C, m2 = warp_sum(a2) / C;
-    for (int q = lane; q < vec; q += 32) {
-        const float4 v = ldg4(xr + 4 * q);
-        const float4 d = ldg4(dr + 4 * q);
-        const float4 g = ldg4(gamma + 4 * q);
-        float o0 = rstd * (d.x * g.x - m1 - (v.x - mean) * rstd * m2);
-        float o1 = rstd * (d.y * g.y - m1 - (v.y - mean) * rstd * m2);
-        float o2 = rstd * (d.z * g.z - m1 - (v.z - mean) * rstd * m2);
-        float o3 = rstd * (d.w * g.w - m1 - (v.w - mean) * rstd * m2);
-        if (add) {
-            const float4 av = ldg4(add + row * ldadd + 4 * q);
-            o0 += av.x; o1 += av.y; o2 += av.z; o3 += av.w;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int q = lane + 32 * i;
+        if (q < vec) {
+            float o0 = rstd * (hd[i].x - m1 - xh[i].x * m2);
+            float o1 = rstd * (hd[i].y - m1 - xh[i].y * m2);
+            float o2 = rstd * (hd[i].z - m1 - xh[i].z * m2);
+            float o3 = rstd * (hd[i].w - m1 - xh[i].w * m2);
+            if (add) {
+                const float4 av = ldg4(add + row * ldadd + 4 * q);
+                o0 += av.x; o1 += av.y; o2 += av.z; o3 += av.w;
+            }
+            if (dx32) *reinterpret_cast<float4*>(dx32 + row * ld32 + 4 * q) = make_float4(o0, o1, o2, o3);
+            if (dx16) *reinterpret_cast<uint2*>(dx16 + row * ld16 + 4 * q) = pack_half4(o0, o1, o2, o3);
         }
-        if (dx32) *reinterpret_cast<float4*>(dx32 + row * ld32 + 4 * q) = make_float4(o0, o1, o2, o3);
-        if (dx16) *reinterpret_cast<uint2*>(dx16 + row * ld16 + 4 * q) = pack_half4(o0, o1, o2, o3);
     }
 }
 
@@ -1460,8 +1483,14 @@ int gn_backward(const float* dy, long ldd, const float* x, long ldx, int B, int 
 int ln_fwd(const float* x, long ldx, long rows, int C, const float* gamma, const float* beta, float eps, void* out16,
            long ld16, float* stats, cudaStream_t st) {
     S2I_REQ((C & 3) == 0 && (ldx & 3) == 0 && (ld16 & 3) == 0, "ln_fwd: alignment");
-    S2I_LAUNCH((ln_fwd_kernel), (unsigned)ceil_div_l(rows, 8), 256, 0, st, x, ldx, rows, C, gamma, beta, eps, (__half*)out16, ld16,
-                                                                stats);
+    S2I_REQ(C <= 2560, "ln_fwd: at most 2560 channels (the row is held in registers)");
+    const unsigned grid = (unsigned)ceil_div_l(rows, 8);
+    __half* o = (__half*)out16;
+    // NV float4 per lane: 320 -> 3, 640 -> 5, 1280 -> 10, up to 2560 -> 20
+    if (C <= 384) S2I_LAUNCH((ln_fwd_kernel<3>), grid, 256, 0, st, x, ldx, rows, C, gamma, beta, eps, o, ld16, stats);
+    else if (C <= 640) S2I_LAUNCH((ln_fwd_kernel<5>), grid, 256, 0, st, x, ldx, rows, C, gamma, beta, eps, o, ld16, stats);
+    else if (C <= 1280) S2I_LAUNCH((ln_fwd_kernel<10>), grid, 256, 0, st, x, ldx, rows, C, gamma, beta, eps, o, ld16, stats);
+    else S2I_LAUNCH((ln_fwd_kernel<20>), grid, 256, 0, st, x, ldx, rows, C, gamma, beta, eps, o, ld16, stats);
     S2I_LAUNCH_CHECK();
     return 0;
 }
@@ -1471,8 +1500,15 @@ int ln_bwd(const float* dy, long ldd, const float* x, long ldx, long rows, int C
            cudaStream_t st) {
     S2I_REQ((C & 3) == 0 && (ldx & 3) == 0 && (ldd & 3) == 0 && (ldadd & 3) == 0 && (ld32 & 3) == 0 && (ld16 & 3) == 0,
             "ln_bwd: alignment");
-    S2I_LAUNCH((ln_bwd_kernel), (unsigned)ceil_div_l(rows, 8), 256, 0, st, dy, ldd, x, ldx, rows, C, gamma, stats, add, ldadd, dx32,
-                                                                ld32, (__half*)dx16, ld16);
+    S2I_REQ(C <= 1280, "ln_bwd: at most 1280 channels (the row and its gradient are held in registers)");
+    const unsigned grid = (unsigned)ceil_div_l(rows, 8);
+    __half* o = (__half*)dx16;
+    if (C <= 384)
+        S2I_LAUNCH((ln_bwd_kernel<3>), grid, 256, 0, st, dy, ldd, x, ldx, rows, C, gamma, stats, add, ldadd, dx32, ld32, o, ld16);
+    else if (C <= 640)
+        S2I_LAUNCH((ln_bwd_kernel<5>), grid, 256, 0, st, dy, ldd, x, ldx, rows, C, gamma, stats, add, ldadd, dx32, ld32, o, ld16);
+    else
+        S2I_LAUNCH((ln_bwd_kernel<10>), grid, 256, 0, st, dy, ldd, x, ldx, rows, C, gamma, stats, add, ldadd, dx32, ld32, o, ld16);
     S2I_LAUNCH_CHECK();
     return 0;
 }
