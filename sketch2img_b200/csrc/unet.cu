@@ -596,9 +596,27 @@ int UNet::accumulate(F32& acc, const F32& g) {
         return 0;
     }
     F32 out = new32(acc.B, acc.H, acc.W, acc.C);
-    RUN(add2d(acc.p, acc.ld, g.p, g.ld, acc.rows(), acc.C, out.p, out.ld, nullptr, 0, st_));
+    H16 oh = new16(acc.B, acc.H, acc.W, acc.C);
+    RUN(add2d(acc.p, acc.ld, g.p, g.ld, acc.rows(), acc.C, out.p, out.ld, oh.p, oh.ld, st_));
+    out.h = oh.p;
+    out.hld = oh.ld;
     acc = out;
     return 0;
+}
+
+H16 UNet::half_of(const F32& t) {
+    H16 h;
+    h.B = t.B; h.H = t.H; h.W = t.W; h.C = t.C;
+    if (t.h) {
+        h.p = t.h;
+        h.ld = t.hld;
+        return h;
+    }
+    h = new16(t.B, t.H, t.W, t.C);
+    if (!dry_) {
+        if (cast2d(t.p, t.ld, t.rows(), t.C, 1.f, h.p, h.ld, st_) != 0) h.p = nullptr;
+    }
+    return h;
 }
 
 // ================================================================================================== ResnetBlock2D
@@ -683,8 +701,8 @@ int UNet::resblock_bwd(int idx, const F32& dout, F32& dx) {
     const ResBlock& R = res_[idx];
     const ResSave S = sub(rsave_[idx]);
     const int B = dout.B, H = dout.H, W = dout.W, HW = H * W;
-    H16 d16 = new16(B, H, W, R.Cout);
-    RUN(cast2d(dout.p, dout.ld, dout.rows(), R.Cout, 1.f, d16.p, d16.ld, st_));
+    H16 d16 = half_of(dout);
+    if (!d16.p) return S2I_ERR_CUDA;
     F32 da2 = new32(B, H, W, R.Cout);
     S2I_TRY(gemm(d16, true, 9, R.c2.wd, 9L * R.Cout, R.Cout, R.Cout, nullptr, nullptr, nullptr, &da2, nullptr));
     double* bs2 = new_stats();
@@ -695,15 +713,18 @@ int UNet::resblock_bwd(int idx, const F32& dout, F32& dx) {
     S2I_TRY(gemm(dh1, true, 9, R.c1.wd, 9L * R.Cout, R.Cin, R.Cout, nullptr, nullptr, nullptr, &da1, nullptr));
     double* bs1 = new_stats();
     dx = new32(B, H, W, R.Cin);
+    H16 dxh = new16(B, H, W, R.Cin);        // fp16 copy for the next layer's GEMMs, written by the same kernel
     if (R.has_sc) {
         F32 tmp = new32(B, H, W, R.Cin);
         RUN(gn_backward(da1.p, da1.ld, S.x.p, S.x.ld, B, HW, R.Cin, S.s1, bs1, R.n1.g, R.n1.b, R.n1.eps, 1, nullptr, 0,
                         tmp.p, tmp.ld, nullptr, 0, st_));
-        S2I_TRY(gemm(d16, false, 1, R.sc.wd, R.Cout, R.Cin, R.Cout, nullptr, nullptr, &tmp, &dx, nullptr));
+        S2I_TRY(gemm(d16, false, 1, R.sc.wd, R.Cout, R.Cin, R.Cout, nullptr, nullptr, &tmp, &dx, &dxh));
     } else {
         RUN(gn_backward(da1.p, da1.ld, S.x.p, S.x.ld, B, HW, R.Cin, S.s1, bs1, R.n1.g, R.n1.b, R.n1.eps, 1, dout.p,
-                        dout.ld, dx.p, dx.ld, nullptr, 0, st_));
+                        dout.ld, dx.p, dx.ld, dxh.p, dxh.ld, st_));
     }
+    dx.h = dxh.p;
+    dx.hld = dxh.ld;
     return 0;
 }
 
@@ -938,8 +959,8 @@ int UNet::transformer_bwd(int idx, const F32& dout, F32& dx) {
     const TfmSave S = sub(tsave_[idx], T);
     const int B = dout.B, H = dout.H, W = dout.W, HW = H * W, C = T.C;
     const long rows = dout.rows();
-    H16 d16 = new16(B, H, W, C);
-    RUN(cast2d(dout.p, dout.ld, rows, C, 1.f, d16.p, d16.ld, st_));
+    H16 d16 = half_of(dout);
+    if (!d16.p) return S2I_ERR_CUDA;
     F32 dt3 = new32(B, H, W, C);
     H16 dt3h = new16(B, H, W, C);
     S2I_TRY(gemm(d16, false, 1, T.proj_out.wd, C, C, C, nullptr, nullptr, nullptr, &dt3, &dt3h));
@@ -976,8 +997,11 @@ int UNet::transformer_bwd(int idx, const F32& dout, F32& dx) {
     S2I_TRY(gemm(dt0h, false, 1, T.proj_in.wd, C, C, C, nullptr, nullptr, nullptr, &dn, nullptr));
     double* bs = new_stats();
     dx = new32(B, H, W, C);
+    H16 dxh = new16(B, H, W, C);
     RUN(gn_backward(dn.p, dn.ld, S.x.p, S.x.ld, B, HW, C, S.gs, bs, T.gn.g, T.gn.b, T.gn.eps, 0, dout.p, dout.ld, dx.p,
-                     dx.ld, nullptr, 0, st_));
+                     dx.ld, dxh.p, dxh.ld, st_));
+    dx.h = dxh.p;
+    dx.hld = dxh.ld;
     return 0;
 }
 
@@ -1157,8 +1181,8 @@ int UNet::run_backward(float* const tap_grads[9], float* dx_nchw) {
     for (int i = 2; i >= 0; --i) {
         S2I_TRY(accumulate(d, tapg(6 + i)));
         {   // upsampler backward: conv dgrad then 2x2 sum-pool
-            H16 d16 = new16(B, d.H, d.W, d.C);
-            RUN(cast2d(d.p, d.ld, d.rows(), d.C, 1.f, d16.p, d16.ld, st_));
+            H16 d16 = half_of(d);
+            if (!d16.p) return S2I_ERR_CUDA;
             F32 du = new32(B, d.H, d.W, d.C);
             S2I_TRY(gemm(d16, true, 9, up_[i].wd, 9L * d.C, d.C, d.C, nullptr, nullptr, nullptr, &du, nullptr));
             F32 dn = new32(B, d.H / 2, d.W / 2, d.C);
@@ -1175,6 +1199,7 @@ int UNet::run_backward(float* const tap_grads[9], float* dx_nchw) {
             const UpCat& uc = up_cat_[--ci];
             F32 dsk = o;
             dsk.p = o.p + uc.ch;
+            if (o.h) dsk.h = o.h + uc.ch;
             dsk.C = o.C - uc.ch;
             dskip[uc.skip] = dsk;
             d = o;
@@ -1219,8 +1244,8 @@ int UNet::run_backward(float* const tap_grads[9], float* dx_nchw) {
     }
     S2I_TRY(accumulate(d, dskip[0]));
     // conv_in backward
-    H16 d16 = new16(B, d.H, d.W, d.C);
-    RUN(cast2d(d.p, d.ld, d.rows(), d.C, 1.f, d16.p, d16.ld, st_));
+    H16 d16 = half_of(d);
+    if (!d16.p) return S2I_ERR_CUDA;
     F32 dx = new32(B, d.H, d.W, cfg.in_ch);
     S2I_TRY(gemm(d16, true, 9, conv_in_d_.wd, 9L * d.C, cfg.in_ch, d.C, nullptr, nullptr, nullptr, &dx, nullptr));
     RUN(nhwc_to_nchw(dx.p, dx.ld, B, cfg.in_ch, d.H, d.W, dx_nchw, st_));

@@ -33,6 +33,10 @@ struct F32 {
     float* p = nullptr;
     long ld = 0;
     int B = 0, H = 0, W = 0, C = 0;
+    // optional fp16 copy of the same values written by the producing kernel (backward pass: the next layer's GEMM operand,
+    // so no separate cast launch); same shape, pixel stride hld
+    __half* h = nullptr;
+    long hld = 0;
     long rows() const { return (long)B * H * W; }
 };
 struct H16 {
@@ -237,6 +241,7 @@ class UNet {
                       int Nk, const H16& P, const H16& o, const float* lse, H16& dq, long dq_c0, H16* dkv, long dk_c0,
                       long dv_c0);
     int accumulate(F32& acc, const F32& g);
+    H16 half_of(const F32& t);      // the fp16 copy of a backward tensor: its companion if the producer wrote one, else a cast
     F32 sub(const F32& t) const;
     H16 sub(const H16& t) const;
     ResSave sub(const ResSave& s) const;
