@@ -54,6 +54,12 @@ typedef struct s2i_gemm_desc {
     float* out32; long long ld32; void* out16; long long ld16; int out16_bf16;
     long long c_sb, c_sh; int relu;
     float qscale;   /* != 0: round the result as fp16(v / qscale) * qscale (mimics unscaled fp16 autograd rounding) */
+    /* Gated-GELU epilogue (diffusers GEGLU, the feed-forward of every BasicTransformerBlock inside modules/pipeline.py:96):
+     * the weight rows are interleaved in blocks of 32 -- output columns [64 b, 64 b + 32) = value features 32 b .., columns
+     * [64 b + 32, 64 b + 64) = their gates -- and out_glu [rows][N / 2] (fp16, pixel stride ld_glu) receives
+     * value * gelu(gate).  out16 (optional) still receives the interleaved projection itself.  Needs N % 64 == 0 and the
+     * TMA-epilogue kernel (K-major operands, Z = 1, no residual / out32 / split-K). */
+    void* out_glu; long long ld_glu;
 } s2i_gemm_desc;
 
 int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream);

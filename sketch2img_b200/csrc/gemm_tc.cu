@@ -53,7 +53,8 @@ struct __align__(64) GemmParams {
     CUtensorMap mapRes;      // fp32 residual  (N, W, H, B), box (32, tw, th, tb), 128B swizzle
     CUtensorMap mapO32;      // fp32 output, same geometry
     CUtensorMap mapO16;      // fp16 output, box (32, tw, th, tb), 64B swizzle
-    int has_res, has_o32, has_o16;
+    CUtensorMap mapGlu;      // fp16 gated-GELU output [rows][N / 2], same box / swizzle
+    int has_res, has_o32, has_o16, has_glu;
     int split_add;           // split-K by fp32 reduce-add into a zeroed output (split 0 carries bias + residual)
     int msub;                // M sub-tiles per CTA (1 or 2): two 128-row A tiles share every B tile (two TMEM accumulators)
     int tiles_m;             // number of 128-row M tiles of the problem
@@ -202,6 +203,8 @@ __device__ __forceinline__ void mma_loop(const GemmParams& p, const TileCtx& t, 
 // No per-thread global addressing, no predicates: ~100 instructions per chunk instead of ~1000 in gemm_tc_kernel.
 // Supports K-major operands, Z = 1, N % 32 == 0, alpha = 1, no ReLU / rounding emulation.
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }   // F.gelu
+
 constexpr int kChunk32Bytes = kBlockM * 32 * 4;   // 16 KB: 128 rows x 32 fp32 columns
 constexpr int kChunk16Bytes = kBlockM * 32 * 2;   //  8 KB: 128 rows x 32 fp16 columns
 constexpr int kMaxChunks = 8;
@@ -209,8 +212,10 @@ constexpr int kMaxChunks = 8;
 // ESETS epilogue warp quartets (warps 2..5, and 6..9 when ESETS = 2) take the tile's 32-column chunks in turn: the chunks
 // are independent (own residual / staging region, own bulk store), and one quartet alone works through them at ~0.75 us
 // per chunk -- a latency chain (TMEM load, shared-memory round trips, proxy fence, barrier), not a bandwidth limit.
-template <int ESETS>
-__global__ void __launch_bounds__(64 + 128 * ESETS, ESETS == 2 ? 2 : 1) gemm_tma_kernel(const __grid_constant__ GemmParams p) {
+// GLU: the gated-GELU epilogue (its own instantiation, so the plain epilogue's register budget is untouched).
+template <int ESETS, bool GLU>
+__global__ void __launch_bounds__(64 + 128 * ESETS, (ESETS == 2 && !GLU) ? 2 : 1)
+gemm_tma_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_stage_bytes = ((p.BN + 63) >> 6) * kChunkBytes;
@@ -219,7 +224,8 @@ __global__ void __launch_bounds__(64 + 128 * ESETS, ESETS == 2 ? 2 : 1) gemm_tma
     const int nch = p.BN >> 5;
     const int use32 = p.has_res | p.has_o32;
     int pipe_bytes = p.stages * stage_bytes;
-    const int epi_bytes = (use32 ? nch * kChunk32Bytes : 0) + (p.has_o16 ? nch * kChunk16Bytes : 0);
+    const int epi_bytes = (use32 ? nch * kChunk32Bytes : 0) + (p.has_o16 ? nch * kChunk16Bytes : 0) +
+                          (p.has_glu ? (nch >> 1) * kChunk16Bytes : 0);
     if (pipe_bytes < epi_bytes) pipe_bytes = epi_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + pipe_bytes);
     uint64_t* empty = full + p.stages;
@@ -239,6 +245,7 @@ __global__ void __launch_bounds__(64 + 128 * ESETS, ESETS == 2 ? 2 : 1) gemm_tma
         if (p.has_res) ptx::prefetch_tmap(&p.mapRes);
         if (p.has_o32) ptx::prefetch_tmap(&p.mapO32);
         if (p.has_o16) ptx::prefetch_tmap(&p.mapO16);
+        if (p.has_glu) ptx::prefetch_tmap(&p.mapGlu);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -322,6 +329,60 @@ __global__ void __launch_bounds__(64 + 128 * ESETS, ESETS == 2 ? 2 : 1) gemm_tma
                         ptx::tma_load_4d(smem + c * kChunk32Bytes, &p.mapRes, &r_full[c], t.n0 + c * 32, xs, ys, bs);
                     }
                 }
+            }
+            if constexpr (GLU) {
+                // gated GELU: chunk 2 pc holds 32 value columns, chunk 2 pc + 1 their gates -> 32 output columns
+                uint8_t* baseG = base16 + (p.has_o16 ? nch * kChunk16Bytes : 0);
+                for (int pc = eset; pc < (nch >> 1); pc += ESETS) {
+                    if (t.n0 + pc * 64 >= p.N) break;
+                    const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * p.BN + pc * 64);
+                    uint8_t* rowG = baseG + pc * kChunk16Bytes + r * 64;
+                    uint8_t* rowA = base16 + (2 * pc) * kChunk16Bytes + r * 64;
+                    uint8_t* rowB = rowA + kChunk16Bytes;
+    #pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {            // 16 value + 16 gate columns at a time (register budget)
+                        uint32_t ra[16], rg[16];
+                        ptx::tmem_ld_32x16(tcol + (uint32_t)(hh * 16), ra);
+                        ptx::tmem_ld_32x16(tcol + 32u + (uint32_t)(hh * 16), rg);
+                        ptx::tmem_ld_wait();
+    #pragma unroll
+                        for (int u = 0; u < 2; ++u) {           // 8 columns -> one 16-byte unit of each staging row
+                            float a[8], g[8];
+    #pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                a[j] = __uint_as_float(ra[8 * u + j]) + bias_s[pc * 64 + hh * 16 + 8 * u + j];
+                                g[j] = __uint_as_float(rg[8 * u + j]) + bias_s[pc * 64 + 32 + hh * 16 + 8 * u + j];
+                            }
+                            uint32_t ho[4], hv[4], hw[4];
+    #pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const __half2 o = __floats2half2_rn(a[2 * j] * gelu_erf(g[2 * j]), a[2 * j + 1] * gelu_erf(g[2 * j + 1]));
+                                const __half2 v = __floats2half2_rn(a[2 * j], a[2 * j + 1]);
+                                const __half2 w = __floats2half2_rn(g[2 * j], g[2 * j + 1]);
+                                ho[j] = *reinterpret_cast<const uint32_t*>(&o);
+                                hv[j] = *reinterpret_cast<const uint32_t*>(&v);
+                                hw[j] = *reinterpret_cast<const uint32_t*>(&w);
+                            }
+                            const uint32_t unit = (uint32_t)(hh * 2 + u);
+                            *reinterpret_cast<uint4*>(rowG + ((unit ^ sw64) << 4)) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+                            if (p.has_o16) {
+                                *reinterpret_cast<uint4*>(rowA + ((unit ^ sw64) << 4)) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+                                *reinterpret_cast<uint4*>(rowB + ((unit ^ sw64) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            }
+                        }
+                    }
+                    ptx::fence_proxy_async();
+                    ptx::named_bar_sync(2 + eset, 128);
+                    if (el == 0) {
+                        ptx::tma_store_4d(&p.mapGlu, baseG + pc * kChunk16Bytes, (t.n0 >> 1) + pc * 32, xs, ys, bs);
+                        if (p.has_o16) {
+                            ptx::tma_store_4d(&p.mapO16, base16 + (2 * pc) * kChunk16Bytes, t.n0 + pc * 64, xs, ys, bs);
+                            ptx::tma_store_4d(&p.mapO16, base16 + (2 * pc + 1) * kChunk16Bytes, t.n0 + pc * 64 + 32, xs, ys, bs);
+                        }
+                        ptx::tma_store_commit();
+                    }
+                }
+                continue;
             }
             for (int c = eset; c < nch; c += ESETS) {
                 if (t.n0 + c * 32 >= p.N) break;
@@ -899,11 +960,28 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict_
 int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters, cudaStream_t stream) {
     GemmDesc d = d_in;
     const long rows_total = (long)d.aW * d.aH * d.aB;
-    const bool nonlinear = d.relu || d.qscale != 0.f;      // ReLU / rounding emulation: the epilogue needs the full K sum
+    const bool glu = d.out_glu != nullptr;
+    const bool nonlinear = d.relu || d.qscale != 0.f || glu;      // ReLU / rounding emulation / gating: the epilogue needs the full K sum
     bool can_split = d.splits >= 0 && d.out32 && !d.out16 && !nonlinear;
     bool via_scratch = false;
-    const int epi = (d.residual ? 1 : 0) | ((d.residual || d.out32) ? 2 : 0) | (d.out16 ? 4 : 0);
+    const int epi = (d.residual ? 1 : 0) | ((d.residual || d.out32) ? 2 : 0) | ((d.out16 || glu) ? 4 : 0);
     TileChoice tc = choose_tiles_tma(d.N, tiles_m, num_iters, can_split, epi);
+    if (glu && tc.BN % 64 != 0) {
+        // value / gate columns come in 32 + 32 pairs: the tile width must hold whole pairs
+        static const int cands[] = {256, 192, 128, 64};
+        double best_c = 1e30;
+        for (int c : cands) {
+            if (c > d.N) continue;
+            for (int ms = 1; ms <= 2; ++ms) {
+                if (ms == 2 && (tiles_m < 2 || ms * c > 512)) break;
+                const double cyc = model_cycles_tma(d.N, tiles_m, num_iters, c, 1, epi, ms);
+                if (cyc < best_c) {
+                    best_c = cyc;
+                    tc = TileChoice{c, 1, ms};
+                }
+            }
+        }
+    }
     if (d.splits >= 0 && !nonlinear && d.out16 && !d.out32 && (size_t)rows_total * d.N * sizeof(float) <= kWsBytes) {
         // fp16-only output of a K-heavy small problem: split K into an fp32 scratch tile matrix, then convert
         const int epi_s = (d.residual ? 1 : 0) | 2;
@@ -919,6 +997,7 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
         }
     }
     if (d.BN > 0) tc.BN = d.BN;
+    if (glu && tc.BN % 64 != 0) return set_error(S2I_ERR_ARG, "gemm: the gated-GELU epilogue needs a tile width that is a multiple of 64 (got %d)", tc.BN);
     if (d.splits > 0 && can_split) tc.splits = d.splits;
     if (g_force_msub > 0) tc.msub = (g_force_msub == 2 && tiles_m >= 2 && 2 * tc.BN <= 512) ? 2 : 1;
     while (tc.splits > 1 && (long)(tc.splits - 1) * ceil_div(num_iters, tc.splits) >= num_iters) --tc.splits;
@@ -933,13 +1012,15 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     p.has_res = d.residual ? 1 : 0;
     p.has_o32 = d.out32 ? 1 : 0;
     p.has_o16 = d.out16 ? 1 : 0;
+    p.has_glu = glu ? 1 : 0;
     const int tiles_n = ceil_div(d.N, BN);
     p.tmem_cols = 32;
     while (p.tmem_cols < msub * BN) p.tmem_cols *= 2;
 
     const int stage_bytes = msub * kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
     const int nch = BN / 32;
-    const size_t epi_bytes = (size_t)((p.has_res || p.has_o32) ? nch * kChunk32Bytes : 0) + (p.has_o16 ? nch * kChunk16Bytes : 0);
+    const size_t epi_bytes = (size_t)((p.has_res || p.has_o32) ? nch * kChunk32Bytes : 0) + (p.has_o16 ? nch * kChunk16Bytes : 0) +
+                             (glu ? (nch / 2) * kChunk16Bytes : 0);
     const long grid_m = ceil_div_l(tiles_m, msub);
     const long ctas = grid_m * tiles_n * tc.splits;
     const size_t tail = (size_t)(2 * 8 + 1 + kMaxChunks) * 8 + 16 + (size_t)BN * 4 + 1024 + 64;
@@ -970,14 +1051,20 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     if (d.residual) S2I_TRY(build_out_map(&p.mapRes, p, d, d.residual, d.res_ld, 2));
     if (d.out32) S2I_TRY(build_out_map(&p.mapO32, p, d, d.out32, d.ld32, 2));
     if (d.out16) S2I_TRY(build_out_map(&p.mapO16, p, d, d.out16, d.ld16, 0));
+    if (glu) {
+        GemmDesc dg = d;
+        dg.N = d.N / 2;
+        S2I_TRY(build_out_map(&p.mapGlu, p, dg, d.out_glu, d.ld_glu, 0));
+    }
     if (p.split_add) {
         const long rows = (long)d.aW * d.aH * d.aB;
         S2I_MEMOP(cudaMemset2DAsync(d.out32, (size_t)d.ld32 * 4, 0, (size_t)d.N * 4, (size_t)rows, stream));
     }
     static bool attr_set = false;
     if (!attr_set) {
-        S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     dim3 grid((unsigned)grid_m, (unsigned)tiles_n, (unsigned)tc.splits);
@@ -986,12 +1073,13 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     // read per call so tools can A/B in one process
     int esets = (BN >> 5) >= 2 ? 2 : 1;
     if (const char* e = getenv("S2I_GEMM_ESETS")) esets = atoi(e) == 1 ? 1 : esets;
-    if (esets == 2) S2I_LAUNCH((gemm_tma_kernel<2>), grid, kThreads + 128, smem_bytes, stream, p);
-    else S2I_LAUNCH((gemm_tma_kernel<1>), grid, kThreads, smem_bytes, stream, p);
+    if (glu) S2I_LAUNCH((gemm_tma_kernel<2, true>), grid, kThreads + 128, smem_bytes, stream, p);
+    else if (esets == 2) S2I_LAUNCH((gemm_tma_kernel<2, false>), grid, kThreads + 128, smem_bytes, stream, p);
+    else S2I_LAUNCH((gemm_tma_kernel<1, false>), grid, kThreads, smem_bytes, stream, p);
     const double m_rows = (double)d.aW * d.aH * d.aB;
     // algorithmic bytes: the activation operand and the weights once (fp16), the fp32 residual, the outputs
     const double alg_bytes = 2.0 * (m_rows * d.Kc + (double)d.N * d.Kc * d.taps) + m_rows * d.N * ((d.residual ? 4.0 : 0.0) +
-                             (d_in.out32 ? 4.0 : 0.0) + (d_in.out16 ? 2.0 : 0.0));
+                             (d_in.out32 ? 4.0 : 0.0) + (d_in.out16 ? 2.0 : 0.0) + (d_in.out_glu ? 1.0 : 0.0));
     S2I_LAUNCH_CHECK_TAG(d.tag, 2.0 * m_rows * d.N * d.Kc * d.taps, alg_bytes);
     if (via_scratch) {
         const long total = rows_total * (d.N / 4);
@@ -1020,7 +1108,7 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     if (d.taps != 1 && d.taps != 9) return set_error(S2I_ERR_ARG, "gemm: taps must be 1 or 9");
     if (d.a_mn && d.taps != 1) return set_error(S2I_ERR_ARG, "gemm: MN-major A has no taps");
     if (d.taps == 9 && (d.Kc % kBlockK) != 0) return set_error(S2I_ERR_ARG, "gemm: conv3x3 needs Cin %% 64 == 0");
-    if (!d.out32 && !d.out16) return set_error(S2I_ERR_ARG, "gemm: no output");
+    if (!d.out32 && !d.out16 && !d.out_glu) return set_error(S2I_ERR_ARG, "gemm: no output");
 
     GemmParams p;
     memset(&p, 0, sizeof(p));
@@ -1095,6 +1183,12 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     if (d.out32) tma = tma && (d.ld32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.out32) & 15) == 0);
     if (d.out16) tma = tma && (d.ld16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(d.out16) & 15) == 0);
     if (d.residual) tma = tma && (d.res_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.residual) & 15) == 0);
+    if (d.out_glu) {
+        if (!tma || d.N % 64 != 0 || d.residual || d.out32 || d.relu || d.qscale != 0.f || (d.ld_glu % 8) != 0 ||
+            (reinterpret_cast<uintptr_t>(d.out_glu) & 15) != 0)
+            return set_error(S2I_ERR_ARG, "gemm: the gated-GELU epilogue needs K-major operands, Z = 1, N %% 64 == 0, aligned fp16 "
+                                          "outputs and no residual / fp32 output / ReLU");
+    }
     if (tma) return launch_tma(p, d, tiles_m, num_iters, stream);
 
     TileChoice tc = choose_tiles(d.N, tiles_m, Z, num_iters, fast && Z == 1 && d.splits >= 0);

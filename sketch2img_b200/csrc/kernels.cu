@@ -999,8 +999,10 @@ __global__ void __launch_bounds__(256) geglu_fwd_kernel(const __half* __restrict
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const long r = idx / vec;
         const int c = (int)(idx - r * vec) << 2;
-        const float4 a = ldh4(ff + r * ldf + c);
-        const float4 g = ldh4(ff + r * ldf + F + c);
+        // interleaved projection: feature c's value sits at column 64 (c / 32) + c % 32, its gate 32 columns further
+        const int ca = ((c >> 5) << 6) + (c & 31);
+        const float4 a = ldh4(ff + r * ldf + ca);
+        const float4 g = ldh4(ff + r * ldf + ca + 32);
         *reinterpret_cast<uint2*>(out16 + r * ld16 + c) =
             pack_half4(a.x * gelu_exact(g.x), a.y * gelu_exact(g.y), a.z * gelu_exact(g.z), a.w * gelu_exact(g.w));
     }
@@ -1016,12 +1018,13 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const float* __restrict_
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const long r = idx / vec;
         const int c = (int)(idx - r * vec) << 2;
+        const int ca = ((c >> 5) << 6) + (c & 31);      // interleaved layout (see geglu_fwd_kernel)
         const float4 d = ldg4(dg + r * ldg + c);
-        const float4 a = ldh4(ff + r * ldf + c);
-        const float4 g = ldh4(ff + r * ldf + F + c);
-        *reinterpret_cast<uint2*>(dff16 + r * ld16 + c) =
+        const float4 a = ldh4(ff + r * ldf + ca);
+        const float4 g = ldh4(ff + r * ldf + ca + 32);
+        *reinterpret_cast<uint2*>(dff16 + r * ld16 + ca) =
             pack_half4(d.x * gelu_exact(g.x), d.y * gelu_exact(g.y), d.z * gelu_exact(g.z), d.w * gelu_exact(g.w));
-        *reinterpret_cast<uint2*>(dff16 + r * ld16 + F + c) =
+        *reinterpret_cast<uint2*>(dff16 + r * ld16 + ca + 32) =
             pack_half4(d.x * a.x * gelu_grad(g.x), d.y * a.y * gelu_grad(g.y), d.z * a.z * gelu_grad(g.z),
                        d.w * a.w * gelu_grad(g.w));
     }
@@ -1529,7 +1532,7 @@ int softmax_bwd(const void* p16, long ldp, const float* dp, long lddp, long rows
 
 int geglu_fwd(const void* ff16, long ldf, long rows, int F, void* out16, long ld16, cudaStream_t st) {
     const __half* ff = static_cast<const __half*>(ff16);
-    S2I_REQ((F & 3) == 0 && (ldf & 3) == 0 && (ld16 & 3) == 0, "geglu_fwd: alignment");
+    S2I_REQ((F & 31) == 0 && (ldf & 3) == 0 && (ld16 & 3) == 0, "geglu_fwd: alignment (interleaved 32-feature blocks)");
     S2I_LAUNCH((geglu_fwd_kernel), grid_for(rows * (F >> 2), 256), 256, 0, st, ff, ldf, rows, F, (__half*)out16, ld16);
     S2I_LAUNCH_CHECK();
     return 0;
@@ -1538,7 +1541,7 @@ int geglu_fwd(const void* ff16, long ldf, long rows, int F, void* out16, long ld
 int geglu_bwd(const float* dg, long ldg, const void* ff16, long ldf, long rows, int F, void* dff16, long ld16,
               cudaStream_t st) {
     const __half* ff = static_cast<const __half*>(ff16);
-    S2I_REQ((F & 3) == 0 && (ldf & 3) == 0 && (ldg & 3) == 0 && (ld16 & 3) == 0, "geglu_bwd: alignment");
+    S2I_REQ((F & 31) == 0 && (ldf & 3) == 0 && (ldg & 3) == 0 && (ld16 & 3) == 0, "geglu_bwd: alignment (interleaved 32-feature blocks)");
     S2I_LAUNCH((geglu_bwd_kernel), grid_for(rows * (F >> 2), 256), 256, 0, st, dg, ldg, ff, ldf, rows, F, (__half*)dff16, ld16);
     S2I_LAUNCH_CHECK();
     return 0;

@@ -43,7 +43,8 @@ int softmax_fwd(const float* s, long lds, long rows, int n, void* p16, long ldp,
 int softmax_bwd(const void* p16, long ldp, const float* dp, long lddp, long rows, int n, float scale, void* ds16,
                 long ldds, cudaStream_t st);
 
-// ---- GEGLU: out = a * gelu(gate), [a | gate] = ff[:, :F], ff[:, F:]; ff is the fp16 output of the C -> 8C Linear ----
+// ---- GEGLU: out = a * gelu(gate); ff is the fp16 output of the C -> 8C Linear with its columns interleaved in blocks of 32
+// (value features 32 b .. at columns [64 b, 64 b + 32), their gates at [64 b + 32, 64 b + 64); UNet Loader::linear_glu) ----
 int geglu_fwd(const void* ff16, long ldf, long rows, int F, void* out16, long ld16, cudaStream_t st);
 int geglu_bwd(const float* dg, long ldg, const void* ff16, long ldf, long rows, int F, void* dff16, long ld16,
               cudaStream_t st);

@@ -188,6 +188,39 @@ struct Loader {
         }
         return true;
     }
+    // GEGLU projection [8C][C]: rows interleaved in blocks of 32 -- packed rows [64 b, 64 b + 32) = value features 32 b ..,
+    // [64 b + 32, 64 b + 64) = their gates (rows 4C + 32 b .. of the checkpoint) -- so a 64-column slice of the GEMM's
+    // output tile holds matching value / gate pairs (gated-GELU epilogue of gemm_tma_kernel); wd permuted alike along K.
+    bool linear_glu(const std::string& pre, int C, Lin& l) {
+        const int N = 8 * C, K = C, F = 4 * C;
+        if (F % 32) {
+            err = "GEGLU width must be a multiple of 32";
+            return false;
+        }
+        const HostParam* hw = find(pre + ".weight", (size_t)N * K);
+        const HostParam* hb = hw ? find(pre + ".bias", (size_t)N) : nullptr;
+        if (!hw || !hb) return false;
+        std::vector<float> w((size_t)N * K), b(N);
+        for (int r = 0; r < N; ++r) {
+            const int blk = r / 64, j = r % 64;
+            const int src = j < 32 ? blk * 32 + j : F + blk * 32 + (j - 32);
+            memcpy(&w[(size_t)r * K], hw->data + (size_t)src * K, (size_t)K * sizeof(float));
+            b[r] = hb->data[src];
+        }
+        l.N = N;
+        l.K = K;
+        l.w = dmalloc<__half>((size_t)N * K);
+        l.wd = dmalloc<__half>((size_t)N * K);
+        l.b = dmalloc<float>(N);
+        if (!l.w || !l.wd || !l.b) return false;
+        HostParam tmp{w.data(), {N, K}};
+        const float* s = stage(&tmp, (size_t)N * K);
+        if (!s) return false;
+        pack2d_kernel<<<1024, 256>>>(s, K, 0, N, K, 0, 0, 0, 0, l.w, K);
+        pack2d_kernel<<<1024, 256>>>(s, K, 1, K, N, 0, 0, 0, 0, l.wd, N);
+        cudaMemcpy(l.b, b.data(), (size_t)N * sizeof(float), cudaMemcpyHostToDevice);
+        return cudaDeviceSynchronize() == cudaSuccess;
+    }
     bool conv3(const std::string& pre, int Co, int Ci, Conv3& c, bool want_dgrad = true, bool want_fwd = true) {
         c.Cin = Ci;
         c.Cout = Co;
@@ -298,7 +331,7 @@ int UNet::load(const std::map<std::string, HostParam>& params) {
         if (!L.linear_into(tb + ".attn2.to_v.weight", C, D, T.d, T.dp, true, false, T.kv2.w, D, T.HP, nullptr, 0, 0, false))
             return false;
         if (!out_proj(tb + ".attn2.to_out.0", T.o2)) return false;
-        if (!L.linear(tb + ".ff.net.0.proj", 8 * C, C, true, T.ff1)) return false;
+        if (!L.linear_glu(tb + ".ff.net.0.proj", C, T.ff1)) return false;
         if (!L.linear(tb + ".ff.net.2", C, 4 * C, true, T.ff2)) return false;
         tfm_.push_back(T);
         return true;
@@ -935,10 +968,31 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     H16 l16c = new16(B, H, W, C);
     sv.l3 = dalloc<float>(rows * 2);
     RUN(ln_fwd(sv.t2.p, sv.t2.ld, rows, C, T.ln3.g, T.ln3.b, T.ln3.eps, l16c.p, l16c.ld, sv.l3, st_));
-    sv.ff = new16(B, H, W, 8 * C);
-    S2I_TRY(gemm(l16c, false, 1, T.ff1.w, C, 8 * C, C, T.ff1.b, nullptr, nullptr, nullptr, &sv.ff));
+    // GEGLU: the projection's epilogue applies value * gelu(gate) (interleaved weight rows, see Loader::linear_glu); the
+    // projection itself is only written when the backward needs it
     H16 g16 = new16(B, H, W, 4 * C);
-    RUN(geglu_fwd(sv.ff.p, sv.ff.ld, rows, 4 * C, g16.p, g16.ld, st_));
+    if (fuse_glu_) {
+        if (save_) sv.ff = new16(B, H, W, 8 * C);
+        if (!dry_) {
+            GemmDesc d;
+            d.tag = "gemm_linear";
+            d.A = l16c.p; d.aC = C; d.aW = (int)rows; d.aH = 1; d.aB = 1; d.a_sw = l16c.ld;
+            d.B = T.ff1.w; d.bI = C; d.bR = 8 * C; d.b_sr = C;
+            d.N = 8 * C; d.Kc = C;
+            d.bias = T.ff1.b;
+            if (save_) {
+                d.out16 = sv.ff.p;
+                d.ld16 = sv.ff.ld;
+            }
+            d.out_glu = g16.p;
+            d.ld_glu = g16.ld;
+            S2I_TRY(gemm_launch(d, st_));
+        }
+    } else {
+        sv.ff = new16(B, H, W, 8 * C);
+        S2I_TRY(gemm(l16c, false, 1, T.ff1.w, C, 8 * C, C, T.ff1.b, nullptr, nullptr, nullptr, &sv.ff));
+        RUN(geglu_fwd(sv.ff.p, sv.ff.ld, rows, 4 * C, g16.p, g16.ld, st_));
+    }
     H16 t3 = new16(B, H, W, C);
     S2I_TRY(gemm(g16, false, 1, T.ff2.w, 4 * C, C, 4 * C, T.ff2.b, nullptr, &sv.t2, nullptr, &t3));
     out = out32(B, H, W, C);

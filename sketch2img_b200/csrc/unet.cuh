@@ -173,6 +173,10 @@ class UNet {
     std::map<std::string, F32> debug;
     bool keep_debug = false;
     bool use_flash_ = true;   // fused attention forward wherever P is not needed afterwards (S2I_NO_FLASH=1 disables)
+    // GEGLU inside the projection's epilogue (gemm_tma_kernel<2, true>) instead of a separate geglu_fwd launch: parity-green
+    // but measured SLOWER on B200 (448 vs 442 ms/image) -- 10 M erf evaluations per level-0 projection land on the 8 epilogue
+    // warps of each CTA instead of a full-occupancy elementwise kernel -- so it is off unless S2I_GLU_FUSION=1
+    bool fuse_glu_ = false;
 
     size_t arena_bytes() const { return arena_.cap; }
 

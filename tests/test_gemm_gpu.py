@@ -352,3 +352,45 @@ def test_relu_and_fp16_rounding_epilogues(L, cuda, M, N, K):
     # identical up to the rare value whose fp32 accumulation-order noise crosses an fp16 rounding boundary
     assert rel(out32, want) < 2e-3
     assert torch.equal(out32, (out32 / q).half().float() * q)              # every output is an fp16 multiple of q
+
+
+@pytest.mark.parametrize("M,C,keep,msub", [(8192, 320, True, 0), (8192, 320, False, 2), (2048, 640, True, 1), (512, 1280, False, 0),
+                                           (300, 64, True, 0)])
+def test_gated_gelu_epilogue(L, cuda, M, C, keep, msub):
+    """The GEGLU feed-forward projection of every BasicTransformerBlock (diffusers FeedForward / GEGLU inside
+    modules/pipeline.py:96):  out = value * gelu(gate),  [value | gate] = x W^T + b,  with the weight rows interleaved in blocks
+    of 32 (value features 32 b .. at packed rows [64 b, 64 b + 32), their gates at [64 b + 32, 64 b + 64)) so the GEMM's
+    epilogue applies the gate; `keep` also writes the interleaved projection (the backward's input).  Against fp64 torch."""
+    import torch.nn.functional as F
+    if not L.tma_epilogue:
+        pytest.skip("the gated-GELU epilogue only exists in gemm_tma_kernel")
+    g = torch.Generator(device="cpu").manual_seed(M + C)
+    N, Fw = 8 * C, 4 * C
+    x = torch.randn(M, C, generator=g).to(cuda).half()
+    w = (torch.randn(N, C, generator=g) * (C ** -0.5))
+    b = torch.randn(N, generator=g) * 0.1
+    ref_ff = x.double().cpu() @ w.half().double().t() + b.double()
+    want = ref_ff[:, :Fw] * F.gelu(ref_ff[:, Fw:])
+    perm = torch.tensor([(r // 64) * 32 + r % 64 if r % 64 < 32 else Fw + (r // 64) * 32 + (r % 64 - 32) for r in range(N)])
+    wp, bp = w[perm].to(cuda).half().contiguous(), b[perm].to(cuda).contiguous()
+    out = torch.full((M, Fw), float("nan"), device=cuda, dtype=torch.float16)
+    ff = torch.full((M, N), float("nan"), device=cuda, dtype=torch.float16)
+    L.lib().s2i_gemm_force_msub(msub)
+    try:
+        d = L.GemmDesc(A=x.data_ptr(), aC=C, aW=M, a_sw=C, B=wp.data_ptr(), bI=C, bR=N, b_sr=C, N=N, Kc=C, bias=bp.data_ptr(),
+                       out_glu=out.data_ptr(), ld_glu=Fw, out16=ff.data_ptr() if keep else None, ld16=N if keep else 0)
+        L.gemm(d)
+        torch.cuda.synchronize()
+    finally:
+        L.lib().s2i_gemm_force_msub(0)
+    assert rel(out.float().cpu(), want) < 2e-3
+    if keep:
+        assert rel(ff.float().cpu(), ref_ff[:, perm]) < 1e-3
+    # a tile width that cannot hold whole value / gate pairs is an error, as are the epilogue forms it does not combine with
+    with pytest.raises(L.S2IError):
+        L.gemm(L.GemmDesc(A=x.data_ptr(), aC=C, aW=M, a_sw=C, B=wp.data_ptr(), bI=C, bR=N, b_sr=C, N=N, Kc=C, BN=96,
+                          out_glu=out.data_ptr(), ld_glu=Fw))
+    o32 = torch.empty(M, N, device=cuda)
+    with pytest.raises(L.S2IError):
+        L.gemm(L.GemmDesc(A=x.data_ptr(), aC=C, aW=M, a_sw=C, B=wp.data_ptr(), bI=C, bR=N, b_sr=C, N=N, Kc=C,
+                          out_glu=out.data_ptr(), ld_glu=Fw, out32=o32.data_ptr(), ld32=N))
