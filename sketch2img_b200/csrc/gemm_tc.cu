@@ -849,8 +849,12 @@ TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, in
         for (int ms = 1; ms <= 2; ++ms) {
             if (ms == 2 && (tiles_m < 2 || ms * c > 512 || !g_allow_msub)) break;
             const long base = ceil_div_l(tiles_m, ms) * ceil_div(N, c);
-            for (int sp = 1; sp <= 32; sp *= 2) {
+            // powers of two, and every count above 8: 180 K iterations split 30 ways (6 each) where 32 would leave empty
+            // splits (measured, tools/gemm_bench.py sweep: conv 1280 @ 8x8 20.3 -> 14.3 us; small odd counts measured worse
+            // than the model predicts)
+            for (int sp = 1; sp <= 32; ++sp) {
                 if (sp > 1 && (!allow_split || base * sp > 2 * kNumSMs + 64 || iters / sp < 2)) break;
+                if (sp < 8 && (sp & (sp - 1)) != 0) continue;
                 if ((long)(sp - 1) * ceil_div(iters, sp) >= iters) continue;
                 const double cyc = model_cycles_tma(N, tiles_m, iters, c, sp, epi, ms);
                 if (cyc < best_c) {

@@ -29,6 +29,14 @@ SHAPES = [
     ("conv 1280@8", 8, 128, 1280, 1280, 9, 1, 1, 0),
     ("conv 2560->1280@8", 8, 128, 1280, 2560, 9, 1, 1, 0),
     ("lin 1280->1280 @8 res", None, 128, 1280, 1280, 1, 1, 1, 0),
+    # the cond-only input-gradient walk: one sample (half the rows)
+    ("conv 320@64 B1", 64, 4096, 320, 320, 9, 1, 1, 0),
+    ("lin 320->320 @64 B1", None, 4096, 320, 320, 1, 1, 1, 0),
+    ("dff 2560->320 @64 B1", None, 4096, 320, 2560, 1, 0, 1, 0),
+    ("conv 640@32 B1", 32, 1024, 640, 640, 9, 1, 1, 0),
+    ("lin 640->640 @32 B1", None, 1024, 640, 640, 1, 1, 1, 0),
+    ("conv 1280@16 B1", 16, 256, 1280, 1280, 9, 1, 1, 0),
+    ("conv 1280@8 B1", 8, 64, 1280, 1280, 9, 1, 1, 0),
 ]
 
 
