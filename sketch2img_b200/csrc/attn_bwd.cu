@@ -16,6 +16,7 @@
 
 #include <cudaTypedefs.h>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -33,7 +34,7 @@ constexpr int kRows = 128;               // resident ("row") tokens per CTA
 constexpr int kCols = 64;                // streamed ("column") tokens per tile
 constexpr int kChunk16 = 128 * 64 * 2;   // 16 KB: 128 rows x 64 fp16 (one swizzle-128B K-major chunk)
 constexpr int kChunk8 = 64 * 64 * 2;     //  8 KB:  64 rows x 64 fp16
-constexpr int kStages = 2;
+constexpr int kMaxStages = 4;            // streamed-operand ring depth is chosen at launch (2 .. 4)
 
 struct __align__(64) BwdParams {
     CUtensorMap mapR1, mapR2, mapC1, mapC2;   // resident (box 64 x 128) and streamed (box 64 x 64) operands
@@ -41,6 +42,7 @@ struct __align__(64) BwdParams {
     int Nrow, Ncol, heads, dp, nkc;
     int r1_c0, r2_c0, c1_c0, c2_c0;           // column of head 0 in each operand tensor
     int sbufs;                                // staging buffers per staged matrix (1 or 2)
+    int stages;                               // streamed-operand ring depth
     int nT, tmem_cols;                        // tile-product buffers in TMEM (1 or 2) and the allocation that holds them
     uint32_t idesc_t, idesc_acc;
     float scale, scale_log2;
@@ -68,17 +70,17 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
     uint8_t* sR2 = sR1 + r_bytes;
     uint8_t* sSt = sR2 + r_bytes;                  // [sbufs][nstaged] x 16 KB
     uint8_t* sC = sSt + p.sbufs * nstaged * kChunk16;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sC + kStages * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sC + p.stages * stage_bytes);
     uint64_t* r_full = bars;            // resident operands landed
     uint64_t* acc_full = bars + 1;      // accumulators complete
     uint64_t* t_full = bars + 2;        // [2] both tile products complete
     uint64_t* t_empty = bars + 4;       // [2] softmax warps drained the TMEM tile buffers
     uint64_t* st_full = bars + 6;       // [2] staging written
     uint64_t* st_empty = bars + 8;      // [2] accumulating MMAs done with the staging buffer
-    uint64_t* c_full = bars + 10;       // [kStages]
-    uint64_t* c_empty = bars + 12;      // [kStages]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-    float* sStat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 16) + 15) & ~uintptr_t(15));   // mode 1: [2][2][64] (lse*log2e, delta)
+    uint64_t* c_full = bars + 10;       // [kMaxStages]
+    uint64_t* c_empty = bars + 14;      // [kMaxStages]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    float* sStat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 20) + 15) & ~uintptr_t(15));   // mode 1: [2][2][64] (lse*log2e, delta)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
                 ptx::mbar_init(&st_full[i], 4);
                 ptx::mbar_init(&st_empty[i], 1);
             }
-            for (int s = 0; s < kStages; ++s) {
+            for (int s = 0; s < p.stages; ++s) {
                 ptx::mbar_init(&c_full[s], 1);
                 ptx::mbar_init(&c_empty[s], 1);
             }
@@ -131,8 +133,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
                 ptx::tma_load_3d(sR2 + c * kChunk16, &p.mapR2, r_full, p.r2_c0 + h * p.dp + c * 64, row0, b);
             }
             for (int j = 0; j < T; ++j) {
-                const int stage = j % kStages;
-                ptx::mbar_wait(&c_empty[stage], ((j / kStages) & 1) ^ 1);
+                const int stage = j % p.stages;
+                ptx::mbar_wait(&c_empty[stage], ((j / p.stages) & 1) ^ 1);
                 ptx::mbar_expect_tx(&c_full[stage], (uint32_t)stage_bytes);
                 uint8_t* s1 = sC + stage * stage_bytes;
                 uint8_t* s2 = s1 + c_bytes;
@@ -149,8 +151,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
             const uint32_t aR1 = ptx::smem_u32(sR1), aR2 = ptx::smem_u32(sR2);
             // T1[g&1] = R1 C1_g^T, T2[g&1] = R2 C2_g^T
             auto issue_T = [&](int g) {
-                const int stage = g % kStages;
-                ptx::mbar_wait(&c_full[stage], (g / kStages) & 1);
+                const int stage = g % p.stages;
+                ptx::mbar_wait(&c_full[stage], (g / p.stages) & 1);
                 const int tb = g % p.nT;
                 ptx::mbar_wait(&t_empty[tb], ((g / p.nT) & 1) ^ 1);
                 ptx::tc_fence_after();
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
                 const int sb = j % p.sbufs;
                 ptx::mbar_wait(&st_full[sb], (j / p.sbufs) & 1);
                 ptx::tc_fence_after();
-                const int stage = j % kStages;
+                const int stage = j % p.stages;
                 const uint32_t aC1 = ptx::smem_u32(sC + stage * stage_bytes);
                 const uint32_t aC2 = aC1 + (uint32_t)c_bytes;
                 const uint32_t aSt = ptx::smem_u32(sSt + sb * nstaged * kChunk16);
@@ -425,12 +427,25 @@ int attn_bwd_launch(const AttnBwdDesc& d, cudaStream_t stream) {
         p.nT = (128 + nacc * d.dp <= 256 || 256 + nacc * d.dp > 512) ? 1 : 2;
         p.tmem_cols = (p.nT * 128 + nacc * d.dp <= 256) ? 256 : 512;
         if (p.nT * 128 + nacc * d.dp > 512) return set_error(S2I_ERR_ARG, "attn_bwd: head dim %d does not fit TMEM", d.dp);
-        const int fixed = 2 * nkc * kChunk16 + kStages * 2 * nkc * kChunk8 + 2048 + 1024;   // operands + barriers/stats + slack
+        const int stage_b = 2 * nkc * kChunk8;
+        const int fixed = 2 * nkc * kChunk16 + 2 * stage_b + 2048 + 1024;   // operands (2-stage ring) + barriers/stats + slack
         p.sbufs = (fixed + 2 * nstaged * kChunk16 <= 227 * 1024) ? 2 : 1;
         // prefer two co-resident CTAs when a single staging buffer makes the footprint fit half an SM
         if (fixed + 2 * nstaged * kChunk16 > 113 * 1024 && fixed + nstaged * kChunk16 <= 113 * 1024) p.sbufs = 1;
-        const size_t smem_bytes = (size_t)fixed + (size_t)p.sbufs * nstaged * kChunk16;
+        size_t smem_bytes = (size_t)fixed + (size_t)p.sbufs * nstaged * kChunk16;
         if (smem_bytes > 227u * 1024u) return set_error(S2I_ERR_ARG, "attn_bwd: head dim %d does not fit shared memory", d.dp);
+        // A streamed tile's stage is only reloaded after the accumulating products that read it, one softmax pass later:
+        // deepen the ring as far as the footprint's occupancy class (two CTAs per SM, or one) allows, like the forward's
+        // "score tiles at most stages - 2 ahead" rule.  S2I_ATTNB_STAGES caps it (tools A/B).
+        const size_t budget = smem_bytes <= 113u * 1024u ? 113u * 1024u : 227u * 1024u;
+        int cap = kMaxStages;
+        if (const char* e = getenv("S2I_ATTNB_STAGES")) cap = atoi(e) < 2 ? 2 : (atoi(e) > kMaxStages ? kMaxStages : atoi(e));
+        p.stages = 2;
+        const int Tcols = (p.Ncol + kCols - 1) / kCols;
+        while (p.stages < cap && p.stages < Tcols && smem_bytes + (size_t)stage_b <= budget) {
+            ++p.stages;
+            smem_bytes += (size_t)stage_b;
+        }
         dim3 grid((unsigned)((p.Nrow + kRows - 1) / kRows), (unsigned)Z, 1);
         S2I_LAUNCH((attn_bwd_kernel), grid, kThreads, smem_bytes, stream, p);
         // algorithmic work of the reference's backward: dP, dQ (mode 0) and dV, dK (mode 1) products at the true head dim

@@ -185,7 +185,7 @@ def test_lgp_forward_loss_backward_match_oracle(tiny):
         # cond-only form (what the sampler calls): the cond sample's gradients, same values
         eng.forward_taps(taps_nhwc, 2, L, lat.cuda().contiguous(), sigma, True)
         l2, gc, scale2 = eng.loss_backward(tgt.cuda().contiguous(), taps_nhwc, cond_only=True)
-        assert scale2 == scale and abs(l2.item() - l.item()) <= 1e-6 * abs(l.item())
+        assert scale2 == scale and abs(l2.item() - l.item()) <= 1e-5 * abs(l.item())      # the loss is summed with float atomics
         for k in range(9):
             assert tuple(gc[k].shape) == (1,) + tuple(grads[k].shape[1:])
             # same arithmetic; the 4096-row layer-1 dgrad may pick another tile / split-K than the 8192-row one

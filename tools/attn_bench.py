@@ -87,7 +87,7 @@ def main():
                                                dkv.data_ptr() if with_kv else None, 2 * HP, 0, HP, L.stream_ptr()))
 
         tf = graph_time(fwd)
-        bwd_ok = dp <= 128
+        bwd_ok = dp <= 192
         tq = graph_time(lambda: bwd(False)) if bwd_ok else float("nan")
         tkv = graph_time(lambda: bwd(True)) if Nk >= 128 and bwd_ok else float("nan")
         gf = 4.0 * B * heads * Nq * Nk * d / 1e9
