@@ -39,12 +39,17 @@ __global__ void __launch_bounds__(256) lgp_features_kernel(TapTable tt, int B, i
     pdl_wait();
     pdl_launch();
     if (dsigma) sigma = __ldg(dsigma);      // graph-replayed steps read the step's scalars from device memory
-    const int chunks = (int)(ldX >> 3);
-    const long total = (long)B * L * L * chunks;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const long row = idx / chunks;
-        const int col = (int)(idx - row * chunks) << 3;
-        const int w = (int)(row % L), h = (int)((row / L) % L), b = (int)(row / ((long)L * L));
+    // 32-bit index arithmetic (the host checks that rows * chunks fits): four 64-bit divisions per 16 output bytes were
+    // most of this kernel's instructions
+    const unsigned chunks = (unsigned)(ldX >> 3);
+    const unsigned total = (unsigned)B * L * L * chunks;
+    const unsigned uL = (unsigned)L;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned urow = idx / chunks;
+        const int col = (int)(idx - urow * chunks) << 3;
+        const unsigned t1 = urow / uL;
+        const int w = (int)(urow - t1 * uL), b = (int)(t1 / uL), h = (int)(t1 - (unsigned)b * uL);
+        const long row = urow;
         float v[8];
         if (col < tt.off[9]) {
             int k = 0;
@@ -735,6 +740,7 @@ int LGP::forward(const LgpTap taps[9], int B, int L, const float* noise, float s
     const long rows = (long)B * L * L;
     groups_ = B / 2;
     S2I_TRY(ensure(lgp_ws_bytes(rows, ldX_, B / 2)));
+    if (rows * (ldX_ / 8) > 0x7fffffffL) return set_error(S2I_ERR_ARG, "lgp: %ld feature rows exceed the kernel's 32-bit indexing", rows);
     X_ = reinterpret_cast<__half*>(buf_);   // first workspace slot (see mlp())
     S2I_LAUNCH((lgp_features_kernel), grid1d(rows * (ldX_ / 8)), 256, 0, st, tt, B, L, noise, sigma, dsigma, P_, D_, X_, ldX_,
                                                       taps_sample_major ? B / 2 : 0);
