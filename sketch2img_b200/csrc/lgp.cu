@@ -41,20 +41,22 @@ __global__ void __launch_bounds__(256) lgp_features_kernel(TapTable tt, int B, i
     if (dsigma) sigma = __ldg(dsigma);      // graph-replayed steps read the step's scalars from device memory
     // 32-bit index arithmetic (the host checks that rows * chunks fits): four 64-bit divisions per 16 output bytes were
     // most of this kernel's instructions
-    const unsigned chunks = (unsigned)(ldX >> 3);
+    // blockIdx.y = one tap (0..8) or the noise-level / positional-encoding tail (9): the tap's geometry is uniform per block
+    const int k = blockIdx.y;
+    const int col0 = tt.off[k < 9 ? k : 9];
+    const unsigned chunks = (unsigned)((k < 9 ? tt.C[k] : (int)ldX - col0) >> 3);
     const unsigned total = (unsigned)B * L * L * chunks;
     const unsigned uL = (unsigned)L;
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const unsigned urow = idx / chunks;
-        const int col = (int)(idx - urow * chunks) << 3;
+        const int col = col0 + ((int)(idx - urow * chunks) << 3);
         const unsigned t1 = urow / uL;
         const int w = (int)(urow - t1 * uL), b = (int)(t1 / uL), h = (int)(t1 - (unsigned)b * uL);
         const long row = urow;
         float v[8];
-        if (col < tt.off[9]) {
-            int k = 0;
-            while (col >= tt.off[k + 1]) ++k;
-            const int S = tt.S[k], C = tt.C[k], c = col - tt.off[k];
+        if (k < 9) {
+            const int S = tt.S[k], C = tt.C[k], c = col - col0;
+            (void)C;
             const int bt = smS > 0 ? ((b & 1) ? smS + (b >> 1) : (b >> 1)) : b;     // batch entry of the tap tensors
             const long ld = tt.ld[k];
             const float* base = tt.p[k] + (long)bt * S * S * ld + c;
@@ -742,7 +744,9 @@ int LGP::forward(const LgpTap taps[9], int B, int L, const float* noise, float s
     S2I_TRY(ensure(lgp_ws_bytes(rows, ldX_, B / 2)));
     if (rows * (ldX_ / 8) > 0x7fffffffL) return set_error(S2I_ERR_ARG, "lgp: %ld feature rows exceed the kernel's 32-bit indexing", rows);
     X_ = reinterpret_cast<__half*>(buf_);   // first workspace slot (see mlp())
-    S2I_LAUNCH((lgp_features_kernel), grid1d(rows * (ldX_ / 8)), 256, 0, st, tt, B, L, noise, sigma, dsigma, P_, D_, X_, ldX_,
+    int cmax = (int)ldX_ - off;
+    for (int k = 0; k < 9; ++k) cmax = taps[k].C > cmax ? taps[k].C : cmax;
+    S2I_LAUNCH((lgp_features_kernel), dim3(grid1d(rows * (cmax / 8), 256, 148 * 4), 10), 256, 0, st, tt, B, L, noise, sigma, dsigma, P_, D_, X_, ldX_,
                                                       taps_sample_major ? B / 2 : 0);
     S2I_LAUNCH_CHECK();
     return mlp(st);
