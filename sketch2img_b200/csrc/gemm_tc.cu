@@ -943,6 +943,19 @@ int build_out_map(CUtensorMap* m, const GemmParams& p, const GemmDesc& d, const 
     return encode_map(m, dtype, 4, ptr, dims, str, box, dtype == 2 ? 128 : 64);
 }
 
+// Zero-fill of a split-K output [rows][n4 * 4] (row pitch ld) as a KERNEL: unlike a memset node it keeps the programmatic
+// dependent launch chain (the GEMM's prologue overlaps it) -- ~150 split-K GEMMs per denoising step each had one.
+__global__ void __launch_bounds__(256) zero_rows_kernel(float* __restrict__ dst, long ld, long rows, int n4) {
+    pdl_wait();
+    pdl_launch();
+    const long total = rows * n4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / n4;
+        const int c = (int)(i - r * n4) * 4;
+        *reinterpret_cast<float4*>(dst + r * ld + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 // fp32 [rows][N] (row pitch lds) -> fp16 [rows][N] (row pitch ldd); N % 4 == 0
 __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ src, long lds, __half* __restrict__ dst,
                                                         long ldd, long rows, int n4) {
@@ -1062,7 +1075,10 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     }
     if (p.split_add) {
         const long rows = (long)d.aW * d.aH * d.aB;
-        S2I_MEMOP(cudaMemset2DAsync(d.out32, (size_t)d.ld32 * 4, 0, (size_t)d.N * 4, (size_t)rows, stream));
+        const long n4 = d.N / 4, total = rows * n4;
+        S2I_LAUNCH((zero_rows_kernel), (unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, stream,
+                   d.out32, (long)d.ld32, rows, (int)n4);
+        S2I_LAUNCH_CHECK_TAG("gemm_split_zero", 0.0, 0.0);
     }
     static bool attr_set = false;
     if (!attr_set) {
