@@ -956,6 +956,22 @@ __global__ void __launch_bounds__(256) zero_rows_kernel(float* __restrict__ dst,
     }
 }
 
+// Every range of a zero plan in one launch: blockIdx.y = range.
+__global__ void __launch_bounds__(256) zero_ranges_kernel(const ZeroRange* __restrict__ ranges) {
+    pdl_wait();
+    pdl_launch();
+    const ZeroRange r = ranges[blockIdx.y];
+    const long total = r.rows * r.n4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long row = i / r.n4;
+        const int c = (int)(i - row * r.n4) * 4;
+        *reinterpret_cast<float4*>(r.p + row * r.ld + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+ZeroMode g_zero_mode = ZeroMode::kOff;
+std::vector<ZeroRange>* g_zero_plan = nullptr;
+
 // fp32 [rows][N] (row pitch lds) -> fp16 [rows][N] (row pitch ldd); N % 4 == 0
 __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ src, long lds, __half* __restrict__ dst,
                                                         long ldd, long rows, int n4) {
@@ -1076,9 +1092,22 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     if (p.split_add) {
         const long rows = (long)d.aW * d.aH * d.aB;
         const long n4 = d.N / 4, total = rows * n4;
-        S2I_LAUNCH((zero_rows_kernel), (unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, stream,
-                   d.out32, (long)d.ld32, rows, (int)n4);
-        S2I_LAUNCH_CHECK_TAG("gemm_split_zero", 0.0, 0.0);
+        bool planned = false;
+        if (g_zero_mode == ZeroMode::kApply && g_zero_plan && !via_scratch) {
+            for (const ZeroRange& z : *g_zero_plan)
+                if (z.p == d.out32 && z.ld == (long)d.ld32 && z.rows == rows && z.n4 == (int)n4) {
+                    planned = true;      // zeroed by the plan's single launch at the top of the captured step
+                    break;
+                }
+        }
+        if (!planned) {
+            S2I_LAUNCH((zero_rows_kernel), (unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, stream,
+                       d.out32, (long)d.ld32, rows, (int)n4);
+            S2I_LAUNCH_CHECK_TAG("gemm_split_zero", 0.0, 0.0);
+            // the shared scratch is reused by several GEMMs of a step: never planned
+            if (g_zero_mode == ZeroMode::kRecord && g_zero_plan && !via_scratch)
+                g_zero_plan->push_back(ZeroRange{d.out32, (long)d.ld32, rows, (int)n4});
+        }
     }
     static bool attr_set = false;
     if (!attr_set) {
@@ -1119,6 +1148,18 @@ int encode_tmap_f16(CUtensorMap* m, int rank, const void* ptr, const uint64_t* d
 
 long g_launches = 0;
 long gemm_launch_count() { return g_launches; }
+
+void gemm_zero_plan(ZeroMode mode, std::vector<ZeroRange>* plan) {
+    g_zero_mode = mode;
+    g_zero_plan = plan;
+}
+
+int gemm_zero_ranges(const ZeroRange* ranges, int n, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    S2I_LAUNCH((zero_ranges_kernel), dim3(32, (unsigned)n), 256, 0, stream, ranges);
+    S2I_LAUNCH_CHECK_TAG("gemm_split_zero", 0.0, 0.0);
+    return 0;
+}
 void gemm_set_tma_epilogue(int on) { g_tma_epi = on ? 1 : 0; }
 void gemm_set_trace(unsigned long long* buf) { g_trace = buf; }
 void gemm_force_msub(int msub) { g_force_msub = msub; }

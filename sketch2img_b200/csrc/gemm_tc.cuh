@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+
+#include <vector>
 #include <cuda_fp16.h>
 #include <cstdint>
 #include <cstring>
@@ -40,6 +42,21 @@ void gemm_set_trace(unsigned long long* buf);
 
 // Tools / tests: force one (1) or two (2) 128-row M sub-tiles per CTA in gemm_tma_kernel; 0 = the cost model decides.
 void gemm_force_msub(int msub);
+
+// Split-K zero-fill plan.  A split-K GEMM reduce-adds its partial tiles into a zeroed output; zeroing each output with its
+// own launch costs ~150 launches per denoising step.  The sampler therefore records the outputs while a step runs eagerly
+// (RECORD: each GEMM still zeroes its own output and appends it to the plan) and, when the step is captured into a CUDA
+// graph, zeroes all of them with ONE kernel at the top of the graph (APPLY: a GEMM whose output is in the plan skips its
+// own zero-fill; anything else -- e.g. the shared split-K scratch, reused within a step -- keeps it).
+struct ZeroRange {
+    float* p;
+    long ld, rows;
+    int n4;
+};
+enum class ZeroMode { kOff, kRecord, kApply };
+void gemm_zero_plan(ZeroMode mode, std::vector<ZeroRange>* plan);
+// One launch that zeroes every range of a plan (ranges: device copy of the plan, n entries).
+int gemm_zero_ranges(const ZeroRange* ranges, int n, cudaStream_t stream);
 
 // Number of kernel launches issued through gemm_launch since process start (bench.py's gpu_launches).
 long gemm_launch_count();

@@ -107,7 +107,32 @@ class Sampler {
         cudaGraphExec_t exec;
         long launches;
         long alloc_gen;
+        // split-K outputs of this step kind, recorded while it ran eagerly; the captured graph zeroes them with one launch
+        std::vector<ZeroRange> plan;
+        ZeroRange* d_plan = nullptr;
     };
+    int record(Entry& e, const Key& key, cudaStream_t st) {
+        e.plan.clear();
+        gemm_zero_plan(ZeroMode::kRecord, &e.plan);
+        const int rc = body(key, st);
+        gemm_zero_plan(ZeroMode::kOff, nullptr);
+        if (e.d_plan) {
+            cudaFree(e.d_plan);
+            e.d_plan = nullptr;
+        }
+        if (rc == 0 && !e.plan.empty()) {
+            if (cudaMalloc(&e.d_plan, e.plan.size() * sizeof(ZeroRange)) != cudaSuccess) {
+                cudaGetLastError();
+                e.d_plan = nullptr;
+                e.plan.clear();      // no plan: every GEMM keeps its own zero-fill
+            } else {
+                // pageable source: the copy is staged before the call returns
+                S2I_MEMOP(cudaMemcpyAsync(e.d_plan, e.plan.data(), e.plan.size() * sizeof(ZeroRange), cudaMemcpyHostToDevice, st));
+            }
+        }
+        e.alloc_gen = g_alloc_gen;
+        return rc;
+    }
 
     int run(const Key& key, cudaStream_t st) {
         if (!use_graphs || g_prof_on) return body(key, st);
@@ -118,17 +143,21 @@ class Sampler {
             // first sighting: run eagerly (sizes every arena / scratch buffer; allocations are illegal during capture)
             if (graphs_.size() >= 12) drop_graphs();
             graphs_.push_back(Entry{key, nullptr, 0, g_alloc_gen});
-            return body(key, st);
+            return record(graphs_.back(), key, st);
         }
-        if (e->exec && e->alloc_gen != g_alloc_gen) {     // some scratch buffer moved since the capture: stale addresses
-            cudaGraphExecDestroy(e->exec);
+        if (e->alloc_gen != g_alloc_gen) {     // some scratch buffer moved since the last eager run / capture: stale addresses
+            if (e->exec) cudaGraphExecDestroy(e->exec);
             e->exec = nullptr;
+            return record(*e, key, st);       // run eagerly again (re-records the zero plan); the next call captures
         }
         if (!e->exec) {
             if (!cap_stream_) S2I_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
             const long l0 = g_launches;
             S2I_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
-            const int rc = body(key, cap_stream_);
+            int rc = e->d_plan ? gemm_zero_ranges(e->d_plan, (int)e->plan.size(), cap_stream_) : 0;
+            gemm_zero_plan(e->d_plan ? ZeroMode::kApply : ZeroMode::kOff, &e->plan);
+            if (rc == 0) rc = body(key, cap_stream_);
+            gemm_zero_plan(ZeroMode::kOff, nullptr);
             cudaGraph_t graph = nullptr;
             const cudaError_t ce = cudaStreamEndCapture(cap_stream_, &graph);
             if (rc != 0 || ce != cudaSuccess || !graph) {
@@ -167,8 +196,10 @@ class Sampler {
     size_t cap_ = 0;
 
     void drop_graphs() {
-        for (auto& c : graphs_)
+        for (auto& c : graphs_) {
             if (c.exec) cudaGraphExecDestroy(c.exec);
+            if (c.d_plan) cudaFree(c.d_plan);
+        }
         graphs_.clear();
     }
     int ensure_params() {
