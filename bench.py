@@ -336,6 +336,9 @@ def run_ours(args):
                        "weights": "random init (seed 1138), broadcast once from rank 0", "setup_s": round(setup_s, 1)},
             "e2e": {"value": ips_e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernel_breakdown_ms_per_image": breakdown,
+            "kernel_breakdown_note": "one extra image run eagerly with a CUDA event per launch (graph replay off): it includes host "
+                                     "launch gaps and the per-GEMM split-K zero-fill launches (gemm_split_zero) that the captured "
+                                     "step replaces by one launch, so the classes sum to more than ms_per_step",
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -1069,6 +1069,10 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     if (pipe_bytes < epi_bytes) pipe_bytes = epi_bytes;
     const size_t smem_bytes = pipe_bytes + tail;
     if (smem_bytes > 227u * 1024u) return set_error(S2I_ERR_ARG, "gemm(tma): %zu bytes of shared memory needed (BN %d)", smem_bytes, BN);
+    static const bool dbg = getenv("S2I_GEMM_DEBUG") != nullptr;       // tools: print the chosen configuration
+    if (dbg)
+        fprintf(stderr, "gemm_tma %s: M-tiles %ld N %d iters %d -> BN %d msub %d splits %d stages %d ctas %ld smem %zu%s\n", d.tag,
+                tiles_m, d.N, num_iters, BN, msub, tc.splits, stages, ctas, smem_bytes, via_scratch ? " (via scratch)" : "");
 
     p.a_c0 = d.a_c0; p.a_hoff = d.a_hoff; p.a_zmode = d.a_zmode;
     p.b_c0 = d.b_c0; p.b_hoff = d.b_hoff; p.b_zmode = d.b_zmode;
