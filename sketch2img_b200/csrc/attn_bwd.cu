@@ -1,4 +1,4 @@
-// Fused attention backward on tcgen05 + TMA: dQ, dK, dV from (Q, K, V, dO, log-sum-exp, delta) with the scores and
+// Fused attention backward on tcgen05 + TMA: dQ, dK, dV from (Q, K, V, O, dO, log-sum-exp) with the scores and
 // probabilities RECOMPUTED on chip -- nothing of size Nq x Nk touches HBM.  Replaces, for the UNet's attention blocks,
 // the part of `torch.autograd.grad(loss, latents_prev)` (modules/pipeline.py:159) that flows through
 // softmax(scale Q K^T) V of diffusers' CrossAttention (app.py:43 / SURVEY A.4).
@@ -47,7 +47,10 @@ struct __align__(64) BwdParams {
     uint32_t idesc_t, idesc_acc;
     float scale, scale_log2;
     const float* lse;                         // [B*heads][Nq]
-    const float* delta;                       // [B*heads][Nq]
+    const float* delta;                       // [B*heads][Nq]: rowsum(dO * O); mode 1 reads what mode 0 wrote
+    float* delta_w;                           // mode 0: where this launch writes it
+    const __half* o_g; long ldo_g;            // mode 0: forward output and its gradient (global, head h at column h * dp)
+    const __half* do_g; long lddo_g;
     int Nq;
     __half* out0; long ld0; int o0_c0;        // dQ (mode 0) or dV (mode 1)
     __half* out1; long ld1; int o1_c0;        // dK (mode 1)
@@ -216,7 +219,24 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
         float lse_r = 0.f, delta_r = 0.f;
         if (p.mode == 0 && row_ok) {
             lse_r = p.lse[(long)z * p.Nq + row0 + r] * kLog2e;
-            delta_r = p.delta[(long)z * p.Nq + row0 + r];
+            // delta_row = <dO_row, O_row>, computed here (each thread owns one query row; the two 2 dp-byte rows are read
+            // while the first operand tiles are still in flight) and left in global memory for the dK / dV launch
+            const uint4* po = reinterpret_cast<const uint4*>(p.o_g + ((long)b * p.Nq + row0 + r) * p.ldo_g + h * p.dp);
+            const uint4* pd = reinterpret_cast<const uint4*>(p.do_g + ((long)b * p.Nq + row0 + r) * p.lddo_g + h * p.dp);
+            float acc = 0.f;
+            for (int c = 0; c < p.dp / 8; ++c) {
+                const uint4 a = __ldg(po + c), g = __ldg(pd + c);
+                const __half2* ha = reinterpret_cast<const __half2*>(&a);
+                const __half2* hg = reinterpret_cast<const __half2*>(&g);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 x = __half22float2(ha[i]), y = __half22float2(hg[i]);
+                    acc = fmaf(x.x, y.x, acc);
+                    acc = fmaf(x.y, y.y, acc);
+                }
+            }
+            delta_r = acc;
+            p.delta_w[(long)z * p.Nq + row0 + r] = acc;
         }
         for (int j = 0; j < T; ++j) {
             const int col0 = j * kCols;
@@ -337,30 +357,6 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
     if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-// delta[z][i] = sum_c dO[b,i,h,c] * O[b,i,h,c]   (one warp per (z, i) row)
-__global__ void __launch_bounds__(256) attn_delta_kernel(const __half* __restrict__ o, long ldo, const __half* __restrict__ dO,
-                                                         long lddo, int B, int heads, int Nq, int dp, float* __restrict__ delta) {
-    pdl_wait();
-    pdl_launch();
-    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    const long total = (long)B * heads * Nq;
-    if (row >= total) return;
-    const int i = (int)(row % Nq);
-    const int z = (int)(row / Nq);
-    const int b = z / heads, h = z - b * heads;
-    const __half2* po = reinterpret_cast<const __half2*>(o + ((long)b * Nq + i) * ldo + h * dp);
-    const __half2* pd = reinterpret_cast<const __half2*>(dO + ((long)b * Nq + i) * lddo + h * dp);
-    float acc = 0.f;
-    for (int c = lane; c < dp / 2; c += 32) {
-        const float2 a = __half22float2(po[c]), g = __half22float2(pd[c]);
-        acc += a.x * g.x + a.y * g.y;
-    }
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) delta[row] = acc;
-}
-
 int make_map(CUtensorMap* m, const __half* ptr, long ld, int N, int B, int box_rows) {
     uint64_t dims[3] = {(uint64_t)ld, (uint64_t)N, (uint64_t)B};
     uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)N * ld * 2};
@@ -381,11 +377,9 @@ int attn_bwd_launch(const AttnBwdDesc& d, cudaStream_t stream) {
     if (!attn_bwd_supported(d.Nq, d.Nk, d.dp)) return set_error(S2I_ERR_ARG, "attn_bwd: unsupported shape Nq=%d Nk=%d dp=%d", d.Nq, d.Nk, d.dp);
     if (!d.q || !d.kv || !d.dO || !d.o || !d.lse || !d.delta || !d.dq) return set_error(S2I_ERR_ARG, "attn_bwd: null argument");
     const int Z = d.B * d.heads;
-    {   // delta = rowsum(dO * O)
-        const long rows = (long)Z * d.Nq;
-        S2I_LAUNCH((attn_delta_kernel), (unsigned)((rows + 7) / 8), 256, 0, stream, d.o, d.ldo, d.dO, d.lddo, d.B, d.heads, d.Nq, d.dp, d.delta);
-        S2I_LAUNCH_CHECK_TAG("attn_bwd_delta", 0.0, 0.0);
-    }
+    if ((d.ldo % 8) != 0 || (d.lddo % 8) != 0 || (d.dp % 8) != 0 || (reinterpret_cast<uintptr_t>(d.o) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(d.dO) & 15) != 0)
+        return set_error(S2I_ERR_ARG, "attn_bwd: O / dO rows must be 16-byte aligned per head");
     static bool attr_set = false;
     if (!attr_set) {
         S2I_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -400,7 +394,8 @@ int attn_bwd_launch(const AttnBwdDesc& d, cudaStream_t stream) {
         p.heads = d.heads; p.dp = d.dp; p.nkc = nkc; p.Nq = d.Nq;
         p.scale = d.scale;
         p.scale_log2 = d.scale * 1.4426950408889634f;
-        p.lse = d.lse; p.delta = d.delta;
+        p.lse = d.lse; p.delta = d.delta; p.delta_w = d.delta;        // delta = rowsum(dO * O): written by the dQ launch
+        p.o_g = d.o; p.ldo_g = d.ldo; p.do_g = d.dO; p.lddo_g = d.lddo;
         p.idesc_t = ptx::make_idesc_f16(128, kCols, 0, 0, 0);
         p.idesc_acc = ptx::make_idesc_f16(128, (uint32_t)d.dp, 0, 0, 1);
         if (mode == 0) {
