@@ -60,6 +60,10 @@ typedef struct s2i_gemm_desc {
      * value * gelu(gate).  out16 (optional) still receives the interleaved projection itself.  Needs N % 64 == 0 and the
      * TMA-epilogue kernel (K-major operands, Z = 1, no residual / out32 / split-K). */
     void* out_glu; long long ld_glu;
+    /* Optional fp32 scratch [rows][N] (dense) owned by the caller: an fp16-only output whose K is split reduce-adds its
+     * partial tiles there before the conversion, instead of in the library's shared scratch -- a per-call buffer can be
+     * zeroed ahead of time together with the other split-K outputs of a captured step. */
+    float* scratch32;
 } s2i_gemm_desc;
 
 int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream);

@@ -1021,10 +1021,10 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
         const TileChoice ts = choose_tiles_tma(d.N, tiles_m, num_iters, true, epi_s);
         if (ts.splits > 1 && model_cycles_tma(d.N, tiles_m, num_iters, ts.BN, ts.splits, epi_s, ts.msub) + 5000.0 <
                                  model_cycles_tma(d.N, tiles_m, num_iters, tc.BN, 1, epi, tc.msub)) {
-            S2I_TRY(ensure_ws());
+            if (!d_in.scratch32) S2I_TRY(ensure_ws());
             tc = ts;
             via_scratch = can_split = true;
-            d.out32 = g_ws;
+            d.out32 = d_in.scratch32 ? d_in.scratch32 : g_ws;
             d.ld32 = d.N;
             d.out16 = nullptr;
         }
@@ -1097,7 +1097,8 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
         const long rows = (long)d.aW * d.aH * d.aB;
         const long n4 = d.N / 4, total = rows * n4;
         bool planned = false;
-        if (g_zero_mode == ZeroMode::kApply && g_zero_plan && !via_scratch) {
+        const bool shared_ws = via_scratch && !d_in.scratch32;      // the library's scratch is reused within a step: never planned
+        if (g_zero_mode == ZeroMode::kApply && g_zero_plan && !shared_ws) {
             for (const ZeroRange& z : *g_zero_plan)
                 if (z.p == d.out32 && z.ld == (long)d.ld32 && z.rows == rows && z.n4 == (int)n4) {
                     planned = true;      // zeroed by the plan's single launch at the top of the captured step
@@ -1108,8 +1109,7 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
             S2I_LAUNCH((zero_rows_kernel), (unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, stream,
                        d.out32, (long)d.ld32, rows, (int)n4);
             S2I_LAUNCH_CHECK_TAG("gemm_split_zero", 0.0, 0.0);
-            // the shared scratch is reused by several GEMMs of a step: never planned
-            if (g_zero_mode == ZeroMode::kRecord && g_zero_plan && !via_scratch)
+            if (g_zero_mode == ZeroMode::kRecord && g_zero_plan && !shared_ws)
                 g_zero_plan->push_back(ZeroRange{d.out32, (long)d.ld32, rows, (int)n4});
         }
     }
@@ -1137,7 +1137,7 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     if (via_scratch) {
         const long total = rows_total * (d.N / 4);
         S2I_LAUNCH((cast_rows_kernel), (unsigned)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048), 256, 0, stream, 
-            g_ws, d.N, static_cast<__half*>(d_in.out16), d_in.ld16, rows_total, d.N / 4);
+            d.out32, d.N, static_cast<__half*>(d_in.out16), d_in.ld16, rows_total, d.N / 4);
         S2I_LAUNCH_CHECK_TAG("gemm_split_cast", 0.0, 0.0);
     }
     return 0;

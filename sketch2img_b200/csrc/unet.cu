@@ -585,6 +585,11 @@ double* UNet::new_stats() {
 
 int UNet::gemm(const H16& a, bool spatial, int taps, const __half* w, long w_ld, int N, int Kc, const float* bias,
                const float* rowvec, const F32* residual, F32* out32, H16* out16) {
+    // An fp16-only output with a long contraction may be computed split-K through an fp32 scratch: give it its own arena
+    // buffer (same allocation in the sizing pass) so its zero-fill joins the step's zero plan instead of a per-call launch.
+    float* scratch = nullptr;
+    if (out16 && !out32 && (long)Kc * taps >= 1024 && a.rows() * (long)N * 4 <= (32L << 20))
+        scratch = dalloc<float>((size_t)a.rows() * N);
     if (dry_) return 0;
     GemmDesc d;
     d.A = a.p;
@@ -619,6 +624,7 @@ int UNet::gemm(const H16& a, bool spatial, int taps, const __half* w, long w_ld,
         d.out16 = out16->p;
         d.ld16 = out16->ld;
     }
+    d.scratch32 = scratch;
     return gemm_launch(d, st_);
 }
 
