@@ -1160,7 +1160,8 @@ void gemm_zero_plan(ZeroMode mode, std::vector<ZeroRange>* plan) {
 
 int gemm_zero_ranges(const ZeroRange* ranges, int n, cudaStream_t stream) {
     if (n <= 0) return 0;
-    S2I_LAUNCH((zero_ranges_kernel), dim3(32, (unsigned)n), 256, 0, stream, ranges);
+    // the ranges differ 20x in size: enough blocks per range that the large ones are not the tail
+    S2I_LAUNCH((zero_ranges_kernel), dim3(148, (unsigned)n), 256, 0, stream, ranges);
     S2I_LAUNCH_CHECK_TAG("gemm_split_zero", 0.0, 0.0);
     return 0;
 }
