@@ -155,7 +155,7 @@ class AntiGradientPipeline:
         emb = prompt_embeds.to(device, torch.float32)
         if emb.shape[0] != 2 * S:
             raise ValueError(f"prompt_embeds must be [2*{S},77,D] ordered [uncond..., cond...], got {tuple(emb.shape)}")
-        # engine layout: (uncond_s, cond_s) pairs
+        # s2i_sampler_step takes the context as (uncond_s, cond_s) pairs (it permutes to its sample-major batch internally)
         ctx = torch.stack([emb[:S], emb[S:]], dim=1).reshape(2 * S, emb.shape[1], emb.shape[2]).contiguous()
 
         self.scheduler.set_timesteps(num_inference_steps, device=device)
