@@ -23,6 +23,8 @@ sys.path.insert(0, ROOT)
 NUM_INFERENCE_STEPS = 50
 GUIDANCE = 7.5
 METRIC = "512x512 50-step sketch-guided SD1.5 images/sec"
+# one string for both arms (the driver compares config.workload of the two JSON lines)
+WORKLOAD = "SD1.5 512x512 50-step DDIM CFG=7.5 + LGP sketch guidance, batch 1 per GPU (configs[1])"
 
 
 def guided_count(n):
@@ -87,12 +89,26 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _latest_profile(prefix, suffix):
+    """Newest tracked summary profiles/r<round>_<prefix>_v<k><suffix> (highest round, then highest version)."""
+    import glob
+    import re
+    best, best_key = None, None
+    for path in glob.glob(os.path.join(ROOT, "profiles", "r*_%s_v*%s" % (prefix, suffix))):
+        m = re.match(r"r(\d+)_%s_v(\d+)" % re.escape(prefix), os.path.basename(path))
+        if m and (best_key is None or (int(m.group(1)), int(m.group(2))) > best_key):
+            best, best_key = path, (int(m.group(1)), int(m.group(2)))
+    return best
+
+
 def ncu_dram_bytes_per_launch():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-    capture (profiles/r1_gemm_tma_ncu_v2.txt: mean over the captured launches); None if the summary is not there."""
-    path = os.path.join(ROOT, "profiles", "r1_gemm_tma_ncu_v2.txt")
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest tracked COLD
+    `ncu --set full` capture of gemm_tma_kernel (profiles/r*_gemm_tma_ncu_v*_cold.txt, else round 1's v5: default cache
+    control, i.e. L2 flushed before every replay -- what a launch reads from HBM when nothing of it is L2-resident, which
+    is the case for the 1.7 GB of weights streamed by every forward).  Returns (bytes, file) or (None, None)."""
+    path = _latest_profile("gemm_tma_ncu", "_cold.txt") or os.path.join(ROOT, "profiles", "r1_gemm_tma_ncu_v5.txt")
     if not os.path.exists(path):
-        return None
+        return None, None
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot, n = 0.0, 0
     for line in open(path):
@@ -101,7 +117,26 @@ def ncu_dram_bytes_per_launch():
             vals = [float(x) for x in line.split(":", 1)[1].split("|")]
             tot += sum(vals) * mult.get(unit, 1.0)
             n = len(vals)
-    return tot / n if n else None
+    return (tot / n if n else None), os.path.relpath(path, ROOT)
+
+
+def ncu_gemm_ms_of_launch_list():
+    """Summed ncu durations of the GEMM kernels in the newest tracked launch list of tools/one_step.py 3 (2 guided + 1
+    unguided denoising steps): (ms, file) or (None, None)."""
+    path = _latest_profile("launches", "_warm.txt")
+    if not path:
+        return None, None
+    ms = 0.0
+    for line in open(path):
+        f = line.split()
+        if len(f) >= 5 and f[0] in ("gemm_tma_kernel", "gemm_tc_kernel"):
+            try:
+                ms += float(f[2])
+            except ValueError:
+                pass
+        if line.startswith("# launch sequence"):
+            break
+    return (ms if ms > 0 else None), os.path.relpath(path, ROOT)
 
 
 # ------------------------------------------------------------------------------------------------- CPU reference
@@ -150,7 +185,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    res = cpu_reference_sample(threads, repeats=args.steps, warmup=min(args.warmup, 1))
+    res = cpu_reference_sample(threads, repeats=args.steps, warmup=args.warmup)
     tg = sum(r[0] for r in res) / len(res)
     tu = sum(r[1] for r in res) / len(res)
     ips = images_per_sec_from_steps(tg, tu)
@@ -158,15 +193,96 @@ def run_reference(args):
               "images/sec = 1 / (26 t_guided + 24 t_unguided)")
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * (tg + tu), "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (tg + tu), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SD1.5 512x512 50-step DDIM CFG=7.5 + LGP sketch guidance, batch 1 (configs[1])",
-                   "cpu_ms_guided_step": 1e3 * tg, "cpu_ms_unguided_step": 1e3 * tu},
+        "config": {"workload": WORKLOAD, "cpu_ms_guided_step": 1e3 * tg, "cpu_ms_unguided_step": 1e3 * tu,
+                   "full_image_check": "profiles/r2_cpu_full_image_v1.txt: a whole 50-step image timed on the authoring "
+                                       "container's 8 cores next to this 2-step extrapolation"},
         "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# ------------------------------------------------------------------------------------------------- configs[3]
+def run_config4(args, rank, world, dev, barrier, n_timed):
+    """BASELINE.json configs[3]: SD2.1-768 topology (latent 96 x 96, v-prediction DDIM, CFG 7.5) with the injected sketch
+    attention (SatMixin, modules/sketch_guided_attn.py) active in all 16 transformer blocks, no LGP / no backward, one image
+    per GPU per call (8 images over 8 GPUs).  Sketch features: synthetic tensors shaped like SketchEncoder's output."""
+    import torch
+    from sketch2img_b200 import synthetic
+    from sketch2img_b200 import distributed as D
+    from sketch2img_b200.pipeline import AntiGradientPipeline
+    from sketch2img_b200.scheduler import DDIMScheduler
+    from sketch2img_b200.sketch_guided_attn import SatMixin
+    from sketch2img_b200.unet import SD21_CONFIG, UNet2DConditionModel
+    cfg = dict(SD21_CONFIG)
+    L, Dc = int(cfg["sample_size"]), int(cfg["cross_attention_dim"])
+    t0 = time.time()
+    if rank == 0:
+        sd = synthetic.unet_state_dict(cfg, seed=2138)
+    else:
+        sd = {k: torch.empty(shape) for k, shape in synthetic.unet_param_shapes(cfg).items()}
+    if world > 1:
+        sd = D.broadcast_state_dict(sd, src=0, device=dev, half_matrices=True)
+    unet = UNet2DConditionModel(cfg, sd, device=dev)
+    del sd
+    torch.manual_seed(2139)                     # same SatMixin weights on every rank
+    sat = SatMixin(unet)
+    boc = cfg["block_out_channels"]
+    g = torch.Generator().manual_seed(2140 + rank)
+    res, side = [], L
+    for i, c in enumerate(boc):                 # modules/sketch_encoder.py:93-98: per down block (layer outputs..., downsampled)
+        maps = [torch.randn(2, c, side, side, generator=g) for _ in range(2)]
+        if i < 3:
+            side //= 2
+            maps.append(torch.randn(2, c, side, side, generator=g))
+        res.append(tuple(m.to(dev) for m in maps))
+    sat.set_res_samples(res)
+    sat.set_scale(1.0)
+    pipe = AntiGradientPipeline(unet=unet, scheduler=DDIMScheduler(prediction_type="v_prediction"))
+    lat = torch.randn(1, 4, L, L, generator=g).to(dev)
+    emb = torch.randn(2, 77, Dc, generator=g).to(dev)
+    setup_s = time.time() - t0
+
+    def call():
+        return pipe("synthetic", num_inference_steps=NUM_INFERENCE_STEPS, guidance_scale=GUIDANCE, latents=lat, sketch_image=None,
+                    prompt_embeds=emb, output_type="latent")
+    call()
+    barrier()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for _ in range(n_timed):
+        out = call()
+    eb.record()
+    barrier()
+    ms = D.max_over_ranks(ea.elapsed_time(eb), dev)
+    # algorithmic FLOPs: SD2.1 forward at 96 x 96 (SURVEY 8d: 1074.6 GMAC) + the injected attention per block:
+    # q / out / 1x1-conv projections (3 N C^2) and QK^T + PV against N sketch tokens (2 N^2 C)
+    macs = synthetic.count_macs(cfg, L)["forward"]
+    sat_macs, side = 0, L
+    levels = [(boc[0], L, 2), (boc[1], L // 2, 2), (boc[2], L // 4, 2), (boc[3], L // 8, 1), (boc[2], L // 4, 3), (boc[1], L // 2, 3),
+              (boc[0], L, 3)]
+    for c, sd_, nblk in levels:
+        n = sd_ * sd_
+        sat_macs += nblk * (3 * n * c * c + 2 * n * n * c)
+    flops_image = NUM_INFERENCE_STEPS * 2 * 2.0 * (macs + sat_macs)
+    tf_peak, _, peak_src = measured_peaks()
+    achieved = flops_image * n_timed / (ms * 1e-3) / 1e12
+    ok = bool(torch.isfinite(out).all().item())
+    del pipe, sat, unet
+    torch.cuda.empty_cache()
+    return {"workload": "SD2.1-768 topology, 96x96 latent, 50-step v-prediction DDIM CFG=7.5 + SatMixin injected sketch attention "
+                        "(16 blocks, scale 1.0), no LGP, 1 image per GPU per call (configs[3]: batch 8 over 8 GPUs)",
+            "global_batch": world, "images_per_sec": world * n_timed / (ms * 1e-3), "ms_per_image": ms / n_timed,
+            "ms_per_denoise_step": ms / n_timed / NUM_INFERENCE_STEPS, "timed_calls": n_timed, "finite": ok,
+            "setup_s": round(setup_s, 1),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                         "peak_source": peak_src, "algorithmic_flops_per_image": flops_image,
+                         "injected_attention_share_of_flops": sat_macs / (macs + sat_macs),
+                         "how": "whole-step figure: algorithmic FLOPs of the CFG-pair forwards incl. the injected attention / "
+                                "CUDA-event time of the graph-replayed images (max over ranks)"}}
 
 
 # ------------------------------------------------------------------------------------------------- CUDA arm
@@ -195,7 +311,7 @@ def run_ours(args):
     else:
         sd = {k: torch.empty(shape) for k, shape in synthetic.unet_param_shapes(cfg).items()}
     if world > 1:
-        sd = D.broadcast_state_dict(sd, src=0, device=dev)
+        sd = D.broadcast_state_dict(sd, src=0, device=dev, half_matrices=True)
     unet = UNet2DConditionModel(cfg, sd, device=dev)
     del sd
     torch.manual_seed(1139)
@@ -268,6 +384,38 @@ def run_ours(args):
     ips = world * args.steps / (ms_total * 1e-3)
     ips_e2e = world * args.steps / (ms_e2e * 1e-3)
 
+    # ---- configs[2] / configs[4]: several images per GPU per call (every image is its own batch-1 reference call;
+    # they share the UNet launches: batch 2 S).  configs[2] = 32 images over 8 GPUs = 4 per GPU per call.
+    extras = {}
+    if not args.headline_only:
+        sweep = {"1": {"images_per_sec": ips, "ms_per_image": ms_total / args.steps}}
+        n_timed = max(1, min(args.steps, 2))
+        for S in (2, 4, 8):
+            lat_s, emb_s, tgt_s = (t.to(dev) for t in synthetic.sample_inputs(cfg, S, seed=5139 + 1000 * rank + S))
+            pipe.max_samples_per_launch = S
+
+            def call():
+                return pipe(["synthetic"] * S, num_inference_steps=NUM_INFERENCE_STEPS, guidance_scale=GUIDANCE, latents=lat_s,
+                            sketch_image=tgt_s, prompt_embeds=emb_s, output_type="latent")
+            call()                      # arena sizing + graph capture for this batch
+            barrier()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            for _ in range(n_timed):
+                call()
+            eb.record()
+            barrier()
+            ms = D.max_over_ranks(ea.elapsed_time(eb), dev)
+            sweep[str(S)] = {"images_per_sec": world * S * n_timed / (ms * 1e-3), "ms_per_image": ms / (S * n_timed),
+                             "arena_gb": round(unet.engine.arena_bytes() / 1e9, 2)}
+        pipe.max_samples_per_launch = 4
+        extras["batch_sweep"] = {"images_per_gpu_per_call": sweep, "n_gpus": world, "timed_calls": n_timed,
+                                 "note": "whole-job images/sec over all ranks at 1 / 2 / 4 / 8 images per GPU per call (configs[4]; "
+                                         "the 1-image entry is the headline value)"}
+        extras["config3"] = {"workload": "SD1.5 512x512 50-step CFG=7.5 + LGP, 4 images per GPU per call (configs[2]: batch 32 over 8 GPUs)",
+                             "global_batch": 4 * world, **sweep["4"]}
+        extras["config4"] = run_config4(args, rank, world, dev, barrier, n_timed)
+
     line = None
     if rank == 0:
         # ---- per-kernel-class device time of one image (CUDA events around every libs2i launch, same stream)
@@ -287,6 +435,16 @@ def run_ours(args):
         achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         gemm_roof_ms = sum(v["roof_ms"] for v in gemm.values())
         gemm_bytes = sum(v["bytes"] for v in gemm.values())
+        traffic, traffic_src = ncu_dram_bytes_per_launch()
+        # the same class under ncu: GEMM FLOPs of tools/one_step.py 3 (2 guided + 1 unguided steps, profiled here the same
+        # way) / the summed ncu durations of the GEMM kernels in the tracked launch list of that command
+        _lib.profile_begin(tf_peak, hbm_peak)
+        pipe("synthetic", num_inference_steps=3, guidance_scale=GUIDANCE, latents=lat_d[:1], sketch_image=tgt_d[:1],
+             prompt_embeds=emb_d[0], output_type="latent")
+        prof3 = _lib.profile_end()
+        fl3 = sum(v["flops"] for k, v in prof3.items() if k.startswith("gemm"))
+        ncu_ms, ncu_src = ncu_gemm_ms_of_launch_list()
+        frac_ncu = (fl3 / (ncu_ms * 1e-3) / 1e12 / tf_peak) if ncu_ms else None
 
         def tensor_class(tag):
             v = prof.get(tag)
@@ -298,7 +456,8 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": "gemm_tma_kernel + gemm_tc_kernel (tcgen05 + TMA implicit GEMM: conv3x3 / conv1x1 / "
                                                  "Linear / LGP MLP, forward and input-gradient)",
                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                    "traffic": ncu_dram_bytes_per_launch(), "peak_source": peak_src,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "frac_ncu": frac_ncu, "frac_ncu_source": ncu_src,
                     "algorithmic_flops_per_launch_mean": gemm_fl / gemm_n if gemm_n else None,
                     "algorithmic_bytes_per_launch_mean": gemm_bytes / gemm_n if gemm_n else None,
                     "per_launch_roofline": {
@@ -317,9 +476,9 @@ def run_ours(args):
                                                           if gemm_ms > 0 and all_ms > 0 else None),
                     "algorithmic_flops_per_image_all_kernels": fl["image"],
                     "other_tensor_kernels": {"attn_fwd_kernel": tensor_class("attn_fwd"), "attn_bwd_kernel": tensor_class("attn_bwd")},
-                    "note": "B = 2 (one CFG pair): every operand is L2-resident (ncu: ~0 DRAM bytes per launch, profiles/"
-                            "r1_gemm_tma_ncu_v2.txt); the binding resource is the chip-wide L2 -> SM operand rate and per-launch "
-                            "latency, not HBM or the tensor pipe (DESIGN.md section 4)",
+                    "note": "B = 2 (one CFG pair): activations stay in the 126 MB L2 from producer to consumer, the 1.7 GB of weights "
+                            "stream from HBM once per forward (traffic = the cold capture: unique operand bytes, no re-reads); what "
+                            "binds most launches is per-launch latency and the L2 -> SM operand rate (DESIGN.md section 4)",
                     "how": "sum of algorithmic FLOPs of one image's GEMM launches / sum of their CUDA-event durations "
                            "(s2i_profile_begin/end on the launch stream)"}
         breakdown = {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in
@@ -329,7 +488,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), fp32 residual stream",
             "data": "synthetic",
-            "config": {"workload": "SD1.5 512x512 50-step DDIM CFG=7.5 + LGP sketch guidance, batch 1 per GPU (configs[1])",
+            "config": {"workload": WORKLOAD,
                        "num_inference_steps": NUM_INFERENCE_STEPS, "guided_steps": guided_count(NUM_INFERENCE_STEPS),
                        "images_per_gpu_per_bench_step": 1, "ms_per_denoise_step": ms_total / args.steps / NUM_INFERENCE_STEPS,
                        "l2": "per-step working set (1.7 GB fp16 weights + >1 GB activations) exceeds the 126 MB L2; no flush needed",
@@ -337,9 +496,9 @@ def run_ours(args):
             "e2e": {"value": ips_e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernel_breakdown_ms_per_image": breakdown,
             "kernel_breakdown_note": "one extra image run eagerly with a CUDA event per launch (graph replay off): it includes host "
-                                     "launch gaps and the per-GEMM split-K zero-fill launches (gemm_split_zero) that the captured "
-                                     "step replaces by one launch, so the classes sum to more than ms_per_step",
+                                     "launch gaps, so the classes sum to more than ms_per_step",
         }
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             (tg, tu), = cpu_reference_sample(threads, repeats=1, warmup=0)
@@ -381,6 +540,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the configs[2]/[3]/[4] measurements (tuning runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

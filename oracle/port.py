@@ -134,10 +134,11 @@ def lgp_features(taps, size):
     return torch.cat([F.interpolate(m.output, size=size, mode="bilinear") for m in taps], dim=1)
 
 
-def anti_gradient(lgp, scheduler, taps, x_in, latents, noise, t, target, beta):
+def anti_gradient(lgp, scheduler, taps, x_in, latents, noise, t, target, beta, record=None):
     """pipeline.py:141-161.  x_in is the CFG-doubled, grad-enabled UNet input [2,4,h,w]; the loss is the
     MSE between the sketch target and the LGP prediction on the cond half; the step is
-    alpha = ||x_in - latents||_F / ||g_cond||_F * beta along g_cond = -dLoss/dx_in (cond half)."""
+    alpha = ||x_in - latents||_F / ||g_cond||_F * beta along g_cond = -dLoss/dx_in (cond half).
+    record (tests / fixtures only): dict that receives the loss, the cond gradient and alpha of this call."""
     if target is None:
         return latents
     feats = lgp_features(taps, latents.shape[2])
@@ -151,7 +152,30 @@ def anti_gradient(lgp, scheduler, taps, x_in, latents, noise, t, target, beta):
     loss = F.mse_loss(target.float(), cond.float(), reduction="mean")
     g = (-torch.autograd.grad(loss, x_in)[0]).chunk(2)[1]
     alpha = torch.linalg.norm(x_in - latents) / torch.linalg.norm(g) * beta
+    if record is not None:
+        record.update(loss=float(loss), g=g.detach().clone(), alpha=float(alpha))
     return latents + alpha * g
+
+
+def guided_step(unet, lgp, scheduler, text_emb, latents, noise, t, target, guided, taps, guidance_scale=7.5, beta=1.6,
+                record=None):
+    """ONE iteration of the loop body pipeline.py:83-110 from explicit state (``scheduler.set_timesteps`` already called).
+    record (tests / fixtures only): receives the pre-guidance scheduler output ``x_ddim`` and anti_gradient's record."""
+    with torch.no_grad():
+        x_in = torch.cat([latents] * 2)                                     # :85
+        x_in = scheduler.scale_model_input(x_in, t).requires_grad_(True)    # :86-87
+        with torch.enable_grad() if guided else torch.no_grad():
+            eps = unet(x_in, t, encoder_hidden_states=text_emb).sample      # :96
+        eps_u, eps_c = eps.chunk(2)                                         # :100
+        eps = eps_u + guidance_scale * (eps_c - eps_u)                      # :101
+        extra = {"eta": 0.0} if "eta" in inspect.signature(scheduler.step).parameters else {}           # :78
+        latents = scheduler.step(eps, t, latents, **extra).prev_sample      # :104
+        if record is not None:
+            record["x_ddim"] = latents.detach().clone()
+        if guided:
+            with torch.enable_grad():
+                latents = anti_gradient(lgp, scheduler, taps, x_in, latents, noise, t, target, beta, record)  # :109
+    return latents
 
 
 @torch.no_grad()
@@ -167,18 +191,8 @@ def guided_sample(unet, lgp, scheduler, text_emb, latents, target, num_steps=50,
     noise = latents.detach().clone()                                        # :75
     stop = stop_frac * len(ts)                                              # :90
     for i, t in enumerate(ts):
-        x_in = torch.cat([latents] * 2)                                     # :85
-        x_in = scheduler.scale_model_input(x_in, t).requires_grad_(True)    # :86-87
         guided = i <= stop                                                  # :89-92,108 (Q4)
-        with torch.enable_grad() if guided else torch.no_grad():
-            eps = unet(x_in, t, encoder_hidden_states=text_emb).sample      # :96
-        eps_u, eps_c = eps.chunk(2)                                         # :100
-        eps = eps_u + guidance_scale * (eps_c - eps_u)                      # :101
-        extra = {"eta": 0.0} if "eta" in inspect.signature(scheduler.step).parameters else {}           # :78
-        latents = scheduler.step(eps, t, latents, **extra).prev_sample      # :104
-        if guided:
-            with torch.enable_grad():
-                latents = anti_gradient(lgp, scheduler, taps, x_in, latents, noise, t, target, beta)  # :109
+        latents = guided_step(unet, lgp, scheduler, text_emb, latents, noise, t, target, guided, taps, guidance_scale, beta)
         if callback is not None:
             callback(i, t, latents)
     return latents

@@ -56,6 +56,9 @@ struct __align__(64) GemmParams {
     CUtensorMap mapGlu;      // fp16 gated-GELU output [rows][N / 2], same box / swizzle
     int has_res, has_o32, has_o16, has_glu;
     int split_add;           // split-K by fp32 reduce-add into a zeroed output (split 0 carries bias + residual)
+    int pipe_bytes;          // shared-memory bytes in front of the barriers (max of pipeline, epilogue staging, partial tile)
+    int csplit;              // split-K inside a thread-block cluster (1, 1, csplit): partial tiles reduced through distributed
+                             // shared memory in rank order (deterministic; no zero-fill, no atomics); 0 / 1 = off
     int msub;                // M sub-tiles per CTA (1 or 2): two 128-row A tiles share every B tile (two TMEM accumulators)
     int tiles_m;             // number of 128-row M tiles of the problem
     unsigned long long* trace;   // optional [ctas][16] %globaltimer stamps of the kernel's phases (tools/gemm_trace.py)
@@ -68,6 +71,20 @@ __device__ __forceinline__ void stamp(const GemmParams& p, int slot) {
         const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
         p.trace[(long)cta * 16 + slot] = t;
     }
+}
+
+// ---- thread-block cluster helpers (split-K inside a cluster) ---------------------------------------------------------
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(rank));
+    return ra;
+}
+__device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
 }
 
 constexpr int kEpiLd = 36;   // floats per row of the per-warp 32x32 transpose buffer (16-byte aligned, conflict-free)
@@ -106,7 +123,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const GemmParams& p) {
     t.mt0 = mt;
     t.n0 = blockIdx.y * p.BN;
     t.z = blockIdx.z / p.splits;
-    t.split = blockIdx.z - t.z * p.splits;
+    t.split = blockIdx.z - t.z * p.splits;      // cluster split-K: clusters are (1, 1, splits), so this is also the cluster rank
     t.zb = t.z / p.zh;
     t.zhd = t.z - t.zb * p.zh;
     t.x0 = t.y0 = t.b0 = t.m0 = 0;
@@ -223,11 +240,8 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
     const int stage_bytes = msub * kAStageBytes + b_stage_bytes;
     const int nch = p.BN >> 5;
     const int use32 = p.has_res | p.has_o32;
-    int pipe_bytes = p.stages * stage_bytes;
-    const int epi_bytes = (use32 ? nch * kChunk32Bytes : 0) + (p.has_o16 ? nch * kChunk16Bytes : 0) +
-                          (p.has_glu ? (nch >> 1) * kChunk16Bytes : 0);
-    if (pipe_bytes < epi_bytes) pipe_bytes = epi_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + pipe_bytes);
+    // pipeline stages; aliased after the mainloop by the epilogue staging / the cluster split-K partial tile (host: launch_tma)
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.pipe_bytes);
     uint64_t* empty = full + p.stages;
     uint64_t* accum_full = empty + p.stages;
     uint64_t* r_full = accum_full + 1;                      // [kMaxChunks]
@@ -269,7 +283,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
     pdl_launch();     // TMEM is held: dependents may become resident
     if (threadIdx.x == 0) stamp(p, 1);
     const bool add_res = p.has_res && (!p.split_add || t.split == 0);
-    const bool add_bias = !p.split_add || t.split == 0;
+    const bool add_bias = p.csplit > 1 || !p.split_add || t.split == 0;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -314,6 +328,23 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
         const uint32_t sw128 = (uint32_t)(r & 7);
         const uint32_t sw64 = (uint32_t)((r >> 1) & 3);
         uint8_t* base16 = smem + (use32 ? nch * kChunk32Bytes : 0);
+        if (p.csplit > 1) {
+            // cluster split-K: this CTA's partial tile (its K range) -> shared memory [128][BN + 4] fp32 (the idle pipeline
+            // stages); the cluster reduces it below, after the role branches
+            float* part = reinterpret_cast<float*>(smem);
+            const int ldp = p.BN + 4;
+            for (int c = eset; c < nch; c += ESETS) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
+                ptx::tmem_ld_wait();
+                float* dst = part + (long)r * ldp + c * 32;
+    #pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    *reinterpret_cast<float4*>(dst + 4 * u) =
+                        make_float4(__uint_as_float(raw[4 * u]), __uint_as_float(raw[4 * u + 1]), __uint_as_float(raw[4 * u + 2]),
+                                    __uint_as_float(raw[4 * u + 3]));
+            }
+        } else
         for (int sub = 0; sub < msub; ++sub) {
             if (t.mt0 + sub >= p.tiles_m) break;          // odd tile count: the last CTA has one sub-tile
             const int xs = sub ? t.x1 : t.x0, ys = sub ? t.y1 : t.y0, bs = sub ? t.b1 : t.b0;
@@ -445,6 +476,74 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
             ptx::tma_store_wait_read0();   // shared memory stays valid until the stores have read it
             if (e == 0) stamp(p, 8);
         }
+    }
+
+    if (p.csplit > 1) {
+        // ---------------------------------------------------- cluster split-K reduction through distributed shared memory
+        // Every CTA of the cluster (1, 1, csplit) holds the partial tile of its K range.  CTA `rank` owns the tile rows
+        // [rank * 128 / csplit, ...): it adds the csplit partial rows in RANK ORDER (so the sum does not depend on timing),
+        // applies the epilogue (bias, ReLU / rounding emulation, fp32 residual) and writes the result rows to global memory.
+        ptx::tc_fence_before();
+        __syncwarp();
+        cluster_arrive();
+        cluster_wait();
+        if (warp >= 2) {
+            const int e = threadIdx.x - 64;
+            const int CS = p.csplit;
+            const int rows_per = kBlockM / CS;
+            const int row0 = t.split * rows_per;
+            const int nq = p.BN >> 2;
+            const int ldp = p.BN + 4;
+            const uint32_t part_local = ptx::smem_u32(smem);
+            uint32_t base_k[8];
+    #pragma unroll
+            for (int k = 0; k < 8; ++k) base_k[k] = map_to_rank(part_local, (uint32_t)(k < CS ? k : 0));
+            for (int idx = e; idx < rows_per * nq; idx += 128 * ESETS) {
+                const int rr = idx / nq;
+                const int c4 = (idx - rr * nq) << 2;
+                const int row = row0 + rr;
+                const int n = t.n0 + c4;
+                if (n >= p.N) continue;
+                const int xi = row % p.tw;
+                const int yi = (row / p.tw) % p.th;
+                const int bi = row / (p.tw * p.th);
+                if (bi >= p.tb || t.x0 + xi >= p.W || t.y0 + yi >= p.H || t.b0 + bi >= p.Bn) continue;
+                const long grow = ((long)(t.b0 + bi) * p.H + (t.y0 + yi)) * p.W + (t.x0 + xi);
+                const uint32_t off = (uint32_t)((row * ldp + c4) * 4);
+                float4 v[8];
+    #pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < CS) v[k] = ld_cluster_f4(base_k[k] + off);
+                float4 acc = v[0];
+    #pragma unroll
+                for (int k = 1; k < 8; ++k)
+                    if (k < CS) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c4);
+                acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+                if (p.relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+                if (p.qscale != 0.f) {
+                    acc.x = __half2float(__float2half_rn(acc.x * p.qinv)) * p.qscale;
+                    acc.y = __half2float(__float2half_rn(acc.y * p.qinv)) * p.qscale;
+                    acc.z = __half2float(__float2half_rn(acc.z * p.qinv)) * p.qscale;
+                    acc.w = __half2float(__float2half_rn(acc.w * p.qinv)) * p.qscale;
+                }
+                if (p.residual) {
+                    const float4 x = ldg_f4(p.residual + grow * p.res_ld + n);
+                    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+                }
+                if (p.out32) *reinterpret_cast<float4*>(p.out32 + grow * p.ld32 + n) = acc;
+                if (p.out16) {
+                    const __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out16) + grow * p.ld16 + n) = pk;
+                }
+            }
+        }
+        __syncwarp();
+        cluster_arrive();         // this CTA no longer reads its peers' shared memory ...
+        cluster_wait();           // ... and no peer reads this CTA's: it may exit
     }
 
     ptx::tc_fence_before();
@@ -840,12 +939,54 @@ bool g_allow_msub = [] {
     return !(e && e[0] == '0');
 }();
 
+// Split-K mode of gemm_tma_kernel.  Default: inside a thread-block cluster (1, 1, S), S in {2, 4, 8}: the partial tiles are
+// reduced through distributed shared memory in rank order -- deterministic, no zero-fill launch, no fp32 scratch + cast for
+// fp16 outputs.  S2I_SPLITK_ADD=1 selects the previous form (up to 32 splits reduce-added into a zeroed output by
+// cp.reduce.async.bulk: the sum order, hence the low bits of the result, varies from run to run).
+bool g_split_add_mode = [] {
+    const char* e = getenv("S2I_SPLITK_ADD");
+    return e && e[0] == '1';
+}();
+
+// cluster split-K: ~2 cluster barriers + the DSMEM reduction of one tile's worth of fp32 per CTA
+double model_cycles_cluster(int N, long tiles_m, int iters, int BN, int splits, int epi) {
+    const int tiles_n = ceil_div(N, BN);
+    const long ctas = tiles_m * tiles_n * splits;
+    const int stage_bytes = kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
+    const long part_bytes = (long)kBlockM * (BN + 4) * 4;
+    const int occ = (2 * stage_bytes <= 100 * 1024 && part_bytes <= 100 * 1024 && BN <= 256) ? 2 : 1;
+    const long slots = (long)kNumSMs * occ;
+    const long waves = ceil_div_l(ctas, slots);
+    const int it = ceil_div(iters, splits);
+    const double resident = (double)(ctas <= kNumSMs ? 1 : occ);
+    const double mma = 2.0 * BN * resident;
+    const double tma = (double)(kAStageBytes + BN * 128) / (resident > 1.0 ? 21.0 : 31.0);
+    const double per_iter = mma > tma ? mma : tma;
+    // prologue / first load / drain as in model_cycles_tma; TMEM -> smem 60 cycles per chunk; two cluster barriers;
+    // the DSMEM reduction moves 128 x BN fp32 per CTA at ~48 B/clk plus the global epilogue of 128 / S rows
+    const double fixed = 9000.0 + 60.0 * (BN / 32) + 1200.0 + (double)kBlockM * BN * 4 / 48.0 +
+                         ((epi & 1) ? 600.0 : 0.0);
+    return (double)waves * (it * per_iter + fixed);
+}
+
 TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, int epi) {
     static const int cands[] = {256, 192, 160, 128, 96, 64, 32};
     TileChoice best{N >= 128 ? 128 : N, 1};
     double best_c = 1e30;
     for (int c : cands) {
         if (c > N && c != 32) continue;
+        if (!g_split_add_mode && allow_split) {
+            const long base = tiles_m * ceil_div(N, c);
+            for (int sp = 2; sp <= 8; sp *= 2) {
+                // clusters must be co-scheduled: keep the grid within one wave of (possibly paired) CTAs
+                if (base * sp > 2 * kNumSMs || iters / sp < 2) break;
+                const double cyc = model_cycles_cluster(N, tiles_m, iters, c, sp, epi);
+                if (cyc < best_c) {
+                    best_c = cyc;
+                    best = TileChoice{c, sp, 1};
+                }
+            }
+        }
         for (int ms = 1; ms <= 2; ++ms) {
             if (ms == 2 && (tiles_m < 2 || ms * c > 512 || !g_allow_msub)) break;
             const long base = ceil_div_l(tiles_m, ms) * ceil_div(N, c);
@@ -853,7 +994,7 @@ TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, in
             // splits (measured, tools/gemm_bench.py sweep: conv 1280 @ 8x8 20.3 -> 14.3 us; small odd counts measured worse
             // than the model predicts)
             for (int sp = 1; sp <= 32; ++sp) {
-                if (sp > 1 && (!allow_split || base * sp > 2 * kNumSMs + 64 || iters / sp < 2)) break;
+                if (sp > 1 && (!allow_split || !g_split_add_mode || base * sp > 2 * kNumSMs + 64 || iters / sp < 2)) break;
                 if (sp < 8 && (sp & (sp - 1)) != 0) continue;
                 if ((long)(sp - 1) * ceil_div(iters, sp) >= iters) continue;
                 const double cyc = model_cycles_tma(N, tiles_m, iters, c, sp, epi, ms);
@@ -990,12 +1131,36 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict_
     }
 }
 
+// gemm_tma_kernel as thread-block clusters (1, 1, cz) along the split-K dimension
+template <typename... KArgs, typename... Args>
+inline void launch_kernel_cluster_z(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, int cz, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)cz;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (g_pdl && g_prev_kernel) ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    g_prev_kernel = true;
+}
+
 int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters, cudaStream_t stream) {
     GemmDesc d = d_in;
     const long rows_total = (long)d.aW * d.aH * d.aB;
     const bool glu = d.out_glu != nullptr;
     const bool nonlinear = d.relu || d.qscale != 0.f || glu;      // ReLU / rounding emulation / gating: the epilogue needs the full K sum
-    bool can_split = d.splits >= 0 && d.out32 && !d.out16 && !nonlinear;
+    const bool cluster_mode = !g_split_add_mode;
+    // cluster split-K applies the epilogue to the reduced tile, so any output form may split; the reduce-add form can only
+    // split a plain fp32 output (fp16 outputs go through an fp32 scratch + cast)
+    bool can_split = cluster_mode ? (d.splits >= 0 && !glu) : (d.splits >= 0 && d.out32 && !d.out16 && !nonlinear);
     bool via_scratch = false;
     const int epi = (d.residual ? 1 : 0) | ((d.residual || d.out32) ? 2 : 0) | ((d.out16 || glu) ? 4 : 0);
     TileChoice tc = choose_tiles_tma(d.N, tiles_m, num_iters, can_split, epi);
@@ -1015,7 +1180,7 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
             }
         }
     }
-    if (d.splits >= 0 && !nonlinear && d.out16 && !d.out32 && (size_t)rows_total * d.N * sizeof(float) <= kWsBytes) {
+    if (!cluster_mode && d.splits >= 0 && !nonlinear && d.out16 && !d.out32 && (size_t)rows_total * d.N * sizeof(float) <= kWsBytes) {
         // fp16-only output of a K-heavy small problem: split K into an fp32 scratch tile matrix, then convert
         const int epi_s = (d.residual ? 1 : 0) | 2;
         const TileChoice ts = choose_tiles_tma(d.N, tiles_m, num_iters, true, epi_s);
@@ -1032,19 +1197,29 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     if (d.BN > 0) tc.BN = d.BN;
     if (glu && tc.BN % 64 != 0) return set_error(S2I_ERR_ARG, "gemm: the gated-GELU epilogue needs a tile width that is a multiple of 64 (got %d)", tc.BN);
     if (d.splits > 0 && can_split) tc.splits = d.splits;
+    if (!can_split) tc.splits = 1;
     if (g_force_msub > 0) tc.msub = (g_force_msub == 2 && tiles_m >= 2 && 2 * tc.BN <= 512) ? 2 : 1;
-    while (tc.splits > 1 && (long)(tc.splits - 1) * ceil_div(num_iters, tc.splits) >= num_iters) --tc.splits;
+    if (cluster_mode && tc.splits > 1) {
+        int sp = 1;                                   // cluster sizes: powers of two up to the portable maximum of 8
+        while (sp * 2 <= tc.splits && sp * 2 <= 8) sp *= 2;
+        while (sp > 1 && num_iters / sp < 1) sp /= 2;
+        tc.splits = sp;
+        if (sp > 1) tc.msub = 1;                      // the partial tile of the cluster reduction is one 128-row accumulator
+    }
+    while (tc.splits > 1 && (long)(tc.splits - 1) * ceil_div(num_iters, tc.splits) >= num_iters) tc.splits -= cluster_mode ? tc.splits / 2 : 1;
     const int BN = tc.BN;
     const int msub = tc.msub;
+    const bool csplit = cluster_mode && tc.splits > 1;
     p.msub = msub;
     p.tiles_m = (int)tiles_m;
     p.BN = BN;
     p.splits = tc.splits;
-    p.split_add = tc.splits > 1 ? 1 : 0;
+    p.split_add = (!cluster_mode && tc.splits > 1) ? 1 : 0;
+    p.csplit = csplit ? tc.splits : 0;
     p.iters_per_split = ceil_div(num_iters, tc.splits);
-    p.has_res = d.residual ? 1 : 0;
-    p.has_o32 = d.out32 ? 1 : 0;
-    p.has_o16 = d.out16 ? 1 : 0;
+    p.has_res = (d.residual && !csplit) ? 1 : 0;
+    p.has_o32 = (d.out32 && !csplit) ? 1 : 0;
+    p.has_o16 = (d.out16 && !csplit) ? 1 : 0;
     p.has_glu = glu ? 1 : 0;
     const int tiles_n = ceil_div(d.N, BN);
     p.tmem_cols = 32;
@@ -1052,8 +1227,9 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
 
     const int stage_bytes = msub * kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
     const int nch = BN / 32;
-    const size_t epi_bytes = (size_t)((p.has_res || p.has_o32) ? nch * kChunk32Bytes : 0) + (p.has_o16 ? nch * kChunk16Bytes : 0) +
-                             (glu ? (nch / 2) * kChunk16Bytes : 0);
+    const size_t epi_bytes = csplit ? (size_t)kBlockM * (BN + 4) * 4
+                                    : (size_t)((p.has_res || p.has_o32) ? nch * kChunk32Bytes : 0) + (p.has_o16 ? nch * kChunk16Bytes : 0) +
+                                          (glu ? (nch / 2) * kChunk16Bytes : 0);
     const long grid_m = ceil_div_l(tiles_m, msub);
     const long ctas = grid_m * tiles_n * tc.splits;
     const size_t tail = (size_t)(2 * 8 + 1 + kMaxChunks) * 8 + 16 + (size_t)BN * 4 + 1024 + 64;
@@ -1067,12 +1243,14 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     p.stages = stages;
     size_t pipe_bytes = (size_t)stages * stage_bytes;
     if (pipe_bytes < epi_bytes) pipe_bytes = epi_bytes;
+    p.pipe_bytes = (int)pipe_bytes;
     const size_t smem_bytes = pipe_bytes + tail;
     if (smem_bytes > 227u * 1024u) return set_error(S2I_ERR_ARG, "gemm(tma): %zu bytes of shared memory needed (BN %d)", smem_bytes, BN);
     static const bool dbg = getenv("S2I_GEMM_DEBUG") != nullptr;       // tools: print the chosen configuration
     if (dbg)
-        fprintf(stderr, "gemm_tma %s: M-tiles %ld N %d iters %d -> BN %d msub %d splits %d stages %d ctas %ld smem %zu%s\n", d.tag,
-                tiles_m, d.N, num_iters, BN, msub, tc.splits, stages, ctas, smem_bytes, via_scratch ? " (via scratch)" : "");
+        fprintf(stderr, "gemm_tma %s: M-tiles %ld N %d iters %d -> BN %d msub %d splits %d%s stages %d ctas %ld smem %zu%s\n", d.tag,
+                tiles_m, d.N, num_iters, BN, msub, tc.splits, csplit ? " (cluster)" : "", stages, ctas, smem_bytes,
+                via_scratch ? " (via scratch)" : "");
 
     p.a_c0 = d.a_c0; p.a_hoff = d.a_hoff; p.a_zmode = d.a_zmode;
     p.b_c0 = d.b_c0; p.b_hoff = d.b_hoff; p.b_zmode = d.b_zmode;
@@ -1085,9 +1263,16 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     p.qscale = d.qscale;
     p.qinv = d.qscale != 0.f ? 1.f / d.qscale : 0.f;
     S2I_TRY(build_operand_maps(p, d, BN));
-    if (d.residual) S2I_TRY(build_out_map(&p.mapRes, p, d, d.residual, d.res_ld, 2));
-    if (d.out32) S2I_TRY(build_out_map(&p.mapO32, p, d, d.out32, d.ld32, 2));
-    if (d.out16) S2I_TRY(build_out_map(&p.mapO16, p, d, d.out16, d.ld16, 0));
+    if (csplit) {
+        // the reducing CTAs address global memory directly (rows of the tile's pixel box)
+        p.residual = d.residual; p.res_ld = d.res_ld;
+        p.out32 = d.out32; p.ld32 = d.ld32;
+        p.out16 = d.out16; p.ld16 = d.ld16;
+    } else {
+        if (d.residual) S2I_TRY(build_out_map(&p.mapRes, p, d, d.residual, d.res_ld, 2));
+        if (d.out32) S2I_TRY(build_out_map(&p.mapO32, p, d, d.out32, d.ld32, 2));
+        if (d.out16) S2I_TRY(build_out_map(&p.mapO16, p, d, d.out16, d.ld16, 0));
+    }
     if (glu) {
         GemmDesc dg = d;
         dg.N = d.N / 2;
@@ -1126,7 +1311,10 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     // read per call so tools can A/B in one process
     int esets = (BN >> 5) >= 2 ? 2 : 1;
     if (const char* e = getenv("S2I_GEMM_ESETS")) esets = atoi(e) == 1 ? 1 : esets;
-    if (glu) S2I_LAUNCH((gemm_tma_kernel<2, true>), grid, kThreads + 128, smem_bytes, stream, p);
+    if (csplit) {
+        if (esets == 2) launch_kernel_cluster_z(gemm_tma_kernel<2, false>, grid, dim3(kThreads + 128), smem_bytes, tc.splits, stream, p);
+        else launch_kernel_cluster_z(gemm_tma_kernel<1, false>, grid, dim3(kThreads), smem_bytes, tc.splits, stream, p);
+    } else if (glu) S2I_LAUNCH((gemm_tma_kernel<2, true>), grid, kThreads + 128, smem_bytes, stream, p);
     else if (esets == 2) S2I_LAUNCH((gemm_tma_kernel<2, false>), grid, kThreads + 128, smem_bytes, stream, p);
     else S2I_LAUNCH((gemm_tma_kernel<1, false>), grid, kThreads, smem_bytes, stream, p);
     const double m_rows = (double)d.aW * d.aH * d.aB;
@@ -1166,6 +1354,7 @@ int gemm_zero_ranges(const ZeroRange* ranges, int n, cudaStream_t stream) {
     return 0;
 }
 void gemm_set_tma_epilogue(int on) { g_tma_epi = on ? 1 : 0; }
+bool gemm_split_add_mode() { return g_split_add_mode; }
 void gemm_set_trace(unsigned long long* buf) { g_trace = buf; }
 void gemm_force_msub(int msub) { g_force_msub = msub; }
 

@@ -37,6 +37,10 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream);
 // use gemm_tma_kernel (epilogue through TMA).  Also settable with S2I_GEMM_TMA_EPI=0 in the environment.
 void gemm_set_tma_epilogue(int on);
 
+// True when S2I_SPLITK_ADD=1 selected the reduce-add split-K form (nondeterministic sum order) instead of the default cluster
+// split-K (partial tiles reduced through distributed shared memory in rank order).
+bool gemm_split_add_mode();
+
 // Debugging: when set, gemm_tma_kernel stamps %globaltimer at its phase boundaries into buf[cta][16] (tools/gemm_trace.py).
 void gemm_set_trace(unsigned long long* buf);
 

@@ -144,15 +144,20 @@ __global__ void __launch_bounds__(256) lgp_features_nchw_kernel(const float* __r
 }
 
 // per (sample, column) sums over R rows.  MODE 0: (h, h^2).  MODE 1: (dy, dy*xhat).
+// Deterministic: every block writes the fp32 partial sums of its `chunk` rows to part [S][chunks][N][2]; the block that
+// arrives last for a sample (self-resetting counter) adds the partials in CHUNK ORDER in double and writes out [S][N][2].
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const __half* __restrict__ h, const __half* __restrict__ dy,
                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                        long R, int N, int chunk, double* __restrict__ out) {
+                                                        long R, int N, int chunk, float* __restrict__ part,
+                                                        unsigned int* __restrict__ counter, double* __restrict__ out) {
     pdl_wait();
     pdl_launch();
+    __shared__ unsigned int is_last;
     const int s = blockIdx.y;
     const long r0 = (long)blockIdx.x * chunk;
     const long r1 = min(R, r0 + chunk);
+    float* mine = part + ((long)s * gridDim.x + blockIdx.x) * N * 2;
     for (int c = threadIdx.x * 2; c < N; c += blockDim.x * 2) {
         float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
         float m0 = 0.f, m1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -172,11 +177,38 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __half* __restrict
                 b0 += dv.x * (hv.x - m0) * q0; b1 += dv.y * (hv.y - m1) * q1;
             }
         }
+        *reinterpret_cast<float4*>(mine + 2 * c) = make_float4(a0, b0, a1, b1);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int old = atomicAdd(counter + s, 1u);
+        is_last = (old == gridDim.x - 1) ? 1u : 0u;
+        if (is_last) counter[s] = 0u;        // ready for the next launch
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const float* base = part + (long)s * gridDim.x * N * 2;
+    const int nchunks = (int)gridDim.x;
+    for (int c = threadIdx.x * 2; c < N; c += blockDim.x * 2) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        int k = 0;
+        for (; k + 8 <= nchunks; k += 8) {      // eight independent loads in flight, added in chunk order
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(base + ((long)(k + u) * N + c) * 2));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                t0 += (double)v[u].x; t1 += (double)v[u].y; t2 += (double)v[u].z; t3 += (double)v[u].w;
+            }
+        }
+        for (; k < nchunks; ++k) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(base + ((long)k * N + c) * 2));
+            t0 += (double)v.x; t1 += (double)v.y; t2 += (double)v.z; t3 += (double)v.w;
+        }
         double* o = out + ((long)s * N + c) * 2;
-        atomicAdd(o + 0, (double)a0);
-        atomicAdd(o + 1, (double)b0);
-        atomicAdd(o + 2, (double)a1);
-        atomicAdd(o + 3, (double)b1);
+        o[0] = t0; o[1] = t1; o[2] = t2; o[3] = t3;
     }
 }
 
@@ -254,22 +286,28 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
     }
 }
 
-// dOut (scaled, fp16-rounded in true units) of the MSE edge loss on the cond half; loss[s] accumulated.
+// dOut (scaled, fp16-rounded in true units) of the MSE edge loss on the cond half; loss[s] = mean squared error.
+// grid (pixel blocks, B).  Deterministic: block sums by a fixed shuffle / shared-memory tree into part [S][blocks]; the block
+// arriving last for a sample (self-resetting counter) adds them in block order.
 __global__ void __launch_bounds__(256) lgp_loss_kernel(const __half* __restrict__ out16, const float* __restrict__ target,
                                                        int B, int L, int O, float inv_n, float gscale, int emulate,
-                                                       __half* __restrict__ dout, float* __restrict__ loss) {
+                                                       __half* __restrict__ dout, float* __restrict__ part,
+                                                       unsigned int* __restrict__ counter, float* __restrict__ loss) {
     pdl_wait();
     pdl_launch();
-    const long rows = (long)B * L * L;
+    __shared__ float wsum[8];
+    __shared__ unsigned int is_last;
     const long hw = (long)L * L;
-    for (long row = (long)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (long)gridDim.x * blockDim.x) {
-        const long b = row / hw, pix = row - b * hw;
+    const int b = blockIdx.y;
+    const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.f;
+    if (pix < hw) {
+        const long row = (long)b * hw + pix;
         __align__(16) __half d8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) d8[j] = __float2half_rn(0.f);
         if (b & 1) {
             const long s = b >> 1;
-            float acc = 0.f;
             for (int c = 0; c < O; ++c) {
                 const float diff = __half2float(out16[row * 8 + c]) - target[(s * O + c) * hw + pix];
                 acc += diff * diff;
@@ -277,9 +315,30 @@ __global__ void __launch_bounds__(256) lgp_loss_kernel(const __half* __restrict_
                 if (emulate) g = __half2float(__float2half_rn(g));   // the reference's unscaled fp16 rounding
                 d8[c] = __float2half_rn(g * gscale);
             }
-            atomicAdd(loss + s, acc * inv_n);
         }
         *reinterpret_cast<uint4*>(dout + row * 8) = *reinterpret_cast<uint4*>(d8);
+    }
+    if (!(b & 1)) return;          // uncond rows carry no loss (whole block: b is blockIdx.y)
+    const int s = b >> 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += wsum[i];
+        part[(long)s * gridDim.x + blockIdx.x] = t;
+        __threadfence();
+        const unsigned int old = atomicAdd(counter + s, 1u);
+        is_last = (old == gridDim.x - 1) ? 1u : 0u;
+        if (is_last) counter[s] = 0u;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        float t = 0.f;
+        for (int k = 0; k < (int)gridDim.x; ++k) t += __ldcg(part + (long)s * gridDim.x + k);
+        loss[s] = t * inv_n;
     }
 }
 
@@ -490,21 +549,23 @@ __global__ void __launch_bounds__(256) cfg_dpmpp_kernel(const float* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(256) guidance_norms_kernel(const float* __restrict__ x_old,
-                                                             const float* __restrict__ x_new,
-                                                             const float* __restrict__ dx, int n,
-                                                             double* __restrict__ scratch, int dmul, int dadd) {
+// One block per sample (n = 4 L^2 is a few thousand elements): fixed strided sums + shuffle / shared-memory tree, so the two
+// squared norms -- and through alpha every latent of the rest of the trajectory -- do not depend on timing.
+__global__ void __launch_bounds__(1024) guidance_norms_kernel(const float* __restrict__ x_old,
+                                                              const float* __restrict__ x_new,
+                                                              const float* __restrict__ dx, int n,
+                                                              double* __restrict__ scratch, int dmul, int dadd) {
     pdl_wait();
     pdl_launch();
     const int s = blockIdx.y;
-    float a = 0.f, b = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float d = x_old[(long)s * n + i] - x_new[(long)s * n + i];
         const float gq = dx[((long)s * dmul + dadd) * n + i];
-        a += d * d;
-        b += gq * gq;
+        a += (double)d * (double)d;
+        b += (double)gq * (double)gq;
     }
-    __shared__ float sa[8], sb[8];
+    __shared__ double sa[32], sb[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -516,13 +577,13 @@ __global__ void __launch_bounds__(256) guidance_norms_kernel(const float* __rest
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        float ta = 0.f, tb = 0.f;
+        double ta = 0.0, tb = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
             ta += sa[i];
             tb += sb[i];
         }
-        atomicAdd(scratch + 2 * s, (double)ta);
-        atomicAdd(scratch + 2 * s + 1, (double)tb);
+        scratch[2 * s] = ta;
+        scratch[2 * s + 1] = tb;
     }
 }
 
@@ -652,6 +713,7 @@ static size_t lgp_ws_bytes(long rows, long ldX, int S) {
     b += (size_t)rows * 8 * 2 * 2;
     b += (size_t)rows * 512 * 2 * 2;
     b += (size_t)S * 512 * 2 * 8 * 8 + (size_t)S * 512 * 4 * 8;
+    b += ((size_t)rows / 128 + (size_t)S + 8) * 512 * 2 * 4 + (size_t)S * 64 + (size_t)rows / 64 * 4 + 4096;   // reduction partials, counters
     return b + (1u << 20);
 }
 
@@ -667,8 +729,13 @@ int LGP::mlp(cudaStream_t st) {
     dout_ = ws.take<__half>((size_t)rows * 8);
     dA_ = ws.take<__half>((size_t)rows * 512);
     dB_ = ws.take<__half>((size_t)rows * 512);
-    double* sums = ws.take<double>((size_t)S * 960 * 2 * 2);
-    S2I_MEMOP(cudaMemsetAsync(sums, 0, (size_t)S * 960 * 2 * 2 * sizeof(double), st));
+    // per-(sample, column) sums, followed by the arrival counters of the deterministic reductions (zeroed together)
+    double* sums = ws.take<double>((size_t)S * 960 * 2 * 2 + (size_t)S + 1);
+    red_counter_ = reinterpret_cast<unsigned int*>(sums + (size_t)S * 960 * 2 * 2);
+    S2I_MEMOP(cudaMemsetAsync(sums, 0, ((size_t)S * 960 * 2 * 2 + (size_t)S + 1) * sizeof(double), st));
+    const long nchunks = ceil_div_l(R, 128);
+    red_part_ = ws.take<float>((size_t)S * nchunks * 512 * 2);
+    loss_part_ = ws.take<float>((size_t)(B_ / 2 + 1) * (size_t)ceil_div_l((long)L_ * L_, 256));
     size_t so = 0;
     for (int l = 0; l < 4; ++l) {
         bsum_[l] = sums + so;
@@ -703,7 +770,7 @@ int LGP::mlp(cudaStream_t st) {
         if (l < 4) {
             if (train_) {
                 dim3 grid((unsigned)ceil_div_l(R, 128), S);
-                S2I_LAUNCH((bn_reduce_kernel<0>), grid, min(256, N / 2), 0, st, h_[l], nullptr, nullptr, nullptr, R, N, 128, bsum_[l]);
+                S2I_LAUNCH((bn_reduce_kernel<0>), grid, min(256, N / 2), 0, st, h_[l], nullptr, nullptr, nullptr, R, N, 128, red_part_, red_counter_, bsum_[l]);
                 S2I_LAUNCH_CHECK();
             }
             S2I_LAUNCH((bn_finalize_kernel), ceil_div(S * N, 256), 256, 0, st, bsum_[l], bn_rm_[l], bn_rv_[l], train_ ? 1 : 0, R, N, S,
@@ -781,9 +848,8 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
     const long R = 2L * L_ * L_;
     const long n_elem = (long)O_ * L_ * L_;
     gscale_ = exp2f(ceilf(log2f((float)n_elem)));
-    S2I_MEMOP(cudaMemsetAsync(loss, 0, S * sizeof(float), st));
-    S2I_LAUNCH((lgp_loss_kernel), grid1d(rows), 256, 0, st, out16_, target, B_, L_, O_, 1.f / (float)n_elem, gscale_,
-                                                  emulate_fp16_grad ? 1 : 0, dout_, loss);
+    S2I_LAUNCH((lgp_loss_kernel), dim3((unsigned)ceil_div_l((long)L_ * L_, 256), (unsigned)B_), 256, 0, st, out16_, target, B_, L_, O_,
+               1.f / (float)n_elem, gscale_, emulate_fp16_grad ? 1 : 0, dout_, loss_part_, red_counter_ + S, loss);
     const float qs = emulate_fp16_grad ? gscale_ : 0.f;
     S2I_LAUNCH_CHECK();
 
@@ -823,7 +889,7 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
         const int bl = l - 1;
         if (train_) {
             dim3 grid((unsigned)ceil_div_l(R, 128), S);
-            S2I_LAUNCH((bn_reduce_kernel<1>), grid, min(256, N / 2), 0, st, h_[bl], o, mean_[bl], rstd_[bl], R, N, 128, bbsum_[bl]);
+            S2I_LAUNCH((bn_reduce_kernel<1>), grid, min(256, N / 2), 0, st, h_[bl], o, mean_[bl], rstd_[bl], R, N, 128, red_part_, red_counter_, bbsum_[bl]);
             S2I_LAUNCH_CHECK();
         }
         __half* o2 = bufs[flip ^ 1];
@@ -902,9 +968,8 @@ int cfg_dpmpp_step(const float* latents, const float* eps, float* x0_hist, int S
 int guidance_update(const float* x_old, float* x_new, const float* dx, int S, int n, float beta, double* scratch,
                     cudaStream_t st, bool dx_cond_only) {
     const int dmul = dx_cond_only ? 1 : 2, dadd = dx_cond_only ? 0 : 1;
-    S2I_MEMOP(cudaMemsetAsync(scratch, 0, (size_t)S * 2 * sizeof(double), st));
     dim3 grid(grid1d(n, 256, 64), S);
-    S2I_LAUNCH((guidance_norms_kernel), grid, 256, 0, st, x_old, x_new, dx, n, scratch, dmul, dadd);
+    S2I_LAUNCH((guidance_norms_kernel), dim3(1, S), 1024, 0, st, x_old, x_new, dx, n, scratch, dmul, dadd);
     S2I_LAUNCH_CHECK();
     S2I_LAUNCH((guidance_apply_kernel), grid, 256, 0, st, x_new, dx, n, beta, scratch, dmul, dadd);
     S2I_LAUNCH_CHECK();

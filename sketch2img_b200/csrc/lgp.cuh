@@ -80,6 +80,9 @@ class LGP {
     double* bbsum_[4] = {};      // backward per (sample, column) sums
     float* mean_[4] = {};
     float* rstd_[4] = {};
+    float* red_part_ = nullptr;          // per-chunk partial sums of the BatchNorm reductions (summed in chunk order)
+    float* loss_part_ = nullptr;         // per-block partial sums of the edge loss
+    unsigned int* red_counter_ = nullptr;    // arrival counters: [S] BatchNorm reductions, then [S] loss
     bool have_fwd_ = false;
     int groups_ = 1;             // BatchNorm statistic groups (pairs on the sampling path, 1 for forward())
     float gscale_ = 1.f;

@@ -65,11 +65,14 @@ class Sampler {
         // The text context is constant over the steps of an image: after the first step that saw it (context_changed()
         // or a new ctx pointer / sample count marks a new one) the cross-attention K/V projections are reused.
         if (ctx != last_ctx_ || S != last_S_) ctx_fresh_ = true;
+        // any forward the sampler did not issue itself (pipe.unet(...) from a callback, apply_anti_gradient) rewrote the cache
+        if (unet->kv_generation() != kv_gen_seen_) ctx_fresh_ = true;
         last_ctx_ = ctx;
         last_S_ = S;
         const int reuse = ctx_fresh_ ? 0 : 1;
         ctx_fresh_ = false;
-        Key key{S, L, a.prediction, do_guide ? 1 : 0, a.lgp_train, reuse, a.solver, a.solver ? a.order : 0, a.guidance, a.beta};
+        Key key{S, L, a.prediction, do_guide ? 1 : 0, a.lgp_train, reuse, a.solver, a.solver ? a.order : 0, unet->sat_signature(),
+                a.guidance, a.beta};
         // The replayed part works on sampler-owned copies of the caller's tensors, so one graph serves every image.
         S2I_TRY(layout(key));
         const size_t nb = (size_t)S * unet->cfg.in_ch * L * L * sizeof(float);
@@ -87,6 +90,7 @@ class Sampler {
             S2I_MEMOP(cudaMemcpyAsync(own_target_, target, nb, cudaMemcpyDeviceToDevice, st));
         }
         S2I_TRY(run(key, st));
+        kv_gen_seen_ = unet->kv_generation();
         S2I_MEMOP(cudaMemcpyAsync(latents, own_lat_, nb, cudaMemcpyDeviceToDevice, st));
         if (a.solver == 1) S2I_MEMOP(cudaMemcpyAsync(x0_hist, own_x0_, nb, cudaMemcpyDeviceToDevice, st));
         if (do_guide && loss_out) S2I_MEMOP(cudaMemcpyAsync(loss_out, own_loss_, S * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -96,10 +100,12 @@ class Sampler {
   private:
     struct Key {
         int S, L, prediction, guided, train, reuse_kv, solver, order;
+        unsigned sat;            // which transformer blocks run the injected sketch attention (UNet::sat_signature)
         float guidance, beta;
         bool operator==(const Key& o) const {
             return S == o.S && L == o.L && prediction == o.prediction && guided == o.guided && train == o.train &&
-                   reuse_kv == o.reuse_kv && solver == o.solver && order == o.order && guidance == o.guidance && beta == o.beta;
+                   reuse_kv == o.reuse_kv && solver == o.solver && order == o.order && sat == o.sat && guidance == o.guidance &&
+                   beta == o.beta;
         }
     };
     struct Entry {
@@ -184,6 +190,7 @@ class Sampler {
     }
 
     bool ctx_fresh_ = true;
+    long kv_gen_seen_ = -1;
     const void* last_ctx_ = nullptr;
     int last_S_ = 0;
     static constexpr int kRing = 256;

@@ -448,32 +448,44 @@ int UNet::load_sat(const std::map<std::string, HostParam>& params) {
         if (L.staging) cudaFree(L.staging);
         return set_error(S2I_ERR_ARG, "sketch attention load (%s): %s", what.c_str(), L.err.c_str());
     };
+    // Re-uploads (SatMixin.sync after load_state_dict / an optimizer step) reuse the device buffers of the first upload: no
+    // leak, and step graphs captured earlier keep reading valid addresses -- they simply see the new weights.
+    auto vec_into = [&](const std::string& nm, size_t n, float*& dst) -> bool {
+        const HostParam* hp = L.find(nm, n);
+        if (!hp) return false;
+        if (!dst) dst = L.dmalloc<float>(n);
+        if (!dst) return false;
+        return cudaMemcpy(dst, hp->data, n * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    };
     for (auto& T : tfm_) {
         std::string name = "sketch_attn_" + T.path + ".transformer_blocks.0";
         for (char& ch : name)
             if (ch == '.') ch = '_';
         const int C = T.C;
         SatBlock& S = T.sat;
-        if (!L.norm(name + ".sketch_norm", C, 1e-5f, S.ln)) return fail(name);
+        S.ln.C = C;
+        S.ln.eps = 1e-5f;
+        if (!vec_into(name + ".sketch_norm.weight", C, S.ln.g) || !vec_into(name + ".sketch_norm.bias", C, S.ln.b)) return fail(name);
         S.q.N = T.HP; S.q.K = C;
-        S.q.w = L.dmalloc<__half>((size_t)T.HP * C, true);
+        if (!S.q.w) S.q.w = L.dmalloc<__half>((size_t)T.HP * C, true);
         S.kv.N = 2 * T.HP; S.kv.K = C;
-        S.kv.w = L.dmalloc<__half>((size_t)2 * T.HP * C, true);
+        if (!S.kv.w) S.kv.w = L.dmalloc<__half>((size_t)2 * T.HP * C, true);
         S.o.N = C; S.o.K = T.HP;
-        S.o.w = L.dmalloc<__half>((size_t)C * T.HP, true);
+        if (!S.o.w) S.o.w = L.dmalloc<__half>((size_t)C * T.HP, true);
         if (!S.q.w || !S.kv.w || !S.o.w) return fail(name);
         if (!L.linear_into(name + ".sketch_attn.to_q.weight", C, C, T.d, T.dp, true, false, S.q.w, C, 0, nullptr, 0, 0, false) ||
             !L.linear_into(name + ".sketch_attn.to_k.weight", C, C, T.d, T.dp, true, false, S.kv.w, C, 0, nullptr, 0, 0, false) ||
             !L.linear_into(name + ".sketch_attn.to_v.weight", C, C, T.d, T.dp, true, false, S.kv.w, C, T.HP, nullptr, 0, 0, false) ||
             !L.linear_into(name + ".sketch_attn.to_out.0.weight", C, C, T.d, T.dp, false, true, S.o.w, T.HP, 0, nullptr, 0, 0, false))
             return fail(name);
-        S.o.b = L.vec(name + ".sketch_attn.to_out.0.bias", C);
-        S.conv_w32 = L.vec(name + ".sketch_conv.weight", (size_t)C * C);     // [C][C][1]
-        S.conv_b32 = L.vec(name + ".sketch_conv.bias", C);
+        if (!vec_into(name + ".sketch_attn.to_out.0.bias", C, S.o.b) ||
+            !vec_into(name + ".sketch_conv.weight", (size_t)C * C, S.conv_w32) ||     // [C][C][1]
+            !vec_into(name + ".sketch_conv.bias", C, S.conv_b32))
+            return fail(name);
         S.conv.N = C; S.conv.K = C;
-        S.conv.w = L.dmalloc<__half>((size_t)C * C);
-        S.conv.b = L.dmalloc<float>(C);
-        if (!S.o.b || !S.conv_w32 || !S.conv_b32 || !S.conv.w || !S.conv.b) return fail(name);
+        if (!S.conv.w) S.conv.w = L.dmalloc<__half>((size_t)C * C);
+        if (!S.conv.b) S.conv.b = L.dmalloc<float>(C);
+        if (!S.conv.w || !S.conv.b) return fail(name);
         S.loaded = true;
     }
     if (L.staging) cudaFree(L.staging);
@@ -540,10 +552,24 @@ int UNet::set_sat_feature(const char* block_path, const float* nchw, int B, int 
 }
 
 // ================================================================================================== helpers
+#define ARENA_CHECK()                                                                                                   \
+    do {                                                                                                                \
+        if (arena_.overflow)                                                                                            \
+            return set_error(S2I_ERR_STATE, "unet: activation arena overflow (%zu of %zu bytes): the forward's topology " \
+                             "differs from the one the arena was sized for", arena_.off, arena_.cap);                   \
+    } while (0)
 #define RUN(call)                  \
     do {                           \
+        ARENA_CHECK();             \
         if (!dry_) S2I_TRY(call);  \
     } while (0)
+
+unsigned UNet::sat_signature() const {
+    unsigned m = 0;
+    for (size_t i = 0; i < tfm_.size() && i < 32; ++i)
+        if (tfm_[i].sat.loaded && tfm_[i].sat.fN > 0) m |= 1u << i;
+    return m;
+}
 
 F32 UNet::new32(int B, int H, int W, int C) {
     F32 t;
@@ -588,9 +614,10 @@ int UNet::gemm(const H16& a, bool spatial, int taps, const __half* w, long w_ld,
     // An fp16-only output with a long contraction may be computed split-K through an fp32 scratch: give it its own arena
     // buffer (same allocation in the sizing pass) so its zero-fill joins the step's zero plan instead of a per-call launch.
     float* scratch = nullptr;
-    if (out16 && !out32 && (long)Kc * taps >= 1024 && a.rows() * (long)N * 4 <= (32L << 20))
+    if (gemm_split_add_mode() && out16 && !out32 && (long)Kc * taps >= 1024 && a.rows() * (long)N * 4 <= (32L << 20))
         scratch = dalloc<float>((size_t)a.rows() * N);
     if (dry_) return 0;
+    ARENA_CHECK();
     GemmDesc d;
     d.A = a.p;
     d.aC = Kc;
@@ -780,6 +807,7 @@ int UNet::attention(const Transformer& T, const H16& q, long q_c0, const H16& kv
         o = new16(q.B, q.H, q.W, T.HP);
         if (fused_bwd) *lse = dalloc<float>((size_t)Z * Nq);
         if (dry_) return 0;
+        ARENA_CHECK();
         AttnDesc a;
         a.q = q.p; a.ldq = q.ld; a.q_c0 = (int)q_c0;
         a.kv = kv.p; a.ldkv = kv.ld; a.k_c0 = (int)k_c0; a.v_c0 = (int)v_c0;
@@ -796,6 +824,7 @@ int UNet::attention(const Transformer& T, const H16& q, long q_c0, const H16& kv
     P.p = dalloc<__half>((size_t)Z * Nq * ldP);
     o = new16(q.B, q.H, q.W, T.HP);
     if (dry_) return 0;
+    ARENA_CHECK();
     GemmDesc d;
     d.tag = "gemm_attn";
     d.A = q.p; d.aC = (int)q.ld; d.aW = Nq; d.aB = B; d.a_sw = q.ld; d.a_sb = (long)Nq * q.ld;
@@ -826,6 +855,7 @@ int UNet::attention_bwd(const Transformer& T, const H16& dO, const H16& q, long 
         // fused: dQ (and dK, dV) with S / P / dP / dS recomputed on chip
         float* delta = dalloc<float>((size_t)Z * Nq);
         if (dry_) return 0;
+        ARENA_CHECK();
         AttnBwdDesc a;
         a.q = q.p; a.ldq = q.ld; a.q_c0 = (int)q_c0;
         a.kv = kv.p; a.ldkv = kv.ld; a.k_c0 = (int)k_c0; a.v_c0 = (int)v_c0;
@@ -844,6 +874,7 @@ int UNet::attention_bwd(const Transformer& T, const H16& dO, const H16& q, long 
     float* dP = dalloc<float>((size_t)Z * Nq * ldS);
     __half* dS = dalloc<__half>((size_t)Z * Nq * ldP);
     if (dry_) return 0;
+    ARENA_CHECK();
     const float scale = 1.f / sqrtf((float)T.d);
     {   // dP = dO V^T
         GemmDesc d;
@@ -980,6 +1011,7 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     if (fuse_glu_) {
         if (save_) sv.ff = new16(B, H, W, 8 * C);
         if (!dry_) {
+            ARENA_CHECK();
             GemmDesc d;
             d.tag = "gemm_linear";
             d.A = l16c.p; d.aC = C; d.aW = (int)rows; d.aH = 1; d.aB = 1; d.a_sw = l16c.ld;
@@ -1352,6 +1384,7 @@ int UNet::forward(const float* x_nchw, int B, int H, int W, float t, const float
     time_ready_ = time_ready;
     reuse_kv_ = reuse_ctx_kv && kv_cache_B_ == B;      // a cache filled for another batch size is not reusable
     kv_cache_B_ = B;
+    if (!reuse_kv_) ++kv_gen_;                         // this forward rewrites the cached context K/V projections
     if (H % 8 || W % 8) return set_error(S2I_ERR_ARG, "unet: latent H, W must be multiples of 8 (got %d x %d)", H, W);
     st_ = st;
     B_ = B; H_ = H; W_ = W;
@@ -1359,7 +1392,8 @@ int UNet::forward(const float* x_nchw, int B, int H, int W, float t, const float
     save_ = save_for_backward;
     have_saved_ = false;
     const long key = ((long)B << 40) ^ ((long)H << 24) ^ ((long)W << 8) ^ (save_ ? 1 : 0);
-    if (key != arena_key_) {
+    const unsigned sat_sig = sat_signature();
+    if (key != arena_key_ || sat_sig != arena_sat_) {
         // measure the footprint of this configuration with a dry run, then (re)allocate
         Arena real = arena_;
         arena_ = Arena();
@@ -1386,8 +1420,11 @@ int UNet::forward(const float* x_nchw, int B, int H, int W, float t, const float
             arena_.cap = need;
         }
         arena_key_ = key;
+        arena_sat_ = sat_sig;
     }
     int rc = run_forward(x_nchw, t, eps_nchw);
+    if (rc == 0 && arena_.overflow)
+        rc = set_error(S2I_ERR_STATE, "unet: activation arena overflow (%zu of %zu bytes)", arena_.peak, arena_.cap);
     if (rc == 0 && save_) have_saved_ = true;
     return rc;
 }
@@ -1401,7 +1438,10 @@ int UNet::backward(float* const tap_grads[9], float* dx_nchw, cudaStream_t st, i
     have_saved_ = false;
     bb0_ = b0;
     bnb_ = nb;
-    return run_backward(tap_grads, dx_nchw);
+    int rc = run_backward(tap_grads, dx_nchw);
+    if (rc == 0 && arena_.overflow)
+        rc = set_error(S2I_ERR_STATE, "unet: activation arena overflow in the backward (%zu of %zu bytes)", arena_.peak, arena_.cap);
+    return rc;
 }
 
 }  // namespace s2i

@@ -125,14 +125,19 @@ class Arena {
   public:
     char* base = nullptr;
     size_t cap = 0, off = 0, peak = 0;
+    bool overflow = false;      // a real allocation ran past `cap` (the sizing pass saw another topology): callers must not launch
     void* alloc(size_t bytes) {
         off = (off + 255) & ~size_t(255);
         void* p = base ? base + off : reinterpret_cast<void*>(off + 256);   // fake pointers while measuring
         off += bytes;
         if (off > peak) peak = off;
+        if (base && off > cap) {
+            overflow = true;
+            p = base;           // never hand out an address past the end
+        }
         return p;
     }
-    void reset() { off = 0; }
+    void reset() { off = 0; overflow = false; }
 };
 
 class UNet {
@@ -179,6 +184,12 @@ class UNet {
     bool fuse_glu_ = false;
 
     size_t arena_bytes() const { return arena_.cap; }
+    // Which transformer blocks currently have a sketch feature (bit i = block i in load order): part of the activation
+    // arena's sizing key and of the sampler's graph key -- a block with a feature runs six more tensors and four more launches.
+    unsigned sat_signature() const;
+    // Bumped by every forward that (re)computes the cached context K/V projections: the sampler compares it with the value it
+    // saw after its own last forward before it reuses the cache (any other forward in between overwrote it).
+    long kv_generation() const { return kv_gen_; }
 
   private:
     // parameters
@@ -213,6 +224,8 @@ class UNet {
     std::vector<UpCat> up_cat_;
     H16 ctx16_;
     long arena_key_ = -1;
+    unsigned arena_sat_ = 0;
+    long kv_gen_ = 0;
     bool have_saved_ = false;
     bool time_ready_ = false;
     bool reuse_kv_ = false;

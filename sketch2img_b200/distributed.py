@@ -29,35 +29,46 @@ def shard_samples(n, rank, world):
     return list(range(rank, n, world))
 
 
-def broadcast_state_dict(state_dict, src=0, device=None, bucket_bytes=256 << 20):
-    """One-time weight broadcast: rank `src`'s tensors overwrite everyone's, in flat fp32 buckets sized for launch
-    latency (NVSwitch gives every peer full bandwidth; the bucket count, not link count, is what matters)."""
+def broadcast_state_dict(state_dict, src=0, device=None, bucket_bytes=1 << 30, half_matrices=False):
+    """One-time weight broadcast: rank `src`'s tensors overwrite everyone's, in flat buckets sized for launch latency
+    (NVSwitch gives every peer full bandwidth; the bucket count, not link count, is what matters).
+
+    half_matrices: tensors with two or more dimensions (conv / linear weights) travel as fp16 -- the engine only ever uses
+    them as fp16 tensor-core operands (packed with round-to-nearest at load), so every rank still packs bit-identical
+    operands from half the bytes (SD1.5: 1.7 GB instead of 3.4 GB); vectors (biases, norm affine) stay fp32."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return state_dict
     keys = sorted(k for k, v in state_dict.items() if torch.is_tensor(v) and v.dtype.is_floating_point)
     dev = torch.device(device) if device is not None else (
         torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
-    bucket, size = [], 0
 
-    def flush():
-        nonlocal bucket, size
-        if not bucket:
-            return
-        flat = torch.cat([state_dict[k].detach().reshape(-1).to(dev, torch.float32) for k in bucket])
-        dist.broadcast(flat, src=src)
-        off = 0
-        for k in bucket:
-            n = state_dict[k].numel()
-            state_dict[k] = flat[off:off + n].reshape(state_dict[k].shape).to(state_dict[k].device, state_dict[k].dtype)
-            off += n
+    def wire(k):
+        return torch.float16 if half_matrices and state_dict[k].dim() >= 2 else torch.float32
+
+    for wdt in (torch.float16, torch.float32):
         bucket, size = [], 0
 
-    for k in keys:
-        bucket.append(k)
-        size += state_dict[k].numel() * 4
-        if size >= bucket_bytes:
-            flush()
-    flush()
+        def flush():
+            nonlocal bucket, size
+            if not bucket:
+                return
+            flat = torch.cat([state_dict[k].detach().reshape(-1).to(dev, wdt) for k in bucket])
+            dist.broadcast(flat, src=src)
+            off = 0
+            for k in bucket:
+                n = state_dict[k].numel()
+                state_dict[k] = flat[off:off + n].reshape(state_dict[k].shape).to(state_dict[k].device, state_dict[k].dtype)
+                off += n
+            bucket, size = [], 0
+
+        for k in keys:
+            if wire(k) != wdt:
+                continue
+            bucket.append(k)
+            size += state_dict[k].numel() * (2 if wdt == torch.float16 else 4)
+            if size >= bucket_bytes:
+                flush()
+        flush()
     return state_dict
 
 

@@ -172,6 +172,11 @@ class AntiGradientPipeline:
             target = sketch_image.to(device, torch.float32)
             if target.shape[0] == 1 and S > 1:
                 target = target.expand(S, -1, -1, -1)
+            if tuple(target.shape) != (S, self.unet.in_channels, L, L):
+                # the reference fails here too (F.mse_loss broadcasting error, pipeline.py:157): a sketch latent encoded at
+                # another resolution, or a batch that is neither 1 nor the number of samples
+                raise ValueError(f"sketch_image must be [{S} or 1, {self.unet.in_channels}, {L}, {L}] (the VAE latent of the sketch at "
+                                 f"the sampling resolution), got {tuple(sketch_image.shape)}")
             target = target.contiguous()
         sampler = self._get_sampler()
         _lib.check(lib.s2i_sampler_context_changed(sampler))       # new prompt embeddings: re-project the context K/V
@@ -233,6 +238,11 @@ class AntiGradientPipeline:
         lgp = self.lgp_model.engine()
         taps = eng.taps()
         B, _, L, _ = latents_prev.shape
+        if B != 2:
+            # the reference only runs for one CFG pair: `latents_prev - latents` is [2B, ...] - [B, ...] (pipeline.py:160;
+            # SURVEY Q1).  Batches go through __call__, which treats every sample as its own batch-1 reference call.
+            raise RuntimeError(f"apply_anti_gradient handles one (uncond, cond) pair, got a batch of {B} (reference: "
+                               f"pipeline.py:160 does not broadcast for more than one sample)")
         lgp.forward_taps(taps, B, L, noise.float().contiguous(), self.scheduler.sigma(int(timestep)), self.lgp_model.training)
         _, grads, _ = lgp.loss_backward(target.float().contiguous(), taps)
         dx = eng.backward(grads)

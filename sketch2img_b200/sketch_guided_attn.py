@@ -18,16 +18,6 @@ import torch.nn as nn
 from . import _lib
 
 
-def transformer_block_paths(unet):
-    """Module paths of the UNet's BasicTransformerBlocks in diffusers' ``named_modules`` order: down_blocks, up_blocks,
-    mid_block (the registration order the reference's ``down + up[::-1] + mid`` assignment relies on)."""
-    layers = int(getattr(unet.config, "layers_per_block", 2))
-    paths = [f"down_blocks.{i}.attentions.{j}" for i in range(3) for j in range(layers)]
-    paths += [f"up_blocks.{i}.attentions.{j}" for i in range(1, 4) for j in range(layers + 1)]
-    paths.append("mid_block.attentions.0")
-    return paths
-
-
 class _SketchCrossAttention(nn.Module):
     """Parameter container with diffusers' CrossAttention names (to_q / to_k / to_v without bias, to_out.0 with)."""
 
@@ -42,12 +32,19 @@ class _SketchCrossAttention(nn.Module):
 
 
 class AttnModule(nn.Module):
-    def __init__(self, sat_name, unet, block_path, dim, heads):
+    def __init__(self, sat_name, base_layer):
+        """sketch_guided_attn.py:48-79.  ``base_layer``: the transformer block the module is injected into -- here the engine's
+        ``BasicTransformerBlock`` handle from ``unet.named_modules()``; width, heads and head width come from its ``attn1``
+        exactly like :51-60."""
         super().__init__()
         self.name = sat_name
-        self._unet, self._path = unet, block_path
+        attn1 = base_layer.attn1
+        dim = attn1.to_q.in_features
+        heads = attn1.heads
+        dim_head = attn1.to_q.out_features // heads
+        self._unet, self._path = base_layer._unet, base_layer._path
         self.sketch_norm = nn.LayerNorm(dim)
-        self.sketch_attn = _SketchCrossAttention(dim, heads, dim // heads)
+        self.sketch_attn = _SketchCrossAttention(dim, heads, dim_head)
         self.sketch_conv = nn.Conv1d(dim, dim, 1)
         self.sketch_scale = 1.0
         self.res_sample = None
@@ -72,23 +69,16 @@ class SatMixin(nn.Module):
         super().__init__()
         self._unet = unet
         self.blocks = []
-        boc = list(unet.config.block_out_channels)
-        heads = unet.config.attention_head_dim
-        heads = list(heads) if isinstance(heads, (tuple, list)) else [int(heads)] * len(boc)
+        prefix = "sketch_attn"
+        for name, module in unet.named_modules():                        # sketch_guided_attn.py:15-21
+            if module.__class__.__name__ == "BasicTransformerBlock":
+                module_name = (prefix + "." + name).replace(".", "_")
+                self.blocks.append(AttnModule(module_name, module))
         names = set()
-        for path in transformer_block_paths(unet):
-            if path.startswith("down_blocks"):
-                lvl = int(path.split(".")[1])
-            elif path.startswith("up_blocks"):
-                lvl = 3 - int(path.split(".")[1])
-            else:
-                lvl = 3
-            name = ("sketch_attn." + path + ".transformer_blocks.0").replace(".", "_")
-            assert name not in names, f"duplicated module name: {name}"
-            names.add(name)
-            blk = AttnModule(name, unet, path, boc[lvl], heads[lvl])
-            self.blocks.append(blk)
-            self.add_module(name, blk)
+        for block in self.blocks:                                        # :23-27
+            assert block.name not in names, f"duplicated module name: {block.name}"
+            names.add(block.name)
+            self.add_module(block.name, block)
         self._pushed = None
         self._scale = None
 

@@ -27,6 +27,14 @@ def _worker(rank, world, port, ret):
     torch.manual_seed(100)
     want = {"a.weight": torch.randn(7, 5), "b.bias": torch.randn(3).half()}
     ok = torch.equal(sd["a.weight"], want["a.weight"]) and torch.equal(sd["b.bias"], want["b.bias"]) and sd["b.bias"].dtype == torch.float16
+    # matrices as fp16 on the wire (the engine packs them to fp16 operands anyway), vectors exact
+    torch.manual_seed(200 + rank)
+    sd2 = {"w": torch.randn(6, 4), "conv.weight": torch.randn(2, 3, 3, 3), "w.bias": torch.randn(6)}
+    D.broadcast_state_dict(sd2, src=0, half_matrices=True)
+    torch.manual_seed(200)
+    w2 = {"w": torch.randn(6, 4), "conv.weight": torch.randn(2, 3, 3, 3), "w.bias": torch.randn(6)}
+    ok = ok and torch.equal(sd2["w"].half(), w2["w"].half()) and torch.equal(sd2["conv.weight"].half(), w2["conv.weight"].half())
+    ok = ok and torch.equal(sd2["w.bias"], w2["w.bias"]) and sd2["w"].dtype == torch.float32
     n = 5
     mine = D.shard_samples(n, rank, world)
     local = torch.stack([torch.full((4, 2, 2), float(k)) for k in mine])

@@ -106,17 +106,34 @@ def test_satmixin_state_dict_contract():
     (sketch_guided_attn.py:14-27, :62-72), so its checkpoints load into the drop-in unchanged."""
     from types import SimpleNamespace
     from oracle import port
-    from sketch2img_b200.sketch_guided_attn import SatMixin, transformer_block_paths
+    from sketch2img_b200.sketch_guided_attn import AttnModule, SatMixin
+    from sketch2img_b200.unet import transformer_block_handles, transformer_block_paths
     o_unet = port.make_unet("tiny21")
     o_sat = port.make_sat(o_unet)
+    cfg = {k: v for k, v in vars(o_unet.config).items() if not k.startswith("_")}
     fake = SimpleNamespace(config=o_unet.config, engine=None)
+    fake.named_modules = lambda: iter([("", fake)] + transformer_block_handles(fake, cfg))
     sat = SatMixin(fake)
     assert len(sat.blocks) == 16 and [b.name for b in sat.blocks] == [b.name for b in o_sat.blocks]
     want = {k: tuple(v.shape) for k, v in o_sat.state_dict().items()}
     got = {k: tuple(v.shape) for k, v in sat.state_dict().items()}
     assert got == want
     sat.load_state_dict(o_sat.state_dict())
-    assert transformer_block_paths(fake)[6] == "up_blocks.1.attentions.0" and transformer_block_paths(fake)[-1] == "mid_block.attentions.0"
+    assert transformer_block_paths(cfg)[6] == "up_blocks.1.attentions.0" and transformer_block_paths(cfg)[-1] == "mid_block.attentions.0"
+    # the reference's constructor signature: AttnModule(sat_name, base_layer) (sketch_guided_attn.py:48), width / heads read
+    # off base_layer.attn1 like :51-60
+    name, blk = transformer_block_handles(fake, cfg)[7]
+    m = AttnModule("x", blk)
+    assert m.sketch_norm.normalized_shape == (blk.attn1.to_q.in_features,) and m.sketch_attn.heads == blk.attn1.heads
+    if os.path.isdir("/root/reference/modules"):
+        # the reference's OWN SatMixin accepts the drop-in UNet's module tree and builds the same parameter set
+        import sys
+        port.add_shim_to_path()
+        if "/root/reference" not in sys.path:
+            sys.path.insert(0, "/root/reference")
+        from modules.sketch_guided_attn import SatMixin as RefSatMixin
+        ref = RefSatMixin(fake)
+        assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == want
 
 
 def test_dpmpp_host_scalars_reproduce_the_oracle_scheduler():

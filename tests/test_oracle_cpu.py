@@ -129,3 +129,66 @@ def test_reference_satmixin_over_shim_equals_port():
     eps, _, sat_port = _port_sat_run(1)
     assert torch.equal(eps, eps_ref)
     assert list(sat.state_dict().keys()) == list(sat_port.state_dict().keys())
+
+
+# ------------------------------------------------------------------------------------------------ teacher-forced fixtures
+def test_port_guided_step_reproduces_teacher_fixture():
+    """tests/golden/tiny_50step_teacher.pt holds every guided step of the reference run (latent before / after guidance,
+    loss, gradient norm).  oracle/port.py's guided_step restarted from the fixture's x_{i-1} must give the fixture's x_i bit
+    for bit: the fixture is the reference files' own trajectory, and the port's single step is the reference's step."""
+    from oracle import port
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    fix = torch.load(os.path.join(GOLD, "tiny_50step_teacher.pt"))
+    assert fix["guided_steps"] == 26 and fix["source"].startswith("reference modules/pipeline.py")
+    unet = port.make_unet("tiny")
+    lgp = port.make_lgp(unet)
+    lat, emb, tgt = port.make_inputs(unet)
+    sch = port.make_scheduler()
+    sch.set_timesteps(fix["steps"])
+    taps, _ = port.register_taps(unet)
+    noise = lat * sch.init_noise_sigma
+    for i in (0, 1, 13, 25):
+        x_prev = noise if i == 0 else fix["x"][i - 1]
+        rec = {}
+        x = port.guided_step(unet, lgp, sch, emb, x_prev, noise, sch.timesteps[i], tgt, True, taps, 7.5, 1.6, rec)
+        assert int(sch.timesteps[i]) == fix["t"][i]
+        assert torch.equal(x, fix["x"][i]) and torch.equal(rec["x_ddim"], fix["x_ddim"][i]), f"step {i}"
+        assert abs(rec["loss"] - float(fix["loss"][i])) <= 1e-6 * float(fix["loss"][i])
+    # the yardsticks the GPU tests lean on are what the docstring of make_golden.run_reference_teacher says they are
+    assert (fix["fp16w"]["e16"] > 1e-3).all() and (fix["fp16w"]["d16"] < 1e-4).all()
+    assert (fix["pert"]["e_pert"] > 5e-4).all()        # a 1e-6 restart moves the next latent by ~1e-3: chaotic (DESIGN.md)
+
+
+def test_teacher_fixture_sd15_metadata():
+    fix = torch.load(os.path.join(GOLD, "sd15_50step_teacher.pt"))
+    assert fix["config"] == "sd15" and fix["steps"] == 50 and fix["guided_steps"] == 26
+    assert fix["t"][0] == 981 and fix["t"][25] == 481
+    assert all(tuple(fix["x"][i].shape) == (1, 4, 64, 64) for i in range(26))
+    assert torch.isfinite(fix["loss"]).all() and torch.isfinite(fix["gnorm"]).all()
+
+
+def test_fp16_operand_floor_of_one_forward():
+    """Why a 4-step unguided run cannot reach 1e-3 (it is asserted at 2e-3; the 50-step run is asserted at 1e-3): the ORACLE
+    itself, evaluated with its weights and every Conv2d / Linear input rounded to fp16 -- exact fp32 accumulation, exact
+    norms / softmax -- is already ~1.2e-3 away from its fp32 self in ONE forward.  That is the floor of the fp16 tensor-core
+    operand format (10 mantissa bits, the same as TF32), not of the kernels; the CUDA forward measures 1.2-1.3e-3."""
+    import copy
+    from oracle import port
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    unet = port.make_unet("tiny")
+    lat, emb, _ = port.make_inputs(unet)
+    x = torch.cat([lat] * 2)
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()
+    with torch.no_grad():
+        ref = unet(x, torch.tensor(751), encoder_hidden_states=emb).sample
+        u16 = copy.deepcopy(unet)
+        for p_ in u16.parameters():
+            p_.copy_(p_.half().float())
+        e_w = rel(u16(x, torch.tensor(751), encoder_hidden_states=emb).sample, ref)
+        pre = lambda m, inp: tuple(i.half().float() if torch.is_tensor(i) and i.is_floating_point() else i for i in inp)
+        for m in u16.modules():
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear)):
+                m.register_forward_pre_hook(pre)
+        e_wa = rel(u16(x, torch.tensor(751), encoder_hidden_states=emb).sample, ref)
+    print("oracle one-forward eps error: fp16 weights %.3e, fp16 weights + fp16 GEMM inputs %.3e" % (e_w, e_wa))
+    assert 5e-4 < e_w < 1.5e-3 and 8e-4 < e_wa < 2.5e-3

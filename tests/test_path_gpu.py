@@ -49,29 +49,46 @@ def tiny(cuda):
 
 
 # ------------------------------------------------------------------------------------------------ UNet
-def test_unet_forward_taps_backward_match_oracle(tiny):
-    port, o_unet, eng = tiny["port"], tiny["o_unet"], tiny["unet"].engine
-    lat, emb, _ = tiny["inputs"]
+def _check_unet_against_oracle(fx, t=981, label="tiny"):
+    port, o_unet, eng = fx["port"], fx["o_unet"], fx["unet"].engine
+    lat, emb, _ = fx["inputs"]
     x = torch.cat([lat] * 2)
     taps, handles = port.register_taps(o_unet)
     xg = x.clone().requires_grad_(True)
     with torch.enable_grad():
-        eps_ref = o_unet(xg, torch.tensor(981), encoder_hidden_states=emb).sample
+        eps_ref = o_unet(xg, torch.tensor(t), encoder_hidden_states=emb).sample
         tap_ref = [m.output for m in taps]
         gen = torch.Generator().manual_seed(7)
-        G = [torch.randn(t.shape, generator=gen) for t in tap_ref]
-        dx_ref = torch.autograd.grad(sum((g * t).sum() for g, t in zip(G, tap_ref)), xg)[0]
+        G = [torch.randn(tr.shape, generator=gen) for tr in tap_ref]
+        dx_ref = torch.autograd.grad(sum((g * tr).sum() for g, tr in zip(G, tap_ref)), xg)[0]
     for h in handles:
         h.remove()
-    eps = eng.forward(x.cuda(), 981, emb.cuda(), save_for_backward=True)
-    assert rel(eps, eps_ref) < 3e-3
+    eps = eng.forward(x.cuda(), t, emb.cuda(), save_for_backward=True)
+    e_eps = rel(eps, eps_ref)
+    assert e_eps < 3e-3
+    e_taps = []
     for k in range(9):
         got = eng.tap(k).permute(0, 3, 1, 2)
         assert got.shape == tap_ref[k].shape
-        assert rel(got, tap_ref[k].detach()) < 3e-3, f"tap {k}"
+        e_taps.append(rel(got, tap_ref[k].detach()))
+        assert e_taps[-1] < 3e-3, f"tap {k}"
     Gd = [g.permute(0, 2, 3, 1).contiguous().cuda() for g in G]
     dx = eng.backward(Gd)
-    assert rel(dx, dx_ref) < 6e-3
+    e_dx = rel(dx, dx_ref)
+    assert e_dx < 6e-3
+    # the sampler's form: the cond sample alone (s2i_unet_backward_samples), against the oracle's gradient of that sample
+    eng.forward(x.cuda(), t, emb.cuda(), save_for_backward=True)
+    part = eng.backward([g[1:2].contiguous() for g in Gd], samples=(1, 1))
+    e_cond = rel(part, dx_ref[1:2])
+    assert e_cond < 6e-3
+    print("%s UNet vs oracle: eps %.2e, taps %s, dx %.2e, cond-only dx %.2e" % (
+        label, e_eps, " ".join("%.1e" % e for e in e_taps), e_dx, e_cond))
+    return x, emb, Gd, dx
+
+
+def test_unet_forward_taps_backward_match_oracle(tiny):
+    eng = tiny["unet"].engine
+    x, emb, Gd, dx = _check_unet_against_oracle(tiny)
     # linearity of the tap->input adjoint (size-independent property): J^T(2g) == 2 J^T(g)
     eng.forward(x.cuda(), 981, emb.cuda(), save_for_backward=True)
     dx2 = eng.backward([2 * g for g in Gd])
@@ -122,9 +139,9 @@ def test_unet_forward_is_reproducible_and_batch_independent(tiny):
     e4 = torch.randn(4, 77, emb.shape[2], generator=g).cuda()
     a = eng.forward(x4, 501, e4).clone()
     b = eng.forward(x4, 501, e4).clone()
-    # GroupNorm statistics are reduced with atomics (order varies at the 1e-9 level); every fp16 operand rounding
-    # downstream turns that into ulp-sized noise, saturating near the fp16 error floor of the forward (1e-3).
-    assert rel(a, b) < 3e-3
+    # every reduction of the forward has a fixed order (GroupNorm partials through distributed shared memory in rank order,
+    # split-K partial tiles likewise): the same input gives the same bits
+    assert torch.equal(a, b)
     # samples are closed computations: a batch equals its samples run alone
     for i in (0, 3):
         one = eng.forward(x4[i:i + 1], 501, e4[i:i + 1])
@@ -162,6 +179,10 @@ def _oracle_lgp(tiny, t=981):
 
 
 def test_lgp_forward_loss_backward_match_oracle(tiny):
+    _check_lgp_against_oracle(tiny)
+
+
+def _check_lgp_against_oracle(tiny):
     lat, _, tgt = tiny["inputs"]
     L = lat.shape[2]
     tap_vals, lvl, sigma, ref = _oracle_lgp(tiny)
@@ -185,7 +206,7 @@ def test_lgp_forward_loss_backward_match_oracle(tiny):
         # cond-only form (what the sampler calls): the cond sample's gradients, same values
         eng.forward_taps(taps_nhwc, 2, L, lat.cuda().contiguous(), sigma, True)
         l2, gc, scale2 = eng.loss_backward(tgt.cuda().contiguous(), taps_nhwc, cond_only=True)
-        assert scale2 == scale and abs(l2.item() - l.item()) <= 1e-5 * abs(l.item())      # the loss is summed with float atomics
+        assert scale2 == scale and l2.item() == l.item()        # the loss is a fixed-order sum: bit-identical
         for k in range(9):
             assert tuple(gc[k].shape) == (1,) + tuple(grads[k].shape[1:])
             # same arithmetic; the 4096-row layer-1 dgrad may pick another tile / split-K than the 8192-row one
@@ -518,12 +539,11 @@ def sd15(cuda):
     o_lgp = port.make_lgp(o_unet)
     unet = UNet2DConditionModel(vars(o_unet.config), o_unet.state_dict())
     lgp = LatentEdgePredictor(port.lgp_input_dim(o_unet), 4, port.NUM_POS_LAYERS)
-    lgp.load_state_dict(o_lgp.float().state_dict())
+    lgp.load_state_dict(copy.deepcopy(o_lgp).float().state_dict())     # nn.Module.float() converts in place
     pipe = AntiGradientPipeline(unet=unet, scheduler=DDIMScheduler())
     pipe.setup_lgp(lgp)
     inputs = port.make_inputs(o_unet)
-    del o_unet
-    return dict(pipe=pipe, inputs=inputs)
+    return dict(port=port, o_unet=o_unet, o_lgp=o_lgp, unet=unet, lgp=lgp, pipe=pipe, inputs=inputs)
 
 
 @pytest.mark.parametrize("steps", [4, 50])
@@ -541,6 +561,24 @@ def test_sd15_guided_matches_reference_golden_at_noise_floor(sd15, steps):
 
 @pytest.mark.parametrize("steps", [4, 50])
 def test_sd15_unguided_matches_reference_golden(sd15, steps):
+    """north_star's tolerance -- final-latent relative L2 within 1e-3 of the reference -- asserted on the configuration it is
+    quoted for (50 steps).  The 4-step schedule (configs[0]) strides 250 timesteps per step: each step's new latent is
+    ~0.6 x0-prediction, so one forward's fp16-operand error (eps: 1.2e-3 relative at SD1.5 size) reaches the latent almost
+    undamped and the floor is the single-forward floor; it is asserted at 2e-3 and printed."""
     gold = torch.load(os.path.join(GOLD, f"sd15_{steps}step.pt"))
-    final = _check_unguided_against_golden(sd15["pipe"], sd15["inputs"], gold, f"sd15 {steps}-step")
+    final = _check_unguided_against_golden(sd15["pipe"], sd15["inputs"], gold, f"sd15 {steps}-step", tol=2e-3)
     print("sd15 %d-step unguided FINAL rel err %.3e (north_star target 1e-3)" % (steps, final))
+    assert final < (1e-3 if steps == 50 else 2e-3)
+
+
+# ---- SD1.5-size kernels against the oracle on identical inputs (the bisecting tools of round 1, now collected by pytest)
+def test_sd15_unet_forward_taps_backward_match_oracle(sd15):
+    """s2i_unet_forward / s2i_unet_backward(_samples) at the size BASELINE.json's metric is quoted on: eps and the 9 taps
+    3e-3, the tap -> input adjoint 6e-3 (whole batch and the sampler's cond-only walk)."""
+    _check_unet_against_oracle(sd15, label="sd15")
+
+
+def test_sd15_lgp_forward_loss_backward_match_oracle(sd15):
+    """The 8192 x 9320 feature matrix, the 9320 -> 512 layer and its cond-only input gradient, train-mode BatchNorm over
+    8192 rows, the separable resize adjoint: against the fp16 oracle and its fp32 restatement (same yardstick as tiny)."""
+    _check_lgp_against_oracle(sd15)
