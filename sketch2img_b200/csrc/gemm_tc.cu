@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
+#include <string>
 
 namespace s2i {
 
@@ -21,6 +23,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;             // elements; 128 bytes = one swizzle row
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kChunkBytes = 64 * kBlockK * 2;         // 8 KB: one 64-row (or 64-col, MN-major) box
+constexpr int kMaxCluster = 16;     // split-K cluster size: 8 is the portable maximum, 16 needs the non-portable attribute
 
 struct __align__(64) GemmParams {
     CUtensorMap mapA;
@@ -57,8 +60,12 @@ struct __align__(64) GemmParams {
     int has_res, has_o32, has_o16, has_glu;
     int split_add;           // split-K by fp32 reduce-add into a zeroed output (split 0 carries bias + residual)
     int pipe_bytes;          // shared-memory bytes in front of the barriers (max of pipeline, epilogue staging, partial tile)
-    int csplit;              // split-K inside a thread-block cluster (1, 1, csplit): partial tiles reduced through distributed
-                             // shared memory in rank order (deterministic; no zero-fill, no atomics); 0 / 1 = off
+    // Deterministic split-K (dsplit != 0): splits = csplit * groups CTAs share an output tile.  The csplit CTAs of a thread-block
+    // cluster (1, 1, csplit) reduce their partial tiles through distributed shared memory in rank order (CTA rank r owns the tile
+    // rows [r * 128 / csplit, ...)); with groups > 1 each cluster writes its reduced rows to ws [group][tile][128][BN] and the CTA
+    // that arrives LAST for its (tile, row slice) adds the groups' rows in group order and runs the epilogue.  No zero-fill, no
+    // floating-point atomics: the result does not depend on timing.
+    int dsplit, csplit, groups;
     int msub;                // M sub-tiles per CTA (1 or 2): two 128-row A tiles share every B tile (two TMEM accumulators)
     int tiles_m;             // number of 128-row M tiles of the problem
     unsigned long long* trace;   // optional [ctas][16] %globaltimer stamps of the kernel's phases (tools/gemm_trace.py)
@@ -283,7 +290,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
     pdl_launch();     // TMEM is held: dependents may become resident
     if (threadIdx.x == 0) stamp(p, 1);
     const bool add_res = p.has_res && (!p.split_add || t.split == 0);
-    const bool add_bias = p.csplit > 1 || !p.split_add || t.split == 0;
+    const bool add_bias = p.dsplit || !p.split_add || t.split == 0;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -328,8 +335,8 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
         const uint32_t sw128 = (uint32_t)(r & 7);
         const uint32_t sw64 = (uint32_t)((r >> 1) & 3);
         uint8_t* base16 = smem + (use32 ? nch * kChunk32Bytes : 0);
-        if (p.csplit > 1) {
-            // cluster split-K: this CTA's partial tile (its K range) -> shared memory [128][BN + 4] fp32 (the idle pipeline
+        if (p.dsplit) {
+            // deterministic split-K: this CTA's partial tile (its K range) -> shared memory [128][BN + 4] fp32 (the idle pipeline
             // stages); the cluster reduces it below, after the role branches
             float* part = reinterpret_cast<float*>(smem);
             const int ldp = p.BN + 4;
@@ -478,46 +485,32 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
         }
     }
 
-    if (p.csplit > 1) {
-        // ---------------------------------------------------- cluster split-K reduction through distributed shared memory
-        // Every CTA of the cluster (1, 1, csplit) holds the partial tile of its K range.  CTA `rank` owns the tile rows
-        // [rank * 128 / csplit, ...): it adds the csplit partial rows in RANK ORDER (so the sum does not depend on timing),
-        // applies the epilogue (bias, ReLU / rounding emulation, fp32 residual) and writes the result rows to global memory.
+    if (p.dsplit) {
+        // ---------------------------------------------------- deterministic split-K reduction (see GemmParams::dsplit)
+        const int CS = p.csplit, G = p.groups;
+        const int rank = t.split % CS, group = t.split / CS;
         ptx::tc_fence_before();
-        __syncwarp();
-        cluster_arrive();
-        cluster_wait();
+        if (CS > 1) {
+            __syncwarp();
+            cluster_arrive();
+            cluster_wait();
+        } else {
+            __syncthreads();
+        }
         if (warp >= 2) {
             const int e = threadIdx.x - 64;
-            const int CS = p.csplit;
             const int rows_per = kBlockM / CS;
-            const int row0 = t.split * rows_per;
+            const int row0 = rank * rows_per;
             const int nq = p.BN >> 2;
             const int ldp = p.BN + 4;
+            const int tile_id = blockIdx.x + gridDim.x * blockIdx.y;
+            const int num_tiles = gridDim.x * gridDim.y;
             const uint32_t part_local = ptx::smem_u32(smem);
-            uint32_t base_k[8];
+            uint32_t base_k[kMaxCluster];
     #pragma unroll
-            for (int k = 0; k < 8; ++k) base_k[k] = map_to_rank(part_local, (uint32_t)(k < CS ? k : 0));
-            for (int idx = e; idx < rows_per * nq; idx += 128 * ESETS) {
-                const int rr = idx / nq;
-                const int c4 = (idx - rr * nq) << 2;
-                const int row = row0 + rr;
-                const int n = t.n0 + c4;
-                if (n >= p.N) continue;
-                const int xi = row % p.tw;
-                const int yi = (row / p.tw) % p.th;
-                const int bi = row / (p.tw * p.th);
-                if (bi >= p.tb || t.x0 + xi >= p.W || t.y0 + yi >= p.H || t.b0 + bi >= p.Bn) continue;
-                const long grow = ((long)(t.b0 + bi) * p.H + (t.y0 + yi)) * p.W + (t.x0 + xi);
-                const uint32_t off = (uint32_t)((row * ldp + c4) * 4);
-                float4 v[8];
-    #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k < CS) v[k] = ld_cluster_f4(base_k[k] + off);
-                float4 acc = v[0];
-    #pragma unroll
-                for (int k = 1; k < 8; ++k)
-                    if (k < CS) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+            for (int k = 0; k < kMaxCluster; ++k) base_k[k] = map_to_rank(part_local, (uint32_t)(k < CS ? k : 0));
+            // bias / ReLU / rounding emulation / residual, then the fp32 and / or fp16 rows of the output
+            auto finish = [&](float4 acc, int c4, int n, long grow, const float4& res4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c4);
                 acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
                 if (p.relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
@@ -527,10 +520,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                     acc.z = __half2float(__float2half_rn(acc.z * p.qinv)) * p.qscale;
                     acc.w = __half2float(__float2half_rn(acc.w * p.qinv)) * p.qscale;
                 }
-                if (p.residual) {
-                    const float4 x = ldg_f4(p.residual + grow * p.res_ld + n);
-                    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
-                }
+                if (p.residual) { acc.x += res4.x; acc.y += res4.y; acc.z += res4.z; acc.w += res4.w; }
                 if (p.out32) *reinterpret_cast<float4*>(p.out32 + grow * p.ld32 + n) = acc;
                 if (p.out16) {
                     const __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
@@ -539,11 +529,115 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                     pk.y = *reinterpret_cast<const uint32_t*>(&h1);
                     *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out16) + grow * p.ld16 + n) = pk;
                 }
+            };
+            // global row of tile row `row`, or -1 when it falls outside the tensor
+            auto global_row = [&](int row) -> long {
+                const int xi = row % p.tw;
+                const int yi = (row / p.tw) % p.th;
+                const int bi = row / (p.tw * p.th);
+                if (bi >= p.tb || t.x0 + xi >= p.W || t.y0 + yi >= p.H || t.b0 + bi >= p.Bn) return -1;
+                return ((long)(t.b0 + bi) * p.H + (t.y0 + yi)) * p.W + (t.x0 + xi);
+            };
+            float* wsT = G > 1 ? p.ws + ((long)group * num_tiles + tile_id) * kBlockM * p.BN : nullptr;
+            // kU float4 units per thread per trip: up to 8 (distributed) shared-memory loads and kU residual loads in flight (more
+            // would spill under the two-CTAs-per-SM register bound)
+            auto reduce_rows = [&](auto cs_tag) {
+                constexpr int kCS = decltype(cs_tag)::value;
+                constexpr int kU = kCS >= 8 ? 1 : 2;
+                constexpr int kL = kCS > 8 ? 8 : kCS;        // loads in flight per unit (a cluster of 16 takes two passes, in rank order)
+                const int total = rows_per * nq;
+                for (int base = e; base < total; base += kU * 128 * ESETS) {
+                    float4 v[8], rs[kU];
+                    long grow[kU];
+                    int c4s[kU], rows[kU];
+    #pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        grow[u] = -1;
+                        const int idx = base + u * 128 * ESETS;
+                        if (idx < total) {
+                            const int rr = idx / nq;
+                            c4s[u] = (idx - rr * nq) << 2;
+                            rows[u] = row0 + rr;
+                            if (t.n0 + c4s[u] < p.N) grow[u] = global_row(rows[u]);
+                            if (grow[u] >= 0) {
+                                const uint32_t off = (uint32_t)((rows[u] * ldp + c4s[u]) * 4);
+    #pragma unroll
+                                for (int k = 0; k < kL; ++k) v[u * kL + k] = ld_cluster_f4(base_k[k] + off);
+                                if (G == 1 && p.residual) rs[u] = ldg_f4(p.residual + grow[u] * p.res_ld + t.n0 + c4s[u]);
+                            }
+                        }
+                    }
+    #pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        if (grow[u] >= 0) {
+                            float4 acc = v[u * kL];
+    #pragma unroll
+                            for (int k = 1; k < kL; ++k) {
+                                const float4 x = v[u * kL + k];
+                                acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+                            }
+                            if (kCS > 8) {
+                                const uint32_t off = (uint32_t)((rows[u] * ldp + c4s[u]) * 4);
+                                float4 w[8];
+    #pragma unroll
+                                for (int k = 0; k < 8; ++k) w[k] = ld_cluster_f4(base_k[8 + k] + off);
+    #pragma unroll
+                                for (int k = 0; k < 8; ++k) { acc.x += w[k].x; acc.y += w[k].y; acc.z += w[k].z; acc.w += w[k].w; }
+                            }
+                            if (G > 1) *reinterpret_cast<float4*>(wsT + (long)rows[u] * p.BN + c4s[u]) = acc;   // this group's rows, raw sums
+                            else finish(acc, c4s[u], t.n0 + c4s[u], grow[u], rs[u]);
+                        }
+                    }
+                }
+            };
+            if (CS == 16) reduce_rows(std::integral_constant<int, 16>());
+            else if (CS == 8) reduce_rows(std::integral_constant<int, 8>());
+            else if (CS == 4) reduce_rows(std::integral_constant<int, 4>());
+            else if (CS == 2) reduce_rows(std::integral_constant<int, 2>());
+            else reduce_rows(std::integral_constant<int, 1>());
+            if (G > 1) {
+                // the CTA arriving last for this (tile, row slice) adds the groups' rows in group order
+                uint32_t* flag = reinterpret_cast<uint32_t*>(bias_s + p.BN);
+                __threadfence();
+                ptx::named_bar_sync(1, 128 * ESETS);
+                if (e == 0) {
+                    unsigned int* ctr = p.counters + tile_id * kMaxCluster + rank;
+                    const unsigned int old = atomicAdd(ctr, 1u);
+                    const bool last = old == (unsigned int)(G - 1);
+                    if (last) *ctr = 0u;              // self-reset for the next launch
+                    *flag = last ? 1u : 0u;
+                }
+                ptx::named_bar_sync(1, 128 * ESETS);
+                if (*flag) {
+                    __threadfence();
+                    const float* ws0 = p.ws + (long)tile_id * kBlockM * p.BN;
+                    const long gstride = (long)num_tiles * kBlockM * p.BN;
+                    for (int idx = e; idx < rows_per * nq; idx += 128 * ESETS) {
+                        const int rr = idx / nq;
+                        const int c4 = (idx - rr * nq) << 2;
+                        const int row = row0 + rr;
+                        const int n = t.n0 + c4;
+                        if (n >= p.N) continue;
+                        const long grow = global_row(row);
+                        if (grow < 0) continue;
+                        const float* src = ws0 + (long)row * p.BN + c4;
+                        float4 acc = ldcg_f4(src);
+                        for (int g = 1; g < G; ++g) {
+                            const float4 x = ldcg_f4(src + g * gstride);
+                            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+                        }
+                        float4 res4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.residual) res4 = ldg_f4(p.residual + grow * p.res_ld + n);
+                        finish(acc, c4, n, grow, res4);
+                    }
+                }
             }
         }
-        __syncwarp();
-        cluster_arrive();         // this CTA no longer reads its peers' shared memory ...
-        cluster_wait();           // ... and no peer reads this CTA's: it may exit
+        if (CS > 1) {
+            __syncwarp();
+            cluster_arrive();         // this CTA no longer reads its peers' shared memory ...
+            cluster_wait();           // ... and no peer reads this CTA's: it may exit
+        }
     }
 
     ptx::tc_fence_before();
@@ -856,9 +950,13 @@ int pow2_floor(int v) {
 // traffic at ~64 B/clk/SM when every SM pulls; ~6 k cycles of fixed launch / prologue / first-load latency; epilogue
 // ~8 cycles per column).  The problem sizes on this path are at most a few waves, so filling the 148 SMs (x2 resident
 // CTAs when shared memory allows) matters as much as the inner-loop rate.
+constexpr size_t kWsBytes = 96u << 20;      // split-K scratch: partial tiles (gemm_tc_kernel) / group rows (gemm_tma_kernel)
+constexpr int kMaxSplitTiles = 4096;        // arrival counters
+
 struct TileChoice {
     int BN, splits;
     int msub = 1;
+    int cs = 1;       // deterministic split-K: cluster size (splits = cs * groups)
 };
 
 double model_cycles(int N, long tiles_m, int Z, int iters, int BN, int splits) {
@@ -948,24 +1046,41 @@ bool g_split_add_mode = [] {
     return e && e[0] == '1';
 }();
 
-// cluster split-K: ~2 cluster barriers + the DSMEM reduction of one tile's worth of fp32 per CTA
-double model_cycles_cluster(int N, long tiles_m, int iters, int BN, int splits, int epi) {
+// How many clusters of `cs` CTAs of gemm_tma_kernel can be resident at once, for CTAs sized to share an SM in pairs
+// (occ = 2: <= 112 KB of shared memory) or not (occ = 1).  Thread-block clusters are gang-scheduled inside a GPC, so this
+// is less than #SMs * occ / cs (measured in round 1 for the GroupNorm kernel: 15 clusters of 8, not 18); a grid with more
+// clusters than this runs in two waves.  Queried once per (cs, occ) from the occupancy API, filled in by launch_tma.
+int g_cluster_cap[kMaxCluster + 1][3] = {};
+int cluster_capacity(int cs, int occ);
+
+// deterministic split-K (cluster size cs, `groups` clusters per tile): model of one CTA's cycles, times the number of waves
+double model_cycles_dsplit(int N, long tiles_m, int iters, int BN, int cs, int groups, int epi) {
+    const int splits = cs * groups;
     const int tiles_n = ceil_div(N, BN);
     const long ctas = tiles_m * tiles_n * splits;
     const int stage_bytes = kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
     const long part_bytes = (long)kBlockM * (BN + 4) * 4;
-    const int occ = (2 * stage_bytes <= 100 * 1024 && part_bytes <= 100 * 1024 && BN <= 256) ? 2 : 1;
-    const long slots = (long)kNumSMs * occ;
-    const long waves = ceil_div_l(ctas, slots);
+    const int occ = (2 * stage_bytes <= 100 * 1024 && part_bytes <= 108 * 1024 && BN <= 256) ? 2 : 1;
+    const long n_clusters = tiles_m * tiles_n * groups;
+    const int cap1 = cluster_capacity(cs, 1);
+    // CTAs are sized to pair up on an SM when the clusters do not fit one per SM (launch_tma does the same).  The occupancy API
+    // reports the same cluster count for such CTAs as for unpaired ones; measured, twice that many clusters still run as one wave
+    const int use_occ = (n_clusters > cap1 && occ == 2) ? 2 : 1;
+    const long cap = (long)cap1 * use_occ;
+    const long waves = ceil_div_l(n_clusters, cap > 0 ? cap : 1);
     const int it = ceil_div(iters, splits);
-    const double resident = (double)(ctas <= kNumSMs ? 1 : occ);
+    const double resident = (double)((ctas <= kNumSMs && use_occ == 1) ? 1 : use_occ);
     const double mma = 2.0 * BN * resident;
     const double tma = (double)(kAStageBytes + BN * 128) / (resident > 1.0 ? 21.0 : 31.0);
     const double per_iter = mma > tma ? mma : tma;
-    // prologue / first load / drain as in model_cycles_tma; TMEM -> smem 60 cycles per chunk; two cluster barriers;
-    // the DSMEM reduction moves 128 x BN fp32 per CTA at ~48 B/clk plus the global epilogue of 128 / S rows
-    const double fixed = 9000.0 + 60.0 * (BN / 32) + 1200.0 + (double)kBlockM * BN * 4 / 48.0 +
-                         ((epi & 1) ? 600.0 : 0.0);
+    const double rows_per = (double)kBlockM / cs;
+    // prologue / first load / drain as in model_cycles_tma; TMEM -> smem 60 cycles per chunk; barriers; one tile's worth of
+    // fp32 through (distributed) shared memory at ~48 B/clk; the row slice's global epilogue; with groups: the slice out to
+    // and back from L2 (groups + 1 passes), fence + counter
+    // (+ 3000: measured, a split costs ~1.5 us more than the terms below add up to -- cluster launch and barrier skew)
+    double fixed = 12000.0 + 60.0 * (BN / 32) + (cs > 1 ? 1200.0 : 300.0) + (double)kBlockM * BN * 4 / 48.0 +
+                   rows_per * BN * 8.0 / 24.0 + ((epi & 1) ? 600.0 : 0.0);
+    if (groups > 1) fixed += 2500.0 + rows_per * BN * 4.0 * (groups + 1) / 24.0;
     return (double)waves * (it * per_iter + fixed);
 }
 
@@ -977,13 +1092,21 @@ TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, in
         if (c > N && c != 32) continue;
         if (!g_split_add_mode && allow_split) {
             const long base = tiles_m * ceil_div(N, c);
-            for (int sp = 2; sp <= 8; sp *= 2) {
-                // clusters must be co-scheduled: keep the grid within one wave of (possibly paired) CTAs
-                if (base * sp > 2 * kNumSMs || iters / sp < 2) break;
-                const double cyc = model_cycles_cluster(N, tiles_m, iters, c, sp, epi);
-                if (cyc < best_c) {
-                    best_c = cyc;
-                    best = TileChoice{c, sp, 1};
+            for (int cs = 2; cs <= kMaxCluster; cs *= 2) {
+                // one cluster per tile: measured (tools/gemm_bench.py dsweep, profiles/r2_gemm_dsweep_v1.txt) the best
+                // configuration of every shape of the step has groups = 1 -- the extra trip through L2 (group rows out, fence,
+                // counter, rows back in) costs more than the added CTAs bring; groups > 1 stays available to callers
+                for (int groups = 1; groups <= 1; ++groups) {
+                    const int sp = cs * groups;
+                    if (sp == 1) continue;
+                    if (iters / sp < 2 || base * sp > 2 * kNumSMs + 64 || base * kMaxCluster > kMaxSplitTiles) break;
+                    if ((long)(sp - 1) * ceil_div(iters, sp) >= iters) continue;      // an empty split
+                    if (groups > 1 && (size_t)groups * base * kBlockM * c * sizeof(float) > kWsBytes) continue;
+                    const double cyc = model_cycles_dsplit(N, tiles_m, iters, c, cs, groups, epi);
+                    if (cyc < best_c) {
+                        best_c = cyc;
+                        best = TileChoice{c, sp, 1, cs};
+                    }
                 }
             }
         }
@@ -1020,8 +1143,6 @@ bool tma_epilogue_enabled() {
 }
 
 // split-K scratch: partial tiles + per-tile arrival counters (one stream at a time uses the library)
-constexpr size_t kWsBytes = 96u << 20;
-constexpr int kMaxSplitTiles = 4096;
 float* g_ws = nullptr;
 unsigned int* g_counters = nullptr;
 int g_ws_device = -1;
@@ -1152,6 +1273,37 @@ inline void launch_kernel_cluster_z(void (*kernel)(KArgs...), dim3 grid, dim3 bl
     g_prev_kernel = true;
 }
 
+int cluster_capacity(int cs, int occ) {
+    if (cs < 1 || cs > kMaxCluster || occ < 1 || occ > 2) return kNumSMs;
+    int& slot = g_cluster_cap[cs][occ];
+    if (slot > 0) return slot;
+    int cap = kNumSMs * occ / cs;                 // fallback when the query is unavailable (e.g. no device at build time)
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gemm_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(gemm_tma_kernel<2, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(gemm_tma_kernel<1, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1, 1, (unsigned)(cs * 64));
+    cfg.blockDim = dim3(kThreads + 128);
+    cfg.dynamicSmemBytes = occ == 2 ? 104 * 1024 : 200 * 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)cs;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tma_kernel<2, false>, &cfg) == cudaSuccess && n > 0) cap = n;
+    else cudaGetLastError();
+    slot = cap;
+    if (getenv("S2I_GEMM_DEBUG")) fprintf(stderr, "gemm_tma: %d clusters of %d CTAs can be resident (%d CTA(s) per SM)\n", cap, cs, occ);
+    return cap;
+}
+
 int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters, cudaStream_t stream) {
     GemmDesc d = d_in;
     const long rows_total = (long)d.aW * d.aH * d.aB;
@@ -1199,14 +1351,28 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     if (d.splits > 0 && can_split) tc.splits = d.splits;
     if (!can_split) tc.splits = 1;
     if (g_force_msub > 0) tc.msub = (g_force_msub == 2 && tiles_m >= 2 && 2 * tc.BN <= 512) ? 2 : 1;
+    while (tc.splits > 1 && (long)(tc.splits - 1) * ceil_div(num_iters, tc.splits) >= num_iters) --tc.splits;
+    int groups = 1;
     if (cluster_mode && tc.splits > 1) {
-        int sp = 1;                                   // cluster sizes: powers of two up to the portable maximum of 8
-        while (sp * 2 <= tc.splits && sp * 2 <= 8) sp *= 2;
-        while (sp > 1 && num_iters / sp < 1) sp /= 2;
-        tc.splits = sp;
-        if (sp > 1) tc.msub = 1;                      // the partial tile of the cluster reduction is one 128-row accumulator
+        // splits = cluster size (a power of two up to the portable maximum of 8, dividing the 128 tile rows) x groups
+        int cs = tc.cs;
+        if ((d.splits > 0 || d.BN > 0) || cs < 1 || tc.splits % cs != 0) {          // forced by the caller: largest fitting cluster
+            cs = 1;
+            while (cs * 2 <= 8 && tc.splits % (cs * 2) == 0) cs *= 2;
+        }
+        if (const char* e = getenv("S2I_GEMM_CS")) {                                  // tools: force the cluster size
+            const int f = atoi(e);
+            if ((f == 1 || f == 2 || f == 4 || f == 8 || f == 16) && tc.splits % f == 0) cs = f;
+        }
+        groups = tc.splits / cs;
+        const long tiles = tiles_m * ceil_div(d.N, tc.BN);
+        if (tiles * kMaxCluster > kMaxSplitTiles || (groups > 1 && (size_t)groups * tiles * kBlockM * tc.BN * sizeof(float) > kWsBytes)) {
+            groups = 1;                               // does not fit the scratch: one cluster per tile
+            tc.splits = cs;
+        }
+        tc.cs = cs;
+        tc.msub = 1;                                  // the partial tile of the reduction is one 128-row accumulator
     }
-    while (tc.splits > 1 && (long)(tc.splits - 1) * ceil_div(num_iters, tc.splits) >= num_iters) tc.splits -= cluster_mode ? tc.splits / 2 : 1;
     const int BN = tc.BN;
     const int msub = tc.msub;
     const bool csplit = cluster_mode && tc.splits > 1;
@@ -1215,7 +1381,14 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     p.BN = BN;
     p.splits = tc.splits;
     p.split_add = (!cluster_mode && tc.splits > 1) ? 1 : 0;
-    p.csplit = csplit ? tc.splits : 0;
+    p.dsplit = csplit ? 1 : 0;
+    p.csplit = csplit ? tc.cs : 1;
+    p.groups = csplit ? groups : 1;
+    if (csplit && groups > 1) {
+        S2I_TRY(ensure_ws());
+        p.ws = g_ws;
+        p.counters = g_counters;
+    }
     p.iters_per_split = ceil_div(num_iters, tc.splits);
     p.has_res = (d.residual && !csplit) ? 1 : 0;
     p.has_o32 = (d.out32 && !csplit) ? 1 : 0;
@@ -1232,10 +1405,12 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
                                           (glu ? (nch / 2) * kChunk16Bytes : 0);
     const long grid_m = ceil_div_l(tiles_m, msub);
     const long ctas = grid_m * tiles_n * tc.splits;
-    const size_t tail = (size_t)(2 * 8 + 1 + kMaxChunks) * 8 + 16 + (size_t)BN * 4 + 1024 + 64;
+    const size_t tail = (size_t)(2 * 8 + 1 + kMaxChunks) * 8 + 16 + (size_t)BN * 4 + 16 + 1024 + 64;   // barriers, TMEM slot, bias, flag, slack
     // aim for two co-resident CTAs (<= 112 KB each) when more than one wave is coming and they can actually share an SM
     const bool can_pair = 2 * (size_t)stage_bytes + tail <= 112u * 1024u && epi_bytes + tail <= 112u * 1024u && msub * BN <= 256;
-    const size_t budget = ((ctas > kNumSMs && can_pair) ? 112u : 220u) * 1024u - tail;
+    // ... or when the split-K clusters do not fit one CTA per SM (clusters are gang-scheduled: one too many means a second wave)
+    const bool pair = can_pair && (ctas > kNumSMs || (csplit && tc.cs > 1 && grid_m * tiles_n * groups > cluster_capacity(tc.cs, 1)));
+    const size_t budget = (pair ? 112u : 220u) * 1024u - tail;
     int stages = (int)(budget / stage_bytes);
     if (stages < 2) stages = 2;
     if (stages > 8) stages = 8;
@@ -1249,7 +1424,7 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     static const bool dbg = getenv("S2I_GEMM_DEBUG") != nullptr;       // tools: print the chosen configuration
     if (dbg)
         fprintf(stderr, "gemm_tma %s: M-tiles %ld N %d iters %d -> BN %d msub %d splits %d%s stages %d ctas %ld smem %zu%s\n", d.tag,
-                tiles_m, d.N, num_iters, BN, msub, tc.splits, csplit ? " (cluster)" : "", stages, ctas, smem_bytes,
+                tiles_m, d.N, num_iters, BN, msub, tc.splits, csplit ? (" (cluster " + std::to_string(tc.cs) + " x " + std::to_string(groups) + " groups)").c_str() : "", stages, ctas, smem_bytes,
                 via_scratch ? " (via scratch)" : "");
 
     p.a_c0 = d.a_c0; p.a_hoff = d.a_hoff; p.a_zmode = d.a_zmode;
@@ -1311,9 +1486,9 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     // read per call so tools can A/B in one process
     int esets = (BN >> 5) >= 2 ? 2 : 1;
     if (const char* e = getenv("S2I_GEMM_ESETS")) esets = atoi(e) == 1 ? 1 : esets;
-    if (csplit) {
-        if (esets == 2) launch_kernel_cluster_z(gemm_tma_kernel<2, false>, grid, dim3(kThreads + 128), smem_bytes, tc.splits, stream, p);
-        else launch_kernel_cluster_z(gemm_tma_kernel<1, false>, grid, dim3(kThreads), smem_bytes, tc.splits, stream, p);
+    if (csplit && tc.cs > 1) {
+        if (esets == 2) launch_kernel_cluster_z(gemm_tma_kernel<2, false>, grid, dim3(kThreads + 128), smem_bytes, tc.cs, stream, p);
+        else launch_kernel_cluster_z(gemm_tma_kernel<1, false>, grid, dim3(kThreads), smem_bytes, tc.cs, stream, p);
     } else if (glu) S2I_LAUNCH((gemm_tma_kernel<2, true>), grid, kThreads + 128, smem_bytes, stream, p);
     else if (esets == 2) S2I_LAUNCH((gemm_tma_kernel<2, false>), grid, kThreads + 128, smem_bytes, stream, p);
     else S2I_LAUNCH((gemm_tma_kernel<1, false>), grid, kThreads, smem_bytes, stream, p);

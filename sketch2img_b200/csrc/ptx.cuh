@@ -95,6 +95,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const void* tmap, uint64
         : "memory");
 }
 
+// contiguous global -> shared bulk copy (bytes: multiple of 16; both addresses 16-byte aligned), completing on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem, const void* gptr, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // smem -> global tile stores (bulk async group of the issuing thread); out-of-bounds parts of the box are clipped
 __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"

@@ -29,8 +29,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
-kErrFactor = 3.0        # per-step bound on (CUDA distance) / (fp16-weight reference distance)
-kMeanFactor = 2.0       # bound on the mean of that ratio over the guided steps
+kErrFactor = 2.5        # per-step bound on (CUDA distance) / (fp16-weight reference distance); measured max 1.93 (tiny), 1.24 (SD1.5)
+kMeanFactor = 1.5       # bound on the mean of that ratio over the guided steps; measured 1.13 (tiny), 1.12 (SD1.5)
 kAngleFloor = 0.02      # radians: below this the yardstick itself is rounding noise
 
 

@@ -83,7 +83,40 @@ def time_desc(kw, reps=20, **over):
     return e0.elapsed_time(e1) / (3 * reps) * 1e3
 
 
+def dsweep():
+    """Deterministic split-K sweep: tile width x cluster size x groups per shape, against the cost model's own choice."""
+    for shape in SHAPES:
+        kw, keep = make(shape)
+        name, side, rows, N, K, taps = shape[:6]
+        os.environ.pop("S2I_GEMM_CS", None)
+        t_def = time_desc(kw)
+        res = []
+        for bn in (64, 96, 128, 160, 192, 256):
+            if bn > N:
+                continue
+            try:
+                res.append((time_desc(kw, reps=10, BN=bn, splits=-1), bn, 1, 1))
+            except L.S2IError:
+                pass
+            for cs in (1, 2, 4, 8, 16):
+                for g in (1, 2, 3):
+                    if cs * g == 1:
+                        continue
+                    os.environ["S2I_GEMM_CS"] = str(cs)
+                    try:
+                        res.append((time_desc(kw, reps=10, BN=bn, splits=cs * g), bn, cs, g))
+                    except L.S2IError:
+                        pass
+                    os.environ.pop("S2I_GEMM_CS", None)
+        res.sort()
+        print(f"{name:28s} model's choice {t_def:6.1f} us; best (us, BN, cluster, groups): "
+              + " ".join("(%.1f %d %d %d)" % r for r in res[:6]), flush=True)
+        del keep
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "dsweep":
+        return dsweep()
     sweep = len(sys.argv) > 1 and sys.argv[1] == "sweep"
     lib = L.lib()
     print(f"{'shape':28s} {'GFLOP':>7s} {'thread_epi us':>13s} {'tma_epi us':>11s} {'TF/s':>7s}")
