@@ -232,21 +232,21 @@ def run_config4(args, rank, world, dev, barrier, n_timed):
     sat = SatMixin(unet)
     boc = cfg["block_out_channels"]
     g = torch.Generator().manual_seed(2140 + rank)
-    res, side = [], L
-    for i, c in enumerate(boc):                 # modules/sketch_encoder.py:93-98: per down block (layer outputs..., downsampled)
-        maps = [torch.randn(2, c, side, side, generator=g) for _ in range(2)]
-        if i < 3:
-            side //= 2
-            maps.append(torch.randn(2, c, side, side, generator=g))
-        res.append(tuple(m.to(dev) for m in maps))
-    sat.set_res_samples(res)
+    # the producer of the sketch features: SketchEncoder (modules/sketch_encoder.py) on the engine, same topology with
+    # attention-free down blocks, random weights (identical on every rank: seeded)
+    from sketch2img_b200.sketch_encoder import SketchEncoder
+    enc_cfg = dict(cfg, down_block_types=("DownBlock2D",) * 4)
+    encoder = SketchEncoder(enc_cfg, synthetic.sketch_encoder_state_dict(enc_cfg, seed=2141), device=dev)
     sat.set_scale(1.0)
     pipe = AntiGradientPipeline(unet=unet, scheduler=DDIMScheduler(prediction_type="v_prediction"))
     lat = torch.randn(1, 4, L, L, generator=g).to(dev)
     emb = torch.randn(2, 77, Dc, generator=g).to(dev)
+    sketch = torch.randn(1, 4, L, L, generator=g).to(dev)         # VAE latent of the sketch (synthetic)
     setup_s = time.time() - t0
 
     def call():
+        # per image: sketch latent -> encoder features (same for both CFG halves) -> K/V of the 16 injected attentions; 50 steps
+        sat.set_res_samples(encoder(torch.cat([sketch] * 2), 0).sample)
         return pipe("synthetic", num_inference_steps=NUM_INFERENCE_STEPS, guidance_scale=GUIDANCE, latents=lat, sketch_image=None,
                     prompt_embeds=emb, output_type="latent")
     call()
@@ -271,10 +271,11 @@ def run_config4(args, rank, world, dev, barrier, n_timed):
     tf_peak, _, peak_src = measured_peaks()
     achieved = flops_image * n_timed / (ms * 1e-3) / 1e12
     ok = bool(torch.isfinite(out).all().item())
-    del pipe, sat, unet
+    del pipe, sat, unet, encoder
     torch.cuda.empty_cache()
     return {"workload": "SD2.1-768 topology, 96x96 latent, 50-step v-prediction DDIM CFG=7.5 + SatMixin injected sketch attention "
-                        "(16 blocks, scale 1.0), no LGP, 1 image per GPU per call (configs[3]: batch 8 over 8 GPUs)",
+                        "(16 blocks, scale 1.0, features from the SketchEncoder down path run once per image), no LGP, 1 image per GPU per call "
+                        "(configs[3]: batch 8 over 8 GPUs)",
             "global_batch": world, "images_per_sec": world * n_timed / (ms * 1e-3), "ms_per_image": ms / n_timed,
             "ms_per_denoise_step": ms / n_timed / NUM_INFERENCE_STEPS, "timed_calls": n_timed, "finite": ok,
             "setup_s": round(setup_s, 1),

@@ -171,6 +171,17 @@ int s2i_unet_load_sat(s2i_unet* u, int n, const char* const* names, const float*
 int s2i_unet_set_sat_feature(s2i_unet* u, const char* block_path, const float* feature_nchw, int B, int C, int H, int W,
                              void* cuda_stream);
 int s2i_unet_set_sat_scale(s2i_unet* u, float scale, void* cuda_stream);
+/* Sketch feature encoder (modules/sketch_encoder.py:11-98, SketchEncoder(UNet2DConditionModel)): conv_in, the time embedding
+ * and the down path of a UNet whose four down blocks are attention-free (the reference's forward calls the down blocks
+ * without encoder_hidden_states, :93-95, which only executes for DownBlock2D); the forward stops after the down blocks and
+ * keeps every block's res_samples -- the input of SatMixin.set_res_samples (modules/sketch_guided_attn.py:29-40).
+ * Weights: host fp32 tensors under their diffusers names (conv_in.*, time_embedding.*, down_blocks.*), loaded with
+ * s2i_unet_load; destroyed with s2i_unet_destroy.  res_sample k: NHWC fp32 view owned by the engine (valid until the next
+ * forward), in block order: per down block its layers_per_block resnet outputs, then the downsampled map (not the last block). */
+int s2i_sketch_encoder_create(const s2i_unet_config* cfg, s2i_unet** out);
+int s2i_sketch_encoder_forward(s2i_unet* u, const float* x, int B, int H, int W, float t, void* cuda_stream);
+int s2i_sketch_encoder_num_res_samples(s2i_unet* u);
+int s2i_sketch_encoder_res_sample(s2i_unet* u, int k, float** ptr, long long* pixel_stride, int* B, int* H, int* W, int* C);
 /* bisecting aid: keep named block outputs of the next forwards ("conv_in", "down0".., "mid", "up0"..) */
 int s2i_unet_debug(s2i_unet* u, int enable);
 int s2i_unet_debug_get(s2i_unet* u, const char* name, float** ptr, long long* ld, int* B, int* H, int* W, int* C);

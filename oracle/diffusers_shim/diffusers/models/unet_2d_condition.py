@@ -272,7 +272,7 @@ class UNet2DConditionModel(nn.Module):
     def __init__(self, sample_size=64, in_channels=4, out_channels=4,
                  block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, attention_head_dim=8,
                  cross_attention_dim=768, use_linear_projection=False, upcast_attention=False,
-                 norm_num_groups=32, flip_sin_to_cos=True, freq_shift=0):
+                 norm_num_groups=32, flip_sin_to_cos=True, freq_shift=0, down_block_types=None):
         super().__init__()
         boc = tuple(block_out_channels)
         nb = len(boc)
@@ -282,7 +282,11 @@ class UNet2DConditionModel(nn.Module):
             block_out_channels=boc, layers_per_block=layers_per_block, attention_head_dim=attention_head_dim,
             cross_attention_dim=cross_attention_dim, use_linear_projection=use_linear_projection,
             upcast_attention=upcast_attention, norm_num_groups=norm_num_groups,
-            flip_sin_to_cos=flip_sin_to_cos, freq_shift=freq_shift)
+            flip_sin_to_cos=flip_sin_to_cos, freq_shift=freq_shift, down_block_types=down_block_types,
+            center_input_sample=False, class_embed_type=None)
+        # read by modules/sketch_encoder.py:39,85 (SketchEncoder.forward)
+        self.num_upsamplers = len(boc) - 1
+        self.class_embedding = None
         self.in_channels = in_channels
         self.sample_size = sample_size
         temb = boc[0] * 4
@@ -301,9 +305,12 @@ class UNet2DConditionModel(nn.Module):
         for i in range(nb):
             in_c, out_c = out_c, boc[i]
             last = i == nb - 1
-            cls = DownBlock2D if last else CrossAttnDownBlock2D
+            # diffusers' down_block_types: default (CrossAttnDownBlock2D x3, DownBlock2D); all-DownBlock2D is the only form the
+            # reference's SketchEncoder.forward can execute (it calls the blocks without encoder_hidden_states)
+            plain = last if down_block_types is None else down_block_types[i] == "DownBlock2D"
+            cls = DownBlock2D if plain else CrossAttnDownBlock2D
             self.down_blocks.append(cls(in_c, out_c, temb, g, layers_per_block, not last,
-                                        None if last else attn_cfg(i)))
+                                        None if plain else attn_cfg(i)))
 
         self.up_blocks = nn.ModuleList()
         rev = boc[::-1]

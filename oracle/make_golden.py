@@ -202,8 +202,32 @@ def run_reference_teacher(name, steps, guidance_scale=7.5, seed=port.SAMPLE_SEED
     }
 
 
+def run_reference_sketch_encoder(name="tiny21"):
+    """The reference's OWN SketchEncoder class (modules/sketch_encoder.py, unmodified) over the shim, attention-free down blocks,
+    on a seeded sketch latent at two timesteps."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from modules.sketch_encoder import SketchEncoder
+    enc = port.make_sketch_encoder(name, cls=SketchEncoder)
+    gen = torch.Generator().manual_seed(port.SAMPLE_SEED + 11)
+    L = enc.config.sample_size
+    x = torch.randn(2, 4, L, L, generator=gen)
+    outs = {}
+    with torch.no_grad():
+        for t in (0, 500):
+            outs[t] = [tuple(m.clone() for m in tup) for tup in enc(x, t).sample]
+    return {"config": name, "x": x, "timesteps": [0, 500], "res_samples": outs, "weight_seed": port.WEIGHT_SEED + 3,
+            "source": "reference modules/sketch_encoder.py (SketchEncoder, down_block_types all DownBlock2D) over oracle/diffusers_shim"}
+
+
 def main(argv):
     torch.set_num_threads(os.cpu_count())
+    if argv and argv[0] == "sketch_encoder":
+        blob = run_reference_sketch_encoder()
+        path = os.path.join(ROOT, "tests", "golden", "tiny21_sketch_encoder.pt")
+        torch.save(blob, path)
+        print("sketch encoder fixture ->", path, [tuple(m.shape) for tup in blob["res_samples"][0] for m in tup])
+        return
     if argv and argv[0] == "teacher":
         for name, steps in zip(argv[1::3], argv[2::3]):
             blob = run_reference_teacher(name, int(steps))

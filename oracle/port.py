@@ -347,6 +347,42 @@ def make_sat(unet, cls=SatMixinOracle, seed=WEIGHT_SEED + 2):
     return sat
 
 
+# --------------------------------------------------------------------------------------------------
+# Sketch feature encoder  (/root/reference/modules/sketch_encoder.py:11-98)
+# --------------------------------------------------------------------------------------------------
+ENCODER_BLOCKS = ("DownBlock2D",) * 4
+
+
+def make_sketch_encoder(name="tiny", seed=WEIGHT_SEED + 3, cls=None):
+    """Seeded SketchEncoder-shaped model: the named UNet topology with attention-free down blocks -- the only form whose
+    forward the reference can execute (sketch_encoder.py:93-95 calls the blocks without encoder_hidden_states).
+    cls: the reference's own ``SketchEncoder`` class (same constructor) or None for the shim UNet."""
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    enc = (cls or UNet2DConditionModel)(**dict(CONFIGS[name], down_block_types=ENCODER_BLOCKS))
+    torch.random.set_rng_state(g)
+    return enc.eval()
+
+
+@torch.no_grad()
+def sketch_encoder_forward(enc, sample, timestep):
+    """sketch_encoder.py:50-98 restated: time embedding, conv_in, the down blocks; returns the list of per-block res_samples
+    tuples (the reference wraps it in UNet2DConditionOutput(sample=...))."""
+    t = timestep
+    if not torch.is_tensor(t):
+        t = torch.tensor([t], dtype=torch.long, device=sample.device)      # :59-66
+    elif t.dim() == 0:
+        t = t[None].to(sample.device)
+    t = t.expand(sample.shape[0])                                          # :71
+    emb = enc.time_embedding(enc.time_proj(t).to(dtype=enc.dtype))         # :73-79
+    sample = enc.conv_in(sample)                                           # :92
+    out = []
+    for blk in enc.down_blocks:                                            # :95-98
+        sample, res = blk(hidden_states=sample, temb=emb)
+        out.append(res)
+    return out
+
+
 def make_res_samples(unet, batch, seed=SAMPLE_SEED + 7, size=None):
     """Synthetic SketchEncoder output (modules/sketch_encoder.py:93-98): one tuple of feature maps per down block --
     (resnet/attn out) x layers_per_block (+ the downsampled map for all but the last block)."""

@@ -89,6 +89,10 @@ def lib():
     h.s2i_unet_set_sat_scale.argtypes = [vp, C.c_float, vp]
     h.s2i_unet_debug.argtypes = [vp, C.c_int]
     h.s2i_unet_debug_get.argtypes = [vp, C.c_char_p, fp, C.POINTER(C.c_longlong), ip, ip, ip, ip]
+    h.s2i_sketch_encoder_create.argtypes = [C.POINTER(UNetConfig), C.POINTER(vp)]
+    h.s2i_sketch_encoder_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]
+    h.s2i_sketch_encoder_num_res_samples.argtypes = [vp]
+    h.s2i_sketch_encoder_res_sample.argtypes = [vp, C.c_int, fp, C.POINTER(C.c_longlong), ip, ip, ip, ip]
     h.s2i_unet_arena_bytes.argtypes = [vp]
     h.s2i_unet_arena_bytes.restype = C.c_longlong
     ll, f = C.POINTER(C.c_longlong), C.c_float

@@ -122,6 +122,34 @@ int s2i_unet_create(const s2i_unet_config* c, s2i_unet** out) {
     return 0;
 }
 
+int s2i_sketch_encoder_create(const s2i_unet_config* c, s2i_unet** out) {
+    int rc = s2i_unet_create(c, out);
+    if (rc != 0) return rc;
+    (*out)->impl->cfg.encoder_only = true;
+    return 0;
+}
+
+int s2i_sketch_encoder_forward(s2i_unet* u, const float* x, int B, int H, int W, float t, void* cuda_stream) {
+    if (!u || !x) return s2i::set_error(S2I_ERR_ARG, "s2i_sketch_encoder_forward: null argument");
+    if (!u->impl->cfg.encoder_only) return s2i::set_error(S2I_ERR_STATE, "s2i_sketch_encoder_forward: not a sketch encoder");
+    return u->impl->forward(x, B, H, W, t, nullptr, nullptr, false, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int s2i_sketch_encoder_num_res_samples(s2i_unet* u) {
+    if (!u) return s2i::set_error(S2I_ERR_ARG, "s2i_sketch_encoder_num_res_samples: null engine");
+    return (int)u->impl->res_samples.size();
+}
+
+int s2i_sketch_encoder_res_sample(s2i_unet* u, int k, float** ptr, long long* pixel_stride, int* B, int* H, int* W, int* C) {
+    if (!u || !ptr || !pixel_stride || !B || !H || !W || !C) return s2i::set_error(S2I_ERR_ARG, "s2i_sketch_encoder_res_sample: null argument");
+    if (k < 0 || k >= (int)u->impl->res_samples.size())
+        return s2i::set_error(S2I_ERR_ARG, "s2i_sketch_encoder_res_sample: index %d outside the %d maps of the last forward", k,
+                              (int)u->impl->res_samples.size());
+    const s2i::F32& t = u->impl->res_samples[k];
+    *ptr = t.p; *pixel_stride = t.ld; *B = t.B; *H = t.H; *W = t.W; *C = t.C;
+    return 0;
+}
+
 void s2i_unet_destroy(s2i_unet* u) {
     if (!u) return;
     delete u->impl;

@@ -366,7 +366,7 @@ int UNet::load(const std::map<std::string, HostParam>& params) {
         const std::string pre = "down_blocks." + std::to_string(i);
         for (int j = 0; j < cfg.layers; ++j) {
             if (!load_res(pre + ".resnets." + std::to_string(j), j == 0 ? ch : boc[i], boc[i])) return fail("down resnet");
-            if (i < 3 && !load_tfm(pre + ".attentions." + std::to_string(j), boc[i], cfg.heads[i])) return fail("down attn");
+            if (i < 3 && !cfg.encoder_only && !load_tfm(pre + ".attentions." + std::to_string(j), boc[i], cfg.heads[i])) return fail("down attn");
         }
         ch = boc[i];
         if (i < 3) {
@@ -376,11 +376,13 @@ int UNet::load(const std::map<std::string, HostParam>& params) {
         }
     }
     // mid
+    if (!cfg.encoder_only) {
     if (!load_res("mid_block.resnets.0", boc[3], boc[3])) return fail("mid");
     if (!load_tfm("mid_block.attentions.0", boc[3], cfg.heads[3])) return fail("mid");
     if (!load_res("mid_block.resnets.1", boc[3], boc[3])) return fail("mid");
+    }
     // up path
-    {
+    if (!cfg.encoder_only) {
         int rev[4] = {boc[3], boc[2], boc[1], boc[0]};
         int out_c = rev[0];
         for (int i = 0; i < 4; ++i) {
@@ -402,8 +404,10 @@ int UNet::load(const std::map<std::string, HostParam>& params) {
             }
         }
     }
-    if (!L.norm("conv_norm_out", boc[0], 1e-5f, norm_out_)) return fail("conv_norm_out");
-    if (!L.conv3("conv_out", cfg.out_ch, boc[0], conv_out_, false, true)) return fail("conv_out");
+    if (!cfg.encoder_only) {
+        if (!L.norm("conv_norm_out", boc[0], 1e-5f, norm_out_)) return fail("conv_norm_out");
+        if (!L.conv3("conv_out", cfg.out_ch, boc[0], conv_out_, false, true)) return fail("conv_out");
+    }
 
     // fused time_emb_proj of every resnet: [sum Cout][temb_dim]
     temb_all_.N = temb_total;
@@ -1115,8 +1119,11 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
     if (!dry_ && !time_ready_) S2I_TRY(prepare_time(t, st_));
 
     // text context as fp16 GEMM operand
-    ctx16_ = new16(B, 1, cfg.ctx_len, cfg.cross_dim);
-    if (!reuse_kv_) RUN(cast2d(ctx_, cfg.cross_dim, (long)B * cfg.ctx_len, cfg.cross_dim, 1.f, ctx16_.p, ctx16_.ld, st_));
+    const bool enc = cfg.encoder_only;
+    if (!enc) {
+        ctx16_ = new16(B, 1, cfg.ctx_len, cfg.cross_dim);
+        if (!reuse_kv_) RUN(cast2d(ctx_, cfg.cross_dim, (long)B * cfg.ctx_len, cfg.cross_dim, 1.f, ctx16_.p, ctx16_.ld, st_));
+    }
 
     // Up-path concat buffers, planned before anything runs: the k-th up resnet reads cat([h, skip]) (diffusers
     // UpBlock2D / CrossAttnUpBlock2D), skip = the (K-1-k)-th tensor the down path pushed.  Both producers write straight
@@ -1124,7 +1131,7 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
     const int K = 4 * (cfg.layers + 1);
     std::vector<F32> cats(K);
     std::vector<int> cat_h(K);
-    {
+    if (!enc) {
         std::vector<int> sC, sH, sW;                  // skip channels / spatial size, push order
         int hh = H, ww = W;
         sC.push_back(boc[0]); sH.push_back(hh); sW.push_back(ww);
@@ -1144,7 +1151,9 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
             }
     }
     // skip n (push order) is the second half of cats[K - 1 - n]
-    auto reserve_skip = [&](int n) { reserve(cats[K - 1 - n], cat_h[K - 1 - n], cats[K - 1 - n].C - cat_h[K - 1 - n]); };
+    auto reserve_skip = [&](int n) {
+        if (!enc) reserve(cats[K - 1 - n], cat_h[K - 1 - n], cats[K - 1 - n].C - cat_h[K - 1 - n]);
+    };
 
     // conv_in (im2col GEMM, K = 9*in_ch padded to 64)
     F32 x = new32(B, H, W, cfg.in_ch);
@@ -1166,7 +1175,7 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
             if (i == 3) reserve_skip((int)skips_.size());        // no transformer follows: the resnet output is the skip
             S2I_TRY(resblock(ri++, h, o));
             h = o;
-            if (i < 3) {
+            if (i < 3 && !enc) {
                 reserve_skip((int)skips_.size());
                 S2I_TRY(transformer(ti++, h, o));
                 h = o;
@@ -1185,6 +1194,12 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
             taps[i] = h;
         }
         if (keep_debug) debug["down" + std::to_string(i)] = h;
+    }
+    if (enc) {
+        // sketch_encoder.py:93-98: the forward ends here; res_samples = everything the down blocks pushed
+        res_samples.assign(skips_.begin() + 1, skips_.end());
+        if (stats_off_ > stats_cap_) return set_error(S2I_ERR_STATE, "GroupNorm statistics arena overflow");
+        return 0;
     }
     // ---- mid
     {
@@ -1386,6 +1401,7 @@ int UNet::forward(const float* x_nchw, int B, int H, int W, float t, const float
     kv_cache_B_ = B;
     if (!reuse_kv_) ++kv_gen_;                         // this forward rewrites the cached context K/V projections
     if (H % 8 || W % 8) return set_error(S2I_ERR_ARG, "unet: latent H, W must be multiples of 8 (got %d x %d)", H, W);
+    if (cfg.encoder_only && save_for_backward) return set_error(S2I_ERR_ARG, "sketch encoder: forward only");
     st_ = st;
     B_ = B; H_ = H; W_ = W;
     ctx_ = ctx;

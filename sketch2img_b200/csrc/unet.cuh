@@ -22,6 +22,10 @@ struct UNetConfig {
     int cross_dim = 768;
     int sample_size = 64;
     int ctx_len = 77;
+    // SketchEncoder (modules/sketch_encoder.py): conv_in + time embedding + four attention-free down blocks, forward stops
+    // after the down path and hands out every block's res_samples.  The reference's forward calls the down blocks without
+    // encoder_hidden_states (:93-95), which only executes for blocks without cross-attention (DownBlock2D).
+    bool encoder_only = false;
 };
 
 struct HostParam {
@@ -174,6 +178,9 @@ class UNet {
 
     // The 9 taps of the last forward (NHWC fp32), hook order of latent_predictor.py:63-80.
     F32 taps[9];
+    // encoder_only: the res_samples of the last forward in block order (sketch_encoder.py:93-96):
+    // per down block its `layers` resnet outputs, then the downsampled map (all but the last block)
+    std::vector<F32> res_samples;
     // Named intermediates of the last forward (debugging / parity bisecting).
     std::map<std::string, F32> debug;
     bool keep_debug = false;

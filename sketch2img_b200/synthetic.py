@@ -122,6 +122,29 @@ def unet_state_dict(cfg, seed=1138):
     return sd
 
 
+def sketch_encoder_state_dict(cfg, seed=1140):
+    """Randomly initialised SketchEncoder (modules/sketch_encoder.py): conv_in, time embedding and the down path of the
+    topology with attention-free down blocks."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    for kind, name, dims in _topology(cfg):
+        if not name.startswith(("conv_in", "time_embedding", "down_blocks")) or ".attentions." in name:
+            continue
+        if kind == "norm":
+            sd[name + ".weight"] = torch.ones(dims[0])
+            sd[name + ".bias"] = torch.zeros(dims[0])
+        elif kind == "conv3":
+            co, ci = dims
+            sd[name + ".weight"] = _uniform(gen, (co, ci, 3, 3), ci * 9)
+            sd[name + ".bias"] = _uniform(gen, (co,), ci * 9)
+        else:
+            n, k, bias, as_conv = dims
+            sd[name + ".weight"] = _uniform(gen, (n, k, 1, 1) if as_conv else (n, k), k)
+            if bias:
+                sd[name + ".bias"] = _uniform(gen, (n,), k)
+    return sd
+
+
 def lgp_input_dim(cfg, num_pos_layers=9):
     boc = cfg["block_out_channels"]
     return boc[0] + boc[1] + boc[2] + 3 * boc[3] + boc[3] + boc[2] + boc[1] + 4 + 4 * num_pos_layers

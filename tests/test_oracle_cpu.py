@@ -192,3 +192,41 @@ def test_fp16_operand_floor_of_one_forward():
         e_wa = rel(u16(x, torch.tensor(751), encoder_hidden_states=emb).sample, ref)
     print("oracle one-forward eps error: fp16 weights %.3e, fp16 weights + fp16 GEMM inputs %.3e" % (e_w, e_wa))
     assert 5e-4 < e_w < 1.5e-3 and 8e-4 < e_wa < 2.5e-3
+
+
+# ------------------------------------------------------------------------------------------------ sketch feature encoder
+def test_port_sketch_encoder_matches_golden():
+    """oracle/port.py's restatement of SketchEncoder.forward (sketch_encoder.py:50-98) reproduces the fixture written by the
+    reference's own class bit for bit."""
+    from oracle import port
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    gold = torch.load(os.path.join(GOLD, "tiny21_sketch_encoder.pt"))
+    enc = port.make_sketch_encoder(gold["config"])
+    for t in gold["timesteps"]:
+        got = port.sketch_encoder_forward(enc, gold["x"], t)
+        want = gold["res_samples"][t]
+        assert [len(tup) for tup in got] == [3, 3, 3, 2] == [len(tup) for tup in want]
+        for a, b in zip(got, want):
+            for m, n in zip(a, b):
+                assert torch.equal(m, n)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/modules"), reason="reference sources only exist in the authoring container")
+def test_reference_sketch_encoder_over_shim_equals_port():
+    from oracle import port
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    from modules.sketch_encoder import SketchEncoder
+    ref = port.make_sketch_encoder("tiny21", cls=SketchEncoder)
+    enc = port.make_sketch_encoder("tiny21")
+    x = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        want = ref(x, 321).sample
+    got = port.sketch_encoder_forward(enc, x, 321)
+    for a, b in zip(got, want):
+        for m, n in zip(a, b):
+            assert torch.equal(m, n)
+    # with the standard cross-attention down blocks the reference's forward cannot run (no encoder_hidden_states reaches them)
+    bad = SketchEncoder(**port.CONFIGS["tiny21"])
+    with pytest.raises(Exception):
+        bad(x, 321)

@@ -7,8 +7,7 @@ REFERENCE's latent x_{i-1} (fixtures tests/golden/*_teacher.pt, written by oracl
 reference files) and its x_i is compared with the reference's x_i:
 
   * the scheduler output before guidance (an unguided call from the same state): 1e-3 relative -- north_star's tolerance;
-  * the edge loss (modules/pipeline.py:157): 1e-2 relative (the LGP output carries the forward's 1e-3 operand noise through
-    four train-mode BatchNorm layers);
+  * the edge loss (modules/pipeline.py:157): 1e-3 relative (measured: at most 6.5e-4 over the 52 steps of both fixtures);
   * the length of the guidance update ||x_i - x_ddim||: 2 % (norm-ratio rule, :160);
   * its direction and the latent itself against the yardstick the fixture carries for that very step: the reference's own
     step recomputed with its UNet weights rounded to fp16 -- the precision the reference ships with (app.py:32-38,
@@ -133,7 +132,7 @@ def _teacher_forced(pipe, inputs, fix, label):
         sum(ratios_e) / len(ratios_e), max(ratios_e), sum(ratios_a) / len(ratios_a), max(ratios_a)))
     for (i, t, d_ddim, loss_err, len_ratio, cs, cos16, e, e16), re_, ra in zip(rows, ratios_e, ratios_a):
         assert d_ddim < 1e-3, f"{label} step {i}: scheduler output before guidance off by {d_ddim:.2e}"
-        assert loss_err < 1e-2, f"{label} step {i}: edge loss off by {loss_err:.2e}"
+        assert loss_err < 1e-3, f"{label} step {i}: edge loss off by {loss_err:.2e}"
         assert abs(len_ratio - 1.0) < 2e-2, f"{label} step {i}: guidance step length ratio {len_ratio:.4f}"
         assert re_ < kErrFactor, f"{label} step {i}: latent error {e:.2e} vs fp16-weight yardstick {e16:.2e}"
         assert ra < kErrFactor, f"{label} step {i}: update direction cosine {cs:.5f} vs yardstick {cos16:.5f}"
