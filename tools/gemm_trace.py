@@ -19,7 +19,8 @@ def main():
     lib.s2i_gemm_set_trace.argtypes = [C.c_void_p]
     buf = torch.zeros(4096 * 16, dtype=torch.int64, device="cuda")
     for shape in SHAPES:
-        if shape[0] not in ("lin 320->320 @64 res", "conv 320@64", "qkv 320->1152 @64", "lin 1280->1280 @16 res", "lin 1280->1280 @8 res"):
+        want = sys.argv[1:] or ["lin 320->320 @64 res", "conv 320@64", "qkv 320->1152 @64", "lin 1280->1280 @16 res", "lin 1280->1280 @8 res"]
+        if shape[0] not in want:
             continue
         kw, keep = make(shape)
         d = L.GemmDesc(**kw)
@@ -35,11 +36,13 @@ def main():
         t = t[t[:, 0] > 0][:, :16].double()
         t0 = t[:, 0].min()
         rel = t - t0
-        med = rel.median(dim=0).values
-        mx = rel.max(dim=0).values
+        rel[t == 0] = float("nan")
+        med = rel.nanmedian(dim=0).values
+        mx = torch.nan_to_num(rel, nan=0.0).max(dim=0).values
+        t = torch.where(t == 0, torch.full_like(t, float("nan")), t)
         print(f"{shape[0]}: {t.shape[0]} CTAs; first entry -> last exit {mx[9]:.0f} ns")
         print("   median ns from first entry: " + ", ".join(f"{n}={v:.0f}" for n, v in zip(NAMES, med.tolist())))
-        print("   per-CTA medians (from own entry): " + ", ".join(f"{n}={v:.0f}" for n, v in zip(NAMES, (t - t[:, :1]).median(dim=0).values.tolist())))
+        print("   per-CTA medians (from own entry): " + ", ".join(f"{n}={v:.0f}" for n, v in zip(NAMES, (t - t[:, :1]).nanmedian(dim=0).values.tolist())))
 
 
 if __name__ == "__main__":
