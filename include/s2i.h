@@ -188,6 +188,30 @@ int s2i_unet_debug_get(s2i_unet* u, const char* name, float** ptr, long long* ld
 long long s2i_unet_arena_bytes(s2i_unet* u);
 
 /* ---------------------------------------------------------------------------------------------
+ * AutoencoderKL (the SD VAE), the step either side of the sampling loop: `vae.encode(sketch).latent_dist` of
+ * app.py:107-109 (the sketch target of modules/pipeline.py:141-161) and `vae.decode(latents / 0.18215).sample` of
+ * modules/pipeline.py:118 / :163-174 (decode_latents, decode_latents_L).  Weights: host fp32 tensors under their diffusers
+ * names (encoder.*, decoder.*, quant_conv.*, post_quant_conv.*; mid-block attention as group_norm / query / key / value /
+ * proj_attn).  All tensors NCHW fp32 device.
+ *   encode: image [B, in_channels, H, W] (H, W multiples of 8) -> moments [B, 2 latent_channels, H/8, W/8] = (mean | logvar);
+ *           the caller forms DiagonalGaussianDistribution (sample = mean + exp(0.5 clamp(logvar, -30, 20)) * noise).
+ *   decode: latents [B, latent_channels, h, w] -> image [B, out_channels, 8h, 8w].
+ * --------------------------------------------------------------------------------------------- */
+typedef struct s2i_vae_config {
+    int in_channels, out_channels, latent_channels;
+    int block_out_channels[4];
+    int layers_per_block;
+} s2i_vae_config;
+typedef struct s2i_vae s2i_vae;
+int s2i_vae_create(const s2i_vae_config* cfg, s2i_vae** out);
+void s2i_vae_destroy(s2i_vae* v);
+int s2i_vae_load(s2i_vae* v, int n, const char* const* names, const float* const* host_ptrs, const int* ndims,
+                 const long long* shapes);
+int s2i_vae_encode(s2i_vae* v, const float* image, int B, int H, int W, float* moments, void* cuda_stream);
+int s2i_vae_decode(s2i_vae* v, const float* latents, int B, int h, int w, float* image, void* cuda_stream);
+long long s2i_vae_arena_bytes(s2i_vae* v);
+
+/* ---------------------------------------------------------------------------------------------
  * Latent Guidance Predictor: replaces LatentEdgePredictor.forward (modules/latent_predictor.py:37-45), the
  * resize + concat of the taps (modules/pipeline.py:145-151), the edge loss (:155-157) and the LGP part of
  * autograd.grad (:159).  State-dict keys: layers.{0,3,6,9,12}.{weight,bias},

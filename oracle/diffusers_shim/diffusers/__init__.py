@@ -6,6 +6,7 @@ directory's parent on sys.path lets the reference's own files run UNMODIFIED on 
 oracle/make_golden.py and SURVEY.md section 8(c).  Nothing under sketch2img_b200/ imports this.
 """
 from .models.unet_2d_condition import UNet2DConditionModel  # noqa: F401
+from .models.vae import AutoencoderKL  # noqa: F401
 from .schedulers import DDIMScheduler, DPMSolverMultistepScheduler  # noqa: F401
 from .pipeline_sd import StableDiffusionPipeline  # noqa: F401
 

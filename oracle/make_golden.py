@@ -220,8 +220,38 @@ def run_reference_sketch_encoder(name="tiny21"):
             "source": "reference modules/sketch_encoder.py (SketchEncoder, down_block_types all DownBlock2D) over oracle/diffusers_shim"}
 
 
+def run_reference_vae(name="tiny"):
+    """Either side of the loop with the reference's own code where it has any: the sketch target as app.py:107-109 forms it
+    (``vae.encode(img).latent_dist`` -- the posterior's moments are stored, its ``sample()`` draws from the global RNG) and the
+    reference's ``AntiGradientPipeline.decode_latents_L`` (modules/pipeline.py:163-174, unmodified) on a seeded latent."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from modules.pipeline import AntiGradientPipeline
+    vae = port.make_vae(name)
+    gen = torch.Generator().manual_seed(port.SAMPLE_SEED + 21)
+    S = vae.config.sample_size
+    img = torch.rand(1, 1, S, S, generator=gen).round()                  # a binary "sketch" like app.py's sketchpad image
+    img = (torch.tile(img, (1, 3, 1, 1)) - 0.5) / 0.5                    # app.py:27-30, :108: ToTensor / Normalize(0.5, 0.5), 3 channels
+    lat = torch.randn(1, 4, S // 8, S // 8, generator=gen) * 0.18215 * 4
+    with torch.no_grad():
+        dist = vae.encode(img).latent_dist
+        pipe = AntiGradientPipeline(unet=port.make_unet("tiny"), scheduler=port.make_scheduler())
+        pipe.vae = vae
+        image_L = pipe.decode_latents_L(lat)
+        decoded = vae.decode(lat / 0.18215).sample
+    return {"config": name, "image": img, "moments": dist.parameters.clone(), "latents": lat, "decoded": decoded,
+            "image_L": torch.from_numpy(image_L.copy()), "weight_seed": port.WEIGHT_SEED + 4,
+            "source": "oracle/diffusers_shim AutoencoderKL + reference modules/pipeline.py decode_latents_L"}
+
+
 def main(argv):
     torch.set_num_threads(os.cpu_count())
+    if argv and argv[0] == "vae":
+        blob = run_reference_vae()
+        path = os.path.join(ROOT, "tests", "golden", "tiny_vae.pt")
+        torch.save(blob, path)
+        print("vae fixture ->", path, tuple(blob["moments"].shape), tuple(blob["decoded"].shape), blob["image_L"].shape, blob["image_L"].float().mean())
+        return
     if argv and argv[0] == "sketch_encoder":
         blob = run_reference_sketch_encoder()
         path = os.path.join(ROOT, "tests", "golden", "tiny21_sketch_encoder.pt")

@@ -383,6 +383,30 @@ def sketch_encoder_forward(enc, sample, timestep):
     return out
 
 
+# --------------------------------------------------------------------------------------------------
+# VAE either side of the loop  (/root/reference/app.py:107-109, modules/pipeline.py:118, :163-174)
+# --------------------------------------------------------------------------------------------------
+def make_vae(name="tiny", seed=WEIGHT_SEED + 4):
+    """Seeded AutoencoderKL (oracle/diffusers_shim): "sd" = the SD VAE topology, "tiny" = the same structure, narrow."""
+    from diffusers.models.vae import SD_VAE_CONFIG, TINY_VAE_CONFIG, AutoencoderKL
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    vae = AutoencoderKL(**(SD_VAE_CONFIG if name == "sd" else TINY_VAE_CONFIG))
+    torch.random.set_rng_state(g)
+    return vae.eval()
+
+
+def decode_latents_L(vae, latents):
+    """pipeline.py:163-174 restated: decode, map to [0, 1], zero everything below 0.5, uint8 HWC."""
+    import numpy as np
+    image = vae.decode(1 / 0.18215 * latents).sample
+    image = (image / 2 + 0.5).clamp(0, 1)
+    image = image.detach().cpu().permute(0, 2, 3, 1).float().numpy()
+    image[image < 0.5] = 0
+    image = image.squeeze(0) * 255
+    return image.astype(np.uint8)
+
+
 def make_res_samples(unet, batch, seed=SAMPLE_SEED + 7, size=None):
     """Synthetic SketchEncoder output (modules/sketch_encoder.py:93-98): one tuple of feature maps per down block --
     (resnet/attn out) x layers_per_block (+ the downsampled map for all but the last block)."""

@@ -44,6 +44,12 @@ class UNetConfig(C.Structure):
                 ("sample_size", C.c_int), ("ctx_len", C.c_int)]
 
 
+class VaeConfig(C.Structure):
+    """Mirror of ``s2i_vae_config`` (include/s2i.h)."""
+    _fields_ = [("in_channels", C.c_int), ("out_channels", C.c_int), ("latent_channels", C.c_int),
+                ("block_out_channels", C.c_int * 4), ("layers_per_block", C.c_int)]
+
+
 def lib():
     """Load (building in-tree first if only sources are present) and return the ctypes handle."""
     global _lib
@@ -93,6 +99,14 @@ def lib():
     h.s2i_sketch_encoder_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]
     h.s2i_sketch_encoder_num_res_samples.argtypes = [vp]
     h.s2i_sketch_encoder_res_sample.argtypes = [vp, C.c_int, fp, C.POINTER(C.c_longlong), ip, ip, ip, ip]
+    h.s2i_vae_create.argtypes = [C.POINTER(VaeConfig), C.POINTER(vp)]
+    h.s2i_vae_destroy.argtypes = [vp]
+    h.s2i_vae_destroy.restype = None
+    h.s2i_vae_load.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(vp), ip, C.POINTER(C.c_longlong)]
+    h.s2i_vae_encode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    h.s2i_vae_decode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    h.s2i_vae_arena_bytes.argtypes = [vp]
+    h.s2i_vae_arena_bytes.restype = C.c_longlong
     h.s2i_unet_arena_bytes.argtypes = [vp]
     h.s2i_unet_arena_bytes.restype = C.c_longlong
     ll, f = C.POINTER(C.c_longlong), C.c_float

@@ -1129,7 +1129,7 @@ __global__ void __launch_bounds__(256) zero_insert2x_kernel(const float* __restr
 }
 
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict__ x, long ldx, int B, int H, int W,
-                                                        int C, int stride, int Ho, int Wo, __half* __restrict__ col,
+                                                        int C, int stride, int pad, int Ho, int Wo, __half* __restrict__ col,
                                                         long ldcol) {
     pdl_wait();
     pdl_launch();
@@ -1143,8 +1143,8 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict_
             const int ox = (int)(pix % Wo);
             const int oy = (int)((pix / Wo) % Ho);
             const int b = (int)(pix / ((long)Wo * Ho));
-            const int iy = oy * stride + tap / 3 - 1;
-            const int ix = ox * stride + tap % 3 - 1;
+            const int iy = oy * stride + tap / 3 - pad;
+            const int ix = ox * stride + tap % 3 - pad;
             if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long)b * H + iy) * W + ix) * ldx + c];
         }
         col[idx] = __float2half_rn(v);
@@ -1587,11 +1587,14 @@ int zero_insert2x(const float* d, long ldd, int B, int Ho, int Wo, int C, void* 
 }
 
 int im2col3x3(const float* x, long ldx, int B, int H, int W, int C, int stride, void* col16, long ldcol,
-              cudaStream_t st) {
+              cudaStream_t st, int pad) {
     S2I_REQ(stride == 1 || stride == 2, "im2col3x3: stride");
-    const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+    S2I_REQ(pad == 1 || (pad == 0 && stride == 2), "im2col3x3: pad 1, or the VAE's right / bottom padding (pad 0, stride 2)");
+    // pad 1: symmetric (UNet).  pad 0: the window of output (oy, ox) starts at (2 oy, 2 ox) and the input is padded by one row /
+    // column at the bottom / right only (diffusers Downsample2D(padding=0): F.pad(x, (0, 1, 0, 1)) then conv stride 2)
+    const int Ho = pad ? (H + 2 - 3) / stride + 1 : (H + 1 - 3) / 2 + 1, Wo = pad ? (W + 2 - 3) / stride + 1 : (W + 1 - 3) / 2 + 1;
     S2I_REQ(ldcol >= 9L * C, "im2col3x3: ldcol too small");
-    S2I_LAUNCH((im2col3x3_kernel), grid_for((long)B * Ho * Wo * ldcol, 256), 256, 0, st, x, ldx, B, H, W, C, stride, Ho, Wo,
+    S2I_LAUNCH((im2col3x3_kernel), grid_for((long)B * Ho * Wo * ldcol, 256), 256, 0, st, x, ldx, B, H, W, C, stride, pad, Ho, Wo,
                                                                               (__half*)col16, ldcol);
     S2I_LAUNCH_CHECK();
     return 0;

@@ -62,7 +62,9 @@ int sumpool2x(const float* d, long ldd, int B, int H, int W, int C, float* dx, l
 // zero-insertion (adjoint geometry of a stride-2 conv): d fp32 [B,Ho,Wo,C] -> out16 [B,2Ho,2Wo,C], d at even sites
 int zero_insert2x(const float* d, long ldd, int B, int Ho, int Wo, int C, void* out16, long ld16, cudaStream_t st);
 // 3x3 patches (pad 1, given stride): x fp32 [B,H,W,C] -> col16 [B*Ho*Wo][ldcol], column = tap*C + c, zero padded
-int im2col3x3(const float* x, long ldx, int B, int H, int W, int C, int stride, void* col16, long ldcol, cudaStream_t st);
+// pad = 0 (stride 2 only): padding on the bottom / right side only, the VAE encoder's downsampler
+int im2col3x3(const float* x, long ldx, int B, int H, int W, int C, int stride, void* col16, long ldcol, cudaStream_t st,
+              int pad = 1);
 // NCHW fp32 <-> NHWC fp32 (latents in/out of the engine; 4 channels padded to ldn)
 int nchw_to_nhwc(const float* src, int B, int C, int H, int W, float* dst, long ldn, cudaStream_t st);
 int nhwc_to_nchw(const float* src, long ldn, int B, int C, int H, int W, float* dst, cudaStream_t st);

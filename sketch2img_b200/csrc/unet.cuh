@@ -73,7 +73,7 @@ struct ResBlock {
     Conv3 c1, c2;
     Lin sc;            // 1x1 shortcut when Cin != Cout
     bool has_sc = false;
-    int temb_off = 0;  // offset of this block's time_emb_proj slice in the fused projection
+    int temb_off = 0;  // offset of this block's time_emb_proj slice in the fused projection (< 0: no time embedding, VAE)
     int Cin = 0, Cout = 0;
 };
 // Injected sketch attention of one transformer block (reference: AttnModule, modules/sketch_guided_attn.py:46-132):
@@ -198,7 +198,7 @@ class UNet {
     // saw after its own last forward before it reuses the cache (any other forward in between overwrote it).
     long kv_generation() const { return kv_gen_; }
 
-  private:
+  protected:      // the VAE engine (vae.cu) builds on the same arena / GEMM / GroupNorm / ResBlock / attention plumbing
     // parameters
     Lin conv_in_;       // as im2col GEMM: w [C0][64]
     Conv3 conv_in_d_;   // dgrad form
@@ -249,7 +249,7 @@ class UNet {
     bool dest_set_ = false;
     H16 new16(int B, int H, int W, int C);
     double* new_stats();
-    template <class T> T* dalloc(size_t n);
+    template <class T> T* dalloc(size_t n) { return static_cast<T*>(arena_.alloc(n * sizeof(T))); }
 
     int k(int rc) { return rc; }
     int gemm(const H16& a, bool spatial, int taps, const __half* w, long w_ld, int N, int Kc, const float* bias,

@@ -230,3 +230,21 @@ def test_reference_sketch_encoder_over_shim_equals_port():
     bad = SketchEncoder(**port.CONFIGS["tiny21"])
     with pytest.raises(Exception):
         bad(x, 321)
+
+
+# ------------------------------------------------------------------------------------------------ VAE either side of the loop
+def test_vae_fixture_is_what_the_oracle_computes():
+    """tests/golden/tiny_vae.pt: posterior moments / decoded image of the shim AutoencoderKL and the uint8 image the
+    reference's decode_latents_L (pipeline.py:163-174) makes of the same latent; the port's restatement reproduces it."""
+    from oracle import port
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    gold = torch.load(os.path.join(GOLD, "tiny_vae.pt"))
+    vae = port.make_vae(gold["config"])
+    with torch.no_grad():
+        assert torch.equal(vae.encode(gold["image"]).latent_dist.parameters, gold["moments"])
+        assert torch.equal(vae.decode(gold["latents"] / 0.18215).sample, gold["decoded"])
+        img = torch.from_numpy(port.decode_latents_L(vae, gold["latents"]))
+    assert torch.equal(img, gold["image_L"]) and img.dtype == torch.uint8 and ((img == 0) | (img >= 127)).all()
+    keys = list(vae.state_dict().keys())
+    assert "encoder.down_blocks.0.resnets.0.norm1.weight" in keys and "decoder.mid_block.attentions.0.proj_attn.bias" in keys
+    assert "quant_conv.weight" in keys and "encoder.down_blocks.2.downsamplers.0.conv.weight" in keys
