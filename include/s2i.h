@@ -244,6 +244,21 @@ int s2i_lgp_loss_backward(s2i_lgp* l, const float* target, float* const* tap_gra
 int s2i_lgp_loss_backward_cond(s2i_lgp* l, const float* target, float* const* tap_grads, float* loss, float* grad_scale,
                                void* cuda_stream);
 
+/* LGP training step (reference trainer.py:228-252: UNet forward on noised latents, taps resized and
+ * concatenated, LatentEdgePredictor forward, MSE against the sketch latents, backward, optimizer step).
+ *   forward_taps_batch: LatentEdgePredictor.forward as the trainer calls it -- B latents (no CFG pairs), BatchNorm batch
+ *     statistics over all B * L * L rows, noise_level NCHW fp32 [B][4][L][L] = sqrt(1 - alpha_bar_t[b]) * noise[b] (trainer.py:197-204).
+ *   train_step: loss = mean((LGP - target)^2) over [B][output_dim][L][L] (device float[1]); gradients of every Linear weight /
+ *     bias and BatchNorm weight / bias (tcgen05 wgrad GEMMs, fixed-order sums); one AdamW update (torch.optim.AdamW's rule;
+ *     the 8-bit state quantisation of the reference's bitsandbytes AdamW8bit is not reproduced) of the fp32 masters, after which
+ *     every forward uses the new weights.  step counts from 1.
+ *   get_param: a parameter's fp32 master by its state-dict name ("layers.0.weight", "layers.2.bias", ...) to host memory. */
+int s2i_lgp_forward_taps_batch(s2i_lgp* l, const float* const* taps, const int* sizes, const int* channels, int B, int L,
+                               const float* noise_level, void* cuda_stream);
+int s2i_lgp_train_step(s2i_lgp* l, const float* target, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                       float* loss, void* cuda_stream);
+int s2i_lgp_get_param(s2i_lgp* l, const char* name, float* host, long long n);
+
 /* ---------------------------------------------------------------------------------------------
  * CFG combine + DDIM step (modules/pipeline.py:100-104; diffusers DDIMScheduler.step, eta = 0) and the
  * norm-ratio guidance update (modules/pipeline.py:160-161).  eps / dx: [2S][n] ordered (uncond_s, cond_s).

@@ -117,6 +117,9 @@ def lib():
     h.s2i_lgp_set_grad_rounding.argtypes = [vp, C.c_int]
     h.s2i_lgp_forward_taps.argtypes = [vp, C.POINTER(vp), ip, ip, C.c_int, C.c_int, vp, f, C.c_int, vp]
     h.s2i_lgp_forward_nchw.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    h.s2i_lgp_forward_taps_batch.argtypes = [vp, C.POINTER(vp), ip, ip, C.c_int, C.c_int, vp, vp]
+    h.s2i_lgp_train_step.argtypes = [vp, vp, f, f, f, f, f, C.c_int, vp, vp]
+    h.s2i_lgp_get_param.argtypes = [vp, C.c_char_p, vp, C.c_longlong]
     h.s2i_lgp_output.argtypes = [vp, vp, vp]
     h.s2i_lgp_loss_backward.argtypes = [vp, vp, C.POINTER(vp), vp, C.POINTER(f), vp]
     h.s2i_lgp_loss_backward_cond.argtypes = [vp, vp, C.POINTER(vp), vp, C.POINTER(f), vp]

@@ -9,6 +9,7 @@
 namespace s2i {
 
 int pack_linear_host(const float* host, int N, int K, __half* w, long w_ld, __half* wd, long wd_ld);   // unet.cu
+int pack_linear_device(const float* dev, int N, int K, __half* w, long w_ld, __half* wd, long wd_ld, cudaStream_t st);   // unet.cu
 
 namespace {
 
@@ -35,7 +36,7 @@ __device__ __forceinline__ void src_index(int dst, float scale, int S, int& i0, 
 // while the feature rows stay in (uncond_s, cond_s) pair order.
 __global__ void __launch_bounds__(256) lgp_features_kernel(TapTable tt, int B, int L, const float* __restrict__ noise,
                                                            float sigma, const float* __restrict__ dsigma, int P, int D,
-                                                           __half* __restrict__ X, long ldX, int smS) {
+                                                           __half* __restrict__ X, long ldX, int smS, int pairs) {
     pdl_wait();
     pdl_launch();
     if (dsigma) sigma = __ldg(dsigma);      // graph-replayed steps read the step's scalars from device memory
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) lgp_features_kernel(TapTable tt, int B, i
                 }
             }
         } else {
-            const int s = b >> 1;     // both CFG halves share the sample's noise level
+            const int s = pairs ? b >> 1 : b;     // both CFG halves share the sample's noise level; training: one per latent
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int cc = col + j - tt.off[9];
@@ -144,16 +145,14 @@ __global__ void __launch_bounds__(256) lgp_features_nchw_kernel(const float* __r
 }
 
 // per (sample, column) sums over R rows.  MODE 0: (h, h^2).  MODE 1: (dy, dy*xhat).
-// Deterministic: every block writes the fp32 partial sums of its `chunk` rows to part [S][chunks][N][2]; the block that
-// arrives last for a sample (self-resetting counter) adds the partials in CHUNK ORDER in double and writes out [S][N][2].
+// Deterministic two-stage reduction: every block writes the fp32 partial sums of its `chunk` rows to part [S][chunks][N][2];
+// bn_sum_kernel adds the partials of a column in a fixed order in double.
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const __half* __restrict__ h, const __half* __restrict__ dy,
                                                         const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                        long R, int N, int chunk, float* __restrict__ part,
-                                                        unsigned int* __restrict__ counter, double* __restrict__ out) {
+                                                        long R, int N, int chunk, float* __restrict__ part) {
     pdl_wait();
     pdl_launch();
-    __shared__ unsigned int is_last;
     const int s = blockIdx.y;
     const long r0 = (long)blockIdx.x * chunk;
     const long r1 = min(R, r0 + chunk);
@@ -165,50 +164,80 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __half* __restrict
             m0 = mean[(long)s * N + c]; m1 = mean[(long)s * N + c + 1];
             q0 = rstd[(long)s * N + c]; q1 = rstd[(long)s * N + c + 1];
         }
-        for (long r = r0; r < r1; ++r) {
-            const long row = (long)s * R + r;
-            const float2 hv = __half22float2(*reinterpret_cast<const __half2*>(h + row * N + c));
-            if (MODE == 0) {
-                a0 += hv.x; a1 += hv.y;
-                b0 += hv.x * hv.x; b1 += hv.y * hv.y;
-            } else {
-                const float2 dv = __half22float2(*reinterpret_cast<const __half2*>(dy + row * N + c));
-                a0 += dv.x; a1 += dv.y;
-                b0 += dv.x * (hv.x - m0) * q0; b1 += dv.y * (hv.y - m1) * q1;
+        constexpr int U = 8;              // rows in flight per thread
+        for (long r = r0; r < r1; r += U) {
+            __half2 hv[U], dv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long row = (long)s * R + (r + u < r1 ? r + u : r0);
+                hv[u] = *reinterpret_cast<const __half2*>(h + row * N + c);
+                if (MODE == 1) dv[u] = *reinterpret_cast<const __half2*>(dy + row * N + c);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (r + u >= r1) break;
+                const float2 x = __half22float2(hv[u]);
+                if (MODE == 0) {
+                    a0 += x.x; a1 += x.y;
+                    b0 += x.x * x.x; b1 += x.y * x.y;
+                } else {
+                    const float2 d = __half22float2(dv[u]);
+                    a0 += d.x; a1 += d.y;
+                    b0 += d.x * (x.x - m0) * q0; b1 += d.y * (x.y - m1) * q1;
+                }
             }
         }
         *reinterpret_cast<float4*>(mine + 2 * c) = make_float4(a0, b0, a1, b1);
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int old = atomicAdd(counter + s, 1u);
-        is_last = (old == gridDim.x - 1) ? 1u : 0u;
-        if (is_last) counter[s] = 0u;        // ready for the next launch
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    const float* base = part + (long)s * gridDim.x * N * 2;
-    const int nchunks = (int)gridDim.x;
-    for (int c = threadIdx.x * 2; c < N; c += blockDim.x * 2) {
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-        int k = 0;
-        for (; k + 8 <= nchunks; k += 8) {      // eight independent loads in flight, added in chunk order
+}
+
+// Second stage: grid (ceil(N / 64), S), 256 threads = 8 warps x 32 column pairs.  Warp w adds chunks w, w + 8, ... (eight loads in
+// flight), the eight warp sums are added in warp order: out [S][N][2] doubles.  With mean_out (forward, train mode) the
+// statistics are finished here too: mean, rstd of the biased variance.
+__global__ void __launch_bounds__(256) bn_sum_kernel(const float* __restrict__ part, int nchunks, long R, int N,
+                                                     double* __restrict__ out, float* __restrict__ mean_out,
+                                                     float* __restrict__ rstd_out) {
+    pdl_wait();
+    pdl_launch();
+    __shared__ double sm[8][32][4];
+    const int s = blockIdx.y;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = (blockIdx.x * 32 + lane) * 2;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    if (c < N) {
+        const float* base = part + (long)s * nchunks * N * 2 + 2 * c;
+        int k = w;
+        for (; k + 56 < nchunks; k += 64) {
             float4 v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(base + ((long)(k + u) * N + c) * 2));
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(base + (long)(k + 8 * u) * N * 2));
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 t0 += (double)v[u].x; t1 += (double)v[u].y; t2 += (double)v[u].z; t3 += (double)v[u].w;
             }
         }
-        for (; k < nchunks; ++k) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(base + ((long)k * N + c) * 2));
+        for (; k < nchunks; k += 8) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(base + (long)k * N * 2));
             t0 += (double)v.x; t1 += (double)v.y; t2 += (double)v.z; t3 += (double)v.w;
         }
+    }
+    sm[w][lane][0] = t0; sm[w][lane][1] = t1; sm[w][lane][2] = t2; sm[w][lane][3] = t3;
+    __syncthreads();
+    if (w == 0 && c < N) {
+        double r[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 4; ++j) r[j] += sm[i][lane][j];
         double* o = out + ((long)s * N + c) * 2;
-        o[0] = t0; o[1] = t1; o[2] = t2; o[3] = t3;
+        o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+        if (mean_out) {
+            for (int j = 0; j < 2; ++j) {
+                const double m = r[2 * j] / (double)R;
+                double var = r[2 * j + 1] / (double)R - m * m;
+                if (var < 0.0) var = 0.0;
+                mean_out[(long)s * N + c + j] = (float)m;
+                rstd_out[(long)s * N + c + j] = (float)(1.0 / sqrt(var + (double)kBnEps));
+            }
+        }
     }
 }
 
@@ -292,7 +321,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
 __global__ void __launch_bounds__(256) lgp_loss_kernel(const __half* __restrict__ out16, const float* __restrict__ target,
                                                        int B, int L, int O, float inv_n, float gscale, int emulate,
                                                        __half* __restrict__ dout, float* __restrict__ part,
-                                                       unsigned int* __restrict__ counter, float* __restrict__ loss) {
+                                                       unsigned int* __restrict__ counter, float* __restrict__ loss, int all) {
     pdl_wait();
     pdl_launch();
     __shared__ float wsum[8];
@@ -306,8 +335,8 @@ __global__ void __launch_bounds__(256) lgp_loss_kernel(const __half* __restrict_
         __align__(16) __half d8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) d8[j] = __float2half_rn(0.f);
-        if (b & 1) {
-            const long s = b >> 1;
+        if (all || (b & 1)) {
+            const long s = all ? b : b >> 1;      // all: the training loss, every latent against its own target (trainer.py:247)
             for (int c = 0; c < O; ++c) {
                 const float diff = __half2float(out16[row * 8 + c]) - target[(s * O + c) * hw + pix];
                 acc += diff * diff;
@@ -318,8 +347,10 @@ __global__ void __launch_bounds__(256) lgp_loss_kernel(const __half* __restrict_
         }
         *reinterpret_cast<uint4*>(dout + row * 8) = *reinterpret_cast<uint4*>(d8);
     }
-    if (!(b & 1)) return;          // uncond rows carry no loss (whole block: b is blockIdx.y)
-    const int s = b >> 1;
+    if (!all && !(b & 1)) return;          // uncond rows carry no loss (whole block: b is blockIdx.y)
+    const int s = all ? 0 : b >> 1;
+    const unsigned int nblk = all ? gridDim.x * gridDim.y : gridDim.x;
+    const unsigned int slot = all ? blockIdx.y * gridDim.x + blockIdx.x : blockIdx.x;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
@@ -327,17 +358,17 @@ __global__ void __launch_bounds__(256) lgp_loss_kernel(const __half* __restrict_
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += wsum[i];
-        part[(long)s * gridDim.x + blockIdx.x] = t;
+        part[(long)s * nblk + slot] = t;
         __threadfence();
         const unsigned int old = atomicAdd(counter + s, 1u);
-        is_last = (old == gridDim.x - 1) ? 1u : 0u;
+        is_last = (old == nblk - 1) ? 1u : 0u;
         if (is_last) counter[s] = 0u;
     }
     __syncthreads();
     if (is_last && threadIdx.x == 0) {
         __threadfence();
         float t = 0.f;
-        for (int k = 0; k < (int)gridDim.x; ++k) t += __ldcg(part + (long)s * gridDim.x + k);
+        for (unsigned int k = 0; k < nblk; ++k) t += __ldcg(part + (long)s * nblk + k);
         loss[s] = t * inv_n;
     }
 }
@@ -558,13 +589,14 @@ __global__ void __launch_bounds__(1024) guidance_norms_kernel(const float* __res
     pdl_wait();
     pdl_launch();
     const int s = blockIdx.y;
-    double a = 0.0, b = 0.0;
+    float fa = 0.f, fb = 0.f;          // a handful of elements per thread in fp32, the tree in double (fp64 units are scarce)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float d = x_old[(long)s * n + i] - x_new[(long)s * n + i];
         const float gq = dx[((long)s * dmul + dadd) * n + i];
-        a += (double)d * (double)d;
-        b += (double)gq * (double)gq;
+        fa += d * d;
+        fb += gq * gq;
     }
+    double a = (double)fa, b = (double)fb;
     __shared__ double sa[32], sb[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -602,6 +634,8 @@ __global__ void __launch_bounds__(256) guidance_apply_kernel(float* __restrict__
         x_new[(long)s * n + i] = __fadd_rn(x_new[(long)s * n + i], __fmul_rn(alpha, gq));
     }
 }
+
+constexpr int kBnChunk = 32;        // rows per block of the BatchNorm column reductions
 
 inline int grid1d(long work, int block = 256, int cap = 148 * 16) {
     long g = (work + block - 1) / block;
@@ -660,6 +694,8 @@ int LGP::load(const std::map<std::string, HostParam>& params) {
         lin_[l].w = static_cast<__half*>(pw);
         lin_[l].wd = static_cast<__half*>(pwd);
         S2I_TRY(pack_linear_host(w, N, K, lin_[l].w, K, lin_[l].wd, wd_ld));
+        master_w_[l] = dvec(w, (size_t)N * K);      // fp32 master (train_step updates it; 19.8 MB in all)
+        if (!master_w_[l]) return set_error(S2I_ERR_OOM, "lgp load: cudaMalloc");
         lin_[l].b = dvec(get(pre + ".bias", N), N);
         if (!lin_[l].b) return set_error(S2I_ERR_ARG, "lgp load: missing %s.bias", pre.c_str());
         if (l < 4) {
@@ -713,7 +749,7 @@ static size_t lgp_ws_bytes(long rows, long ldX, int S) {
     b += (size_t)rows * 8 * 2 * 2;
     b += (size_t)rows * 512 * 2 * 2;
     b += (size_t)S * 512 * 2 * 8 * 8 + (size_t)S * 512 * 4 * 8;
-    b += ((size_t)rows / 128 + (size_t)S + 8) * 512 * 2 * 4 + (size_t)S * 64 + (size_t)rows / 64 * 4 + 4096;   // reduction partials, counters
+    b += ((size_t)rows / kBnChunk + (size_t)S + 8) * 512 * 2 * 4 + (size_t)S * 64 + (size_t)rows / 64 * 4 + 4096;   // reduction partials, counters
     return b + (1u << 20);
 }
 
@@ -733,9 +769,9 @@ int LGP::mlp(cudaStream_t st) {
     double* sums = ws.take<double>((size_t)S * 960 * 2 * 2 + (size_t)S + 1);
     red_counter_ = reinterpret_cast<unsigned int*>(sums + (size_t)S * 960 * 2 * 2);
     S2I_MEMOP(cudaMemsetAsync(sums, 0, ((size_t)S * 960 * 2 * 2 + (size_t)S + 1) * sizeof(double), st));
-    const long nchunks = ceil_div_l(R, 128);
+    const long nchunks = ceil_div_l(R, kBnChunk);
     red_part_ = ws.take<float>((size_t)S * nchunks * 512 * 2);
-    loss_part_ = ws.take<float>((size_t)(B_ / 2 + 1) * (size_t)ceil_div_l((long)L_ * L_, 256));
+    loss_part_ = ws.take<float>((size_t)(B_ + 1) * (size_t)ceil_div_l((long)L_ * L_, 256));
     size_t so = 0;
     for (int l = 0; l < 4; ++l) {
         bsum_[l] = sums + so;
@@ -769,13 +805,18 @@ int LGP::mlp(cudaStream_t st) {
         S2I_TRY(gemm_launch(d, st));
         if (l < 4) {
             if (train_) {
-                dim3 grid((unsigned)ceil_div_l(R, 128), S);
-                S2I_LAUNCH((bn_reduce_kernel<0>), grid, min(256, N / 2), 0, st, h_[l], nullptr, nullptr, nullptr, R, N, 128, red_part_, red_counter_, bsum_[l]);
+                const int nchunks = (int)ceil_div_l(R, kBnChunk);
+                S2I_LAUNCH((bn_reduce_kernel<0>), dim3((unsigned)nchunks, S), min(256, N / 2), 0, st, h_[l], nullptr, nullptr, nullptr, R, N,
+                           kBnChunk, red_part_);
+                S2I_LAUNCH_CHECK();
+                S2I_LAUNCH((bn_sum_kernel), dim3((unsigned)ceil_div(N, 64), S), 256, 0, st, red_part_, nchunks, R, N, bsum_[l], mean_[l],
+                           rstd_[l]);
+                S2I_LAUNCH_CHECK();
+            } else {
+                S2I_LAUNCH((bn_finalize_kernel), ceil_div(S * N, 256), 256, 0, st, bsum_[l], bn_rm_[l], bn_rv_[l], 0, R, N, S, mean_[l],
+                           rstd_[l]);
                 S2I_LAUNCH_CHECK();
             }
-            S2I_LAUNCH((bn_finalize_kernel), ceil_div(S * N, 256), 256, 0, st, bsum_[l], bn_rm_[l], bn_rv_[l], train_ ? 1 : 0, R, N, S,
-                                                                     mean_[l], rstd_[l]);
-            S2I_LAUNCH_CHECK();
             S2I_LAUNCH((bn_apply_kernel), grid1d(rows * (N / 2)), 256, 0, st, h_[l], mean_[l], rstd_[l], bn_[l].g, bn_[l].b, R, N, rows,
                                                                     a_[l]);
             S2I_LAUNCH_CHECK();
@@ -786,9 +827,10 @@ int LGP::mlp(cudaStream_t st) {
 }
 
 int LGP::forward(const LgpTap taps[9], int B, int L, const float* noise, float sigma, bool train, cudaStream_t st,
-                 const float* dsigma, bool taps_sample_major) {
+                 const float* dsigma, bool taps_sample_major, int groups) {
     if (!loaded_) return set_error(S2I_ERR_STATE, "lgp: weights not loaded");
-    if (B % 2 != 0) return set_error(S2I_ERR_ARG, "lgp: batch must hold (uncond, cond) pairs");
+    if (groups == 0 && B % 2 != 0) return set_error(S2I_ERR_ARG, "lgp: batch must hold (uncond, cond) pairs");
+    if (groups != 0 && groups != 1) return set_error(S2I_ERR_ARG, "lgp: statistics groups must be 0 (pairs) or 1 (whole batch)");
     TapTable tt;
     int off = 0;
     for (int k = 0; k < 9; ++k) {
@@ -807,14 +849,14 @@ int LGP::forward(const LgpTap taps[9], int B, int L, const float* noise, float s
         return set_error(S2I_ERR_ARG, "lgp: taps give %d channels (+%d) but input_dim is %d", off, 4 + 4 * P_, D_);
     B_ = B; L_ = L; train_ = train;
     const long rows = (long)B * L * L;
-    groups_ = B / 2;
-    S2I_TRY(ensure(lgp_ws_bytes(rows, ldX_, B / 2)));
+    groups_ = groups == 0 ? B / 2 : 1;
+    S2I_TRY(ensure(lgp_ws_bytes(rows, ldX_, groups_)));
     if (rows * (ldX_ / 8) > 0x7fffffffL) return set_error(S2I_ERR_ARG, "lgp: %ld feature rows exceed the kernel's 32-bit indexing", rows);
     X_ = reinterpret_cast<__half*>(buf_);   // first workspace slot (see mlp())
     int cmax = (int)ldX_ - off;
     for (int k = 0; k < 9; ++k) cmax = taps[k].C > cmax ? taps[k].C : cmax;
     S2I_LAUNCH((lgp_features_kernel), dim3(grid1d(rows * (cmax / 8), 256, 148 * 4), 10), 256, 0, st, tt, B, L, noise, sigma, dsigma, P_, D_, X_, ldX_,
-                                                      taps_sample_major ? B / 2 : 0);
+                                                      taps_sample_major ? B / 2 : 0, groups == 0 ? 1 : 0);
     S2I_LAUNCH_CHECK();
     return mlp(st);
 }
@@ -849,7 +891,7 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
     const long n_elem = (long)O_ * L_ * L_;
     gscale_ = exp2f(ceilf(log2f((float)n_elem)));
     S2I_LAUNCH((lgp_loss_kernel), dim3((unsigned)ceil_div_l((long)L_ * L_, 256), (unsigned)B_), 256, 0, st, out16_, target, B_, L_, O_,
-               1.f / (float)n_elem, gscale_, emulate_fp16_grad ? 1 : 0, dout_, loss_part_, red_counter_ + S, loss);
+               1.f / (float)n_elem, gscale_, emulate_fp16_grad ? 1 : 0, dout_, loss_part_, red_counter_ + S, loss, 0);
     const float qs = emulate_fp16_grad ? gscale_ : 0.f;
     S2I_LAUNCH_CHECK();
 
@@ -888,8 +930,11 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
         // BatchNorm(l-1) + ReLU backward
         const int bl = l - 1;
         if (train_) {
-            dim3 grid((unsigned)ceil_div_l(R, 128), S);
-            S2I_LAUNCH((bn_reduce_kernel<1>), grid, min(256, N / 2), 0, st, h_[bl], o, mean_[bl], rstd_[bl], R, N, 128, red_part_, red_counter_, bbsum_[bl]);
+            const int nchunks = (int)ceil_div_l(R, kBnChunk);
+            S2I_LAUNCH((bn_reduce_kernel<1>), dim3((unsigned)nchunks, S), min(256, N / 2), 0, st, h_[bl], o, mean_[bl], rstd_[bl], R, N,
+                       kBnChunk, red_part_);
+            S2I_LAUNCH_CHECK();
+            S2I_LAUNCH((bn_sum_kernel), dim3((unsigned)ceil_div(N, 64), S), 256, 0, st, red_part_, nchunks, R, N, bbsum_[bl], nullptr, nullptr);
             S2I_LAUNCH_CHECK();
         }
         __half* o2 = bufs[flip ^ 1];
@@ -944,6 +989,180 @@ int LGP::loss_backward(const float* target, float* const tap_grads[9], float* lo
         }
         off += taps_[k].C;
     }
+    return 0;
+}
+
+// ================================================================================================== training step
+namespace {
+
+// AdamW (decoupled weight decay, bias-corrected), torch.optim.AdamW's update rule.  The gradient comes either as fp32 [n]
+// (g32) or as every `gstride`-th double of a column-sum buffer (g64 + goff: bias / BatchNorm-affine gradients); both carry
+// the loss scale `inv_scale` undoes.
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g32,
+                                                    const double* __restrict__ g64, int gstride, int goff, long n, float inv_scale,
+                                                    float lr, float b1, float b2, float eps, float wd, float bc1, float bc2,
+                                                    float* __restrict__ m, float* __restrict__ v) {
+    pdl_wait();       // launched as a programmatic dependent like every kernel of the library
+    pdl_launch();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float g = (g32 ? g32[i] : (float)g64[i * gstride + goff]) * inv_scale;
+        float w = p[i] * (1.f - lr * wd);
+        const float mi = b1 * m[i] + (1.f - b1) * g;
+        const float vi = b2 * v[i] + (1.f - b2) * g * g;
+        m[i] = mi;
+        v[i] = vi;
+        w -= lr / bc1 * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+        p[i] = w;
+    }
+}
+
+}  // namespace
+
+int LGP::train_step(const float* target, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float* loss,
+                    cudaStream_t st) {
+    if (!have_fwd_) return set_error(S2I_ERR_STATE, "lgp: train_step needs a preceding forward");
+    have_fwd_ = false;
+    if (groups_ != 1 || !train_)
+        return set_error(S2I_ERR_STATE, "lgp: train_step needs the whole-batch, train-mode forward (forward_taps with groups = 1)");
+    if (step < 1) return set_error(S2I_ERR_ARG, "lgp: train_step counts steps from 1");
+    const long rows = (long)B_ * L_ * L_;
+    const long R = rows;
+    const long n_elem = (long)B_ * O_ * L_ * L_;
+    gscale_ = exp2f(ceilf(log2f((float)n_elem)));          // loss scale: the fp16 gradients stay in the normal range
+    auto moments = [&](Moment& mo, size_t n) -> int {
+        if (mo.m) return 0;
+        void *a = nullptr, *b = nullptr;
+        if (cudaMalloc(&a, n * sizeof(float)) != cudaSuccess || cudaMalloc(&b, n * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(S2I_ERR_OOM, "lgp: cannot allocate the optimizer state");
+        }
+        owned_.push_back(a);
+        owned_.push_back(b);
+        cudaMemsetAsync(a, 0, n * sizeof(float), st);
+        cudaMemsetAsync(b, 0, n * sizeof(float), st);
+        mo.m = static_cast<float*>(a);
+        mo.v = static_cast<float*>(b);
+        return 0;
+    };
+    for (int l = 0; l < 5; ++l) {
+        const size_t n = (size_t)widths_[l + 1] * widths_[l];
+        if (!grad_w_[l]) {
+            void* q = nullptr;
+            if (cudaMalloc(&q, n * sizeof(float)) != cudaSuccess) {
+                cudaGetLastError();
+                return set_error(S2I_ERR_OOM, "lgp: cannot allocate the weight gradients");
+            }
+            owned_.push_back(q);
+            grad_w_[l] = static_cast<float*>(q);
+        }
+        S2I_TRY(moments(mom_w_[l], n));
+        S2I_TRY(moments(mom_b_[l], widths_[l + 1]));
+        if (l < 4) {
+            S2I_TRY(moments(mom_g_[l], widths_[l + 1]));
+            S2I_TRY(moments(mom_beta_[l], widths_[l + 1]));
+        }
+    }
+    g_prev_kernel = false;
+
+    // loss over every latent (trainer.py:247) and its gradient wrt the MLP output
+    S2I_LAUNCH((lgp_loss_kernel), dim3((unsigned)ceil_div_l((long)L_ * L_, 256), (unsigned)B_), 256, 0, st, out16_, target, B_, L_, O_,
+               1.f / (float)n_elem, gscale_, 0, dout_, loss_part_, red_counter_ + 1, loss, 1);
+    S2I_LAUNCH_CHECK();
+
+    const float inv_scale = 1.f / gscale_;
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    auto adamw = [&](float* p, const float* g32, const double* g64, int gstride, int goff, long n, Moment& mo) -> int {
+        S2I_LAUNCH((adamw_kernel), grid1d(n), 256, 0, st, p, g32, g64, gstride, goff, n, inv_scale, lr, beta1, beta2, eps, weight_decay, bc1,
+                   bc2, mo.m, mo.v);
+        S2I_LAUNCH_CHECK();
+        return 0;
+    };
+    // column sums of a gradient matrix [rows][ld] (bias gradients): the BatchNorm reduction's first stage + fixed-order second
+    double* bias_sums = bsum_[0];             // the forward's statistics are consumed: reuse the [512][2] double buffer
+    auto colsum = [&](const __half* d, int N) -> int {
+        const int nchunks = (int)ceil_div_l(R, kBnChunk);
+        S2I_LAUNCH((bn_reduce_kernel<0>), dim3((unsigned)nchunks, 1), min(256, N / 2), 0, st, d, nullptr, nullptr, nullptr, R, N, kBnChunk,
+                   red_part_);
+        S2I_LAUNCH_CHECK();
+        S2I_LAUNCH((bn_sum_kernel), dim3((unsigned)ceil_div(N, 64), 1), 256, 0, st, red_part_, nchunks, R, N, bias_sums, nullptr, nullptr);
+        S2I_LAUNCH_CHECK();
+        return 0;
+    };
+
+    const __half* d = dout_;        // dZ of the current layer (scaled), [rows][d_ld]
+    long d_ld = 8;
+    __half* bufs[2] = {dA_, dB_};
+    for (int l = 4; l >= 0; --l) {
+        const int No = widths_[l + 1];   // this layer's output width
+        const int Ki = widths_[l];       // this layer's input width
+        const int Np = l == 4 ? 8 : No;  // stored width of dZ (the 4-wide output rows are padded to 8)
+        // ---- weight gradient  dW [No][Ki] = dZ^T A_prev : both operands MN-major (rows are the contraction)
+        {
+            GemmDesc g;
+            g.tag = "gemm_lgp";
+            g.A = d; g.a_mn = 1; g.aC = No; g.aW = (int)rows; g.a_sw = d_ld;
+            g.B = l == 0 ? X_ : a_[l - 1]; g.b_mn = 1; g.bI = Ki; g.bR = (int)rows; g.b_sr = l == 0 ? ldX_ : Ki;
+            g.N = Ki; g.Kc = (int)rows;
+            g.out32 = grad_w_[l]; g.ld32 = Ki;
+            S2I_TRY(gemm_launch(g, st));
+        }
+        // ---- bias gradient = column sums of dZ; update bias and weight
+        S2I_TRY(colsum(d, Np));
+        S2I_TRY(adamw(lin_[l].b, nullptr, bias_sums, 2, 0, No, mom_b_[l]));
+        if (l > 0) {
+            // ---- input gradient d(a_{l-1}) = dZ W_l (with the weights of THIS step: the update of W_l comes after)
+            GemmDesc g;
+            g.tag = "gemm_lgp";
+            g.A = d; g.aC = No; g.aW = (int)rows; g.a_sw = d_ld;
+            g.B = lin_[l].wd; g.bI = No; g.bR = Ki; g.b_sr = (No + 7) / 8 * 8;
+            g.N = Ki; g.Kc = No;
+            __half* o = bufs[0];
+            g.out16 = o; g.ld16 = Ki;
+            S2I_TRY(gemm_launch(g, st));
+            // ---- BatchNorm(l-1): (sum dy, sum dy xhat) give the affine gradients and the input gradient; ReLU mask inside
+            const int bl = l - 1;
+            const int nchunks = (int)ceil_div_l(R, kBnChunk);
+            S2I_LAUNCH((bn_reduce_kernel<1>), dim3((unsigned)nchunks, 1), min(256, Ki / 2), 0, st, h_[bl], o, mean_[bl], rstd_[bl], R, Ki,
+                       kBnChunk, red_part_);
+            S2I_LAUNCH_CHECK();
+            S2I_LAUNCH((bn_sum_kernel), dim3((unsigned)ceil_div(Ki, 64), 1), 256, 0, st, red_part_, nchunks, R, Ki, bbsum_[bl], nullptr, nullptr);
+            S2I_LAUNCH_CHECK();
+            __half* o2 = bufs[1];
+            S2I_LAUNCH((bn_bwd_apply_kernel), grid1d(rows * (Ki / 2)), 256, 0, st, o, h_[bl], mean_[bl], rstd_[bl], bn_[bl].g, bbsum_[bl], 1, R, Ki,
+                       rows, 0.f, o2);
+            S2I_LAUNCH_CHECK();
+            // the affine parameters change only after their old values were used above
+            S2I_TRY(adamw(bn_[bl].b, nullptr, bbsum_[bl], 2, 0, Ki, mom_beta_[bl]));
+            S2I_TRY(adamw(bn_[bl].g, nullptr, bbsum_[bl], 2, 1, Ki, mom_g_[bl]));
+            // dZ_{l-1} lives in bufs[1]; the next layer's dgrad output goes to bufs[0] again
+            d = o2;
+            d_ld = Ki;
+        }
+        S2I_TRY(adamw(master_w_[l], grad_w_[l], nullptr, 0, 0, (long)No * Ki, mom_w_[l]));
+        S2I_TRY(pack_linear_device(master_w_[l], No, Ki, lin_[l].w, Ki, lin_[l].wd, (No + 7) / 8 * 8, st));
+    }
+    return 0;
+}
+
+int LGP::get_param(const std::string& name, float* host, size_t n) {
+    if (!loaded_) return set_error(S2I_ERR_STATE, "lgp: weights not loaded");
+    const float* src = nullptr;
+    size_t have = 0;
+    for (int l = 0; l < 5 && !src; ++l) {
+        const std::string pre = "layers." + std::to_string(3 * l);
+        if (name == pre + ".weight") { src = master_w_[l]; have = (size_t)widths_[l + 1] * widths_[l]; }
+        else if (name == "grad." + pre + ".weight") { src = grad_w_[l]; have = (size_t)widths_[l + 1] * widths_[l]; }   // x grad_scale()
+        else if (name == pre + ".bias") { src = lin_[l].b; have = widths_[l + 1]; }
+        if (l < 4) {
+            const std::string bp = "layers." + std::to_string(3 * l + 2);
+            if (name == bp + ".weight") { src = bn_[l].g; have = widths_[l + 1]; }
+            else if (name == bp + ".bias") { src = bn_[l].b; have = widths_[l + 1]; }
+        }
+    }
+    if (!src) return set_error(S2I_ERR_ARG, "lgp: no trainable parameter named %s", name.c_str());
+    if (have != n) return set_error(S2I_ERR_ARG, "lgp: %s has %zu elements, the buffer %zu", name.c_str(), have, n);
+    S2I_CUDA(cudaDeviceSynchronize());
+    S2I_CUDA(cudaMemcpy(host, src, n * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
 

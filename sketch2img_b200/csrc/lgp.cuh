@@ -32,8 +32,19 @@ class LGP {
     // dsigma (optional, device): overrides `sigma` at run time (graph-replayed steps).
     // taps_sample_major: the taps' batch is ordered [uncond_0.., cond_0..] (the sampler's internal order) instead of
     // (uncond_s, cond_s) pairs; the LGP's own rows stay in pair order either way.
+    // groups: 0 = BatchNorm statistics per (uncond, cond) pair, noise shared by a pair (the sampling path); 1 = statistics over
+    // the whole batch and one noise map per latent (LatentEdgePredictor.forward as the trainer calls it, trainer.py:245)
     int forward(const LgpTap taps[9], int B, int L, const float* noise, float sigma, bool train, cudaStream_t st,
-                const float* dsigma = nullptr, bool taps_sample_major = false);
+                const float* dsigma = nullptr, bool taps_sample_major = false, int groups = 0);
+    // One optimisation step of the LGP on the batch of the last forward(groups = 1, train) (reference: trainer.py:245-252):
+    // loss = mse(LGP(features), target) over every latent, weight / bias / BatchNorm-affine gradients (tcgen05 wgrad GEMMs,
+    // fixed-order column sums), AdamW update of the fp32 master parameters, fp16 operand copies re-packed.
+    // target: NCHW fp32 [B][output_dim][L][L]; loss: device float[1]; step: 1-based count for the bias correction.
+    int train_step(const float* target, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float* loss,
+                   cudaStream_t st);
+    // copy a parameter's fp32 master (state-dict name, e.g. "layers.3.weight") to the host; n = element count.
+    // "grad.layers.N.weight": the weight gradient of the last train_step, multiplied by grad_scale() (tests)
+    int get_param(const std::string& name, float* host, size_t n);
     // Edge loss on the cond half + backward to the taps.  target: NCHW fp32 [samples,4,L,L].
     // tap_grads[k]: NHWC fp32 like tap k, multiplied by grad_scale(); loss: device float [samples].
     // cond_only: only the cond samples' tap gradients are produced (tap_grads[k] then holds `samples` maps, sample s =
@@ -80,6 +91,11 @@ class LGP {
     double* bbsum_[4] = {};      // backward per (sample, column) sums
     float* mean_[4] = {};
     float* rstd_[4] = {};
+    // training (train_step): fp32 masters of the Linear weights, their gradients and the AdamW moments of every parameter
+    float* master_w_[5] = {};
+    float* grad_w_[5] = {};
+    struct Moment { float *m = nullptr, *v = nullptr; };
+    Moment mom_w_[5], mom_b_[5], mom_g_[4], mom_beta_[4];
     float* red_part_ = nullptr;          // per-chunk partial sums of the BatchNorm reductions (summed in chunk order)
     float* loss_part_ = nullptr;         // per-block partial sums of the edge loss
     unsigned int* red_counter_ = nullptr;    // arrival counters: [S] BatchNorm reductions, then [S] loss

@@ -363,6 +363,25 @@ int s2i_lgp_forward_taps(s2i_lgp* l, const float* const* taps, const int* sizes,
     return l->impl->forward(tp, B, L, noise, sigma, train != 0, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int s2i_lgp_forward_taps_batch(s2i_lgp* l, const float* const* taps, const int* sizes, const int* channels, int B, int L,
+                               const float* noise_level, void* cuda_stream) {
+    if (!l || !taps || !sizes || !channels || !noise_level) return s2i::set_error(S2I_ERR_ARG, "s2i_lgp_forward_taps_batch: null argument");
+    s2i::LgpTap tp[9];
+    for (int k = 0; k < 9; ++k) tp[k] = s2i::LgpTap{taps[k], sizes[k], channels[k], 0};
+    return l->impl->forward(tp, B, L, noise_level, 1.f, true, static_cast<cudaStream_t>(cuda_stream), nullptr, false, /*groups=*/1);
+}
+
+int s2i_lgp_train_step(s2i_lgp* l, const float* target, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                       float* loss, void* cuda_stream) {
+    if (!l || !target || !loss) return s2i::set_error(S2I_ERR_ARG, "s2i_lgp_train_step: null argument");
+    return l->impl->train_step(target, lr, beta1, beta2, eps, weight_decay, step, loss, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int s2i_lgp_get_param(s2i_lgp* l, const char* name, float* host, long long n) {
+    if (!l || !name || !host || n < 0) return s2i::set_error(S2I_ERR_ARG, "s2i_lgp_get_param: bad argument");
+    return l->impl->get_param(name, host, (size_t)n);
+}
+
 int s2i_lgp_forward_nchw(s2i_lgp* l, const float* x, const float* t, int B, int L, int train, void* cuda_stream) {
     if (!l || !x || !t) return s2i::set_error(S2I_ERR_ARG, "s2i_lgp_forward_nchw: null argument");
     return l->impl->forward_nchw(x, t, B, L, train != 0, static_cast<cudaStream_t>(cuda_stream));

@@ -25,6 +25,15 @@ int pack_linear_host(const float* host, int N, int K, __half* w, long w_ld, __ha
     return 0;
 }
 
+// Same from a device fp32 matrix, enqueued on `st` (LGP training: the fp16 operand copies follow the updated masters).
+int pack_linear_device(const float* dev, int N, int K, __half* w, long w_ld, __half* wd, long wd_ld, cudaStream_t st) {
+    pack2d_kernel<<<1024, 256, 0, st>>>(dev, K, 0, N, K, 0, 0, 0, 0, w, w_ld);
+    if (wd) pack2d_kernel<<<1024, 256, 0, st>>>(dev, K, 1, K, N, 0, 0, 0, 0, wd, wd_ld);
+    g_prev_kernel = false;
+    S2I_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ================================================================================================== loading
 UNet::~UNet() {
     for (auto& T : tfm_) {

@@ -45,6 +45,18 @@ class LatentEdgePredictor(nn.Module):
             self._engine_key = key
         return self._engine
 
+    def pull_from_engine(self):
+        """After ``trainer.training_step``: copy the engine's updated fp32 masters back into this module's parameters (so
+        ``state_dict()`` / ``torch.save`` see them) without triggering a re-upload."""
+        eng = self._engine
+        if eng is None:
+            return self
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                p.copy_(eng.get_param(name, tuple(p.shape)).to(p.device, p.dtype))
+        self._engine_key = self._params_key()
+        return self
+
     def forward(self, x, t):
         """x [b, input_dim-4-4P, h, w] (resized, concatenated taps), t [b,4,h,w] -> fp16 [(b w h), output_dim]
         (latent_predictor.py:37-45).  b must hold (uncond, cond) pairs: BatchNorm statistics are per pair
@@ -108,6 +120,28 @@ class LGPEngine:
         chans = (C.c_int * 9)(*[t.shape[3] for t in taps])
         _lib.check(self.lib.s2i_lgp_forward_taps(self._h, ptrs, sizes, chans, B, L, noise.data_ptr(), float(sigma),
                                                  int(train), _lib.stream_ptr()))
+
+    def forward_taps_batch(self, taps, B, L, noise_level):
+        """LatentEdgePredictor.forward as the trainer calls it (trainer.py:245): B latents, BatchNorm statistics over all rows;
+        taps: 9 NHWC fp32 cuda tensors [B, S, S, C]; noise_level NCHW [B, 4, L, L]."""
+        taps = [t.contiguous() for t in taps]
+        self._taps_keepalive = taps
+        ptrs = (C.c_void_p * 9)(*[t.data_ptr() for t in taps])
+        sizes = (C.c_int * 9)(*[t.shape[1] for t in taps])
+        chans = (C.c_int * 9)(*[t.shape[3] for t in taps])
+        _lib.check(self.lib.s2i_lgp_forward_taps_batch(self._h, ptrs, sizes, chans, B, L, noise_level.data_ptr(), _lib.stream_ptr()))
+
+    def train_step(self, target, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, step=1):
+        """One AdamW step on the batch of the last ``forward_taps_batch``; returns the loss (python float)."""
+        loss = torch.empty(1, device=target.device, dtype=torch.float32)
+        _lib.check(self.lib.s2i_lgp_train_step(self._h, target.data_ptr(), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                               float(weight_decay), int(step), loss.data_ptr(), _lib.stream_ptr()))
+        return loss.item()
+
+    def get_param(self, name, shape):
+        out = torch.empty(shape, dtype=torch.float32)
+        _lib.check(self.lib.s2i_lgp_get_param(self._h, name.encode(), out.data_ptr(), out.numel()))
+        return out
 
     def output(self, B, L, device):
         out = torch.empty(B * L * L, self.output_dim, device=device, dtype=torch.float32)
