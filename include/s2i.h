@@ -73,6 +73,9 @@ int s2i_gemm_set_tma_epilogue(int on);
 /* Tools / tests: 2 forces gemm_tma_kernel's two-sub-tile form (256 x BN per CTA: two A tiles share each B tile, two TMEM
  * accumulators) wherever it is legal, 1 forbids it, 0 (default) lets the cost model choose. */
 int s2i_gemm_force_msub(int msub);
+/* Tools / tests: CTA pairs in gemm_tma_kernel (two adjacent 128-row tiles run one tcgen05.mma.cta_group::2 stream and load half
+ * of each B tile each).  1 = wherever legal, 0 = never, -1 (default) = the cost model's choice (env S2I_GEMM_PAIR overrides). */
+int s2i_gemm_set_pair(int mode);
 /* Debugging: device buffer of [ctas][16] uint64 that gemm_tma_kernel fills with %globaltimer stamps of its phases
  * (entry, setup done, loads issued, MMAs issued, epilogue start, accumulator ready, residual ready, chunks done, stores
  * read, exit); NULL switches it off. */

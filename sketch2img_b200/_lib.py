@@ -71,6 +71,7 @@ def lib():
     h.s2i_gemm.restype = C.c_int
     h.s2i_gemm_set_tma_epilogue.argtypes = [C.c_int]
     h.s2i_gemm_force_msub.argtypes = [C.c_int]
+    h.s2i_gemm_set_pair.argtypes = [C.c_int]
     vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_void_p)
     h.s2i_attention.argtypes = [vp, C.c_longlong, C.c_int, vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_longlong, vp, vp]

@@ -38,6 +38,11 @@ int s2i_gemm_force_msub(int msub) {
     return 0;
 }
 
+int s2i_gemm_set_pair(int mode) {
+    s2i::gemm_set_pair(mode);
+    return 0;
+}
+
 int s2i_gemm_set_trace(void* device_buf) {
     s2i::gemm_set_trace(static_cast<unsigned long long*>(device_buf));
     return 0;

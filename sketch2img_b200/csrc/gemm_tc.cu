@@ -67,6 +67,10 @@ struct __align__(64) GemmParams {
     // floating-point atomics: the result does not depend on timing.
     int dsplit, csplit, groups;
     int msub;                // M sub-tiles per CTA (1 or 2): two 128-row A tiles share every B tile (two TMEM accumulators)
+    // CTA pair (pair != 0): the CTAs of two adjacent M tiles (cluster x = 2) run ONE tcgen05.mma.cta_group::2 stream of 256 x BN
+    // instructions, issued by the even CTA.  Each CTA loads its own 128 A rows and HALF of the B tile (b_rows = BN / 2), so a tile
+    // costs 16 KB + BN * 64 B per K step instead of 16 KB + BN * 128 B from L2; accumulators, epilogue and split-K are per CTA.
+    int pair, b_rows;
     int tiles_m;             // number of 128-row M tiles of the problem
     unsigned long long* trace;   // optional [ctas][16] %globaltimer stamps of the kernel's phases (tools/gemm_trace.py)
 };
@@ -87,6 +91,11 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(rank));
     return ra;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
     float4 v;
@@ -148,6 +157,10 @@ __device__ __forceinline__ TileCtx tile_ctx(const GemmParams& p) {
 }
 
 // One thread: stream the A / B operand tiles of this CTA's K range through the stage ring.
+// The loop body is ONE thread's dependent instruction chain and it paces the whole CTA (measured: with the stage index, phase, tap
+// and K-chunk recomputed by division every trip the chain was ~150 instructions and a stage was issued only every ~0.5 us,
+// whatever the pipeline depth), so everything loop-invariant is hoisted and the counters advance incrementally.
+template <bool PAIR = false>
 __device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx& t, uint8_t* smem, int stage_bytes,
                                               uint64_t* full, uint64_t* empty) {
     const int a_inner = p.a_c0 + (p.a_zmode ? 0 : t.zhd * p.a_hoff);
@@ -155,69 +168,128 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx
     const int b_inner = p.b_c0 + (p.b_zmode ? 0 : t.zhd * p.b_hoff);
     const int b_bz = p.b_zmode ? t.z : t.zb;
     const int nchunks_b = (p.BN + 63) >> 6;
-    for (int it = t.it_begin; it < t.it_end; ++it) {
-        const int li = it - t.it_begin;
-        const int stage = li % p.stages;
-        const uint32_t phase = (li / p.stages) & 1;
-        ptx::mbar_wait(&empty[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&full[stage], p.tx_bytes);
-        uint8_t* sa = smem + stage * stage_bytes;
-        uint8_t* sb = sa + (p.msub > 1 ? 2 : 1) * kAStageBytes;
-        if (!p.a_mn) {
-            const int tap = it / p.k_chunks;
-            const int kc = it - tap * p.k_chunks;
-            int dx = 0, dy = 0;
-            if (p.taps == 9) {
-                dy = tap / 3 - 1;
-                dx = tap % 3 - 1;
+    const int pr = PAIR ? (int)(cluster_ctarank() & 1u) : 0;
+    const int stages = p.stages, k_chunks = p.k_chunks;
+    const bool a_mn = p.a_mn != 0, b_mn = p.b_mn != 0, two = p.msub > 1, taps9 = p.taps == 9, traced = p.trace != nullptr;
+    const uint32_t tx = p.tx_bytes;
+    const int a_bytes = (two ? 2 : 1) * kAStageBytes;
+    const int ab = t.b0 + a_bz, ab1 = t.b1 + a_bz;
+    const int bn0 = t.n0 + pr * p.b_rows;
+    // running state: ring slot, K chunk within the tap, tap offsets, K coordinates
+    int stage = 0;
+    uint32_t parity = 1;                 // empty[] parity to wait for: the ring starts free
+    uint8_t* sa = smem;
+    int tap = t.it_begin / k_chunks;
+    int kc = t.it_begin - tap * k_chunks;
+    int dx = 0, dy = 0;
+    if (taps9) {
+        dy = tap / 3 - 1;
+        dx = tap - (dy + 1) * 3 - 1;
+    }
+    int ak = a_inner + kc * kBlockK;     // A's K coordinate (K-major A: restarts with every tap)
+    int lk = t.it_begin * kBlockK;       // linear K coordinate (B, MN-major A)
+    const int n_it = t.it_end - t.it_begin;
+    for (int li = 0; li < n_it; ++li) {
+        ptx::mbar_wait(&empty[stage], parity);
+        uint8_t* sb = sa + a_bytes;
+        if constexpr (PAIR) {
+            // both CTAs' boxes complete on the even CTA's barrier (tx counts the pair's four boxes)
+            if (pr == 0) ptx::mbar_expect_tx(&full[stage], tx);
+            ptx::tma_load_4d_2sm(sa, &p.mapA, &full[stage], ak, t.x0 + dx, t.y0 + dy, ab);
+            ptx::tma_load_3d_2sm(sb, &p.mapB, &full[stage], b_inner + lk, bn0, b_bz);
+        } else {
+            ptx::mbar_expect_tx(&full[stage], tx);
+            if (!a_mn) {
+                ptx::tma_load_4d(sa, &p.mapA, &full[stage], ak, t.x0 + dx, t.y0 + dy, ab);
+                if (two) ptx::tma_load_4d(sa + kAStageBytes, &p.mapA, &full[stage], ak, t.x1 + dx, t.y1 + dy, ab1);
+            } else {
+                ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + t.m0, lk, 0, a_bz);
+                ptx::tma_load_4d(sa + kChunkBytes, &p.mapA, &full[stage], a_inner + t.m0 + 64, lk, 0, a_bz);
             }
-            ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + kc * kBlockK, t.x0 + dx, t.y0 + dy, t.b0 + a_bz);
-            if (p.msub > 1)
-                ptx::tma_load_4d(sa + kAStageBytes, &p.mapA, &full[stage], a_inner + kc * kBlockK, t.x1 + dx, t.y1 + dy,
-                                 t.b1 + a_bz);
-        } else {
-            ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + t.m0, it * kBlockK, 0, a_bz);
-            ptx::tma_load_4d(sa + kChunkBytes, &p.mapA, &full[stage], a_inner + t.m0 + 64, it * kBlockK, 0, a_bz);
+            if (!b_mn) {
+                ptx::tma_load_3d(sb, &p.mapB, &full[stage], b_inner + lk, bn0, b_bz);
+            } else {
+                for (int j = 0; j < nchunks_b; ++j)
+                    ptx::tma_load_3d(sb + j * kChunkBytes, &p.mapB, &full[stage], b_inner + t.n0 + j * 64, lk, b_bz);
+            }
         }
-        if (!p.b_mn) {
-            ptx::tma_load_3d(sb, &p.mapB, &full[stage], b_inner + it * kBlockK, t.n0, b_bz);
-        } else {
-            for (int j = 0; j < nchunks_b; ++j)
-                ptx::tma_load_3d(sb + j * kChunkBytes, &p.mapB, &full[stage], b_inner + t.n0 + j * 64, it * kBlockK, b_bz);
+        if (traced && li < 3) stamp(p, 10 + li);
+        lk += kBlockK;
+        ak += kBlockK;
+        if (++kc == k_chunks) {
+            kc = 0;
+            ak = a_inner;
+            if (taps9 && ++dx == 2) {
+                dx = -1;
+                ++dy;
+            }
         }
-        if (li < 3) stamp(p, 10 + li);
+        sa += stage_bytes;
+        if (++stage == stages) {
+            stage = 0;
+            sa = smem;
+            parity ^= 1u;
+        }
     }
 }
 
 // One thread: issue the tcgen05.mma stream of this CTA's K range; accum_full fires when the accumulator is complete.
+// Same discipline as producer_loop: incremental ring / chunk counters, descriptors built by adding to a per-stage base.
+template <bool PAIR = false>
 __device__ __forceinline__ void mma_loop(const GemmParams& p, const TileCtx& t, uint8_t* smem, int stage_bytes,
                                          uint64_t* full, uint64_t* empty, uint64_t* accum_full, uint32_t tmem_base) {
     const uint32_t a_kstep = p.a_mn ? 2048u : 32u;   // bytes per UMMA_K = 16 elements
     const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
     const uint32_t a_lbo = p.a_mn ? (uint32_t)kChunkBytes : 16u;
     const uint32_t b_lbo = p.b_mn ? (uint32_t)kChunkBytes : 16u;
-    for (int it = t.it_begin; it < t.it_end; ++it) {
-        const int li = it - t.it_begin;
-        const int stage = li % p.stages;
-        const uint32_t phase = (li / p.stages) & 1;
-        ptx::mbar_wait(&full[stage], phase);
+    const uint32_t pair_mask = PAIR ? (3u << (cluster_ctarank() & ~1u)) : 0u;      // this pair's two cluster ranks
+    const int stages = p.stages, k_chunks = p.k_chunks, k_last = p.k_last_steps;
+    const bool two = p.msub > 1;
+    const uint32_t idesc = p.idesc;
+    const uint32_t a_bytes = (two ? 2u : 1u) * kAStageBytes;
+    const uint32_t tmem1 = tmem_base + (uint32_t)p.BN;
+    // descriptors of ring slot 0, K step 0; the start-address field counts 16-byte units, so slots and K steps are additions
+    const uint32_t s0 = ptx::smem_u32(smem);
+    const uint64_t adesc0 = ptx::make_smem_desc_sw128(s0, a_lbo, 1024u);
+    const uint64_t bdesc0 = ptx::make_smem_desc_sw128(s0 + a_bytes, b_lbo, 1024u);
+    const uint64_t a_step = a_kstep >> 4, b_step = b_kstep >> 4, slot_step = (uint32_t)stage_bytes >> 4;
+    const uint64_t a1_off = (uint32_t)kAStageBytes >> 4;
+    int stage = 0;
+    uint32_t parity = 0;
+    uint64_t slot_off = 0;
+    int kc = t.it_begin % k_chunks;
+    uint32_t accumulate = 0;
+    const int n_it = t.it_end - t.it_begin;
+    for (int li = 0; li < n_it; ++li) {
+        ptx::mbar_wait(&full[stage], parity);
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
-        const uint32_t sb = sa + (p.msub > 1 ? 2u : 1u) * kAStageBytes;
         // The last K chunk of a tap may be partial: head-sliced operands must not read past Kc.
-        const int ksteps = ((it + 1) % p.k_chunks == 0) ? p.k_last_steps : kBlockK / 16;
+        const int ksteps = (kc == k_chunks - 1) ? k_last : kBlockK / 16;
+        uint64_t adesc = adesc0 + slot_off, bdesc = bdesc0 + slot_off;
         for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = ptx::make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024u);
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024u);
-            ptx::umma_f16(tmem_base, adesc, bdesc, p.idesc, (li | k) != 0 ? 1u : 0u);
-            if (p.msub > 1) {     // second 128-row sub-tile against the same B tile -> second accumulator
-                const uint64_t adesc1 = ptx::make_smem_desc_sw128(sa + kAStageBytes + k * a_kstep, a_lbo, 1024u);
-                ptx::umma_f16(tmem_base + (uint32_t)p.BN, adesc1, bdesc, p.idesc, (li | k) != 0 ? 1u : 0u);
+            if constexpr (PAIR) {
+                ptx::umma_f16_2sm(tmem_base, adesc, bdesc, idesc, accumulate);
+            } else {
+                ptx::umma_f16(tmem_base, adesc, bdesc, idesc, accumulate);
+                // second 128-row sub-tile against the same B tile -> second accumulator
+                if (two) ptx::umma_f16(tmem1, adesc + a1_off, bdesc, idesc, accumulate);
             }
+            accumulate = 1u;
+            adesc += a_step;
+            bdesc += b_step;
         }
-        ptx::umma_commit(&empty[stage]);   // frees the smem stage once these MMAs have read it
+        if constexpr (PAIR) ptx::umma_commit_2sm(&empty[stage], pair_mask);   // frees the stage in both CTAs
+        else ptx::umma_commit(&empty[stage]);                                 // frees the smem stage once these MMAs have read it
+        if (++kc == k_chunks) kc = 0;
+        slot_off += slot_step;
+        if (++stage == stages) {
+            stage = 0;
+            slot_off = 0;
+            parity ^= 1u;
+        }
     }
-    ptx::umma_commit(accum_full);          // accumulator complete
+    if constexpr (PAIR) ptx::umma_commit_2sm(accum_full, pair_mask);
+    else ptx::umma_commit(accum_full);     // accumulator complete
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -237,16 +309,21 @@ constexpr int kMaxChunks = 8;
 // are independent (own residual / staging region, own bulk store), and one quartet alone works through them at ~0.75 us
 // per chunk -- a latency chain (TMEM load, shared-memory round trips, proxy fence, barrier), not a bandwidth limit.
 // GLU: the gated-GELU epilogue (its own instantiation, so the plain epilogue's register budget is untouched).
-template <int ESETS, bool GLU>
+// PAIR: the CTA-pair form (GemmParams::pair) -- its own instantiations: a kernel containing cta_group::2 instructions can only be
+// launched as clusters of an even number of CTAs.
+template <int ESETS, bool GLU, bool PAIR = false>
 __global__ void __launch_bounds__(64 + 128 * ESETS, (ESETS == 2 && !GLU) ? 2 : 1)
 gemm_tma_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_stage_bytes = ((p.BN + 63) >> 6) * kChunkBytes;
+    const int b_stage_bytes = PAIR ? ((p.b_rows * 128 + 1023) & ~1023) : ((p.BN + 63) >> 6) * kChunkBytes;
     const int msub = p.msub > 1 ? 2 : 1;
     const int stage_bytes = msub * kAStageBytes + b_stage_bytes;
     const int nch = p.BN >> 5;
     const int use32 = p.has_res | p.has_o32;
+    const bool in_cluster = PAIR || (p.dsplit && p.csplit > 1);
+    const uint32_t crank = in_cluster ? cluster_ctarank() : 0u;
+    const bool mma_leader = !PAIR || (crank & 1u) == 0;
     // pipeline stages; aliased after the mainloop by the epilogue staging / the cluster split-K partial tile (host: launch_tma)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.pipe_bytes);
     uint64_t* empty = full + p.stages;
@@ -279,11 +356,23 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
             ptx::fence_mbar_init();
         }
         __syncwarp();
-        ptx::tmem_alloc(tmem_slot, p.tmem_cols);
-        ptx::tmem_relinquish();
+        if constexpr (PAIR) {
+            ptx::tmem_alloc_2sm(tmem_slot, p.tmem_cols);
+            ptx::tmem_relinquish_2sm();
+        } else {
+            ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) {
+        // the peer's loads complete on, and the even CTA's commits arrive at, barriers of the OTHER CTA: both must be initialised
+        __syncwarp();
+        cluster_arrive();
+        cluster_wait();
+    } else {
+        __syncthreads();
+    }
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();       // everything above is local setup; global memory of earlier kernels is touched only below
@@ -294,7 +383,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
 
     if (warp == 0) {
         if (lane == 0) {
-            producer_loop(p, t, smem, stage_bytes, full, empty);
+            producer_loop<PAIR>(p, t, smem, stage_bytes, full, empty);
             stamp(p, 2);
             if (add_res) {
                 // the pipeline stages are idle once the accumulator is complete: land the residual tile there
@@ -307,8 +396,8 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            mma_loop(p, t, smem, stage_bytes, full, empty, accum_full, tmem_base);
+        if (lane == 0 && mma_leader) {
+            mma_loop<PAIR>(p, t, smem, stage_bytes, full, empty, accum_full, tmem_base);
             stamp(p, 3);
         }
     } else {
@@ -490,7 +579,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
         const int CS = p.csplit, G = p.groups;
         const int rank = t.split % CS, group = t.split / CS;
         ptx::tc_fence_before();
-        if (CS > 1) {
+        if (CS > 1 || PAIR) {
             __syncwarp();
             cluster_arrive();
             cluster_wait();
@@ -508,7 +597,8 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
             const uint32_t part_local = ptx::smem_u32(smem);
             uint32_t base_k[kMaxCluster];
     #pragma unroll
-            for (int k = 0; k < kMaxCluster; ++k) base_k[k] = map_to_rank(part_local, (uint32_t)(k < CS ? k : 0));
+            for (int k = 0; k < kMaxCluster; ++k)       // split k of this tile: cluster rank k, or 2 k + (M tile parity) in pair mode
+                base_k[k] = map_to_rank(part_local, PAIR ? (uint32_t)(k < CS ? 2 * k : 0) + (crank & 1u) : (uint32_t)(k < CS ? k : 0));
             // bias / ReLU / rounding emulation / residual, then the fp32 and / or fp16 rows of the output
             auto finish = [&](float4 acc, int c4, int n, long grow, const float4& res4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c4);
@@ -633,7 +723,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                 }
             }
         }
-        if (CS > 1) {
+        if (CS > 1 && !PAIR) {
             __syncwarp();
             cluster_arrive();         // this CTA no longer reads its peers' shared memory ...
             cluster_wait();           // ... and no peer reads this CTA's: it may exit
@@ -641,6 +731,15 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
     }
 
     ptx::tc_fence_before();
+    if constexpr (PAIR) {
+        // both CTAs are done with the pair's tensor memory and with each other's shared memory (barriers, split-K partial tiles)
+        __syncwarp();
+        cluster_arrive();
+        cluster_wait();
+        if (threadIdx.x == 0) stamp(p, 9);
+        if (warp == 1) ptx::tmem_dealloc_2sm(tmem_base, p.tmem_cols);
+        return;
+    }
     __syncthreads();
     if (threadIdx.x == 0) stamp(p, 9);
     if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
@@ -1004,7 +1103,7 @@ TileChoice choose_tiles(int N, long tiles_m, int Z, int iters, bool allow_split)
 // Same pacing model with this kernel's constants: prologue + first-load latency ~4.5 k cycles, ~450 cycles per
 // 32-column epilogue chunk (+ the residual tile's L2 round trip), operands arriving at ~48 B/clk per SM when every SM
 // pulls from L2.  Split-K partial tiles are reduce-added into the (zeroed) output by the bulk-copy engine.
-double model_cycles_tma(int N, long tiles_m_all, int iters, int BN, int splits, int epi, int msub = 1) {
+double model_cycles_tma(int N, long tiles_m_all, int iters, int BN, int splits, int epi, int msub = 1, bool cta_pair = false) {
     const bool residual = (epi & 1) != 0;
     const long tiles_m = ceil_div_l(tiles_m_all, msub);
     // Calibrated on B200 with tools/gemm_bench.py (profiles/r1_gemm_bench_v2.txt): every CTA pays ~9 k cycles of launch,
@@ -1024,9 +1123,10 @@ double model_cycles_tma(int N, long tiles_m_all, int iters, int BN, int splits, 
     const double mma = 2.0 * BN * resident * msub;
     // measured operand arrival: ~31 B/clk for a CTA alone on its SM, ~42 B/clk shared by two co-resident CTAs
     // (the chip-wide L2 rate: what matters is bytes per FLOP, hence the two-sub-tile form for K-heavy problems)
-    const double tma = (double)(msub * kAStageBytes + BN * 128) / (resident > 1.0 ? 21.0 : 31.0);
+    // (a CTA pair loads half of each B tile per CTA)
+    const double tma = (double)(msub * kAStageBytes + BN * (cta_pair ? 64 : 128)) / (resident > 1.0 ? 21.0 : 31.0);
     const double per_iter = mma > tma ? mma : tma;
-    double fixed = 9000.0 + msub * 350.0 * (BN / 32) + (residual ? 900.0 * msub : 0.0) + (msub - 1) * 500.0;
+    double fixed = 9000.0 + msub * 350.0 * (BN / 32) + (residual ? 900.0 * msub : 0.0) + (msub - 1) * 500.0 + (cta_pair ? 800.0 : 0.0);
     double total = (double)waves * (it * per_iter + fixed);
     if (splits > 1) total += 4500.0;      // zero-fill node + reduce-add traffic
     return total;
@@ -1054,7 +1154,7 @@ int g_cluster_cap[kMaxCluster + 1][3] = {};
 int cluster_capacity(int cs, int occ);
 
 // deterministic split-K (cluster size cs, `groups` clusters per tile): model of one CTA's cycles, times the number of waves
-double model_cycles_dsplit(int N, long tiles_m, int iters, int BN, int cs, int groups, int epi) {
+double model_cycles_dsplit(int N, long tiles_m, int iters, int BN, int cs, int groups, int epi, bool cta_pair = false) {
     const int splits = cs * groups;
     const int tiles_n = ceil_div(N, BN);
     const long ctas = tiles_m * tiles_n * splits;
@@ -1062,7 +1162,8 @@ double model_cycles_dsplit(int N, long tiles_m, int iters, int BN, int cs, int g
     const long part_bytes = (long)kBlockM * (BN + 4) * 4;
     const int occ = (2 * stage_bytes <= 100 * 1024 && part_bytes <= 108 * 1024 && BN <= 256) ? 2 : 1;
     const long n_clusters = tiles_m * tiles_n * groups;
-    const int cap1 = cluster_capacity(cs, 1);
+    const int cw = cta_pair ? 2 : 1;                      // CTA pairs: clusters (2, 1, cs) span two tiles
+    const int cap1 = cluster_capacity(cs * cw, 1) * cw;   // ... in tile-clusters
     // CTAs are sized to pair up on an SM when the clusters do not fit one per SM (launch_tma does the same).  The occupancy API
     // reports the same cluster count for such CTAs as for unpaired ones; measured, twice that many clusters still run as one wave
     const int use_occ = (n_clusters > cap1 && occ == 2) ? 2 : 1;
@@ -1071,7 +1172,7 @@ double model_cycles_dsplit(int N, long tiles_m, int iters, int BN, int cs, int g
     const int it = ceil_div(iters, splits);
     const double resident = (double)((ctas <= kNumSMs && use_occ == 1) ? 1 : use_occ);
     const double mma = 2.0 * BN * resident;
-    const double tma = (double)(kAStageBytes + BN * 128) / (resident > 1.0 ? 21.0 : 31.0);
+    const double tma = (double)(kAStageBytes + BN * (cta_pair ? 64 : 128)) / (resident > 1.0 ? 21.0 : 31.0);
     const double per_iter = mma > tma ? mma : tma;
     const double rows_per = (double)kBlockM / cs;
     // prologue / first load / drain as in model_cycles_tma; TMEM -> smem 60 cycles per chunk; barriers; one tile's worth of
@@ -1084,7 +1185,10 @@ double model_cycles_dsplit(int N, long tiles_m, int iters, int BN, int cs, int g
     return (double)waves * (it * per_iter + fixed);
 }
 
-TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, int epi) {
+// no_msub: the caller will run CTA pairs (which take the place of the two-sub-tile form).  The tile width and cluster size are
+// chosen with the single-CTA model -- the sweeps of both forms (tools/gemm_bench.py psweep) agree on them except where a
+// cluster of 16 would not fit (launch_tma adjusts those).
+TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, int epi, bool no_msub = false) {
     static const int cands[] = {256, 192, 160, 128, 96, 64, 32};
     TileChoice best{N >= 128 ? 128 : N, 1};
     double best_c = 1e30;
@@ -1092,7 +1196,7 @@ TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, in
         if (c > N && c != 32) continue;
         if (!g_split_add_mode && allow_split) {
             const long base = tiles_m * ceil_div(N, c);
-            for (int cs = 2; cs <= kMaxCluster; cs *= 2) {
+            for (int cs = 2; cs * (no_msub ? 2 : 1) <= kMaxCluster; cs *= 2) {
                 // one cluster per tile: measured (tools/gemm_bench.py dsweep, profiles/r2_gemm_dsweep_v1.txt) the best
                 // configuration of every shape of the step has groups = 1 -- the extra trip through L2 (group rows out, fence,
                 // counter, rows back in) costs more than the added CTAs bring; groups > 1 stays available to callers
@@ -1111,7 +1215,7 @@ TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, in
             }
         }
         for (int ms = 1; ms <= 2; ++ms) {
-            if (ms == 2 && (tiles_m < 2 || ms * c > 512 || !g_allow_msub)) break;
+            if (ms == 2 && (tiles_m < 2 || ms * c > 512 || !g_allow_msub || no_msub)) break;
             const long base = ceil_div_l(tiles_m, ms) * ceil_div(N, c);
             // powers of two, and every count above 8: 180 K iterations split 30 ways (6 each) where 32 would leave empty
             // splits (measured, tools/gemm_bench.py sweep: conv 1280 @ 8x8 20.3 -> 14.3 us; small odd counts measured worse
@@ -1132,6 +1236,8 @@ TileChoice choose_tiles_tma(int N, long tiles_m, int iters, bool allow_split, in
 }
 
 unsigned long long* g_trace = nullptr;
+// CTA pairs in gemm_tma_kernel: 1 = wherever legal, 0 = never, -1 = the cost model's choice
+int g_pair_mode = [] { const char* e = getenv("S2I_GEMM_PAIR"); return e ? atoi(e) : -1; }();
 int g_force_msub = 0;      // tools / tests: 1 or 2 forces the M sub-tile count of gemm_tma_kernel, 0 = model's choice
 int g_tma_epi = -1;
 bool tma_epilogue_enabled() {
@@ -1165,7 +1271,7 @@ int ensure_ws() {
     return 0;
 }
 
-int build_operand_maps(GemmParams& p, const GemmDesc& d, int BN) {
+int build_operand_maps(GemmParams& p, const GemmDesc& d, int BN) {      // BN: rows of one CTA's B box
     {
         const long sw = d.a_sw > 0 ? d.a_sw : d.aC;
         const long sh = d.a_sh > 0 ? d.a_sh : sw * d.aW;
@@ -1254,7 +1360,7 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict_
 
 // gemm_tma_kernel as thread-block clusters (1, 1, cz) along the split-K dimension
 template <typename... KArgs, typename... Args>
-inline void launch_kernel_cluster_z(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, int cz, cudaStream_t st, Args&&... args) {
+inline void launch_kernel_cluster_z(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, int cx, int cz, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -1262,7 +1368,7 @@ inline void launch_kernel_cluster_z(void (*kernel)(KArgs...), dim3 grid, dim3 bl
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.x = (unsigned)cx;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = (unsigned)cz;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1283,6 +1389,9 @@ int cluster_capacity(int cs, int occ) {
         cudaFuncSetAttribute(gemm_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(gemm_tma_kernel<2, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaFuncSetAttribute(gemm_tma_kernel<1, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(gemm_tma_kernel<2, false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(gemm_tma_kernel<1, false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(gemm_tma_kernel<2, true, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -1315,7 +1424,12 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     bool can_split = cluster_mode ? (d.splits >= 0 && !glu) : (d.splits >= 0 && d.out32 && !d.out16 && !nonlinear);
     bool via_scratch = false;
     const int epi = (d.residual ? 1 : 0) | ((d.residual || d.out32) ? 2 : 0) | ((d.out16 || glu) ? 4 : 0);
-    TileChoice tc = choose_tiles_tma(d.N, tiles_m, num_iters, can_split, epi);
+    // CTA pairs pay where the K loop is long enough for the halved B traffic to outweigh the cluster launch (measured with
+    // tools/gemm_bench.py pair, profiles/r2_gemm_pair_v1.txt: -10..-25 % on the convolutions and the K-heavy projections,
+    // +0.3..0.6 us on the 5- and 10-step projections)
+    const bool pair_wanted = cluster_mode && tiles_m % 2 == 0 && d.N >= 64 &&
+                             (g_pair_mode == 1 || (g_pair_mode < 0 && num_iters >= 20 && (tiles_m >= 8 || num_iters >= 40)));
+    TileChoice tc = choose_tiles_tma(d.N, tiles_m, num_iters, can_split, epi, pair_wanted);
     if (glu && tc.BN % 64 != 0) {
         // value / gate columns come in 32 + 32 pairs: the tile width must hold whole pairs
         static const int cands[] = {256, 192, 128, 64};
@@ -1323,7 +1437,7 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
         for (int c : cands) {
             if (c > d.N) continue;
             for (int ms = 1; ms <= 2; ++ms) {
-                if (ms == 2 && (tiles_m < 2 || ms * c > 512)) break;
+                if (ms == 2 && (tiles_m < 2 || ms * c > 512 || pair_wanted)) break;
                 const double cyc = model_cycles_tma(d.N, tiles_m, num_iters, c, 1, epi, ms);
                 if (cyc < best_c) {
                     best_c = cyc;
@@ -1372,10 +1486,24 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
         }
         tc.cs = cs;
         tc.msub = 1;                                  // the partial tile of the reduction is one 128-row accumulator
+        if (pair_wanted && cs == 8 && d.splits <= 0 && d.BN <= 0 && groups == 1) {
+            // pairs of 8-way split tiles are clusters of 16 CTAs, of which 14 fit the chip (7 by the occupancy query, twice that
+            // with two CTAs per SM): widen the tile to 192 if that gets there, else split 4 ways
+            const long pairs = tiles_m / 2;
+            if (pairs * ceil_div(d.N, tc.BN) > 14) {
+                if (d.N >= 192 && pairs * ceil_div(d.N, 192) <= 14) tc.BN = 192;
+                else tc.cs = tc.splits = 4;
+            }
+        }
     }
     const int BN = tc.BN;
     const int msub = tc.msub;
     const bool csplit = cluster_mode && tc.splits > 1;
+    // CTA pairs (GemmParams::pair): adjacent M tiles share every B tile through tcgen05.mma.cta_group::2
+    const bool cta_pair = pair_wanted && msub == 1 && BN % 32 == 0 && BN >= 64 && (tc.splits == 1 || csplit) &&
+                          (csplit ? tc.cs : 1) * 2 <= kMaxCluster;
+    p.pair = cta_pair ? 1 : 0;
+    p.b_rows = cta_pair ? BN / 2 : BN;
     p.msub = msub;
     p.tiles_m = (int)tiles_m;
     p.BN = BN;
@@ -1398,7 +1526,7 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     p.tmem_cols = 32;
     while (p.tmem_cols < msub * BN) p.tmem_cols *= 2;
 
-    const int stage_bytes = msub * kAStageBytes + ceil_div(BN, 64) * kChunkBytes;
+    const int stage_bytes = msub * kAStageBytes + (cta_pair ? (int)round_up_l(p.b_rows * 128, 1024) : ceil_div(BN, 64) * kChunkBytes);
     const int nch = BN / 32;
     const size_t epi_bytes = csplit ? (size_t)kBlockM * (BN + 4) * 4
                                     : (size_t)((p.has_res || p.has_o32) ? nch * kChunk32Bytes : 0) + (p.has_o16 ? nch * kChunk16Bytes : 0) +
@@ -1409,7 +1537,8 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     // aim for two co-resident CTAs (<= 112 KB each) when more than one wave is coming and they can actually share an SM
     const bool can_pair = 2 * (size_t)stage_bytes + tail <= 112u * 1024u && epi_bytes + tail <= 112u * 1024u && msub * BN <= 256;
     // ... or when the split-K clusters do not fit one CTA per SM (clusters are gang-scheduled: one too many means a second wave)
-    const bool pair = can_pair && (ctas > kNumSMs || (csplit && tc.cs > 1 && grid_m * tiles_n * groups > cluster_capacity(tc.cs, 1)));
+    const int cluster_ctas = (csplit ? tc.cs : 1) * (cta_pair ? 2 : 1);
+    const bool pair = can_pair && (ctas > kNumSMs || (cluster_ctas > 1 && ctas / cluster_ctas > cluster_capacity(cluster_ctas, 1)));
     const size_t budget = (pair ? 112u : 220u) * 1024u - tail;
     int stages = (int)(budget / stage_bytes);
     if (stages < 2) stages = 2;
@@ -1423,21 +1552,22 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     if (smem_bytes > 227u * 1024u) return set_error(S2I_ERR_ARG, "gemm(tma): %zu bytes of shared memory needed (BN %d)", smem_bytes, BN);
     static const bool dbg = getenv("S2I_GEMM_DEBUG") != nullptr;       // tools: print the chosen configuration
     if (dbg)
-        fprintf(stderr, "gemm_tma %s: M-tiles %ld N %d iters %d -> BN %d msub %d splits %d%s stages %d ctas %ld smem %zu%s\n", d.tag,
-                tiles_m, d.N, num_iters, BN, msub, tc.splits, csplit ? (" (cluster " + std::to_string(tc.cs) + " x " + std::to_string(groups) + " groups)").c_str() : "", stages, ctas, smem_bytes,
+        fprintf(stderr, "gemm_tma %s: M-tiles %ld N %d iters %d -> BN %d msub %d%s splits %d%s stages %d ctas %ld smem %zu%s\n", d.tag,
+                tiles_m, d.N, num_iters, BN, msub, cta_pair ? " CTA pairs" : "", tc.splits, csplit ? (" (cluster " + std::to_string(tc.cs) + " x " + std::to_string(groups) + " groups)").c_str() : "", stages, ctas, smem_bytes,
                 via_scratch ? " (via scratch)" : "");
 
     p.a_c0 = d.a_c0; p.a_hoff = d.a_hoff; p.a_zmode = d.a_zmode;
     p.b_c0 = d.b_c0; p.b_hoff = d.b_hoff; p.b_zmode = d.b_zmode;
-    p.idesc = ptx::make_idesc_f16(kBlockM, BN, d.bf16, 0, 0);
-    p.tx_bytes = (uint32_t)(msub * p.tw * p.th * p.tb * kBlockK * 2) + (uint32_t)(BN * kBlockK * 2);
+    p.idesc = ptx::make_idesc_f16(cta_pair ? 2 * kBlockM : kBlockM, BN, d.bf16, 0, 0);
+    p.tx_bytes = (uint32_t)(msub * p.tw * p.th * p.tb * kBlockK * 2) + (uint32_t)(p.b_rows * kBlockK * 2);
+    if (cta_pair) p.tx_bytes *= 2;          // the pair's boxes all complete on the even CTA's barrier
     p.alpha = 1.f;
     p.bias = d.bias;
     p.rowvec = d.rowvec;
     p.relu = d.relu;
     p.qscale = d.qscale;
     p.qinv = d.qscale != 0.f ? 1.f / d.qscale : 0.f;
-    S2I_TRY(build_operand_maps(p, d, BN));
+    S2I_TRY(build_operand_maps(p, d, p.b_rows));
     if (csplit) {
         // the reducing CTAs address global memory directly (rows of the tile's pixel box)
         p.residual = d.residual; p.res_ld = d.res_ld;
@@ -1478,6 +1608,9 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
         S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        S2I_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     dim3 grid((unsigned)grid_m, (unsigned)tiles_n, (unsigned)tc.splits);
@@ -1486,9 +1619,14 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     // read per call so tools can A/B in one process
     int esets = (BN >> 5) >= 2 ? 2 : 1;
     if (const char* e = getenv("S2I_GEMM_ESETS")) esets = atoi(e) == 1 ? 1 : esets;
-    if (csplit && tc.cs > 1) {
-        if (esets == 2) launch_kernel_cluster_z(gemm_tma_kernel<2, false>, grid, dim3(kThreads + 128), smem_bytes, tc.cs, stream, p);
-        else launch_kernel_cluster_z(gemm_tma_kernel<1, false>, grid, dim3(kThreads), smem_bytes, tc.cs, stream, p);
+    if (cta_pair) {
+        const int cz = csplit ? tc.cs : 1;
+        if (glu) launch_kernel_cluster_z(gemm_tma_kernel<2, true, true>, grid, dim3(kThreads + 128), smem_bytes, 2, cz, stream, p);
+        else if (esets == 2) launch_kernel_cluster_z(gemm_tma_kernel<2, false, true>, grid, dim3(kThreads + 128), smem_bytes, 2, cz, stream, p);
+        else launch_kernel_cluster_z(gemm_tma_kernel<1, false, true>, grid, dim3(kThreads), smem_bytes, 2, cz, stream, p);
+    } else if (cluster_ctas > 1) {
+        if (esets == 2) launch_kernel_cluster_z(gemm_tma_kernel<2, false>, grid, dim3(kThreads + 128), smem_bytes, 1, tc.cs, stream, p);
+        else launch_kernel_cluster_z(gemm_tma_kernel<1, false>, grid, dim3(kThreads), smem_bytes, 1, tc.cs, stream, p);
     } else if (glu) S2I_LAUNCH((gemm_tma_kernel<2, true>), grid, kThreads + 128, smem_bytes, stream, p);
     else if (esets == 2) S2I_LAUNCH((gemm_tma_kernel<2, false>), grid, kThreads + 128, smem_bytes, stream, p);
     else S2I_LAUNCH((gemm_tma_kernel<1, false>), grid, kThreads, smem_bytes, stream, p);
@@ -1532,6 +1670,7 @@ void gemm_set_tma_epilogue(int on) { g_tma_epi = on ? 1 : 0; }
 bool gemm_split_add_mode() { return g_split_add_mode; }
 void gemm_set_trace(unsigned long long* buf) { g_trace = buf; }
 void gemm_force_msub(int msub) { g_force_msub = msub; }
+void gemm_set_pair(int mode) { g_pair_mode = mode; }
 
 int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
     if (!d.A || !d.B) return set_error(S2I_ERR_ARG, "gemm: null operand");

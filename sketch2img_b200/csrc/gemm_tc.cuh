@@ -46,6 +46,7 @@ void gemm_set_trace(unsigned long long* buf);
 
 // Tools / tests: force one (1) or two (2) 128-row M sub-tiles per CTA in gemm_tma_kernel; 0 = the cost model decides.
 void gemm_force_msub(int msub);
+void gemm_set_pair(int mode);
 
 // Split-K zero-fill plan.  A split-K GEMM reduce-adds its partial tiles into a zeroed output; zeroing each output with its
 // own launch costs ~150 launches per denoising step.  The sampler therefore records the outputs while a step runs eagerly

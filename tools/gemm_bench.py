@@ -114,9 +114,79 @@ def dsweep():
         del keep
 
 
+def pair():
+    """CTA pairs (tcgen05.mma.cta_group::2, half a B tile per CTA) against single CTAs: same bits, device time per shape,
+    at the model's tile width and at forced widths."""
+    lib = L.lib()
+    print(f"{'shape':28s} {'single us':>10s} {'pair us':>9s}   same bits   forced BN: (BN single pair)")
+    for shape in SHAPES:
+        kw, keep = make(shape)
+        out32, out16 = keep[4], keep[5]
+        lib.s2i_gemm_set_pair(0)
+        L.gemm(L.GemmDesc(**kw))
+        torch.cuda.synchronize()
+        ref = (out32.clone(), out16.clone())
+        t0 = time_desc(kw)
+        out32.zero_(); out16.zero_()
+        lib.s2i_gemm_set_pair(1)
+        L.gemm(L.GemmDesc(**kw))
+        torch.cuda.synchronize()
+        same = torch.equal(ref[0], out32) and torch.equal(ref[1], out16)
+        err = max((ref[0] - out32).abs().max().item(), (ref[1].float() - out16.float()).abs().max().item())
+        t1 = time_desc(kw)
+        lib.s2i_gemm_set_pair(-1)
+        t2 = time_desc(kw)
+        extra = ["auto %.1f  " % t2]
+        for bn in (128, 192, 256):
+            if bn > shape[3]:
+                continue
+            try:
+                lib.s2i_gemm_set_pair(0)
+                a = time_desc(kw, reps=10, BN=bn)
+                lib.s2i_gemm_set_pair(1)
+                b = time_desc(kw, reps=10, BN=bn)
+                extra.append("(%d %.1f %.1f)" % (bn, a, b))
+            except L.S2IError as e:
+                extra.append("(%d err)" % bn)
+        lib.s2i_gemm_set_pair(-1)
+        print(f"{shape[0]:28s} {t0:10.1f} {t1:9.1f}   {str(same):5s} {err:.1e}   " + " ".join(extra), flush=True)
+        del keep
+
+
+def psweep():
+    """Tile width x cluster split-K size, single CTAs against CTA pairs: best four of each per shape."""
+    lib = L.lib()
+    for shape in SHAPES:
+        kw, keep = make(shape)
+        line = f"{shape[0]:28s}"
+        for pair_mode in (0, 1):
+            lib.s2i_gemm_set_pair(pair_mode)
+            res = []
+            for bn in (64, 96, 128, 160, 192, 256):
+                if bn > shape[3]:
+                    continue
+                for cs in (1, 2, 4, 8):
+                    if cs > 1:
+                        os.environ["S2I_GEMM_CS"] = str(cs)
+                    try:
+                        res.append((time_desc(kw, reps=10, BN=bn, splits=cs if cs > 1 else -1), bn, cs))
+                    except L.S2IError:
+                        pass
+                    os.environ.pop("S2I_GEMM_CS", None)
+            res.sort()
+            line += ("  pair: " if pair_mode else "  single: ") + " ".join("(%.1f %d %d)" % r for r in res[:4])
+        lib.s2i_gemm_set_pair(-1)
+        print(line, flush=True)
+        del keep
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "dsweep":
         return dsweep()
+    if len(sys.argv) > 1 and sys.argv[1] == "psweep":
+        return psweep()
+    if len(sys.argv) > 1 and sys.argv[1] == "pair":
+        return pair()
     sweep = len(sys.argv) > 1 and sys.argv[1] == "sweep"
     lib = L.lib()
     print(f"{'shape':28s} {'GFLOP':>7s} {'thread_epi us':>13s} {'tma_epi us':>11s} {'TF/s':>7s}")
