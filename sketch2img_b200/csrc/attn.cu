@@ -128,16 +128,26 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
             ptx::mbar_expect_tx(q_full, (uint32_t)q_bytes);
             for (int c = 0; c < p.nkc; ++c)
                 ptx::tma_load_3d(sQ + c * kChunk16, &p.mapQ, q_full, p.q_c0 + h * p.dp + c * 64, q0, b);
-            for (int j = 0; j < T; ++j) {
-                const int stage = j % p.stages;
-                const uint32_t phase = (j / p.stages) & 1;
-                ptx::mbar_wait(&kv_empty[stage], phase ^ 1);
+            // (ring counters advance incrementally: a division per tile in these single-thread loops is a few hundred cycles
+            // of dependent latency, see producer_loop in gemm_tc.cu)
+            const int stages = p.stages, nkc = p.nkc;
+            const int kc0 = p.k_c0 + h * p.dp, vc0 = p.v_c0 + h * p.dp;
+            int stage = 0;
+            uint32_t parity = 1;
+            uint8_t* sK = sKV;
+            for (int j = 0, key0 = 0; j < T; ++j, key0 += kTileK) {
+                ptx::mbar_wait(&kv_empty[stage], parity);
                 ptx::mbar_expect_tx(&kv_full[stage], (uint32_t)stage_bytes);
-                uint8_t* sK = sKV + stage * stage_bytes;
                 uint8_t* sV = sK + k_bytes;
-                for (int c = 0; c < p.nkc; ++c) {
-                    ptx::tma_load_3d(sK + c * kChunk8, &p.mapKV, &kv_full[stage], p.k_c0 + h * p.dp + c * 64, j * kTileK, b);
-                    ptx::tma_load_3d(sV + c * kChunk8, &p.mapKV, &kv_full[stage], p.v_c0 + h * p.dp + c * 64, j * kTileK, b);
+                for (int c = 0; c < nkc; ++c) {
+                    ptx::tma_load_3d(sK + c * kChunk8, &p.mapKV, &kv_full[stage], kc0 + c * 64, key0, b);
+                    ptx::tma_load_3d(sV + c * kChunk8, &p.mapKV, &kv_full[stage], vc0 + c * 64, key0, b);
+                }
+                sK += stage_bytes;
+                if (++stage == stages) {
+                    stage = 0;
+                    sK = sKV;
+                    parity ^= 1u;
                 }
             }
         }
@@ -145,43 +155,75 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
         if (lane == 0) {
             // ------------------------------------------------ MMA issuer
             const int nks = p.dp >> 4;             // K steps of the QK^T product
-            const uint32_t aQ = ptx::smem_u32(sQ);
+            const int stages = p.stages, nS = p.nS, pbufs = p.pbufs;
+            const uint32_t idesc_s = p.idesc_s, idesc_o = p.idesc_o;
+            // descriptors of the first ring slots; the start-address field counts 16-byte units, so slots / K steps are additions
+            const uint64_t dQ = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ), 16u, 1024u);
+            const uint64_t dK0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sKV), 16u, 1024u);
+            const uint64_t dV0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sKV + k_bytes), (uint32_t)kChunk8, 1024u);
+            const uint64_t dP0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sP), 16u, 1024u);
+            const uint64_t stage_step = (uint32_t)stage_bytes >> 4;
+            // score-tile issue state: K ring slot + parity, S buffer + parity
+            int s_stage = 0, s_buf = 0;
+            uint32_t s_kv_par = 0, s_buf_par = 1;
+            uint64_t s_koff = 0;
             // S[g % nS] = Q K_g^T once the tile has landed and the softmax warps have drained that S buffer
-            auto issue_S = [&](int g) {
-                const int stage = g % p.stages;
-                const int sb = g % p.nS;
-                ptx::mbar_wait(&kv_full[stage], (g / p.stages) & 1);
-                ptx::mbar_wait(&s_empty[sb], ((g / p.nS) & 1) ^ 1);
+            auto issue_S = [&]() {
+                ptx::mbar_wait(&kv_full[s_stage], s_kv_par);
+                ptx::mbar_wait(&s_empty[s_buf], s_buf_par);
                 ptx::tc_fence_after();
-                const uint32_t aK = ptx::smem_u32(sKV + stage * stage_bytes);
-                const uint32_t tS = tmem_base + (uint32_t)sb * 64u;
+                const uint32_t tS = tmem_base + (uint32_t)s_buf * 64u;
                 for (int k = 0; k < nks; ++k) {
-                    const uint32_t kq = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3) * 32u;
-                    ptx::umma_f16(tS, ptx::make_smem_desc_sw128(aQ + kq * kChunk16 + ks, 16u, 1024u),
-                                  ptx::make_smem_desc_sw128(aK + kq * kChunk8 + ks, 16u, 1024u), p.idesc_s,
-                                  k != 0 ? 1u : 0u);
+                    // K step k: 64-column chunk k >> 2 (16 KB apart in Q, 8 KB in K), 32 bytes per step inside it
+                    const uint64_t ks = (uint64_t)((k & 3) * 2);
+                    ptx::umma_f16(tS, dQ + (uint64_t)((k >> 2) * (kChunk16 >> 4)) + ks,
+                                  dK0 + s_koff + (uint64_t)((k >> 2) * (kChunk8 >> 4)) + ks, idesc_s, k != 0 ? 1u : 0u);
                 }
-                ptx::umma_commit(&s_full[sb]);
+                ptx::umma_commit(&s_full[s_buf]);
+                s_koff += stage_step;
+                if (++s_stage == stages) {
+                    s_stage = 0;
+                    s_koff = 0;
+                    s_kv_par ^= 1u;
+                }
+                if (++s_buf == nS) {
+                    s_buf = 0;
+                    s_buf_par ^= 1u;
+                }
             };
             ptx::mbar_wait(q_full, 0);
             int next_s = 0;
+            int stage = 0, pb = 0;
+            uint32_t pb_par = 0;
+            uint64_t voff = 0, poff = 0;
+            uint32_t accumulate = 0;
             for (int j = 0; j < T; ++j) {
                 // keep score tiles issued up to nS tiles ahead of the P V products: buffer (j + nS) % nS is the one the
                 // softmax warps drained for tile j (before P_j exists), and its K tile's stage was freed by P V (j + nS -
                 // stages) <= j - 1 because nS <= stages - 1 -- no wait below depends on a later step of this loop
-                while (next_s < T && next_s <= j + p.nS) issue_S(next_s++);
-                ptx::mbar_wait(&p_full[j % p.pbufs], (j / p.pbufs) & 1);
+                while (next_s < T && next_s <= j + nS) {
+                    issue_S();
+                    ++next_s;
+                }
+                ptx::mbar_wait(&p_full[pb], pb_par);
                 ptx::tc_fence_after();
-                const int stage = j % p.stages;
-                const uint32_t aV = ptx::smem_u32(sKV + stage * stage_bytes + k_bytes);
-                const uint32_t aP = ptx::smem_u32(sP + (j % p.pbufs) * kChunk16);
                 for (int kk = 0; kk < 4; ++kk) {
-                    ptx::umma_f16(tmem_O, ptx::make_smem_desc_sw128(aP + (uint32_t)kk * 32u, 16u, 1024u),
-                                  ptx::make_smem_desc_sw128(aV + (uint32_t)kk * 2048u, (uint32_t)kChunk8, 1024u),
-                                  p.idesc_o, (j | kk) != 0 ? 1u : 0u);
+                    ptx::umma_f16(tmem_O, dP0 + poff + (uint64_t)(kk * 2), dV0 + voff + (uint64_t)(kk * (2048 >> 4)), idesc_o, accumulate);
+                    accumulate = 1u;
                 }
                 ptx::umma_commit(&kv_empty[stage]);
-                ptx::umma_commit(&p_empty[j % p.pbufs]);
+                ptx::umma_commit(&p_empty[pb]);
+                voff += stage_step;
+                if (++stage == stages) {
+                    stage = 0;
+                    voff = 0;
+                }
+                poff += (uint64_t)(kChunk16 >> 4);
+                if (++pb == pbufs) {
+                    pb = 0;
+                    poff = 0;
+                    pb_par ^= 1u;
+                }
             }
             ptx::umma_commit(o_full);
         }
@@ -193,9 +235,13 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
         const bool row_ok = (q0 + r) < p.Nq;
         float mref = 0.f;       // reference maximum of this row, in log2 units (score * scale * log2 e)
         float l = 0.f;          // sum of p relative to mref
+        const int nS = p.nS, pbufs = p.pbufs;
+        const float scale_log2 = p.scale_log2;
+        // ring state (no divisions in the per-tile chain): S buffer + parity, P buffer + parity, and the previous tile's P buffer
+        int sbuf = 0, pb = 0, prev_pb = 0;
+        uint32_t s_par = 0, pb_par = 1, prev_par = 0;       // pb_par: parity of p_empty to wait for before writing P_j
         for (int j = 0; j < T; ++j) {
-            const int sbuf = j % p.nS;
-            ptx::mbar_wait(&s_full[sbuf], (j / p.nS) & 1);
+            ptx::mbar_wait(&s_full[sbuf], s_par);
             ptx::tc_fence_after();
             const uint32_t tS = tmem_base + (uint32_t)sbuf * 64u + lane_addr;
             uint32_t s[kTileK];
@@ -210,6 +256,10 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&s_empty[sbuf]);     // S is in registers: TMEM buffer may be overwritten
+            if (++sbuf == nS) {
+                sbuf = 0;
+                s_par ^= 1u;
+            }
 
             const int kvalid = p.Nk - j * kTileK;                // columns >= kvalid are padding (last tile only)
             float mx = -INFINITY;
@@ -221,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
                 for (int i = 0; i < kTileK; ++i)
                     if (i < kvalid) mx = fmaxf(mx, __uint_as_float(s[i]));
             }
-            const float mt = mx * p.scale_log2;
+            const float mt = mx * scale_log2;
             // lazy reference update: only when this tile would push p above 2^8 (always on the first tile)
             const bool need = (j == 0) || (mt > mref + 8.f);
             if (__any_sync(0xffffffffu, need)) {
@@ -231,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
                 mref = mnew;
                 if (j > 0) {
                     // every P V product issued so far must have landed before the accumulator rows are rescaled
-                    ptx::mbar_wait(&p_empty[(j - 1) % p.pbufs], ((j - 1) / p.pbufs) & 1);
+                    ptx::mbar_wait(&p_empty[prev_pb], prev_par);
                     ptx::tc_fence_after();
                     for (int c = 0; c < p.dp; c += 16) {
                         uint32_t o[16];
@@ -253,10 +303,10 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
             if (kvalid >= kTileK) {
 #pragma unroll
                 for (int i = 0; i < kTileK; i += 4) {
-                    const float e0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, mneg));
-                    const float e1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, mneg));
-                    const float e2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), p.scale_log2, mneg));
-                    const float e3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), p.scale_log2, mneg));
+                    const float e0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, mneg));
+                    const float e1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, mneg));
+                    const float e2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), scale_log2, mneg));
+                    const float e3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), scale_log2, mneg));
                     l0 += e0; l1 += e1; l2 += e2; l3 += e3;
                     const __half2 ha = __floats2half2_rn(e0, e1), hb = __floats2half2_rn(e2, e3);
                     pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&ha);
@@ -265,8 +315,8 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
             } else {
 #pragma unroll
                 for (int i = 0; i < kTileK; i += 2) {
-                    float e0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, mneg));
-                    float e1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, mneg));
+                    float e0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, mneg));
+                    float e1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, mneg));
                     if (i >= kvalid) e0 = 0.f;
                     if (i + 1 >= kvalid) e1 = 0.f;
                     l0 += e0; l1 += e1;
@@ -275,8 +325,7 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
                 }
             }
             l += (l0 + l1) + (l2 + l3);
-            const int pb = j % p.pbufs;
-            ptx::mbar_wait(&p_empty[pb], ((j / p.pbufs) & 1) ^ 1);    // the P V product that read this buffer is done
+            ptx::mbar_wait(&p_empty[pb], pb_par);    // the P V product that read this buffer is done
             // row r of the K-major swizzled tile: 16-byte unit u lives at r * 128 + ((u ^ (r & 7)) * 16)
             uint8_t* prow = sP + pb * kChunk16 + r * 128;
 #pragma unroll
@@ -286,6 +335,13 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
             ptx::fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&p_full[pb]);
+            // P_j's product completes phase (j / pbufs) of p_empty[pb]: what the next tile's rescale waits for
+            prev_pb = pb;
+            prev_par = pb_par ^ 1u;
+            if (++pb == pbufs) {
+                pb = 0;
+                pb_par ^= 1u;
+            }
         }
         // epilogue: O / rowsum -> fp16
         ptx::mbar_wait(o_full, 0);

@@ -135,15 +135,25 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
                 ptx::tma_load_3d(sR1 + c * kChunk16, &p.mapR1, r_full, p.r1_c0 + h * p.dp + c * 64, row0, b);
                 ptx::tma_load_3d(sR2 + c * kChunk16, &p.mapR2, r_full, p.r2_c0 + h * p.dp + c * 64, row0, b);
             }
-            for (int j = 0; j < T; ++j) {
-                const int stage = j % p.stages;
-                ptx::mbar_wait(&c_empty[stage], ((j / p.stages) & 1) ^ 1);
+            // ring counters advance incrementally (no division in the single-thread issue loops, cf. producer_loop in gemm_tc.cu)
+            const int stages = p.stages, nkc = p.nkc;
+            const int c1 = p.c1_c0 + h * p.dp, c2 = p.c2_c0 + h * p.dp;
+            int stage = 0;
+            uint32_t parity = 1;
+            uint8_t* s1 = sC;
+            for (int j = 0, col0 = 0; j < T; ++j, col0 += kCols) {
+                ptx::mbar_wait(&c_empty[stage], parity);
                 ptx::mbar_expect_tx(&c_full[stage], (uint32_t)stage_bytes);
-                uint8_t* s1 = sC + stage * stage_bytes;
                 uint8_t* s2 = s1 + c_bytes;
-                for (int c = 0; c < p.nkc; ++c) {
-                    ptx::tma_load_3d(s1 + c * kChunk8, &p.mapC1, &c_full[stage], p.c1_c0 + h * p.dp + c * 64, j * kCols, b);
-                    ptx::tma_load_3d(s2 + c * kChunk8, &p.mapC2, &c_full[stage], p.c2_c0 + h * p.dp + c * 64, j * kCols, b);
+                for (int c = 0; c < nkc; ++c) {
+                    ptx::tma_load_3d(s1 + c * kChunk8, &p.mapC1, &c_full[stage], c1 + c * 64, col0, b);
+                    ptx::tma_load_3d(s2 + c * kChunk8, &p.mapC2, &c_full[stage], c2 + c * 64, col0, b);
+                }
+                s1 += stage_bytes;
+                if (++stage == stages) {
+                    stage = 0;
+                    s1 = sC;
+                    parity ^= 1u;
                 }
             }
         }
@@ -151,60 +161,84 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
         if (lane == 0) {
             // ------------------------------------------------ MMA issuer
             const int nks = p.dp >> 4;
-            const uint32_t aR1 = ptx::smem_u32(sR1), aR2 = ptx::smem_u32(sR2);
-            // T1[g&1] = R1 C1_g^T, T2[g&1] = R2 C2_g^T
-            auto issue_T = [&](int g) {
-                const int stage = g % p.stages;
-                ptx::mbar_wait(&c_full[stage], (g / p.stages) & 1);
-                const int tb = g % p.nT;
-                ptx::mbar_wait(&t_empty[tb], ((g / p.nT) & 1) ^ 1);
+            const int stages = p.stages, nT = p.nT, sbufs = p.sbufs, mode = p.mode;
+            const uint32_t idesc_t = p.idesc_t, idesc_acc = p.idesc_acc;
+            // descriptors of the first ring slots; the start-address field counts 16-byte units, so slots / K steps are additions
+            const uint64_t dR1 = ptx::make_smem_desc_sw128(ptx::smem_u32(sR1), 16u, 1024u);
+            const uint64_t dR2 = ptx::make_smem_desc_sw128(ptx::smem_u32(sR2), 16u, 1024u);
+            const uint64_t dC1k = ptx::make_smem_desc_sw128(ptx::smem_u32(sC), 16u, 1024u);                        // K-major read (T products)
+            const uint64_t dC1m = ptx::make_smem_desc_sw128(ptx::smem_u32(sC), (uint32_t)kChunk8, 1024u);          // MN-major read (accumulations)
+            const uint64_t dSt0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sSt), 16u, 1024u);
+            const uint64_t stage_step = (uint32_t)stage_bytes >> 4, c2_off = (uint32_t)c_bytes >> 4;
+            const uint64_t st_step = (uint32_t)(nstaged * kChunk16) >> 4;
+            int t_stage = 0, tb = 0;
+            uint32_t t_c_par = 0, tb_par = 1;
+            uint64_t t_coff = 0;
+            // T1[g % nT] = R1 C1_g^T, T2[g % nT] = R2 C2_g^T
+            auto issue_T = [&]() {
+                ptx::mbar_wait(&c_full[t_stage], t_c_par);
+                ptx::mbar_wait(&t_empty[tb], tb_par);
                 ptx::tc_fence_after();
-                const uint32_t aC1 = ptx::smem_u32(sC + stage * stage_bytes);
-                const uint32_t aC2 = aC1 + (uint32_t)c_bytes;
                 const uint32_t t1 = tmem_base + (uint32_t)tb * 64u;
-                const uint32_t t2 = tmem_base + (uint32_t)p.nT * 64u + (uint32_t)tb * 64u;
+                const uint32_t t2 = tmem_base + (uint32_t)nT * 64u + (uint32_t)tb * 64u;
                 for (int k = 0; k < nks; ++k) {
-                    const uint32_t kq = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3) * 32u;
-                    ptx::umma_f16(t1, ptx::make_smem_desc_sw128(aR1 + kq * kChunk16 + ks, 16u, 1024u),
-                                  ptx::make_smem_desc_sw128(aC1 + kq * kChunk8 + ks, 16u, 1024u), p.idesc_t, k != 0 ? 1u : 0u);
+                    const uint64_t ks = (uint64_t)((k & 3) * 2);
+                    ptx::umma_f16(t1, dR1 + (uint64_t)((k >> 2) * (kChunk16 >> 4)) + ks,
+                                  dC1k + t_coff + (uint64_t)((k >> 2) * (kChunk8 >> 4)) + ks, idesc_t, k != 0 ? 1u : 0u);
                 }
                 for (int k = 0; k < nks; ++k) {
-                    const uint32_t kq = (uint32_t)(k >> 2), ks = (uint32_t)(k & 3) * 32u;
-                    ptx::umma_f16(t2, ptx::make_smem_desc_sw128(aR2 + kq * kChunk16 + ks, 16u, 1024u),
-                                  ptx::make_smem_desc_sw128(aC2 + kq * kChunk8 + ks, 16u, 1024u), p.idesc_t, k != 0 ? 1u : 0u);
+                    const uint64_t ks = (uint64_t)((k & 3) * 2);
+                    ptx::umma_f16(t2, dR2 + (uint64_t)((k >> 2) * (kChunk16 >> 4)) + ks,
+                                  dC1k + t_coff + c2_off + (uint64_t)((k >> 2) * (kChunk8 >> 4)) + ks, idesc_t, k != 0 ? 1u : 0u);
                 }
                 ptx::umma_commit(&t_full[tb]);
+                t_coff += stage_step;
+                if (++t_stage == stages) {
+                    t_stage = 0;
+                    t_coff = 0;
+                    t_c_par ^= 1u;
+                }
+                if (++tb == nT) {
+                    tb = 0;
+                    tb_par ^= 1u;
+                }
             };
             ptx::mbar_wait(r_full, 0);
-            issue_T(0);
+            issue_T();
+            int stage = 0, sb = 0;
+            uint32_t sb_par = 0, accumulate = 0;
+            uint64_t coff = 0, stoff = 0;
             for (int j = 0; j < T; ++j) {
-                if (j + 1 < T) issue_T(j + 1);      // keep the softmax warps fed while tile j's staging is produced
-                const int sb = j % p.sbufs;
-                ptx::mbar_wait(&st_full[sb], (j / p.sbufs) & 1);
+                if (j + 1 < T) issue_T();           // keep the softmax warps fed while tile j's staging is produced
+                ptx::mbar_wait(&st_full[sb], sb_par);
                 ptx::tc_fence_after();
-                const int stage = j % p.stages;
-                const uint32_t aC1 = ptx::smem_u32(sC + stage * stage_bytes);
-                const uint32_t aC2 = aC1 + (uint32_t)c_bytes;
-                const uint32_t aSt = ptx::smem_u32(sSt + sb * nstaged * kChunk16);
-                if (p.mode == 0) {
+                const uint64_t dSt = dSt0 + stoff, dC1 = dC1m + coff, dC2 = dC1 + c2_off;
+                if (mode == 0) {
                     // dQ += dS K_j   (B = K_j read MN-major: N = head channels, K = keys)
                     for (int kk = 0; kk < 4; ++kk)
-                        ptx::umma_f16(tmem_acc0, ptx::make_smem_desc_sw128(aSt + (uint32_t)kk * 32u, 16u, 1024u),
-                                      ptx::make_smem_desc_sw128(aC1 + (uint32_t)kk * 2048u, (uint32_t)kChunk8, 1024u),
-                                      p.idesc_acc, (j | kk) != 0 ? 1u : 0u);
+                        ptx::umma_f16(tmem_acc0, dSt + (uint64_t)(kk * 2), dC1 + (uint64_t)(kk * 128), idesc_acc, accumulate | (uint32_t)(kk != 0));
                 } else {
                     // dV += P^T dO_i ; dK += dS^T Q_i
                     for (int kk = 0; kk < 4; ++kk)
-                        ptx::umma_f16(tmem_acc0, ptx::make_smem_desc_sw128(aSt + (uint32_t)kk * 32u, 16u, 1024u),
-                                      ptx::make_smem_desc_sw128(aC2 + (uint32_t)kk * 2048u, (uint32_t)kChunk8, 1024u),
-                                      p.idesc_acc, (j | kk) != 0 ? 1u : 0u);
+                        ptx::umma_f16(tmem_acc0, dSt + (uint64_t)(kk * 2), dC2 + (uint64_t)(kk * 128), idesc_acc, accumulate | (uint32_t)(kk != 0));
                     for (int kk = 0; kk < 4; ++kk)
-                        ptx::umma_f16(tmem_acc1, ptx::make_smem_desc_sw128(aSt + kChunk16 + (uint32_t)kk * 32u, 16u, 1024u),
-                                      ptx::make_smem_desc_sw128(aC1 + (uint32_t)kk * 2048u, (uint32_t)kChunk8, 1024u),
-                                      p.idesc_acc, (j | kk) != 0 ? 1u : 0u);
+                        ptx::umma_f16(tmem_acc1, dSt + (uint64_t)((kChunk16 >> 4) + kk * 2), dC1 + (uint64_t)(kk * 128), idesc_acc,
+                                      accumulate | (uint32_t)(kk != 0));
                 }
+                accumulate = 1u;
                 ptx::umma_commit(&c_empty[stage]);
                 ptx::umma_commit(&st_empty[sb]);
+                coff += stage_step;
+                if (++stage == stages) {
+                    stage = 0;
+                    coff = 0;
+                }
+                stoff += st_step;
+                if (++sb == sbufs) {
+                    sb = 0;
+                    stoff = 0;
+                    sb_par ^= 1u;
+                }
             }
             ptx::umma_commit(acc_full);
         }
@@ -238,6 +272,9 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
             delta_r = acc;
             p.delta_w[(long)z * p.Nq + row0 + r] = acc;
         }
+        const int nT = p.nT, sbufs = p.sbufs;
+        int tb = 0, sb = 0;
+        uint32_t tb_par = 0, sb_par = 1;
         for (int j = 0; j < T; ++j) {
             const int col0 = j * kCols;
             if (p.mode == 1) {
@@ -249,15 +286,13 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
                 st[e] = ok ? (e < 64 ? p.lse[idx] * kLog2e : p.delta[idx]) : 0.f;
                 ptx::named_bar_sync(1, 128);
             }
-            const int tb = j % p.nT;
-            ptx::mbar_wait(&t_full[tb], (j / p.nT) & 1);
+            ptx::mbar_wait(&t_full[tb], tb_par);
             ptx::tc_fence_after();
             const uint32_t t1 = tmem_base + (uint32_t)tb * 64u + lane_addr;
-            const uint32_t t2 = t1 + (uint32_t)p.nT * 64u;
+            const uint32_t t2 = t1 + (uint32_t)nT * 64u;
             const int nvalid = p.Ncol - col0;          // columns >= nvalid are padding
             const float* stl = sStat + (j & 1) * 128;
-            const int sb = j % p.sbufs;
-            ptx::mbar_wait(&st_empty[sb], ((j / p.sbufs) & 1) ^ 1);   // the MMAs that read this staging buffer are done
+            ptx::mbar_wait(&st_empty[sb], sb_par);   // the MMAs that read this staging buffer are done
             // K-major 128B-swizzled tile: 16-byte unit u of row r lives at r * 128 + ((u ^ (r & 7)) * 16)
             uint8_t* st0 = sSt + sb * nstaged * kChunk16 + r * 128;
 #pragma unroll
@@ -323,6 +358,14 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&st_full[sb]);
+            if (++tb == nT) {
+                tb = 0;
+                tb_par ^= 1u;
+            }
+            if (++sb == sbufs) {
+                sb = 0;
+                sb_par ^= 1u;
+            }
         }
         // epilogue: accumulators -> fp16
         ptx::mbar_wait(acc_full, 0);

@@ -29,6 +29,7 @@ struct __align__(64) GemmParams {
     CUtensorMap mapA;
     CUtensorMap mapB;
     int tw, th, tb, tiles_x, tiles_y;
+    int tw_shift, th_shift;  // tw and th are powers of two: tile row -> pixel by shifts
     int W, H, Bn, M, N;
     int k_chunks, k_last_steps, taps, a_mn, b_mn;
     int BN, stages, tmem_cols;
@@ -621,10 +622,11 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                 }
             };
             // global row of tile row `row`, or -1 when it falls outside the tensor
+            const int tw_shift = p.tw_shift, th_shift = p.th_shift;
             auto global_row = [&](int row) -> long {
-                const int xi = row % p.tw;
-                const int yi = (row / p.tw) % p.th;
-                const int bi = row / (p.tw * p.th);
+                const int xi = row & (p.tw - 1);
+                const int yi = (row >> tw_shift) & (p.th - 1);
+                const int bi = row >> (tw_shift + th_shift);
                 if (bi >= p.tb || t.x0 + xi >= p.W || t.y0 + yi >= p.H || t.b0 + bi >= p.Bn) return -1;
                 return ((long)(t.b0 + bi) * p.H + (t.y0 + yi)) * p.W + (t.x0 + xi);
             };
@@ -636,6 +638,10 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                 constexpr int kU = kCS >= 8 ? 1 : 2;
                 constexpr int kL = kCS > 8 ? 8 : kCS;        // loads in flight per unit (a cluster of 16 takes two passes, in rank order)
                 const int total = rows_per * nq;
+                // unit index -> (row, column unit), advanced without divisions: one per thread up front
+                constexpr int kStep = 128 * ESETS;
+                const int step_r = kStep / nq, step_c = kStep - step_r * nq;
+                int ur = e / nq, uc = e - ur * nq;
                 for (int base = e; base < total; base += kU * 128 * ESETS) {
                     float4 v[8], rs[kU];
                     long grow[kU];
@@ -644,9 +650,16 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                     for (int u = 0; u < kU; ++u) {
                         grow[u] = -1;
                         const int idx = base + u * 128 * ESETS;
+                        const int rr = ur;
+                        const int cc = uc;
+                        ur += step_r;
+                        uc += step_c;
+                        if (uc >= nq) {
+                            uc -= nq;
+                            ++ur;
+                        }
                         if (idx < total) {
-                            const int rr = idx / nq;
-                            c4s[u] = (idx - rr * nq) << 2;
+                            c4s[u] = cc << 2;
                             rows[u] = row0 + rr;
                             if (t.n0 + c4s[u] < p.N) grow[u] = global_row(rows[u]);
                             if (grow[u] >= 0) {
@@ -1715,6 +1728,8 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
         p.tw = tw;
         p.th = th;
         p.tb = tb;
+        for (p.tw_shift = 0; (1 << p.tw_shift) < tw; ++p.tw_shift) {}
+        for (p.th_shift = 0; (1 << p.th_shift) < th; ++p.th_shift) {}
         p.tiles_x = ceil_div(d.aW, tw);
         p.tiles_y = ceil_div(d.aH, th);
         const int tiles_b = d.Z > 1 ? 1 : ceil_div(d.aB, tb);
@@ -1729,6 +1744,8 @@ int gemm_launch(const GemmDesc& d, cudaStream_t stream) {
         tiles_m = ceil_div(d.aC, kBlockM);
         p.tw = kBlockM;
         p.th = p.tb = 1;
+        p.tw_shift = 7;
+        p.th_shift = 0;
         p.tiles_x = (int)tiles_m;
         p.tiles_y = 1;
     }
