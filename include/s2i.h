@@ -64,6 +64,10 @@ typedef struct s2i_gemm_desc {
      * partial tiles there before the conversion, instead of in the library's shared scratch -- a per-call buffer can be
      * zeroed ahead of time together with the other split-K outputs of a captured step. */
     float* scratch32;
+    /* != 0: B is a tensor no kernel of the surrounding stream writes (packed weights).  gemm_tma_kernel then loads its first B
+     * tiles BEFORE waiting for the preceding kernel (programmatic dependent launch), so the weight stream of launch n + 1
+     * overlaps the epilogue of launch n.  Leave 0 when B is an activation. */
+    int b_static;
 } s2i_gemm_desc;
 
 int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream);

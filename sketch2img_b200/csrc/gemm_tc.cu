@@ -72,6 +72,7 @@ struct __align__(64) GemmParams {
     // instructions, issued by the even CTA.  Each CTA loads its own 128 A rows and HALF of the B tile (b_rows = BN / 2), so a tile
     // costs 16 KB + BN * 64 B per K step instead of 16 KB + BN * 128 B from L2; accumulators, epilogue and split-K are per CTA.
     int pair, b_rows;
+    int early_b;             // B is static (weights): its first tiles are requested before griddepcontrol.wait
     int tiles_m;             // number of 128-row M tiles of the problem
     unsigned long long* trace;   // optional [ctas][16] %globaltimer stamps of the kernel's phases (tools/gemm_trace.py)
 };
@@ -163,7 +164,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const GemmParams& p) {
 // whatever the pipeline depth), so everything loop-invariant is hoisted and the counters advance incrementally.
 template <bool PAIR = false>
 __device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx& t, uint8_t* smem, int stage_bytes,
-                                              uint64_t* full, uint64_t* empty) {
+                                              uint64_t* full, uint64_t* empty, bool early_b = false) {
     const int a_inner = p.a_c0 + (p.a_zmode ? 0 : t.zhd * p.a_hoff);
     const int a_bz = p.a_zmode ? t.z : t.zb;
     const int b_inner = p.b_c0 + (p.b_zmode ? 0 : t.zhd * p.b_hoff);
@@ -190,16 +191,35 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx
     int ak = a_inner + kc * kBlockK;     // A's K coordinate (K-major A: restarts with every tap)
     int lk = t.it_begin * kBlockK;       // linear K coordinate (B, MN-major A)
     const int n_it = t.it_end - t.it_begin;
+    // Static B (weights): the first ring's worth of B tiles does not depend on the preceding kernel -- request them, THEN wait for
+    // it (programmatic dependent launch); the A tiles of those slots follow in the loop below.
+    int pre = 0;
+    if (early_b) {
+        pre = n_it < stages ? n_it : stages;
+        uint8_t* sbp = smem + a_bytes;
+        int lkp = lk;
+        for (int s = 0; s < pre; ++s, sbp += stage_bytes, lkp += kBlockK) {
+            if constexpr (PAIR) {
+                if (pr == 0) ptx::mbar_expect_tx(&full[s], tx);
+                ptx::tma_load_3d_2sm(sbp, &p.mapB, &full[s], b_inner + lkp, bn0, b_bz);
+            } else {
+                ptx::mbar_expect_tx(&full[s], tx);
+                ptx::tma_load_3d(sbp, &p.mapB, &full[s], b_inner + lkp, bn0, b_bz);
+            }
+        }
+        pdl_wait();
+    }
     for (int li = 0; li < n_it; ++li) {
-        ptx::mbar_wait(&empty[stage], parity);
+        const bool b_done = li < pre;          // this slot's barrier is armed and its B tile requested
+        if (!b_done) ptx::mbar_wait(&empty[stage], parity);
         uint8_t* sb = sa + a_bytes;
         if constexpr (PAIR) {
             // both CTAs' boxes complete on the even CTA's barrier (tx counts the pair's four boxes)
-            if (pr == 0) ptx::mbar_expect_tx(&full[stage], tx);
+            if (pr == 0 && !b_done) ptx::mbar_expect_tx(&full[stage], tx);
             ptx::tma_load_4d_2sm(sa, &p.mapA, &full[stage], ak, t.x0 + dx, t.y0 + dy, ab);
-            ptx::tma_load_3d_2sm(sb, &p.mapB, &full[stage], b_inner + lk, bn0, b_bz);
+            if (!b_done) ptx::tma_load_3d_2sm(sb, &p.mapB, &full[stage], b_inner + lk, bn0, b_bz);
         } else {
-            ptx::mbar_expect_tx(&full[stage], tx);
+            if (!b_done) ptx::mbar_expect_tx(&full[stage], tx);
             if (!a_mn) {
                 ptx::tma_load_4d(sa, &p.mapA, &full[stage], ak, t.x0 + dx, t.y0 + dy, ab);
                 if (two) ptx::tma_load_4d(sa + kAStageBytes, &p.mapA, &full[stage], ak, t.x1 + dx, t.y1 + dy, ab1);
@@ -207,7 +227,9 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx
                 ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + t.m0, lk, 0, a_bz);
                 ptx::tma_load_4d(sa + kChunkBytes, &p.mapA, &full[stage], a_inner + t.m0 + 64, lk, 0, a_bz);
             }
-            if (!b_mn) {
+            if (b_done) {
+                // requested before the wait (K-major static B)
+            } else if (!b_mn) {
                 ptx::tma_load_3d(sb, &p.mapB, &full[stage], b_inner + lk, bn0, b_bz);
             } else {
                 for (int j = 0; j < nchunks_b; ++j)
@@ -376,7 +398,10 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
     }
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();       // everything above is local setup; global memory of earlier kernels is touched only below
+    // Everything above is local setup; global memory of earlier kernels is touched only below.  With static B (weights) the wait
+    // moves into the roles that touch global memory: the producer (after requesting its first B tiles) and the epilogue warps.
+    const bool early_b = p.early_b != 0;
+    if (!early_b) pdl_wait();
     pdl_launch();     // TMEM is held: dependents may become resident
     if (threadIdx.x == 0) stamp(p, 1);
     const bool add_res = p.has_res && (!p.split_add || t.split == 0);
@@ -384,7 +409,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
 
     if (warp == 0) {
         if (lane == 0) {
-            producer_loop<PAIR>(p, t, smem, stage_bytes, full, empty);
+            producer_loop<PAIR>(p, t, smem, stage_bytes, full, empty, early_b);
             stamp(p, 2);
             if (add_res) {
                 // the pipeline stages are idle once the accumulator is complete: land the residual tile there
@@ -403,6 +428,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
         }
     } else {
         // ---------------------------------------------------- epilogue (warps 2..5), thread <-> tile row
+        if (early_b) pdl_wait();
         const int e = threadIdx.x - 64;
         const int eset = e >> 7;                // warp quartet: chunks eset, eset + ESETS, ...
         const int el = e & 127;
@@ -1515,6 +1541,8 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     // CTA pairs (GemmParams::pair): adjacent M tiles share every B tile through tcgen05.mma.cta_group::2
     const bool cta_pair = pair_wanted && msub == 1 && BN % 32 == 0 && BN >= 64 && (tc.splits == 1 || csplit) &&
                           (csplit ? tc.cs : 1) * 2 <= kMaxCluster;
+    static const bool early_ok = [] { const char* e = getenv("S2I_GEMM_EARLY_B"); return !(e && e[0] == '0'); }();
+    p.early_b = (d.b_static && early_ok) ? 1 : 0;
     p.pair = cta_pair ? 1 : 0;
     p.b_rows = cta_pair ? BN / 2 : BN;
     p.msub = msub;
@@ -1552,7 +1580,9 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     // ... or when the split-K clusters do not fit one CTA per SM (clusters are gang-scheduled: one too many means a second wave)
     const int cluster_ctas = (csplit ? tc.cs : 1) * (cta_pair ? 2 : 1);
     const bool pair = can_pair && (ctas > kNumSMs || (cluster_ctas > 1 && ctas / cluster_ctas > cluster_capacity(cluster_ctas, 1)));
-    const size_t budget = (pair ? 112u : 220u) * 1024u - tail;
+    // S2I_GEMM_SMEM_CAP (KB, experiment): shared-memory budget of a CTA that has the SM to itself
+    static const unsigned solo_kb = [] { const char* e = getenv("S2I_GEMM_SMEM_CAP"); const int v = e ? atoi(e) : 0; return v >= 64 && v <= 220 ? (unsigned)v : 220u; }();
+    const size_t budget = (pair ? 112u : solo_kb) * 1024u - tail;
     int stages = (int)(budget / stage_bytes);
     if (stages < 2) stages = 2;
     if (stages > 8) stages = 8;

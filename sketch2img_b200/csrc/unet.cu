@@ -427,6 +427,7 @@ int UNet::gemm(const H16& a, bool spatial, int taps, const __half* w, long w_ld,
     d.taps = taps;
     d.tag = taps == 9 ? "gemm_conv3x3" : "gemm_linear";
     d.B = w;
+    d.b_static = 1;         // packed weights: nothing in the step writes them
     d.bI = taps * Kc;
     d.bR = N;
     d.b_sr = w_ld;
