@@ -72,6 +72,7 @@ struct __align__(64) GemmParams {
     // instructions, issued by the even CTA.  Each CTA loads its own 128 A rows and HALF of the B tile (b_rows = BN / 2), so a tile
     // costs 16 KB + BN * 64 B per K step instead of 16 KB + BN * 128 B from L2; accumulators, epilogue and split-K are per CTA.
     int pair, b_rows;
+    int split_issue;         // A and B tiles issued by two warps
     int early_b;             // B is static (weights): its first tiles are requested before griddepcontrol.wait
     int tiles_m;             // number of 128-row M tiles of the problem
     unsigned long long* trace;   // optional [ctas][16] %globaltimer stamps of the kernel's phases (tools/gemm_trace.py)
@@ -79,8 +80,8 @@ struct __align__(64) GemmParams {
 
 __device__ __forceinline__ void stamp(const GemmParams& p, int slot) {
     if (p.trace) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        // SM cycle counter: reading %globaltimer costs ~1 us (it distorted every phase it was meant to measure)
+        const unsigned long long t = (unsigned long long)clock64();
         const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
         p.trace[(long)cta * 16 + slot] = t;
     }
@@ -158,13 +159,19 @@ __device__ __forceinline__ TileCtx tile_ctx(const GemmParams& p) {
     return t;
 }
 
-// One thread: stream the A / B operand tiles of this CTA's K range through the stage ring.
-// The loop body is ONE thread's dependent instruction chain and it paces the whole CTA (measured: with the stage index, phase, tap
-// and K-chunk recomputed by division every trip the chain was ~150 instructions and a stage was issued only every ~0.5 us,
-// whatever the pipeline depth), so everything loop-invariant is hoisted and the counters advance incrementally.
+// Stream the A / B operand tiles of this CTA's K range through the stage ring.  Called by ALL lanes of the producer warp: the loop
+// state is warp-uniform (the compiler keeps it in uniform registers) and one elected lane issues the barrier arrive and the copies.
+// The loop body is a dependent instruction chain that paces the whole CTA.  Measured (tools/gemm_trace.py, clock64 stamps): with the
+// stage index / phase / tap / K chunk recomputed by integer division every trip a stage was issued every ~1000 cycles whatever the
+// pipeline depth; with incremental counters in a single-lane (divergent) loop ~700; hence everything loop-invariant is hoisted,
+// counters advance incrementally, and the loop runs converged.
+// role: 0 = this warp issues both operands; 1 = A tiles (and arms the barriers), 2 = B tiles only -- two warps then issue in
+// parallel (a tensor copy costs its issuing thread ~200 cycles, and one thread issuing both operands paced the ring).
 template <bool PAIR = false>
 __device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx& t, uint8_t* smem, int stage_bytes,
-                                              uint64_t* full, uint64_t* empty, bool early_b = false) {
+                                              uint64_t* full, uint64_t* empty, bool early_b = false, int role = 0) {
+    const bool leader = ptx::elect_one();
+    const bool do_a = role != 2, do_b = role != 1;
     const int a_inner = p.a_c0 + (p.a_zmode ? 0 : t.zhd * p.a_hoff);
     const int a_bz = p.a_zmode ? t.z : t.zb;
     const int b_inner = p.b_c0 + (p.b_zmode ? 0 : t.zhd * p.b_hoff);
@@ -194,17 +201,20 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx
     // Static B (weights): the first ring's worth of B tiles does not depend on the preceding kernel -- request them, THEN wait for
     // it (programmatic dependent launch); the A tiles of those slots follow in the loop below.
     int pre = 0;
-    if (early_b) {
+    if (early_b && role == 1) pdl_wait();       // the B warp streams the weights on its own; A depends on the preceding kernel
+    if (early_b && role == 0) {
         pre = n_it < stages ? n_it : stages;
-        uint8_t* sbp = smem + a_bytes;
-        int lkp = lk;
-        for (int s = 0; s < pre; ++s, sbp += stage_bytes, lkp += kBlockK) {
-            if constexpr (PAIR) {
-                if (pr == 0) ptx::mbar_expect_tx(&full[s], tx);
-                ptx::tma_load_3d_2sm(sbp, &p.mapB, &full[s], b_inner + lkp, bn0, b_bz);
-            } else {
-                ptx::mbar_expect_tx(&full[s], tx);
-                ptx::tma_load_3d(sbp, &p.mapB, &full[s], b_inner + lkp, bn0, b_bz);
+        if (leader) {
+            uint8_t* sbp = smem + a_bytes;
+            int lkp = lk;
+            for (int s = 0; s < pre; ++s, sbp += stage_bytes, lkp += kBlockK) {
+                if constexpr (PAIR) {
+                    if (pr == 0) ptx::mbar_expect_tx(&full[s], tx);
+                    ptx::tma_load_3d_2sm(sbp, &p.mapB, &full[s], b_inner + lkp, bn0, b_bz);
+                } else {
+                    ptx::mbar_expect_tx(&full[s], tx);
+                    ptx::tma_load_3d(sbp, &p.mapB, &full[s], b_inner + lkp, bn0, b_bz);
+                }
             }
         }
         pdl_wait();
@@ -212,31 +222,34 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx
     for (int li = 0; li < n_it; ++li) {
         const bool b_done = li < pre;          // this slot's barrier is armed and its B tile requested
         if (!b_done) ptx::mbar_wait(&empty[stage], parity);
-        uint8_t* sb = sa + a_bytes;
-        if constexpr (PAIR) {
-            // both CTAs' boxes complete on the even CTA's barrier (tx counts the pair's four boxes)
-            if (pr == 0 && !b_done) ptx::mbar_expect_tx(&full[stage], tx);
-            ptx::tma_load_4d_2sm(sa, &p.mapA, &full[stage], ak, t.x0 + dx, t.y0 + dy, ab);
-            if (!b_done) ptx::tma_load_3d_2sm(sb, &p.mapB, &full[stage], b_inner + lk, bn0, b_bz);
-        } else {
-            if (!b_done) ptx::mbar_expect_tx(&full[stage], tx);
-            if (!a_mn) {
-                ptx::tma_load_4d(sa, &p.mapA, &full[stage], ak, t.x0 + dx, t.y0 + dy, ab);
-                if (two) ptx::tma_load_4d(sa + kAStageBytes, &p.mapA, &full[stage], ak, t.x1 + dx, t.y1 + dy, ab1);
+        if (leader) {
+            uint8_t* sb = sa + a_bytes;
+            if constexpr (PAIR) {
+                // both CTAs' boxes complete on the even CTA's barrier (tx counts the pair's four boxes)
+                if (pr == 0 && !b_done && do_a) ptx::mbar_expect_tx(&full[stage], tx);
+                if (do_a) ptx::tma_load_4d_2sm(sa, &p.mapA, &full[stage], ak, t.x0 + dx, t.y0 + dy, ab);
+                if (!b_done && do_b) ptx::tma_load_3d_2sm(sb, &p.mapB, &full[stage], b_inner + lk, bn0, b_bz);
             } else {
-                ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + t.m0, lk, 0, a_bz);
-                ptx::tma_load_4d(sa + kChunkBytes, &p.mapA, &full[stage], a_inner + t.m0 + 64, lk, 0, a_bz);
+                if (!b_done && do_a) ptx::mbar_expect_tx(&full[stage], tx);
+                if (!do_a) {
+                } else if (!a_mn) {
+                    ptx::tma_load_4d(sa, &p.mapA, &full[stage], ak, t.x0 + dx, t.y0 + dy, ab);
+                    if (two) ptx::tma_load_4d(sa + kAStageBytes, &p.mapA, &full[stage], ak, t.x1 + dx, t.y1 + dy, ab1);
+                } else {
+                    ptx::tma_load_4d(sa, &p.mapA, &full[stage], a_inner + t.m0, lk, 0, a_bz);
+                    ptx::tma_load_4d(sa + kChunkBytes, &p.mapA, &full[stage], a_inner + t.m0 + 64, lk, 0, a_bz);
+                }
+                if (b_done || !do_b) {
+                    // requested before the wait (K-major static B) / the other warp's
+                } else if (!b_mn) {
+                    ptx::tma_load_3d(sb, &p.mapB, &full[stage], b_inner + lk, bn0, b_bz);
+                } else {
+                    for (int j = 0; j < nchunks_b; ++j)
+                        ptx::tma_load_3d(sb + j * kChunkBytes, &p.mapB, &full[stage], b_inner + t.n0 + j * 64, lk, b_bz);
+                }
             }
-            if (b_done) {
-                // requested before the wait (K-major static B)
-            } else if (!b_mn) {
-                ptx::tma_load_3d(sb, &p.mapB, &full[stage], b_inner + lk, bn0, b_bz);
-            } else {
-                for (int j = 0; j < nchunks_b; ++j)
-                    ptx::tma_load_3d(sb + j * kChunkBytes, &p.mapB, &full[stage], b_inner + t.n0 + j * 64, lk, b_bz);
-            }
+            if (traced && li < 3 && do_a) stamp(p, 10 + li);
         }
-        if (traced && li < 3) stamp(p, 10 + li);
         lk += kBlockK;
         ak += kBlockK;
         if (++kc == k_chunks) {
@@ -254,13 +267,16 @@ __device__ __forceinline__ void producer_loop(const GemmParams& p, const TileCtx
             parity ^= 1u;
         }
     }
+    __syncwarp();
 }
 
-// One thread: issue the tcgen05.mma stream of this CTA's K range; accum_full fires when the accumulator is complete.
-// Same discipline as producer_loop: incremental ring / chunk counters, descriptors built by adding to a per-stage base.
+// Issue the tcgen05.mma stream of this CTA's K range; accum_full fires when the accumulator is complete.  Called by ALL lanes of the
+// MMA warp (warp-uniform loop state, one elected lane issues), same discipline as producer_loop: incremental ring / chunk counters,
+// descriptors built by adding to a per-stage base.
 template <bool PAIR = false>
 __device__ __forceinline__ void mma_loop(const GemmParams& p, const TileCtx& t, uint8_t* smem, int stage_bytes,
                                          uint64_t* full, uint64_t* empty, uint64_t* accum_full, uint32_t tmem_base) {
+    const bool leader = ptx::elect_one();
     const uint32_t a_kstep = p.a_mn ? 2048u : 32u;   // bytes per UMMA_K = 16 elements
     const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
     const uint32_t a_lbo = p.a_mn ? (uint32_t)kChunkBytes : 16u;
@@ -288,21 +304,25 @@ __device__ __forceinline__ void mma_loop(const GemmParams& p, const TileCtx& t, 
         ptx::tc_fence_after();
         // The last K chunk of a tap may be partial: head-sliced operands must not read past Kc.
         const int ksteps = (kc == k_chunks - 1) ? k_last : kBlockK / 16;
-        uint64_t adesc = adesc0 + slot_off, bdesc = bdesc0 + slot_off;
-        for (int k = 0; k < ksteps; ++k) {
-            if constexpr (PAIR) {
-                ptx::umma_f16_2sm(tmem_base, adesc, bdesc, idesc, accumulate);
-            } else {
-                ptx::umma_f16(tmem_base, adesc, bdesc, idesc, accumulate);
-                // second 128-row sub-tile against the same B tile -> second accumulator
-                if (two) ptx::umma_f16(tmem1, adesc + a1_off, bdesc, idesc, accumulate);
+        if (leader) {
+            uint64_t adesc = adesc0 + slot_off, bdesc = bdesc0 + slot_off;
+            uint32_t acc = accumulate;
+            for (int k = 0; k < ksteps; ++k) {
+                if constexpr (PAIR) {
+                    ptx::umma_f16_2sm(tmem_base, adesc, bdesc, idesc, acc);
+                } else {
+                    ptx::umma_f16(tmem_base, adesc, bdesc, idesc, acc);
+                    // second 128-row sub-tile against the same B tile -> second accumulator
+                    if (two) ptx::umma_f16(tmem1, adesc + a1_off, bdesc, idesc, acc);
+                }
+                acc = 1u;
+                adesc += a_step;
+                bdesc += b_step;
             }
-            accumulate = 1u;
-            adesc += a_step;
-            bdesc += b_step;
+            if constexpr (PAIR) ptx::umma_commit_2sm(&empty[stage], pair_mask);   // frees the stage in both CTAs
+            else ptx::umma_commit(&empty[stage]);                                 // frees the smem stage once these MMAs have read it
         }
-        if constexpr (PAIR) ptx::umma_commit_2sm(&empty[stage], pair_mask);   // frees the stage in both CTAs
-        else ptx::umma_commit(&empty[stage]);                                 // frees the smem stage once these MMAs have read it
+        accumulate = 1u;
         if (++kc == k_chunks) kc = 0;
         slot_off += slot_step;
         if (++stage == stages) {
@@ -311,8 +331,11 @@ __device__ __forceinline__ void mma_loop(const GemmParams& p, const TileCtx& t, 
             parity ^= 1u;
         }
     }
-    if constexpr (PAIR) ptx::umma_commit_2sm(accum_full, pair_mask);
-    else ptx::umma_commit(accum_full);     // accumulator complete
+    if (leader) {
+        if constexpr (PAIR) ptx::umma_commit_2sm(accum_full, pair_mask);
+        else ptx::umma_commit(accum_full);     // accumulator complete
+    }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -407,9 +430,10 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
     const bool add_res = p.has_res && (!p.split_add || t.split == 0);
     const bool add_bias = p.dsplit || !p.split_add || t.split == 0;
 
+    const bool split_issue = p.split_issue != 0;      // warp 0 issues the A tiles, warp 2 the B tiles (then joins the epilogue)
     if (warp == 0) {
+        producer_loop<PAIR>(p, t, smem, stage_bytes, full, empty, early_b, split_issue ? 1 : 0);       // all lanes: warp-uniform loop, one elected issuer
         if (lane == 0) {
-            producer_loop<PAIR>(p, t, smem, stage_bytes, full, empty, early_b);
             stamp(p, 2);
             if (add_res) {
                 // the pipeline stages are idle once the accumulator is complete: land the residual tile there
@@ -422,12 +446,11 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && mma_leader) {
-            mma_loop<PAIR>(p, t, smem, stage_bytes, full, empty, accum_full, tmem_base);
-            stamp(p, 3);
-        }
+        if (mma_leader) mma_loop<PAIR>(p, t, smem, stage_bytes, full, empty, accum_full, tmem_base);     // all lanes, one elected issuer
+        if (lane == 0 && mma_leader) stamp(p, 3);
     } else {
         // ---------------------------------------------------- epilogue (warps 2..5), thread <-> tile row
+        if (split_issue && warp == 2) producer_loop<PAIR>(p, t, smem, stage_bytes, full, empty, early_b, 2);
         if (early_b) pdl_wait();
         const int e = threadIdx.x - 64;
         const int eset = e >> 7;                // warp quartet: chunks eset, eset + ESETS, ...
@@ -467,6 +490,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                         make_float4(__uint_as_float(raw[4 * u]), __uint_as_float(raw[4 * u + 1]), __uint_as_float(raw[4 * u + 2]),
                                     __uint_as_float(raw[4 * u + 3]));
             }
+            if (e == 0) stamp(p, 6);       // split-K: partial tile parked
         } else
         for (int sub = 0; sub < msub; ++sub) {
             if (t.mt0 + sub >= p.tiles_m) break;          // odd tile count: the last CTA has one sub-tile
@@ -615,6 +639,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
         }
         if (warp >= 2) {
             const int e = threadIdx.x - 64;
+            if (e == 0) stamp(p, 7);       // split-K: every partial of the cluster is visible
             const int rows_per = kBlockM / CS;
             const int row0 = rank * rows_per;
             const int nq = p.BN >> 2;
@@ -719,11 +744,13 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                     }
                 }
             };
+            if (e == 0) stamp(p, 13);      // split-K: reduction starts (addresses mapped)
             if (CS == 16) reduce_rows(std::integral_constant<int, 16>());
             else if (CS == 8) reduce_rows(std::integral_constant<int, 8>());
             else if (CS == 4) reduce_rows(std::integral_constant<int, 4>());
             else if (CS == 2) reduce_rows(std::integral_constant<int, 2>());
             else reduce_rows(std::integral_constant<int, 1>());
+            if (e == 0) stamp(p, 8);       // split-K: this CTA's rows written
             if (G > 1) {
                 // the CTA arriving last for this (tile, row slice) adds the groups' rows in group order
                 uint32_t* flag = reinterpret_cast<uint32_t*>(bias_s + p.BN);
@@ -826,9 +853,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     pdl_launch();     // TMEM is held: dependents may become resident
 
     if (warp == 0) {
-        if (lane == 0) producer_loop(p, t, smem, stage_bytes, full, empty);
+        producer_loop(p, t, smem, stage_bytes, full, empty);
     } else if (warp == 1) {
-        if (lane == 0) mma_loop(p, t, smem, stage_bytes, full, empty, accum_full, tmem_base);
+        mma_loop(p, t, smem, stage_bytes, full, empty, accum_full, tmem_base);
     } else {
         // ---------------------------------------------------- epilogue (warps 2..5)
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -1543,6 +1570,8 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
                           (csplit ? tc.cs : 1) * 2 <= kMaxCluster;
     static const bool early_ok = [] { const char* e = getenv("S2I_GEMM_EARLY_B"); return !(e && e[0] == '0'); }();
     p.early_b = (d.b_static && early_ok) ? 1 : 0;
+    static const bool split_ok = [] { const char* e = getenv("S2I_GEMM_SPLIT_ISSUE"); return !(e && e[0] == '0'); }();
+    p.split_issue = split_ok ? 1 : 0;
     p.pair = cta_pair ? 1 : 0;
     p.b_rows = cta_pair ? BN / 2 : BN;
     p.msub = msub;
