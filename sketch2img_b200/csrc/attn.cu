@@ -123,11 +123,15 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
     const uint32_t tmem_O = tmem_base + (uint32_t)p.nS * 64u;        // S buffers: nS x 64 columns, then O
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------ TMA producer
-            ptx::mbar_expect_tx(q_full, (uint32_t)q_bytes);
-            for (int c = 0; c < p.nkc; ++c)
-                ptx::tma_load_3d(sQ + c * kChunk16, &p.mapQ, q_full, p.q_c0 + h * p.dp + c * 64, q0, b);
+        {
+            // ------------------------------------------------ TMA producer: the whole warp runs the (warp-uniform) loop, one
+            // elected lane issues -- a single-lane loop keeps its state in per-thread registers and converts it for every copy
+            const bool leader = ptx::elect_one();
+            if (leader) {
+                ptx::mbar_expect_tx(q_full, (uint32_t)q_bytes);
+                for (int c = 0; c < p.nkc; ++c)
+                    ptx::tma_load_3d(sQ + c * kChunk16, &p.mapQ, q_full, p.q_c0 + h * p.dp + c * 64, q0, b);
+            }
             // (ring counters advance incrementally: a division per tile in these single-thread loops is a few hundred cycles
             // of dependent latency, see producer_loop in gemm_tc.cu)
             const int stages = p.stages, nkc = p.nkc;
@@ -137,11 +141,13 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
             uint8_t* sK = sKV;
             for (int j = 0, key0 = 0; j < T; ++j, key0 += kTileK) {
                 ptx::mbar_wait(&kv_empty[stage], parity);
-                ptx::mbar_expect_tx(&kv_full[stage], (uint32_t)stage_bytes);
-                uint8_t* sV = sK + k_bytes;
-                for (int c = 0; c < nkc; ++c) {
-                    ptx::tma_load_3d(sK + c * kChunk8, &p.mapKV, &kv_full[stage], kc0 + c * 64, key0, b);
-                    ptx::tma_load_3d(sV + c * kChunk8, &p.mapKV, &kv_full[stage], vc0 + c * 64, key0, b);
+                if (leader) {
+                    ptx::mbar_expect_tx(&kv_full[stage], (uint32_t)stage_bytes);
+                    uint8_t* sV = sK + k_bytes;
+                    for (int c = 0; c < nkc; ++c) {
+                        ptx::tma_load_3d(sK + c * kChunk8, &p.mapKV, &kv_full[stage], kc0 + c * 64, key0, b);
+                        ptx::tma_load_3d(sV + c * kChunk8, &p.mapKV, &kv_full[stage], vc0 + c * 64, key0, b);
+                    }
                 }
                 sK += stage_bytes;
                 if (++stage == stages) {
@@ -152,8 +158,9 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer
+        {
+            // ------------------------------------------------ MMA issuer (whole warp in the loop, one elected lane issues)
+            const bool leader = ptx::elect_one();
             const int nks = p.dp >> 4;             // K steps of the QK^T product
             const int stages = p.stages, nS = p.nS, pbufs = p.pbufs;
             const uint32_t idesc_s = p.idesc_s, idesc_o = p.idesc_o;
@@ -173,13 +180,15 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
                 ptx::mbar_wait(&s_empty[s_buf], s_buf_par);
                 ptx::tc_fence_after();
                 const uint32_t tS = tmem_base + (uint32_t)s_buf * 64u;
-                for (int k = 0; k < nks; ++k) {
-                    // K step k: 64-column chunk k >> 2 (16 KB apart in Q, 8 KB in K), 32 bytes per step inside it
-                    const uint64_t ks = (uint64_t)((k & 3) * 2);
-                    ptx::umma_f16(tS, dQ + (uint64_t)((k >> 2) * (kChunk16 >> 4)) + ks,
-                                  dK0 + s_koff + (uint64_t)((k >> 2) * (kChunk8 >> 4)) + ks, idesc_s, k != 0 ? 1u : 0u);
+                if (leader) {
+                    for (int k = 0; k < nks; ++k) {
+                        // K step k: 64-column chunk k >> 2 (16 KB apart in Q, 8 KB in K), 32 bytes per step inside it
+                        const uint64_t ks = (uint64_t)((k & 3) * 2);
+                        ptx::umma_f16(tS, dQ + (uint64_t)((k >> 2) * (kChunk16 >> 4)) + ks,
+                                      dK0 + s_koff + (uint64_t)((k >> 2) * (kChunk8 >> 4)) + ks, idesc_s, k != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&s_full[s_buf]);
                 }
-                ptx::umma_commit(&s_full[s_buf]);
                 s_koff += stage_step;
                 if (++s_stage == stages) {
                     s_stage = 0;
@@ -207,12 +216,14 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
                 }
                 ptx::mbar_wait(&p_full[pb], pb_par);
                 ptx::tc_fence_after();
-                for (int kk = 0; kk < 4; ++kk) {
-                    ptx::umma_f16(tmem_O, dP0 + poff + (uint64_t)(kk * 2), dV0 + voff + (uint64_t)(kk * (2048 >> 4)), idesc_o, accumulate);
-                    accumulate = 1u;
+                if (leader) {
+                    for (int kk = 0; kk < 4; ++kk)
+                        ptx::umma_f16(tmem_O, dP0 + poff + (uint64_t)(kk * 2), dV0 + voff + (uint64_t)(kk * (2048 >> 4)), idesc_o,
+                                      accumulate | (uint32_t)(kk != 0));
+                    ptx::umma_commit(&kv_empty[stage]);
+                    ptx::umma_commit(&p_empty[pb]);
                 }
-                ptx::umma_commit(&kv_empty[stage]);
-                ptx::umma_commit(&p_empty[pb]);
+                accumulate = 1u;
                 voff += stage_step;
                 if (++stage == stages) {
                     stage = 0;
@@ -225,7 +236,8 @@ __global__ void __launch_bounds__(kThreads, MINB) attn_fwd_kernel(const __grid_c
                     pb_par ^= 1u;
                 }
             }
-            ptx::umma_commit(o_full);
+            if (leader) ptx::umma_commit(o_full);
+            __syncwarp();
         }
     } else {
         // ---------------------------------------------------- softmax + epilogue (one query row per thread)

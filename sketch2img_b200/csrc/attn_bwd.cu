@@ -128,12 +128,15 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
     const uint32_t tmem_acc1 = tmem_acc0 + (uint32_t)p.dp;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------ TMA producer
-            ptx::mbar_expect_tx(r_full, (uint32_t)(2 * r_bytes));
-            for (int c = 0; c < p.nkc; ++c) {
-                ptx::tma_load_3d(sR1 + c * kChunk16, &p.mapR1, r_full, p.r1_c0 + h * p.dp + c * 64, row0, b);
-                ptx::tma_load_3d(sR2 + c * kChunk16, &p.mapR2, r_full, p.r2_c0 + h * p.dp + c * 64, row0, b);
+        {
+            // ------------------------------------------------ TMA producer (whole warp in the loop, one elected lane issues)
+            const bool leader = ptx::elect_one();
+            if (leader) {
+                ptx::mbar_expect_tx(r_full, (uint32_t)(2 * r_bytes));
+                for (int c = 0; c < p.nkc; ++c) {
+                    ptx::tma_load_3d(sR1 + c * kChunk16, &p.mapR1, r_full, p.r1_c0 + h * p.dp + c * 64, row0, b);
+                    ptx::tma_load_3d(sR2 + c * kChunk16, &p.mapR2, r_full, p.r2_c0 + h * p.dp + c * 64, row0, b);
+                }
             }
             // ring counters advance incrementally (no division in the single-thread issue loops, cf. producer_loop in gemm_tc.cu)
             const int stages = p.stages, nkc = p.nkc;
@@ -143,11 +146,13 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
             uint8_t* s1 = sC;
             for (int j = 0, col0 = 0; j < T; ++j, col0 += kCols) {
                 ptx::mbar_wait(&c_empty[stage], parity);
-                ptx::mbar_expect_tx(&c_full[stage], (uint32_t)stage_bytes);
-                uint8_t* s2 = s1 + c_bytes;
-                for (int c = 0; c < nkc; ++c) {
-                    ptx::tma_load_3d(s1 + c * kChunk8, &p.mapC1, &c_full[stage], c1 + c * 64, col0, b);
-                    ptx::tma_load_3d(s2 + c * kChunk8, &p.mapC2, &c_full[stage], c2 + c * 64, col0, b);
+                if (leader) {
+                    ptx::mbar_expect_tx(&c_full[stage], (uint32_t)stage_bytes);
+                    uint8_t* s2 = s1 + c_bytes;
+                    for (int c = 0; c < nkc; ++c) {
+                        ptx::tma_load_3d(s1 + c * kChunk8, &p.mapC1, &c_full[stage], c1 + c * 64, col0, b);
+                        ptx::tma_load_3d(s2 + c * kChunk8, &p.mapC2, &c_full[stage], c2 + c * 64, col0, b);
+                    }
                 }
                 s1 += stage_bytes;
                 if (++stage == stages) {
@@ -158,8 +163,9 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer
+        {
+            // ------------------------------------------------ MMA issuer (whole warp in the loop, one elected lane issues)
+            const bool leader = ptx::elect_one();
             const int nks = p.dp >> 4;
             const int stages = p.stages, nT = p.nT, sbufs = p.sbufs, mode = p.mode;
             const uint32_t idesc_t = p.idesc_t, idesc_acc = p.idesc_acc;
@@ -181,17 +187,19 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
                 ptx::tc_fence_after();
                 const uint32_t t1 = tmem_base + (uint32_t)tb * 64u;
                 const uint32_t t2 = tmem_base + (uint32_t)nT * 64u + (uint32_t)tb * 64u;
-                for (int k = 0; k < nks; ++k) {
-                    const uint64_t ks = (uint64_t)((k & 3) * 2);
-                    ptx::umma_f16(t1, dR1 + (uint64_t)((k >> 2) * (kChunk16 >> 4)) + ks,
-                                  dC1k + t_coff + (uint64_t)((k >> 2) * (kChunk8 >> 4)) + ks, idesc_t, k != 0 ? 1u : 0u);
+                if (leader) {
+                    for (int k = 0; k < nks; ++k) {
+                        const uint64_t ks = (uint64_t)((k & 3) * 2);
+                        ptx::umma_f16(t1, dR1 + (uint64_t)((k >> 2) * (kChunk16 >> 4)) + ks,
+                                      dC1k + t_coff + (uint64_t)((k >> 2) * (kChunk8 >> 4)) + ks, idesc_t, k != 0 ? 1u : 0u);
+                    }
+                    for (int k = 0; k < nks; ++k) {
+                        const uint64_t ks = (uint64_t)((k & 3) * 2);
+                        ptx::umma_f16(t2, dR2 + (uint64_t)((k >> 2) * (kChunk16 >> 4)) + ks,
+                                      dC1k + t_coff + c2_off + (uint64_t)((k >> 2) * (kChunk8 >> 4)) + ks, idesc_t, k != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&t_full[tb]);
                 }
-                for (int k = 0; k < nks; ++k) {
-                    const uint64_t ks = (uint64_t)((k & 3) * 2);
-                    ptx::umma_f16(t2, dR2 + (uint64_t)((k >> 2) * (kChunk16 >> 4)) + ks,
-                                  dC1k + t_coff + c2_off + (uint64_t)((k >> 2) * (kChunk8 >> 4)) + ks, idesc_t, k != 0 ? 1u : 0u);
-                }
-                ptx::umma_commit(&t_full[tb]);
                 t_coff += stage_step;
                 if (++t_stage == stages) {
                     t_stage = 0;
@@ -213,7 +221,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
                 ptx::mbar_wait(&st_full[sb], sb_par);
                 ptx::tc_fence_after();
                 const uint64_t dSt = dSt0 + stoff, dC1 = dC1m + coff, dC2 = dC1 + c2_off;
-                if (mode == 0) {
+                if (!leader) {
+                } else if (mode == 0) {
                     // dQ += dS K_j   (B = K_j read MN-major: N = head channels, K = keys)
                     for (int kk = 0; kk < 4; ++kk)
                         ptx::umma_f16(tmem_acc0, dSt + (uint64_t)(kk * 2), dC1 + (uint64_t)(kk * 128), idesc_acc, accumulate | (uint32_t)(kk != 0));
@@ -226,8 +235,10 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
                                       accumulate | (uint32_t)(kk != 0));
                 }
                 accumulate = 1u;
-                ptx::umma_commit(&c_empty[stage]);
-                ptx::umma_commit(&st_empty[sb]);
+                if (leader) {
+                    ptx::umma_commit(&c_empty[stage]);
+                    ptx::umma_commit(&st_empty[sb]);
+                }
                 coff += stage_step;
                 if (++stage == stages) {
                     stage = 0;
@@ -240,7 +251,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_bwd_kernel(const __grid_cons
                     sb_par ^= 1u;
                 }
             }
-            ptx::umma_commit(acc_full);
+            if (leader) ptx::umma_commit(acc_full);
+            __syncwarp();
         }
     } else {
         // ---------------------------------------------------- softmax warps: thread <-> row token

@@ -814,6 +814,7 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
             d.tag = "gemm_linear";
             d.A = l16c.p; d.aC = C; d.aW = (int)rows; d.aH = 1; d.aB = 1; d.a_sw = l16c.ld;
             d.B = T.ff1.w; d.bI = C; d.bR = 8 * C; d.b_sr = C;
+            d.b_static = 1;
             d.N = 8 * C; d.Kc = C;
             d.bias = T.ff1.b;
             if (save_) {
