@@ -1494,7 +1494,8 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     // tools/gemm_bench.py pair, profiles/r2_gemm_pair_v1.txt: -10..-25 % on the convolutions and the K-heavy projections,
     // +0.3..0.6 us on the 5- and 10-step projections)
     const bool pair_wanted = cluster_mode && tiles_m % 2 == 0 && d.N >= 64 &&
-                             (g_pair_mode == 1 || (g_pair_mode < 0 && num_iters >= 20 && (tiles_m >= 8 || num_iters >= 40)));
+                             (g_pair_mode == 1 ||
+                              (g_pair_mode < 0 && (num_iters >= 40 || (num_iters >= 20 && tiles_m >= 8) || d.N >= 2048)));
     TileChoice tc = choose_tiles_tma(d.N, tiles_m, num_iters, can_split, epi, pair_wanted);
     if (glu && tc.BN % 64 != 0) {
         // value / gate columns come in 32 + 32 pairs: the tile width must hold whole pairs
@@ -1552,14 +1553,15 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
         }
         tc.cs = cs;
         tc.msub = 1;                                  // the partial tile of the reduction is one 128-row accumulator
-        if (pair_wanted && cs == 8 && d.splits <= 0 && d.BN <= 0 && groups == 1) {
-            // pairs of 8-way split tiles are clusters of 16 CTAs, of which 14 fit the chip (7 by the occupancy query, twice that
-            // with two CTAs per SM): widen the tile to 192 if that gets there, else split 4 ways
-            const long pairs = tiles_m / 2;
-            if (pairs * ceil_div(d.N, tc.BN) > 14) {
-                if (d.N >= 192 && pairs * ceil_div(d.N, 192) <= 14) tc.BN = 192;
-                else tc.cs = tc.splits = 4;
-            }
+        if (pair_wanted && d.splits <= 0 && d.BN <= 0 && groups == 1) {
+            // CTA pairs make the K loop cheaper, so fewer, longer splits win (tools/gemm_bench.py psweep, profiles/r2_gemm_pair_v2.txt):
+            // one wave of CTAs (two when every split still has >= 64 K steps), and 192-wide tiles for the 1280-channel levels
+            // (7 column tiles instead of 8: fewer re-reads of A)
+            if (d.N >= 1280 && tc.BN == 160) tc.BN = 192;
+            const long base = tiles_m * ceil_div(d.N, tc.BN);
+            int c2 = 1;
+            while (c2 * 2 <= cs && (base * c2 * 2 <= kNumSMs + 4 || (base * c2 * 2 <= 2 * kNumSMs && num_iters / (c2 * 2) >= 64))) c2 *= 2;
+            if (tiles_m >= 4) tc.cs = tc.splits = c2;
         }
     }
     const int BN = tc.BN;
