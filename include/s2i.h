@@ -68,6 +68,12 @@ typedef struct s2i_gemm_desc {
      * tiles BEFORE waiting for the preceding kernel (programmatic dependent launch), so the weight stream of launch n + 1
      * overlaps the epilogue of launch n.  Leave 0 when B is an activation. */
     int b_static;
+    /* Optional per-channel statistics of the fp32 result, for a GroupNorm that follows (norm1 / norm2 of diffusers' ResnetBlock2D,
+     * the norm of Transformer2DModel): colstat [B][colstat_cap][2][colstat_ld] floats receives, for every block of result rows a
+     * CTA (or one CTA of a split-K cluster) owns, the column sums and the column sums of squares; *colstat_bps (host) is set to the
+     * number of blocks per sample used, or to 0 when this launch could not provide them (the caller then computes the statistics
+     * itself).  Needs the TMA-epilogue kernel, out32, and an exactly tiled pixel grid. */
+    float* colstat; long long colstat_ld; int colstat_cap; int* colstat_bps;
 } s2i_gemm_desc;
 
 int s2i_gemm(const s2i_gemm_desc* d, void* cuda_stream);

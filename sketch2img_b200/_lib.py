@@ -26,6 +26,7 @@ class GemmDesc(C.Structure):
         ("out32", C.c_void_p), ("ld32", C.c_longlong), ("out16", C.c_void_p), ("ld16", C.c_longlong),
         ("out16_bf16", C.c_int), ("c_sb", C.c_longlong), ("c_sh", C.c_longlong), ("relu", C.c_int), ("qscale", C.c_float),
         ("out_glu", C.c_void_p), ("ld_glu", C.c_longlong), ("scratch32", C.c_void_p), ("b_static", C.c_int),
+        ("colstat", C.c_void_p), ("colstat_ld", C.c_longlong), ("colstat_cap", C.c_int), ("colstat_bps", C.POINTER(C.c_int)),
     ]
 
     def __init__(self, **kw):

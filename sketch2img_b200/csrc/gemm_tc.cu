@@ -72,6 +72,10 @@ struct __align__(64) GemmParams {
     // instructions, issued by the even CTA.  Each CTA loads its own 128 A rows and HALF of the B tile (b_rows = BN / 2), so a tile
     // costs 16 KB + BN * 64 B per K step instead of 16 KB + BN * 128 B from L2; accumulators, epilogue and split-K are per CTA.
     int pair, b_rows;
+    // Column statistics of the result for a following GroupNorm (GemmDesc::colstat): cstat [B][cst_cap][2][cst_ld]
+    float* cstat;
+    long cst_ld;
+    int cst_cap, hw_shift;   // hw_shift = log2(tw * th): tile row >> hw_shift = sample within the tile
     int split_issue;         // A and B tiles issued by two warps
     int early_b;             // B is static (weights): its first tiles are requested before griddepcontrol.wait
     int tiles_m;             // number of 128-row M tiles of the problem
@@ -377,6 +381,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
     uint64_t* r_full = accum_full + 1;                      // [kMaxChunks]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + kMaxChunks);
     float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [BN]
+    float* cst_s = bias_s + ((p.BN + 8 + 3) & ~3);          // [ESETS][4 quarters][2][32]: column statistics being combined
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -616,6 +621,39 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                     ptx::tma_store_commit();
                     if (e == 0 && c < 3) stamp(p, 13 + c);
                 }
+                if (p.cstat) {
+                    // column sums / sums of squares of this chunk for the GroupNorm that follows: each warp takes its 32 rows
+                    // from the staged fp32 tile (lane = column: conflict-free under the 128-byte swizzle), the quarters of one
+                    // sample are combined in quarter order, one float per (sample, tile, statistic, column) goes out
+                    const uint8_t* c32 = smem + c * kChunk32Bytes;
+                    const uint32_t cu = (uint32_t)lane >> 2, cw = ((uint32_t)lane & 3u) << 2;
+                    float s1 = 0.f, s2 = 0.f;
+    #pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const uint32_t row = (uint32_t)(q * 32 + rr);
+                        const float v = *reinterpret_cast<const float*>(c32 + row * 128u + (((cu ^ (row & 7u)) << 4) | cw));
+                        s1 += v;
+                        s2 = fmaf(v, v, s2);
+                    }
+                    float* cs = cst_s + eset * 256;
+                    cs[q * 64 + lane] = s1;
+                    cs[q * 64 + 32 + lane] = s2;
+                    ptx::named_bar_sync(2 + eset, 128);
+                    const int qps = (1 << p.hw_shift) >> 5;                  // quarters per sample (tw * th >= 32)
+                    const int bi = (q * 32) >> p.hw_shift;                   // sample within the tile
+                    if ((q & (qps - 1)) == 0 && bi < p.tb) {
+                        float t1 = 0.f, t2 = 0.f;
+                        for (int k = 0; k < qps; ++k) {
+                            t1 += cs[(q + k) * 64 + lane];
+                            t2 += cs[(q + k) * 64 + 32 + lane];
+                        }
+                        const int tile_xy = (ys >> p.th_shift) * p.tiles_x + (xs >> p.tw_shift);
+                        float* dst = p.cstat + (((long)(bs + bi) * p.cst_cap + tile_xy) * 2) * p.cst_ld + t.n0 + c * 32 + lane;
+                        dst[0] = t1;
+                        dst[p.cst_ld] = t2;
+                    }
+                    ptx::named_bar_sync(2 + eset, 128);                      // the scratch is reused by this quartet's next chunk
+                }
             }
         }
         if (el == 0) {
@@ -652,7 +690,8 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
             for (int k = 0; k < kMaxCluster; ++k)       // split k of this tile: cluster rank k, or 2 k + (M tile parity) in pair mode
                 base_k[k] = map_to_rank(part_local, PAIR ? (uint32_t)(k < CS ? 2 * k : 0) + (crank & 1u) : (uint32_t)(k < CS ? k : 0));
             // bias / ReLU / rounding emulation / residual, then the fp32 and / or fp16 rows of the output
-            auto finish = [&](float4 acc, int c4, int n, long grow, const float4& res4) {
+            float* part_own = reinterpret_cast<float*>(smem);
+            auto finish = [&](float4 acc, int c4, int n, long grow, const float4& res4, int row) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c4);
                 acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
                 if (p.relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
@@ -663,6 +702,8 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                     acc.w = __half2float(__float2half_rn(acc.w * p.qinv)) * p.qscale;
                 }
                 if (p.residual) { acc.x += res4.x; acc.y += res4.y; acc.z += res4.z; acc.w += res4.w; }
+                // column statistics: park the finished values in this CTA's own rows of its partial tile (no peer reads those)
+                if (p.cstat) *reinterpret_cast<float4*>(part_own + (long)row * ldp + c4) = acc;
                 if (p.out32) *reinterpret_cast<float4*>(p.out32 + grow * p.ld32 + n) = acc;
                 if (p.out16) {
                     const __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
@@ -739,7 +780,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                                 for (int k = 0; k < 8; ++k) { acc.x += w[k].x; acc.y += w[k].y; acc.z += w[k].z; acc.w += w[k].w; }
                             }
                             if (G > 1) *reinterpret_cast<float4*>(wsT + (long)rows[u] * p.BN + c4s[u]) = acc;   // this group's rows, raw sums
-                            else finish(acc, c4s[u], t.n0 + c4s[u], grow[u], rs[u]);
+                            else finish(acc, c4s[u], t.n0 + c4s[u], grow[u], rs[u], rows[u]);
                         }
                     }
                 }
@@ -751,6 +792,28 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
             else if (CS == 2) reduce_rows(std::integral_constant<int, 2>());
             else reduce_rows(std::integral_constant<int, 1>());
             if (e == 0) stamp(p, 8);       // split-K: this CTA's rows written
+            if (p.cstat && G == 1) {
+                // column statistics of this CTA's row slice (all rows of one sample: host guarantees rows_per <= tw * th)
+                ptx::named_bar_sync(1, 128 * ESETS);
+                const int bi = row0 >> p.hw_shift;
+                if (bi < p.tb) {
+                    const int pps = (1 << p.hw_shift) / rows_per;                          // row slices per sample in this tile
+                    const int tile_xy = (t.y0 >> p.th_shift) * p.tiles_x + (t.x0 >> p.tw_shift);
+                    const int blk = tile_xy * pps + ((row0 & ((1 << p.hw_shift) - 1)) / rows_per);
+                    for (int col = e; col < p.BN; col += 128 * ESETS) {
+                        if (t.n0 + col >= p.N) continue;
+                        float s1 = 0.f, s2 = 0.f;
+                        for (int rr = 0; rr < rows_per; ++rr) {
+                            const float v = part_own[(long)(row0 + rr) * ldp + col];
+                            s1 += v;
+                            s2 = fmaf(v, v, s2);
+                        }
+                        float* dst = p.cstat + (((long)(t.b0 + bi) * p.cst_cap + blk) * 2) * p.cst_ld + t.n0 + col;
+                        dst[0] = s1;
+                        dst[p.cst_ld] = s2;
+                    }
+                }
+            }
             if (G > 1) {
                 // the CTA arriving last for this (tile, row slice) adds the groups' rows in group order
                 uint32_t* flag = reinterpret_cast<uint32_t*>(bias_s + p.BN);
@@ -784,7 +847,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                         }
                         float4 res4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (p.residual) res4 = ldg_f4(p.residual + grow * p.res_ld + n);
-                        finish(acc, c4, n, grow, res4);
+                        finish(acc, c4, n, grow, res4, row);
                     }
                 }
             }
@@ -1594,6 +1657,27 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
     p.has_o32 = (d.out32 && !csplit) ? 1 : 0;
     p.has_o16 = (d.out16 && !csplit) ? 1 : 0;
     p.has_glu = glu ? 1 : 0;
+    // column statistics for a following GroupNorm (GemmDesc::colstat): possible when every tile lies inside the tensor, a block of
+    // result rows (a warp's 32 rows, or one CTA's row slice of a split-K cluster) belongs to one sample, and the blocks fit `cap`
+    p.cstat = nullptr;
+    if (d.colstat_bps) *d.colstat_bps = 0;
+    if (d.colstat && d.colstat_bps && !glu && !p.split_add && msub >= 1 && d.aW % p.tw == 0 && d.aH % p.th == 0 && d.aB % p.tb == 0) {
+        const int hw = p.tw * p.th;
+        const int tiles_xy = p.tiles_x * p.tiles_y;
+        int bps = 0;
+        if (!csplit) {
+            if (d.out32 && hw >= 32) bps = tiles_xy;
+        } else if (groups == 1 && kBlockM / tc.cs <= hw) {
+            bps = tiles_xy * (hw / (kBlockM / tc.cs));
+        }
+        if (bps > 0 && bps <= d.colstat_cap) {
+            p.cstat = d.colstat;
+            p.cst_ld = (long)d.colstat_ld;
+            p.cst_cap = d.colstat_cap;
+            p.hw_shift = p.tw_shift + p.th_shift;
+            *d.colstat_bps = bps;
+        }
+    }
     const int tiles_n = ceil_div(d.N, BN);
     p.tmem_cols = 32;
     while (p.tmem_cols < msub * BN) p.tmem_cols *= 2;
@@ -1605,7 +1689,7 @@ int launch_tma(GemmParams& p, const GemmDesc& d_in, long tiles_m, int num_iters,
                                           (glu ? (nch / 2) * kChunk16Bytes : 0);
     const long grid_m = ceil_div_l(tiles_m, msub);
     const long ctas = grid_m * tiles_n * tc.splits;
-    const size_t tail = (size_t)(2 * 8 + 1 + kMaxChunks) * 8 + 16 + (size_t)BN * 4 + 16 + 1024 + 64;   // barriers, TMEM slot, bias, flag, slack
+    const size_t tail = (size_t)(2 * 8 + 1 + kMaxChunks) * 8 + 16 + (size_t)BN * 4 + 64 + (d.colstat ? 2048 : 0) + 1024 + 64;   // barriers, TMEM slot, bias, flag, column statistics, slack
     // aim for two co-resident CTAs (<= 112 KB each) when more than one wave is coming and they can actually share an SM
     const bool can_pair = 2 * (size_t)stage_bytes + tail <= 112u * 1024u && epi_bytes + tail <= 112u * 1024u && msub * BN <= 256;
     // ... or when the split-K clusters do not fit one CTA per SM (clusters are gang-scheduled: one too many means a second wave)

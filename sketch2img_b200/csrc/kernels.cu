@@ -580,8 +580,7 @@ __global__ void __launch_bounds__(kGnClT) gn_cluster_kernel(const GnClArgs a) {
     float* slab = gsm + kGnClColp + kGnClRed;     // MODE 0: x [P][W];  MODE 1: xhat [P][W] then dxhat [P][W]
     __shared__ double part[2 * kGroups];
     __shared__ float s_mean[kGroups], s_rstd[kGroups], s_m1[kGroups], s_m2[kGroups];
-    pdl_wait();
-    pdl_launch();
+    // index arithmetic and the affine parameters (weights) first: they overlap the tail of the preceding kernel
     const int t = threadIdx.x, b = blockIdx.y;
     const int cs = a.cs;
     const int rank = blockIdx.x % cs;             // == %cluster_ctarank (clusters are 1-D along x)
@@ -598,6 +597,15 @@ __global__ void __launch_bounds__(kGnClT) gn_cluster_kernel(const GnClArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) gl[j] = (4 * q + j) / Cg;
     float gm[4], bt[4], mu[4], rs[4];
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            gm[j] = __ldg(a.gamma + c + j);
+            bt[j] = __ldg(a.beta + c + j);
+        }
+    }
+    pdl_wait();
+    pdl_launch();
     if (MODE == 1) {
         if (t < gpc) {
             const float2 v = reinterpret_cast<const float2*>(a.fslot + (long)b * kSlotDoubles)[g0 + t];
@@ -606,15 +614,11 @@ __global__ void __launch_bounds__(kGnClT) gn_cluster_kernel(const GnClArgs a) {
         }
         __syncthreads();
     }
-    if (active) {
+    if (active && MODE == 1) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            gm[j] = __ldg(a.gamma + c + j);
-            bt[j] = __ldg(a.beta + c + j);
-            if (MODE == 1) {
-                mu[j] = s_mean[gl[j]];
-                rs[j] = s_rstd[gl[j]];
-            }
+            mu[j] = s_mean[gl[j]];
+            rs[j] = s_rstd[gl[j]];
         }
     }
     // ---------------- phase 1: slab reduction (and staging)
@@ -812,6 +816,120 @@ __global__ void __launch_bounds__(kGnClT) gn_cluster_kernel(const GnClArgs a) {
         }
     }
     cluster_wait_();
+}
+
+// ---- statistics from the producer: normalise + SiLU in one streaming pass ------------------------------------------------
+// The GEMM that wrote x also left per-channel partial sums (sum, sum of squares) of every block of rows it owned
+// (gemm_tc.cuh, GemmDesc::colstat: [B][cap][2][ld] floats, `bps` blocks per sample used).  Each CTA here adds the partials of its
+// channels in block order (fixed order: the result does not depend on timing), derives its groups' mean / rstd in double, and
+// streams its [P pixels][W channels] slab once: x is read once and there is no reduction pass, no cluster, no barrier between
+// CTAs.  A concatenated input (up path) brings two sources, one per producer.
+struct GnNormArgs {
+    const float* x; long ldx;
+    int HW, C, Cg, gpc, W, P;
+    const float* sp[2]; int scap[2], sbps[2], sc0[2], sc1[2]; long sld[2]; int nsrc;
+    const float* gamma; const float* beta;
+    float eps; int silu;
+    double* slot;
+    __half* out16; long ld16; __half* raw16; long ldraw;
+};
+constexpr int kGnNormT = 256;
+constexpr int kGnNormMaxW = 512;
+
+__global__ void __launch_bounds__(kGnNormT) gn_norm_kernel(const GnNormArgs a) {
+    __shared__ double chs[2 * kGnNormMaxW];
+    __shared__ float s_mean[kGroups], s_rstd[kGroups];
+    const int t = threadIdx.x, b = blockIdx.z;
+    const int W = a.W, Wq = W >> 2, Cg = a.Cg, gpc = a.gpc;
+    const int c0 = blockIdx.x * W, g0 = blockIdx.x * gpc;
+    const int p0 = blockIdx.y * a.P, p1 = min(a.HW, p0 + a.P);
+    const int prow = kGnNormT / Wq;
+    const int r = t / Wq, q = t - r * Wq;
+    const bool active = r < prow;
+    const int c = c0 + 4 * q;
+    int gl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gl[j] = (4 * q + j) / Cg;
+    float gm[4], bt[4];
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            gm[j] = __ldg(a.gamma + c + j);
+            bt[j] = __ldg(a.beta + c + j);
+        }
+    }
+    pdl_wait();
+    pdl_launch();
+    // channel sums of this CTA's W channels (both statistics), blocks added in order
+    for (int idx = t; idx < 2 * W; idx += kGnNormT) {
+        const int st = idx >= W ? 1 : 0, col = idx - st * W;
+        const int ch = c0 + col;
+        const int k = (a.nsrc > 1 && ch >= a.sc0[1]) ? 1 : 0;
+        const float* src = a.sp[k] + ((long)b * a.scap[k] * 2 + st) * a.sld[k] + (ch - a.sc0[k]);
+        const long step = 2 * a.sld[k];
+        double acc = 0.0;
+        const int n = a.sbps[k];
+        int i = 0;
+        for (; i + 4 <= n; i += 4) {
+            const float v0 = __ldcg(src + (long)i * step), v1 = __ldcg(src + (long)(i + 1) * step);
+            const float v2 = __ldcg(src + (long)(i + 2) * step), v3 = __ldcg(src + (long)(i + 3) * step);
+            acc += (double)v0; acc += (double)v1; acc += (double)v2; acc += (double)v3;
+        }
+        for (; i < n; ++i) acc += (double)__ldcg(src + (long)i * step);
+        chs[idx] = acc;
+    }
+    __syncthreads();
+    if (t < gpc) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int j = 0; j < Cg; ++j) {
+            s1 += chs[t * Cg + j];
+            s2 += chs[W + t * Cg + j];
+        }
+        const double n = (double)Cg * a.HW;
+        const double m = s1 / n;
+        double var = s2 / n - m * m;
+        if (var < 0.0) var = 0.0;
+        float2 o;
+        o.x = (float)m;
+        o.y = (float)(1.0 / sqrt(var + (double)a.eps));
+        s_mean[t] = o.x;
+        s_rstd[t] = o.y;
+        if (blockIdx.y == 0) reinterpret_cast<float2*>(a.slot + (long)b * kSlotDoubles)[g0 + t] = o;
+    }
+    __syncthreads();
+    if (!active) return;
+    float k0[4], k1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        k0[j] = s_mean[gl[j]];
+        k1[j] = s_rstd[gl[j]] * gm[j];
+    }
+    constexpr int U = 4;
+    for (int pb = p0 + r; pb < p1; pb += U * prow) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int pp = pb + u * prow;
+            const long row = (long)b * a.HW + (pp < p1 ? pp : pb);
+            v[u] = ldg4(a.x + row * a.ldx + c);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int pp = pb + u * prow;
+            if (pp >= p1) continue;
+            const long row = (long)b * a.HW + pp;
+            const float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            float y[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float w = (xs[j] - k0[j]) * k1[j] + bt[j];
+                if (a.silu) w = w * sigmoidf_(w);
+                y[j] = w;
+            }
+            *reinterpret_cast<uint2*>(a.out16 + row * a.ld16 + c) = pack_half4(y[0], y[1], y[2], y[3]);
+            if (a.raw16) *reinterpret_cast<uint2*>(a.raw16 + row * a.ldraw + c) = pack_half4(xs[0], xs[1], xs[2], xs[3]);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
@@ -1179,24 +1297,42 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, long ldn, int
 }
 
 // ------------------------------------------------------------------------------------------------ time embedding
+// out[n] = bias[n] + sum_k w[n][k] * act(x[k]): one warp per output row, 16-byte weight loads (all of a lane's loads independent and in
+// flight together), the activated input vector staged once per block in shared memory.  K % 8 == 0, K <= 2048.
 __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, int K, const __half* __restrict__ w,
                                                    const float* __restrict__ bias, int N, int silu_in,
                                                    float* __restrict__ out) {
-    pdl_wait();
-    pdl_launch();
+    __shared__ __align__(16) float xs[2048];
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nv = K >> 3;                       // 16-byte units per weight row
+    // the weights do not depend on the preceding kernel: request this lane's units before waiting for it
+    uint4 wv[8];
+    const uint4* wr = reinterpret_cast<const uint4*>(w + (long)(n < N ? n : 0) * K);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int u = lane + 32 * i;
+        wv[i] = u < nv ? __ldg(wr + u) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    pdl_wait();
+    pdl_launch();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float v = x[k];
+        if (silu_in) v = v * sigmoidf_(v);
+        xs[k] = v;
+    }
+    __syncthreads();
     if (n >= N) return;
-    const __half* wr = w + (long)n * K;
     float acc = 0.f;
-    for (int k = 2 * lane; k < K; k += 64) {
-        const __half2 w2 = *reinterpret_cast<const __half2*>(wr + k);
-        float x0 = x[k], x1 = x[k + 1];
-        if (silu_in) {
-            x0 = x0 * sigmoidf_(x0);
-            x1 = x1 * sigmoidf_(x1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int u = lane + 32 * i;
+        if (u < nv) {
+            const __half2* h = reinterpret_cast<const __half2*>(&wv[i]);
+            const float4 a = *reinterpret_cast<const float4*>(xs + 8 * u), c = *reinterpret_cast<const float4*>(xs + 8 * u + 4);
+            const float2 w0 = __half22float2(h[0]), w1 = __half22float2(h[1]), w2 = __half22float2(h[2]), w3 = __half22float2(h[3]);
+            acc += (w0.x * a.x + w0.y * a.y) + (w1.x * a.z + w1.y * a.w) + (w2.x * c.x + w2.y * c.y) + (w3.x * c.z + w3.y * c.w);
         }
-        acc += __low2float(w2) * x0 + __high2float(w2) * x1;
     }
     acc = warp_sum(acc);
     if (lane == 0) out[n] = acc + (bias ? bias[n] : 0.f);
@@ -1447,6 +1583,54 @@ int gn_forward(const float* x, long ldx, int B, int HW, int C, double* slot, con
     return 0;
 }
 
+bool gn_norm_supported(int C) {
+    static const bool on = [] { const char* e = getenv("S2I_GN_FUSED_STATS"); return !(e && e[0] == '0'); }();
+    if (!on || C % kGroups) return false;
+    const int Cg = C / kGroups;
+    for (int gpc = 1; gpc <= kGroups; gpc *= 2)
+        if ((gpc * Cg) % 4 == 0 && gpc * Cg <= kGnNormMaxW) return true;
+    return false;
+}
+
+int gn_norm(const float* x, long ldx, int B, int HW, int C, const GnStatSrc* src, int nsrc, double* slot, const float* gamma,
+            const float* beta, float eps, int silu, void* out16, long ld16, void* raw16, long ldraw, cudaStream_t st) {
+    S2I_REQ(C % 4 == 0 && C % kGroups == 0 && (ldx & 3) == 0 && (ld16 & 3) == 0 && (ldraw & 3) == 0, "gn_norm: alignment");
+    S2I_REQ(nsrc >= 1 && nsrc <= 2, "gn_norm: one or two statistics sources");
+    GnNormArgs a;
+    memset(&a, 0, sizeof(a));
+    const int Cg = C / kGroups;
+    // channels per CTA: whole groups, rows of at least 256 bytes where the group size allows
+    int gpc = 0;
+    for (int g = 1; g <= kGroups; g *= 2) {
+        const int W = g * Cg;
+        if (W % 4 || W > kGnNormMaxW) continue;
+        gpc = g;
+        if (W >= 64) break;
+    }
+    S2I_REQ(gpc > 0, "gn_norm: no channel chunk fits this channel count");
+    a.x = x; a.ldx = ldx; a.HW = HW; a.C = C; a.Cg = Cg; a.gpc = gpc; a.W = gpc * Cg;
+    const int chunks = kGroups / gpc;
+    // pixel chunks: about four CTAs per SM in total, at least 32 pixel rows each
+    int np = ceil_div(4 * kNumSMs, B * chunks);
+    const int prow = kGnNormT / (a.W / 4);
+    const int max_np = ceil_div(HW, 4 * prow > 32 ? 4 * prow : 32);
+    if (np > max_np) np = max_np;
+    if (np < 1) np = 1;
+    a.P = ceil_div(HW, np);
+    np = ceil_div(HW, a.P);
+    for (int k = 0; k < nsrc; ++k) {
+        a.sp[k] = src[k].p; a.scap[k] = src[k].cap; a.sbps[k] = src[k].bps; a.sld[k] = src[k].ld;
+        a.sc0[k] = src[k].c0; a.sc1[k] = src[k].c1;
+    }
+    a.nsrc = nsrc;
+    a.gamma = gamma; a.beta = beta; a.eps = eps; a.silu = silu;
+    a.slot = slot;
+    a.out16 = (__half*)out16; a.ld16 = ld16; a.raw16 = (__half*)raw16; a.ldraw = ldraw;
+    S2I_LAUNCH((gn_norm_kernel), dim3(chunks, np, B), kGnNormT, 0, st, a);
+    S2I_LAUNCH_CHECK_TAG("gn_forward", 0.0, 0.0);
+    return 0;
+}
+
 int gn_backward(const float* dy, long ldd, const float* x, long ldx, int B, int HW, int C, const double* fslot, double* bslot,
                 const float* gamma, const float* beta, float eps, int silu, const float* add, long ldadd, float* dx32,
                 long ld32, void* dx16, long ld16, cudaStream_t st) {
@@ -1613,7 +1797,7 @@ int nhwc_to_nchw(const float* src, long ldn, int B, int C, int H, int W, float* 
 }
 
 int gemv(const float* x, int K, const void* w16, const float* bias, int N, int silu_in, float* out, cudaStream_t st) {
-    S2I_REQ((K & 1) == 0, "gemv: K must be even");
+    S2I_REQ((K & 7) == 0 && K <= 2048 && (reinterpret_cast<uintptr_t>(w16) & 15) == 0, "gemv: K must be a multiple of 8, at most 2048, and the weights 16-byte aligned");
     S2I_LAUNCH((gemv_kernel), ceil_div(N, 8), 256, 0, st, x, K, (const __half*)w16, bias, N, silu_in, out);
     S2I_LAUNCH_CHECK();
     return 0;

@@ -26,6 +26,18 @@ int gn_bwd_apply(const float* dy, long ldd, const float* x, long ldx, int B, int
 // Fused forms (one launch: reduction, grid-wide arrival, apply); same slot convention as above.
 int gn_forward(const float* x, long ldx, int B, int HW, int C, double* slot, const float* gamma, const float* beta, float eps,
                int silu, void* out16, long ld16, void* raw16, long ldraw, cudaStream_t st);
+// GroupNorm forward with the statistics taken from the producing GEMM (GemmDesc::colstat): per-channel partial sums
+// [B][cap][2][ld] floats (sum, sum of squares), `bps` row blocks per sample, covering the tensor's channels [c0, c1).  One source
+// per producer: two for a concatenated input.  Same outputs as gn_forward (slot included, for the backward).
+struct GnStatSrc {
+    const float* p = nullptr;
+    int cap = 0, bps = 0;
+    long ld = 0;
+    int c0 = 0, c1 = 0;
+};
+bool gn_norm_supported(int C);
+int gn_norm(const float* x, long ldx, int B, int HW, int C, const GnStatSrc* src, int nsrc, double* slot, const float* gamma,
+            const float* beta, float eps, int silu, void* out16, long ld16, void* raw16, long ldraw, cudaStream_t st);
 int gn_backward(const float* dy, long ldd, const float* x, long ldx, int B, int HW, int C, const double* fslot, double* bslot,
                 const float* gamma, const float* beta, float eps, int silu, const float* add, long ldadd, float* dx32,
                 long ld32, void* dx16, long ld16, cudaStream_t st);

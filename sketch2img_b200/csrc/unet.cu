@@ -405,13 +405,38 @@ double* UNet::new_stats() {
     return p;
 }
 
+// GroupNorm forward: statistics from the producer's column sums when the input carries them (F32::st), else the two-phase kernel.
+int UNet::group_norm(const F32& x, int C, double* slot, const float* gamma, const float* beta, float eps, int silu, H16& out,
+                     H16* raw) {
+    const int B = x.B, HW = x.H * x.W;
+    // (every CTA of gn_norm adds up its channels' partials: beyond ~128 blocks per sample that costs more than a second read of x)
+    bool fused = x.nst > 0 && gn_norm_supported(C);
+    for (int k = 0; k < x.nst; ++k) fused = fused && x.st[k].bps <= 128;
+    if (fused)
+        RUN(gn_norm(x.p, x.ld, B, HW, C, x.st, x.nst, slot, gamma, beta, eps, silu, out.p, out.ld, raw ? raw->p : nullptr,
+                    raw ? raw->ld : 0, st_));
+    else
+        RUN(gn_forward(x.p, x.ld, B, HW, C, slot, gamma, beta, eps, silu, out.p, out.ld, raw ? raw->p : nullptr, raw ? raw->ld : 0,
+                       st_));
+    return 0;
+}
+
 int UNet::gemm(const H16& a, bool spatial, int taps, const __half* w, long w_ld, int N, int Kc, const float* bias,
-               const float* rowvec, const F32* residual, F32* out32, H16* out16) {
+               const float* rowvec, const F32* residual, F32* out32, H16* out16, bool stats) {
     // An fp16-only output with a long contraction may be computed split-K through an fp32 scratch: give it its own arena
     // buffer (same allocation in the sizing pass) so its zero-fill joins the step's zero plan instead of a per-call launch.
     float* scratch = nullptr;
     if (gemm_split_add_mode() && out16 && !out32 && (long)Kc * taps >= 1024 && a.rows() * (long)N * 4 <= (32L << 20))
         scratch = dalloc<float>((size_t)a.rows() * N);
+    // column statistics for the GroupNorm that reads this output: [B][cap][2][N] partial sums (same allocation in the sizing pass)
+    float* cst = nullptr;
+    int cst_cap = 0;
+    if (stats && out32 && spatial_stats_ && gn_norm_supported(N)) {
+        const int HW = a.H * a.W;
+        cst_cap = HW / 64 > 32 ? HW / 64 : 32;
+        cst = dalloc<float>((size_t)a.B * cst_cap * 2 * N);
+    }
+    if (out32) out32->nst = 0;
     if (dry_) return 0;
     ARENA_CHECK();
     GemmDesc d;
@@ -449,7 +474,29 @@ int UNet::gemm(const H16& a, bool spatial, int taps, const __half* w, long w_ld,
         d.ld16 = out16->ld;
     }
     d.scratch32 = scratch;
-    return gemm_launch(d, st_);
+    int bps = 0;
+    if (cst) {
+        // the pixel geometry of the OUTPUT: a non-spatial A (im2col rows) still produces B * H * W result rows in sample order
+        if (!spatial) {
+            d.aW = a.W; d.aH = a.H; d.aB = a.B;
+            d.a_sw = a.ld; d.a_sh = a.ld * a.W; d.a_sb = a.ld * a.W * a.H;
+        }
+        d.colstat = cst;
+        d.colstat_ld = N;
+        d.colstat_cap = cst_cap;
+        d.colstat_bps = &bps;
+    }
+    S2I_TRY(gemm_launch(d, st_));
+    if (cst && bps > 0) {
+        out32->nst = 1;
+        out32->st[0].p = cst;
+        out32->st[0].cap = cst_cap;
+        out32->st[0].bps = bps;
+        out32->st[0].ld = N;
+        out32->st[0].c0 = 0;
+        out32->st[0].c1 = N;
+    }
+    return 0;
 }
 
 int UNet::accumulate(F32& acc, const F32& g) {
@@ -490,14 +537,13 @@ int UNet::resblock(int idx, const F32& x, F32& out) {
     H16 a1 = new16(B, H, W, R.Cin);
     H16 x16;
     if (R.has_sc) x16 = new16(B, H, W, R.Cin);
-    RUN(gn_forward(x.p, x.ld, B, HW, R.Cin, s1, R.n1.g, R.n1.b, R.n1.eps, 1, a1.p, a1.ld, R.has_sc ? x16.p : nullptr,
-                   R.has_sc ? x16.ld : 0, st_));
+    S2I_TRY(group_norm(x, R.Cin, s1, R.n1.g, R.n1.b, R.n1.eps, 1, a1, R.has_sc ? &x16 : nullptr));
     F32 h1 = new32(B, H, W, R.Cout);
     S2I_TRY(gemm(a1, true, 9, R.c1.w, 9L * R.Cin, R.Cout, R.Cin, R.c1.b, R.temb_off >= 0 ? temb_ + R.temb_off : nullptr, nullptr, &h1,
-                 nullptr));
+                 nullptr, true));
     double* s2 = new_stats();
     H16 a2 = new16(B, H, W, R.Cout);
-    RUN(gn_forward(h1.p, h1.ld, B, HW, R.Cout, s2, R.n2.g, R.n2.b, R.n2.eps, 1, a2.p, a2.ld, nullptr, 0, st_));
+    S2I_TRY(group_norm(h1, R.Cout, s2, R.n2.g, R.n2.b, R.n2.eps, 1, a2, nullptr));
     F32 res = x;
     if (R.has_sc) {
         F32 sc = new32(B, H, W, R.Cout);
@@ -505,7 +551,7 @@ int UNet::resblock(int idx, const F32& x, F32& out) {
         res = sc;
     }
     out = out32(B, H, W, R.Cout);
-    S2I_TRY(gemm(a2, true, 9, R.c2.w, 9L * R.Cout, R.Cout, R.Cout, R.c2.b, nullptr, &res, &out, nullptr));
+    S2I_TRY(gemm(a2, true, 9, R.c2.w, 9L * R.Cout, R.Cout, R.Cout, R.c2.b, nullptr, &res, &out, nullptr, true));
     if (keep_debug) {
         debug["r" + std::to_string(idx) + ".h1"] = h1;
         debug["r" + std::to_string(idx) + ".out"] = out;
@@ -729,7 +775,7 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     sv.x = x;
     sv.gs = new_stats();
     H16 n16 = new16(B, H, W, C);
-    RUN(gn_forward(x.p, x.ld, B, HW, C, sv.gs, T.gn.g, T.gn.b, T.gn.eps, 0, n16.p, n16.ld, nullptr, 0, st_));
+    S2I_TRY(group_norm(x, C, sv.gs, T.gn.g, T.gn.b, T.gn.eps, 0, n16, nullptr));
     sv.t0 = new32(B, H, W, C);
     S2I_TRY(gemm(n16, false, 1, T.proj_in.w, C, C, C, T.proj_in.b, nullptr, nullptr, &sv.t0, nullptr));
     // --- self attention
@@ -833,7 +879,7 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     H16 t3 = new16(B, H, W, C);
     S2I_TRY(gemm(g16, false, 1, T.ff2.w, 4 * C, C, 4 * C, T.ff2.b, nullptr, &sv.t2, nullptr, &t3));
     out = out32(B, H, W, C);
-    S2I_TRY(gemm(t3, false, 1, T.proj_out.w, C, C, C, T.proj_out.b, nullptr, &x, &out, nullptr));
+    S2I_TRY(gemm(t3, false, 1, T.proj_out.w, C, C, C, T.proj_out.b, nullptr, &x, &out, nullptr, true));
     if (keep_debug) {
         const std::string pre = "t" + std::to_string(idx);
         debug[pre + ".t0"] = sv.t0;
@@ -958,7 +1004,7 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
     skips_.clear();
     reserve_skip(0);
     F32 h = out32(B, H, W, boc[0]);
-    S2I_TRY(gemm(col, false, 1, conv_in_.w, 64, boc[0], 64, conv_in_.b, nullptr, nullptr, &h, nullptr));
+    S2I_TRY(gemm(col, false, 1, conv_in_.w, 64, boc[0], 64, conv_in_.b, nullptr, nullptr, &h, nullptr, true));
     if (keep_debug) debug["conv_in"] = h;
 
     skips_.push_back(h);
@@ -983,7 +1029,7 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
             RUN(im2col3x3(h.p, h.ld, B, h.H, h.W, C, 2, c2.p, c2.ld, st_));
             reserve_skip((int)skips_.size());
             F32 o = out32(B, Ho, Wo, C);
-            S2I_TRY(gemm(c2, false, 1, down_[i].w, 9L * C, C, 9 * C, down_[i].b, nullptr, nullptr, &o, nullptr));
+            S2I_TRY(gemm(c2, false, 1, down_[i].w, 9L * C, C, 9 * C, down_[i].b, nullptr, nullptr, &o, nullptr, true));
             h = o;
             skips_.push_back(h);
             taps[i] = h;
@@ -1022,6 +1068,15 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
             if (cat.C != h.C + sk.C || cat.H != h.H || h.p != cat.p || sk.p != cat.p + h.C)
                 return set_error(S2I_ERR_STATE, "unet: concat plan out of sync at up resnet %d", k);
             up_cat_.push_back({h.C, sp});
+            // the concat's statistics: the first half from whatever produced h, the second from the skip's producer
+            cat.nst = 0;
+            if (h.nst == 1 && sk.nst == 1) {
+                cat.nst = 2;
+                cat.st[0] = h.st[0];
+                cat.st[1] = sk.st[0];
+                cat.st[1].c0 = h.C;
+                cat.st[1].c1 = h.C + sk.C;
+            }
             // whichever call ends this iteration produces the first half of the next concat buffer
             const bool ups = j == cfg.layers && i < 3, tfm = i > 0, more = k + 1 < K;
             F32 o;
@@ -1039,7 +1094,7 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
             RUN(upsample2x(h.p, h.ld, B, h.H, h.W, h.C, u.p, u.ld, st_));
             reserve(cats[(i + 1) * (cfg.layers + 1)], 0, cat_h[(i + 1) * (cfg.layers + 1)]);
             F32 o = out32(B, 2 * h.H, 2 * h.W, h.C);
-            S2I_TRY(gemm(u, true, 9, up_[i].w, 9L * h.C, h.C, h.C, up_[i].b, nullptr, nullptr, &o, nullptr));
+            S2I_TRY(gemm(u, true, 9, up_[i].w, 9L * h.C, h.C, h.C, up_[i].b, nullptr, nullptr, &o, nullptr, true));
             h = o;
             taps[6 + i] = h;
         }
@@ -1048,7 +1103,7 @@ int UNet::run_forward(const float* x_nchw, float t, float* eps_nchw) {
     // ---- out
     double* so = new_stats();
     H16 a = new16(B, H, W, boc[0]);
-    RUN(gn_forward(h.p, h.ld, B, H * W, boc[0], so, norm_out_.g, norm_out_.b, norm_out_.eps, 1, a.p, a.ld, nullptr, 0, st_));
+    S2I_TRY(group_norm(h, boc[0], so, norm_out_.g, norm_out_.b, norm_out_.eps, 1, a, nullptr));
     F32 eps = new32(B, H, W, cfg.out_ch);
     S2I_TRY(gemm(a, true, 9, conv_out_.w, 9L * boc[0], cfg.out_ch, boc[0], conv_out_.b, nullptr, nullptr, &eps, nullptr));
     RUN(nhwc_to_nchw(eps.p, eps.ld, B, cfg.out_ch, H, W, eps_nchw, st_));

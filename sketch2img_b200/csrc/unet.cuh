@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace s2i {
 
@@ -41,6 +42,10 @@ struct F32 {
     // so no separate cast launch); same shape, pixel stride hld
     __half* h = nullptr;
     long hld = 0;
+    // per-channel partial sums left by the GEMM(s) that produced this tensor (kernels.cuh gn_norm): a following GroupNorm takes
+    // its statistics from them instead of reading the tensor twice.  Two sources for an up-path concat buffer.
+    GnStatSrc st[2];
+    int nst = 0;
     long rows() const { return (long)B * H * W; }
 };
 struct H16 {
@@ -189,6 +194,7 @@ class UNet {
     // but measured SLOWER on B200 (448 vs 442 ms/image) -- 10 M erf evaluations per level-0 projection land on the 8 epilogue
     // warps of each CTA instead of a full-occupancy elementwise kernel -- so it is off unless S2I_GLU_FUSION=1
     bool fuse_glu_ = false;
+    bool spatial_stats_ = true;      // GroupNorm statistics from the producing GEMM's epilogue (S2I_GN_FUSED_STATS=0: off)
 
     size_t arena_bytes() const { return arena_.cap; }
     // Which transformer blocks currently have a sketch feature (bit i = block i in load order): part of the activation
@@ -253,7 +259,9 @@ class UNet {
 
     int k(int rc) { return rc; }
     int gemm(const H16& a, bool spatial, int taps, const __half* w, long w_ld, int N, int Kc, const float* bias,
-             const float* rowvec, const F32* residual, F32* out32, H16* out16);
+             const float* rowvec, const F32* residual, F32* out32, H16* out16, bool stats = false);
+    int group_norm(const F32& x, int C, double* slot, const float* gamma, const float* beta, float eps, int silu, H16& out,
+                   H16* raw);
     int resblock(int idx, const F32& x, F32& out);
     int resblock_bwd(int idx, const F32& dout, F32& dx);
     int transformer(int idx, const F32& x, F32& out);

@@ -394,3 +394,44 @@ def test_gated_gelu_epilogue(L, cuda, M, C, keep, msub):
     with pytest.raises(L.S2IError):
         L.gemm(L.GemmDesc(A=x.data_ptr(), aC=C, aW=M, a_sw=C, B=wp.data_ptr(), bI=C, bR=N, b_sr=C, N=N, Kc=C,
                           out_glu=out.data_ptr(), ld_glu=Fw, out32=o32.data_ptr(), ld32=N))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps", [(2, 64, 64, 320, 320, 9), (2, 32, 32, 640, 640, 9), (2, 16, 16, 1280, 1280, 9),
+                                                 (2, 8, 8, 1280, 1280, 9), (2, 64, 64, 320, 320, 1), (2, 16, 16, 1280, 1280, 1),
+                                                 (1, 8, 8, 1280, 640, 9), (2, 32, 32, 960, 640, 9)])
+def test_column_statistics_for_groupnorm(L, cuda, B, H, W, Cin, Cout, taps):
+    """GemmDesc.colstat: the per-block column sums / sums of squares a following GroupNorm takes its statistics from
+    (norm1 / norm2 of diffusers' ResnetBlock2D inside modules/pipeline.py:96).  Summed over the blocks of a sample they must equal
+    the sums of the fp32 result the same launch wrote, whichever form the launch takes (single CTAs, CTA pairs, cluster split-K),
+    and be the same bits on every run."""
+    if not L.tma_epilogue:
+        pytest.skip("column statistics come from the TMA-epilogue kernel")
+    import ctypes as C
+    g = torch.Generator(device="cpu").manual_seed(B * 31 + Cin + H + taps)
+    x = torch.randn(B, H, W, Cin, generator=g).to(cuda).half()
+    w = (torch.randn(Cout, taps * Cin, generator=g) * 0.02).to(cuda).half()
+    bias = torch.randn(Cout, generator=g).to(cuda)
+    r = torch.randn(B, H, W, Cout, generator=g).to(cuda)
+    cap = max(32, H * W // 64)
+    runs = []
+    for rep in range(2):
+        out32 = torch.zeros(B, H, W, Cout, device=cuda)
+        stat = torch.full((B, cap, 2, Cout), float("nan"), device=cuda)
+        bps = C.c_int(-1)
+        d = L.GemmDesc(A=x.data_ptr(), aC=Cin, aW=W, aH=H, aB=B, a_sw=Cin, a_sh=Cin * W, a_sb=Cin * W * H, taps=taps,
+                       B=w.data_ptr(), bI=taps * Cin, bR=Cout, b_sr=taps * Cin, N=Cout, Kc=Cin, bias=bias.data_ptr(),
+                       residual=r.data_ptr(), res_ld=Cout, out32=out32.data_ptr(), ld32=Cout,
+                       colstat=stat.data_ptr(), colstat_ld=Cout, colstat_cap=cap, colstat_bps=C.pointer(bps))
+        L.gemm(d)
+        torch.cuda.synchronize()
+        n = bps.value
+        assert 0 < n <= cap, f"the launch did not provide statistics (bps = {n})"
+        used = stat[:, :n].double()
+        assert torch.isfinite(used).all()
+        assert torch.isnan(stat[:, n:]).all()                               # nothing written beyond the blocks in use
+        flat = out32.double().reshape(B, H * W, Cout)
+        s1, s2 = flat.sum(1), (flat * flat).sum(1)
+        assert (used[:, :, 0].sum(1) - s1).abs().max() <= 1e-4 * s1.abs().max() + 1e-2
+        assert ((used[:, :, 1].sum(1) - s2).abs() / s2).max() < 1e-5
+        runs.append(stat[:, :n].clone())
+    assert torch.equal(runs[0], runs[1])
