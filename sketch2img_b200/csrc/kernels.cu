@@ -869,13 +869,13 @@ __global__ void __launch_bounds__(kGnNormT) gn_norm_kernel(const GnNormArgs a) {
         const long step = 2 * a.sld[k];
         double acc = 0.0;
         const int n = a.sbps[k];
-        for (int i0 = 0; i0 < n; i0 += 16) {        // 16 loads in flight, added in block order
-            float w[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) w[i] = (i0 + i < n) ? __ldcg(src + (long)(i0 + i) * step) : 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc += (double)w[i];
+        int i = 0;
+        for (; i + 4 <= n; i += 4) {
+            const float v0 = __ldcg(src + (long)i * step), v1 = __ldcg(src + (long)(i + 1) * step);
+            const float v2 = __ldcg(src + (long)(i + 2) * step), v3 = __ldcg(src + (long)(i + 3) * step);
+            acc += (double)v0; acc += (double)v1; acc += (double)v2; acc += (double)v3;
         }
+        for (; i < n; ++i) acc += (double)__ldcg(src + (long)i * step);
         chs[idx] = acc;
     }
     __syncthreads();
