@@ -431,7 +431,8 @@ int UNet::gemm(const H16& a, bool spatial, int taps, const __half* w, long w_ld,
     // column statistics for the GroupNorm that reads this output: [B][cap][2][N] partial sums (same allocation in the sizing pass)
     float* cst = nullptr;
     int cst_cap = 0;
-    if (stats && out32 && spatial_stats_ && gn_norm_supported(N)) {
+    // (only while a sample has at most 128 row blocks: beyond that group_norm() keeps the two-phase kernel, e.g. the VAE at 512 x 512)
+    if (stats && out32 && spatial_stats_ && gn_norm_supported(N) && a.H * a.W <= 128 * 128) {
         const int HW = a.H * a.W;
         cst_cap = HW / 64 > 32 ? HW / 64 : 32;
         cst = dalloc<float>((size_t)a.B * cst_cap * 2 * N);
