@@ -762,6 +762,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                             }
                         }
                     }
+                    if (e == 0 && base == 0) stamp(p, 14);       // split-K: first trip's loads issued
     #pragma unroll
                     for (int u = 0; u < kU; ++u) {
                         if (grow[u] >= 0) {
@@ -783,6 +784,7 @@ gemm_tma_kernel(const __grid_constant__ GemmParams p) {
                             else finish(acc, c4s[u], t.n0 + c4s[u], grow[u], rs[u], rows[u]);
                         }
                     }
+                    if (e == 0 && base == 0) stamp(p, 15);       // split-K: first trip finished
                 }
             };
             if (e == 0) stamp(p, 13);      // split-K: reduction starts (addresses mapped)

@@ -13,6 +13,8 @@ from tools.gemm_bench import SHAPES, make  # noqa: E402
 
 NAMES = ["entry", "setup", "loads_issued", "mmas_issued", "epi_start", "accum_ready", "res_ready", "chunks_done", "stores_read", "exit",
          "load0", "load1", "load2", "chunk0", "chunk1", "chunk2"]
+# split-K launches reuse slots: res_ready = partial tile parked, chunks_done = cluster barrier passed, chunk0 = reduction starts,
+# chunk1 = first trip's loads issued, chunk2 = first trip finished, stores_read = rows written
 
 
 def main():
@@ -20,7 +22,7 @@ def main():
     lib.s2i_gemm_set_trace.argtypes = [C.c_void_p]
     buf = torch.zeros(4096 * 16, dtype=torch.int64, device="cuda")
     for shape in SHAPES:
-        want = sys.argv[1:] or ["lin 320->320 @64 res", "conv 320@64", "qkv 320->1152 @64", "conv 1280@16", "conv 1280@8", "lin 1280->1280 @8 res"]
+        want = sys.argv[1:] or ["lin 320->320 @64 res", "conv 320@64", "qkv 320->1152 @64", "conv 1280@16", "conv 1280@8", "lin 1280->1280 @8 res", "lin 1280->1280 @16 res", "conv 640@32"]
         if shape[0] not in want:
             continue
         kw, keep = make(shape)
