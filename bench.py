@@ -478,8 +478,10 @@ def run_ours(args):
                     "algorithmic_flops_per_image_all_kernels": fl["image"],
                     "other_tensor_kernels": {"attn_fwd_kernel": tensor_class("attn_fwd"), "attn_bwd_kernel": tensor_class("attn_bwd")},
                     "note": "B = 2 (one CFG pair): activations stay in the 126 MB L2 from producer to consumer, the 1.7 GB of weights "
-                            "stream from HBM once per forward (traffic = the cold capture: unique operand bytes, no re-reads); what "
-                            "binds most launches is per-launch latency and the L2 -> SM operand rate (DESIGN.md section 4)",
+                            "stream from HBM once per forward (traffic = the cold capture: unique operand bytes, no re-reads); at batch 1 "
+                            "the ~310 GEMM launches of a step average 17 us: what binds them is per-launch latency (prologue, first "
+                            "loads, split-K reduction) and the write-bound epilogues, not the tensor pipe -- four images per call "
+                            "run the same kernels at 214 ms per image (batch_sweep; DESIGN.md section 4)",
                     "how": "sum of algorithmic FLOPs of one image's GEMM launches / sum of their CUDA-event durations "
                            "(s2i_profile_begin/end on the launch stream)"}
         breakdown = {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in
