@@ -123,7 +123,7 @@ int s2i_unet_create(const s2i_unet_config* c, s2i_unet** out) {
     if (cfg.cross_dim % 8 != 0) return s2i::set_error(S2I_ERR_ARG, "cross_attention_dim must be a multiple of 8");
     *out = new s2i_unet{new s2i::UNet(cfg)};
     if (const char* e = getenv("S2I_NO_FLASH")) (*out)->impl->use_flash_ = !(e[0] == '1');
-    if (const char* e = getenv("S2I_GLU_FUSION")) (*out)->impl->fuse_glu_ = e[0] == '1';
+    if (const char* e = getenv("S2I_GLU_FUSION")) (*out)->impl->fuse_glu_ = atoi(e);
     return 0;
 }
 

@@ -362,7 +362,7 @@ constexpr int kMaxChunks = 8;
 // PAIR: the CTA-pair form (GemmParams::pair) -- its own instantiations: a kernel containing cta_group::2 instructions can only be
 // launched as clusters of an even number of CTAs.
 template <int ESETS, bool GLU, bool PAIR = false>
-__global__ void __launch_bounds__(64 + 128 * ESETS, (ESETS == 2 && !GLU) ? 2 : 1)
+__global__ void __launch_bounds__(64 + 128 * ESETS, ESETS == 2 ? 2 : 1)
 gemm_tma_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

@@ -853,7 +853,8 @@ int UNet::transformer(int idx, const F32& x, F32& out) {
     // GEGLU: the projection's epilogue applies value * gelu(gate) (interleaved weight rows, see Loader::linear_glu); the
     // projection itself is only written when the backward needs it
     H16 g16 = new16(B, H, W, 4 * C);
-    if (fuse_glu_) {
+    // S2I_GLU_FUSION=2: fuse only in forwards that save nothing for a backward (there the epilogue writes the gated output alone)
+    if (fuse_glu_ == 1 || (fuse_glu_ == 2 && !save_)) {
         if (save_) sv.ff = new16(B, H, W, 8 * C);
         if (!dry_) {
             ARENA_CHECK();

@@ -193,7 +193,7 @@ class UNet {
     // GEGLU inside the projection's epilogue (gemm_tma_kernel<2, true>) instead of a separate geglu_fwd launch: parity-green
     // but measured SLOWER on B200 (448 vs 442 ms/image) -- 10 M erf evaluations per level-0 projection land on the 8 epilogue
     // warps of each CTA instead of a full-occupancy elementwise kernel -- so it is off unless S2I_GLU_FUSION=1
-    bool fuse_glu_ = false;
+    int fuse_glu_ = 1;               // gated-GELU in the ff1 epilogue: 0 never (separate geglu kernel), 1 always, 2 only when nothing is saved for a backward
     bool spatial_stats_ = true;      // GroupNorm statistics from the producing GEMM's epilogue (S2I_GN_FUSED_STATS=0: off)
 
     size_t arena_bytes() const { return arena_.cap; }
