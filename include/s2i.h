@@ -131,6 +131,13 @@ int s2i_attention_backward(const void* q, long long ldq, int q_c0, const void* k
 int s2i_groupnorm_forward(const float* x, long long ldx, int B, int HW, int C, const float* gamma, const float* beta,
                           float eps, int silu, void* out16, long long ld16, void* raw16, long long ldraw, void* stats,
                           void* cuda_stream);
+/* The same forward with the statistics taken from the GEMM that produced x (s2i_gemm_desc.colstat: per-block column sums and sums
+ * of squares [B][colstat_cap][2][colstat_ld], colstat_bps blocks per sample in use): ONE streaming pass over x, no reduction pass.
+ * `stats` receives the per-group mean / rstd like s2i_groupnorm_forward (the backward reads them). */
+int s2i_groupnorm_forward_colstat(const float* x, long long ldx, int B, int HW, int C, const float* colstat,
+                                  long long colstat_ld, int colstat_cap, int colstat_bps, const float* gamma,
+                                  const float* beta, float eps, int silu, void* out16, long long ld16, void* raw16,
+                                  long long ldraw, void* stats, void* cuda_stream);
 int s2i_groupnorm_backward(const float* dy, long long ldd, const float* x, long long ldx, int B, int HW, int C,
                            const float* gamma, const float* beta, float eps, int silu, const void* fwd_stats,
                            void* bwd_stats, const float* add, long long ldadd, float* dx32, long long ld32, void* dx16,

@@ -88,6 +88,8 @@ def lib():
     h.s2i_unet_tap_stride.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong)]
     L = C.c_longlong
     h.s2i_groupnorm_forward.argtypes = [vp, L, C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_int, vp, L, vp, L, vp, vp]
+    h.s2i_groupnorm_forward_colstat.argtypes = [vp, L, C.c_int, C.c_int, C.c_int, vp, L, C.c_int, C.c_int, vp, vp, C.c_float, C.c_int,
+                                                vp, L, vp, L, vp, vp]
     h.s2i_groupnorm_backward.argtypes = [vp, L, vp, L, C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp, vp, L,
                                          vp, L, vp, L, vp]
     h.s2i_unet_backward.argtypes = [vp, C.POINTER(vp), vp, vp]

@@ -63,6 +63,21 @@ int s2i_groupnorm_forward(const float* x, long long ldx, int B, int HW, int C, c
                            static_cast<cudaStream_t>(cuda_stream));
 }
 
+int s2i_groupnorm_forward_colstat(const float* x, long long ldx, int B, int HW, int C, const float* colstat,
+                                  long long colstat_ld, int colstat_cap, int colstat_bps, const float* gamma,
+                                  const float* beta, float eps, int silu, void* out16, long long ld16, void* raw16,
+                                  long long ldraw, void* stats, void* cuda_stream) {
+    if (!x || !colstat || !gamma || !beta || !out16 || !stats)
+        return s2i::set_error(S2I_ERR_ARG, "s2i_groupnorm_forward_colstat: null argument");
+    if (B < 1 || HW < 1 || C < 32 || colstat_bps < 1 || colstat_bps > colstat_cap || colstat_ld < C)
+        return s2i::set_error(S2I_ERR_ARG, "s2i_groupnorm_forward_colstat: bad shape");
+    if (!s2i::gn_norm_supported(C)) return s2i::set_error(S2I_ERR_ARG, "s2i_groupnorm_forward_colstat: unsupported channel count %d", C);
+    s2i::GnStatSrc src;
+    src.p = colstat; src.cap = colstat_cap; src.bps = colstat_bps; src.ld = colstat_ld; src.c0 = 0; src.c1 = C;
+    return s2i::gn_norm(x, ldx, B, HW, C, &src, 1, static_cast<double*>(stats), gamma, beta, eps, silu, out16, ld16, raw16, ldraw,
+                        static_cast<cudaStream_t>(cuda_stream));
+}
+
 int s2i_groupnorm_backward(const float* dy, long long ldd, const float* x, long long ldx, int B, int HW, int C,
                            const float* gamma, const float* beta, float eps, int silu, const void* fwd_stats,
                            void* bwd_stats, const float* add, long long ldadd, float* dx32, long long ld32, void* dx16,

@@ -114,3 +114,54 @@ def test_groupnorm_rejects_bad_arguments(L, cuda):
     with pytest.raises(L.S2IError):      # null input
         L.check(lib.s2i_groupnorm_forward(None, 64, 1, 16, 64, w.data_ptr(), w.data_ptr(), 1e-5, 1, out.data_ptr(), 64,
                                           None, 0, st.data_ptr(), L.stream_ptr()))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,C,taps", [(2, 64, 64, 320, 320, 9), (2, 32, 32, 320, 640, 9), (2, 16, 16, 640, 1280, 1),
+                                              (2, 8, 8, 1280, 1280, 9), (1, 64, 64, 320, 320, 1), (2, 32, 32, 960, 960, 1)])
+@pytest.mark.parametrize("silu", [1, 0])
+def test_groupnorm_forward_from_producer_statistics(L, cuda, B, H, W, Cin, C, taps, silu):
+    """gn_norm_kernel (C ABI s2i_groupnorm_forward_colstat): the GEMM that produces x leaves per-block column sums
+    (s2i_gemm_desc.colstat) and the GroupNorm takes its statistics from them -- ONE pass over x.  Same reference, same
+    tolerance as the two-phase kernel, the per-group statistics handed to the backward included, and the same bits twice."""
+    import ctypes as C_
+    g = torch.Generator().manual_seed(B * 131 + H + C + taps)
+    a = torch.randn(B, H, W, Cin, generator=g).to(cuda).half()
+    w = (torch.randn(C, taps * Cin, generator=g) * 0.03).to(cuda).half()
+    bias = (torch.randn(C, generator=g) * 0.5).to(cuda)
+    gamma = (1.0 + 0.2 * torch.randn(C, generator=g)).to(cuda)
+    beta = (0.1 * torch.randn(C, generator=g)).to(cuda)
+    HW, eps = H * W, 1e-5
+    cap = max(32, HW // 64)
+    x = torch.zeros(B, H, W, C, device=cuda)
+    stat = torch.zeros(B, cap, 2, C, device=cuda)
+    bps = C_.c_int(0)
+    d = L.GemmDesc(A=a.data_ptr(), aC=Cin, aW=W, aH=H, aB=B, a_sw=Cin, a_sh=Cin * W, a_sb=Cin * W * H, taps=taps,
+                   B=w.data_ptr(), bI=taps * Cin, bR=C, b_sr=taps * Cin, N=C, Kc=Cin, bias=bias.data_ptr(),
+                   out32=x.data_ptr(), ld32=C, colstat=stat.data_ptr(), colstat_ld=C, colstat_cap=cap,
+                   colstat_bps=C_.pointer(bps))
+    L.gemm(d)
+    torch.cuda.synchronize()
+    assert bps.value > 0
+    lib = L.lib()
+    outs = []
+    for rep in range(2):
+        out = torch.full((B, HW, C), float("nan"), device=cuda, dtype=torch.float16)
+        raw = torch.full((B, HW, C), float("nan"), device=cuda, dtype=torch.float16)
+        slot = torch.zeros(B * 64, device=cuda, dtype=torch.float64)
+        L.check(lib.s2i_groupnorm_forward_colstat(x.data_ptr(), C, B, HW, C, stat.data_ptr(), C, cap, bps.value, gamma.data_ptr(),
+                                                  beta.data_ptr(), eps, silu, out.data_ptr(), C, raw.data_ptr(), C, slot.data_ptr(),
+                                                  L.stream_ptr()))
+        torch.cuda.synchronize()
+        outs.append(out.clone())
+    xf = x.reshape(B, HW, C)
+    ref = _ref(xf.cpu(), gamma.cpu(), beta.cpu(), eps, silu)
+    assert rel(outs[0].cpu(), ref) < 1e-3
+    assert rel(raw.cpu().float(), xf.cpu()) < 1e-3
+    assert torch.equal(outs[0], outs[1])
+    # per-group mean / rstd in the slot (float2 per group): what the backward will read
+    xg = xf.double().reshape(B, HW, 32, C // 32)
+    mean = xg.mean(dim=(1, 3))
+    rstd = 1.0 / torch.sqrt(xg.var(dim=(1, 3), unbiased=False) + eps)
+    got = slot.view(torch.float32).reshape(B, 64, 2)[:, :32]
+    assert (got[..., 0].double() - mean).abs().max() < 1e-4 * (1 + mean.abs().max())
+    assert ((got[..., 1].double() - rstd) / rstd).abs().max() < 1e-4
